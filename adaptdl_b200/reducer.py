@@ -1,0 +1,259 @@
+"""Control-plane star reducer for small Python objects.
+
+Rank 0 hosts a server thread; every replica (rank 0 included) is a client
+over TCP. A collective is: every client sends one framed, pickled object
+tagged with a per-client sequence number (the *key*); once the server holds
+the objects of all replicas for a key it folds them in rank order with the
+reduce function that rank 0 registered for that key and sends the result
+back to everyone. Futures may be waited out of order.
+
+Capabilities match the reference's ``adaptdl/adaptdl/reducer.py:30-160``
+(allreduce / allreduce_async / broadcast, local mode with port 0, connect
+retries); the design differs: length-prefixed frames instead of streaming
+``pickle.load``, a selector-driven server that accepts contributions in any
+arrival order (so no reply-ordering trick is needed to dodge GIL deadlocks),
+an event instead of sleep-polling for local-mode port discovery, and a real
+``close``.
+
+All replicas must invoke collectives in the same order.
+"""
+
+import logging
+import pickle
+import selectors
+import socket
+import struct
+import threading
+import time
+
+LOG = logging.getLogger(__name__)
+
+_HDR = struct.Struct("!IQ")          # key (u32), payload length (u64)
+_HELLO = 0xFFFFFFFF                  # key of the rank-announcement frame
+
+
+def default_reduce_fn(a, b):
+    a += b
+    return a
+
+
+def _send_frame(sock, key, obj):
+    payload = pickle.dumps(obj, protocol=pickle.HIGHEST_PROTOCOL)
+    sock.sendall(_HDR.pack(key, len(payload)) + payload)
+
+
+def _recv_exact(sock, n):
+    buf = bytearray(n)
+    view = memoryview(buf)
+    got = 0
+    while got < n:
+        r = sock.recv_into(view[got:], n - got)
+        if r == 0:
+            raise ConnectionError("control-plane peer closed the connection")
+        got += r
+    return bytes(buf)
+
+
+def _recv_frame(sock):
+    key, length = _HDR.unpack(_recv_exact(sock, _HDR.size))
+    return key, pickle.loads(_recv_exact(sock, length))
+
+
+class Future(object):
+    """Handle to the result of an asynchronous all-reduce."""
+
+    _UNSET = object()
+
+    def __init__(self, reducer, key):
+        self._reducer = reducer
+        self._key = key
+        self._value = Future._UNSET
+
+    def result(self):
+        if self._value is Future._UNSET:
+            self._value = self._reducer._wait_for(self._key)
+        return self._value
+
+
+class _Server(threading.Thread):
+    """Rank-0 server: gathers one object per replica per key, reduces,
+    replies."""
+
+    def __init__(self, port, replicas, reduce_fns, reduce_fns_lock):
+        super().__init__(daemon=True, name="adaptdl-b200-reducer")
+        self._replicas = replicas
+        self._reduce_fns = reduce_fns
+        self._lock = reduce_fns_lock
+        self._listener = socket.socket(socket.AF_INET, socket.SOCK_STREAM)
+        self._listener.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
+        self._listener.bind(("0.0.0.0", port))
+        self._listener.listen(max(replicas, 8))
+        self.port = self._listener.getsockname()[1]
+        self._stop = threading.Event()
+        self.error = None
+
+    def stop(self):
+        self._stop.set()
+        try:
+            self._listener.close()
+        except OSError:
+            pass
+
+    def _accept_all(self):
+        clients = [None] * self._replicas
+        while any(c is None for c in clients):
+            conn, _ = self._listener.accept()
+            conn.setsockopt(socket.IPPROTO_TCP, socket.TCP_NODELAY, 1)
+            key, rank = _recv_frame(conn)
+            if key != _HELLO or not (0 <= rank < self._replicas) \
+                    or clients[rank] is not None:
+                conn.close()
+                raise RuntimeError("bad control-plane handshake")
+            clients[rank] = conn
+        return clients
+
+    def run(self):
+        try:
+            clients = self._accept_all()
+            sel = selectors.DefaultSelector()
+            for rank, conn in enumerate(clients):
+                sel.register(conn, selectors.EVENT_READ, rank)
+            pending = {}                         # key -> {rank: obj}
+            alive = self._replicas
+            while alive and not self._stop.is_set():
+                for skey, _ in sel.select(timeout=0.5):
+                    conn, rank = skey.fileobj, skey.data
+                    try:
+                        key, obj = _recv_frame(conn)
+                    except (ConnectionError, OSError):
+                        sel.unregister(conn)
+                        alive -= 1
+                        continue
+                    slot = pending.setdefault(key, {})
+                    slot[rank] = obj
+                    if len(slot) == self._replicas:
+                        del pending[key]
+                        self._finish(key, slot, clients)
+        except Exception as exc:  # noqa: BLE001 - surfaced to clients
+            if not self._stop.is_set():
+                self.error = exc
+                LOG.exception("control-plane reducer server failed")
+        finally:
+            try:
+                self._listener.close()
+            except OSError:
+                pass
+
+    def _finish(self, key, slot, clients):
+        with self._lock:
+            reduce_fn = self._reduce_fns.pop(key)
+        result = slot[0]
+        for rank in range(1, self._replicas):
+            result = reduce_fn(result, slot[rank])
+        payload = pickle.dumps(result, protocol=pickle.HIGHEST_PROTOCOL)
+        frame = _HDR.pack(key, len(payload)) + payload
+        # Rank 0 is answered last: it hosts this thread, and once it has its
+        # result it may run ahead and even exit; by then every other
+        # replica's reply is already in its socket buffer.
+        for conn in reversed(clients):
+            try:
+                conn.sendall(frame)
+            except OSError:
+                pass
+
+
+class Reducer(object):
+    """Asynchronous (all)reduce of Python objects over a TCP star.
+
+    Arguments:
+        rank, replicas: this replica's rank and the job size.
+        root_host, root_port: where rank 0 listens. ``root_port == 0`` is
+            *local mode*: rank 0 binds an ephemeral port (only meaningful
+            when every replica lives in this process or the port is
+            communicated out of band).
+    """
+
+    CONNECT_RETRIES = 25
+
+    def __init__(self, rank, replicas, root_host, root_port):
+        self._rank = rank
+        self._replicas = replicas
+        self._next_key = 0
+        self._results = {}
+        self._server = None
+        self._root_port = root_port
+        if rank == 0:
+            self._reduce_fns = {}
+            self._fn_lock = threading.Lock()
+            self._server = _Server(root_port, replicas, self._reduce_fns,
+                                   self._fn_lock)
+            self._root_port = self._server.port
+            self._server.start()
+            root_host = "127.0.0.1" if root_host in ("0.0.0.0", "") \
+                else root_host
+        elif root_host in ("0.0.0.0", ""):
+            root_host = "127.0.0.1"
+        self._sock = self._connect(root_host, self._root_port)
+        _send_frame(self._sock, _HELLO, rank)
+
+    @property
+    def root_port(self):
+        return self._root_port
+
+    def _connect(self, host, port):
+        delay = 0.05
+        last = None
+        for attempt in range(self.CONNECT_RETRIES + 1):
+            sock = socket.socket(socket.AF_INET, socket.SOCK_STREAM)
+            try:
+                if port == 0:
+                    raise ConnectionRefusedError("root port not known yet")
+                sock.connect((host, port))
+                sock.setsockopt(socket.IPPROTO_TCP, socket.TCP_NODELAY, 1)
+                return sock
+            except (ConnectionRefusedError, socket.gaierror, OSError) as e:
+                last = e
+                sock.close()
+                LOG.debug("rank %d: root %s:%s not ready (%s), retrying",
+                          self._rank, host, port, e)
+                time.sleep(delay)
+                delay = min(delay * 2, 5.0)
+        raise ConnectionError("rank {} could not reach the root reducer at "
+                              "{}:{}: {}".format(self._rank, host, port, last))
+
+    # -- collectives -------------------------------------------------------
+
+    def allreduce_async(self, obj, reduce_fn=default_reduce_fn):
+        key = self._next_key
+        self._next_key = (self._next_key + 1) % _HELLO
+        if self._rank == 0:
+            with self._fn_lock:
+                self._reduce_fns[key] = reduce_fn
+        _send_frame(self._sock, key, obj)
+        return Future(self, key)
+
+    def allreduce(self, obj, reduce_fn=default_reduce_fn):
+        return self.allreduce_async(obj, reduce_fn).result()
+
+    def broadcast(self, obj):
+        """Rank 0's value wins (all-reduce with the left projection)."""
+        return self.allreduce(obj, lambda x, y: x)
+
+    def _wait_for(self, key):
+        while key not in self._results:
+            try:
+                got_key, value = _recv_frame(self._sock)
+            except Exception as exc:
+                LOG.error("rank %d lost the control plane: %s",
+                          self._rank, exc)
+                raise
+            self._results[got_key] = value
+        return self._results.pop(key)
+
+    def close(self):
+        try:
+            self._sock.close()
+        except OSError:
+            pass
+        if self._server is not None:
+            self._server.stop()

@@ -1,0 +1,546 @@
+"""Elastic, adaptive-batch-size data loading.
+
+* :class:`ElasticSampler` -- partitions a dataset over replicas with a
+  deterministic per-(epoch, pass) shuffle and can resume at any global sample
+  index after a restart at a *different* replica count.
+* :class:`AdaptiveDataLoaderHelper` -- the per-iteration heartbeat shared by
+  all loaders: exit-flag consensus -> checkpoint -> ``exit(143)``, step
+  profiling, gradient-accumulation bookkeeping, goodput-driven choice of
+  ``(local_bsz, accumulation_steps)``, loop-position tracking for replay.
+* :class:`AdaptiveDataLoader` -- a ``torch.utils.data.DataLoader`` whose
+  ``batch_size`` is the *global* target batch size.
+
+Parity: reference ``adaptdl/adaptdl/torch/data.py:41-575`` (same public names,
+semantics and checkpoint format). B200 additions: :class:`DevicePrefetcher`
+(pinned-host -> HBM copies on a side stream, one batch ahead).
+"""
+
+import collections
+import functools
+import logging
+import math
+import pickle
+import random
+import sys
+from contextlib import contextmanager
+
+import numpy as np
+import torch
+from torch.utils.data import DataLoader, Sampler
+
+from adaptdl_b200 import checkpoint, collective, env
+from adaptdl_b200._signal import get_exit_flag
+from adaptdl_b200.torch import _metrics
+from adaptdl_b200.torch.epoch import current_epoch
+
+LOG = logging.getLogger(__name__)
+
+EXIT_CODE_PREEMPTED = 143     # the contract with the job controller
+
+
+def _shuffle_seed(epoch, pass_index):
+    # Explicit integer mix (the reference seeds with Python's hash() of a
+    # tuple, which is an implementation detail of CPython).
+    return (int(epoch) * 0x9E3779B1 + int(pass_index) * 0x85EBCA77
+            + 0x5BD1E995) & 0x7FFFFFFFFFFFFFFF
+
+
+class ElasticSampler(Sampler):
+    """Partition ``dataset`` across replicas; resumable at a global index.
+
+    ``index`` counts samples consumed by *all* replicas in the current loop,
+    so a checkpoint taken at N replicas resumes correctly at M replicas.
+
+    Arguments:
+        dataset: the dataset (only ``len()`` is used).
+        shuffle (bool): shuffle deterministically per (epoch, pass).
+    """
+
+    def __init__(self, dataset, shuffle=True):
+        self.dataset = dataset
+        self.shuffle = shuffle
+        self.num_replicas = env.num_replicas()
+        self.rank = env.replica_rank()
+        self.epoch = 0
+        self.index = 0
+
+    def _order(self):
+        n = len(self.dataset)
+        if not self.shuffle:
+            return list(range(n))
+        gen = torch.Generator()
+        gen.manual_seed(_shuffle_seed(self.epoch, self.index // n))
+        return torch.randperm(n, generator=gen).tolist()
+
+    def __iter__(self):
+        """Indices of this replica's samples, from the set index onward."""
+        order = self._order()
+        base = self.index % len(self.dataset)
+        mine = order[base + self.rank::self.num_replicas]
+        if len(mine) < len(self):       # pad so all replicas are equal
+            mine.append(order[self.rank])
+        assert len(mine) == len(self)
+        return iter(mine)
+
+    def __len__(self):
+        """Samples this replica still has to visit in the current pass."""
+        base = self.index % len(self.dataset)
+        return math.ceil((len(self.dataset) - base) / self.num_replicas)
+
+    def set_epoch(self, epoch, index=0):
+        """Select the epoch (shuffle order) and the global start index."""
+        self.epoch = epoch
+        self.index = index
+
+
+def current_dataloader():
+    """The :class:`AdaptiveDataLoaderHelper` currently being iterated."""
+    return AdaptiveDataLoaderHelper._current
+
+
+class _AdaptiveDataLoaderState(checkpoint.State):
+    # Loaders are created in the same order on every replica; the name is
+    # derived from (epoch at creation, creation ordinal within that epoch).
+    init_count = collections.Counter()
+
+    def __init__(self):
+        if current_dataloader() is not None:
+            raise RuntimeError("dataloader may not be initialized during "
+                               "dataloader iteration")
+        epoch = current_epoch()
+        ordinal = _AdaptiveDataLoaderState.init_count[epoch]
+        super().__init__("adaptdl-dataloader-epoch{}-{}".format(epoch,
+                                                                ordinal))
+        _AdaptiveDataLoaderState.init_count[epoch] += 1
+        self.current_index = 0    # samples consumed in the current loop
+        self.end_index = 0        # optional, for custom loaders
+        self.last_position = {}   # epoch -> position of last finished loop
+        self.current_local_bsz = 0
+        self.accumulation_steps = 0
+
+    def save(self, fileobj):
+        pickle.dump((self.current_index, self.end_index,
+                     self.last_position), fileobj)
+
+    def load(self, fileobj):
+        self.current_index, self.end_index, self.last_position = \
+            pickle.load(fileobj)
+
+
+class AdaptiveDataLoaderHelper(object):
+    """Fine-grained control over adaptive training loops; the building block
+    for custom loaders (see :class:`AdaptiveDataLoaderMixin`).
+
+    Arguments:
+        batch_size (int): target *global* batch size.
+    """
+
+    _position = collections.Counter()  # epoch -> loops finished (all loaders)
+    _training = None                   # the loader that feeds training
+    _current = None                    # the loader being iterated
+
+    SPEEDUP_THRESHOLD = 1.05
+
+    def __init__(self, batch_size=1):
+        self._max_batch_size = None
+        self._local_bsz_bounds = None
+        self._state = _AdaptiveDataLoaderState()
+        checkpoint.load_state(self._state)
+        self.batch_size = batch_size
+        self.future_exit = None
+        self._gradient_accumulation = False
+        self._speedup_threshold = self.SPEEDUP_THRESHOLD
+        self._accum_count = 0
+        self._step_time_source = None   # optional device-side step timer
+
+    # -- positions -----------------------------------------------------
+
+    @property
+    def current_index(self):
+        """Samples processed so far in the current loop by all replicas
+        (``None`` unless this loader is being iterated)."""
+        if AdaptiveDataLoaderHelper._current is not self:
+            return None
+        return self._state.current_index
+
+    @current_index.setter
+    def current_index(self, index):
+        if AdaptiveDataLoaderHelper._current is not self:
+            return
+        self._state.current_index = index
+
+    @property
+    def end_index(self):
+        return self._state.end_index
+
+    @end_index.setter
+    def end_index(self, index):
+        self._state.end_index = index
+
+    # -- batch size ----------------------------------------------------
+
+    @property
+    def max_batch_size(self):
+        """Upper bound of the adaptive global batch size (``None`` when
+        adaptive batch size is off)."""
+        return self._max_batch_size
+
+    @property
+    def local_bsz_bounds(self):
+        """``(min_local_bsz, max_local_bsz)`` per replica."""
+        return self._local_bsz_bounds
+
+    @property
+    def current_local_bsz(self):
+        """Per-replica micro-batch size currently in use."""
+        return self._state.current_local_bsz
+
+    @property
+    def accumulation_steps(self):
+        """Extra micro-batches accumulated before each optimizer step."""
+        return self._state.accumulation_steps
+
+    @property
+    def current_batch_size(self):
+        return (self.current_local_bsz * (self.accumulation_steps + 1)
+                * env.num_replicas())
+
+    def is_accum_step(self):
+        """This step's gradient is only accumulated (no sync, no update)."""
+        return self._accum_count < self._state.accumulation_steps
+
+    def is_optim_step(self):
+        """This step ends with a gradient sync and an optimizer update."""
+        return not self.is_accum_step()
+
+    def train(self):
+        """Mark this loader as the one feeding training (first wins)."""
+        if AdaptiveDataLoaderHelper._training is None:
+            AdaptiveDataLoaderHelper._training = self
+        _metrics.set_batch_size(self.batch_size, self.max_batch_size,
+                                self.local_bsz_bounds,
+                                self._gradient_accumulation)
+
+    @property
+    def training(self):
+        return self is AdaptiveDataLoaderHelper._training
+
+    def autoscale_batch_size(self, max_batch_size, local_bsz_bounds=None,
+                             gradient_accumulation=False):
+        """Enable adaptive batch size.
+
+        Arguments:
+            max_batch_size (int): largest global batch size allowed.
+            local_bsz_bounds (tuple): ``(min, max)`` per-replica batch size.
+            gradient_accumulation (bool): allow accumulation to go beyond
+                the per-replica maximum.
+
+        Raises:
+            ValueError: on inconsistent bounds.
+        """
+        if not isinstance(max_batch_size, int) \
+                or max_batch_size < self.batch_size:
+            raise ValueError("invalid max_batch_size")
+        if local_bsz_bounds is not None:
+            lo, hi = local_bsz_bounds
+            if (lo is not None and lo > self.batch_size) or \
+                    (hi is not None and hi < self.batch_size):
+                raise ValueError("invalid local_bsz_bounds")
+        self._max_batch_size = max_batch_size
+        self._local_bsz_bounds = local_bsz_bounds
+        self._gradient_accumulation = gradient_accumulation
+        self.train()
+
+    def _sync_local_bsz(self):
+        """Decide ``(local_bsz, accumulation_steps)`` for the next pass and
+        agree on rank 0's choice."""
+        goodput_fn = _metrics.get_goodput_fn()
+        state = self._state
+        if self.max_batch_size is None or goodput_fn is None:
+            state.current_local_bsz = math.ceil(
+                self.batch_size / env.num_replicas())
+            state.accumulation_steps = 0
+        else:
+            suggestion = goodput_fn.optimize(
+                env.num_nodes(), env.num_replicas(),
+                max_batch_size=self._max_batch_size,
+                atomic_bsz_range=self._local_bsz_bounds,
+                accumulation=self._gradient_accumulation)
+            best_goodput, atomic_bsz, accum_steps = suggestion
+            if not state.current_local_bsz:
+                switch = True          # first decision: take the suggestion
+            else:
+                current = goodput_fn(env.num_nodes(), env.num_replicas(),
+                                     self.current_local_bsz,
+                                     self.accumulation_steps)
+                switch = best_goodput / max(current, 1e-8) \
+                    > self._speedup_threshold
+            if switch:
+                state.current_local_bsz = atomic_bsz
+                state.accumulation_steps = accum_steps
+        state.current_local_bsz, state.accumulation_steps = \
+            collective.broadcast((state.current_local_bsz,
+                                  state.accumulation_steps))
+        return self.current_local_bsz
+
+    # -- per-iteration heartbeat -------------------------------------------
+
+    def set_step_time_source(self, fn):
+        """Install a callable returning the last step's duration in seconds
+        measured on the device (or ``None`` to fall back to wall-clock)."""
+        self._step_time_source = fn
+
+    @contextmanager
+    def profile(self, commit):
+        """Wrap every training iteration. Must be entered the same number
+        of times on every replica.
+
+        Resolves the exit-flag consensus launched one iteration earlier: if
+        any replica was signalled, *all* replicas checkpoint now and exit
+        with code 143.
+        """
+        if self.future_exit is not None and self.future_exit.result():
+            checkpoint.save_all_states()
+            sys.exit(EXIT_CODE_PREEMPTED)
+        self.future_exit = collective.allreduce_async(
+            get_exit_flag(), lambda a, b: a or b)
+        _metrics.profile_step_start(self.current_local_bsz)
+        yield
+        if commit:
+            step_time = None
+            if self._step_time_source is not None:
+                step_time = self._step_time_source()
+            _metrics.profile_step_commit(self.is_accum_step(),
+                                         step_time=step_time)
+        self._accum_count = (0 if self.is_optim_step()
+                             else self._accum_count + 1)
+
+    @contextmanager
+    def context(self):
+        """Wrap a whole loader iteration (one ``for batch in loader``)."""
+        epoch = current_epoch()
+        try:
+            if AdaptiveDataLoaderHelper._current is not None:
+                raise RuntimeError("overlapping dataloader iterations "
+                                   "detected")
+            AdaptiveDataLoaderHelper._current = self
+            yield
+        finally:
+            self._state.current_index = 0
+            self._state.end_index = 0
+            self._state.last_position[epoch] = self._position[epoch]
+            self._position[epoch] += 1
+            AdaptiveDataLoaderHelper._current = None
+
+    def skipdone(self):
+        """Call right after entering :meth:`context`: True if this loop had
+        already completed before the last restart (and must be skipped)."""
+        epoch = current_epoch()
+        position = self._position[epoch]
+        if position <= self._state.last_position.get(epoch, -1):
+            LOG.info("skipping %s loop at position %s in epoch %s",
+                     self.__class__.__name__, position, epoch)
+            self._position[epoch] += 1
+            return True
+        return False
+
+    def to_tensorboard(self, writer, global_step, tag_prefix=""):
+        """Write batch-size metrics to a TensorBoard ``SummaryWriter``."""
+        if tag_prefix and not tag_prefix.endswith("/"):
+            tag_prefix += "/"
+        writer.add_scalar(tag_prefix + "Total_Batch_Size",
+                          self.current_batch_size, global_step)
+        writer.add_scalar(tag_prefix + "Local_Batch_Size",
+                          self.current_local_bsz, global_step)
+        writer.add_scalar(tag_prefix + "Accumulation_Steps",
+                          self.accumulation_steps, global_step)
+
+
+class AdaptiveDataLoaderMixin(object):
+    """Give any custom loader elastic behaviour: it owns ``self._elastic``
+    (an :class:`AdaptiveDataLoaderHelper`) and re-exports the user-facing
+    knobs."""
+
+    def __init__(self, batch_size):
+        self._elastic = AdaptiveDataLoaderHelper(batch_size)
+
+    def autoscale_batch_size(self, max_batch_size, local_bsz_bounds=None,
+                             gradient_accumulation=False):
+        self._elastic.autoscale_batch_size(max_batch_size, local_bsz_bounds,
+                                           gradient_accumulation)
+    autoscale_batch_size.__doc__ = \
+        AdaptiveDataLoaderHelper.autoscale_batch_size.__doc__
+
+    def _iterating(self):
+        return AdaptiveDataLoaderHelper._current is self._elastic
+
+    @property
+    def current_local_bsz(self):
+        return self._elastic.current_local_bsz if self._iterating() else None
+
+    @property
+    def accumulation_steps(self):
+        return self._elastic.accumulation_steps
+
+    @property
+    def training(self):
+        return self._elastic.training
+
+    @property
+    def current_batch_size(self):
+        return self._elastic.current_batch_size if self._iterating() else None
+
+    def to_tensorboard(self, writer, global_step, tag_prefix=""):
+        self._elastic.to_tensorboard(writer, global_step, tag_prefix)
+    to_tensorboard.__doc__ = AdaptiveDataLoaderHelper.to_tensorboard.__doc__
+
+
+def _worker_init_wrapper(worker_init_fn, num_workers):
+    """Give every (replica, worker) pair distinct python/numpy/torch seeds."""
+    workers = num_workers or 1
+
+    @functools.wraps(worker_init_fn)
+    def wrapper(worker_id):
+        seed = torch.initial_seed() + env.replica_rank() * workers
+        torch.manual_seed(seed)
+        np.random.seed(seed % 2 ** 32)
+        random.seed(seed)
+        if worker_init_fn is not None:
+            return worker_init_fn(worker_id)
+    return wrapper
+
+
+class AdaptiveDataLoader(DataLoader, AdaptiveDataLoaderMixin):
+    """Drop-in ``DataLoader`` with adaptive batch size and elasticity.
+
+    Differences from ``torch.utils.data.DataLoader``:
+
+    1. ``batch_size`` is the target *global* batch size over all replicas.
+    2. Custom ``sampler`` / ``batch_sampler`` are not supported.
+    3. Iterate only inside an epoch loop
+       (:func:`adaptdl_b200.torch.remaining_epochs_until`); only one loader
+       may be iterated at a time.
+
+    Raises:
+        ValueError: if ``sampler`` or ``batch_sampler`` is given.
+    """
+
+    def __init__(self, dataset, batch_size=1, shuffle=False, **kwargs):
+        if kwargs.get("batch_sampler") is not None \
+                or kwargs.get("sampler") is not None:
+            raise ValueError("AdaptiveDataLoader does not support "
+                             "custom 'sampler' or 'batch_sampler'")
+        kwargs["sampler"] = ElasticSampler(dataset, shuffle=shuffle)
+        kwargs["worker_init_fn"] = _worker_init_wrapper(
+            kwargs.get("worker_init_fn"), kwargs.get("num_workers"))
+        super().__init__(dataset, batch_size, shuffle=False, **kwargs)
+        AdaptiveDataLoaderMixin.__init__(self, batch_size)
+
+    def _set_local_batch_size(self, local_bsz):
+        # DataLoader forbids re-assigning batch_sampler, but mutating the
+        # BatchSampler it built is allowed (and what the reference does).
+        self.batch_sampler.batch_size = local_bsz
+
+    def __iter__(self):
+        """Yield batches until one epoch's worth of *progress* is made.
+
+        Without adaptive batch size: one pass over this replica's 1/N share
+        of the dataset. With it: until the scale-invariant progress equals
+        one pass at the initial batch size, possibly more than one pass over
+        the data. A checkpoint-restart may happen between any two batches.
+        """
+        epoch = current_epoch()
+        num_replicas = env.num_replicas()
+        elastic = self._elastic
+        with elastic.context():
+            if elastic.skipdone():
+                return
+            done = False
+            while not done:
+                self.sampler.set_epoch(epoch, index=elastic.current_index)
+                self._set_local_batch_size(elastic._sync_local_bsz())
+                for idx, batch in enumerate(super().__iter__()):
+                    # the first batch of a pass is warm-up: never committed
+                    with elastic.profile(self.training and idx >= 1):
+                        yield batch
+                        elastic.current_index += \
+                            num_replicas * self.batch_sampler.batch_size
+                        if elastic.max_batch_size is not None and \
+                                _metrics.get_progress() >= \
+                                len(self.dataset) * (epoch + 1) \
+                                / self.batch_size:
+                            done = True
+                            break
+                if elastic.max_batch_size is None:
+                    done = True
+                # round up to the end of this pass over the dataset
+                elastic.current_index -= \
+                    elastic.current_index % -len(self.dataset)
+
+
+class DevicePrefetcher(object):
+    """Wrap a loader that yields (nested) CPU tensors: pin them, and copy the
+    *next* batch to ``device`` on a side stream while the current one is
+    being consumed (B200 addition; keeps the H2D copy off the step's critical
+    path).
+
+    The wrapped loader's elastic bookkeeping is untouched because this wraps
+    the iterator, not the loader class.
+    """
+
+    def __init__(self, loader, device):
+        self.loader = loader
+        self.device = torch.device(device)
+        self._stream = torch.cuda.Stream(self.device) \
+            if self.device.type == "cuda" else None
+
+    def __getattr__(self, name):
+        return getattr(self.loader, name)
+
+    def __len__(self):
+        return len(self.loader)
+
+    def _to_device(self, obj):
+        if torch.is_tensor(obj):
+            if self._stream is not None and not obj.is_pinned():
+                obj = obj.pin_memory()
+            return obj.to(self.device, non_blocking=True)
+        if isinstance(obj, (list, tuple)):
+            return type(obj)(self._to_device(o) for o in obj)
+        if isinstance(obj, dict):
+            return {k: self._to_device(v) for k, v in obj.items()}
+        return obj
+
+    def _record(self, obj, stream):
+        if torch.is_tensor(obj):
+            obj.record_stream(stream)
+        elif isinstance(obj, (list, tuple)):
+            for o in obj:
+                self._record(o, stream)
+        elif isinstance(obj, dict):
+            for o in obj.values():
+                self._record(o, stream)
+
+    def __iter__(self):
+        if self._stream is None:
+            for batch in self.loader:
+                yield self._to_device(batch)
+            return
+        it = iter(self.loader)
+        # NOTE: prefetching one batch ahead would advance the elastic loader's
+        # profile()/current_index one step early; so only the H2D copy is
+        # overlapped (issued on the side stream, waited by the consumer).
+        for batch in it:
+            with torch.cuda.stream(self._stream):
+                dev = self._to_device(batch)
+            cur = torch.cuda.current_stream(self.device)
+            cur.wait_stream(self._stream)
+            self._record(dev, cur)
+            yield dev
+
+
+def _reset_for_tests():
+    AdaptiveDataLoaderHelper._position = collections.Counter()
+    AdaptiveDataLoaderHelper._training = None
+    AdaptiveDataLoaderHelper._current = None
+    _AdaptiveDataLoaderState.init_count = collections.Counter()

@@ -1,0 +1,251 @@
+"""AdaptiveDataParallel: elastic data parallelism with adaptive batch size.
+
+Public behaviour follows the reference's
+``adaptdl/adaptdl/torch/parallel.py:39-239`` (constructor signature,
+``forward`` accumulation control, ``gain``, ``to_tensorboard``, checkpoint
+format) but the implementation is not a ``DistributedDataParallel`` subclass:
+gradients live in flat, NVLink-mapped arenas owned by a
+:class:`~adaptdl_b200.parallel.reducer_base.GradReducer`, and one fused
+sm_100a kernel per bucket performs the all-reduce, the ``1/(N*accum)``
+scaling and the gradient-noise-scale statistics while backward is still
+running. On CPU (gloo) the same control flow runs on stock torch ops.
+"""
+
+import contextlib
+import logging
+import warnings
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.distributed
+
+from adaptdl_b200 import checkpoint, env
+from adaptdl_b200.parallel import make_reducer
+from adaptdl_b200.torch import _metrics
+from adaptdl_b200.torch.data import current_dataloader
+from adaptdl_b200.torch.gradient_noise_scale import (
+    AdamGradientNoiseScale, GradientNoiseScale)
+from adaptdl_b200.torch.scaling_rules import (
+    AdaScale, AdamScale, ScalingRuleBase)
+
+LOG = logging.getLogger(__name__)
+
+_IGNORED_DDP_KWARGS = (
+    "device_ids", "output_device", "dim", "find_unused_parameters",
+    "check_reduction", "gradient_as_bucket_view", "static_graph",
+    "delay_all_reduce_named_params", "param_to_hook_all_reduce",
+    "mixed_precision", "device_mesh", "init_sync", "skip_all_reduce_unused_params")
+
+
+class AdaptiveDataParallel(torch.nn.Module):
+    """Wrap ``model`` for elastic, adaptive-batch-size data parallelism.
+
+    Saves/restores the model, optimizer, LR scheduler and AMP scaler as part
+    of every checkpoint, patches ``optimizer.step`` / ``zero_grad`` with the
+    chosen LR scaling rule, and keeps replicas' gradients averaged.
+
+    Arguments:
+        model (torch.nn.Module): model to distribute (already on its device).
+        optimizer (torch.optim.Optimizer): updates ``model``'s parameters.
+        lr_scheduler: optional LR scheduler to checkpoint.
+        mp_scaler: optional ``torch.amp.GradScaler`` (AMP loss scaling).
+        scaling_rule (ScalingRuleBase): defaults to ``AdamScale`` for
+            Adam/AdamW, else ``AdaScale``.
+        name (str): unique name, needed only with several instances.
+        **kwargs: ``DistributedDataParallel`` keyword arguments are accepted
+            for compatibility: ``broadcast_buffers``, ``bucket_cap_mb`` and
+            ``process_group`` are honoured, the rest ignored.
+            ``reducer`` = ``"auto" | "cuda" | "torch"`` picks the gradient
+            reducer.
+    """
+
+    def __init__(self, model, optimizer, lr_scheduler=None, mp_scaler=None,
+                 scaling_rule: Optional[ScalingRuleBase] = None,
+                 name="adaptdl-dataparallel", **kwargs):
+        super().__init__()
+        self.module = model
+        self._key = id(self)
+        self.require_backward_grad_sync = True
+        self.broadcast_buffers = kwargs.pop("broadcast_buffers", True)
+        bucket_cap_mb = kwargs.pop("bucket_cap_mb", None) or 25
+        process_group = kwargs.pop("process_group", None)
+        backend = kwargs.pop("reducer", "auto")
+        for key in list(kwargs):
+            if key in _IGNORED_DDP_KWARGS:
+                kwargs.pop(key)
+        if kwargs:
+            raise TypeError("unexpected arguments: {}".format(sorted(kwargs)))
+
+        if torch.distributed.is_available() and \
+                torch.distributed.is_initialized():
+            self._world_size = torch.distributed.get_world_size(process_group)
+            self._rank = torch.distributed.get_rank(process_group)
+        else:
+            self._world_size, self._rank = 1, 0
+
+        if not scaling_rule and isinstance(
+                optimizer, (torch.optim.Adam, torch.optim.AdamW)):
+            self.scaling_rule = AdamScale()
+        else:
+            self.scaling_rule = scaling_rule or AdaScale()
+
+        self._reducer = make_reducer(
+            optimizer.param_groups, self._world_size, self._rank,
+            lambda: self.require_backward_grad_sync,
+            bucket_cap_mb=bucket_cap_mb, process_group=process_group,
+            backend=backend, name=name)
+        # Reference quirk kept (App. D1): preconditioned statistics only
+        # when an AdamScale instance was passed explicitly.
+        gns_cls = AdamGradientNoiseScale if isinstance(scaling_rule, AdamScale) \
+            else GradientNoiseScale
+        self.gns = gns_cls(self, optimizer, mp_scaler=mp_scaler,
+                           num_replicas=self._world_size,
+                           reducer=self._reducer)
+        self.gns.add_listener(self._on_stats)
+        self.gns.add_backward_listener(self._on_backward_end)
+        self.scaling_rule.initialize(self, optimizer, patch_optimizer=True)
+
+        self._state = _AdaptiveDataParallelState(
+            model, optimizer, lr_scheduler, mp_scaler, name)
+        checkpoint.load_state(self._state)
+        self._sync_module_states()
+
+    # ------------------------------------------------------------------
+
+    @property
+    def reducer(self):
+        return self._reducer
+
+    def _module_tensors(self, buffers_only=False):
+        tensors = [] if buffers_only else \
+            [p.data for p in self.module.parameters()]
+        tensors += [b for b in self.module.buffers()
+                    if torch.is_tensor(b) and b.numel() > 0]
+        return tensors
+
+    def _sync_module_states(self):
+        """Rank 0's parameters and buffers win (construction and after every
+        elastic restart)."""
+        if self._world_size > 1:
+            self._reducer.broadcast_parameters(self._module_tensors())
+
+    def forward(self, *args, **kwargs):
+        dataloader = current_dataloader()
+        if dataloader is not None and dataloader.training:
+            # no gradient synchronisation on accumulation micro-steps
+            self.require_backward_grad_sync = dataloader.is_optim_step()
+            accum_scale = (dataloader.current_local_bsz
+                           * env.num_replicas() / dataloader.batch_size)
+            self.gns.set_accum_scale(accum_scale)
+        if self.broadcast_buffers and self._world_size > 1 \
+                and self.require_backward_grad_sync \
+                and torch.is_grad_enabled():
+            buffers = self._module_tensors(buffers_only=True)
+            if buffers:
+                self._reducer.broadcast_parameters(buffers)
+        return self.module(*args, **kwargs)
+
+    @contextlib.contextmanager
+    def no_sync(self):
+        """DDP-compatible context: backward passes inside only accumulate."""
+        old = self.require_backward_grad_sync
+        self.require_backward_grad_sync = False
+        try:
+            yield
+        finally:
+            self.require_backward_grad_sync = old
+
+    def _on_backward_end(self, sync):
+        dataloader = current_dataloader()
+        if dataloader is None:
+            raise RuntimeError("backpropagation outside AdaptiveDataLoader")
+        dataloader.train()
+
+    def _on_stats(self, stats):
+        # invoked when the statistics of a synchronised backward have been
+        # folded into the running averages
+        if stats.sync_time is not None:
+            try:
+                _metrics.profile_sync_time(stats.sync_time)
+            except AttributeError:
+                pass       # not inside a profiled step
+        dataloader = current_dataloader()
+        if dataloader is None:
+            return
+        scale = dataloader.current_batch_size / dataloader.batch_size
+        self._state.gain = self.gns.gain(scale)
+        self._state.lr_factor = float(
+            np.average(self.scaling_rule.scale_lr(scale)))
+        _metrics.update_progress(self.gns.get_progress())
+        if dataloader.max_batch_size and \
+                dataloader.max_batch_size > dataloader.batch_size:
+            _metrics.update_grad_params(self._key, self.gns.sqr_avg(),
+                                        self.gns.var_avg())
+
+    def zero_grad(self, *args, **kwargs):
+        warnings.warn("zero_grad has no effect with AdaptiveDataParallel")
+
+    @property
+    def gain(self):
+        """Current estimate of the AdaScale gain (r_t)."""
+        self.gns._flush()
+        return self._state.gain
+
+    def to_tensorboard(self, writer, global_step, tag_prefix=""):
+        """Write gradient statistics to a TensorBoard ``SummaryWriter``."""
+        if tag_prefix and not tag_prefix.endswith("/"):
+            tag_prefix += "/"
+        gns = self.gns
+        writer.add_scalar(tag_prefix + "Gradient_Norm_Sqr", gns.sqr_avg(),
+                          global_step)
+        writer.add_scalar(tag_prefix + "Gradient_Variance", gns.var_avg(),
+                          global_step)
+        writer.add_scalar(tag_prefix + "Gain", self._state.gain, global_step)
+        writer.add_scalar(tag_prefix + "Learning_Rate_Factor",
+                          self._state.lr_factor, global_step)
+        writer.add_scalar(tag_prefix + "Accum_Scale", gns.accum_scale,
+                          global_step)
+        if gns.accum_count > 0:
+            writer.add_scalar(tag_prefix + "Accum_Count", gns.accum_count,
+                              global_step)
+        writer.add_scalar(tag_prefix + "Progress", gns.get_progress(),
+                          global_step)
+
+
+class _AdaptiveDataParallelState(checkpoint.State):
+    """``torch.save(([model_sd, optim_sd, sched_sd|None, scaler_sd|None],
+    gain, lr_factor))`` -- the reference's layout (App. B); the GNS running
+    averages ride inside ``optim_sd["state"]["gns"]``."""
+
+    def __init__(self, model, optimizer, lr_scheduler, mp_scaler,
+                 name="adaptdl-dataparallel"):
+        super().__init__(name)
+        self.model = model
+        self.optimizer = optimizer
+        self.lr_scheduler = lr_scheduler
+        self.mp_scaler = mp_scaler
+        self.gain = 1.0
+        self.lr_factor = 1.0
+
+    def save(self, fileobj):
+        state_dicts = [
+            self.model.state_dict(),
+            self.optimizer.state_dict(),
+            self.lr_scheduler.state_dict()
+            if self.lr_scheduler is not None else None,
+            self.mp_scaler.state_dict()
+            if self.mp_scaler is not None else None,
+        ]
+        torch.save((state_dicts, self.gain, self.lr_factor), fileobj)
+
+    def load(self, fileobj):
+        # numpy arrays inside optimizer.state["gns"] need full unpickling
+        state_dicts, self.gain, self.lr_factor = torch.load(
+            fileobj, map_location="cpu", weights_only=False)
+        self.model.load_state_dict(state_dicts[0])
+        self.optimizer.load_state_dict(state_dicts[1])
+        if state_dicts[2] is not None and self.lr_scheduler is not None:
+            self.lr_scheduler.load_state_dict(state_dicts[2])
+        if state_dicts[3] is not None and self.mp_scaler is not None:
+            self.mp_scaler.load_state_dict(state_dicts[3])

@@ -1,0 +1,359 @@
+"""Gradient noise scale estimator, LR scaling rules (exact factors and
+convergence), and the flat gradient reducer on CPU."""
+import math
+import random
+from unittest.mock import Mock
+
+import numpy as np
+import pytest
+import torch
+
+from adaptdl_b200.torch.gradient_noise_scale import (
+    GradientNoiseScale, AdamGradientNoiseScale, estimate)
+from adaptdl_b200.torch.scaling_rules import (
+    AdaScale, AdamScale, LinearScale, SqrtScale, LEGWScale)
+
+
+def _mk(params=None, lr=0.1, **kw):
+    params = params or [torch.nn.Parameter(torch.tensor([1.0, 2.0]))]
+    sgd = torch.optim.SGD(params, lr=lr)
+    adp = Mock(require_backward_grad_sync=True)
+    gns = GradientNoiseScale(adp, sgd, **kw)
+    adp.gns = gns
+    return params, sgd, adp, gns
+
+
+def test_object():
+    params = [{"params": [torch.nn.Parameter(torch.rand(2))]},
+              {"params": [torch.nn.Parameter(torch.rand(3))]}]
+    _, sgd, adp, obj = _mk(params, accum_scale=1.0, num_replicas=1)
+    assert obj.accum_scale == 1.0
+    obj.set_accum_scale(3.0)
+    assert obj.accum_scale == 3.0
+    assert np.isclose(obj.gain(2.0), 1.0)       # var=0 (clipped 1e-6), sqr=2
+    obj._state["var_avg"] = np.array([1.5, 1.5])
+    obj._state["sqr_avg"] = np.array([0.5, 0.5])
+    assert np.isclose(obj.gain(3.0), 2.0)
+    assert obj.raw_var_avg.flags.writeable is False
+    assert sgd.state["gns"] is obj._state
+
+
+def test_estimator_is_unbiased():
+    """Replica estimator: E[grad_sqr] = |mu|^2, E[grad_var] = scale * tr(S)
+    where S is the covariance of ONE sample gradient at scale 1."""
+    rng = np.random.RandomState(0)
+    mu = np.array([1.0, -2.0, 0.5])
+    sigma = 0.7
+    count, trials = 4, 20000
+    sqr, var = [], []
+    for _ in range(trials):
+        g = mu + sigma * rng.randn(count, 3)
+        local = np.mean(np.sum(g * g, axis=1))
+        total = np.sum(np.mean(g, axis=0) ** 2)
+        s, v = estimate(local, total, count, scale=count)
+        sqr.append(s)
+        var.append(v)
+    assert np.mean(sqr) == pytest.approx(np.sum(mu ** 2), rel=0.02)
+    # each sample is one "scale-1" gradient with covariance sigma^2 I
+    assert np.mean(var) == pytest.approx(3 * sigma ** 2 * count / count
+                                         * 1.0 * count / count, rel=0.05) \
+        or True
+    assert np.mean(var) == pytest.approx(3 * sigma ** 2, rel=0.05)
+
+
+def test_differenced_estimator_single_replica():
+    """N=1, no accumulation: statistics come from consecutive gradients."""
+    p = torch.nn.Parameter(torch.zeros(4))
+    _, sgd, adp, gns = _mk([p], accum_scale=1.0, num_replicas=1)
+    grads = [torch.tensor([1., 0, 0, 0]), torch.tensor([0., 1, 0, 0]),
+             torch.tensor([0., 0, 2, 0])]
+    for g in grads:
+        gns.reset_accumulation()
+        (p * g).sum().backward()
+        gns._flush()
+    # after step 2: local=(1+1)/2=1, total=|(g0+g1)/2|^2=0.5; count=2,
+    # scale=2 -> sqr=(2*.5-1)/1=0, var=(1-.5)*2=1
+    # after step 3: local=(1+4)/2=2.5, total=|(g1+g2)/2|^2=1.25 ->
+    #   sqr=0, var=2.5
+    theta = 0.999 ** 2
+    b_var = (1 - theta) * 1.0
+    u = 1 - theta
+    b_var = theta * b_var + (1 - theta) * 2.5
+    u = theta * u + (1 - theta)
+    assert gns._state["biased"] is True
+    assert gns.raw_var_avg[0] == pytest.approx(b_var / u)
+    assert gns.raw_sqr_avg[0] == pytest.approx(0.0, abs=1e-12)
+    assert torch.equal(p.grad, grads[-1])
+
+
+def test_accumulation_statistics_match_manual():
+    """N=1 with 3 micro-steps: count=3 replica-style estimator, grads are
+    averaged over micro-steps in place."""
+    p = torch.nn.Parameter(torch.zeros(3))
+    _, sgd, adp, gns = _mk([p], accum_scale=1.0, num_replicas=1)
+    micro = [torch.tensor([1., 2, 3]), torch.tensor([3., 2, 1]),
+             torch.tensor([0., 0, 6])]
+    gns.reset_accumulation()
+    for i, g in enumerate(micro):
+        adp.require_backward_grad_sync = i == len(micro) - 1
+        (p * g).sum().backward()
+        assert gns.should_zero_grad == adp.require_backward_grad_sync
+    assert gns.accum_count == 3
+    mean = sum(micro) / 3
+    assert torch.allclose(p.grad, mean)
+    local = np.mean([float((g * g).sum()) for g in micro])
+    total = float((mean * mean).sum())
+    s, v = estimate(local, total, 3, 3.0)
+    assert gns.raw_sqr_avg[0] == pytest.approx(s)
+    assert gns.raw_var_avg[0] == pytest.approx(v)
+    assert gns._state["biased"] is False
+    # zero_grad semantics: a fresh cycle starts from zero
+    gns.reset_accumulation()
+    assert gns.accum_count == 0 and float(p.grad.abs().sum()) == 0.0
+
+
+def test_param_groups_are_separate_statistics():
+    a = torch.nn.Parameter(torch.zeros(5))
+    b = torch.nn.Parameter(torch.zeros(2, 3))
+    groups = [{"params": [a]}, {"params": [b]}]
+    _, sgd, adp, gns = _mk(groups, accum_scale=1.0, num_replicas=1)
+    for step in range(2):
+        gns.reset_accumulation()
+        adp.require_backward_grad_sync = False
+        ((a * (step + 1)).sum() + (b * 2).sum()).backward()
+        adp.require_backward_grad_sync = True
+        ((a * 3).sum() + (b * (step + 4)).sum()).backward()
+        gns._flush()
+    assert gns.raw_sqr_avg.shape == (2,)
+    # last step, group 0: micro grads 2*ones(5), 3*ones(5)
+    l0, t0 = (4 * 5 + 9 * 5) / 2, 2.5 ** 2 * 5
+    l1, t1 = (4 * 6 + 25 * 6) / 2, 3.5 ** 2 * 6
+    s0, v0 = estimate(l0, t0, 2, 2.0)
+    s1, v1 = estimate(l1, t1, 2, 2.0)
+    # two equally-weighted-ish EMA samples; just check ordering/positivity
+    assert gns.raw_var_avg[0] > 0 and gns.raw_var_avg[1] > 0
+    assert gns.raw_sqr_avg[0] < gns.raw_sqr_avg[1]
+    assert v1 > v0 and s1 > s0
+
+
+def test_nan_gradients_do_not_poison_statistics():
+    random.seed(0)
+
+    def nan_objective(tensor):
+        target = float("nan") if random.random() > 0.5 else 4.0
+        return (tensor - target) ** 2
+
+    p = torch.nn.Parameter(torch.tensor([1.0]))
+    _, sgd, adp, gns = _mk([p], lr=0.1, accum_scale=1.0, num_replicas=1)
+    for _ in range(200):
+        gns.reset_accumulation()
+        loss = nan_objective(p)
+        loss.backward()
+        if np.all(np.isfinite(loss.detach().numpy())):
+            sgd.step()
+        if p.allclose(torch.tensor([4.0]), atol=0.01):
+            break
+    else:
+        pytest.fail("did not converge: {}".format(p))
+    assert np.isfinite(gns.sqr_avg()) and np.isfinite(gns.var_avg())
+
+
+def test_adam_preconditioned_statistics():
+    p = torch.nn.Parameter(torch.tensor([1.0, -1.0, 2.0]))
+    adam = torch.optim.Adam([p], lr=0.01)
+    adp = Mock(require_backward_grad_sync=True)
+    gns = AdamGradientNoiseScale(adp, adam, accum_scale=1.0, num_replicas=1)
+    adp.gns = gns
+    rule = AdamScale()
+    rule.initialize(adp, adam, patch_optimizer=True)
+    torch.manual_seed(0)
+    for i in range(12):
+        adam.zero_grad()
+        ((p - torch.randn(3)) ** 2).sum().backward()
+        adam.step()
+    state = adam.state[p]
+    assert float(state["step"]) == 12
+    pinv = gns._calculate_preconditioner(p)
+    expect = (state["exp_avg_sq"].sqrt()
+              / math.sqrt(1 - 0.999 ** 12)) + 1e-8
+    assert torch.allclose(pinv, expect)
+    assert np.isfinite(gns.sqr_avg()) and gns.var_avg() > 0
+    assert gns.get_progress() > 0
+
+
+# ---------------------------------------------------------------- rules
+
+def _rule_fixture(rule, var, sqr, accum_scale=1.0):
+    adp = Mock(require_backward_grad_sync=True)
+    adp.gns.raw_var_avg = np.asarray(var, dtype=float)
+    adp.gns.raw_sqr_avg = np.asarray(sqr, dtype=float)
+    adp.gns.accum_scale = accum_scale
+    adp.gns.accum_count = 1
+    adp.gns.get_progress.return_value = 0.0
+    adp.gns.gain.return_value = 1.5
+    optim = Mock()
+    optim.param_groups = [{"lr": 0.1}, {"lr": 0.2}]
+    optim.step = Mock()
+    rule.initialize(adp, optim)
+    return adp, optim
+
+
+def test_scaling_rule_factors():
+    rule = AdaScale()
+    _rule_fixture(rule, [1.0, 2.0], [1.0, 0.0])
+    out = rule.scale_lr(4.0)
+    assert np.allclose(out, [(1 + 1) / (0.25 + 1), (2 + 0) / (0.5 + 0)])
+    rule = AdamScale()
+    _rule_fixture(rule, [1.0, 2.0], [1.0, 0.0])
+    assert np.allclose(rule.scale_lr(4.0), np.sqrt([1.6, 4.0]))
+    assert LinearScale().scale_lr(3.0) == 3.0
+    assert SqrtScale().scale_lr(9.0) == 3.0
+    # clamps: var >= 1e-6, sqr >= 0
+    rule = AdaScale()
+    _rule_fixture(rule, [-1.0], [-1.0])
+    assert np.allclose(rule.scale_lr(2.0), [2.0])
+
+
+def test_scaling_rule_step_applies_and_restores_lr():
+    rule = AdaScale()
+    adp, optim = _rule_fixture(rule, [1.0, 2.0], [1.0, 0.0], accum_scale=4.0)
+    seen = []
+    optim.step.side_effect = lambda: seen.append(
+        [pg["lr"] for pg in optim.param_groups])
+    rule.step()
+    assert np.allclose(seen[0], [0.1 * 1.6, 0.2 * 4.0])
+    assert [pg["lr"] for pg in optim.param_groups] == [0.1, 0.2]
+    adp.gns.set_progress.assert_called_once_with(1.5)
+    adp.require_backward_grad_sync = False     # accumulation: no-op
+    rule.step()
+    assert len(seen) == 1
+
+
+def test_legw(monkeypatch):
+    import adaptdl_b200.torch.scaling_rules as sr
+    rule = LEGWScale(base_warmup_epochs=2, data_size=1000)
+    adp, _ = _rule_fixture(rule, [1.0], [1.0])
+    monkeypatch.setattr(sr, "current_dataloader",
+                        lambda: Mock(batch_size=100))
+    # total warm-up steps = 2 * 4 * 1000/100 = 80
+    adp.gns.get_progress.return_value = 20.0
+    assert rule.scale_lr(4.0) == pytest.approx(2.0 * 20 / 80)
+    adp.gns.get_progress.return_value = 200.0
+    assert rule.scale_lr(4.0) == pytest.approx(2.0)
+
+
+LR = 0.001
+ATOL = 0.01
+
+
+def _rosenbrock(x, y):
+    return (1 - x) ** 2 + 100 * (y - x ** 2) ** 2
+
+
+def _run(params, loss_fn, accum_scale=1.0, accumulate=False, atol=ATOL,
+         steps=100000):
+    flat = [q for g in params for q in
+            (g["params"] if isinstance(g, dict) else [g])]
+    sgd = torch.optim.SGD(params, lr=LR)
+    schedule = torch.optim.lr_scheduler.MultiStepLR(sgd, [1000])
+    adp = Mock(require_backward_grad_sync=not accumulate)
+    gns = GradientNoiseScale(adp, sgd, accum_scale=accum_scale,
+                             num_replicas=1)
+    adp.gns = gns
+    rule = AdaScale()
+    rule.initialize(adp, sgd, patch_optimizer=True)
+    for i in range(steps):
+        if accumulate:
+            adp.require_backward_grad_sync = i % 2 == 1
+        sgd.zero_grad()
+        loss_fn().backward()
+        sgd.step()
+        if adp.require_backward_grad_sync:
+            schedule.step()
+        if all(q.allclose(torch.ones_like(q), atol=atol) for q in flat):
+            return
+    pytest.fail("did not converge: {}".format(flat))
+
+
+def test_optimization_rosenbrock():
+    p = torch.nn.Parameter(torch.tensor([1.0, 1.5]))
+    _run([p], lambda: _rosenbrock(p[0], p[1]))
+
+
+def test_optimization_noisy():
+    np.random.seed(0)
+    p = torch.nn.Parameter(torch.tensor([1.0, 1.5]))
+
+    def noisy():
+        return (np.random.normal(1.0, 0.2) * (1 - p[0]) ** 2 +
+                np.random.normal(1.0, 0.2) * 100 * (p[1] - p[0] ** 2) ** 2)
+    _run([p], lambda: (noisy() + noisy()) / 2.0, accum_scale=2.0,
+         atol=5 * ATOL)
+
+
+def test_optimization_param_groups():
+    x = torch.nn.Parameter(torch.tensor([1.0]))
+    y = torch.nn.Parameter(torch.tensor([1.5]))
+    _run([{"params": [x]}, {"params": [y]}],
+         lambda: _rosenbrock(x, y).sum(), atol=5 * ATOL)
+
+
+def test_optimization_gradient_accumulation():
+    p = torch.nn.Parameter(torch.tensor([1.0, 1.5]))
+    _run([p], lambda: _rosenbrock(p[0], p[1]), accumulate=True,
+         atol=10 * ATOL)
+
+
+# ------------------------------------------------------------- reducer
+
+def test_flat_layout_and_views():
+    from adaptdl_b200.parallel.reducer_torch import TorchGradReducer
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.ReLU(),
+                                torch.nn.Linear(5, 3))
+    groups = [{"params": list(model[0].parameters())},
+              {"params": list(model[2].parameters())}]
+    red = TorchGradReducer(groups, 1, 0, lambda: True, bucket_cap_mb=1e-4)
+    arena = red.arenas[0]
+    assert len(arena.buckets) >= 2
+    for p, view in zip(arena.params, arena.views):
+        assert p.grad.data_ptr() == view.data_ptr()
+        assert view.data_ptr() % 16 == 0
+    x = torch.randn(4, 7)
+    model(x).sum().backward()
+    ref = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.ReLU(),
+                              torch.nn.Linear(5, 3))
+    ref.load_state_dict(model.state_dict())
+    ref(x).sum().backward()
+    for p, q in zip(model.parameters(), ref.parameters()):
+        assert torch.allclose(p.grad, q.grad)
+    stats = red.pop_stats()
+    want0 = sum(float((q.grad.double() ** 2).sum())
+                for q in ref[0].parameters())
+    want1 = sum(float((q.grad.double() ** 2).sum())
+                for q in ref[2].parameters())
+    assert stats.total_sqr == pytest.approx([want0, want1])
+    assert stats.count == 1 and stats.pair is None
+    # .grad replaced behind our back is folded back into the arena
+    red.zero()
+    for p in model.parameters():
+        p.grad = None
+    model(x).sum().backward()
+    for p, q, view in zip(model.parameters(), ref.parameters(),
+                          arena.views):
+        assert torch.allclose(p.grad, q.grad)
+    for p, view in zip(arena.params, arena.views):
+        assert p.grad.data_ptr() == view.data_ptr()
+
+
+def test_unused_parameters_do_not_stall():
+    from adaptdl_b200.parallel.reducer_torch import TorchGradReducer
+    used = torch.nn.Parameter(torch.ones(3))
+    unused = torch.nn.Parameter(torch.ones(2))
+    red = TorchGradReducer([{"params": [used, unused]}], 1, 0, lambda: True)
+    for _ in range(2):
+        red.zero()
+        (used * 2).sum().backward()
+        stats = red.pop_stats()
+        assert stats.total_sqr == pytest.approx([12.0])
+        assert float(unused.grad.abs().sum()) == 0.0

@@ -1,0 +1,176 @@
+"""L2 runtime: env, checkpoint registry, control-plane collectives."""
+import os
+import pickle
+
+import pytest
+
+from adaptdl_b200.utils.testing import elastic_multiprocessing
+
+
+def test_env_defaults(monkeypatch):
+    from adaptdl_b200 import env
+    for key in list(os.environ):
+        if key.startswith("ADAPTDL_"):
+            monkeypatch.delenv(key)
+    assert env.checkpoint_path() is None
+    assert env.share_path() is None
+    assert env.job_id() is None
+    assert env.master_addr() == "0.0.0.0"
+    assert env.master_port() == 0
+    assert env.replica_rank() == 0
+    assert env.num_replicas() == 1
+    assert env.num_nodes() == 1
+    assert env.num_restarts() == 0
+    assert env.supervisor_url() is None
+    assert env.from_ray() is False
+    monkeypatch.setenv("ADAPTDL_NUM_REPLICAS", "4")
+    assert env.num_nodes() == 4          # defaults to one node per replica
+    monkeypatch.setenv("ADAPTDL_NUM_NODES", "2")
+    monkeypatch.setenv("ADAPTDL_REPLICA_RANK", "3")
+    assert env.num_nodes() == 2 and env.replica_rank() == 3
+    assert env.local_rank() == 1
+
+
+@elastic_multiprocessing
+def test_duplicate_state():
+    from adaptdl_b200.env import num_restarts
+    from adaptdl_b200.checkpoint import State
+    State("state_1")
+    State("state_2")
+    with pytest.raises(ValueError):
+        State("state_1")
+    return [2, 0][num_restarts()]
+
+
+@elastic_multiprocessing
+def test_save_load():
+    from adaptdl_b200.checkpoint import State, save_all_states, load_state
+    from adaptdl_b200.env import replica_rank, num_restarts, checkpoint_path
+
+    class TestState(State):
+        def __init__(self, name):
+            super().__init__(name)
+            self.synced = False
+
+        def sync(self):
+            self.synced = True
+
+        def save(self, fileobj):
+            assert replica_rank() == 0
+            pickle.dump(self.value, fileobj)
+
+        def load(self, fileobj):
+            self.value = pickle.load(fileobj)
+
+    state_1 = TestState("state_1")
+    state_2 = TestState("state_2")
+    if num_restarts() == 0:
+        assert not load_state(state_1)
+        state_1.value, state_2.value = 10, 20
+        save_all_states()
+        assert state_1.synced and state_2.synced
+        assert sorted(os.listdir(checkpoint_path())) == ["checkpoint-0"]
+        assert sorted(os.listdir(os.path.join(
+            checkpoint_path(), "checkpoint-0"))) == ["state_1", "state_2"]
+        return 2
+    assert load_state(state_1) and load_state(state_2)
+    if num_restarts() == 1:
+        assert (state_1.value, state_2.value) == (10, 20)
+        # a newer generation replaces the older one atomically
+        from adaptdl_b200 import collective
+        collective.initialize()
+        state_1.value = 11
+        save_all_states()
+        collective.allreduce(0)   # barrier: rank 0 finished publishing
+        assert sorted(d for d in os.listdir(checkpoint_path())
+                      if d.startswith("checkpoint-")) == ["checkpoint-1"]
+        return 1
+    assert state_1.value == 11
+    return 0
+
+
+@elastic_multiprocessing
+def test_allreduce():
+    from adaptdl_b200 import collective, env
+    collective.initialize()
+    assert collective.allreduce(1) == env.num_replicas()
+    result = collective.allreduce({env.replica_rank()},
+                                  reduce_fn=lambda a, b: a | b)
+    assert result == set(range(env.num_replicas()))
+    return [5, 0][env.num_restarts()]
+
+
+@elastic_multiprocessing
+def test_allreduce_async_out_of_order():
+    from adaptdl_b200 import collective, env
+    collective.initialize()
+    f1 = collective.allreduce_async(1)
+    f2 = collective.allreduce_async(2)
+    f3 = collective.allreduce_async(3)
+    n = env.num_replicas()
+    assert f2.result() == 2 * n
+    assert f1.result() == 1 * n
+    assert f3.result() == 3 * n
+    assert f2.result() == 2 * n        # idempotent
+    return [5, 0][env.num_restarts()]
+
+
+@elastic_multiprocessing
+def test_broadcast_and_teardown():
+    from adaptdl_b200 import collective, env
+    with pytest.raises(RuntimeError):
+        collective.broadcast(1)
+    collective.initialize()
+    with pytest.raises(RuntimeError):
+        collective.initialize()
+    assert collective.broadcast(env.replica_rank()) == 0
+    big = collective.broadcast(list(range(200000)))
+    assert len(big) == 200000
+    collective.allreduce(0)
+    collective.teardown()
+    assert not collective.is_initialized()
+    return [3, 0][env.num_restarts()]
+
+
+def test_reducer_many_steps():
+    """3 raw processes, Counter reduce, async loop (reference
+    reducer_test)."""
+    import collections
+    import multiprocessing as mp
+    from adaptdl_b200.utils import pick_unused_port
+    port = pick_unused_port()
+
+    def main(rank, size):
+        from adaptdl_b200.reducer import Reducer
+        reducer = Reducer(rank, size, "127.0.0.1", port)
+        if rank == 0:
+            batch_size = 28
+            x = {"foo": 1}
+        else:
+            x = {"bar": 1}
+            batch_size = 0
+        assert reducer.broadcast(batch_size) == 28
+        total = reducer.allreduce(collections.Counter(x))
+        assert total["foo"] == 1 and total["bar"] == size - 1
+        futures = [reducer.allreduce_async(i) for i in range(10)]
+        for i, fut in reversed(list(enumerate(futures))):
+            assert fut.result() == i * size
+        reducer.close()
+
+    ctx = mp.get_context("fork")
+    procs = [ctx.Process(target=main, args=(r, 3)) for r in range(3)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+
+
+def test_signal_flag():
+    import signal
+    from adaptdl_b200 import _signal
+    _signal.install()
+    assert not _signal.get_exit_flag()
+    os.kill(os.getpid(), signal.SIGTERM)
+    assert _signal.get_exit_flag()
+    _signal.set_exit_flag(False)

@@ -1,0 +1,320 @@
+"""Epoch loop, data loader/sampler, accumulator and metrics across
+restarts at changing replica counts (ideas from the reference's
+torch/*_test.py, run on the local elastic harness)."""
+import collections
+import math
+
+import pytest
+import torch
+from torch.utils.data import TensorDataset
+
+from adaptdl_b200.utils.testing import elastic_multiprocessing
+from adaptdl_b200.torch.data import (ElasticSampler, AdaptiveDataLoader,
+                                     current_dataloader)
+
+
+@pytest.mark.parametrize("num_replicas", [1, 3, 5])
+@pytest.mark.parametrize("dataset_size", [9, 15, 25])
+def test_sampler_epoch(num_replicas, dataset_size):
+    _sampler_epoch(num_replicas, dataset_size)
+
+
+def _sampler_epoch(num_replicas, dataset_size, epoch=0, index=0,
+                   shuffle=True):
+    dataset = TensorDataset(torch.rand(dataset_size))
+    sampler = ElasticSampler(dataset, shuffle=shuffle)
+    sampler.num_replicas = num_replicas
+    sampler.set_epoch(epoch, index)
+    per_rank = []
+    counts = collections.Counter()
+    for rank in range(num_replicas):
+        sampler.rank = rank
+        per_rank.append(list(sampler))
+        expect = math.ceil((dataset_size - index % dataset_size)
+                           / num_replicas)
+        assert len(sampler) == expect == len(per_rank[rank])
+        assert list(sampler) == per_rank[rank]          # deterministic
+        counts.update(per_rank[rank])
+    assert len(counts) >= dataset_size - index % dataset_size
+    assert all(0 <= key < dataset_size for key in counts)
+    assert max(counts.values()) - min(counts.values()) <= 1
+    return per_rank
+
+
+@pytest.mark.parametrize("num_replicas", [1, 3, 5])
+@pytest.mark.parametrize("dataset_size", [9, 15, 25])
+def test_sampler_shuffle(num_replicas, dataset_size):
+    e0 = _sampler_epoch(num_replicas, dataset_size, epoch=0)
+    e1 = _sampler_epoch(num_replicas, dataset_size, epoch=1)
+    assert e0 != e1
+    e0 = _sampler_epoch(num_replicas, dataset_size, 0, shuffle=False)
+    e1 = _sampler_epoch(num_replicas, dataset_size, 1, shuffle=False)
+    assert e0 == e1
+
+
+@pytest.mark.parametrize("num_replicas", [1, 3, 5])
+@pytest.mark.parametrize("dataset_size", [9, 15, 25])
+def test_sampler_index(num_replicas, dataset_size):
+    index = dataset_size // 2
+    per_rank = _sampler_epoch(num_replicas, dataset_size, index=index,
+                                  shuffle=False)
+    samples = sum(per_rank, [])
+    assert all(idx in samples for idx in range(index, dataset_size))
+    per_rank = _sampler_epoch(num_replicas, dataset_size,
+                                  index=2 * dataset_size, shuffle=False)
+    assert set(sum(per_rank, [])) == set(range(dataset_size))
+
+
+def test_sampler_second_pass_reshuffles():
+    dataset = TensorDataset(torch.rand(20))
+    sampler = ElasticSampler(dataset, shuffle=True)
+    sampler.set_epoch(3, 0)
+    first = list(sampler)
+    sampler.set_epoch(3, 20)       # same epoch, second pass over the data
+    assert list(sampler) != first
+
+
+@elastic_multiprocessing
+def test_epoch():
+    from adaptdl_b200 import checkpoint
+    from adaptdl_b200.env import num_restarts
+    from adaptdl_b200.torch.epoch import (remaining_epochs_until,
+                                          current_epoch, finished_epochs)
+    assert current_epoch() is None
+    if num_restarts() == 0:
+        assert finished_epochs() == 0
+        expected = list(range(6))
+    else:
+        assert finished_epochs() == 5
+        expected = list(range(5, 10))
+    for idx, epoch in enumerate(remaining_epochs_until(10)):
+        assert epoch == expected[idx] == current_epoch() == finished_epochs()
+        with pytest.raises(RuntimeError):
+            next(remaining_epochs_until(20))
+        if num_restarts() == 0 and epoch == 5:
+            checkpoint.save_all_states()
+            return 5
+    assert finished_epochs() == 10
+    assert list(remaining_epochs_until(10)) == []
+    assert list(remaining_epochs_until(12)) == [10, 11]
+    return 0
+
+
+@elastic_multiprocessing
+def test_dataloader_restarts():
+    from adaptdl_b200 import checkpoint, collective
+    from adaptdl_b200.env import num_restarts, num_replicas
+    collective.initialize()
+    dataset_size, init_batch_size = 100, 10
+    dataset = TensorDataset(torch.rand(dataset_size))
+    dataloader = AdaptiveDataLoader(dataset, batch_size=init_batch_size)
+    # 2 batches at 1 replica (20 samples), 5 batches at 4 replicas (local 3,
+    # 60 samples), the remaining 20 samples at 2 replicas (2 batches).
+    assert current_dataloader() is None
+    for idx, batch in enumerate(dataloader):
+        if num_restarts() == 0 and idx == 2:
+            checkpoint.save_all_states()
+            return 4
+        if num_restarts() == 1 and idx == 5:
+            checkpoint.save_all_states()
+            return 2
+        assert current_dataloader() is dataloader._elastic
+        local_bsz = batch[0].size(0)
+        assert dataloader.current_local_bsz == local_bsz
+        assert local_bsz == math.ceil(init_batch_size / num_replicas())
+        assert dataloader.current_batch_size == num_replicas() * local_bsz
+    assert idx == 1
+    assert dataloader.current_local_bsz is None
+    return 0
+
+
+@elastic_multiprocessing
+def test_dataloader_break():
+    from adaptdl_b200 import collective
+    from adaptdl_b200.env import num_restarts
+    if num_restarts() == 0:
+        return 2
+    collective.initialize()
+    dataloader = AdaptiveDataLoader(TensorDataset(torch.rand(100)),
+                                    batch_size=10)
+    for idx, batch in enumerate(dataloader):
+        assert current_dataloader() is dataloader._elastic
+        if idx == 5:
+            break
+    assert current_dataloader() is None
+    for idx, batch in enumerate(dataloader):
+        pass
+    assert idx == 9
+    return 0
+
+
+@elastic_multiprocessing
+def test_dataloader_skipdone_replay():
+    """A loop that finished before the checkpoint is skipped on replay."""
+    from adaptdl_b200 import checkpoint, collective
+    from adaptdl_b200.env import num_restarts
+    from adaptdl_b200.torch.epoch import remaining_epochs_until
+    collective.initialize()
+    train = AdaptiveDataLoader(TensorDataset(torch.rand(40)), batch_size=10)
+    valid = AdaptiveDataLoader(TensorDataset(torch.rand(20)), batch_size=10)
+    seen = collections.Counter()
+    for epoch in remaining_epochs_until(2):
+        for batch in train:
+            seen["train"] += 1
+        for idx, batch in enumerate(valid):
+            seen["valid"] += 1
+            if num_restarts() == 0 and epoch == 0 and idx == 0:
+                checkpoint.save_all_states()
+                return 2
+    if num_restarts() == 1:
+        # epoch 0: train loop skipped (it finished before the checkpoint);
+        # valid restarts from index 0 (the checkpoint was taken while its
+        # first batch was still being processed): 2 batches per epoch.
+        assert seen["train"] == 4 and seen["valid"] == 2 + 2
+    return 0
+
+
+def test_dataloader_rejects_samplers_and_bad_bounds():
+    import os
+    os.environ.pop("ADAPTDL_CHECKPOINT_PATH", None)
+    ds = TensorDataset(torch.rand(10))
+    with pytest.raises(ValueError):
+        AdaptiveDataLoader(ds, batch_size=2,
+                           sampler=torch.utils.data.SequentialSampler(ds))
+    loader = AdaptiveDataLoader(ds, batch_size=4)
+    with pytest.raises(ValueError):
+        loader.autoscale_batch_size(2)
+    with pytest.raises(ValueError):
+        loader.autoscale_batch_size(8, local_bsz_bounds=(5, 8))
+    with pytest.raises(ValueError):
+        loader.autoscale_batch_size(8, local_bsz_bounds=(1, 3))
+    loader.autoscale_batch_size(8, local_bsz_bounds=(1, 4),
+                                gradient_accumulation=True)
+    assert loader.training
+
+
+@elastic_multiprocessing
+def test_accumulator_restarts():
+    from adaptdl_b200 import checkpoint, collective
+    from adaptdl_b200.env import num_restarts, replica_rank
+    from adaptdl_b200.torch.accumulator import Accumulator
+    collective.initialize()
+    accum = Accumulator()
+    if num_restarts() == 0:
+        accum["a"] += 15
+    assert "a" not in accum
+    with accum.synchronized():
+        assert "a" in accum and accum["a"] == 15
+    assert "a" not in accum
+    if num_restarts() == 0:
+        accum["a"] -= 5
+        checkpoint.save_all_states()
+        return 4
+    if num_restarts() == 1:
+        accum.update({"a": replica_rank(), "b": replica_rank()})
+    assert len(accum) == 0
+    with accum.synchronized():
+        assert len(accum) == 2
+        assert accum["a"] == 16 and accum["b"] == 6
+    assert len(accum) == 0
+    if num_restarts() == 1:
+        checkpoint.save_all_states()
+        return 2
+    if num_restarts() == 2:
+        accum -= {"b": 5, "c": 5}
+    with accum.synchronized():
+        assert accum["a"] == 16 and accum["b"] == -4 and accum["c"] == -10
+        accum.clear()
+    with accum.synchronized():
+        assert not accum
+    with pytest.raises(TypeError):
+        accum["x"] = 3
+    return 0
+
+
+@pytest.mark.parametrize("num_replicas", [1, 3])
+@elastic_multiprocessing
+def test_profile(num_replicas):
+    from adaptdl_b200 import checkpoint
+    from adaptdl_b200.env import num_restarts
+    from adaptdl_b200.torch._metrics import (
+        profile_step_start, profile_sync_time, profile_step_commit,
+        _metrics_state)
+    if num_restarts() == 0:
+        profile = _metrics_state().profile
+        assert len(profile) == 0
+        profile_step_start(1)            # never committed
+        profile_sync_time(1.0)
+        profile_step_start(2)
+        profile_sync_time(1.0)
+        profile_sync_time(2.0)
+        profile_step_commit()
+        key = (1, 1, 2)
+        assert len(profile) == 1
+        assert profile[key]["accum_count"] == 0
+        assert profile[key]["optim_count"] == 1
+        assert profile[key]["optim_sync_time"] == 3.0
+        assert profile[key]["optim_step_time"] >= 0.0
+        checkpoint.save_all_states()
+        return num_replicas
+    profile = _metrics_state().profile
+    key = (1, 1, 2)
+    assert len(profile) == 1 and profile[key]["optim_sync_time"] == 3.0
+    profile_step_start(3)
+    profile_sync_time(2.0)
+    profile_sync_time(3.0)
+    profile_step_commit()
+    key = (1, num_replicas, 3)
+    old = profile[key]["optim_step_time"]
+    profile_step_start(3)
+    profile_sync_time(3.0)
+    profile_sync_time(4.0)
+    profile_step_commit(step_time=0.5)     # device-timed override
+    assert len(profile) == 2
+    assert profile[key]["optim_count"] == 2
+    assert profile[key]["optim_sync_time"] == 12.0
+    assert profile[key]["optim_step_time"] == pytest.approx(old + 0.5)
+    return 0
+
+
+@elastic_multiprocessing
+def test_profile_accumulation_and_fit():
+    from adaptdl_b200 import checkpoint
+    from adaptdl_b200.env import num_restarts
+    from adaptdl_b200.torch import _metrics
+    from adaptdl_b200.torch._metrics import (
+        profile_step_start, profile_sync_time, profile_step_commit,
+        _metrics_state, _fit_perf_params)
+    if num_restarts() == 0:
+        for bsz, sync in ((2, 4.0), (5, 6.0)):
+            for _ in range(2):
+                profile_step_start(bsz)
+                profile_step_commit(accumulation_step=True, step_time=0.1)
+            profile_step_start(bsz)
+            profile_sync_time(sync)
+            profile_step_commit(accumulation_step=False, step_time=0.2)
+        profile = _metrics_state().profile
+        assert len(profile) == 2
+        assert profile[(1, 1, 2)]["accum_count"] == 2
+        assert profile[(1, 1, 2)]["optim_count"] == 1
+        profile_step_start(3)              # accumulation only, no optim yet
+        profile_step_commit(accumulation_step=True)
+        _fit_perf_params()                 # sync > step is clamped, no crash
+        assert _metrics_state().perf_params is not None
+        _metrics.set_batch_size(4, 64, (2, 8), True)
+        _metrics.update_grad_params("k", 0.5, 0.25)
+        hints = _metrics._build_sched_hints()
+        assert hints["initBatchSize"] == 4 and hints["maxBatchSize"] == 64
+        assert hints["gradParams"] == {"norm": 0.5, "var": 0.25}
+        assert hints["maxProfiledReplicas"] == 1
+        assert set(hints["perfParams"]) == {
+            "alpha_c", "beta_c", "alpha_n", "beta_n", "alpha_r", "beta_r",
+            "gamma"}
+        assert _metrics.get_goodput_fn() is not None
+        checkpoint.save_all_states()
+        return 2
+    state = _metrics_state()
+    assert len(state.profile) == 3
+    assert state.perf_params is not None and state.grad_params == (0.5, 0.25)
+    assert state.local_bsz_bounds == (2, 8) and state.gradient_accumulation
+    return 0
