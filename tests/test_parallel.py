@@ -1,0 +1,186 @@
+"""AdaptiveDataParallel end to end on CPU/gloo: single replica, two
+replicas (statistics vs. a manual computation), gradient accumulation, and
+a mid-training rescale through a checkpoint."""
+import numpy as np
+import pytest
+import torch
+from torch.utils.data import Dataset
+
+from adaptdl_b200.utils.testing import elastic_multiprocessing
+
+
+class LRIterableDataset(Dataset):
+    def __init__(self, size, true_values, noise):
+        torch.manual_seed(1234)
+        x = torch.randn(size, 1)
+        self._values = (x, true_values[0] + true_values[1] * x
+                        + noise * torch.randn(size, 1))
+        self._len = size
+
+    def __getitem__(self, index):
+        return self._values[0][index], self._values[1][index]
+
+    def __len__(self):
+        return self._len
+
+
+@elastic_multiprocessing
+def test_single_replica_parallel():
+    """Reference parallel_test: fit y = 3 + 4x to atol 0.1."""
+    import adaptdl_b200.torch as adl
+    true_values = np.asarray([3.0, 4.0])
+    dataset = LRIterableDataset(1000, true_values, 1.0)
+    dataloader = adl.AdaptiveDataLoader(dataset, batch_size=32,
+                                        shuffle=False, num_workers=0)
+    adl.init_process_group("gloo")
+    model = torch.nn.Linear(1, 1, bias=True)
+    params = [model.bias, model.weight]
+    sgd = torch.optim.SGD([{"params": [param]} for param in params], lr=0.01)
+    schedule = torch.optim.lr_scheduler.MultiStepLR(sgd, [50])
+    model = adl.AdaptiveDataParallel(model, sgd, schedule)
+    loss = torch.nn.MSELoss()
+    for epoch in adl.remaining_epochs_until(100):
+        for inputs, targets in dataloader:
+            sgd.zero_grad()
+            loss(model(inputs), targets).backward()
+            sgd.step()
+        schedule.step()
+    got = np.asarray([float(p.detach()) for p in params])
+    assert np.all(np.isclose(got, true_values, atol=0.1)), got
+    assert model.gain >= 1.0 - 1e-6
+    assert model.gns.get_progress() > 0
+    return 0
+
+
+@elastic_multiprocessing
+def test_two_replicas_statistics_and_rescale():
+    import adaptdl_b200.torch as adl
+    from adaptdl_b200 import checkpoint, env
+    from adaptdl_b200.torch.gradient_noise_scale import estimate
+    if env.num_restarts() == 0:
+        return 2
+    adl.init_process_group("gloo")
+    rank, world = env.replica_rank(), env.num_replicas()
+    torch.manual_seed(0)                         # same init on all ranks
+    model = torch.nn.Sequential(torch.nn.Linear(4, 8), torch.nn.Tanh(),
+                                torch.nn.Linear(8, 1))
+    if rank == 1:                                # broadcast must fix this
+        with torch.no_grad():
+            for p in model.parameters():
+                p.add_(1.0)
+    sgd = torch.optim.SGD(model.parameters(), lr=0.05, momentum=0.9)
+    net = adl.AdaptiveDataParallel(model, sgd)
+    ref = torch.nn.Sequential(torch.nn.Linear(4, 8), torch.nn.Tanh(),
+                              torch.nn.Linear(8, 1))
+    if env.num_restarts() == 1:
+        torch.manual_seed(0)
+        ref0 = torch.nn.Sequential(torch.nn.Linear(4, 8), torch.nn.Tanh(),
+                                   torch.nn.Linear(8, 1))
+        for p, q in zip(model.parameters(), ref0.parameters()):
+            assert torch.allclose(p, q), "rank 0's parameters must win"
+    ref.load_state_dict(model.state_dict())
+
+    torch.manual_seed(100)
+    data = torch.randn(64, 4)
+    target = data.sum(dim=1, keepdim=True)
+    dataset = torch.utils.data.TensorDataset(data, target)
+    loader = adl.AdaptiveDataLoader(dataset, batch_size=16, shuffle=False,
+                                    drop_last=True)
+    loss_fn = torch.nn.MSELoss()
+    for epoch in adl.remaining_epochs_until(2):
+        for step, (x, y) in enumerate(loader):
+            assert x.shape[0] == -(-16 // world)
+            sgd.zero_grad()
+            loss_fn(net(x), y).backward()
+            if env.num_restarts() == 1 and epoch == 0 and step == 0:
+                # check the fused statistics against a manual computation
+                # over BOTH replicas' micro-batches
+                idx = [list(range(r, 16, world))[:16 // world]
+                       for r in range(world)]
+                per_replica = []
+                for r in range(world):
+                    ref.zero_grad()
+                    loss_fn(ref(data[idx[r]]), target[idx[r]]).backward()
+                    per_replica.append(torch.cat(
+                        [p.grad.reshape(-1).clone()
+                         for p in ref.parameters()]))
+                mean = sum(per_replica) / world
+                mine = torch.cat([p.grad.reshape(-1)
+                                  for p in model.parameters()])
+                assert torch.allclose(mine, mean, atol=1e-6)
+                stats_local = np.mean([float((g.double() ** 2).sum())
+                                       for g in per_replica])
+                stats_total = float((mean.double() ** 2).sum())
+                # first step: the loader is not yet marked as the training
+                # loader, so accum_scale is still its default (= replicas)
+                want = estimate(stats_local, stats_total, world,
+                                scale=float(world))
+                assert net.gns.raw_sqr_avg[0] == pytest.approx(want[0],
+                                                               rel=1e-5)
+                assert net.gns.raw_var_avg[0] == pytest.approx(want[1],
+                                                               rel=1e-5)
+            sgd.step()
+            if env.num_restarts() == 1 and epoch == 1 and step == 1:
+                checkpoint.save_all_states()
+                return 3                         # rescale 2 -> 3 replicas
+    # replicas stay identical
+    flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+    from adaptdl_b200 import collective
+    everyone = collective.allreduce([flat.tolist()], lambda a, b: a + b)
+    for other in everyone[1:]:
+        assert np.allclose(other, everyone[0], atol=1e-6)
+    assert adl.finished_epochs() == 2
+    if env.num_restarts() == 2:
+        assert world == 3
+        assert net.gns.get_progress() > 0          # restored from checkpoint
+    return 0
+
+
+@elastic_multiprocessing
+def test_accumulation_through_dataloader():
+    """Gradient accumulation driven by the dataloader (accumulation_steps
+    micro-batches, sync + optimizer step on the last one)."""
+    import adaptdl_b200.torch as adl
+    from adaptdl_b200 import env
+    if env.num_restarts() == 0:
+        return 2
+    adl.init_process_group("gloo")
+    torch.manual_seed(0)
+    model = torch.nn.Linear(3, 1)
+    sgd = torch.optim.SGD(model.parameters(), lr=0.01)
+    net = adl.AdaptiveDataParallel(model, sgd)
+    data = torch.randn(96, 3)
+    dataset = torch.utils.data.TensorDataset(data, data.sum(1, keepdim=True))
+    loader = adl.AdaptiveDataLoader(dataset, batch_size=8, drop_last=True)
+    loader.autoscale_batch_size(64, local_bsz_bounds=(2, 8),
+                                gradient_accumulation=True)
+    # force a known configuration: local_bsz 4, 2 accumulation steps
+    helper = loader._elastic
+    orig = helper._sync_local_bsz
+
+    def fixed():
+        orig()
+        helper._state.current_local_bsz = 4
+        helper._state.accumulation_steps = 2
+        return 4
+    helper._sync_local_bsz = fixed
+    updates = 0
+    for epoch in adl.remaining_epochs_until(1):
+        for i, (x, y) in enumerate(loader):
+            assert x.shape[0] == 4
+            before = model.weight.detach().clone()
+            sgd.zero_grad()
+            torch.nn.functional.mse_loss(net(x), y).backward()
+            sgd.step()
+            changed = not torch.equal(before, model.weight.detach())
+            assert changed == (i % 3 == 2), (i, changed)
+            updates += changed
+            if i % 3 == 2:
+                assert net.gns.accum_count == 3
+                # scale = (4*2/8) * 3 = 3
+                assert loader.current_batch_size == 4 * 3 * 2
+            if i == 8:
+                break
+    assert updates == 3
+    assert net.gns._state["biased"] is False
+    return 0
