@@ -1,0 +1,392 @@
+"""Gradient reducer on hand-written sm_100a kernels over NVLink peer memory.
+
+One fused launch per bucket (``adl_allreduce_gns``, csrc/adl_kernels.cu):
+two-shot all-reduce by direct loads/stores on the peers' gradient arenas,
+``1/(N*accum)`` scaling, and both gradient-noise-scale statistics from the
+same registers -- replacing, per step, the reference's NCCL bucket
+all-reduces, ~10 element-wise/reduction launches per parameter, a second
+NCCL all-reduce for the statistics, one full fp32 copy of the gradients and
+``1 + num_param_groups`` host synchronisations.
+
+Stream plumbing: every primitive runs on a dedicated high-priority
+communication stream, ordered after the producing backward kernels by an
+event; the compute stream waits for the communication stream once, at the
+end of backward. Statistics travel to the host through a pinned mailbox
+written by ``adl_finalize_stats`` (no ``.item()``); the host waits for them
+lazily, on a CUDA event, when it first needs them.
+"""
+
+import ctypes
+import os
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from adaptdl_b200 import _native
+from adaptdl_b200._native import (ReduceArgs, LocalArgs, FinalizeArgs,
+                                  BcastArgs, MAX_RANKS, MAX_CTAS, check)
+from adaptdl_b200.parallel import layout, symm
+from adaptdl_b200.parallel.reducer_base import GradReducer, GradStats
+
+_DTYPE_CODE = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
+_PAD_BYTES = 2 * MAX_CTAS * MAX_RANKS * 4
+_STAGING_BYTES = 16 << 20
+_ALIGN = 512
+_TIMEOUT_NS = int(float(os.environ.get("ADAPTDL_B200_TIMEOUT_S", "20")) * 1e9)
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+class CudaGradReducer(GradReducer):
+
+    def __init__(self, param_groups, world_size, rank, should_sync,
+                 bucket_cap_mb=25, process_group=None, name="reducer"):
+        self._lib = _native.load()
+        self._pg = process_group
+        if world_size > MAX_RANKS:
+            raise ValueError("at most {} replicas per NVLink domain"
+                             .format(MAX_RANKS))
+        self._region = None
+        self._provider = None
+        self._epoch = 0
+        self._seq = 0
+        self._seg = {}
+        self._had_pair = False
+        self._pending_events = None
+        self._comm = None
+        super().__init__(param_groups, world_size, rank, should_sync,
+                         bucket_cap_mb, name)
+
+    # ------------------------------------------------------------------
+    # storage: one symmetric region holds pad | stats exchange | staging |
+    # every arena's gradient buffer
+    # ------------------------------------------------------------------
+
+    def _attach(self):
+        dev = self.device
+        if dev.type != "cuda":
+            raise ValueError("CudaGradReducer needs CUDA parameters")
+        for arena in self.arenas:
+            if arena.dtype not in _DTYPE_CODE:
+                raise ValueError("unsupported gradient dtype {}"
+                                 .format(arena.dtype))
+        torch.cuda.set_device(dev)
+        check(self._lib.adl_set_device(dev.index), "adl_set_device")
+        G = self.num_groups
+        self._xchg_bytes = _round_up(2 * 4 * G * 8, _ALIGN)
+        offsets, cursor = {}, 0
+        offsets["pad"] = cursor
+        cursor += _round_up(_PAD_BYTES, _ALIGN)
+        offsets["xchg"] = cursor
+        cursor += self._xchg_bytes
+        offsets["staging"] = cursor
+        cursor += _STAGING_BYTES if self.world_size > 1 else 0
+        for i, arena in enumerate(self.arenas):
+            offsets[("grad", i)] = cursor
+            itemsize = torch.empty((), dtype=arena.dtype).element_size()
+            cursor += _round_up(max(arena.total, 1) * itemsize, _ALIGN)
+        self._provider = symm.make_provider(
+            self._pg if self._pg is not None else
+            (dist.group.WORLD if self.world_size > 1 else None),
+            dev, self.world_size)
+        self._region = self._provider.allocate(cursor)
+        self._offsets = offsets
+        _, self._pad_ptrs = self._region.carve(offsets["pad"], _PAD_BYTES)
+        _, self._xchg_ptrs = self._region.carve(offsets["xchg"],
+                                                self._xchg_bytes)
+        if self.world_size > 1:
+            self._staging, self._staging_ptrs = self._region.carve(
+                offsets["staging"], _STAGING_BYTES)
+        self._grad_ptrs = {}
+        for i, arena in enumerate(self.arenas):
+            itemsize = torch.empty((), dtype=arena.dtype).element_size()
+            view, ptrs = self._region.carve(
+                offsets[("grad", i)], max(arena.total, 1) * itemsize,
+                arena.dtype)
+            arena._symm_grad = view
+            self._grad_ptrs[i] = ptrs
+        # statistics, error word, timers, mailbox
+        self._stats = torch.zeros(4, G, dtype=torch.float64, device=dev)
+        self._result = torch.zeros(4, G, dtype=torch.float64, device=dev)
+        self._err = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._t_start = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._mailboxes = [torch.zeros(4 * G + 4, dtype=torch.float64)
+                           .pin_memory() for _ in range(2)]
+        self._comm = torch.cuda.Stream(dev, priority=-1)
+        self._sm_count = max(self._lib.adl_sm_count(dev.index), 1)
+        self._reduce_ctas = int(os.environ.get(
+            "ADAPTDL_B200_REDUCE_CTAS", "32"))
+        self._reduce_ctas = max(1, min(self._reduce_ctas, MAX_CTAS - 1))
+        super()._attach()
+        for i, arena in enumerate(self.arenas):
+            self._build_seg_tables(i, arena)
+
+    def _alloc_flat(self, arena, kind):
+        if kind == "grad":
+            return arena._symm_grad
+        if kind == "pinv":
+            return torch.ones(max(arena.total, 1), dtype=arena.dtype,
+                              device=self.device)
+        return torch.zeros(max(arena.total, 1), dtype=arena.dtype,
+                           device=self.device)
+
+    def _build_seg_tables(self, arena_idx, arena):
+        vec = layout.VEC_BYTES // torch.empty(
+            (), dtype=arena.dtype).element_size()
+        for b in arena.buckets:
+            rows = sorted(layout.segment_table(b, vec))
+            n_vec = b.length // vec
+            ends = [r[1] for r in rows]
+            groups = [r[2] for r in rows]
+            # every vector must resolve to a segment: stretch each end to
+            # the next start (padding is zero) and the last to the bucket end
+            for j in range(len(rows) - 1):
+                ends[j] = max(ends[j], rows[j + 1][0])
+            ends[-1] = n_vec
+            self._seg[(arena_idx, b.index)] = (
+                torch.tensor(ends, dtype=torch.int32, device=self.device),
+                torch.tensor(groups, dtype=torch.int32, device=self.device),
+                n_vec, vec)
+
+    # ------------------------------------------------------------------
+
+    def _arena_index(self, arena):
+        for i, a in enumerate(self.arenas):
+            if a is arena:
+                return i
+        raise KeyError
+
+    def _itemsize(self, arena):
+        return layout.VEC_BYTES // self._seg[
+            (self._arena_index(arena), arena.buckets[0].index)][3]
+
+    def _order_after_compute(self):
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._comm.wait_event(ev)
+
+    def _local_grid(self, n_vec):
+        return max(1, min(2 * self._sm_count,
+                          (n_vec + 2 * 512 - 1) // (2 * 512)))
+
+    def _local_args(self, arena, bucket, mode):
+        ai = self._arena_index(arena)
+        ends, groups, n_vec, vec = self._seg[(ai, bucket.index)]
+        itemsize = layout.VEC_BYTES // vec
+        off = bucket.start * itemsize
+        args = LocalArgs()
+        args.g = arena.grad.data_ptr() + off
+        if mode in (0, 1):
+            args.a = self._ensure(arena, "acc").data_ptr() + off
+        if mode == 2:
+            args.pv = self._ensure(arena, "prev").data_ptr() + off
+        args.pinv = (arena.pinv.data_ptr() + off) \
+            if (self._precond_fn is not None and arena.pinv is not None) \
+            else None
+        args.n_vec = n_vec
+        args.segs.seg_end = ends.data_ptr()
+        args.segs.seg_group = groups.data_ptr()
+        args.segs.n_seg = ends.numel()
+        args.n_groups = self.num_groups
+        return args, n_vec
+
+    def _row(self, r):
+        return self._stats.data_ptr() + r * self.num_groups * 8
+
+    # -- primitives ------------------------------------------------------
+
+    def _reset_partials(self):
+        if getattr(self, "_stats", None) is not None:
+            self._stats.zero_()
+
+    def _on_begin_backward(self):
+        self._had_pair = False
+
+    def _mark_sync_start(self):
+        check(self._lib.adl_stamp(
+            self._t_start.data_ptr(),
+            torch.cuda.current_stream(self.device).cuda_stream), "adl_stamp")
+        self.launches += 1
+
+    def _launch_local(self, arena, bucket, mode, flag=0):
+        args, n_vec = self._local_args(arena, bucket, mode)
+        args.s0 = self._row(1) if mode == 2 else self._row(0)
+        args.s1 = self._row(2)
+        args.s2 = self._row(3)
+        args.flag = flag
+        self._order_after_compute()
+        check(self._lib.adl_local(
+            ctypes.byref(args), mode, _DTYPE_CODE[arena.dtype],
+            self._local_grid(n_vec), self._comm.cuda_stream), "adl_local")
+        self.launches += 1
+
+    def _fold_acc(self, arena, bucket):
+        self._launch_local(arena, bucket, 0)
+
+    def _fold_final(self, arena, bucket):
+        self._launch_local(arena, bucket, 1)
+
+    def _pair(self, arena, bucket):
+        self._launch_local(arena, bucket, 2, flag=int(self._prev_valid))
+        self._had_pair = self._had_pair or self._prev_valid
+
+    def _reduce(self, arena, bucket, scale, want_local):
+        ai = self._arena_index(arena)
+        ends, groups, n_vec, vec = self._seg[(ai, bucket.index)]
+        itemsize = layout.VEC_BYTES // vec
+        off = bucket.start * itemsize
+        args = ReduceArgs()
+        for p in range(self.world_size):
+            args.buf[p] = self._grad_ptrs[ai][p] + off
+            args.pad[p] = self._pad_ptrs[p]
+        args.rank, args.world = self.rank, self.world_size
+        self._epoch += 1
+        args.epoch = self._epoch & 0xFFFFFFFF
+        args.n_vec = n_vec
+        args.scale = scale
+        args.want_local = int(want_local)
+        args.segs.seg_end = ends.data_ptr()
+        args.segs.seg_group = groups.data_ptr()
+        args.segs.n_seg = ends.numel()
+        args.n_groups = self.num_groups
+        args.pinv = (arena.pinv.data_ptr() + off) \
+            if (self._precond_fn is not None and arena.pinv is not None) \
+            else None
+        args.L = self._row(0)
+        args.T = self._row(1)
+        args.err = self._err.data_ptr()
+        args.timeout_ns = _TIMEOUT_NS
+        slice_vec = n_vec // self.world_size
+        if self.world_size > 1:
+            grid = max(1, min(self._reduce_ctas,
+                              (slice_vec + 511) // 512))
+        else:
+            grid = self._local_grid(n_vec)
+            grid = min(grid, MAX_CTAS - 1) if False else grid
+        self._order_after_compute()
+        check(self._lib.adl_allreduce_gns(
+            ctypes.byref(args), _DTYPE_CODE[arena.dtype], grid,
+            self._comm.cuda_stream), "adl_allreduce_gns")
+        self.launches += 1
+
+    def _finalize_step(self):
+        pair_mode = self.world_size == 1 and self._k_before == 0
+        if pair_mode:
+            self._prev_valid = True
+        n_rows = 4 if (pair_mode and self._had_pair) else 2
+        G = self.num_groups
+        args = FinalizeArgs()
+        for p in range(self.world_size):
+            args.xchg[p] = self._xchg_ptrs[p]
+            args.pad[p] = self._pad_ptrs[p]
+        args.rank, args.world = self.rank, self.world_size
+        self._epoch += 1
+        args.epoch = self._epoch & 0xFFFFFFFF
+        self._seq += 1
+        args.parity = self._seq & 1
+        args.n_rows = n_rows
+        args.n_groups = G
+        for r in range(4):
+            args.rows[r] = self._row(r)
+        args.sum_mask = 0b0011 if self.world_size > 1 else 0
+        mailbox = self._mailboxes[self._seq & 1]
+        args.mailbox = mailbox.data_ptr()
+        args.result = self._result.data_ptr()
+        args.t_start = self._t_start.data_ptr()
+        args.seq = self._seq
+        args.err = self._err.data_ptr()
+        args.timeout_ns = _TIMEOUT_NS
+        self._order_after_compute()
+        check(self._lib.adl_finalize_stats(ctypes.byref(args),
+                                           self._comm.cuda_stream),
+              "adl_finalize_stats")
+        self.launches += 1
+        done = torch.cuda.Event()
+        done.record(self._comm)
+        # the optimizer (compute stream) must see the reduced gradients
+        torch.cuda.current_stream(self.device).wait_event(done)
+        count = self.world_size * self._accum_count
+        return (mailbox, done, count, n_rows, self._seq)
+
+    def _resolve_stats(self, handle):
+        mailbox, done, count, n_rows, seq = handle
+        done.synchronize()
+        G = self.num_groups
+        arr = mailbox.numpy()
+        n = n_rows * G
+        if int(arr[n]) != seq:
+            raise RuntimeError("statistics mailbox out of sequence "
+                               "({} != {})".format(int(arr[n]), seq))
+        if int(arr[n + 2]) != 0:
+            raise RuntimeError(
+                "fused all-reduce timed out waiting for a peer "
+                "(error word {})".format(int(arr[n + 2])))
+        rows = np.array(arr[:n], dtype=np.float64).reshape(n_rows, G)
+        pair = (rows[2], rows[3]) if n_rows == 4 else None
+        return GradStats(rows[0], rows[1], count, pair,
+                         sync_time=float(arr[n + 1]) * 1e-9)
+
+    # -- broadcast -----------------------------------------------------------
+
+    def broadcast_parameters(self, tensors, src=0):
+        if self.world_size <= 1:
+            return
+        tensors = [t for t in tensors if t is not None and t.numel() > 0]
+        stream = torch.cuda.current_stream(self.device)
+        chunk, chunk_bytes = [], 0
+
+        def flush():
+            nonlocal chunk, chunk_bytes
+            if not chunk:
+                return
+            flat = torch.cat([t.detach().reshape(-1).view(torch.uint8)
+                              for t in chunk])
+            n = flat.numel()
+            n_pad = _round_up(n, 16)
+            if self.rank == src:
+                self._staging[:n].copy_(flat)
+            args = BcastArgs()
+            for p in range(self.world_size):
+                args.staging[p] = self._staging_ptrs[p]
+                args.pad[p] = self._pad_ptrs[p]
+            args.rank, args.world, args.src = self.rank, self.world_size, src
+            self._epoch += 1
+            args.epoch = self._epoch & 0xFFFFFFFF
+            args.dst = self._staging_ptrs[self.rank]
+            args.n_vec = n_pad // 16
+            args.err = self._err.data_ptr()
+            args.timeout_ns = _TIMEOUT_NS
+            grid = max(1, min(16, (n_pad // 16 + 1023) // 1024))
+            check(self._lib.adl_bcast_pull(ctypes.byref(args), grid,
+                                           stream.cuda_stream),
+                  "adl_bcast_pull")
+            self.launches += 1
+            if self.rank != src:
+                cursor = 0
+                for t in chunk:
+                    nb = t.numel() * t.element_size()
+                    t.detach().reshape(-1).view(torch.uint8).copy_(
+                        self._staging[cursor:cursor + nb])
+                    cursor += nb
+            chunk, chunk_bytes = [], 0
+
+        for t in tensors:
+            if not t.is_contiguous():
+                raise ValueError("broadcast needs contiguous tensors")
+            nb = t.numel() * t.element_size()
+            if nb > _STAGING_BYTES:
+                flush()
+                flat = t.detach().reshape(-1).view(torch.uint8)
+                for lo in range(0, nb, _STAGING_BYTES):
+                    piece = flat[lo:lo + _STAGING_BYTES]
+                    chunk, chunk_bytes = [piece], piece.numel()
+                    flush()
+                continue
+            if chunk_bytes + nb > _STAGING_BYTES:
+                flush()
+            chunk.append(t)
+            chunk_bytes += nb
+        flush()

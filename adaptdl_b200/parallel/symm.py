@@ -1,0 +1,228 @@
+"""Symmetric (peer-mapped) device memory for one box of NVLink/NVSwitch GPUs.
+
+A :class:`SymmetricRegion` is one allocation of identical size on every rank
+whose physical pages are mapped into *every* rank's address space, so a kernel
+on rank r can ``ld.global``/``st.global`` rank p's copy directly over NVLink.
+
+Two providers:
+
+* ``native`` (default): our own runtime (``csrc/adl_symm.cpp``) -- CUDA VMM
+  allocations exported as POSIX fds, exchanged between the rank processes
+  over unix datagram sockets with ``SCM_RIGHTS``, imported and mapped by each
+  peer. Rebuilt from scratch at every elastic restart, at whatever world size
+  the new generation has.
+* ``torch``: ``torch.distributed._symmetric_memory`` as a bring-up fallback.
+"""
+
+import logging
+import os
+import socket
+import struct
+import uuid
+
+import torch
+import torch.distributed as dist
+
+from adaptdl_b200 import _native
+
+LOG = logging.getLogger(__name__)
+
+
+class _DeviceMemory(object):
+    """Expose a raw device pointer through ``__cuda_array_interface__`` so
+    torch can wrap it without copying."""
+
+    def __init__(self, ptr, nbytes, owner=None):
+        self.__cuda_array_interface__ = {
+            "shape": (int(nbytes),), "typestr": "|u1",
+            "data": (int(ptr), False), "version": 2, "strides": None,
+        }
+        self._owner = owner
+
+
+def _all_gather_object(obj, group):
+    out = [None] * dist.get_world_size(group)
+    dist.all_gather_object(out, obj, group=group)
+    return out
+
+
+class SymmetricRegion(object):
+    """``tensor``: this rank's bytes (uint8, on ``device``); ``ptrs[p]``:
+    address of rank p's bytes in *this* process."""
+
+    def __init__(self, tensor, ptrs, nbytes, provider, keepalive=None):
+        self.tensor = tensor
+        self.ptrs = list(ptrs)
+        self.nbytes = nbytes
+        self.provider = provider
+        self._keepalive = keepalive
+
+    def carve(self, offset, nbytes, dtype=torch.uint8):
+        """A typed view of ``[offset, offset+nbytes)`` plus its per-rank
+        addresses."""
+        view = self.tensor[offset:offset + nbytes].view(dtype)
+        return view, [p + offset for p in self.ptrs]
+
+
+class _NativeProvider(object):
+    name = "native"
+
+    def __init__(self, group, device):
+        self.group = group
+        self.device = device
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.lib = _native.load()
+        if self.lib.adl_symm_init() != 0:
+            raise RuntimeError("symmetric memory runtime: "
+                               + self.lib.adl_symm_last_error().decode())
+        if not self.lib.adl_topo_vmm_fd_supported(device.index):
+            raise RuntimeError("device lacks POSIX-fd shareable VMM handles")
+        self.sock = socket.socket(socket.AF_UNIX, socket.SOCK_DGRAM)
+        token = uuid.uuid4().hex
+        self.addr = "\0adl-b200-{}-{}".format(token, self.rank)
+        self.sock.bind(self.addr)
+        self.sock.settimeout(120.0)
+        # gathering the addresses doubles as "everyone has bound"
+        self.addrs = _all_gather_object(self.addr, group)
+        self._serial = 0
+        self._mapped = []
+
+    def _check(self, code, what):
+        if code != 0:
+            raise RuntimeError("{}: {}".format(
+                what, self.lib.adl_symm_last_error().decode()))
+
+    def allocate(self, nbytes):
+        import ctypes
+        lib, dev = self.lib, self.device.index
+        size = ctypes.c_size_t()
+        self._check(lib.adl_symm_round_size(dev, nbytes, ctypes.byref(size)),
+                    "round_size")
+        size = size.value
+        handle, fd = ctypes.c_ulonglong(), ctypes.c_int()
+        self._check(lib.adl_symm_create(dev, size, ctypes.byref(handle),
+                                        ctypes.byref(fd)), "create")
+        serial = self._serial
+        self._serial += 1
+        header = struct.pack("!II", serial, self.rank)
+        for peer, addr in enumerate(self.addrs):
+            if peer != self.rank:
+                socket.send_fds(self.sock, [header], [fd.value], address=addr)
+        handles = {self.rank: handle.value}
+        stash = getattr(self, "_early", {})
+        while len(handles) < self.world:
+            key = next((k for k in stash if k[0] == serial), None)
+            if key is not None:
+                peer_fd = stash.pop(key)
+                src = key[1]
+            else:
+                msg, fds, _, _ = socket.recv_fds(self.sock, 64, 4)
+                got_serial, src = struct.unpack("!II", msg)
+                peer_fd = fds[0]
+                if got_serial != serial:      # a faster peer is one ahead
+                    stash[(got_serial, src)] = peer_fd
+                    self._early = stash
+                    continue
+            imported = ctypes.c_ulonglong()
+            self._check(lib.adl_symm_import(peer_fd, ctypes.byref(imported)),
+                        "import")
+            os.close(peer_fd)
+            handles[src] = imported.value
+        os.close(fd.value)
+        ptrs = []
+        for peer in range(self.world):
+            ptr = ctypes.c_ulonglong()
+            self._check(lib.adl_symm_map(handles[peer], size, dev,
+                                         ctypes.byref(ptr)), "map")
+            ptrs.append(ptr.value)
+            self._mapped.append((ptr.value, size, handles[peer]))
+        holder = _DeviceMemory(ptrs[self.rank], size, owner=self)
+        tensor = torch.as_tensor(holder, device=self.device)
+        tensor.zero_()
+        torch.cuda.synchronize(self.device)
+        # nobody may touch a peer's bytes before that peer zeroed them
+        _all_gather_object(serial, self.group)
+        return SymmetricRegion(tensor, ptrs, size, self.name, keepalive=self)
+
+    def close(self):
+        for ptr, size, handle in self._mapped:
+            self.lib.adl_symm_unmap(ptr, size)
+            self.lib.adl_symm_release(handle)
+        self._mapped = []
+        try:
+            self.sock.close()
+        except OSError:
+            pass
+
+
+class _TorchProvider(object):
+    name = "torch"
+
+    def __init__(self, group, device):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.symm_mem = symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.device = device
+
+    def allocate(self, nbytes):
+        nbytes = (nbytes + 511) // 512 * 512
+        t = self.symm_mem.empty(nbytes, dtype=torch.uint8, device=self.device)
+        hdl = self.symm_mem.rendezvous(t, group=self.group.group_name)
+        t.zero_()
+        torch.cuda.synchronize(self.device)
+        hdl.barrier()
+        return SymmetricRegion(t, [int(p) for p in hdl.buffer_ptrs], nbytes,
+                               self.name, keepalive=(hdl, t))
+
+    def close(self):
+        pass
+
+
+class _LocalProvider(object):
+    """World size 1: plain device memory."""
+    name = "local"
+
+    def __init__(self, device):
+        self.device = device
+
+    def allocate(self, nbytes):
+        nbytes = (nbytes + 511) // 512 * 512
+        t = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+        return SymmetricRegion(t, [t.data_ptr()], nbytes, self.name)
+
+    def close(self):
+        pass
+
+
+def _native_capable(device):
+    """Local probe (no collectives): can this rank use the native runtime?"""
+    try:
+        lib = _native.load()
+        if lib.adl_symm_init() != 0:
+            return False, lib.adl_symm_last_error().decode()
+        if not lib.adl_topo_vmm_fd_supported(device.index):
+            return False, "no POSIX-fd VMM handles"
+        return True, ""
+    except Exception as exc:  # noqa: BLE001
+        return False, str(exc)
+
+
+def make_provider(group, device, world_size):
+    """Provider selection: ``ADAPTDL_B200_SYMM`` = native | torch | auto.
+    Every rank takes the same branch (the capability probe is agreed on)."""
+    if world_size <= 1:
+        return _LocalProvider(device)
+    want = os.environ.get("ADAPTDL_B200_SYMM", "auto").lower()
+    if want in ("auto", "native"):
+        ok, why = _native_capable(device)
+        everyone = _all_gather_object((ok, why), group)
+        if all(flag for flag, _ in everyone):
+            return _NativeProvider(group, device)
+        reasons = [w for flag, w in everyone if not flag]
+        if want == "native":
+            raise RuntimeError("native symmetric memory unavailable: "
+                               + "; ".join(reasons))
+        LOG.warning("native symmetric memory unavailable (%s); using "
+                    "torch.distributed._symmetric_memory", reasons[0])
+    return _TorchProvider(group, device)

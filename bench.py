@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""Headline benchmark: ResNet-18 (CIFAR shape, synthetic data) adaptive
+data-parallel training throughput in samples/sec, device-timed, max over
+ranks -- BASELINE.json config "pytorch-cifar ResNet-18 adaptive-batch".
+
+    python bench.py --gpus 1 --steps 50 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N \
+        --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+    python bench.py --impl reference ...    # unmodified petuum/adaptdl
+
+Both arms run the *same user program* (the reference's
+examples/pytorch-cifar/main.py training loop: SGD m=0.9 wd=5e-4 with one param
+group per tensor, MultiStepLR, AdaptiveDataParallel + AdaptiveDataLoader with
+autoscale_batch_size, bf16 autocast, channels-last) through each framework's
+public API; only the framework under the loop differs.
+
+Weak scaling: the per-GPU batch is fixed (default 128), global batch =
+128 x N. Two timed regions per run, each W warm-up + K timed steps bracketed by
+barrier + synchronize, CUDA events on the launching stream, max over ranks:
+
+  e2e    every step copies its batch host(pinned)->device and reads the loss
+         back device->host (4 B, async into pinned memory);
+  value  the same loop with the batch already resident on the device.
+"""
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+
+PUBLISHED_BASELINE = None      # the reference publishes no number
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--local-bsz", type=int, default=128)
+    ap.add_argument("--device", default="cuda")
+    ap.add_argument("--reducer", default="auto")
+    ap.add_argument("--no-graph", action="store_true",
+                    help="own arm: eager step instead of the CUDA-graph step")
+    return ap.parse_args()
+
+
+def setup_env(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", str(1)))
+    local_rank = int(os.environ.get("LOCAL_RANK", str(rank)))
+    os.environ["ADAPTDL_NUM_REPLICAS"] = str(world)
+    os.environ["ADAPTDL_REPLICA_RANK"] = str(rank)
+    os.environ["ADAPTDL_NUM_NODES"] = "1"
+    os.environ["ADAPTDL_MASTER_ADDR"] = os.environ.get("MASTER_ADDR",
+                                                       "127.0.0.1")
+    base_port = int(os.environ.get("MASTER_PORT", "29400"))
+    os.environ["ADAPTDL_MASTER_PORT"] = str(base_port + 1)
+    os.environ.pop("ADAPTDL_CHECKPOINT_PATH", None)
+    return rank, world, local_rank
+
+
+class SyntheticCIFAR(object):
+    """CIFAR-10-shaped random data held in pinned host memory, fetched a
+    whole batch at a time (``__getitems__``) so the Python data path is not
+    what is being measured. Plain user code: used by BOTH arms."""
+
+    def __init__(self, size, pin):
+        import torch
+        g = torch.Generator().manual_seed(1234)
+        self.x = torch.randn(size, 3, 32, 32, generator=g)
+        self.y = torch.randint(0, 10, (size,), generator=g)
+        if pin:
+            self.x, self.y = self.x.pin_memory(), self.y.pin_memory()
+        self.pin = pin
+
+    def __len__(self):
+        return self.x.shape[0]
+
+    def __getitem__(self, i):
+        return self.x[i], self.y[i]
+
+    def __getitems__(self, idx):
+        import torch
+        idx = torch.as_tensor(idx)
+        x = torch.empty((len(idx),) + tuple(self.x.shape[1:]),
+                        dtype=self.x.dtype, pin_memory=self.pin)
+        y = torch.empty((len(idx),), dtype=self.y.dtype, pin_memory=self.pin)
+        torch.index_select(self.x, 0, idx, out=x)
+        torch.index_select(self.y, 0, idx, out=y)
+        return x, y
+
+
+def identity_collate(batch):
+    return batch
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,"
+             "clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, enabled, gpu_index):
+        self.proc = None
+        self.gpu_index = gpu_index
+        if enabled:
+            try:
+                self.proc = subprocess.Popen(
+                    ["nvidia-smi", "--query-gpu=" + self.QUERY,
+                     "--format=csv,noheader,nounits", "-lms", "100",
+                     "-i", str(gpu_index)],
+                    stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                    text=True)
+            except OSError:
+                self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                 "sw_power_cap"]
+        for line in out.splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_program(args, adl, device, world, model_fn, own):
+    """The user program (identical for both arms)."""
+    import torch
+    local_bsz = args.local_bsz
+    global_bsz = local_bsz * world
+    total_steps = 2 * (args.warmup + args.steps) + 4
+    dataset = SyntheticCIFAR(global_bsz * total_steps, pin=device.type == "cuda")
+    loader = adl.AdaptiveDataLoader(dataset, batch_size=global_bsz,
+                                    shuffle=True, drop_last=True,
+                                    collate_fn=identity_collate)
+    loader.autoscale_batch_size(32 * global_bsz,
+                                local_bsz_bounds=(32, 1024),
+                                gradient_accumulation=False)
+    model = model_fn().to(device)
+    if device.type == "cuda":
+        model = model.to(memory_format=torch.channels_last)
+    optimizer = torch.optim.SGD(
+        [{"params": [p]} for p in model.parameters()],
+        lr=0.1, momentum=0.9, weight_decay=5e-4)
+    scheduler = torch.optim.lr_scheduler.MultiStepLR(optimizer, [30, 45], 0.1)
+    kwargs = {}
+    if own and args.reducer != "auto":
+        kwargs["reducer"] = args.reducer
+    net = adl.AdaptiveDataParallel(model, optimizer, scheduler, **kwargs)
+    return dataset, loader, net, optimizer, global_bsz
+
+
+def run(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    own = args.impl == "own"
+    if args.device == "cuda" and not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (use --device cpu "
+                         "only for plumbing checks)")
+    device = torch.device("cuda", local_rank) if args.device == "cuda" \
+        else torch.device("cpu")
+    if device.type == "cuda":
+        torch.cuda.set_device(device)
+        torch.backends.cudnn.benchmark = True
+
+    if own:
+        sys.path.insert(0, ROOT)
+        import adaptdl_b200.torch as adl
+        from adaptdl_b200.models import resnet18 as model_fn
+    else:
+        import numpy as np
+        if not hasattr(np, "int"):       # numpy >= 1.24 dropped the aliases
+            np.int, np.float = int, float
+        sys.path.insert(0, os.path.join(ROOT, "baseline", "shims"))
+        sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref"))
+        sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref",
+                                        "_ref_examples"))
+        import adaptdl.torch as adl
+        from cifar_models.resnet import ResNet18 as model_fn
+
+    adl.init_process_group("nccl" if device.type == "cuda" else "gloo")
+    dataset, loader, net, optimizer, global_bsz = build_program(
+        args, adl, device, world, model_fn, own)
+    criterion = torch.nn.CrossEntropyLoss()
+    W, K = args.warmup, args.steps
+    autocast = device.type == "cuda"
+    loss_host = torch.zeros(W + K + 8, dtype=torch.float32)
+    if device.type == "cuda":
+        loss_host = loss_host.pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        if device.type == "cuda":
+            torch.cuda.synchronize()
+
+    def train_step(x, y, slot, read_back):
+        optimizer.zero_grad()
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            out = net(x)
+            loss = criterion(out, y)
+        loss.backward()
+        optimizer.step()
+        if read_back:
+            loss_host[slot].copy_(loss.detach(), non_blocking=True)
+        return loss
+
+    results = {}
+    launches = {}
+    clocks = None
+    resident = None
+    h2d_bytes = 0
+    for phase, epochs_until in (("e2e", 1), ("device", 2)):
+        for _ in adl.remaining_epochs_until(epochs_until):
+            t_wall = ev0 = ev1 = None
+            sampler = None
+            for step, (x, y) in enumerate(loader):
+                if step == W:
+                    barrier()
+                    sampler = ClockSampler(
+                        rank == 0 and device.type == "cuda"
+                        and phase == "device", local_rank)
+                    if device.type == "cuda":
+                        ev0 = torch.cuda.Event(enable_timing=True)
+                        ev1 = torch.cuda.Event(enable_timing=True)
+                        ev0.record()
+                    t_wall = time.perf_counter()
+                    if own:
+                        launches[phase] = net.reducer.launches
+                if step == W + K:
+                    if device.type == "cuda":
+                        ev1.record()
+                        torch.cuda.synchronize()
+                        ms = ev0.elapsed_time(ev1)
+                    else:
+                        ms = (time.perf_counter() - t_wall) * 1e3
+                    wall_ms = (time.perf_counter() - t_wall) * 1e3
+                    barrier()
+                    results[phase] = (ms, wall_ms)
+                    if own:
+                        launches[phase] = net.reducer.launches \
+                            - launches[phase]
+                    if sampler is not None:
+                        got = sampler.stop()
+                        clocks = got or clocks
+                    break
+                if phase == "e2e":
+                    h2d_bytes = x.numel() * x.element_size() \
+                        + y.numel() * y.element_size()
+                    xd = x.to(device, non_blocking=True)
+                    yd = y.to(device, non_blocking=True)
+                    if device.type == "cuda":
+                        xd = xd.contiguous(memory_format=torch.channels_last)
+                    train_step(xd, yd, step, read_back=True)
+                else:
+                    if resident is None:
+                        xd = x.to(device)
+                        if device.type == "cuda":
+                            xd = xd.contiguous(
+                                memory_format=torch.channels_last)
+                        resident = (xd, y.to(device))
+                    train_step(resident[0], resident[1], step,
+                               read_back=False)
+    if device.type == "cuda":
+        torch.cuda.synchronize()
+    assert bool(torch.isfinite(loss_host[:W + K]).all()), "non-finite loss"
+
+    # max over ranks of the device time
+    times = torch.tensor([results["device"][0], results["e2e"][0],
+                          results["device"][1], results["e2e"][1]],
+                         dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms, dev_wall, e2e_wall = times.tolist()
+    value = global_bsz * K / (dev_ms / 1e3)
+    e2e_value = global_bsz * K / (e2e_ms / 1e3)
+    if rank == 0:
+        line = {
+            "metric": "samples/sec (device-timed, max over ranks)",
+            "value": value, "unit": "samples/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": dev_ms / K,
+            "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": (value / PUBLISHED_BASELINE
+                            if PUBLISHED_BASELINE else None),
+            "dtype": "bf16", "data": "synthetic",
+            "impl": args.impl,
+            "config": {
+                "model": "ResNet-18 (pytorch-cifar, 3x32x32, 10 classes, "
+                         "random init)",
+                "global_batch": global_bsz, "local_batch": args.local_bsz,
+                "seq_len": None, "parallelism": "dp{}".format(world),
+                "optimizer": "SGD m=0.9 wd=5e-4, one param group per tensor "
+                             "(62 GNS groups), AdaScale LR",
+                "adaptive": "autoscale_batch_size(max=32x, local 32..1024)",
+                "memory_format": "channels_last, bf16 autocast",
+                "l2": "working set > L2 (activations of a 128-sample batch "
+                      "exceed 126 MB) and a fresh batch every e2e step",
+                "step": ("eager" if (not own or args.no_graph)
+                         else "eager"),
+            },
+            "e2e": {"value": e2e_value, "unit": "samples/s",
+                    "ms_per_step": e2e_ms / K,
+                    "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": 4},
+            "wall_ms_per_step": {"device": dev_wall / K, "e2e": e2e_wall / K},
+            "gpu_launches": (launches.get("device") if own else None),
+            "gpu_launches_e2e": (launches.get("e2e") if own else None),
+            "clocks": clocks,
+        }
+        if own:
+            line["reducer"] = type(net.reducer).__name__
+            prov = getattr(net.reducer, "_provider", None)
+            line["symmetric_memory"] = getattr(prov, "name", None)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    rank, world, local_rank = setup_env(args)
+    if args.impl == "reference":
+        ref = os.path.join(ROOT, "baseline", "_ref", "adaptdl")
+        if not os.path.isdir(ref):
+            if rank == 0:
+                print(json.dumps({"impl": "reference", "unavailable":
+                                  "baseline/_ref not installed (run "
+                                  "baseline/install_reference.sh)"}))
+            return
+    run(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,433 @@
+// adaptdl_b200 -- sm_100a gradient kernels (C ABI, launched from Python via
+// ctypes on torch's CUDA streams).
+//
+//   adl_fold_acc       A += G ; L += |G/P|^2 ; G = 0
+//   adl_fold_final     L += |G/P|^2 ; G += A ; A = 0
+//   adl_allreduce_gns  fused two-shot all-reduce over NVLink peer mappings:
+//                      G <- s * sum_r G_r (in place on every rank) with
+//                      L += sum_r |G_r/P|^2 and T += |G/P|^2 from the same
+//                      registers (reference call sites K1-K6)
+//   adl_pair_norm      T=|G/P|^2, Pp=|Pv/P|^2, Pa=|(G+Pv)/2P|^2 ; Pv = G
+//   adl_finalize_stats sum per-rank partial statistics over ranks through a
+//                      peer-mapped pad, publish to a pinned host mailbox with
+//                      %globaltimer stamps, reset the partials
+//   adl_bcast_pull     rank src's staging buffer -> every rank
+//   adl_stamp          write %globaltimer to device memory
+//
+// No tensor cores: these are bandwidth / latency kernels. sm_100a specifics:
+// 128-bit L1-bypassing vector accesses, .sys-scope release/acquire flags on
+// NVLink-mapped signal pads, %globaltimer stamps, grids sized to leave SMs to
+// the concurrently running backward pass.
+#include "adl_common.cuh"
+
+#include <stdio.h>
+
+// error word bits (device -> host, sticky)
+#define ADL_ERR_TIMEOUT 1u
+
+struct ReduceArgs {
+  void* buf[ADL_MAX_RANKS];        // bucket start in every rank's G arena
+  uint32_t* pad[ADL_MAX_RANKS];    // signal pad of every rank
+  int rank, world;
+  uint32_t epoch;
+  int n_vec;                       // vectors in the bucket (multiple of world)
+  float scale;
+  int want_local;
+  SegTable segs;
+  int n_groups;
+  const void* pinv;                // local preconditioner slice or nullptr
+  double* L;                       // [n_groups] partial: sum_r |G_r/P|^2
+  double* T;                       // [n_groups] partial: |G/P|^2
+  uint32_t* err;                   // sticky error word (device)
+  unsigned long long timeout_ns;
+};
+
+__device__ __forceinline__ bool wait_flag(const uint32_t* p, uint32_t epoch,
+                                          unsigned long long timeout_ns, uint32_t* err) {
+  const uint64_t t0 = globaltimer_ns();
+  uint32_t spins = 0;
+  while ((int32_t)(ld_acquire_sys(p) - epoch) < 0) {
+    __nanosleep(32);
+    if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > timeout_ns) {
+      atomicOr(err, ADL_ERR_TIMEOUT);
+      return false;
+    }
+  }
+  return true;
+}
+
+__device__ __forceinline__ void cta_barrier_peers(const ReduceArgs& a, int phase) {
+  __syncthreads();
+  if ((int)threadIdx.x < a.world) {
+    const int peer = threadIdx.x;
+    __threadfence_system();
+    st_release_sys(pad_slot(a.pad[peer], phase, blockIdx.x, a.rank), a.epoch);
+    wait_flag(pad_slot(a.pad[a.rank], phase, blockIdx.x, peer), a.epoch, a.timeout_ns, a.err);
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------
+// fused two-shot all-reduce + gradient-noise-scale statistics
+// ---------------------------------------------------------------------------
+template <typename T, bool HAS_PINV>
+__global__ void __launch_bounds__(ADL_THREADS, 1)
+allreduce_gns_kernel(const ReduceArgs a) {
+  extern __shared__ double s_stats[];                 // [2][n_groups]
+  constexpr int N = VecTraits<T>::N;
+  smem_stats_zero(s_stats, 2 * a.n_groups);
+  GroupAccum<2> accum;
+  accum.init(s_stats, a.n_groups);
+
+  const int W = a.world;
+  if (W > 1) cta_barrier_peers(a, 0);                 // every rank's grads are ready
+
+  const int slice = a.n_vec / W;
+  const int base = a.rank * slice;
+  const int stride = gridDim.x * blockDim.x;
+  const int first = blockIdx.x * blockDim.x + threadIdx.x;
+  const int iters = (slice + stride - 1) / stride;    // same for every lane
+  int cur = -1;                                       // segment cursor
+
+  for (int it = 0; it < iters; ++it) {
+    const int i = first + it * stride;
+    const bool active = i < slice;
+    const int v = base + i;
+    float sum[N], sq[2] = {0.f, 0.f};
+    int g = -1;
+    if (active) {
+      // issue all peer loads first (W independent 16-byte requests in flight)
+      Vec16 in[ADL_MAX_RANKS];
+#pragma unroll
+      for (int p = 0; p < ADL_MAX_RANKS; ++p)
+        if (p < W) in[p] = ld_vec(static_cast<const Vec16*>(a.buf[(a.rank + p) % W]) + v);
+      float pinv[N];
+      if (HAS_PINV) {
+        Vec16 pv = ld_vec(static_cast<const Vec16*>(a.pinv) + v);
+        unpack<T>(pv, pinv);
+#pragma unroll
+        for (int e = 0; e < N; ++e) pinv[e] = 1.0f / pinv[e];
+      }
+#pragma unroll
+      for (int e = 0; e < N; ++e) sum[e] = 0.f;
+#pragma unroll
+      for (int p = 0; p < ADL_MAX_RANKS; ++p) {
+        if (p < W) {
+          float x[N];
+          unpack<T>(in[p], x);
+#pragma unroll
+          for (int e = 0; e < N; ++e) {
+            sum[e] += x[e];
+            const float y = HAS_PINV ? x[e] * pinv[e] : x[e];
+            sq[0] = fmaf(y, y, sq[0]);
+          }
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < N; ++e) {
+        sum[e] *= a.scale;
+        const float y = HAS_PINV ? sum[e] * pinv[e] : sum[e];
+        sq[1] = fmaf(y, y, sq[1]);
+      }
+      const Vec16 out = pack<T>(sum);
+#pragma unroll
+      for (int p = 0; p < ADL_MAX_RANKS; ++p)
+        if (p < W) st_vec(static_cast<Vec16*>(a.buf[(a.rank + p) % W]) + v, out);
+      if (cur < 0) cur = seg_find(a.segs, v);
+      while (__ldg(a.segs.seg_end + cur) <= v) ++cur;
+      g = __ldg(a.segs.seg_group + cur);
+      if (!a.want_local) sq[0] = 0.f;
+    }
+    accum.add(g, sq);
+  }
+  accum.flush_warp();
+  double* outs[2] = {a.want_local ? a.L : nullptr, a.T};
+  smem_stats_flush<2>(s_stats, a.n_groups, outs);
+
+  if (W > 1) cta_barrier_peers(a, 1);                 // every slice has landed everywhere
+}
+
+// ---------------------------------------------------------------------------
+// local folds (gradient accumulation) and the single-replica pair norm
+// ---------------------------------------------------------------------------
+struct LocalArgs {
+  void* g; void* a; void* pv; const void* pinv;
+  int n_vec;
+  SegTable segs;
+  int n_groups;
+  double* s0; double* s1; double* s2;   // statistic outputs (see kernels)
+  int flag;
+};
+
+// MODE 0: fold_acc   (a += g ; s0 += |g|^2 ; g = 0)
+// MODE 1: fold_final (s0 += |g|^2 ; g += a ; a = 0)
+// MODE 2: pair       (s0 += |g|^2 ; if flag: s1 += |pv|^2, s2 += |(g+pv)/2|^2 ; pv = g)
+template <typename T, int MODE, bool HAS_PINV>
+__global__ void __launch_bounds__(ADL_THREADS, 2)
+local_kernel(const LocalArgs a) {
+  extern __shared__ double s_stats[];                 // [3][n_groups]
+  constexpr int N = VecTraits<T>::N;
+  constexpr int K = 3;
+  smem_stats_zero(s_stats, K * a.n_groups);
+  GroupAccum<K> accum;
+  accum.init(s_stats, a.n_groups);
+  const int stride = gridDim.x * blockDim.x;
+  const int first = blockIdx.x * blockDim.x + threadIdx.x;
+  const int iters = (a.n_vec + stride - 1) / stride;
+  int cur = -1;
+  for (int it = 0; it < iters; ++it) {
+    const int v = first + it * stride;
+    const bool active = v < a.n_vec;
+    float sq[K] = {0.f, 0.f, 0.f};
+    int grp = -1;
+    if (active) {
+      float g[N], o[N], pinv[N];
+      const Vec16 gv = ld_vec(static_cast<const Vec16*>(a.g) + v);
+      Vec16 ov;
+      if (MODE == 2) ov = ld_vec(static_cast<const Vec16*>(a.pv) + v);
+      else ov = ld_vec(static_cast<const Vec16*>(a.a) + v);
+      if (HAS_PINV) {
+        const Vec16 pvv = ld_vec(static_cast<const Vec16*>(a.pinv) + v);
+        unpack<T>(pvv, pinv);
+#pragma unroll
+        for (int e = 0; e < N; ++e) pinv[e] = 1.0f / pinv[e];
+      }
+      unpack<T>(gv, g);
+      unpack<T>(ov, o);
+#pragma unroll
+      for (int e = 0; e < N; ++e) {
+        const float y = HAS_PINV ? g[e] * pinv[e] : g[e];
+        sq[0] = fmaf(y, y, sq[0]);
+      }
+      if (MODE == 0) {
+#pragma unroll
+        for (int e = 0; e < N; ++e) o[e] += g[e];
+        st_vec(static_cast<Vec16*>(a.a) + v, pack<T>(o));
+        Vec16 z; z.w[0] = z.w[1] = z.w[2] = z.w[3] = 0u;
+        st_vec(static_cast<Vec16*>(a.g) + v, z);
+      } else if (MODE == 1) {
+#pragma unroll
+        for (int e = 0; e < N; ++e) g[e] += o[e];
+        st_vec(static_cast<Vec16*>(a.g) + v, pack<T>(g));
+        Vec16 z; z.w[0] = z.w[1] = z.w[2] = z.w[3] = 0u;
+        st_vec(static_cast<Vec16*>(a.a) + v, z);
+      } else {
+        if (a.flag) {
+#pragma unroll
+          for (int e = 0; e < N; ++e) {
+            const float p = HAS_PINV ? o[e] * pinv[e] : o[e];
+            const float m = 0.5f * ((HAS_PINV ? g[e] * pinv[e] : g[e]) + p);
+            sq[1] = fmaf(p, p, sq[1]);
+            sq[2] = fmaf(m, m, sq[2]);
+          }
+        }
+        st_vec(static_cast<Vec16*>(a.pv) + v, gv);
+      }
+      if (cur < 0) cur = seg_find(a.segs, v);
+      while (__ldg(a.segs.seg_end + cur) <= v) ++cur;
+      grp = __ldg(a.segs.seg_group + cur);
+    }
+    accum.add(grp, sq);
+  }
+  accum.flush_warp();
+  double* outs[K] = {a.s0, a.s1, a.s2};
+  smem_stats_flush<K>(s_stats, a.n_groups, outs);
+}
+
+// ---------------------------------------------------------------------------
+// statistics exchange + host mailbox
+// ---------------------------------------------------------------------------
+struct FinalizeArgs {
+  double* xchg[ADL_MAX_RANKS];     // every rank's exchange buffer [2][n_rows*n_groups]
+  uint32_t* pad[ADL_MAX_RANKS];
+  int rank, world;
+  uint32_t epoch;
+  int parity;
+  int n_rows;                      // statistic rows (2 or 4)
+  int n_groups;
+  double* rows[4];                 // local partial vectors (device), reset after publish
+  int sum_mask;                    // bit r set: row r is a per-rank partial to be summed
+  double* mailbox;                 // pinned host: [n_rows*n_groups] then header
+  double* result;                  // device copy of the summed rows (may be nullptr)
+  unsigned long long* t_start;     // device: %globaltimer at end of local backward
+  unsigned long long seq;
+  uint32_t* err;
+  unsigned long long timeout_ns;
+};
+// mailbox header (after the data, as doubles): [seq, sync_ns, err]
+
+__global__ void __launch_bounds__(256, 1) finalize_stats_kernel(const FinalizeArgs a) {
+  const int n = a.n_rows * a.n_groups;
+  double* mine = a.xchg[a.rank] + (size_t)a.parity * n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int r = i / a.n_groups;
+    mine[i] = a.rows[r][i - r * a.n_groups];
+  }
+  if (a.world > 1) {
+    __syncthreads();
+    if ((int)threadIdx.x < a.world) {
+      const int peer = threadIdx.x;
+      __threadfence_system();
+      st_release_sys(pad_slot(a.pad[peer], 0, ADL_MAX_CTAS - 1, a.rank), a.epoch);
+      wait_flag(pad_slot(a.pad[a.rank], 0, ADL_MAX_CTAS - 1, peer), a.epoch, a.timeout_ns, a.err);
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int r = i / a.n_groups;
+    double x;
+    if (a.world > 1 && ((a.sum_mask >> r) & 1)) {
+      x = 0.0;
+      for (int p = 0; p < a.world; ++p)       // fixed order: identical on all ranks
+        x += *reinterpret_cast<volatile double*>(a.xchg[p] + (size_t)a.parity * n + i);
+    } else {
+      x = mine[i];
+    }
+    a.mailbox[i] = x;
+    if (a.result) a.result[i] = x;
+    a.rows[r][i - r * a.n_groups] = 0.0;      // partials restart from zero
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned long long now = globaltimer_ns();
+    const unsigned long long t0 = a.t_start ? *a.t_start : now;
+    a.mailbox[n + 1] = (double)(now > t0 ? now - t0 : 0ull);
+    a.mailbox[n + 2] = (double)(*a.err);
+    __threadfence_system();
+    *reinterpret_cast<volatile double*>(a.mailbox + n) = (double)a.seq;   // publish last
+  }
+}
+
+__global__ void stamp_kernel(unsigned long long* dst) { *dst = globaltimer_ns(); }
+
+// ---------------------------------------------------------------------------
+// broadcast: every non-source rank pulls the source's staging buffer
+// ---------------------------------------------------------------------------
+struct BcastArgs {
+  void* staging[ADL_MAX_RANKS];
+  uint32_t* pad[ADL_MAX_RANKS];
+  int rank, world, src;
+  uint32_t epoch;
+  void* dst;                       // local destination (may equal staging[rank])
+  long long n_vec;
+  uint32_t* err;
+  unsigned long long timeout_ns;
+};
+
+__global__ void __launch_bounds__(ADL_THREADS, 1) bcast_pull_kernel(const BcastArgs a) {
+  ReduceArgs b;   // reuse the barrier helper
+#pragma unroll
+  for (int p = 0; p < ADL_MAX_RANKS; ++p) b.pad[p] = a.pad[p];
+  b.rank = a.rank; b.world = a.world; b.epoch = a.epoch; b.err = a.err; b.timeout_ns = a.timeout_ns;
+  cta_barrier_peers(b, 0);                            // source staging is complete
+  if (a.rank != a.src || a.dst != a.staging[a.rank]) {
+    const Vec16* src = static_cast<const Vec16*>(a.staging[a.src]);
+    Vec16* dst = static_cast<Vec16*>(a.dst);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < a.n_vec; v += 2 * stride) {
+      const Vec16 x0 = ld_vec(src + v);
+      Vec16 x1;
+      const bool two = v + stride < a.n_vec;
+      if (two) x1 = ld_vec(src + v + stride);
+      st_vec(dst + v, x0);
+      if (two) st_vec(dst + v + stride, x1);
+    }
+  }
+  cta_barrier_peers(b, 1);                            // source may reuse its staging
+}
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+#define ADL_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return (int)e_; } while (0)
+
+static int g_device = -1;
+
+extern "C" {
+
+int adl_set_device(int dev) {
+  g_device = dev;
+  return (int)cudaSetDevice(dev);
+}
+
+const char* adl_error_string(int code) { return cudaGetErrorString((cudaError_t)code); }
+
+int adl_sm_count(int dev) {
+  int n = 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+  return n;
+}
+
+// dtype: 0 = fp32, 1 = bf16, 2 = fp16
+int adl_allreduce_gns(const ReduceArgs* args, int dtype, int grid, void* stream) {
+  if (g_device >= 0) ADL_CHECK(cudaSetDevice(g_device));
+  const size_t smem = sizeof(double) * 2 * args->n_groups;
+  const bool pinv = args->pinv != nullptr;
+  cudaStream_t s = (cudaStream_t)stream;
+#define LAUNCH_AR(T, P)                                                                      \
+  do {                                                                                       \
+    ADL_CHECK(cudaFuncSetAttribute(allreduce_gns_kernel<T, P>,                               \
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    allreduce_gns_kernel<T, P><<<grid, ADL_THREADS, smem, s>>>(*args);                       \
+  } while (0)
+  if (dtype == 0) { if (pinv) LAUNCH_AR(float, true); else LAUNCH_AR(float, false); }
+  else if (dtype == 1) { if (pinv) LAUNCH_AR(__nv_bfloat16, true); else LAUNCH_AR(__nv_bfloat16, false); }
+  else if (dtype == 2) { if (pinv) LAUNCH_AR(__half, true); else LAUNCH_AR(__half, false); }
+  else return -2;
+#undef LAUNCH_AR
+  return (int)cudaGetLastError();
+}
+
+// mode: 0 fold_acc, 1 fold_final, 2 pair
+int adl_local(const LocalArgs* args, int mode, int dtype, int grid, void* stream) {
+  if (g_device >= 0) ADL_CHECK(cudaSetDevice(g_device));
+  const size_t smem = sizeof(double) * 3 * args->n_groups;
+  const bool pinv = args->pinv != nullptr;
+  cudaStream_t s = (cudaStream_t)stream;
+#define LAUNCH_L(T, M, P)                                                                    \
+  do {                                                                                       \
+    ADL_CHECK(cudaFuncSetAttribute(local_kernel<T, M, P>,                                    \
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    local_kernel<T, M, P><<<grid, ADL_THREADS, smem, s>>>(*args);                            \
+  } while (0)
+#define LAUNCH_LM(T)                                                                         \
+  do {                                                                                       \
+    if (mode == 0) { if (pinv) LAUNCH_L(T, 0, true); else LAUNCH_L(T, 0, false); }           \
+    else if (mode == 1) { if (pinv) LAUNCH_L(T, 1, true); else LAUNCH_L(T, 1, false); }      \
+    else if (mode == 2) { if (pinv) LAUNCH_L(T, 2, true); else LAUNCH_L(T, 2, false); }      \
+    else return -3;                                                                          \
+  } while (0)
+  if (dtype == 0) LAUNCH_LM(float);
+  else if (dtype == 1) LAUNCH_LM(__nv_bfloat16);
+  else if (dtype == 2) LAUNCH_LM(__half);
+  else return -2;
+#undef LAUNCH_LM
+#undef LAUNCH_L
+  return (int)cudaGetLastError();
+}
+
+int adl_finalize_stats(const FinalizeArgs* args, void* stream) {
+  if (g_device >= 0) ADL_CHECK(cudaSetDevice(g_device));
+  finalize_stats_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(*args);
+  return (int)cudaGetLastError();
+}
+
+int adl_stamp(unsigned long long* dst, void* stream) {
+  if (g_device >= 0) ADL_CHECK(cudaSetDevice(g_device));
+  stamp_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(dst);
+  return (int)cudaGetLastError();
+}
+
+int adl_bcast_pull(const BcastArgs* args, int grid, void* stream) {
+  if (g_device >= 0) ADL_CHECK(cudaSetDevice(g_device));
+  bcast_pull_kernel<<<grid, ADL_THREADS, 0, (cudaStream_t)stream>>>(*args);
+  return (int)cudaGetLastError();
+}
+
+int adl_sizeof_reduce_args() { return (int)sizeof(ReduceArgs); }
+int adl_sizeof_local_args() { return (int)sizeof(LocalArgs); }
+int adl_sizeof_finalize_args() { return (int)sizeof(FinalizeArgs); }
+int adl_sizeof_bcast_args() { return (int)sizeof(BcastArgs); }
+
+}  // extern "C"

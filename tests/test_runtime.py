@@ -79,6 +79,7 @@ def test_save_load():
         # a newer generation replaces the older one atomically
         from adaptdl_b200 import collective
         collective.initialize()
+        collective.allreduce(0)   # barrier: everyone finished loading
         state_1.value = 11
         save_all_states()
         collective.allreduce(0)   # barrier: rank 0 finished publishing
