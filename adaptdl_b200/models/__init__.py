@@ -4,3 +4,9 @@ framework's own kernels are on the gradient path)."""
 
 from .resnet import (resnet18, resnet34, resnet50, resnet101,  # noqa: F401
                      resnet152, ResNet)
+from .bert import (BertModel, MLMTask, NextSentenceTask,  # noqa: F401
+                   QuestionAnswerTask, bert_base_mlm)
+from .transformer_lm import TransformerModel  # noqa: F401
+from .ncf import NCF  # noqa: F401
+from .dcgan import Generator, Discriminator  # noqa: F401
+from .simple import LinearRegression, MnistNet  # noqa: F401

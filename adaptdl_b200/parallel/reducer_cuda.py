@@ -265,7 +265,6 @@ class CudaGradReducer(GradReducer):
                               (slice_vec + 511) // 512))
         else:
             grid = self._local_grid(n_vec)
-            grid = min(grid, MAX_CTAS - 1) if False else grid
         self._order_after_compute()
         check(self._lib.adl_allreduce_gns(
             ctypes.byref(args), _DTYPE_CODE[arena.dtype], grid,

@@ -167,6 +167,10 @@ class _TorchProvider(object):
 
     def allocate(self, nbytes):
         nbytes = (nbytes + 511) // 512 * 512
+        try:
+            self.symm_mem.enable_symm_mem_for_group(self.group.group_name)
+        except Exception:  # noqa: BLE001 - not needed on newer torch
+            pass
         t = self.symm_mem.empty(nbytes, dtype=torch.uint8, device=self.device)
         hdl = self.symm_mem.rendezvous(t, group=self.group.group_name)
         t.zero_()

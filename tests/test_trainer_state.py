@@ -318,3 +318,30 @@ def test_profile_accumulation_and_fit():
     assert state.perf_params is not None and state.grad_params == (0.5, 0.25)
     assert state.local_bsz_bounds == (2, 8) and state.gradient_accumulation
     return 0
+
+
+@elastic_multiprocessing
+def test_bptt_iterator():
+    """500 tokens, bsz 10, bptt 5: one (5x10) batch at 1 replica, restart,
+    then (5x5) windows on 2 replicas until the stream is consumed."""
+    from adaptdl_b200 import checkpoint, collective, env
+    from adaptdl_b200.torch.iterator import AdaptiveBPTTIterator
+    collective.initialize()
+    tokens = torch.arange(500)
+    it = AdaptiveBPTTIterator(tokens, batch_size=10, bptt_len=5)
+    seen = 0
+    for idx, batch in enumerate(it):
+        if env.num_restarts() == 0 and idx == 1:
+            assert batch.text.shape == (5, 10)
+            assert torch.equal(batch.target[:-1], batch.text[1:])
+            checkpoint.save_all_states()
+            return 2
+        if env.num_replicas() == 2:
+            assert batch.text.shape in ((5, 5), (4, 5))
+            assert torch.equal(batch.target[:-1], batch.text[1:])
+        seen += 1
+    if env.num_replicas() == 2:
+        # fold is 100 rows x 5 cols; resumed at row ceil(5*100/50)=10;
+        # rows 10..98 in windows of 5 shared by 2 replicas -> 9 steps each
+        assert idx == 8 and seen == 9
+    return 0
