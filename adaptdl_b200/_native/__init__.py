@@ -106,7 +106,8 @@ class ReduceArgs(ctypes.Structure):
         ("buf", ctypes.c_void_p * MAX_RANKS),
         ("pad", ctypes.c_void_p * MAX_RANKS),
         ("rank", ctypes.c_int), ("world", ctypes.c_int),
-        ("epoch", ctypes.c_uint32),
+        ("step_ctr", ctypes.c_void_p),
+        ("site", ctypes.c_uint32),
         ("n_vec", ctypes.c_int),
         ("scale", ctypes.c_float),
         ("want_local", ctypes.c_int),
@@ -129,6 +130,7 @@ class LocalArgs(ctypes.Structure):
         ("s0", ctypes.c_void_p), ("s1", ctypes.c_void_p),
         ("s2", ctypes.c_void_p),
         ("flag", ctypes.c_int),
+        ("flag_ptr", ctypes.c_void_p),
     ]
 
 
@@ -137,16 +139,23 @@ class FinalizeArgs(ctypes.Structure):
         ("xchg", ctypes.c_void_p * MAX_RANKS),
         ("pad", ctypes.c_void_p * MAX_RANKS),
         ("rank", ctypes.c_int), ("world", ctypes.c_int),
-        ("epoch", ctypes.c_uint32),
-        ("parity", ctypes.c_int),
+        ("step_ctr", ctypes.c_void_p),
+        ("site", ctypes.c_uint32),
         ("n_rows", ctypes.c_int),
         ("n_groups", ctypes.c_int),
         ("rows", ctypes.c_void_p * 4),
         ("sum_mask", ctypes.c_int),
+        ("micro_steps", ctypes.c_int),
+        ("pair_mode", ctypes.c_int),
+        ("pair_flag", ctypes.c_int),
+        ("pair_state", ctypes.c_void_p),
         ("mailbox", ctypes.c_void_p),
+        ("ring", ctypes.c_int), ("slot_doubles", ctypes.c_int),
         ("result", ctypes.c_void_p),
         ("t_start", ctypes.c_void_p),
-        ("seq", ctypes.c_ulonglong),
+        ("gns_state", ctypes.c_void_p),
+        ("gns_ctrl", ctypes.c_void_p),
+        ("lr_factor", ctypes.c_void_p),
         ("err", ctypes.c_void_p),
         ("timeout_ns", ctypes.c_ulonglong),
     ]
@@ -158,12 +167,39 @@ class BcastArgs(ctypes.Structure):
         ("pad", ctypes.c_void_p * MAX_RANKS),
         ("rank", ctypes.c_int), ("world", ctypes.c_int),
         ("src", ctypes.c_int),
-        ("epoch", ctypes.c_uint32),
+        ("step_ctr", ctypes.c_void_p),
+        ("site", ctypes.c_uint32),
         ("dst", ctypes.c_void_p),
         ("n_vec", ctypes.c_longlong),
         ("err", ctypes.c_void_p),
         ("timeout_ns", ctypes.c_ulonglong),
     ]
+
+
+class OptimArgs(ctypes.Structure):
+    _fields_ = [
+        ("grad", ctypes.c_void_p),
+        ("state0", ctypes.c_void_p), ("state1", ctypes.c_void_p),
+        ("param_ptr", ctypes.c_void_p),
+        ("seg_start", ctypes.c_void_p), ("seg_numel", ctypes.c_void_p),
+        ("segs", SegTable),
+        ("n_vec", ctypes.c_int),
+        ("hyper", ctypes.c_void_p),
+        ("lr_factor", ctypes.c_void_p),
+        ("step_ctr", ctypes.c_void_p),
+        ("step_offset", ctypes.c_void_p),
+        ("n_groups", ctypes.c_int),
+    ]
+
+
+MBOX_HDR = 8
+SITES_PER_STEP = 1024
+HYPER_STRIDE = 8
+(RULE_ADASCALE, RULE_ADAMSCALE, RULE_LINEAR, RULE_SQRT, RULE_LEGW) = range(5)
+(CTL_ACCUM_SCALE, CTL_SMOOTHING, CTL_RULE, CTL_RULE_ARG, CTL_ENABLED) = \
+    range(5)
+GNS_TAIL = 8
+(GNS_SQR_UNBIAS, GNS_VAR_UNBIAS, GNS_PROGRESS, GNS_BIASED) = range(4)
 
 
 def _declare(lib):
@@ -203,7 +239,10 @@ def _declare(lib):
                                   c.POINTER(c.c_int)]
     lib.adl_mc_add_device.argtypes = [c.c_ulonglong, c.c_int]
     lib.adl_mc_bind.argtypes = [c.c_ulonglong, c.c_ulonglong, c.c_size_t]
-    for name, struct in (("adl_sizeof_reduce_args", ReduceArgs),
+    lib.adl_fused_optim.argtypes = [c.POINTER(OptimArgs), c.c_int, c.c_int,
+                                    c.c_int, c.c_void_p]
+    for name, struct in (("adl_sizeof_optim_args", OptimArgs),
+                         ("adl_sizeof_reduce_args", ReduceArgs),
                          ("adl_sizeof_local_args", LocalArgs),
                          ("adl_sizeof_finalize_args", FinalizeArgs),
                          ("adl_sizeof_bcast_args", BcastArgs)):
@@ -212,8 +251,6 @@ def _declare(lib):
             raise RuntimeError(
                 "ABI mismatch for {}: C {} vs ctypes {}".format(
                     struct.__name__, got, c.sizeof(struct)))
-    if hasattr(lib, "adl_optim_declare"):
-        pass
     return lib
 
 
@@ -229,8 +266,6 @@ def load(build_if_needed=True):
         raise RuntimeError("native library missing: " + LIB_PATH)
     lib = ctypes.CDLL(LIB_PATH)
     _lib = _declare(lib)
-    from adaptdl_b200._native import optim_abi
-    optim_abi.declare(_lib)
     return _lib
 
 

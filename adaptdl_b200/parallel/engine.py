@@ -1,0 +1,356 @@
+"""Device-resident training-step engine.
+
+With the engine enabled, nothing in an optimizer step needs the host:
+
+* the gradient-noise-scale **estimator** (EMA state, AdaScale gain,
+  per-group LR factors, scale-invariant progress) runs inside
+  ``adl_finalize_stats`` on the device, right after the last bucket's fused
+  all-reduce;
+* the **optimizer** is one fused kernel per gradient arena
+  (``adl_fused_optim``: SGD-momentum / Adam / AdamW) that multiplies each
+  group's learning rate by the factor the estimator just wrote to device
+  memory;
+* the host sees the statistics through a pinned **mailbox ring**, consumed
+  with a fixed lag (deterministic and identical on every replica), so there
+  is no ``.item()`` / event synchronisation on the step path -- and the whole
+  step can be captured in a CUDA graph (:mod:`adaptdl_b200.parallel.graph`).
+
+The reference computes the same quantities on the host from numpy state
+(``torch/scaling_rules.py:64-125``, ``torch/gradient_noise_scale.py:212-273``)
+and pays two device synchronisations per step for it.
+"""
+
+import ctypes
+import os
+
+import numpy as np
+import torch
+
+from adaptdl_b200 import _native
+from adaptdl_b200._native import (
+    OptimArgs, HYPER_STRIDE, MBOX_HDR, GNS_TAIL, GNS_SQR_UNBIAS,
+    GNS_VAR_UNBIAS, GNS_PROGRESS, GNS_BIASED, CTL_ACCUM_SCALE, CTL_SMOOTHING,
+    CTL_RULE, CTL_RULE_ARG, CTL_ENABLED, RULE_ADASCALE, RULE_ADAMSCALE,
+    RULE_LINEAR, RULE_SQRT, RULE_LEGW, check)
+from adaptdl_b200.parallel import layout
+
+_DTYPE_CODE = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
+
+
+def stats_lag():
+    """How many optimizer steps the host mirror trails the device by."""
+    return max(0, int(os.environ.get("ADAPTDL_B200_STATS_LAG", "1")))
+
+
+def _rule_code(rule):
+    from adaptdl_b200.torch import scaling_rules as sr
+    table = {sr.AdaScale: RULE_ADASCALE, sr.AdamScale: RULE_ADAMSCALE,
+             sr.LinearScale: RULE_LINEAR, sr.SqrtScale: RULE_SQRT,
+             sr.LEGWScale: RULE_LEGW}
+    return table.get(type(rule))
+
+
+def supported_optimizer(optimizer):
+    """'sgd' / 'adam' / None (exact torch classes with options the fused
+    kernel reproduces bit-for-bit in exact arithmetic)."""
+    kind = type(optimizer)
+    if kind is torch.optim.SGD:
+        for g in optimizer.param_groups:
+            if g.get("dampening", 0) != 0 or g.get("maximize", False):
+                return None
+        return "sgd"
+    if kind in (torch.optim.Adam, torch.optim.AdamW):
+        for g in optimizer.param_groups:
+            if g.get("amsgrad", False) or g.get("maximize", False):
+                return None
+            if torch.is_tensor(g.get("lr")):
+                return None
+        return "adam"
+    return None
+
+
+class DeviceEngine(object):
+
+    def __init__(self, reducer, optimizer, rule, gns_state):
+        self.reducer = reducer
+        self.optimizer = optimizer
+        self.rule = rule
+        self.kind = supported_optimizer(optimizer)
+        self.rule_code = _rule_code(rule)
+        if self.kind is None or self.rule_code is None:
+            raise ValueError("optimizer / scaling rule not supported by the "
+                             "device engine")
+        self._lib = _native.load()
+        dev = reducer.device
+        G = reducer.num_groups
+        self.num_groups = G
+        self.enabled = True
+        self.state = torch.zeros(4 * G + GNS_TAIL, dtype=torch.float64,
+                                 device=dev)
+        self.ctrl = torch.zeros(8, dtype=torch.float64, device=dev)
+        self._ctrl_host = torch.zeros(8, dtype=torch.float64).pin_memory()
+        self._ctrl_last = None
+        self.lr_factor = torch.ones(G + 1, dtype=torch.float32, device=dev)
+        self.hyper = torch.zeros(G, HYPER_STRIDE, dtype=torch.float32,
+                                 device=dev)
+        self._hyper_host = torch.zeros(G, HYPER_STRIDE,
+                                       dtype=torch.float32).pin_memory()
+        self._hyper_last = None
+        self.opt_steps = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._one_i32 = torch.ones(1, dtype=torch.int32, device=dev)
+        self._opt_steps_host = 0
+        self._consumed = -1          # last optimizer step mirrored on host
+        self._tables = []
+        for arena in reducer.arenas:
+            self._tables.append(self._build_tables(arena))
+        self.push_gns_state(gns_state)
+        reducer.engine = self
+
+    # ------------------------------------------------------------------
+    # layout tables + optimizer state arenas
+    # ------------------------------------------------------------------
+
+    def _build_tables(self, arena):
+        dev = self.reducer.device
+        itemsize = torch.empty((), dtype=arena.dtype).element_size()
+        vec = layout.VEC_BYTES // itemsize
+        segs = sorted((seg for b in arena.buckets for seg in b.segments),
+                      key=lambda s: s.start)
+        n_vec = max(arena.total, 1) // vec
+        ends = []
+        for j, seg in enumerate(segs):
+            nxt = segs[j + 1].start // vec if j + 1 < len(segs) else n_vec
+            ends.append(nxt)
+        params = [arena.params[seg.param_index] for seg in segs]
+        for p in params:
+            if not (p.is_contiguous() or _dense(p)):
+                raise ValueError("parameter with a non-dense layout")
+        t = {
+            "segs": segs, "params": params, "n_vec": n_vec,
+            "seg_end": torch.tensor(ends, dtype=torch.int32, device=dev),
+            "seg_group": torch.tensor([s.group for s in segs],
+                                      dtype=torch.int32, device=dev),
+            "seg_start": torch.tensor([s.start for s in segs],
+                                      dtype=torch.int32, device=dev),
+            "seg_numel": torch.tensor([s.length for s in segs],
+                                      dtype=torch.int32, device=dev),
+            "param_ptr": torch.tensor([p.data_ptr() for p in params],
+                                      dtype=torch.int64, device=dev),
+            "state0": None, "state1": None,
+        }
+        needs0 = self.kind == "adam" or any(
+            g.get("momentum", 0) != 0 for g in self.optimizer.param_groups)
+        if needs0:
+            t["state0"] = torch.zeros(max(arena.total, 1), dtype=arena.dtype,
+                                      device=dev)
+        if self.kind == "adam":
+            t["state1"] = torch.zeros(max(arena.total, 1), dtype=arena.dtype,
+                                      device=dev)
+        return t
+
+    def _state_views(self, table, key):
+        flat = table[key]
+        out = []
+        for seg, p in zip(table["segs"], table["params"]):
+            piece = flat[seg.start:seg.start + seg.length]
+            out.append(piece.as_strided(p.shape, p.stride())
+                       if not p.is_contiguous() else piece.view(p.shape))
+        return out
+
+    def adopt_optimizer_state(self):
+        """Move whatever state the torch optimizer holds (fresh, or just
+        loaded from a checkpoint) into the flat arenas and expose views of
+        the arenas as ``optimizer.state[p][...]``."""
+        opt = self.optimizer
+        names = ("momentum_buffer", None) if self.kind == "sgd" \
+            else ("exp_avg", "exp_avg_sq")
+        loaded_step = None
+        for table in self._tables:
+            views0 = self._state_views(table, "state0") \
+                if table["state0"] is not None else None
+            views1 = self._state_views(table, "state1") \
+                if table["state1"] is not None else None
+            for i, p in enumerate(table["params"]):
+                st = opt.state.get(p, None)
+                if st is None:
+                    st = {}
+                    opt.state[p] = st
+                for views, name in ((views0, names[0]), (views1, names[1])):
+                    if views is None or name is None:
+                        continue
+                    old = st.get(name)
+                    if old is not None and old.data_ptr() != \
+                            views[i].data_ptr():
+                        views[i].copy_(old)
+                    st[name] = views[i]
+                if self.kind == "adam":
+                    step = st.get("step")
+                    if step is not None:
+                        loaded_step = int(float(step))
+                    else:
+                        st["step"] = torch.tensor(0.0)
+        if self.kind == "adam" and loaded_step is not None:
+            self.opt_steps.fill_(loaded_step)
+            self._opt_steps_host = loaded_step
+
+    def refresh_param_pointers(self):
+        for table in self._tables:
+            ptrs = [p.data_ptr() for p in table["params"]]
+            table["param_ptr"].copy_(torch.tensor(ptrs, dtype=torch.int64))
+
+    # ------------------------------------------------------------------
+    # estimator state <-> host
+    # ------------------------------------------------------------------
+
+    def push_gns_state(self, gns):
+        """Host dict (``optimizer.state['gns']``) -> device."""
+        G = self.num_groups
+        host = np.zeros(4 * G + GNS_TAIL)
+        sqr_unbias = float(gns.get("sqr_avg_unbias", 0.0))
+        var_unbias = float(gns.get("var_avg_unbias", 0.0))
+        host[0:G] = np.broadcast_to(gns.get("sqr_avg_biased", 0.0), (G,))
+        host[G:2 * G] = np.broadcast_to(gns.get("var_avg_biased", 0.0), (G,))
+        host[2 * G:3 * G] = np.broadcast_to(gns["sqr_avg"], (G,))
+        host[3 * G:4 * G] = np.broadcast_to(gns["var_avg"], (G,))
+        host[4 * G + GNS_SQR_UNBIAS] = sqr_unbias
+        host[4 * G + GNS_VAR_UNBIAS] = var_unbias
+        host[4 * G + GNS_PROGRESS] = float(gns.get("progress", 0.0))
+        host[4 * G + GNS_BIASED] = 1.0 if gns.get("biased", False) else 0.0
+        self.state.copy_(torch.from_numpy(host))
+
+    def pull_gns_state(self, gns):
+        """Device -> host dict (synchronises; used for checkpoints)."""
+        G = self.num_groups
+        host = self.state.cpu().numpy()
+        gns["sqr_avg_biased"] = host[0:G].copy()
+        gns["var_avg_biased"] = host[G:2 * G].copy()
+        gns["sqr_avg"] = host[2 * G:3 * G].copy()
+        gns["var_avg"] = host[3 * G:4 * G].copy()
+        gns["sqr_avg_unbias"] = float(host[4 * G + GNS_SQR_UNBIAS])
+        gns["var_avg_unbias"] = float(host[4 * G + GNS_VAR_UNBIAS])
+        gns["progress"] = float(host[4 * G + GNS_PROGRESS])
+        gns["biased"] = bool(host[4 * G + GNS_BIASED])
+        if self.kind == "adam":
+            steps = int(self.opt_steps.item())
+            for table in self._tables:
+                for p in table["params"]:
+                    self.optimizer.state[p]["step"] = torch.tensor(
+                        float(steps))
+
+    def set_progress(self, progress):
+        G = self.num_groups
+        self.state[4 * G + GNS_PROGRESS] = float(progress)
+
+    # ------------------------------------------------------------------
+    # host -> device control (only copies when something changed)
+    # ------------------------------------------------------------------
+
+    def sync_ctrl(self, accum_scale, smoothing, legw_unit=0.0):
+        vals = (float(accum_scale), float(smoothing), float(self.rule_code),
+                float(legw_unit), 1.0 if self.enabled else 0.0)
+        if vals == self._ctrl_last:
+            return
+        self._ctrl_last = vals
+        # a fresh pinned staging buffer per change (changes are rare): the
+        # previous async copy may not have executed yet
+        h = self._ctrl_host = torch.zeros(8, dtype=torch.float64).pin_memory()
+        h[CTL_ACCUM_SCALE], h[CTL_SMOOTHING] = vals[0], vals[1]
+        h[CTL_RULE], h[CTL_RULE_ARG], h[CTL_ENABLED] = vals[2], vals[3], \
+            vals[4]
+        self.ctrl.copy_(h, non_blocking=True)
+
+    def sync_hyper(self):
+        rows = []
+        for g in self.optimizer.param_groups:
+            if self.kind == "sgd":
+                rows.append((float(g["lr"]), float(g.get("momentum", 0)),
+                             float(g.get("weight_decay", 0)),
+                             1.0 if g.get("nesterov", False) else 0.0,
+                             0.0, 0.0, 0.0, 0.0))
+            else:
+                b1, b2 = g["betas"]
+                adamw = type(self.optimizer) is torch.optim.AdamW or \
+                    g.get("decoupled_weight_decay", False)
+                rows.append((float(g["lr"]), float(b1),
+                             float(g.get("weight_decay", 0)),
+                             1.0 if adamw else 0.0, float(b2),
+                             float(g["eps"]), 0.0, 0.0))
+        rows = tuple(rows)
+        if rows == self._hyper_last:
+            return
+        self._hyper_last = rows
+        self._hyper_host = torch.tensor(rows, dtype=torch.float32) \
+            .pin_memory()
+        self.hyper.copy_(self._hyper_host, non_blocking=True)
+
+    # ------------------------------------------------------------------
+    # the fused optimizer step
+    # ------------------------------------------------------------------
+
+    def optimizer_step(self):
+        self.sync_hyper()
+        red = self.reducer
+        stream = torch.cuda.current_stream(red.device).cuda_stream
+        for arena, table in zip(red.arenas, self._tables):
+            args = OptimArgs()
+            args.grad = arena.grad.data_ptr()
+            args.state0 = table["state0"].data_ptr() \
+                if table["state0"] is not None else None
+            args.state1 = table["state1"].data_ptr() \
+                if table["state1"] is not None else None
+            args.param_ptr = table["param_ptr"].data_ptr()
+            args.seg_start = table["seg_start"].data_ptr()
+            args.seg_numel = table["seg_numel"].data_ptr()
+            args.segs.seg_end = table["seg_end"].data_ptr()
+            args.segs.seg_group = table["seg_group"].data_ptr()
+            args.segs.n_seg = table["seg_end"].numel()
+            args.n_vec = table["n_vec"]
+            args.hyper = self.hyper.data_ptr()
+            args.lr_factor = self.lr_factor.data_ptr()
+            # adam step = opt_steps (device) + 1, via step_ctr/step_offset
+            args.step_ctr = self.opt_steps.data_ptr()
+            args.step_offset = self._one().data_ptr()
+            args.n_groups = self.num_groups
+            grid = max(1, min(2 * red._sm_count,
+                              (table["n_vec"] + 2 * 512 - 1) // (2 * 512)))
+            check(self._lib.adl_fused_optim(
+                ctypes.byref(args), 1 if self.kind == "adam" else 0,
+                _DTYPE_CODE[arena.dtype], grid, stream), "adl_fused_optim")
+            red.launches += 1
+        if self.kind == "adam":
+            self.opt_steps.add_(self._one())
+        self._opt_steps_host += 1
+        self.optimizer._opt_called = True    # keep LR schedulers quiet
+
+    def _one(self):
+        return self._one_i32
+
+    # ------------------------------------------------------------------
+    # host mirror of the device statistics
+    # ------------------------------------------------------------------
+
+    def mirror(self, gns_dict, force_latest=False):
+        """Fold the newest mailbox slot the lag policy allows into the host
+        dict. Returns the slot header (numpy) or ``None`` if nothing new."""
+        red = self.reducer
+        latest = red._steps - 1
+        target = latest if force_latest else latest - stats_lag()
+        if target < 0 or target <= self._consumed:
+            return None
+        arr = red.read_slot(target)
+        self._consumed = target
+        if int(arr[5]) != 0:
+            raise RuntimeError("fused all-reduce timed out waiting for a "
+                               "peer (error word {})".format(int(arr[5])))
+        G = self.num_groups
+        gns_dict["sqr_avg"] = np.array(arr[MBOX_HDR:MBOX_HDR + G])
+        gns_dict["var_avg"] = np.array(arr[MBOX_HDR + G:MBOX_HDR + 2 * G])
+        gns_dict["progress"] = float(arr[3])
+        return np.array(arr[:MBOX_HDR])
+
+
+def _dense(p):
+    try:
+        return torch.empty_like(p).stride() == p.stride()
+    except RuntimeError:
+        return False

@@ -162,8 +162,15 @@ class GradReducer(object):
             for b in arena.buckets:
                 for seg in b.segments:
                     p = arena.params[seg.param_index]
-                    view = arena.grad[seg.start:seg.start + seg.length] \
-                        .view(p.shape)
+                    piece = arena.grad[seg.start:seg.start + seg.length]
+                    if p.is_contiguous() or not _is_dense(p):
+                        view = piece.view(p.shape)
+                    else:
+                        # dense permuted layout (channels_last): give .grad
+                        # the parameter's strides so autograd's accumulation
+                        # and the optimizer run on matching layouts; the
+                        # kernels only ever see the flat bytes.
+                        view = piece.as_strided(p.shape, p.stride())
                     arena.views[seg.param_index] = view
                     if p.grad is not None:
                         view.copy_(p.grad)
@@ -346,6 +353,13 @@ class GradReducer(object):
     def broadcast_parameters(self, tensors, src=0):
         """Broadcast ``tensors`` (params/buffers) from ``src`` in place."""
         raise NotImplementedError
+
+
+def _is_dense(p):
+    try:
+        return torch.empty_like(p).stride() == p.stride()
+    except RuntimeError:
+        return False
 
 
 def count_of(reducer):

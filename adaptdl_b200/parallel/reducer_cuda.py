@@ -25,7 +25,8 @@ import torch.distributed as dist
 
 from adaptdl_b200 import _native
 from adaptdl_b200._native import (ReduceArgs, LocalArgs, FinalizeArgs,
-                                  BcastArgs, MAX_RANKS, MAX_CTAS, check)
+                                  BcastArgs, MAX_RANKS, MAX_CTAS, MBOX_HDR,
+                                  SITES_PER_STEP, check)
 from adaptdl_b200.parallel import layout, symm
 from adaptdl_b200.parallel.reducer_base import GradReducer, GradStats
 
@@ -51,8 +52,9 @@ class CudaGradReducer(GradReducer):
                              .format(MAX_RANKS))
         self._region = None
         self._provider = None
-        self._epoch = 0
-        self._seq = 0
+        self._site = 0          # launch ordinal within the current step
+        self._steps = 0         # finalize launches so far (== device step_ctr)
+        self.engine = None      # DeviceEngine (device-resident estimator)
         self._seg = {}
         self._had_pair = False
         self._pending_events = None
@@ -76,6 +78,10 @@ class CudaGradReducer(GradReducer):
         torch.cuda.set_device(dev)
         check(self._lib.adl_set_device(dev.index), "adl_set_device")
         G = self.num_groups
+        if G > self._lib.adl_max_groups():
+            raise ValueError("too many param groups for the fused "
+                             "statistics kernels ({} > {})".format(
+                                 G, self._lib.adl_max_groups()))
         self._xchg_bytes = _round_up(2 * 4 * G * 8, _ALIGN)
         offsets, cursor = {}, 0
         offsets["pad"] = cursor
@@ -113,8 +119,12 @@ class CudaGradReducer(GradReducer):
         self._result = torch.zeros(4, G, dtype=torch.float64, device=dev)
         self._err = torch.zeros(1, dtype=torch.int32, device=dev)
         self._t_start = torch.zeros(1, dtype=torch.int64, device=dev)
-        self._mailboxes = [torch.zeros(4 * G + 4, dtype=torch.float64)
-                           .pin_memory() for _ in range(2)]
+        self._step_ctr = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._pair_state = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._ring = 8
+        self._slot = MBOX_HDR + 4 * G
+        self._mailbox = torch.zeros(self._ring * self._slot,
+                                    dtype=torch.float64).pin_memory()
         self._comm = torch.cuda.Stream(dev, priority=-1)
         self._sm_count = max(self._lib.adl_sm_count(dev.index), 1)
         self._reduce_ctas = int(os.environ.get(
@@ -217,6 +227,8 @@ class CudaGradReducer(GradReducer):
         args.s1 = self._row(2)
         args.s2 = self._row(3)
         args.flag = flag
+        if mode == 2 and self.engine is not None and self.engine.enabled:
+            args.flag_ptr = self._pair_state.data_ptr()
         self._order_after_compute()
         check(self._lib.adl_local(
             ctypes.byref(args), mode, _DTYPE_CODE[arena.dtype],
@@ -243,8 +255,8 @@ class CudaGradReducer(GradReducer):
             args.buf[p] = self._grad_ptrs[ai][p] + off
             args.pad[p] = self._pad_ptrs[p]
         args.rank, args.world = self.rank, self.world_size
-        self._epoch += 1
-        args.epoch = self._epoch & 0xFFFFFFFF
+        args.step_ctr = self._step_ctr.data_ptr()
+        args.site = self._next_site()
         args.n_vec = n_vec
         args.scale = scale
         args.want_local = int(want_local)
@@ -271,31 +283,47 @@ class CudaGradReducer(GradReducer):
             self._comm.cuda_stream), "adl_allreduce_gns")
         self.launches += 1
 
+    def _next_site(self):
+        self._site += 1
+        if self._site >= SITES_PER_STEP:
+            raise RuntimeError("too many fused launches in one step")
+        return self._site
+
     def _finalize_step(self):
         pair_mode = self.world_size == 1 and self._k_before == 0
+        engine = self.engine if (self.engine is not None
+                                 and self.engine.enabled) else None
+        if engine is not None:
+            n_rows = 4 if pair_mode else 2
+        else:
+            n_rows = 4 if (pair_mode and self._had_pair) else 2
         if pair_mode:
             self._prev_valid = True
-        n_rows = 4 if (pair_mode and self._had_pair) else 2
         G = self.num_groups
         args = FinalizeArgs()
         for p in range(self.world_size):
             args.xchg[p] = self._xchg_ptrs[p]
             args.pad[p] = self._pad_ptrs[p]
         args.rank, args.world = self.rank, self.world_size
-        self._epoch += 1
-        args.epoch = self._epoch & 0xFFFFFFFF
-        self._seq += 1
-        args.parity = self._seq & 1
+        args.step_ctr = self._step_ctr.data_ptr()
+        args.site = self._next_site()
         args.n_rows = n_rows
         args.n_groups = G
         for r in range(4):
             args.rows[r] = self._row(r)
         args.sum_mask = 0b0011 if self.world_size > 1 else 0
-        mailbox = self._mailboxes[self._seq & 1]
-        args.mailbox = mailbox.data_ptr()
+        args.micro_steps = self._accum_count
+        args.pair_mode = int(pair_mode)
+        args.pair_flag = int(self._had_pair)
+        args.pair_state = self._pair_state.data_ptr()
+        args.mailbox = self._mailbox.data_ptr()
+        args.ring, args.slot_doubles = self._ring, self._slot
         args.result = self._result.data_ptr()
         args.t_start = self._t_start.data_ptr()
-        args.seq = self._seq
+        if engine is not None:
+            args.gns_state = engine.state.data_ptr()
+            args.gns_ctrl = engine.ctrl.data_ptr()
+            args.lr_factor = engine.lr_factor.data_ptr()
         args.err = self._err.data_ptr()
         args.timeout_ns = _TIMEOUT_NS
         self._order_after_compute()
@@ -308,25 +336,64 @@ class CudaGradReducer(GradReducer):
         # the optimizer (compute stream) must see the reduced gradients
         torch.cuda.current_stream(self.device).wait_event(done)
         count = self.world_size * self._accum_count
-        return (mailbox, done, count, n_rows, self._seq)
+        handle = self.note_step_finalized(done, count, n_rows)
+        return handle
+
+    def note_step_finalized(self, done, count, n_rows):
+        """Host bookkeeping for one finalize launch (also used when a
+        captured CUDA graph containing the launch is replayed)."""
+        step = self._steps
+        self._steps += 1
+        self._site = 0
+        return (step, done, count, n_rows)
+
+    def replay_bookkeeping(self, sync, k_before):
+        """Host state after a captured step (one backward pass) has been
+        replayed: mirrors what the autograd hooks record in eager mode."""
+        self._sync = bool(sync)
+        self._k_before = int(k_before)
+        self._accum_count = self._k_before + 1
+        if sync:
+            pair_mode = self.world_size == 1 and self._k_before == 0
+            self._stats_ready = self.note_step_finalized(
+                None, self.world_size * self._accum_count,
+                4 if pair_mode else 2)
+
+    def read_slot(self, step, wait_event=None, spin=True):
+        """Mailbox slot of optimizer step ``step`` (0-based) as a numpy
+        view; waits until the device has published it."""
+        if wait_event is not None:
+            wait_event.synchronize()
+        lo = (step % self._ring) * self._slot
+        arr = self._mailbox.numpy()[lo:lo + self._slot]
+        if spin:
+            import time
+            t0 = time.time()
+            while int(arr[0]) != step + 1:
+                if int(arr[0]) > step + 1:
+                    raise RuntimeError(
+                        "statistics mailbox overrun: wanted step {} but the "
+                        "slot holds {}".format(step + 1, int(arr[0])))
+                if time.time() - t0 > _TIMEOUT_NS * 1e-9:
+                    raise RuntimeError("timed out waiting for the "
+                                       "statistics of step {}".format(step))
+                time.sleep(0)
+        return arr
 
     def _resolve_stats(self, handle):
-        mailbox, done, count, n_rows, seq = handle
-        done.synchronize()
+        step, done, count, n_rows = handle
+        arr = self.read_slot(step, wait_event=done)
         G = self.num_groups
-        arr = mailbox.numpy()
-        n = n_rows * G
-        if int(arr[n]) != seq:
-            raise RuntimeError("statistics mailbox out of sequence "
-                               "({} != {})".format(int(arr[n]), seq))
-        if int(arr[n + 2]) != 0:
+        if int(arr[5]) != 0:
             raise RuntimeError(
                 "fused all-reduce timed out waiting for a peer "
-                "(error word {})".format(int(arr[n + 2])))
-        rows = np.array(arr[:n], dtype=np.float64).reshape(n_rows, G)
+                "(error word {})".format(int(arr[5])))
+        n = n_rows * G
+        rows = np.array(arr[MBOX_HDR:MBOX_HDR + n],
+                        dtype=np.float64).reshape(n_rows, G)
         pair = (rows[2], rows[3]) if n_rows == 4 else None
         return GradStats(rows[0], rows[1], count, pair,
-                         sync_time=float(arr[n + 1]) * 1e-9)
+                         sync_time=float(arr[4]) * 1e-9)
 
     # -- broadcast -----------------------------------------------------------
 
@@ -352,8 +419,8 @@ class CudaGradReducer(GradReducer):
                 args.staging[p] = self._staging_ptrs[p]
                 args.pad[p] = self._pad_ptrs[p]
             args.rank, args.world, args.src = self.rank, self.world_size, src
-            self._epoch += 1
-            args.epoch = self._epoch & 0xFFFFFFFF
+            args.step_ctr = self._step_ctr.data_ptr()
+            args.site = self._next_site()
             args.dst = self._staging_ptrs[self.rank]
             args.n_vec = n_pad // 16
             args.err = self._err.data_ptr()

@@ -14,6 +14,7 @@ Two providers:
 * ``torch``: ``torch.distributed._symmetric_memory`` as a bring-up fallback.
 """
 
+import array
 import logging
 import os
 import socket
@@ -44,6 +45,69 @@ def _all_gather_object(obj, group):
     out = [None] * dist.get_world_size(group)
     dist.all_gather_object(out, obj, group=group)
     return out
+
+
+def send_fd(sock, address, payload, fd):
+    """One datagram carrying ``payload`` and the file descriptor ``fd``
+    (SCM_RIGHTS). (``socket.send_fds`` drops its ``address`` argument on
+    CPython <= 3.12, hence the explicit ``sendmsg``.)"""
+    sock.sendmsg([payload],
+                 [(socket.SOL_SOCKET, socket.SCM_RIGHTS,
+                   array.array("i", [fd]))], 0, address)
+
+
+def recv_fd(sock, bufsize=64):
+    msg, fds, _, _ = socket.recv_fds(sock, bufsize, 4)
+    if len(fds) != 1:
+        for extra in fds:
+            os.close(extra)
+        raise RuntimeError("expected exactly one file descriptor")
+    return msg, fds[0]
+
+
+class FdExchange(object):
+    """All-to-all exchange of one file descriptor per rank per round over
+    unix datagram sockets in the abstract namespace."""
+
+    def __init__(self, rank, world, gather_addresses):
+        self.rank, self.world = rank, world
+        self.sock = socket.socket(socket.AF_UNIX, socket.SOCK_DGRAM)
+        self.addr = "\0adl-b200-{}-{}".format(uuid.uuid4().hex, rank)
+        self.sock.bind(self.addr)
+        self.sock.settimeout(120.0)
+        # gathering the addresses doubles as "everyone has bound"
+        self.addrs = gather_addresses(self.addr)
+        self._serial = 0
+        self._early = {}
+
+    def exchange(self, fd):
+        """Send ``fd`` to every peer; returns ``{rank: fd}`` of the peers'
+        descriptors for the same round (caller closes them)."""
+        serial = self._serial
+        self._serial += 1
+        header = struct.pack("!II", serial, self.rank)
+        for peer, addr in enumerate(self.addrs):
+            if peer != self.rank:
+                send_fd(self.sock, addr, header, fd)
+        got = {}
+        while len(got) < self.world - 1:
+            key = next((k for k in self._early if k[0] == serial), None)
+            if key is not None:
+                got[key[1]] = self._early.pop(key)
+                continue
+            msg, peer_fd = recv_fd(self.sock)
+            got_serial, src = struct.unpack("!II", msg)
+            if got_serial != serial:          # a faster peer is a round ahead
+                self._early[(got_serial, src)] = peer_fd
+            else:
+                got[src] = peer_fd
+        return got
+
+    def close(self):
+        try:
+            self.sock.close()
+        except OSError:
+            pass
 
 
 class SymmetricRegion(object):
@@ -78,14 +142,8 @@ class _NativeProvider(object):
                                + self.lib.adl_symm_last_error().decode())
         if not self.lib.adl_topo_vmm_fd_supported(device.index):
             raise RuntimeError("device lacks POSIX-fd shareable VMM handles")
-        self.sock = socket.socket(socket.AF_UNIX, socket.SOCK_DGRAM)
-        token = uuid.uuid4().hex
-        self.addr = "\0adl-b200-{}-{}".format(token, self.rank)
-        self.sock.bind(self.addr)
-        self.sock.settimeout(120.0)
-        # gathering the addresses doubles as "everyone has bound"
-        self.addrs = _all_gather_object(self.addr, group)
-        self._serial = 0
+        self.fds = FdExchange(self.rank, self.world,
+                              lambda addr: _all_gather_object(addr, group))
         self._mapped = []
 
     def _check(self, code, what):
@@ -103,33 +161,18 @@ class _NativeProvider(object):
         handle, fd = ctypes.c_ulonglong(), ctypes.c_int()
         self._check(lib.adl_symm_create(dev, size, ctypes.byref(handle),
                                         ctypes.byref(fd)), "create")
-        serial = self._serial
-        self._serial += 1
-        header = struct.pack("!II", serial, self.rank)
-        for peer, addr in enumerate(self.addrs):
-            if peer != self.rank:
-                socket.send_fds(self.sock, [header], [fd.value], address=addr)
         handles = {self.rank: handle.value}
-        stash = getattr(self, "_early", {})
-        while len(handles) < self.world:
-            key = next((k for k in stash if k[0] == serial), None)
-            if key is not None:
-                peer_fd = stash.pop(key)
-                src = key[1]
-            else:
-                msg, fds, _, _ = socket.recv_fds(self.sock, 64, 4)
-                got_serial, src = struct.unpack("!II", msg)
-                peer_fd = fds[0]
-                if got_serial != serial:      # a faster peer is one ahead
-                    stash[(got_serial, src)] = peer_fd
-                    self._early = stash
-                    continue
-            imported = ctypes.c_ulonglong()
-            self._check(lib.adl_symm_import(peer_fd, ctypes.byref(imported)),
-                        "import")
-            os.close(peer_fd)
-            handles[src] = imported.value
-        os.close(fd.value)
+        try:
+            for src, peer_fd in self.fds.exchange(fd.value).items():
+                imported = ctypes.c_ulonglong()
+                try:
+                    self._check(lib.adl_symm_import(
+                        peer_fd, ctypes.byref(imported)), "import")
+                finally:
+                    os.close(peer_fd)
+                handles[src] = imported.value
+        finally:
+            os.close(fd.value)
         ptrs = []
         for peer in range(self.world):
             ptr = ctypes.c_ulonglong()
@@ -142,7 +185,7 @@ class _NativeProvider(object):
         tensor.zero_()
         torch.cuda.synchronize(self.device)
         # nobody may touch a peer's bytes before that peer zeroed them
-        _all_gather_object(serial, self.group)
+        _all_gather_object(size, self.group)
         return SymmetricRegion(tensor, ptrs, size, self.name, keepalive=self)
 
     def close(self):
@@ -150,10 +193,7 @@ class _NativeProvider(object):
             self.lib.adl_symm_unmap(ptr, size)
             self.lib.adl_symm_release(handle)
         self._mapped = []
-        try:
-            self.sock.close()
-        except OSError:
-            pass
+        self.fds.close()
 
 
 class _TorchProvider(object):

@@ -24,6 +24,7 @@ from .data import (current_dataloader, AdaptiveDataLoader, ElasticSampler,
                    DevicePrefetcher)
 from .parallel import AdaptiveDataParallel
 from .accumulator import Accumulator
+from adaptdl_b200.parallel.graph import GraphedTrainStep
 
 LOG = logging.getLogger(__name__)
 
@@ -38,6 +39,7 @@ __all__ = [
     "AdaptiveDataParallel",
     "Accumulator",
     "DevicePrefetcher",
+    "GraphedTrainStep",
 ]
 
 

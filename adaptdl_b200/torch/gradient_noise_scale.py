@@ -79,6 +79,8 @@ class GradientNoiseScale(object):
         self._smoothing = SMOOTHING
         self._listeners = []
         self._backward_listeners = []
+        self._engine = None
+        self._in_flush = False
         num_groups = len(optimizer.param_groups)
         self._optimizer.state.setdefault("gns", {
             "progress": 0.0,
@@ -120,6 +122,12 @@ class GradientNoiseScale(object):
         """``fn()`` is invoked after every statistics update (used by
         AdaptiveDataParallel to publish gain / progress)."""
         self._listeners.append(fn)
+
+    def attach_engine(self, engine):
+        """Switch to the device-resident estimator: statistics are folded
+        into the running averages on the GPU; this object then only mirrors
+        them (with a fixed lag, see ``parallel/engine.py``)."""
+        self._engine = engine
 
     def add_backward_listener(self, fn):
         """``fn(sync)`` is invoked at the end of every backward pass."""
@@ -181,6 +189,8 @@ class GradientNoiseScale(object):
 
     def set_progress(self, progress):
         self._state["progress"] = progress
+        if self._engine is not None and self._engine.enabled:
+            self._engine.set_progress(progress)
 
     def gain(self, scale):
         """AdaScale gain ratio at batch-size scale ``scale``."""
@@ -226,6 +236,23 @@ class GradientNoiseScale(object):
         """Fold the statistics of the last synchronised backward (if any)
         into the running averages. The one place the host waits for the
         device."""
+        if self._engine is not None and self._engine.enabled:
+            if self._in_flush:
+                return
+            self._in_flush = True
+            try:
+                self._pending = False
+                self._reducer._stats_ready = None
+                header = self._engine.mirror(self._state)
+                if header is not None:
+                    from adaptdl_b200.parallel.reducer_base import GradStats
+                    stats = GradStats(None, None, 0, None,
+                                      sync_time=float(header[4]) * 1e-9)
+                    for fn in self._listeners:
+                        fn(stats)
+            finally:
+                self._in_flush = False
+            return
         if not self._pending:
             return
         self._pending = False

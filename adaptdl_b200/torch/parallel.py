@@ -71,6 +71,7 @@ class AdaptiveDataParallel(torch.nn.Module):
         bucket_cap_mb = kwargs.pop("bucket_cap_mb", None) or 25
         process_group = kwargs.pop("process_group", None)
         backend = kwargs.pop("reducer", "auto")
+        fused_step = kwargs.pop("fused_step", None)
         for key in list(kwargs):
             if key in _IGNORED_DDP_KWARGS:
                 kwargs.pop(key)
@@ -105,10 +106,14 @@ class AdaptiveDataParallel(torch.nn.Module):
         self.gns.add_listener(self._on_stats)
         self.gns.add_backward_listener(self._on_backward_end)
         self.scaling_rule.initialize(self, optimizer, patch_optimizer=True)
+        self._engine = self._make_engine(optimizer, mp_scaler, fused_step)
 
         self._state = _AdaptiveDataParallelState(
-            model, optimizer, lr_scheduler, mp_scaler, name)
+            model, optimizer, lr_scheduler, mp_scaler, name, self._engine)
         checkpoint.load_state(self._state)
+        if self._engine is not None:
+            self._engine.adopt_optimizer_state()
+            self._engine.push_gns_state(optimizer.state["gns"])
         self._sync_module_states()
 
     # ------------------------------------------------------------------
@@ -116,6 +121,44 @@ class AdaptiveDataParallel(torch.nn.Module):
     @property
     def reducer(self):
         return self._reducer
+
+    @property
+    def engine(self):
+        """The device-resident step engine, or ``None`` (host path)."""
+        return self._engine
+
+    def _make_engine(self, optimizer, mp_scaler, fused_step):
+        import os
+        if fused_step is None:
+            fused_step = os.environ.get("ADAPTDL_B200_FUSED", "1") != "0"
+        if not fused_step or mp_scaler is not None \
+                or isinstance(self.gns, AdamGradientNoiseScale) \
+                or type(self._reducer).__name__ != "CudaGradReducer":
+            return None
+        from adaptdl_b200.parallel.engine import DeviceEngine
+        try:
+            engine = DeviceEngine(self._reducer, optimizer, self.scaling_rule,
+                                  optimizer.state["gns"])
+        except ValueError as exc:
+            LOG.info("device engine unavailable (%s); using the host path",
+                     exc)
+            return None
+        self.gns.attach_engine(engine)
+        return engine
+
+    def _sync_engine_ctrl(self):
+        engine = self._engine
+        if engine is None or not engine.enabled:
+            return
+        legw_unit = 0.0
+        rule = self.scaling_rule
+        if hasattr(rule, "_base_warmup_epochs"):
+            dataloader = current_dataloader()
+            if dataloader is not None:
+                legw_unit = (rule._base_warmup_epochs * rule._data_size
+                             / dataloader.batch_size)
+        engine.sync_ctrl(self.gns.accum_scale, self.gns._smoothing,
+                         legw_unit)
 
     def _module_tensors(self, buffers_only=False):
         tensors = [] if buffers_only else \
@@ -130,7 +173,8 @@ class AdaptiveDataParallel(torch.nn.Module):
         if self._world_size > 1:
             self._reducer.broadcast_parameters(self._module_tensors())
 
-    def forward(self, *args, **kwargs):
+    def _pre_forward(self):
+        """Host-side step set-up (also run before a CUDA-graph replay)."""
         dataloader = current_dataloader()
         if dataloader is not None and dataloader.training:
             # no gradient synchronisation on accumulation micro-steps
@@ -138,6 +182,10 @@ class AdaptiveDataParallel(torch.nn.Module):
             accum_scale = (dataloader.current_local_bsz
                            * env.num_replicas() / dataloader.batch_size)
             self.gns.set_accum_scale(accum_scale)
+        self._sync_engine_ctrl()
+
+    def forward(self, *args, **kwargs):
+        self._pre_forward()
         if self.broadcast_buffers and self._world_size > 1 \
                 and self.require_backward_grad_sync \
                 and torch.is_grad_enabled():
@@ -219,14 +267,20 @@ class _AdaptiveDataParallelState(checkpoint.State):
     averages ride inside ``optim_sd["state"]["gns"]``."""
 
     def __init__(self, model, optimizer, lr_scheduler, mp_scaler,
-                 name="adaptdl-dataparallel"):
+                 name="adaptdl-dataparallel", engine=None):
         super().__init__(name)
+        self.engine = engine
         self.model = model
         self.optimizer = optimizer
         self.lr_scheduler = lr_scheduler
         self.mp_scaler = mp_scaler
         self.gain = 1.0
         self.lr_factor = 1.0
+
+    def sync(self):
+        # device-resident estimator / Adam step counters -> host dicts
+        if self.engine is not None and self.engine.enabled:
+            self.engine.pull_gns_state(self.optimizer.state["gns"])
 
     def save(self, fileobj):
         state_dicts = [

@@ -59,6 +59,14 @@ class ScalingRuleBase(object):
             raise ValueError("AdaptiveDataParallel instance is not set!")
         if not self.adp.require_backward_grad_sync:
             return None
+        engine = getattr(self.adp, "__dict__", {}).get("_engine")
+        if engine is not None and engine.enabled and not args \
+                and not kwargs:
+            # device-resident path: the LR factors and the progress counter
+            # were produced on the GPU by the statistics kernel; one fused
+            # launch per gradient arena applies the update. No host sync.
+            engine.optimizer_step()
+            return None
         gns = self.adp.gns
         scale = gns.accum_scale * gns.accum_count
         groups = self._optimizer.param_groups

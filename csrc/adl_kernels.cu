@@ -24,12 +24,14 @@
 
 // error word bits (device -> host, sticky)
 #define ADL_ERR_TIMEOUT 1u
+#define ADL_MAX_STAT_SMEM (96 * 1024)
 
 struct ReduceArgs {
   void* buf[ADL_MAX_RANKS];        // bucket start in every rank's G arena
   uint32_t* pad[ADL_MAX_RANKS];    // signal pad of every rank
   int rank, world;
-  uint32_t epoch;
+  const uint32_t* step_ctr;        // device: optimizer steps finalized so far
+  uint32_t site;                   // launch ordinal within the current step
   int n_vec;                       // vectors in the bucket (multiple of world)
   float scale;
   int want_local;
@@ -56,13 +58,23 @@ __device__ __forceinline__ bool wait_flag(const uint32_t* p, uint32_t epoch,
   return true;
 }
 
+// Flag values ("epochs") are derived on the device: step counter (bumped by
+// the finalize kernel once per optimizer step) * ADL_SITES_PER_STEP + the
+// launch's ordinal within the step. Nothing launch-specific is baked into
+// kernel arguments, so a captured CUDA graph can be replayed step after step.
+#define ADL_SITES_PER_STEP 1024u
+__device__ __forceinline__ uint32_t launch_epoch(const uint32_t* step_ctr, uint32_t site) {
+  return (*reinterpret_cast<const volatile uint32_t*>(step_ctr)) * ADL_SITES_PER_STEP + site;
+}
+
 __device__ __forceinline__ void cta_barrier_peers(const ReduceArgs& a, int phase) {
   __syncthreads();
   if ((int)threadIdx.x < a.world) {
     const int peer = threadIdx.x;
+    const uint32_t epoch = launch_epoch(a.step_ctr, a.site);
     __threadfence_system();
-    st_release_sys(pad_slot(a.pad[peer], phase, blockIdx.x, a.rank), a.epoch);
-    wait_flag(pad_slot(a.pad[a.rank], phase, blockIdx.x, peer), a.epoch, a.timeout_ns, a.err);
+    st_release_sys(pad_slot(a.pad[peer], phase, blockIdx.x, a.rank), epoch);
+    wait_flag(pad_slot(a.pad[a.rank], phase, blockIdx.x, peer), epoch, a.timeout_ns, a.err);
   }
   __syncthreads();
 }
@@ -156,7 +168,8 @@ struct LocalArgs {
   SegTable segs;
   int n_groups;
   double* s0; double* s1; double* s2;   // statistic outputs (see kernels)
-  int flag;
+  int flag;                             // MODE 2: previous-step stash is valid
+  const int* flag_ptr;                  // if non-null, overrides `flag` (device-resident state)
 };
 
 // MODE 0: fold_acc   (a += g ; s0 += |g|^2 ; g = 0)
@@ -174,6 +187,7 @@ local_kernel(const LocalArgs a) {
   const int stride = gridDim.x * blockDim.x;
   const int first = blockIdx.x * blockDim.x + threadIdx.x;
   const int iters = (a.n_vec + stride - 1) / stride;
+  const bool have_prev = a.flag_ptr ? (*a.flag_ptr != 0) : (a.flag != 0);
   int cur = -1;
   for (int it = 0; it < iters; ++it) {
     const int v = first + it * stride;
@@ -212,7 +226,7 @@ local_kernel(const LocalArgs a) {
         Vec16 z; z.w[0] = z.w[1] = z.w[2] = z.w[3] = 0u;
         st_vec(static_cast<Vec16*>(a.a) + v, z);
       } else {
-        if (a.flag) {
+        if (have_prev) {
 #pragma unroll
           for (int e = 0; e < N; ++e) {
             const float p = HAS_PINV ? o[e] * pinv[e] : o[e];
@@ -235,67 +249,216 @@ local_kernel(const LocalArgs a) {
 }
 
 // ---------------------------------------------------------------------------
-// statistics exchange + host mailbox
+// statistics exchange + gradient-noise-scale estimator + host mailbox
 // ---------------------------------------------------------------------------
+// Device-resident estimator state (doubles): see GNS_* offsets.
+//   [0,G) sqr_biased  [G,2G) var_biased  [2G,3G) sqr_avg  [3G,4G) var_avg
+//   4G+0 sqr_unbias  4G+1 var_unbias  4G+2 progress  4G+3 biased flag
+// Host-written control block (doubles):
+//   0 accum_scale  1 smoothing  2 rule id  3 rule arg (LEGW unit)  4 enabled
+enum { GNS_SQR_UNBIAS = 0, GNS_VAR_UNBIAS = 1, GNS_PROGRESS = 2, GNS_BIASED = 3, GNS_TAIL = 8 };
+enum { CTL_ACCUM_SCALE = 0, CTL_SMOOTHING = 1, CTL_RULE = 2, CTL_RULE_ARG = 3, CTL_ENABLED = 4 };
+enum { RULE_ADASCALE = 0, RULE_ADAMSCALE = 1, RULE_LINEAR = 2, RULE_SQRT = 3, RULE_LEGW = 4 };
+// Mailbox slot (doubles): header then payload.
+//   0 seq  1 finite  2 gain  3 progress  4 sync_ns  5 err  6 scale  7 n_rows
+//   host mode   : 8.. raw rows [n_rows][G]
+//   device mode : 8.. sqr_avg[G], var_avg[G], lr_factor[G]
+#define ADL_MBOX_HDR 8
+
 struct FinalizeArgs {
-  double* xchg[ADL_MAX_RANKS];     // every rank's exchange buffer [2][n_rows*n_groups]
+  double* xchg[ADL_MAX_RANKS];     // every rank's exchange buffer [2][4*n_groups]
   uint32_t* pad[ADL_MAX_RANKS];
   int rank, world;
-  uint32_t epoch;
-  int parity;
-  int n_rows;                      // statistic rows (2 or 4)
+  uint32_t* step_ctr;              // device; bumped at the end of this kernel
+  uint32_t site;
+  int n_rows;                      // statistic rows in use (2, or 4 in pair mode)
   int n_groups;
   double* rows[4];                 // local partial vectors (device), reset after publish
   int sum_mask;                    // bit r set: row r is a per-rank partial to be summed
-  double* mailbox;                 // pinned host: [n_rows*n_groups] then header
+  int micro_steps;                 // k: backward passes folded into this step
+  int pair_mode;                   // single replica, no accumulation
+  int pair_flag;                   // host-mode: stash was valid (rows 2,3 meaningful)
+  int* pair_state;                 // device-mode: stash validity (read, then updated)
+  double* mailbox;                 // pinned host ring: [ring][slot_doubles]
+  int ring, slot_doubles;
   double* result;                  // device copy of the summed rows (may be nullptr)
   unsigned long long* t_start;     // device: %globaltimer at end of local backward
-  unsigned long long seq;
+  double* gns_state;               // device estimator state or nullptr (host mode)
+  const double* gns_ctrl;          // host-written control block (device memory)
+  float* lr_factor;                // [n_groups] out (device mode)
   uint32_t* err;
   unsigned long long timeout_ns;
 };
-// mailbox header (after the data, as doubles): [seq, sync_ns, err]
+
+__device__ __forceinline__ double block_sum(double x, double* scratch) {
+  // blockDim.x == 256
+  __syncthreads();
+  scratch[threadIdx.x] = x;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) scratch[threadIdx.x] += scratch[threadIdx.x + o];
+    __syncthreads();
+  }
+  return scratch[0];
+}
 
 __global__ void __launch_bounds__(256, 1) finalize_stats_kernel(const FinalizeArgs a) {
-  const int n = a.n_rows * a.n_groups;
-  double* mine = a.xchg[a.rank] + (size_t)a.parity * n;
+  __shared__ double scratch[256];
+  const int G = a.n_groups;
+  const int n = a.n_rows * G;
+  const uint32_t step = *reinterpret_cast<volatile uint32_t*>(a.step_ctr);
+  const int parity = step & 1;
+  double* mine = a.xchg[a.rank] + (size_t)parity * 4 * G;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const int r = i / a.n_groups;
-    mine[i] = a.rows[r][i - r * a.n_groups];
+    const int r = i / G;
+    mine[i] = a.rows[r][i - r * G];
   }
   if (a.world > 1) {
     __syncthreads();
     if ((int)threadIdx.x < a.world) {
       const int peer = threadIdx.x;
+      const uint32_t epoch = step * ADL_SITES_PER_STEP + a.site;
       __threadfence_system();
-      st_release_sys(pad_slot(a.pad[peer], 0, ADL_MAX_CTAS - 1, a.rank), a.epoch);
-      wait_flag(pad_slot(a.pad[a.rank], 0, ADL_MAX_CTAS - 1, peer), a.epoch, a.timeout_ns, a.err);
+      st_release_sys(pad_slot(a.pad[peer], 0, ADL_MAX_CTAS - 1, a.rank), epoch);
+      wait_flag(pad_slot(a.pad[a.rank], 0, ADL_MAX_CTAS - 1, peer), epoch, a.timeout_ns, a.err);
     }
     __syncthreads();
   }
+  double* slot = a.mailbox + (size_t)(step % a.ring) * a.slot_doubles;
+  double* summed = a.result;                 // [4][G] device scratch (always provided)
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const int r = i / a.n_groups;
+    const int r = i / G;
     double x;
     if (a.world > 1 && ((a.sum_mask >> r) & 1)) {
       x = 0.0;
       for (int p = 0; p < a.world; ++p)       // fixed order: identical on all ranks
-        x += *reinterpret_cast<volatile double*>(a.xchg[p] + (size_t)a.parity * n + i);
+        x += *reinterpret_cast<volatile double*>(a.xchg[p] + (size_t)parity * 4 * G + i);
     } else {
       x = mine[i];
     }
-    a.mailbox[i] = x;
-    if (a.result) a.result[i] = x;
-    a.rows[r][i - r * a.n_groups] = 0.0;      // partials restart from zero
+    summed[i] = x;
+    a.rows[r][i - r * G] = 0.0;               // partials restart from zero
+  }
+  __syncthreads();
+
+  const bool device_mode = a.gns_state != nullptr && a.gns_ctrl[CTL_ENABLED] != 0.0;
+  double finite_flag = 1.0, gain = 1.0, progress = 0.0, scale_out = 0.0;
+  if (!device_mode) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) slot[ADL_MBOX_HDR + i] = summed[i];
+  } else {
+    double* st = a.gns_state;
+    double* tail = st + 4 * G;
+    const double accum_scale = a.gns_ctrl[CTL_ACCUM_SCALE];
+    const double smoothing = a.gns_ctrl[CTL_SMOOTHING];
+    const int rule = (int)a.gns_ctrl[CTL_RULE];
+    const double* L = summed;
+    const double* T = summed + G;
+    // non-finite gradients: skip the statistics update (and the progress)
+    double bad = 0.0;
+    for (int g = threadIdx.x; g < G; g += blockDim.x)
+      if (!isfinite(T[g]) || !isfinite(L[g])) bad += 1.0;
+    bad = block_sum(bad, scratch);
+    const bool finite = bad == 0.0;
+    finite_flag = finite ? 1.0 : 0.0;
+    int count = a.world * a.micro_steps;
+    double scale = accum_scale * a.micro_steps;
+    const double lr_scale = scale;            // ScalingRuleBase.step uses accum_scale * k
+    const bool had_stash = a.pair_mode && a.pair_state && (*a.pair_state != 0);
+    bool update = finite;
+    bool was_biased = tail[GNS_BIASED] != 0.0;
+    __syncthreads();
+    if (finite) {
+      if (count > 1) {
+        if (was_biased) {                     // biased -> unbiased: restart the averages
+          for (int g = threadIdx.x; g < G; g += blockDim.x) { st[g] = 0.0; st[G + g] = 0.0; }
+          __syncthreads();
+          if (threadIdx.x == 0) { tail[GNS_SQR_UNBIAS] = 0.0; tail[GNS_VAR_UNBIAS] = 0.0; }
+        }
+        if (threadIdx.x == 0) tail[GNS_BIASED] = 0.0;
+      } else {
+        if (threadIdx.x == 0) tail[GNS_BIASED] = 1.0;
+        if (!had_stash) update = false;       // first sample: nothing to difference yet
+      }
+    }
+    __syncthreads();
+    if (update) {
+      const double theta_scale = (count > 1) ? scale : 2.0 * accum_scale;
+      const double theta = pow(smoothing, theta_scale);
+      const double su = theta * tail[GNS_SQR_UNBIAS] + (1.0 - theta);
+      const double vu = theta * tail[GNS_VAR_UNBIAS] + (1.0 - theta);
+      for (int g = threadIdx.x; g < G; g += blockDim.x) {
+        double local, total, cnt, sc;
+        if (count > 1) {
+          local = L[g] / count; total = T[g]; cnt = count; sc = scale;
+        } else {
+          const double* Pp = summed + 2 * G;
+          const double* Pa = summed + 3 * G;
+          local = 0.5 * (Pp[g] + T[g]); total = Pa[g]; cnt = 2.0; sc = 2.0 * accum_scale;
+        }
+        const double grad_sqr = (cnt * total - local) / (cnt - 1.0);
+        const double grad_var = (local - total) * sc / (cnt - 1.0);
+        const double sb = theta * st[g] + (1.0 - theta) * grad_sqr;
+        const double vb = theta * st[G + g] + (1.0 - theta) * grad_var;
+        st[g] = sb; st[G + g] = vb;
+        st[2 * G + g] = sb / su; st[3 * G + g] = vb / vu;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) { tail[GNS_SQR_UNBIAS] = su; tail[GNS_VAR_UNBIAS] = vu; }
+    }
+    __syncthreads();
+    if (a.pair_state && threadIdx.x == 0)
+      *a.pair_state = (a.pair_mode && finite) ? 1 : 0;
+    // learning-rate factors and gain from the (possibly just updated) averages
+    double sqr_sum = 0.0, var_sum = 0.0;
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+      const double var = fmax(st[3 * G + g], 1e-6);
+      const double sqr = fmax(st[2 * G + g], 0.0);
+      sqr_sum += sqr; var_sum += var;
+    }
+    sqr_sum = block_sum(sqr_sum, scratch);
+    var_sum = block_sum(var_sum, scratch);
+    gain = (var_sum + sqr_sum) / (var_sum / lr_scale + sqr_sum);
+    progress = tail[GNS_PROGRESS];
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+      const double var = fmax(st[3 * G + g], 1e-6);
+      const double sqr = fmax(st[2 * G + g], 0.0);
+      const double ada = (var + sqr) / (var / lr_scale + sqr);
+      double f;
+      if (rule == RULE_ADASCALE) f = ada;
+      else if (rule == RULE_ADAMSCALE) f = sqrt(ada);
+      else if (rule == RULE_LINEAR) f = lr_scale;
+      else if (rule == RULE_SQRT) f = sqrt(lr_scale);
+      else {                                  // LEGW: sqrt(scale) with progress warm-up
+        const double total_steps = a.gns_ctrl[CTL_RULE_ARG] * lr_scale;
+        f = sqrt(lr_scale) * ((progress < total_steps) ? progress / total_steps : 1.0);
+      }
+      a.lr_factor[g] = (float)f;
+      slot[ADL_MBOX_HDR + g] = st[2 * G + g];
+      slot[ADL_MBOX_HDR + G + g] = st[3 * G + g];
+      slot[ADL_MBOX_HDR + 2 * G + g] = f;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && finite) {         // progress advances with every update
+      progress += gain;
+      tail[GNS_PROGRESS] = progress;
+    }
+    scale_out = lr_scale;
   }
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
     const unsigned long long now = globaltimer_ns();
     const unsigned long long t0 = a.t_start ? *a.t_start : now;
-    a.mailbox[n + 1] = (double)(now > t0 ? now - t0 : 0ull);
-    a.mailbox[n + 2] = (double)(*a.err);
+    slot[1] = finite_flag;
+    slot[2] = gain;
+    slot[3] = progress;
+    slot[4] = (double)(now > t0 ? now - t0 : 0ull);
+    slot[5] = (double)(*a.err);
+    slot[6] = scale_out;
+    slot[7] = (double)a.n_rows;
     __threadfence_system();
-    *reinterpret_cast<volatile double*>(a.mailbox + n) = (double)a.seq;   // publish last
+    *reinterpret_cast<volatile double*>(slot) = (double)(step + 1);   // publish last
+    *a.step_ctr = step + 1;                                           // next optimizer step
   }
 }
 
@@ -308,7 +471,8 @@ struct BcastArgs {
   void* staging[ADL_MAX_RANKS];
   uint32_t* pad[ADL_MAX_RANKS];
   int rank, world, src;
-  uint32_t epoch;
+  const uint32_t* step_ctr;
+  uint32_t site;
   void* dst;                       // local destination (may equal staging[rank])
   long long n_vec;
   uint32_t* err;
@@ -319,7 +483,7 @@ __global__ void __launch_bounds__(ADL_THREADS, 1) bcast_pull_kernel(const BcastA
   ReduceArgs b;   // reuse the barrier helper
 #pragma unroll
   for (int p = 0; p < ADL_MAX_RANKS; ++p) b.pad[p] = a.pad[p];
-  b.rank = a.rank; b.world = a.world; b.epoch = a.epoch; b.err = a.err; b.timeout_ns = a.timeout_ns;
+  b.rank = a.rank; b.world = a.world; b.step_ctr = a.step_ctr; b.site = a.site; b.err = a.err; b.timeout_ns = a.timeout_ns;
   cta_barrier_peers(b, 0);                            // source staging is complete
   if (a.rank != a.src || a.dst != a.staging[a.rank]) {
     const Vec16* src = static_cast<const Vec16*>(a.staging[a.src]);
@@ -344,12 +508,39 @@ __global__ void __launch_bounds__(ADL_THREADS, 1) bcast_pull_kernel(const BcastA
 
 static int g_device = -1;
 
+// Raise the dynamic shared memory limit of every statistics kernel ONCE (not
+// per launch: launches may happen under CUDA-graph capture).
+template <typename T>
+static int set_attrs_for() {
+  const int lim = ADL_MAX_STAT_SMEM;
+  ADL_CHECK(cudaFuncSetAttribute(allreduce_gns_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+  ADL_CHECK(cudaFuncSetAttribute(allreduce_gns_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+  ADL_CHECK(cudaFuncSetAttribute(local_kernel<T, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+  ADL_CHECK(cudaFuncSetAttribute(local_kernel<T, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+  ADL_CHECK(cudaFuncSetAttribute(local_kernel<T, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+  ADL_CHECK(cudaFuncSetAttribute(local_kernel<T, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+  ADL_CHECK(cudaFuncSetAttribute(local_kernel<T, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+  ADL_CHECK(cudaFuncSetAttribute(local_kernel<T, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+  return 0;
+}
+
 extern "C" {
 
 int adl_set_device(int dev) {
   g_device = dev;
-  return (int)cudaSetDevice(dev);
+  ADL_CHECK(cudaSetDevice(dev));
+  if (int rc = set_attrs_for<float>()) return rc;
+  if (int rc = set_attrs_for<__nv_bfloat16>()) return rc;
+  if (int rc = set_attrs_for<__half>()) return rc;
+  return 0;
 }
+
+int adl_bind_thread() {
+  if (g_device >= 0) ADL_CHECK(cudaSetDevice(g_device));
+  return 0;
+}
+
+int adl_max_groups() { return ADL_MAX_STAT_SMEM / (3 * (int)sizeof(double)); }
 
 const char* adl_error_string(int code) { return cudaGetErrorString((cudaError_t)code); }
 
@@ -363,14 +554,10 @@ int adl_sm_count(int dev) {
 int adl_allreduce_gns(const ReduceArgs* args, int dtype, int grid, void* stream) {
   if (g_device >= 0) ADL_CHECK(cudaSetDevice(g_device));
   const size_t smem = sizeof(double) * 2 * args->n_groups;
+  if (smem > ADL_MAX_STAT_SMEM) return -4;
   const bool pinv = args->pinv != nullptr;
   cudaStream_t s = (cudaStream_t)stream;
-#define LAUNCH_AR(T, P)                                                                      \
-  do {                                                                                       \
-    ADL_CHECK(cudaFuncSetAttribute(allreduce_gns_kernel<T, P>,                               \
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    allreduce_gns_kernel<T, P><<<grid, ADL_THREADS, smem, s>>>(*args);                       \
-  } while (0)
+#define LAUNCH_AR(T, P) allreduce_gns_kernel<T, P><<<grid, ADL_THREADS, smem, s>>>(*args)
   if (dtype == 0) { if (pinv) LAUNCH_AR(float, true); else LAUNCH_AR(float, false); }
   else if (dtype == 1) { if (pinv) LAUNCH_AR(__nv_bfloat16, true); else LAUNCH_AR(__nv_bfloat16, false); }
   else if (dtype == 2) { if (pinv) LAUNCH_AR(__half, true); else LAUNCH_AR(__half, false); }
@@ -383,14 +570,10 @@ int adl_allreduce_gns(const ReduceArgs* args, int dtype, int grid, void* stream)
 int adl_local(const LocalArgs* args, int mode, int dtype, int grid, void* stream) {
   if (g_device >= 0) ADL_CHECK(cudaSetDevice(g_device));
   const size_t smem = sizeof(double) * 3 * args->n_groups;
+  if (smem > ADL_MAX_STAT_SMEM) return -4;
   const bool pinv = args->pinv != nullptr;
   cudaStream_t s = (cudaStream_t)stream;
-#define LAUNCH_L(T, M, P)                                                                    \
-  do {                                                                                       \
-    ADL_CHECK(cudaFuncSetAttribute(local_kernel<T, M, P>,                                    \
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    local_kernel<T, M, P><<<grid, ADL_THREADS, smem, s>>>(*args);                            \
-  } while (0)
+#define LAUNCH_L(T, M, P) local_kernel<T, M, P><<<grid, ADL_THREADS, smem, s>>>(*args)
 #define LAUNCH_LM(T)                                                                         \
   do {                                                                                       \
     if (mode == 0) { if (pinv) LAUNCH_L(T, 0, true); else LAUNCH_L(T, 0, false); }           \

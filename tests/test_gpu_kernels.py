@@ -210,3 +210,181 @@ def test_multi_gpu_fused_allreduce(provider):
                           stderr=subprocess.STDOUT, text=True, timeout=600)
     assert proc.returncode == 0, proc.stdout[-4000:]
     assert "MULTIGPU_OK" in proc.stdout
+
+
+# ------------------------------------------------------------------------
+# device engine (on-GPU estimator + fused optimizer) and CUDA-graph step
+# ------------------------------------------------------------------------
+
+_COUNTER = [0]
+
+
+def _single_process_runtime():
+    import adaptdl_b200.torch as adl
+    from adaptdl_b200 import collective
+    os.environ.pop("ADAPTDL_CHECKPOINT_PATH", None)
+    if not torch.distributed.is_initialized():
+        os.environ.setdefault("ADAPTDL_MASTER_ADDR", "127.0.0.1")
+        adl.init_process_group("nccl")
+    elif not collective.is_initialized():
+        collective.initialize("127.0.0.1", 0, 0, 1)
+    return adl
+
+
+def _train(adl, make_opt, rule_fn, fused, graphed, steps=14, accum=False,
+           model_fn=None, lag=None):
+    """Train a small model through the public API; returns (params, gns
+    dict, net)."""
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    if model_fn is None:
+        model = torch.nn.Sequential(
+            torch.nn.Linear(32, 64), torch.nn.ReLU(),
+            torch.nn.Linear(64, 64), torch.nn.Tanh(),
+            torch.nn.Linear(64, 10)).to(dev)
+    else:
+        model = model_fn().to(dev)
+    opt = make_opt(model)
+    _COUNTER[0] += 1
+    net = adl.AdaptiveDataParallel(model, opt, scaling_rule=rule_fn(),
+                                   name="t{}".format(_COUNTER[0]),
+                                   fused_step=fused)
+    assert (net.engine is not None) == bool(fused)
+    gen = torch.Generator().manual_seed(3)
+    data = torch.utils.data.TensorDataset(
+        torch.randn(16 * steps * 2, 32, generator=gen),
+        torch.randint(0, 10, (16 * steps * 2,), generator=gen))
+    loader = adl.AdaptiveDataLoader(data, batch_size=16, drop_last=True)
+    if accum:
+        loader.autoscale_batch_size(64, local_bsz_bounds=(8, 16),
+                                    gradient_accumulation=True)
+        helper = loader._elastic
+        orig = helper._sync_local_bsz
+
+        def fixed():
+            orig()
+            helper._state.current_local_bsz = 16
+            helper._state.accumulation_steps = 1
+            return 16
+        helper._sync_local_bsz = fixed
+    trainer = adl.GraphedTrainStep(
+        net, opt, lambda n, x, y: torch.nn.functional.cross_entropy(n(x), y),
+        warmup=2, enabled=graphed)
+    losses = []
+    for epoch in adl.remaining_epochs_until(adl.finished_epochs() + 1):
+        for i, (x, y) in enumerate(loader):
+            losses.append(trainer(x, y).clone())
+            if i + 1 >= steps * (2 if accum else 1):
+                break
+    torch.cuda.synchronize()
+    if net.engine is not None:
+        net.engine.pull_gns_state(opt.state["gns"])
+    else:
+        net.gns._flush()
+    gns = {k: np.array(v, dtype=float) for k, v in opt.state["gns"].items()
+           if k in ("sqr_avg", "var_avg", "progress")}
+    params = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+    return params, gns, net, trainer, torch.stack(losses)
+
+
+def _sgd(model):
+    return torch.optim.SGD([{"params": [p]} for p in model.parameters()],
+                           lr=0.05, momentum=0.9, weight_decay=5e-4,
+                           nesterov=True)
+
+
+@pytest.mark.parametrize("accum", [False, True])
+def test_device_engine_matches_host_path(accum):
+    """On-GPU estimator + fused SGD reproduce the host estimator + torch SGD
+    (same LR factors => same parameters, same running averages)."""
+    adl = _single_process_runtime()
+    from adaptdl_b200.torch.scaling_rules import AdaScale
+    pa, ga, net_a, _, la = _train(adl, _sgd, AdaScale, True, False,
+                                  accum=accum)
+    pb, gb, net_b, _, lb = _train(adl, _sgd, AdaScale, False, False,
+                                  accum=accum)
+    assert net_a.engine is not None and net_b.engine is None
+    torch.testing.assert_close(la, lb, rtol=2e-4, atol=2e-5)
+    torch.testing.assert_close(pa, pb, rtol=2e-4, atol=2e-5)
+    for key in ("sqr_avg", "var_avg", "progress"):
+        np.testing.assert_allclose(ga[key], gb[key], rtol=2e-3, atol=1e-9)
+    assert ga["progress"] > 0
+
+
+@pytest.mark.parametrize("opt_name", ["adam", "adamw", "sgd_plain"])
+def test_fused_optimizers_match_torch(opt_name):
+    adl = _single_process_runtime()
+    from adaptdl_b200.torch.scaling_rules import LinearScale
+
+    def make(model):
+        if opt_name == "adam":
+            return torch.optim.Adam(model.parameters(), lr=1e-3,
+                                    weight_decay=1e-2)
+        if opt_name == "adamw":
+            return torch.optim.AdamW(
+                [{"params": list(model.parameters())[:2], "lr": 2e-3},
+                 {"params": list(model.parameters())[2:]}],
+                lr=1e-3, weight_decay=5e-2, betas=(0.8, 0.95))
+        return torch.optim.SGD(model.parameters(), lr=0.1)
+    pa, _, _, _, la = _train(adl, make, LinearScale, True, False, steps=10)
+    pb, _, _, _, lb = _train(adl, make, LinearScale, False, False, steps=10)
+    torch.testing.assert_close(la, lb, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(pa, pb, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("accum", [False, True])
+def test_graphed_step_matches_eager(accum):
+    adl = _single_process_runtime()
+    from adaptdl_b200.torch.scaling_rules import AdaScale
+
+    def bn_model():
+        return torch.nn.Sequential(
+            torch.nn.Linear(32, 64), torch.nn.BatchNorm1d(64),
+            torch.nn.ReLU(), torch.nn.Linear(64, 10))
+    pa, ga, net_a, tr_a, la = _train(adl, _sgd, AdaScale, True, True,
+                                     steps=12, accum=accum,
+                                     model_fn=bn_model)
+    pb, gb, net_b, tr_b, lb = _train(adl, _sgd, AdaScale, True, False,
+                                     steps=12, accum=accum,
+                                     model_fn=bn_model)
+    assert tr_a.replays >= 6 and tr_b.replays == 0
+    torch.testing.assert_close(la, lb, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(pa, pb, rtol=1e-5, atol=1e-6)
+    for key in ("sqr_avg", "var_avg", "progress"):
+        np.testing.assert_allclose(ga[key], gb[key], rtol=1e-6)
+    # the host mirror trails the device but is alive
+    assert net_a.gns.get_progress() > 0
+    assert net_a.reducer.launches > 0
+
+
+def test_checkpoint_roundtrip_with_device_engine(tmp_path):
+    """optimizer.state_dict() sees the live device state (GNS averages,
+    momentum buffers) and a reload restores it."""
+    adl = _single_process_runtime()
+    from adaptdl_b200.torch.scaling_rules import AdaScale
+    _, gns, net, _, _ = _train(adl, _sgd, AdaScale, True, False, steps=6)
+    import io
+    buf = io.BytesIO()
+    net._state.sync()
+    net._state.save(buf)
+    sd = torch.load(io.BytesIO(buf.getvalue()), weights_only=False)
+    optim_sd = sd[0][1]
+    np.testing.assert_allclose(optim_sd["state"]["gns"]["sqr_avg"],
+                               gns["sqr_avg"])
+    first = next(iter(k for k in optim_sd["state"] if k != "gns"))
+    assert optim_sd["state"][first]["momentum_buffer"].abs().sum() > 0
+    # perturb, reload, verify restoration
+    before = torch.cat([p.detach().reshape(-1).clone()
+                        for p in net.module.parameters()])
+    with torch.no_grad():
+        for p in net.module.parameters():
+            p.add_(1.0)
+    net._state.load(io.BytesIO(buf.getvalue()))
+    net.engine.adopt_optimizer_state()
+    net.engine.push_gns_state(net._state.optimizer.state["gns"])
+    after = torch.cat([p.detach().reshape(-1)
+                       for p in net.module.parameters()])
+    torch.testing.assert_close(before, after)
+    probe = {}
+    net.engine.pull_gns_state(probe)
+    np.testing.assert_allclose(probe["sqr_avg"], gns["sqr_avg"])

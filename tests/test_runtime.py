@@ -175,3 +175,54 @@ def test_signal_flag():
     os.kill(os.getpid(), signal.SIGTERM)
     assert _signal.get_exit_flag()
     _signal.set_exit_flag(False)
+
+
+def test_fd_exchange_between_processes():
+    """The SCM_RIGHTS all-to-all used to share GPU memory handles, exercised
+    with ordinary file descriptors: every rank sends an unlinked file's
+    descriptor to every peer for two rounds; peers read the token through it."""
+    import multiprocessing as mp
+    import tempfile
+    world = 3
+    tmp = tempfile.mkdtemp()
+
+    def main(rank):
+        import time
+        from adaptdl_b200.parallel.symm import FdExchange
+
+        def gather(addr):
+            with open(os.path.join(tmp, "addr{}".format(rank)), "wb") as f:
+                f.write(addr.encode("utf-8", "surrogateescape"))
+            out = []
+            for r in range(world):
+                path = os.path.join(tmp, "addr{}".format(r))
+                while not os.path.exists(path) or \
+                        os.path.getsize(path) == 0:
+                    time.sleep(0.01)
+                with open(path, "rb") as f:
+                    out.append(f.read().decode("utf-8", "surrogateescape"))
+            time.sleep(0.2)
+            return out
+        ex = FdExchange(rank, world, gather)
+        for rnd in range(2):
+            path = os.path.join(tmp, "tok{}-{}".format(rank, rnd))
+            with open(path, "wb") as f:
+                f.write("r{}-{}".format(rank, rnd).encode())
+            mine = os.open(path, os.O_RDONLY)
+            os.unlink(path)          # only reachable through the descriptor
+            got = ex.exchange(mine)
+            assert sorted(got) == [p for p in range(world) if p != rank]
+            for src, fd in got.items():
+                assert os.pread(fd, 64, 0) == \
+                    "r{}-{}".format(src, rnd).encode()
+                os.close(fd)
+            os.close(mine)
+        ex.close()
+
+    ctx = mp.get_context("fork")
+    procs = [ctx.Process(target=main, args=(r,)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
