@@ -1,0 +1,362 @@
+"""Pollux: goodput-driven co-adaptive allocation of replicas to nodes.
+
+Capabilities match the reference's ``sched/adaptdl_sched/policy/pollux.py``
+(``allocate_job`` first-fit for new arrivals; ``optimize`` = multi-objective
+genetic search over job x node replica matrices, maximising the sum of
+dominant-share-scaled speedups and minimising the number of nodes used, with
+a restart penalty, warm start from the previous cycle, "virtual" nodes for
+cluster autoscaling and a utilisation band that picks the desired cluster
+size) -- but implemented on the small in-house NSGA-II in ``nsga2.py`` rather
+than on pymoo, with the problem's operators written against this module's
+own state layout.
+
+State layout: ``states[p, j, n]`` = replicas of job ``j`` on node ``n`` in
+candidate ``p``. Nodes ``[0, N)`` are the real nodes (non-preemptible first),
+nodes ``[N, 2N)`` are copies of the autoscaling node template ("what if the
+cluster were bigger").
+"""
+
+import collections
+import copy
+import logging
+
+import numpy as np
+
+from adaptdl_b200.sched.policy import nsga2
+
+LOG = logging.getLogger(__name__)
+
+POP_SIZE = 100
+GENERATIONS = 100
+RESTART_PENALTY = 0.1
+MIN_UTIL, MAX_UTIL = 0.35, 0.65
+
+
+def _sorted_nodes(nodes):
+    """Non-preemptible nodes first, then by key."""
+    return collections.OrderedDict(
+        sorted(nodes.items(), key=lambda kv: (kv[1].preemptible, kv[0])))
+
+
+class ClusterProblem(object):
+    """Objectives and genetic operators for one optimisation cycle."""
+
+    def __init__(self, jobs, nodes, base_state, restart_penalty=RESTART_PENALTY):
+        assert base_state.shape == (len(jobs), len(nodes))
+        self.jobs, self.nodes = jobs, nodes
+        self.base = base_state
+        self.restart_penalty = restart_penalty
+        J, N = base_state.shape
+        self.pinned = np.array(
+            [j for j, job in enumerate(jobs)
+             if not job.preemptible and base_state[j].any()], dtype=int)
+        rtypes = sorted(set().union(*[set(job.resources) for job in jobs]))
+        self.job_res = np.array(
+            [[job.resources.get(r, 0) for r in rtypes] for job in jobs],
+            dtype=np.int64)                                    # [J, R]
+        self.node_res = np.array(
+            [[node.resources.get(r, 0) for r in rtypes] for node in nodes],
+            dtype=np.int64)                                    # [N, R]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            share = self.job_res / self.node_res.sum(axis=0)
+        self.dominant_share = np.nan_to_num(share, nan=0.0,
+                                            posinf=0.0).max(axis=1)
+        # capacity left on each node once pinned jobs are accounted for
+        pinned_use = np.einsum("jn,jr->nr", base_state[self.pinned],
+                               self.job_res[self.pinned]) \
+            if len(self.pinned) else np.zeros_like(self.node_res)
+        free = self.node_res - pinned_use
+        assert (free >= 0).all()
+        # most replicas of job j that fit on node n by itself
+        with np.errstate(divide="ignore"):
+            fit = np.where(self.job_res[:, None, :] > 0,
+                           free[None, :, :] // np.maximum(
+                               self.job_res[:, None, :], 1),
+                           np.iinfo(np.int64).max)
+        self.max_fit = fit.min(axis=2).astype(np.int64)        # [J, N]
+        self.max_fit = np.minimum(self.max_fit, 1 << 20)
+        # spread each job's min_replicas greedily over nodes: the lower
+        # bound used by mutation
+        self.min_fill = np.zeros((J, N), dtype=np.int64)
+        for j, job in enumerate(jobs):
+            need = job.min_replicas
+            for n in range(N):
+                take = min(need, int(self.max_fit[j, n]))
+                self.min_fill[j, n] = take
+                need -= take
+        self.max_replicas = np.array([[job.max_replicas] for job in jobs])
+        self.min_replicas = np.array([job.min_replicas for job in jobs])
+
+    # -- objectives --------------------------------------------------------
+
+    def speedups(self, states):
+        nodes_used = np.count_nonzero(states, axis=2)
+        replicas = states.sum(axis=2)
+        cols = [job.speedup_fn(nodes_used[:, j], replicas[:, j])
+                for j, job in enumerate(self.jobs)]
+        return np.stack(cols, axis=1).astype(float)
+
+    def cluster_sizes(self, states):
+        """Index of the last used node + 1 (nodes are in preference order)."""
+        used = states.any(axis=-2)
+        ordinal = np.arange(states.shape[-1]) + 1
+        return np.where(used, ordinal, 0).max(axis=-1)
+
+    def evaluate(self, states):
+        speedup = self.speedups(states)
+        # a dominant share worth one node <=> speedup 1
+        scaled = speedup * self.dominant_share * len(self.nodes)
+        moved = (states != self.base).any(axis=2)
+        scaled = np.where(moved, scaled * (1.0 - self.restart_penalty),
+                          scaled)
+        return np.column_stack([-scaled.sum(axis=1),
+                                self.cluster_sizes(states)])
+
+    def utilities(self, states):
+        """Average fraction of ideal scaling (speedup / replicas) weighted by
+        each job's share of the most contended resource of the nodes in
+        use."""
+        replicas = states.sum(axis=2)
+        speedup = self.speedups(states)
+        active = states.sum(axis=1) > 0                        # [P, N]
+        total = (active[:, :, None] * self.node_res).sum(axis=1)  # [P, R]
+        alloc = replicas[:, :, None] * self.job_res            # [P, J, R]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            share = np.where(alloc > 0, alloc / total[:, None, :], 0.0)
+            ideal = np.where(replicas > 0, speedup / replicas, 0.0)
+        return (ideal[:, :, None] * share).sum(axis=1).max(axis=1)
+
+    # -- genetic operators ---------------------------------------------------
+
+    def crossover(self, a, b, rng):
+        """Single cut over the job axis; children also inherit a cluster
+        size drawn between the parents' sizes (nodes beyond it emptied)."""
+        pairs, J, N = a.shape
+        cut = rng.integers(J, size=(pairs, 1, 1))
+        take_a = np.arange(J)[None, :, None] < cut
+        children = np.concatenate([np.where(take_a, a, b),
+                                   np.where(take_a, b, a)])
+        size_a, size_b = self.cluster_sizes(a), self.cluster_sizes(b)
+        lo, hi = np.minimum(size_a, size_b), np.maximum(size_a, size_b)
+        lo, hi = np.tile(lo, 2), np.tile(hi, 2)
+        size = lo + rng.integers(1 << 15, size=len(children)) % (hi - lo + 1)
+        beyond = np.arange(N)[None, None, :] >= size[:, None, None]
+        return np.where(beyond, 0, children)
+
+    def mutate(self, states, rng):
+        """Re-draw a few entries within their feasible range; zero and
+        non-zero entries of a row are equally likely to be touched."""
+        states = np.asarray(states)
+        nonzero = np.count_nonzero(states, axis=2, keepdims=True)
+        zero = states.shape[2] - nonzero
+        with np.errstate(divide="ignore"):
+            prob = 1.0 / np.where(states > 0, nonzero, zero)
+        hit = rng.random(states.shape) < prob
+        # a mutation grows the cluster by a geometrically distributed number
+        # of nodes (usually one): unrestricted hits in far columns would erase
+        # every small-cluster candidate and the Pareto front would lose the
+        # sizes that fit the real nodes
+        limit = self.cluster_sizes(states) + rng.geometric(
+            0.5, size=len(states))
+        hit &= np.arange(states.shape[2])[None, None, :] < \
+            limit[:, None, None]
+        draw = rng.integers(self.min_fill, self.max_fit + 1,
+                            size=states.shape)
+        out = np.where(hit, draw, states)
+        return np.maximum(out, self.min_fill)
+
+    def repair(self, states):
+        states = np.array(states, dtype=np.int64, copy=True)
+        P, J, N = states.shape
+        # 1. non-preemptible jobs that already run keep their placement
+        if len(self.pinned):
+            states[:, self.pinned] = self.base[self.pinned]
+        # 2. a node hosts at most one multi-node job (first in job order)
+        spread = np.count_nonzero(states, axis=2) > 1          # [P, J]
+        on_node = (states > 0) & spread[:, :, None]
+        extra = on_node.cumsum(axis=1) > 1
+        states[extra & on_node] = 0
+        # 3. no more than max_replicas per job (trim in random node order)
+        order = np.argsort(np.random.random(states.shape), axis=2)
+        shuffled = np.take_along_axis(states, order, axis=2)
+        capped = np.minimum(shuffled.cumsum(axis=2), self.max_replicas)
+        shuffled = np.diff(capped, axis=2, prepend=0)
+        states = np.take_along_axis(shuffled, np.argsort(order, axis=2),
+                                    axis=2)
+        # 4. node capacities: jobs claim resources in priority order
+        demand = states[:, :, :, None] * self.job_res[None, :, None, :]
+        granted = np.minimum(demand.cumsum(axis=1), self.node_res)
+        granted = np.diff(granted, axis=1, prepend=0)          # [P,J,N,R]
+        per_type = np.where(self.job_res[None, :, None, :] > 0,
+                            granted // np.maximum(
+                                self.job_res[None, :, None, :], 1),
+                            np.iinfo(np.int64).max)
+        states = np.minimum(per_type.min(axis=3), states)
+        # 5. all-or-nothing below min_replicas
+        short = states.sum(axis=2) < self.min_replicas
+        states[short] = 0
+        return states
+
+
+class PolluxPolicy(object):
+
+    def __init__(self, pop_size=POP_SIZE, generations=GENERATIONS, seed=None):
+        self._pop_size = pop_size
+        self._generations = generations
+        self._rng = np.random.default_rng(seed)
+        self._prev_states = None
+        self._prev_jobs = None
+        self._prev_nodes = None
+        self._min_util = MIN_UTIL
+        self._max_util = MAX_UTIL
+
+    # -- single-job fast path ------------------------------------------------
+
+    def allocate_job(self, job_info, nodes):
+        """First node (non-preemptible first) that fits ``min_replicas`` (at
+        least one) replicas of a newly arrived job; ``[]`` if none does.
+        ``nodes`` must already account for every running pod."""
+        want = max(job_info.min_replicas, 1)
+        for name, node in _sorted_nodes(nodes).items():
+            fits = min(node.resources.get(key, 0) // val
+                       for key, val in job_info.resources.items())
+            if fits >= want:
+                return [name] * want
+        return []
+
+    # -- state <-> allocation ------------------------------------------------
+
+    @staticmethod
+    def _allocations_to_state(allocations, jobs, nodes):
+        job_idx = {key: i for i, key in enumerate(jobs)}
+        node_idx = {key: i for i, key in enumerate(nodes)}
+        state = np.zeros((len(jobs), len(nodes)), dtype=np.int64)
+        for key, alloc in allocations.items():
+            if key not in job_idx:
+                continue
+            for node in alloc:
+                if node in node_idx:
+                    state[job_idx[key], node_idx[node]] += 1
+        return state
+
+    @staticmethod
+    def _state_to_allocations(state, jobs, nodes):
+        node_keys = list(nodes)
+        out = {}
+        for j, key in enumerate(jobs):
+            placement = []
+            for n, node in enumerate(node_keys):
+                placement.extend([node] * int(state[j, n]))
+            out[key] = placement
+        return out
+
+    def _warm_start(self, jobs, nodes):
+        """Re-index last cycle's final population onto this cycle's jobs and
+        nodes; nodes that appeared since take over a virtual node's column."""
+        prev = self._prev_states
+        P = prev.shape[0]
+        N = len(nodes)
+        out = np.zeros((P, len(jobs), 2 * N), dtype=np.int64)
+        prev_job = {key: i for i, key in enumerate(self._prev_jobs)}
+        src_rows = [prev_job[k] for k in jobs if k in prev_job]
+        dst_rows = [i for i, k in enumerate(jobs) if k in prev_job]
+        if not src_rows:
+            return out
+        prev_node = {key: i for i, key in enumerate(self._prev_nodes)}
+        spare = len(self._prev_nodes)         # next unused virtual column
+        width = prev.shape[2]
+        for col in range(2 * N):
+            key = list(nodes)[col] if col < N else None
+            if key is not None and key in prev_node:
+                src = prev_node[key]
+            elif spare < width:
+                src = spare
+                spare += 1
+            else:
+                continue
+            out[:, dst_rows, col] = prev[:, src_rows, src]
+        return out
+
+    # -- choosing from the Pareto front -------------------------------------------
+
+    @staticmethod
+    def _best_within(values, max_nodes):
+        ok = values[:, 1] <= max_nodes
+        if not ok.any():
+            return None
+        return int(np.argmin(np.where(ok, values[:, 0], 0.0)))
+
+    def _desired_nodes(self, utilities, values, num_nodes):
+        idx = self._best_within(values, num_nodes)
+        if idx is not None and \
+                self._min_util <= utilities[idx] <= self._max_util:
+            return num_nodes
+        target = (self._min_util + self._max_util) / 2
+        best_util, best_nodes = np.inf, num_nodes
+        for util, (_, size) in zip(utilities, values):
+            if util < self._min_util:
+                continue
+            if np.isclose(util, best_util) and size > best_nodes:
+                best_nodes = size
+            if abs(util - target) < abs(best_util - target):
+                best_util, best_nodes = util, size
+        return int(best_nodes)
+
+    # -- the optimisation cycle ------------------------------------------------
+
+    def optimize(self, jobs, nodes, base_allocations, node_template):
+        """One scheduling cycle.
+
+        Arguments:
+            jobs (dict): job key -> :class:`JobInfo` of every incomplete job.
+            nodes (dict): node key -> :class:`NodeInfo`; resources net of
+                non-adaptdl pods only.
+            base_allocations (dict): job key -> current allocation (list with
+                one node key per replica).
+            node_template (NodeInfo): a node the cluster autoscaler could add.
+
+        Returns ``(allocations, desired_nodes)``.
+        """
+        def pinned(key, job):
+            return not job.preemptible and bool(base_allocations.get(key))
+
+        # pinned jobs first (their placement is fixed), then fewer guaranteed
+        # replicas first, then FIFO
+        jobs = collections.OrderedDict(sorted(
+            jobs.items(), key=lambda kv: (not pinned(kv[0], kv[1]),
+                                          kv[1].min_replicas,
+                                          kv[1].creation_timestamp)))
+        nodes = _sorted_nodes(nodes)
+        N = len(nodes)
+        base = np.concatenate(
+            [self._allocations_to_state(base_allocations, jobs, nodes),
+             np.zeros((len(jobs), N), dtype=np.int64)], axis=1)
+        if self._prev_states is None:
+            initial = base[None]
+        else:
+            initial = np.concatenate([self._warm_start(jobs, nodes),
+                                      base[None]])
+        problem = ClusterProblem(list(jobs.values()),
+                                 list(nodes.values()) + [node_template] * N,
+                                 base)
+        states, values = nsga2.minimize(problem, initial, self._pop_size,
+                                        self._generations, self._rng)
+        self._prev_states = states.copy()
+        self._prev_jobs = list(jobs)
+        self._prev_nodes = list(nodes)
+        front = nsga2.non_dominated_fronts(values)[0]
+        states, values = states[front], values[front]
+        utilities = problem.utilities(states)
+        desired = self._desired_nodes(utilities, values, N)
+        idx = self._best_within(values, min(N, desired))
+        if LOG.isEnabledFor(logging.DEBUG):
+            for i, state in enumerate(states):
+                LOG.debug("solution %d value=%s utility=%.3f\n%s", i,
+                          values[i].tolist(), utilities[i], state)
+        if idx is None:
+            return {}, desired
+        return self._state_to_allocations(states[idx][:, :N], jobs,
+                                          nodes), desired
+
+
+_ = copy

@@ -1,0 +1,202 @@
+"""Scheduling policy: NSGA-II, speedup memoisation, Pollux allocation
+invariants (ideas from the reference's policy/*_test.py)."""
+import copy
+import random
+from collections import Counter
+from datetime import datetime, timedelta
+from unittest.mock import Mock
+
+import numpy as np
+import pytest
+
+from adaptdl_b200.goodput import GoodputFunction, GradParams, PerfParams
+from adaptdl_b200.sched.policy import (JobInfo, NodeInfo, PolluxPolicy,
+                                       SpeedupFunction)
+from adaptdl_b200.sched.policy import nsga2
+
+PERF = PerfParams(0.121, 0.00568, 0.0236, 0.00634, 0.0118, 0.00317, 1.14)
+GRAD = GradParams(sqr=0.00136, var=0.000502)
+
+
+def _speedup_fn():
+    return SpeedupFunction(GoodputFunction(PERF, GRAD, 128),
+                           max_batch_size=1280, atomic_bsz_range=(64, 256))
+
+
+def test_non_dominated_fronts_and_crowding():
+    F = np.array([[1, 5], [2, 2], [5, 1], [3, 3], [6, 6], [2, 2]], float)
+    fronts = nsga2.non_dominated_fronts(F)
+    assert sorted(fronts[0].tolist()) == [0, 1, 2, 5]
+    assert sorted(fronts[1].tolist()) == [3]
+    assert sorted(fronts[2].tolist()) == [4]
+    d = nsga2.crowding_distance(F[[0, 1, 2]])
+    assert np.isinf(d[0]) and np.isinf(d[2]) and np.isfinite(d[1])
+
+
+def test_nsga2_finds_pareto_front_of_toy_problem():
+    # genome: one integer x in [0, 20]; objectives (x^2, (x-10)^2):
+    # the Pareto set is x in [0, 10]
+    class Toy:
+        def evaluate(self, X):
+            x = X[:, 0].astype(float)
+            return np.column_stack([x ** 2, (x - 10) ** 2])
+
+        def crossover(self, a, b, rng):
+            mix = (a + b) // 2
+            return np.concatenate([mix, np.maximum(a, b)])
+
+        def mutate(self, X, rng):
+            return X + rng.integers(-2, 3, size=X.shape)
+
+        def repair(self, X):
+            return np.clip(X, 0, 20)
+    X, F = nsga2.minimize(Toy(), np.array([[20]]), pop_size=24, n_gen=40,
+                          rng=np.random.default_rng(0))
+    front = nsga2.non_dominated_fronts(F)[0]
+    xs = set(X[front, 0].tolist())
+    assert xs <= set(range(0, 11)) and len(xs) >= 8
+
+
+def test_speedup_memoization():
+    goodput_fn = Mock()
+    calls = []
+
+    def optimize(num_nodes, num_replicas, **kw):
+        calls.append(np.size(num_replicas))
+        r = np.asarray(num_replicas, dtype=float)
+        return r, r.astype(int), np.zeros_like(r, dtype=int)
+    goodput_fn.optimize.side_effect = optimize
+    fn = SpeedupFunction(goodput_fn, mem_size=8)
+    assert calls == [1]                       # the (1, 1) baseline
+    assert fn(1, 3) == pytest.approx(3.0)
+    assert fn(1, 3) == pytest.approx(3.0)     # memoised: no new call
+    assert len(calls) == 2
+    out = fn(np.array([1, 1, 2, 0]), np.array([3, 4, 4, 0]))
+    assert out.tolist() == pytest.approx([3.0, 4.0, 4.0, 0.0])
+    assert calls[-1] == 2                     # only the 2 unseen pairs
+    assert fn(2, 16) == pytest.approx(16.0)   # beyond the table: computed
+    assert fn(2, 16) == pytest.approx(16.0)
+    assert len(calls) == 5
+
+
+def test_speedup_realistic_is_sublinear_and_monotone():
+    fn = _speedup_fn()
+    replicas = np.arange(1, 17)
+    single = fn(np.ones_like(replicas), replicas)
+    assert single[0] == pytest.approx(1.0)
+    assert np.all(np.diff(single[:8]) >= -1e-9)   # retrogression later
+    assert np.all(single <= replicas + 1e-9)
+    multi = fn(np.minimum(replicas, 4), replicas)
+    assert np.all(multi[1:] <= single[1:] + 1e-9)   # crossing nodes costs
+
+
+@pytest.mark.parametrize("num_nodes", [1, 2, 4, 8, 16])
+def test_optimize_respects_capacities(num_nodes, total_devices=16):
+    num_devices = total_devices // num_nodes
+    speedup_fn = _speedup_fn()
+    now = datetime.now()
+    jobs = {}
+    for i in range(16):
+        jobs[i] = JobInfo({"nvidia.com/gpu": 1, "pods": 1}, speedup_fn,
+                          now + timedelta(minutes=i), 0, 8)
+    node_resources = {"nvidia.com/gpu": num_devices, "pods": 32}
+    nodes = {i: NodeInfo(node_resources, preemptible=False)
+             for i in range(num_nodes)}
+    template = NodeInfo(node_resources, preemptible=True)
+    policy = PolluxPolicy(generations=30, seed=0)
+    prev = {}
+    for cycle in range(3):
+        allocations, desired = policy.optimize(jobs, nodes, prev, template)
+        assert desired >= 1
+        per_node = Counter()
+        for key, placement in allocations.items():
+            assert len(placement) <= jobs[key].max_replicas
+            per_node.update(placement)
+            # at most one multi-node job per node is checked below
+        for node, count in per_node.items():
+            assert count <= nodes[node].resources["nvidia.com/gpu"]
+        spread = {k: set(v) for k, v in allocations.items()
+                  if len(set(v)) > 1}
+        for node in nodes:
+            assert sum(node in s for s in spread.values()) <= 1
+        assert sum(len(v) for v in allocations.values()) > 0
+        prev = allocations
+
+
+def test_allocate_job():
+    nodes = {
+        "0": NodeInfo({"gpu": 1, "cpu": 500, "pods": 32}, preemptible=False),
+        "1": NodeInfo({"gpu": 2, "cpu": 2000, "pods": 32}, preemptible=False),
+        "2": NodeInfo({"gpu": 2, "cpu": 3000, "pods": 32}, preemptible=True),
+    }
+    fn = _speedup_fn()
+    now = datetime.now()
+    job_1 = JobInfo({"gpu": 1, "cpu": 500, "pods": 1}, fn, now, 0, 1)
+    job_2 = JobInfo({"gpu": 1, "cpu": 1000, "pods": 1}, fn, now, 0, 1)
+    job_3 = JobInfo({"gpu": 1, "cpu": 1000, "pods": 1}, fn, now, 2, 2)
+    job_4 = JobInfo({"gpu": 1, "cpu": 2000, "pods": 1}, fn, now, 2, 2)
+    policy = PolluxPolicy()
+    assert policy.allocate_job(job_1, nodes) == ["0"]
+    assert policy.allocate_job(job_2, nodes) == ["1"]
+    assert policy.allocate_job(job_3, nodes) == ["1", "1"]
+    assert policy.allocate_job(job_4, nodes) == []
+
+
+def test_unusable_node_asks_for_more_nodes():
+    nodes = {
+        0: NodeInfo({"gpu": 1, "cpu": 500, "pods": 32}, preemptible=False),
+        1: NodeInfo({"gpu": 1, "cpu": 8000, "pods": 32}, preemptible=False),
+        2: NodeInfo({"gpu": 1, "cpu": 8000, "pods": 32}, preemptible=False),
+    }
+    template = NodeInfo({"gpu": 1, "cpu": 8000, "pods": 32}, preemptible=True)
+    fn = _speedup_fn()
+    now = datetime.now()
+    jobs = {i: JobInfo({"gpu": 1, "cpu": 1000, "pods": 1}, fn,
+                       now + timedelta(minutes=i), 0, 1) for i in range(3)}
+    policy = PolluxPolicy(seed=1)
+    allocations, desired = policy.optimize(jobs, nodes, {}, template)
+    assert desired > 3
+    assert max(len(a) for a in allocations.values()) == 1
+    assert sum(len(a) for a in allocations.values()) == 2
+
+
+@pytest.mark.parametrize("num_nodes", [1, 2, 4, 8])
+def test_non_preemptible_jobs_keep_their_allocation(num_nodes,
+                                                    total_devices=16):
+    random.seed(num_nodes)
+    ids = list(range(10))
+    random.shuffle(ids)
+    preemptible, fixed = ids[:5], ids[5:]
+    num_devices = total_devices // num_nodes
+    fn = _speedup_fn()
+    now = datetime.now()
+    policy = PolluxPolicy(generations=30, seed=num_nodes)
+    res = {"nvidia.com/gpu": 1, "pods": 1}
+    node_res = {"nvidia.com/gpu": num_devices, "pods": 32}
+    nodes = {i: NodeInfo(node_res, preemptible=False)
+             for i in range(num_nodes)}
+    template = NodeInfo(node_res, preemptible=True)
+    prev = {i: [] for i in ids}
+    for cycle in range(3):
+        jobs = {}
+        for i in preemptible:
+            jobs[i] = JobInfo(res, fn, now + timedelta(minutes=i), 0, 8)
+        for i in fixed:
+            jobs[i] = JobInfo(res, fn, now + timedelta(minutes=i), 2, 4,
+                              preemptible=False)
+        allocations, _ = policy.optimize(jobs, nodes, prev, template)
+        per_node = Counter()
+        for key, placement in allocations.items():
+            assert len(placement) <= jobs[key].max_replicas
+            if placement:
+                assert len(placement) >= jobs[key].min_replicas
+            per_node.update(placement)
+        for node, count in per_node.items():
+            assert count <= nodes[node].resources["nvidia.com/gpu"]
+        for i in fixed:
+            if i in allocations and prev.get(i):
+                assert sorted(allocations[i]) == sorted(prev[i])
+        prev = copy.deepcopy(allocations)
+        victim = random.choice(sorted(allocations))
+        (fixed if victim in fixed else preemptible).remove(victim)
+        prev.pop(victim)
