@@ -1,0 +1,295 @@
+"""Single-box elastic launcher: AdaptDL scheduling without Kubernetes.
+
+Runs ONE elastic job on the GPUs of this machine. Each replica is a process
+with the same ``ADAPTDL_*`` contract a pod would get
+(:func:`adaptdl_b200.sched.controller.build_pod`); a rescale is what it is
+on a cluster -- SIGTERM every replica, they agree on the step, checkpoint and
+exit with code 143, and the next generation starts at the new replica count
+with ``ADAPTDL_NUM_RESTARTS + 1`` (peer GPU mappings are rebuilt by the new
+processes at the new world size).
+
+The replica count comes either from a fixed schedule (``--schedule
+2,4,8,4 --interval 20``: benchmark config "elastic rescale 2->4->8->4") or
+from the job's own scheduling hints: an embedded supervisor receives
+``PUT /hints``, builds the goodput speedup function and picks the count that
+maximises speedup among the GPUs available (the single-job specialisation of
+the Pollux policy; 5 % hysteresis like the reference's Ray-AWS optimiser,
+``ray/adaptdl_ray/aws/optimizer.py:70-94``).
+
+    python -m adaptdl_b200.sched.local --gpus 8 --schedule 2,4,8,4 \
+        --interval 20 examples/transformer/transformer.py --epochs 5
+"""
+
+import argparse
+import json
+import logging
+import os
+import signal
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+from adaptdl_b200.goodput import GoodputFunction, GradParams, PerfParams
+from adaptdl_b200.sched.policy import SpeedupFunction
+from adaptdl_b200.sched_hints import PERF_PARAMS, SCHED_HINTS
+from adaptdl_b200.utils import pick_unused_port
+
+LOG = logging.getLogger(__name__)
+EXIT_PREEMPTED = 143
+
+
+class HintsServer(object):
+    """Tiny supervisor: ``PUT /hints/<job>`` and ``GET /discover/...`` (all
+    replicas are local, so discovery always answers 127.0.0.1)."""
+
+    def __init__(self):
+        from http.server import BaseHTTPRequestHandler, ThreadingHTTPServer
+        outer = self
+        self.hints = None
+        self.replicas = 1
+
+        class Handler(BaseHTTPRequestHandler):
+            def log_message(self, *args):     # quiet
+                pass
+
+            def do_GET(self):
+                if self.path.startswith("/discover/"):
+                    body = json.dumps(["127.0.0.1"] * outer.replicas)
+                    self._reply(200, body)
+                else:
+                    self._reply(200, "")
+
+            def do_PUT(self):
+                length = int(self.headers.get("Content-Length", 0))
+                try:
+                    hints = json.loads(self.rfile.read(length) or b"{}")
+                    outer.hints = {k: hints[k] for k in SCHED_HINTS
+                                   if k in hints}
+                    self._reply(200, "")
+                except ValueError:
+                    self._reply(400, "")
+
+            def _reply(self, code, body):
+                data = body.encode()
+                self.send_response(code)
+                self.send_header("Content-Type", "application/json")
+                self.send_header("Content-Length", str(len(data)))
+                self.end_headers()
+                self.wfile.write(data)
+        self._server = ThreadingHTTPServer(("127.0.0.1", 0), Handler)
+        self.url = "http://127.0.0.1:{}".format(self._server.server_port)
+        threading.Thread(target=self._server.serve_forever,
+                         daemon=True).start()
+
+    def close(self):
+        self._server.shutdown()
+
+
+def best_replicas(hints, max_replicas, current, hysteresis=0.05):
+    """Replica count in ``[1, max_replicas]`` with the best goodput speedup
+    according to the job's hints; keeps ``current`` unless the best is more
+    than ``hysteresis`` better. Exploration is capped at twice the largest
+    profiled count (like the cluster allocator)."""
+    if not hints or not hints.get("perfParams") or \
+            not hints.get("initBatchSize"):
+        return current
+    perf = PerfParams(*[hints["perfParams"][k] for k in PERF_PARAMS])
+    grad = hints.get("gradParams")
+    grad = GradParams(grad["norm"], grad["var"]) if grad \
+        else GradParams(0.0, 1.0)
+    bounds = hints.get("localBszBounds")
+    fn = SpeedupFunction(
+        GoodputFunction(perf, grad, hints["initBatchSize"]),
+        hints.get("maxBatchSize"), tuple(bounds) if bounds else None,
+        hints.get("gradientAccumulation", False))
+    cap = min(max_replicas, max(2 * hints.get("maxProfiledReplicas", 1), 1))
+    speedups = {n: fn(1, n) for n in range(1, cap + 1)}
+    best = max(speedups, key=lambda n: (speedups[n], -n))
+    if current in speedups and \
+            speedups[best] <= speedups[current] * (1 + hysteresis):
+        return current
+    return best
+
+
+class LocalElasticJob(object):
+    """One elastic job on this machine's GPUs."""
+
+    def __init__(self, command, max_replicas, checkpoint_dir=None,
+                 job_id="local/job", env=None, gpu_ids=None):
+        self.command = list(command)
+        self.max_replicas = max_replicas
+        self.checkpoint_dir = checkpoint_dir or tempfile.mkdtemp(
+            prefix="adaptdl-b200-ckpt-")
+        self.job_id = job_id
+        self.extra_env = dict(env or {})
+        self.gpu_ids = list(gpu_ids) if gpu_ids is not None else None
+        self.num_restarts = 0
+        self.replicas = 0
+        self.procs = []
+        self.server = HintsServer()
+        self.events = []             # (time, what, detail) for reports
+
+    def _log(self, what, **detail):
+        self.events.append((time.time(), what, detail))
+        LOG.info("%s %s", what, detail)
+
+    def start(self, replicas):
+        assert not self.procs
+        port = pick_unused_port()
+        self.replicas = self.server.replicas = replicas
+        for rank in range(replicas):
+            env = dict(os.environ)
+            env.update(self.extra_env)
+            env.update({
+                "ADAPTDL_JOB_ID": self.job_id,
+                "ADAPTDL_CHECKPOINT_PATH": self.checkpoint_dir,
+                "ADAPTDL_MASTER_ADDR": "127.0.0.1",
+                "ADAPTDL_MASTER_PORT": str(port),
+                "ADAPTDL_NUM_NODES": "1",
+                "ADAPTDL_NUM_REPLICAS": str(replicas),
+                "ADAPTDL_REPLICA_RANK": str(rank),
+                "ADAPTDL_NUM_RESTARTS": str(self.num_restarts),
+                "ADAPTDL_SUPERVISOR_URL": "",
+                "ADAPTDL_LOCAL_RANK": str(
+                    self.gpu_ids[rank] if self.gpu_ids else rank),
+                "ADAPTDL_HINTS_URL": self.server.url,
+            })
+            for stale in ("RANK", "WORLD_SIZE", "LOCAL_RANK",
+                          "MASTER_ADDR", "MASTER_PORT"):
+                env.pop(stale, None)
+            self.procs.append(subprocess.Popen(self.command, env=env))
+        self._log("started", replicas=replicas, generation=self.num_restarts)
+
+    def poll(self):
+        """``None`` while running; else ``"finished"`` / ``"preempted"`` /
+        ``"failed"`` once every replica has exited."""
+        codes = [p.poll() for p in self.procs]
+        if any(c is None for c in codes):
+            if any(c not in (None, 0, EXIT_PREEMPTED) for c in codes):
+                self.kill()
+                return "failed"
+            return None
+        self.procs = []
+        if all(c == 0 for c in codes):
+            return "finished"
+        if all(c in (0, EXIT_PREEMPTED) for c in codes):
+            return "preempted"
+        return "failed"
+
+    def signal_stop(self):
+        for p in self.procs:
+            if p.poll() is None:
+                p.send_signal(signal.SIGTERM)
+
+    def kill(self):
+        for p in self.procs:
+            if p.poll() is None:
+                p.kill()
+        for p in self.procs:
+            p.wait()
+        self.procs = []
+
+    def rescale(self, replicas, timeout=300.0):
+        """SIGTERM -> wait for the checkpoint exit -> start the next
+        generation. Returns the state (``"running"`` / ``"finished"`` /
+        ``"failed"``)."""
+        t0 = time.time()
+        self.signal_stop()
+        deadline = t0 + timeout
+        state = None
+        while state is None and time.time() < deadline:
+            state = self.poll()
+            if state is None:
+                time.sleep(0.05)
+        if state is None:
+            self.kill()
+            state = "failed"
+        self._log("stopped", state=state, seconds=time.time() - t0)
+        if state != "preempted":
+            return state
+        self.num_restarts += 1
+        self.start(replicas)
+        self._log("rescaled", replicas=replicas,
+                  seconds=time.time() - t0)
+        return "running"
+
+    def run(self, schedule=None, interval=30.0, adaptive=False,
+            initial=None):
+        """Run to completion. ``schedule``: replica counts applied every
+        ``interval`` seconds (the last one stays); ``adaptive``: follow the
+        job's hints instead."""
+        schedule = list(schedule or [])
+        first = initial or (schedule.pop(0) if schedule else 1)
+        self.start(min(first, self.max_replicas))
+        next_change = time.time() + interval
+        try:
+            while True:
+                state = self.poll()
+                if state in ("finished", "failed"):
+                    self._log(state)
+                    return state
+                if state == "preempted":          # exited on its own signal
+                    self.num_restarts += 1
+                    self.start(self.replicas)
+                if time.time() >= next_change:
+                    next_change = time.time() + interval
+                    target = self.replicas
+                    if schedule:
+                        target = min(schedule.pop(0), self.max_replicas)
+                    elif adaptive:
+                        target = best_replicas(self.server.hints,
+                                               self.max_replicas,
+                                               self.replicas)
+                    if target != self.replicas:
+                        state = self.rescale(target)
+                        if state != "running":
+                            self._log(state)
+                            return state
+                time.sleep(0.1)
+        finally:
+            self.kill()
+            self.server.close()
+
+
+def main(argv=None):
+    parser = argparse.ArgumentParser(
+        description="run an elastic adaptdl_b200 job on this box")
+    parser.add_argument("--gpus", type=int, default=None,
+                        help="GPUs (max replicas); default: all visible")
+    parser.add_argument("--schedule", default="",
+                        help="comma-separated replica counts, e.g. 2,4,8,4")
+    parser.add_argument("--interval", type=float, default=30.0)
+    parser.add_argument("--adaptive", action="store_true",
+                        help="choose the replica count from the job's hints")
+    parser.add_argument("--checkpoint-dir", default=None)
+    parser.add_argument("--report", default=None,
+                        help="write the event log (JSON) here")
+    parser.add_argument("script", nargs=argparse.REMAINDER)
+    args = parser.parse_args(argv)
+    logging.basicConfig(level=logging.INFO)
+    if not args.script:
+        parser.error("missing training script")
+    gpus = args.gpus
+    if gpus is None:
+        try:
+            import torch
+            gpus = max(torch.cuda.device_count(), 1)
+        except Exception:  # noqa: BLE001
+            gpus = 1
+    command = args.script
+    if command[0].endswith(".py"):
+        command = [sys.executable] + command
+    job = LocalElasticJob(command, gpus, args.checkpoint_dir)
+    schedule = [int(x) for x in args.schedule.split(",") if x]
+    state = job.run(schedule, args.interval, args.adaptive)
+    if args.report:
+        with open(args.report, "w") as f:
+            json.dump([{"t": t, "event": what, **detail}
+                       for t, what, detail in job.events], f, indent=1)
+    return 0 if state == "finished" else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())

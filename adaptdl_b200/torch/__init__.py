@@ -135,5 +135,10 @@ def init_process_group(backend, init_method=None, world_size=None,
     LOG.info("Initializing torch.distributed using %s", store_url)
     if str(backend).startswith("nccl") and torch.cuda.is_available():
         torch.cuda.set_device(env.local_rank() % torch.cuda.device_count())
+    # Under torchrun the elastic agent hosts the rendezvous store and sets
+    # TORCHELASTIC_USE_AGENT_STORE, which makes rank 0 NOT start a server for
+    # a fresh tcp:// URL (every rank would wait forever): we bring our own
+    # store (port agreed over the control plane), so opt out of the agent's.
+    os.environ.pop("TORCHELASTIC_USE_AGENT_STORE", None)
     torch.distributed.init_process_group(backend, store_url)
     LOG.info("torch.distributed initialized")

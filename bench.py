@@ -62,6 +62,10 @@ def setup_env(args):
     base_port = int(os.environ.get("MASTER_PORT", "29400"))
     os.environ["ADAPTDL_MASTER_PORT"] = str(base_port + 1)
     os.environ.pop("ADAPTDL_CHECKPOINT_PATH", None)
+    # both frameworks rendezvous over their own tcp:// store (port agreed on
+    # their control plane); torchrun's agent-store flag would stop rank 0
+    # from hosting it
+    os.environ.pop("TORCHELASTIC_USE_AGENT_STORE", None)
     return rank, world, local_rank
 
 
