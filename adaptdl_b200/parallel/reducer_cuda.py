@@ -397,10 +397,25 @@ class CudaGradReducer(GradReducer):
 
     # -- broadcast -----------------------------------------------------------
 
+    @staticmethod
+    def _memory_bytes(t):
+        """The tensor's bytes in memory order (layouts are identical on all
+        ranks, so broadcasting memory order preserves e.g. channels_last)."""
+        t = t.detach()
+        if t.is_contiguous():
+            flat = t.reshape(-1)
+        else:
+            from adaptdl_b200.parallel.reducer_base import _is_dense
+            if not _is_dense(t):
+                raise ValueError("broadcast needs dense tensors")
+            flat = t.as_strided((t.numel(),), (1,))
+        return flat.view(torch.uint8)
+
     def broadcast_parameters(self, tensors, src=0):
         if self.world_size <= 1:
             return
-        tensors = [t for t in tensors if t is not None and t.numel() > 0]
+        tensors = [self._memory_bytes(t) for t in tensors
+                   if t is not None and t.numel() > 0]
         stream = torch.cuda.current_stream(self.device)
         chunk, chunk_bytes = [], 0
 
@@ -408,8 +423,7 @@ class CudaGradReducer(GradReducer):
             nonlocal chunk, chunk_bytes
             if not chunk:
                 return
-            flat = torch.cat([t.detach().reshape(-1).view(torch.uint8)
-                              for t in chunk])
+            flat = torch.cat(chunk)
             n = flat.numel()
             n_pad = _round_up(n, 16)
             if self.rank == src:
@@ -433,21 +447,17 @@ class CudaGradReducer(GradReducer):
             if self.rank != src:
                 cursor = 0
                 for t in chunk:
-                    nb = t.numel() * t.element_size()
-                    t.detach().reshape(-1).view(torch.uint8).copy_(
-                        self._staging[cursor:cursor + nb])
+                    nb = t.numel()
+                    t.copy_(self._staging[cursor:cursor + nb])
                     cursor += nb
             chunk, chunk_bytes = [], 0
 
         for t in tensors:
-            if not t.is_contiguous():
-                raise ValueError("broadcast needs contiguous tensors")
-            nb = t.numel() * t.element_size()
+            nb = t.numel()
             if nb > _STAGING_BYTES:
                 flush()
-                flat = t.detach().reshape(-1).view(torch.uint8)
                 for lo in range(0, nb, _STAGING_BYTES):
-                    piece = flat[lo:lo + _STAGING_BYTES]
+                    piece = t[lo:lo + _STAGING_BYTES]
                     chunk, chunk_bytes = [piece], piece.numel()
                     flush()
                 continue

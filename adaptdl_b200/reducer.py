@@ -89,11 +89,11 @@ class _Server(threading.Thread):
         self._listener.bind(("0.0.0.0", port))
         self._listener.listen(max(replicas, 8))
         self.port = self._listener.getsockname()[1]
-        self._stop = threading.Event()
+        self._stop_event = threading.Event()
         self.error = None
 
     def stop(self):
-        self._stop.set()
+        self._stop_event.set()
         try:
             self._listener.close()
         except OSError:
@@ -120,7 +120,7 @@ class _Server(threading.Thread):
                 sel.register(conn, selectors.EVENT_READ, rank)
             pending = {}                         # key -> {rank: obj}
             alive = self._replicas
-            while alive and not self._stop.is_set():
+            while alive and not self._stop_event.is_set():
                 for skey, _ in sel.select(timeout=0.5):
                     conn, rank = skey.fileobj, skey.data
                     try:
@@ -135,7 +135,7 @@ class _Server(threading.Thread):
                         del pending[key]
                         self._finish(key, slot, clients)
         except Exception as exc:  # noqa: BLE001 - surfaced to clients
-            if not self._stop.is_set():
+            if not self._stop_event.is_set():
                 self.error = exc
                 LOG.exception("control-plane reducer server failed")
         finally:

@@ -69,7 +69,7 @@ class ElasticSampler(Sampler):
         if not self.shuffle:
             return list(range(n))
         gen = torch.Generator()
-        gen.manual_seed(_shuffle_seed(self.epoch, self.index // n))
+        gen.manual_seed(_shuffle_seed(self.epoch or 0, self.index // n))
         return torch.randperm(n, generator=gen).tolist()
 
     def __iter__(self):
@@ -467,7 +467,7 @@ class AdaptiveDataLoader(DataLoader, AdaptiveDataLoaderMixin):
                             num_replicas * self.batch_sampler.batch_size
                         if elastic.max_batch_size is not None and \
                                 _metrics.get_progress() >= \
-                                len(self.dataset) * (epoch + 1) \
+                                len(self.dataset) * ((epoch or 0) + 1) \
                                 / self.batch_size:
                             done = True
                             break

@@ -21,16 +21,20 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def timed(fn, iters, warmup=5):
+def timed(fn, iters, warmup=5, stream=None):
+    """Device time per call (max over ranks); events are recorded on the
+    stream the kernels actually run on."""
+    stream = stream or torch.cuda.current_stream()
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()
     dist.barrier()
+    torch.cuda.synchronize()
     start, end = torch.cuda.Event(True), torch.cuda.Event(True)
-    start.record()
+    start.record(stream)
     for _ in range(iters):
         fn()
-    end.record()
+    end.record(stream)
     torch.cuda.synchronize()
     ms = torch.tensor([start.elapsed_time(end) / iters], device="cuda")
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -63,7 +67,7 @@ def main():
         nbytes = bucket.length * 4
         iters = 200 if mb <= 4 else 40
         fused = timed(lambda: red._reduce(arena, bucket, 1.0 / world, True),
-                      iters)
+                      iters, stream=red._comm)
         flat = torch.randn(bucket.length, device=dev)
         nccl = timed(lambda: dist.all_reduce(flat), iters)
 

@@ -18,15 +18,18 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def timed(fn, iters=20, warmup=5):
+def timed(fn, iters=20, warmup=5, stream=None):
+    """Device time per call; events are recorded on the stream the kernels
+    actually run on (the reducer's communication stream)."""
+    stream = stream or torch.cuda.current_stream()
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()
     start, end = torch.cuda.Event(True), torch.cuda.Event(True)
-    start.record()
+    start.record(stream)
     for _ in range(iters):
         fn()
-    end.record()
+    end.record(stream)
     torch.cuda.synchronize()
     return start.elapsed_time(end) / iters
 
@@ -80,11 +83,12 @@ def main():
 
     red._ensure(arena, "acc")
     red._ensure(arena, "prev")
-    report("pair_norm_stash (F2)", timed(lambda: red._pair(arena, bucket)), 3)
-    report("fold_acc", timed(lambda: red._fold_acc(arena, bucket)), 4)
-    report("fold_final", timed(lambda: red._fold_final(arena, bucket)), 4)
+    report("pair_norm_stash (F2)", timed(lambda: red._pair(arena, bucket), stream=red._comm), 3)
+    report("fold_acc", timed(lambda: red._fold_acc(arena, bucket), stream=red._comm), 4)
+    report("fold_final", timed(lambda: red._fold_final(arena, bucket), stream=red._comm), 4)
     report("allreduce_gns world=1",
-           timed(lambda: red._reduce(arena, bucket, 0.5, False)), 2)
+           timed(lambda: red._reduce(arena, bucket, 0.5, False),
+                 stream=red._comm), 2)
     report("fused_sgd (F4)", timed(engine.optimizer_step), 5)
     src = torch.empty_like(arena.grad)
     report("torch copy_ (reference)", timed(lambda: src.copy_(arena.grad)), 2)
@@ -92,7 +96,7 @@ def main():
 
     def fin():
         red._finalize_step()
-    ms = timed(fin, iters=50)
+    ms = timed(fin, iters=50, stream=red._comm)
     results["finalize+estimator (62 groups)"] = {"ms": ms}
     print("{:<26s} {:8.3f} ms (latency-bound, one CTA)".format(
         "finalize+estimator", ms))
