@@ -1,0 +1,41 @@
+"""Ray integration (optional: needs ``ray[tune]``, which is not a hard
+dependency): a Tune trial scheduler that rescales elastic trials with the
+Pollux policy (``tune/``), and a single-job elastic controller for Ray
+clusters on AWS spot instances (``aws/``). Reference: ``ray/adaptdl_ray``.
+
+Everything that does not strictly need Ray (allocation <-> placement-group
+arithmetic, the single-job replica optimiser, checkpoint (de)serialisation,
+the spot-termination poller) is importable and tested without it."""
+
+import os
+
+
+def have_ray():
+    try:
+        import ray  # noqa: F401
+        return True
+    except ImportError:
+        return False
+
+
+def require_ray():
+    if not have_ray():
+        raise ImportError("this feature needs the optional 'ray[tune]' "
+                          "package")
+    import ray
+    return ray
+
+
+def tune_checkpoint_dir(for_save):
+    """Checkpoint directory under Ray Tune (used by
+    ``adaptdl_b200.checkpoint`` when ``ADAPTDL_TUNE_TRIAL_SCHED`` is set)."""
+    if for_save:
+        path = os.path.join("/tmp", "adaptdl-tune-ckpt-{}".format(
+            os.getpid()))
+        os.makedirs(path, exist_ok=True)
+        return path
+    try:
+        from ray.tune import session
+        return session.get_session().get_checkpoint()
+    except Exception:  # noqa: BLE001
+        return None

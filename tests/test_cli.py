@@ -1,0 +1,81 @@
+"""CLI manifest construction (pure functions)."""
+from datetime import datetime
+
+import pytest
+
+from adaptdl_b200.cli import manifests
+from adaptdl_b200.cli.main import build_parser
+
+JOB = {"apiVersion": "adaptdl.petuum.com/v1", "kind": "AdaptDLJob",
+       "metadata": {"name": "cifar"},
+       "spec": {"maxReplicas": 8, "template": {"spec": {"containers": [
+           {"name": "main", "command": ["python3", "main.py"]}]}}}}
+
+
+def test_prepare_job_injects_volumes_and_env():
+    job, pvc = manifests.prepare_job(JOB, "repo/img@sha256:abc",
+                                     ["--epochs", "3"], name="run",
+                                     pull_secret="creds", tensorboard="tb1",
+                                     pvc_name="adaptdl-pvc-x")
+    assert pvc == "adaptdl-pvc-x"
+    assert job["metadata"] == {"generateName": "run-"}
+    spec = job["spec"]["template"]["spec"]
+    main = spec["containers"][0]
+    assert main["image"] == "repo/img@sha256:abc"
+    assert main["args"] == ["--epochs", "3"]
+    assert spec["imagePullSecrets"] == [{"name": "creds"}]
+    env = {e["name"]: e["value"] for e in main["env"]}
+    assert env == {"ADAPTDL_TENSORBOARD_LOGDIR": "/adaptdl/tensorboard",
+                   "ADAPTDL_CHECKPOINT_PATH": "/adaptdl/checkpoint",
+                   "ADAPTDL_SHARE_PATH": "/adaptdl/share"}
+    mounts = {m["mountPath"]: m for m in main["volumeMounts"]}
+    assert mounts["/adaptdl/checkpoint"]["subPath"] == "adaptdl/checkpoint"
+    assert mounts["/adaptdl/share"]["subPath"] == "adaptdl/share"
+    claims = {v["name"]: v["persistentVolumeClaim"]["claimName"]
+              for v in spec["volumes"]}
+    assert claims == {"adaptdl-tensorboard": "adaptdl-tensorboard-tb1",
+                      "adaptdl-pvc": "adaptdl-pvc-x"}
+    assert "volumes" not in JOB["spec"]["template"]["spec"]   # not mutated
+
+
+def test_storageclass_choice_and_manifests():
+    classes = [
+        {"metadata": {"name": "gp2", "annotations": {
+            "storageclass.kubernetes.io/is-default-class": "true"}},
+         "provisioner": "kubernetes.io/aws-ebs"},
+        {"metadata": {"name": "efs"}, "provisioner": "efs.csi.aws.com"}]
+    assert manifests.choose_storageclass(classes) == "efs"
+    assert manifests.choose_storageclass(classes[:1]) == "gp2"
+    assert manifests.choose_storageclass(classes, "gp2") == "gp2"
+    with pytest.raises(SystemExit):
+        manifests.choose_storageclass(classes, "nope")
+    pvc = manifests.pvc_manifest("p", "efs", "5Gi",
+                                 {"name": "job", "uid": "u"})
+    assert pvc["spec"]["accessModes"] == ["ReadWriteMany"]
+    assert pvc["metadata"]["ownerReferences"][0]["kind"] == "AdaptDLJob"
+    pod = manifests.copy_pod_manifest("p", "1234")
+    assert pod["spec"]["containers"][0]["volumeMounts"][0]["mountPath"] \
+        == "/adaptdl_pvc"
+    objs = manifests.tensorboard_manifests("exp", "efs")
+    assert [o["kind"] for o in objs] == ["PersistentVolumeClaim",
+                                         "Deployment", "Service"]
+    assert objs[1]["metadata"]["name"] == "adaptdl-tensorboard-exp"
+
+
+def test_ls_summary_and_parser():
+    items = [{"metadata": {"name": "a",
+                           "creationTimestamp": "2026-01-01T00:00:00Z"},
+              "status": {"phase": "Running", "replicas": 4, "group": 2}},
+             {"metadata": {"name": "b",
+                           "creationTimestamp": "2026-01-01T00:00:00Z"},
+              "status": {"phase": "Succeeded",
+                         "completionTimestamp":
+                             "2026-01-01T01:30:00.000000+00:00"}}]
+    rows = manifests.summarize_jobs(items, datetime(2026, 1, 1, 0, 10))
+    assert rows[0]["run_time"] == "0:10:00" and rows[0]["restarts"] == 2
+    assert rows[1]["run_time"] == "1:30:00" and rows[1]["replicas"] == "N/A"
+    args, rest = build_parser().parse_known_args(
+        ["submit", "proj", "--tensorboard", "tb", "--", "--lr", "0.1"])
+    assert args.project == "proj" and rest[-2:] == ["--lr", "0.1"]
+    args, _ = build_parser().parse_known_args(["tensorboard", "proxy", "x"])
+    assert args.tb_command == "proxy" and args.port == 6006

@@ -1,0 +1,169 @@
+"""Ray integration: the Ray-independent logic (Ray itself is optional)."""
+import os
+import threading
+from http.server import BaseHTTPRequestHandler, HTTPServer
+
+import pytest
+
+from adaptdl_b200.ray import have_ray, utils as ray_utils
+from adaptdl_b200.ray.allocator import AdaptDLAllocator
+from adaptdl_b200.ray.aws import optimizer
+from adaptdl_b200.ray.aws.controller import (JobState, cluster_ready,
+                                             speedup_from_hints,
+                                             trim_allocation)
+from adaptdl_b200.ray.aws.utils import (Status, checkpoint_obj_to_dir,
+                                        serialize_checkpoint)
+from adaptdl_b200.ray.aws.worker import (poll_spot_termination, run_script,
+                                         worker_environment)
+from adaptdl_b200.ray.job_mixin import AdaptDLJobMixin
+from adaptdl_b200.sched.policy import PolluxPolicy, SpeedupFunction
+
+HINTS = {"initBatchSize": 128, "maxBatchSize": 1280,
+         "localBszBounds": [64, 256], "maxProfiledReplicas": 4,
+         "gradientAccumulation": False,
+         "gradParams": {"norm": 0.00136, "var": 0.000502},
+         "perfParams": dict(alpha_c=0.121, beta_c=0.00568, alpha_n=0.0236,
+                            beta_n=0.00634, alpha_r=0.0118, beta_r=0.00317,
+                            gamma=1.14)}
+
+
+def test_bundle_allocation_roundtrip():
+    alloc = ["10.0.0.1", "10.0.0.1", "10.0.0.2", "virtual-3"]
+    bundles = ray_utils.allocation_to_bundles(alloc, {"CPU": 1, "GPU": 1})
+    assert bundles[0] == {"CPU": 1, "GPU": 1, "node:10.0.0.1": 0.01}
+    assert "node:virtual-3" not in bundles[3]
+    assert ray_utils.bundles_to_allocation(bundles) == alloc
+    assert ray_utils.unique_nodes(bundles) == 3
+
+
+def test_checkpoint_serialisation_roundtrip(tmp_path):
+    src = tmp_path / "src"
+    (src / "checkpoint-0").mkdir(parents=True)
+    (src / "checkpoint-0" / "a").write_bytes(b"123")
+    (src / "checkpoint-0" / "b").write_bytes(b"\x00\x01")
+    obj = serialize_checkpoint(str(src))
+    assert obj == {"checkpoint-0/a": b"123", "checkpoint-0/b": b"\x00\x01"}
+    dst = tmp_path / "dst"
+    checkpoint_obj_to_dir(str(dst), obj)
+    assert (dst / "checkpoint-0" / "b").read_bytes() == b"\x00\x01"
+
+
+def test_single_job_optimizer_hysteresis():
+    fn = speedup_from_hints(HINTS)
+    nodes = [("10.0.0.{}".format(i), {"CPU": 8, "GPU": 4}) for i in range(2)]
+    res = {"CPU": 1, "GPU": 1}
+    assert optimizer.optimize(None, None, nodes, res, 4, 1) == \
+        ["adaptdl_virtual_node_0"]
+    alloc = optimizer.greedy_allocation(nodes, res, 3)
+    assert alloc[:8] == ["10.0.0.0"] * 4 + ["10.0.0.1"] * 4
+    assert alloc[8:] == ["adaptdl_virtual_node_0"]
+    grown = optimizer.optimize(HINTS, fn, nodes, res, 2, 1)
+    assert 1 < len(grown) <= 8
+    again = optimizer.optimize(HINTS, fn, nodes, res, 2, len(grown))
+    assert len(again) == len(grown)          # already at the optimum
+
+
+def test_cluster_ready_and_trim():
+    res = {"CPU": 1, "GPU": 1}
+    nodes = {"a": {"CPU": 4, "GPU": 2}, "b": {"CPU": 4, "GPU": 1}}
+    assert cluster_ready(["a", "a", "b"], nodes, res) == (True, 3)
+    ready, n = cluster_ready(["a", "a", "adaptdl_virtual_node_0",
+                              "adaptdl_virtual_node_1"], nodes, res)
+    assert (ready, n) == (False, 3)
+    assert trim_allocation(["adaptdl_virtual_node_0", "a", "a"], 2) == \
+        ["a", "a"]
+    job = JobState(res, 60, {"path": "x.py"})
+    job.register_hints(dict(HINTS, junk=1))
+    assert "junk" not in job.hints
+    job.register_status(Status.SUCCEEDED.value)
+    job.register_status(Status.FAILED.value)
+    assert job.status is Status.SUCCEEDED
+
+
+def test_spot_termination_poller():
+    state = {"calls": 0}
+
+    class Handler(BaseHTTPRequestHandler):
+        def log_message(self, *a):
+            pass
+
+        def do_GET(self):
+            state["calls"] += 1
+            if state["calls"] < 3:
+                self.send_response(404)
+                self.end_headers()
+                return
+            body = b'{"action": "terminate", "time": "soon"}'
+            self.send_response(200)
+            self.send_header("Content-Length", str(len(body)))
+            self.end_headers()
+            self.wfile.write(body)
+    server = HTTPServer(("127.0.0.1", 0), Handler)
+    threading.Thread(target=server.serve_forever, daemon=True).start()
+    endpoint = "127.0.0.1:{}".format(server.server_port)
+    assert poll_spot_termination(endpoint, timeout=10, period=0.01) == \
+        "terminate"
+    assert state["calls"] == 3
+    state["calls"] = -100
+    assert poll_spot_termination(endpoint, timeout=0.05, period=0.01) is None
+    server.shutdown()
+
+
+def test_worker_environment_and_script_runner(tmp_path):
+    env = worker_environment("ns/job", "uid1", 2, 4, 3, "http://c:8080",
+                             offset=10, base_dir=str(tmp_path))
+    assert env["ADAPTDL_MASTER_PORT"] == "47013"
+    assert env["ADAPTDL_REPLICA_RANK"] == "2"
+    assert env["ADAPTDL_NUM_REPLICAS"] == "4"
+    assert env["ADAPTDL_NUM_RESTARTS"] == "3"
+    script = tmp_path / "train.py"
+    script.write_text(
+        "import os, sys\n"
+        "ck = os.environ['ADAPTDL_CHECKPOINT_PATH']\n"
+        "prev = os.path.exists(os.path.join(ck, 'state'))\n"
+        "open(os.path.join(ck, 'state'), 'w').write(sys.argv[1])\n"
+        "sys.exit(0 if prev else 143)\n")
+    saved, saved_argv = dict(os.environ), list(__import__("sys").argv)
+    try:
+        status, ckpt = run_script(str(script), ["first"], env)
+        assert status is Status.RUNNING and ckpt == {"state": b"first"}
+        status, ckpt = run_script(str(script), ["second"], env, ckpt)
+        assert status is Status.SUCCEEDED and ckpt is None
+    finally:
+        os.environ.clear()
+        os.environ.update(saved)
+        __import__("sys").argv = saved_argv
+
+
+def test_ray_allocator_with_job_mixin():
+    class Job(AdaptDLJobMixin):
+        rescale_resources = {"CPU": 1, "GPU": 1}
+
+        def __init__(self, job_id, alloc):
+            super().__init__(job_id=job_id)
+            self._alloc = alloc
+
+        def _allocation_in_use(self):
+            return self._alloc
+    nodes = {"n0": {"CPU": 8, "GPU": 4}, "n1": {"CPU": 8, "GPU": 4}}
+    allocator = AdaptDLAllocator(nodes, PolluxPolicy(generations=20, seed=0))
+    assert allocator.default_allocation(2) == ["n0", "n0"]
+    jobs = [Job("a", ["n0"]), Job("b", [])]
+    jobs[0].update_hints(HINTS)
+    info = jobs[0].job_info
+    assert isinstance(info.speedup_fn, SpeedupFunction)
+    assert info.max_replicas == 8 and jobs[1].job_info.max_replicas == 1
+    changed, desired = allocator.allocate(jobs)
+    assert desired >= 1
+    assert set(changed) <= {"a", "b"}
+    for alloc in changed.values():
+        assert set(alloc) <= set(nodes)
+
+
+@pytest.mark.skipif(have_ray(), reason="only meaningful without ray")
+def test_ray_missing_is_reported_clearly():
+    from adaptdl_b200.ray import require_ray
+    with pytest.raises(ImportError):
+        require_ray()
+    with pytest.raises(ImportError):
+        from adaptdl_b200.ray.tune import AdaptDLScheduler  # noqa: F401
