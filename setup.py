@@ -1,0 +1,49 @@
+"""Packaging. The CUDA extension is NOT a setuptools ext_module: it is built
+in-tree by ``adaptdl_b200._native.build()`` (plain nvcc, sm_100a) so the same
+``.so`` ships with a repo snapshot; ``python setup.py build_native`` runs it."""
+import os
+
+import setuptools
+from setuptools import Command
+
+
+class BuildNative(Command):
+    description = "compile csrc/ for sm_100a into adaptdl_b200/_native"
+    user_options = []
+
+    def initialize_options(self):
+        pass
+
+    def finalize_options(self):
+        pass
+
+    def run(self):
+        import sys
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        from adaptdl_b200 import _native
+        print(_native.build(force=True))
+
+
+setuptools.setup(
+    name="adaptdl-b200",
+    version=os.getenv("ADAPTDL_VERSION", "0.1.0"),
+    description="Blackwell-native elastic data-parallel training engine with "
+                "adaptive batch size / learning rate and goodput-driven "
+                "scheduling",
+    packages=setuptools.find_packages(include=["adaptdl_b200",
+                                               "adaptdl_b200.*"]),
+    package_data={"adaptdl_b200._native": ["*.so"]},
+    python_requires=">=3.9",
+    install_requires=["numpy", "scipy", "torch", "requests"],
+    extras_require={
+        "sched": ["aiohttp", "prometheus_client", "kubernetes_asyncio",
+                  "pyyaml"],
+        "ray": ["ray[tune]"],
+    },
+    entry_points={"console_scripts": [
+        "adaptdl-b200=adaptdl_b200.cli.main:main",
+        "adaptdl-b200-local=adaptdl_b200.sched.local:main",
+        "adaptdl-b200-on-ray-aws=adaptdl_b200.ray.aws.launch_job:main",
+    ]},
+    cmdclass={"build_native": BuildNative},
+)
