@@ -37,7 +37,7 @@ NVCC_FLAGS = [
 ]
 
 MAX_RANKS = 16
-MAX_CTAS = 64
+MAX_CTAS = 128
 
 _lock = threading.Lock()
 _lib = None

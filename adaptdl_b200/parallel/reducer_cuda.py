@@ -273,8 +273,10 @@ class CudaGradReducer(GradReducer):
         args.timeout_ns = _TIMEOUT_NS
         slice_vec = n_vec // self.world_size
         if self.world_size > 1:
+            # each thread keeps 16/W vectors in flight per iteration
+            per_cta = 512 * max(16 // self.world_size, 1)
             grid = max(1, min(self._reduce_ctas,
-                              (slice_vec + 511) // 512))
+                              (slice_vec + per_cta - 1) // per_cta))
         else:
             grid = self._local_grid(n_vec)
         self._order_after_compute()

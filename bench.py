@@ -51,6 +51,10 @@ def parse_args():
 
 
 def setup_env(args):
+    # torchrun pins OMP_NUM_THREADS=1 for N>1; do the same for the plain
+    # `python bench.py` (N=1) launch so every point of the scaling curve -- and
+    # both arms -- run with the same host threading
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", str(1)))
     local_rank = int(os.environ.get("LOCAL_RANK", str(rank)))

@@ -11,7 +11,7 @@
 #include <stdint.h>
 
 #define ADL_MAX_RANKS 16
-#define ADL_MAX_CTAS 64
+#define ADL_MAX_CTAS 128
 #define ADL_THREADS 512
 
 // ---------------------------------------------------------------------------

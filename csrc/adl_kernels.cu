@@ -82,81 +82,115 @@ __device__ __forceinline__ void cta_barrier_peers(const ReduceArgs& a, int phase
 // ---------------------------------------------------------------------------
 // fused two-shot all-reduce + gradient-noise-scale statistics
 // ---------------------------------------------------------------------------
-template <typename T, bool HAS_PINV>
+// W > 0: world size known at compile time (2, 4, 8): the per-peer loads are a
+// fully unrolled register array and each thread keeps U = 16/W vectors in
+// flight (16 independent 16-byte requests per thread; with 32 CTAs x 512
+// threads that is ~4 MB outstanding, enough to cover the ~2-3 us NVLink
+// round trip at full link bandwidth). W == 0: generic fallback, runtime world.
+template <int W> struct ReduceUnroll { static constexpr int U = 16 / W; };
+template <> struct ReduceUnroll<0> { static constexpr int U = 1; };
+template <> struct ReduceUnroll<1> { static constexpr int U = 8; };
+
+template <typename T, int W, bool HAS_PINV>
 __global__ void __launch_bounds__(ADL_THREADS, 1)
 allreduce_gns_kernel(const ReduceArgs a) {
   extern __shared__ double s_stats[];                 // [2][n_groups]
   constexpr int N = VecTraits<T>::N;
+  constexpr int U = ReduceUnroll<W>::U;
+  constexpr int WMAX = (W > 0) ? W : ADL_MAX_RANKS;
   smem_stats_zero(s_stats, 2 * a.n_groups);
   GroupAccum<2> accum;
   accum.init(s_stats, a.n_groups);
 
-  const int W = a.world;
-  if (W > 1) cta_barrier_peers(a, 0);                 // every rank's grads are ready
+  const int world = (W > 0) ? W : a.world;
+  if (world > 1) cta_barrier_peers(a, 0);             // every rank's grads are ready
 
-  const int slice = a.n_vec / W;
+  const int slice = a.n_vec / world;
   const int base = a.rank * slice;
   const int stride = gridDim.x * blockDim.x;
   const int first = blockIdx.x * blockDim.x + threadIdx.x;
-  const int iters = (slice + stride - 1) / stride;    // same for every lane
-  int cur = -1;                                       // segment cursor
+  const int iters = (slice + stride * U - 1) / (stride * U);   // same for every lane
+  int cur[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) cur[u] = -1;
+
+  // peer order rotated so that rank r starts with its own copy and the ranks
+  // do not all hammer the same peer at once
+  const Vec16* src[WMAX];
+  Vec16* dst[WMAX];
+#pragma unroll
+  for (int p = 0; p < WMAX; ++p) {
+    const int q = (p < world) ? (a.rank + p) % world : a.rank;
+    src[p] = static_cast<const Vec16*>(a.buf[q]);
+    dst[p] = static_cast<Vec16*>(a.buf[q]);
+  }
 
   for (int it = 0; it < iters; ++it) {
-    const int i = first + it * stride;
-    const bool active = i < slice;
-    const int v = base + i;
-    float sum[N], sq[2] = {0.f, 0.f};
-    int g = -1;
-    if (active) {
-      // issue all peer loads first (W independent 16-byte requests in flight)
-      Vec16 in[ADL_MAX_RANKS];
+    Vec16 in[U][WMAX];
+    Vec16 pv[U];
+    int idx[U];
+    bool active[U];
 #pragma unroll
-      for (int p = 0; p < ADL_MAX_RANKS; ++p)
-        if (p < W) in[p] = ld_vec(static_cast<const Vec16*>(a.buf[(a.rank + p) % W]) + v);
-      float pinv[N];
-      if (HAS_PINV) {
-        Vec16 pv = ld_vec(static_cast<const Vec16*>(a.pinv) + v);
-        unpack<T>(pv, pinv);
+    for (int u = 0; u < U; ++u) {
+      idx[u] = first + (it * U + u) * stride;
+      active[u] = idx[u] < slice;
+      if (active[u]) {
 #pragma unroll
-        for (int e = 0; e < N; ++e) pinv[e] = 1.0f / pinv[e];
+        for (int p = 0; p < WMAX; ++p)
+          if (p < world) in[u][p] = ld_vec(src[p] + base + idx[u]);
+        if (HAS_PINV) pv[u] = ld_vec(static_cast<const Vec16*>(a.pinv) + base + idx[u]);
       }
+    }
 #pragma unroll
-      for (int e = 0; e < N; ++e) sum[e] = 0.f;
+    for (int u = 0; u < U; ++u) {
+      float sq[2] = {0.f, 0.f};
+      int g = -1;
+      if (active[u]) {
+        const int v = base + idx[u];
+        float sum[N], pinv[N];
+        if (HAS_PINV) {
+          unpack<T>(pv[u], pinv);
 #pragma unroll
-      for (int p = 0; p < ADL_MAX_RANKS; ++p) {
-        if (p < W) {
-          float x[N];
-          unpack<T>(in[p], x);
+          for (int e = 0; e < N; ++e) pinv[e] = 1.0f / pinv[e];
+        }
 #pragma unroll
-          for (int e = 0; e < N; ++e) {
-            sum[e] += x[e];
-            const float y = HAS_PINV ? x[e] * pinv[e] : x[e];
-            sq[0] = fmaf(y, y, sq[0]);
+        for (int e = 0; e < N; ++e) sum[e] = 0.f;
+#pragma unroll
+        for (int p = 0; p < WMAX; ++p) {
+          if (p < world) {
+            float x[N];
+            unpack<T>(in[u][p], x);
+#pragma unroll
+            for (int e = 0; e < N; ++e) {
+              sum[e] += x[e];
+              const float y = HAS_PINV ? x[e] * pinv[e] : x[e];
+              sq[0] = fmaf(y, y, sq[0]);
+            }
           }
         }
-      }
 #pragma unroll
-      for (int e = 0; e < N; ++e) {
-        sum[e] *= a.scale;
-        const float y = HAS_PINV ? sum[e] * pinv[e] : sum[e];
-        sq[1] = fmaf(y, y, sq[1]);
-      }
-      const Vec16 out = pack<T>(sum);
+        for (int e = 0; e < N; ++e) {
+          sum[e] *= a.scale;
+          const float y = HAS_PINV ? sum[e] * pinv[e] : sum[e];
+          sq[1] = fmaf(y, y, sq[1]);
+        }
+        const Vec16 out = pack<T>(sum);
 #pragma unroll
-      for (int p = 0; p < ADL_MAX_RANKS; ++p)
-        if (p < W) st_vec(static_cast<Vec16*>(a.buf[(a.rank + p) % W]) + v, out);
-      if (cur < 0) cur = seg_find(a.segs, v);
-      while (__ldg(a.segs.seg_end + cur) <= v) ++cur;
-      g = __ldg(a.segs.seg_group + cur);
-      if (!a.want_local) sq[0] = 0.f;
+        for (int p = 0; p < WMAX; ++p)
+          if (p < world) st_vec(dst[p] + v, out);
+        if (cur[u] < 0) cur[u] = seg_find(a.segs, v);
+        while (__ldg(a.segs.seg_end + cur[u]) <= v) ++cur[u];
+        g = __ldg(a.segs.seg_group + cur[u]);
+        if (!a.want_local) sq[0] = 0.f;
+      }
+      accum.add(g, sq);
     }
-    accum.add(g, sq);
   }
   accum.flush_warp();
   double* outs[2] = {a.want_local ? a.L : nullptr, a.T};
   smem_stats_flush<2>(s_stats, a.n_groups, outs);
 
-  if (W > 1) cta_barrier_peers(a, 1);                 // every slice has landed everywhere
+  if (world > 1) cta_barrier_peers(a, 1);             // every slice has landed everywhere
 }
 
 // ---------------------------------------------------------------------------
@@ -513,8 +547,11 @@ static int g_device = -1;
 template <typename T>
 static int set_attrs_for() {
   const int lim = ADL_MAX_STAT_SMEM;
-  ADL_CHECK(cudaFuncSetAttribute(allreduce_gns_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
-  ADL_CHECK(cudaFuncSetAttribute(allreduce_gns_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+#define ADL_AR_ATTR(W)                                                                                          \
+  ADL_CHECK(cudaFuncSetAttribute(allreduce_gns_kernel<T, W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim)); \
+  ADL_CHECK(cudaFuncSetAttribute(allreduce_gns_kernel<T, W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+  ADL_AR_ATTR(0) ADL_AR_ATTR(1) ADL_AR_ATTR(2) ADL_AR_ATTR(4) ADL_AR_ATTR(8)
+#undef ADL_AR_ATTR
   ADL_CHECK(cudaFuncSetAttribute(local_kernel<T, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
   ADL_CHECK(cudaFuncSetAttribute(local_kernel<T, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
   ADL_CHECK(cudaFuncSetAttribute(local_kernel<T, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
@@ -557,12 +594,23 @@ int adl_allreduce_gns(const ReduceArgs* args, int dtype, int grid, void* stream)
   if (smem > ADL_MAX_STAT_SMEM) return -4;
   const bool pinv = args->pinv != nullptr;
   cudaStream_t s = (cudaStream_t)stream;
-#define LAUNCH_AR(T, P) allreduce_gns_kernel<T, P><<<grid, ADL_THREADS, smem, s>>>(*args)
+#define LAUNCH_AR_W(T, P, W) allreduce_gns_kernel<T, W, P><<<grid, ADL_THREADS, smem, s>>>(*args)
+#define LAUNCH_AR(T, P)                                        \
+  do {                                                         \
+    switch (args->world) {                                     \
+      case 1: LAUNCH_AR_W(T, P, 1); break;                     \
+      case 2: LAUNCH_AR_W(T, P, 2); break;                     \
+      case 4: LAUNCH_AR_W(T, P, 4); break;                     \
+      case 8: LAUNCH_AR_W(T, P, 8); break;                     \
+      default: LAUNCH_AR_W(T, P, 0); break;                    \
+    }                                                          \
+  } while (0)
   if (dtype == 0) { if (pinv) LAUNCH_AR(float, true); else LAUNCH_AR(float, false); }
   else if (dtype == 1) { if (pinv) LAUNCH_AR(__nv_bfloat16, true); else LAUNCH_AR(__nv_bfloat16, false); }
   else if (dtype == 2) { if (pinv) LAUNCH_AR(__half, true); else LAUNCH_AR(__half, false); }
   else return -2;
 #undef LAUNCH_AR
+#undef LAUNCH_AR_W
   return (int)cudaGetLastError();
 }
 
