@@ -216,7 +216,7 @@ class LocalElasticJob(object):
         return "running"
 
     def run(self, schedule=None, interval=30.0, adaptive=False,
-            initial=None):
+            initial=None, stop_after=None):
         """Run to completion. ``schedule``: replica counts applied every
         ``interval`` seconds (the last one stays); ``adaptive``: follow the
         job's hints instead."""
@@ -224,8 +224,20 @@ class LocalElasticJob(object):
         first = initial or (schedule.pop(0) if schedule else 1)
         self.start(min(first, self.max_replicas))
         next_change = time.time() + interval
+        deadline = time.time() + stop_after if stop_after else None
         try:
             while True:
+                if deadline is not None and time.time() >= deadline:
+                    # preempt for good: checkpoint and leave
+                    t0 = time.time()
+                    self.signal_stop()
+                    state = None
+                    while state is None and time.time() - t0 < 300:
+                        state = self.poll()
+                        time.sleep(0.05)
+                    self._log("stopped", state=state,
+                              seconds=time.time() - t0)
+                    return "stopped"
                 state = self.poll()
                 if state in ("finished", "failed"):
                     self._log(state)
@@ -264,6 +276,9 @@ def main(argv=None):
     parser.add_argument("--adaptive", action="store_true",
                         help="choose the replica count from the job's hints")
     parser.add_argument("--checkpoint-dir", default=None)
+    parser.add_argument("--stop-after", type=float, default=None,
+                        help="preempt the job for good after this many "
+                             "seconds (checkpoint + exit)")
     parser.add_argument("--report", default=None,
                         help="write the event log (JSON) here")
     parser.add_argument("script", nargs=argparse.REMAINDER)
@@ -283,12 +298,13 @@ def main(argv=None):
         command = [sys.executable] + command
     job = LocalElasticJob(command, gpus, args.checkpoint_dir)
     schedule = [int(x) for x in args.schedule.split(",") if x]
-    state = job.run(schedule, args.interval, args.adaptive)
+    state = job.run(schedule, args.interval, args.adaptive,
+                    stop_after=args.stop_after)
     if args.report:
         with open(args.report, "w") as f:
             json.dump([{"t": t, "event": what, **detail}
                        for t, what, detail in job.events], f, indent=1)
-    return 0 if state == "finished" else 1
+    return 0 if state in ("finished", "stopped") else 1
 
 
 if __name__ == "__main__":

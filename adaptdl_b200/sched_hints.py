@@ -39,7 +39,10 @@ def validate_hints(hints):
 
 def post_sched_hints(sched_hints, job_key):
     """PUT the hints to the supervisor; silently a no-op without one."""
-    url = env.supervisor_url()
+    import os
+    # the single-box launcher (sched/local.py) has no /discover but does
+    # accept hints
+    url = env.supervisor_url() or os.environ.get("ADAPTDL_HINTS_URL")
     if not url:
         return None
     try:

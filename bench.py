@@ -374,6 +374,7 @@ def run(args, rank, world, local_rank):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
+    if dist.is_initialized():
         dist.destroy_process_group()
 
 
