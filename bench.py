@@ -42,7 +42,13 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
-    ap.add_argument("--local-bsz", type=int, default=128)
+    ap.add_argument("--local-bsz", type=int, default=None)
+    ap.add_argument("--workload", default="resnet18",
+                    choices=["resnet18", "ncf", "bert"],
+                    help="resnet18 = the headline config (default); ncf = "
+                         "small-model/latency path; bert = BERT-base MLM "
+                         "bf16 (own arm only: the reference's BERT model "
+                         "needs torchtext)")
     ap.add_argument("--device", default="cuda")
     ap.add_argument("--reducer", default="auto")
     ap.add_argument("--no-graph", action="store_true",
@@ -160,29 +166,155 @@ class ClockSampler(object):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_program(args, adl, device, world, model_fn, own):
+class SyntheticNCF(object):
+    """MovieLens-1M shaped implicit feedback (6040 users x 3706 items)."""
+    USERS, ITEMS = 6040, 3706
+
+    def __init__(self, size, pin):
+        import torch
+        g = torch.Generator().manual_seed(1234)
+        self.u = torch.randint(0, self.USERS, (size,), generator=g)
+        self.i = torch.randint(0, self.ITEMS, (size,), generator=g)
+        self.y = torch.randint(0, 2, (size,), generator=g).float()
+        if pin:
+            self.u, self.i, self.y = (t.pin_memory()
+                                      for t in (self.u, self.i, self.y))
+
+    def __len__(self):
+        return self.u.shape[0]
+
+    def __getitem__(self, k):
+        return self.u[k], self.i[k], self.y[k]
+
+    def __getitems__(self, idx):
+        import torch
+        idx = torch.as_tensor(idx)
+        return self.u[idx], self.i[idx], self.y[idx]
+
+
+class SyntheticMLM(object):
+    """Token sequences for masked-LM pre-training (BERT vocabulary size)."""
+    NTOKEN, SEQ = 28996, 128
+
+    def __init__(self, size, pin):
+        import torch
+        g = torch.Generator().manual_seed(1234)
+        self.x = torch.randint(2, self.NTOKEN, (size, self.SEQ), generator=g)
+        self.y = self.x.clone()
+        mask = torch.rand(size, self.SEQ, generator=g) < 0.15
+        self.y[~mask] = -100
+        self.x[mask] = 1
+        if pin:
+            self.x, self.y = self.x.pin_memory(), self.y.pin_memory()
+
+    def __len__(self):
+        return self.x.shape[0]
+
+    def __getitem__(self, k):
+        return self.x[k], self.y[k]
+
+    def __getitems__(self, idx):
+        import torch
+        idx = torch.as_tensor(idx)
+        return self.x[idx], self.y[idx]
+
+
+class Workload(object):
+    """One benchmark configuration: dataset, model, optimizer, loss."""
+
+    def __init__(self, name, own):
+        self.name, self.own = name, own
+        self.channels_last = name == "resnet18"
+        self.default_local_bsz = {"resnet18": 128, "ncf": 256,
+                                  "bert": 32}[name]
+        self.unit = {"resnet18": "samples/s", "ncf": "samples/s",
+                     "bert": "sequences/s"}[name]
+
+    def dataset(self, size, pin):
+        return {"resnet18": SyntheticCIFAR, "ncf": SyntheticNCF,
+                "bert": SyntheticMLM}[self.name](size, pin)
+
+    def model(self):
+        if self.name == "resnet18":
+            if self.own:
+                from adaptdl_b200.models import resnet18
+                return resnet18()
+            from cifar_models.resnet import ResNet18
+            return ResNet18()
+        if self.name == "ncf":
+            if self.own:
+                from adaptdl_b200.models import NCF
+            else:
+                from ncf_model import NCF
+            return NCF(SyntheticNCF.USERS, SyntheticNCF.ITEMS, 32, 3, 0.0,
+                       "NeuMF-end")
+        from adaptdl_b200.models import bert_base_mlm
+        return bert_base_mlm(SyntheticMLM.NTOKEN, max_len=SyntheticMLM.SEQ)
+
+    def optimizer(self, model):
+        import torch
+        if self.name == "resnet18":
+            opt = torch.optim.SGD([{"params": [p]}
+                                   for p in model.parameters()],
+                                  lr=0.1, momentum=0.9, weight_decay=5e-4)
+            sched = torch.optim.lr_scheduler.MultiStepLR(opt, [30, 45], 0.1)
+        elif self.name == "ncf":
+            opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+            sched = None
+        else:
+            opt = torch.optim.AdamW(model.parameters(), lr=1e-4,
+                                    weight_decay=0.01)
+            sched = None
+        return opt, sched
+
+    def loss_fn(self):
+        import torch
+        if self.name == "resnet18":
+            ce = torch.nn.CrossEntropyLoss()
+            return lambda net, x, y: ce(net(x), y)
+        if self.name == "ncf":
+            bce = torch.nn.BCEWithLogitsLoss()
+            return lambda net, u, i, y: bce(net(u, i), y)
+        ce = torch.nn.CrossEntropyLoss(ignore_index=-100)
+        return lambda net, x, y: ce(
+            net(x).view(-1, SyntheticMLM.NTOKEN), y.view(-1))
+
+    def describe(self):
+        return {
+            "resnet18": ("ResNet-18 (pytorch-cifar, 3x32x32, 10 classes, "
+                         "random init)",
+                         "SGD m=0.9 wd=5e-4, one param group per tensor "
+                         "(62 GNS groups), AdaScale LR"),
+            "ncf": ("NeuMF-end NCF (MovieLens-1M shape, 1.6 M params, "
+                    "random init)", "Adam lr=1e-3, AdamScale LR"),
+            "bert": ("BERT-base MLM (768/3072/12L/12H, seq 128, untied "
+                     "head, random init)", "AdamW lr=1e-4, AdamScale LR"),
+        }[self.name]
+
+
+def build_program(args, adl, device, world, workload):
     """The user program (identical for both arms)."""
     import torch
-    local_bsz = args.local_bsz
+    local_bsz = args.local_bsz or workload.default_local_bsz
     global_bsz = local_bsz * world
     total_steps = 2 * (args.warmup + args.steps) + 4
-    dataset = SyntheticCIFAR(global_bsz * total_steps, pin=device.type == "cuda")
+    dataset = workload.dataset(global_bsz * total_steps,
+                               pin=device.type == "cuda")
     loader = adl.AdaptiveDataLoader(dataset, batch_size=global_bsz,
                                     shuffle=True, drop_last=True,
                                     collate_fn=identity_collate)
     loader.autoscale_batch_size(32 * global_bsz,
-                                local_bsz_bounds=(32, 1024),
+                                local_bsz_bounds=(min(32, local_bsz), 1024),
                                 gradient_accumulation=False)
-    model = model_fn().to(device)
-    if device.type == "cuda":
+    model = workload.model().to(device)
+    if device.type == "cuda" and workload.channels_last:
         model = model.to(memory_format=torch.channels_last)
-    optimizer = torch.optim.SGD(
-        [{"params": [p]} for p in model.parameters()],
-        lr=0.1, momentum=0.9, weight_decay=5e-4)
-    scheduler = torch.optim.lr_scheduler.MultiStepLR(optimizer, [30, 45], 0.1)
+    optimizer, scheduler = workload.optimizer(model)
     kwargs = {}
-    if own and args.reducer != "auto":
+    if workload.own and args.reducer != "auto":
         kwargs["reducer"] = args.reducer
+    if workload.name == "ncf":
+        kwargs["find_unused_parameters"] = True
     net = adl.AdaptiveDataParallel(model, optimizer, scheduler, **kwargs)
     return dataset, loader, net, optimizer, global_bsz
 
@@ -203,7 +335,6 @@ def run(args, rank, world, local_rank):
     if own:
         sys.path.insert(0, ROOT)
         import adaptdl_b200.torch as adl
-        from adaptdl_b200.models import resnet18 as model_fn
     else:
         import numpy as np
         if not hasattr(np, "int"):       # numpy >= 1.24 dropped the aliases
@@ -213,12 +344,13 @@ def run(args, rank, world, local_rank):
         sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref",
                                         "_ref_examples"))
         import adaptdl.torch as adl
-        from cifar_models.resnet import ResNet18 as model_fn
 
     adl.init_process_group("nccl" if device.type == "cuda" else "gloo")
+    workload = Workload(args.workload, own)
     dataset, loader, net, optimizer, global_bsz = build_program(
-        args, adl, device, world, model_fn, own)
-    criterion = torch.nn.CrossEntropyLoss()
+        args, adl, device, world, workload)
+    loss_fn = workload.loss_fn()
+    cl = device.type == "cuda" and workload.channels_last
     W, K = args.warmup, args.steps
     autocast = device.type == "cuda"
     loss_host = torch.zeros(W + K + 8, dtype=torch.float32)
@@ -236,19 +368,18 @@ def run(args, rank, world, local_rank):
         # the framework's own step API: whole-step CUDA graph on top of the
         # device-resident estimator + fused optimizer (eager with --no-graph)
         trainer = adl.GraphedTrainStep(
-            net, optimizer, lambda n, x, y: criterion(n(x), y),
+            net, optimizer, loss_fn,
             autocast_dtype=torch.bfloat16 if autocast else None,
-            enabled=not args.no_graph, channels_last=device.type == "cuda")
+            enabled=not args.no_graph, channels_last=cl)
 
-    def train_step(x, y, slot, read_back):
+    def train_step(batch, slot, read_back):
         if trainer is not None:
-            loss = trainer(x, y)
+            loss = trainer(*batch)
         else:
             optimizer.zero_grad()
             with torch.autocast("cuda", dtype=torch.bfloat16,
                                 enabled=autocast):
-                out = net(x)
-                loss = criterion(out, y)
+                loss = loss_fn(net, *batch)
             loss.backward()
             optimizer.step()
         if read_back:
@@ -264,7 +395,7 @@ def run(args, rank, world, local_rank):
         for _ in adl.remaining_epochs_until(epochs_until):
             t_wall = ev0 = ev1 = None
             sampler = None
-            for step, (x, y) in enumerate(loader):
+            for step, batch in enumerate(loader):
                 if step == W:
                     barrier()
                     sampler = ClockSampler(
@@ -294,29 +425,25 @@ def run(args, rank, world, local_rank):
                         got = sampler.stop()
                         clocks = got or clocks
                     break
+                def on_device(t, blocking):
+                    t = t.to(device, non_blocking=not blocking)
+                    if cl and t.dim() == 4:
+                        t = t.contiguous(memory_format=torch.channels_last)
+                    return t
                 if phase == "e2e":
-                    h2d_bytes = x.numel() * x.element_size() \
-                        + y.numel() * y.element_size()
+                    h2d_bytes = sum(t.numel() * t.element_size()
+                                    for t in batch)
                     if trainer is not None:
                         # pinned host tensors go straight into the step
                         # (copied H2D into the graph's static inputs)
-                        train_step(x, y, step, read_back=True)
+                        train_step(batch, step, read_back=True)
                     else:
-                        xd = x.to(device, non_blocking=True)
-                        yd = y.to(device, non_blocking=True)
-                        if device.type == "cuda":
-                            xd = xd.contiguous(
-                                memory_format=torch.channels_last)
-                        train_step(xd, yd, step, read_back=True)
+                        train_step([on_device(t, False) for t in batch],
+                                   step, read_back=True)
                 else:
                     if resident is None:
-                        xd = x.to(device)
-                        if device.type == "cuda":
-                            xd = xd.contiguous(
-                                memory_format=torch.channels_last)
-                        resident = (xd, y.to(device))
-                    train_step(resident[0], resident[1], step,
-                               read_back=False)
+                        resident = [on_device(t, True) for t in batch]
+                    train_step(resident, step, read_back=False)
     if device.type == "cuda":
         torch.cuda.synchronize()
     assert bool(torch.isfinite(loss_host[:W + K]).all()), "non-finite loss"
@@ -333,7 +460,7 @@ def run(args, rank, world, local_rank):
     if rank == 0:
         line = {
             "metric": "samples/sec (device-timed, max over ranks)",
-            "value": value, "unit": "samples/s", "n_gpus": world,
+            "value": value, "unit": workload.unit, "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": dev_ms / K,
             "higher_is_better": True, "scaling": "weak",
             "vs_baseline": (value / PUBLISHED_BASELINE
@@ -341,21 +468,24 @@ def run(args, rank, world, local_rank):
             "dtype": "bf16", "data": "synthetic",
             "impl": args.impl,
             "config": {
-                "model": "ResNet-18 (pytorch-cifar, 3x32x32, 10 classes, "
-                         "random init)",
-                "global_batch": global_bsz, "local_batch": args.local_bsz,
-                "seq_len": None, "parallelism": "dp{}".format(world),
-                "optimizer": "SGD m=0.9 wd=5e-4, one param group per tensor "
-                             "(62 GNS groups), AdaScale LR",
+                "workload": workload.name,
+                "model": workload.describe()[0],
+                "global_batch": global_bsz,
+                "local_batch": global_bsz // world,
+                "seq_len": (SyntheticMLM.SEQ if workload.name == "bert"
+                            else None),
+                "parallelism": "dp{}".format(world),
+                "optimizer": workload.describe()[1],
                 "adaptive": "autoscale_batch_size(max=32x, local 32..1024)",
-                "memory_format": "channels_last, bf16 autocast",
+                "memory_format": ("channels_last, " if workload.channels_last
+                                  else "") + "bf16 autocast",
                 "l2": "working set > L2 (activations of a 128-sample batch "
                       "exceed 126 MB) and a fresh batch every e2e step",
                 "step": ("eager" if (not own or args.no_graph)
                          else "CUDA graph (whole step), device-resident "
-                              "GNS estimator, fused SGD"),
+                              "GNS estimator, fused optimizer"),
             },
-            "e2e": {"value": e2e_value, "unit": "samples/s",
+            "e2e": {"value": e2e_value, "unit": workload.unit,
                     "ms_per_step": e2e_ms / K,
                     "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": 4},
@@ -381,6 +511,12 @@ def run(args, rank, world, local_rank):
 def main():
     args = parse_args()
     rank, world, local_rank = setup_env(args)
+    if args.impl == "reference" and args.workload == "bert":
+        if rank == 0:
+            print(json.dumps({"impl": "reference", "unavailable":
+                              "the reference's BERT example model imports "
+                              "torchtext.nn (not installable offline)"}))
+        return
     if args.impl == "reference":
         ref = os.path.join(ROOT, "baseline", "_ref", "adaptdl")
         if not os.path.isdir(ref):
