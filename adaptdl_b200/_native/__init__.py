@@ -117,6 +117,7 @@ class ReduceArgs(ctypes.Structure):
         ("L", ctypes.c_void_p), ("T", ctypes.c_void_p),
         ("err", ctypes.c_void_p),
         ("timeout_ns", ctypes.c_ulonglong),
+        ("mc_buf", ctypes.c_void_p),
     ]
 
 

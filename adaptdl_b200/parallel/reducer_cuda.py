@@ -107,6 +107,10 @@ class CudaGradReducer(GradReducer):
             self._staging, self._staging_ptrs = self._region.carve(
                 offsets["staging"], _STAGING_BYTES)
         self._grad_ptrs = {}
+        self._grad_mc = {}
+        # NVLS: buckets at least this large go through the switch
+        self._nvls_min_bytes = int(float(os.environ.get(
+            "ADAPTDL_B200_NVLS_MIN_MB", "1")) * (1 << 20))
         for i, arena in enumerate(self.arenas):
             itemsize = torch.empty((), dtype=arena.dtype).element_size()
             view, ptrs = self._region.carve(
@@ -114,6 +118,8 @@ class CudaGradReducer(GradReducer):
                 arena.dtype)
             arena._symm_grad = view
             self._grad_ptrs[i] = ptrs
+            self._grad_mc[i] = (self._region.mc_ptr + offsets[("grad", i)]
+                                if self._region.mc_ptr else 0)
         # statistics, error word, timers, mailbox
         self._stats = torch.zeros(4, G, dtype=torch.float64, device=dev)
         self._result = torch.zeros(4, G, dtype=torch.float64, device=dev)
@@ -271,6 +277,10 @@ class CudaGradReducer(GradReducer):
         args.T = self._row(1)
         args.err = self._err.data_ptr()
         args.timeout_ns = _TIMEOUT_NS
+        if self._grad_mc.get(ai) and self.world_size > 1 and \
+                n_vec * layout.VEC_BYTES >= self._nvls_min_bytes:
+            args.mc_buf = self._grad_mc[ai] + off
+            self.nvls_launches = getattr(self, "nvls_launches", 0) + 1
         slice_vec = n_vec // self.world_size
         if self.world_size > 1:
             # each thread keeps 16/W vectors in flight per iteration
@@ -425,11 +435,10 @@ class CudaGradReducer(GradReducer):
             nonlocal chunk, chunk_bytes
             if not chunk:
                 return
-            flat = torch.cat(chunk)
-            n = flat.numel()
+            n = sum(t.numel() for t in chunk)
             n_pad = _round_up(n, 16)
             if self.rank == src:
-                self._staging[:n].copy_(flat)
+                torch.cat(chunk, out=self._staging[:n])
             args = BcastArgs()
             for p in range(self.world_size):
                 args.staging[p] = self._staging_ptrs[p]
@@ -447,11 +456,13 @@ class CudaGradReducer(GradReducer):
                   "adl_bcast_pull")
             self.launches += 1
             if self.rank != src:
-                cursor = 0
+                cursor, pieces = 0, []
                 for t in chunk:
                     nb = t.numel()
-                    t.copy_(self._staging[cursor:cursor + nb])
+                    pieces.append(self._staging[cursor:cursor + nb])
                     cursor += nb
+                # one multi-tensor launch instead of one copy per tensor
+                torch._foreach_copy_(chunk, pieces)
             chunk, chunk_bytes = [], 0
 
         for t in tensors:

@@ -114,11 +114,13 @@ class SymmetricRegion(object):
     """``tensor``: this rank's bytes (uint8, on ``device``); ``ptrs[p]``:
     address of rank p's bytes in *this* process."""
 
-    def __init__(self, tensor, ptrs, nbytes, provider, keepalive=None):
+    def __init__(self, tensor, ptrs, nbytes, provider, keepalive=None,
+                 mc_ptr=0):
         self.tensor = tensor
         self.ptrs = list(ptrs)
         self.nbytes = nbytes
         self.provider = provider
+        self.mc_ptr = int(mc_ptr or 0)   # NVLS multicast address (0 = none)
         self._keepalive = keepalive
 
     def carve(self, offset, nbytes, dtype=torch.uint8):
@@ -158,6 +160,15 @@ class _NativeProvider(object):
         self._check(lib.adl_symm_round_size(dev, nbytes, ctypes.byref(size)),
                     "round_size")
         size = size.value
+        want_mc = os.environ.get("ADAPTDL_B200_NVLS", "auto") != "0" \
+            and bool(lib.adl_topo_multicast_supported(dev))
+        if want_mc:              # multicast binding has its own granularity
+            mc_size = ctypes.c_size_t()
+            if lib.adl_mc_round_size(self.world, size,
+                                     ctypes.byref(mc_size)) == 0:
+                size = max(size, mc_size.value)
+            else:
+                want_mc = False
         handle, fd = ctypes.c_ulonglong(), ctypes.c_int()
         self._check(lib.adl_symm_create(dev, size, ctypes.byref(handle),
                                         ctypes.byref(fd)), "create")
@@ -185,8 +196,52 @@ class _NativeProvider(object):
         tensor.zero_()
         torch.cuda.synchronize(self.device)
         # nobody may touch a peer's bytes before that peer zeroed them
-        _all_gather_object(size, self.group)
-        return SymmetricRegion(tensor, ptrs, size, self.name, keepalive=self)
+        flags = _all_gather_object(bool(want_mc), self.group)
+        mc_ptr = 0
+        if all(flags):
+            mc_ptr = self._bind_multicast(handle.value, size)
+        return SymmetricRegion(tensor, ptrs, size, self.name, keepalive=self,
+                               mc_ptr=mc_ptr)
+
+    def _bind_multicast(self, mem_handle, size):
+        """Create (rank 0) / import the NVLS multicast object, add every
+        device, bind this rank's physical memory and map the multicast
+        address. Any failure on any rank disables it everywhere."""
+        import ctypes
+        lib, dev = self.lib, self.device.index
+        ok, mc_handle, fd = True, ctypes.c_ulonglong(), ctypes.c_int(-1)
+        if self.rank == 0:
+            ok = lib.adl_mc_create(self.world, size, ctypes.byref(mc_handle),
+                                   ctypes.byref(fd)) == 0
+        send_fd_ = fd.value if (self.rank == 0 and ok) \
+            else os.open(os.devnull, os.O_RDONLY)
+        try:
+            got = self.fds.exchange(send_fd_)
+        finally:
+            os.close(send_fd_)
+        for src, peer_fd in got.items():
+            if src == 0 and self.rank != 0:
+                ok = lib.adl_symm_import(peer_fd,
+                                         ctypes.byref(mc_handle)) == 0
+            os.close(peer_fd)
+        ok = all(_all_gather_object(bool(ok), self.group))
+        if ok:
+            ok = lib.adl_mc_add_device(mc_handle.value, dev) == 0
+        ok = all(_all_gather_object(bool(ok), self.group))
+        if ok:
+            ok = lib.adl_mc_bind(mc_handle.value, mem_handle, size) == 0
+        ok = all(_all_gather_object(bool(ok), self.group))
+        ptr = ctypes.c_ulonglong()
+        if ok:
+            ok = lib.adl_symm_map(mc_handle.value, size, dev,
+                                  ctypes.byref(ptr)) == 0
+        ok = all(_all_gather_object(bool(ok), self.group))
+        if not ok:
+            LOG.info("NVLS multicast unavailable (%s); using P2P loads",
+                     lib.adl_symm_last_error().decode())
+            return 0
+        self._mapped.append((ptr.value, size, mc_handle.value))
+        return ptr.value
 
     def close(self):
         for ptr, size, handle in self._mapped:
@@ -216,8 +271,14 @@ class _TorchProvider(object):
         t.zero_()
         torch.cuda.synchronize(self.device)
         hdl.barrier()
+        mc_ptr = 0
+        if os.environ.get("ADAPTDL_B200_NVLS", "auto") != "0":
+            try:
+                mc_ptr = int(hdl.multicast_ptr or 0)
+            except Exception:  # noqa: BLE001
+                mc_ptr = 0
         return SymmetricRegion(t, [int(p) for p in hdl.buffer_ptrs], nbytes,
-                               self.name, keepalive=(hdl, t))
+                               self.name, keepalive=(hdl, t), mc_ptr=mc_ptr)
 
     def close(self):
         pass

@@ -501,6 +501,7 @@ def run(args, rank, world, local_rank):
             line["device_engine"] = net.engine is not None
             prov = getattr(net.reducer, "_provider", None)
             line["symmetric_memory"] = getattr(prov, "name", None)
+            line["nvls_launches"] = getattr(net.reducer, "nvls_launches", 0)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

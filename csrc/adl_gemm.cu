@@ -1,0 +1,343 @@
+// adaptdl_b200 -- tcgen05 GEMM with a fused bias + GELU epilogue (sm_100a).
+//
+//   Y[M,N] = act( X[M,K] . W[N,K]^T + bias[N] )      bf16 in, fp32 accumulate
+//   (optionally also stores the pre-activation Z for the backward pass)
+//
+// This is the feed-forward up-projection of the BERT / transformer workloads
+// (examples/BERT: 768 -> 3072 + GELU): PyTorch runs it as cuBLAS GEMM + a
+// bias kernel + a GELU kernel, i.e. the [M, 3072] activation makes three
+// extra HBM round trips. Here the epilogue is applied to the accumulator
+// while it is still in tensor memory.
+//
+// Structure (one CTA per 128 x BLOCK_N output tile, 192 threads):
+//   warp 0   TMA producer: cp.async.bulk.tensor loads of the A (128 x 64) and
+//            B (BLOCK_N x 64) K-slices into a STAGES-deep shared-memory ring
+//            (128-byte swizzle), completion on mbarriers (complete_tx::bytes)
+//   warp 1   MMA issuer: one elected lane issues tcgen05.mma.cta_group::1
+//            .kind::f16 (M=128, N=BLOCK_N, K=16) x4 per stage, accumulating in
+//            TMEM; tcgen05.commit releases the smem stage / signals the epilogue
+//            (warp 1 also allocates / frees the TMEM columns)
+//   warps 2-5  epilogue: tcgen05.ld (32 lanes x 32 columns per warp), + bias,
+//            GELU, bf16 pack, 128-bit stores
+//
+// Every wait loop is bounded: a stuck pipeline sets an error flag and the CTA
+// exits instead of hanging the GPU.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;                  // 64 bf16 = 128 B = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 4;
+constexpr int NUM_THREADS = 192;             // warp0 TMA, warp1 MMA, warps 2..5 epilogue
+constexpr uint32_t SPIN_LIMIT = 1u << 26;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+               :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// bounded wait; returns false on timeout
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, uint32_t* err) {
+  const uint32_t addr = smem_u32(bar);
+  for (uint32_t spin = 0; spin < SPIN_LIMIT; ++spin) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (done) return true;
+  }
+  atomicOr(err, 2u);
+  return false;
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar,
+                                            int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];"
+      :: "r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+               :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                                uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// Shared-memory matrix descriptor, K-major operand, 128-byte swizzle:
+//   bits [ 0,14) start address >> 4        bits [16,30) leading byte offset >> 4 (unused here)
+//   bits [32,46) stride byte offset >> 4   (8 rows x 128 B = 1024 B between core-matrix groups)
+//   bits [46,48) descriptor version = 1    bits [61,64) layout type: 2 = SWIZZLE_128B
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t desc = 0;
+  desc |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  desc |= (uint64_t)1 << 16;                       // LBO (ignored for swizzled K-major)
+  desc |= (uint64_t)(1024 >> 4) << 32;             // SBO
+  desc |= (uint64_t)1 << 46;                       // version
+  desc |= (uint64_t)2 << 61;                       // SWIZZLE_128B
+  return desc;
+}
+// Instruction descriptor (kind::f16): c=F32 (1 @4), a=BF16 (1 @7), b=BF16 (1 @10),
+// a/b K-major (0 @15, 0 @16), N>>3 @17, M>>4 @24.
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ float gelu_erf(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+}
+
+struct GemmArgs {
+  __nv_bfloat16* y;            // [M, N] activation output
+  __nv_bfloat16* z;            // [M, N] pre-activation (may be nullptr)
+  const float* bias;           // [N] (may be nullptr)
+  int M, N, K;
+  int act;                     // 0 = identity, 1 = GELU (erf)
+  uint32_t* err;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_bias_act_kernel(const __grid_constant__ CUtensorMap map_a,
+                     const __grid_constant__ CUtensorMap map_b, const GemmArgs args) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte alignment is required by the 128 B swizzle atoms
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_blk = blockIdx.y, n_blk = blockIdx.x;
+  const int num_k = args.K / BLOCK_K;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" :: "l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" :: "l"(&map_b) : "memory");
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {                      // TMEM: BLOCK_N fp32 columns x 128 lanes
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 :: "r"(smem_u32(tmem_base_slot)), "r"(BLOCK_N) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_acc = *reinterpret_cast<volatile uint32_t*>(tmem_base_slot);
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (elect_one()) {
+      for (int k = 0; k < num_k; ++k) {
+        const int s = k % STAGES;
+        const uint32_t phase = (k / STAGES) & 1;
+        if (!mbar_wait(&empty_bar[s], phase ^ 1, args.err)) break;
+        uint8_t* a_dst = smem + s * STAGE_BYTES;
+        uint8_t* b_dst = a_dst + A_BYTES;
+        mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+        tma_load_2d(a_dst, &map_a, &full_bar[s], k * BLOCK_K, m_blk * BLOCK_M);
+        tma_load_2d(b_dst, &map_b, &full_bar[s], k * BLOCK_K, n_blk * BLOCK_N);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N);
+    for (int k = 0; k < num_k; ++k) {
+      const int s = k % STAGES;
+      const uint32_t phase = (k / STAGES) & 1;
+      if (!mbar_wait(&full_bar[s], phase, args.err)) break;
+      tcgen05_fence_after();
+      if (elect_one()) {
+        const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+        const uint32_t b_addr = a_addr + A_BYTES;
+        const uint64_t a_desc = make_smem_desc(a_addr);
+        const uint64_t b_desc = make_smem_desc(b_addr);
+#pragma unroll
+        for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
+          // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in (addr >> 4) units
+          tcgen05_mma_f16(tmem_acc, a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), idesc,
+                          (k > 0 || kk > 0) ? 1u : 0u);
+        }
+        tcgen05_commit(&empty_bar[s]);                 // smem stage reusable once the MMAs retire
+        if (k == num_k - 1) tcgen05_commit(tmem_full_bar);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===== epilogue warps 2..5: TMEM lanes 32*(warp%4) .. +31 =====
+    const int lane_grp = warp & 3;
+    if (mbar_wait(tmem_full_bar, 0, args.err)) {
+      tcgen05_fence_after();
+      const int row = m_blk * BLOCK_M + lane_grp * 32 + lane;
+      __nv_bfloat16* y_row = args.y + (size_t)row * args.N + (size_t)n_blk * BLOCK_N;
+      __nv_bfloat16* z_row = args.z ? args.z + (size_t)row * args.N + (size_t)n_blk * BLOCK_N : nullptr;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_acc + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)c0;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+              "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+              "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr) : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (row < args.M) {
+          const int col0 = n_blk * BLOCK_N + c0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              v[e] = __uint_as_float(r[j + e]);
+              if (args.bias) v[e] += __ldg(args.bias + col0 + j + e);
+            }
+            if (z_row) {
+              uint4 zp;
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
+              zp.x = *reinterpret_cast<uint32_t*>(&h0); zp.y = *reinterpret_cast<uint32_t*>(&h1);
+              zp.z = *reinterpret_cast<uint32_t*>(&h2); zp.w = *reinterpret_cast<uint32_t*>(&h3);
+              *reinterpret_cast<uint4*>(z_row + c0 + j) = zp;
+            }
+            if (args.act == 1) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = gelu_erf(v[e]);
+            }
+            uint4 yp;
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
+            yp.x = *reinterpret_cast<uint32_t*>(&h0); yp.y = *reinterpret_cast<uint32_t*>(&h1);
+            yp.z = *reinterpret_cast<uint32_t*>(&h2); yp.w = *reinterpret_cast<uint32_t*>(&h3);
+            *reinterpret_cast<uint4*>(y_row + c0 + j) = yp;
+          }
+        }
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_acc), "r"(BLOCK_N) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host side: TMA descriptors via the driver entry point (no libcuda link)
+// ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+
+bool load_encode() {
+  if (g_encode) return true;
+  void* lib = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) lib = dlopen("libcuda.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) return false;
+  g_encode = reinterpret_cast<EncodeTiledFn>(dlsym(lib, "cuTensorMapEncodeTiled"));
+  return g_encode != nullptr;
+}
+
+// row-major [rows, cols] bf16 matrix, box = [box_rows, 64 cols], 128 B swizzle
+int make_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, box_rows};
+  cuuint32_t elem[2] = {1, 1};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box,
+                        elem, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return (int)r;
+}
+
+template <int BLOCK_N>
+int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& a, cudaStream_t s) {
+  constexpr int smem = STAGES * (BLOCK_M * BLOCK_K * 2 + BLOCK_N * BLOCK_K * 2) + 1024 + 256;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bias_act_kernel<BLOCK_N>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  dim3 grid(a.N / BLOCK_N, (a.M + BLOCK_M - 1) / BLOCK_M);
+  gemm_bias_act_kernel<BLOCK_N><<<grid, NUM_THREADS, smem, s>>>(ma, mb, a);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+extern "C" int adl_bind_thread();
+
+extern "C" {
+
+// y[M,N] (and optionally z) = act(x[M,K] @ w[N,K]^T + bias). bf16 row-major; K % 64 == 0,
+// N % 128 == 0. Returns 0, a CUDA error code, or a negative shape/driver error.
+int adl_gemm_bias_act(const void* x, const void* w, const float* bias, void* y, void* z, int M, int N,
+                      int K, int act, void* err, void* stream) {
+  if (K % BLOCK_K != 0 || N % 128 != 0 || M <= 0) return -10;
+  if (!load_encode()) return -11;
+  if (int rc = adl_bind_thread()) return rc;
+  CUtensorMap ma, mb;
+  const int block_n = (N % 256 == 0 && (long long)M * N >= (1ll << 22)) ? 256 : 128;
+  if (int rc = make_map(&ma, x, (uint64_t)M, (uint64_t)K, BLOCK_M)) return -100 - rc;
+  if (int rc = make_map(&mb, w, (uint64_t)N, (uint64_t)K, (uint32_t)block_n)) return -200 - rc;
+  GemmArgs a;
+  a.y = static_cast<__nv_bfloat16*>(y);
+  a.z = static_cast<__nv_bfloat16*>(z);
+  a.bias = bias;
+  a.M = M; a.N = N; a.K = K; a.act = act;
+  a.err = static_cast<uint32_t*>(err);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (block_n == 256) return launch<256>(ma, mb, a, s);
+  return launch<128>(ma, mb, a, s);
+}
+
+}  // extern "C"

@@ -42,6 +42,7 @@ struct ReduceArgs {
   double* T;                       // [n_groups] partial: |G/P|^2
   uint32_t* err;                   // sticky error word (device)
   unsigned long long timeout_ns;
+  void* mc_buf;                    // NVLS: multicast address of the bucket (or nullptr)
 };
 
 __device__ __forceinline__ bool wait_flag(const uint32_t* p, uint32_t epoch,
@@ -191,6 +192,155 @@ allreduce_gns_kernel(const ReduceArgs a) {
   smem_stats_flush<2>(s_stats, a.n_groups, outs);
 
   if (world > 1) cta_barrier_peers(a, 1);             // every slice has landed everywhere
+}
+
+// ---------------------------------------------------------------------------
+// NVLS flavour: the NVSwitch reduces. `multimem.ld_reduce` on the multicast
+// address returns sum_r g_r of a vector in ONE load (the switch pulls every
+// GPU's copy and adds in flight), `multimem.st` writes the mean into every
+// GPU's arena with ONE store. Per GPU that is ~B out + ~B(1+1/W) in instead
+// of 2(W-1)/W*B each way, and W times fewer load instructions.
+// The switch hides the per-replica values, so sum_r |g_r|^2 comes from a local
+// pass over this rank's own bucket (HBM speed, before the start barrier --
+// peers may only overwrite it after they have seen this rank's start flag);
+// the per-rank partials are summed by the finalize kernel like all others.
+// ---------------------------------------------------------------------------
+template <typename T> struct Multimem;
+template <> struct Multimem<float> {
+  static __device__ __forceinline__ Vec16 ld_reduce(const void* p) {
+    Vec16 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.w[0]), "=r"(v.w[1]), "=r"(v.w[2]), "=r"(v.w[3]) : "l"(p) : "memory");
+    return v;
+  }
+};
+template <> struct Multimem<__nv_bfloat16> {
+  static __device__ __forceinline__ Vec16 ld_reduce(const void* p) {
+    Vec16 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.w[0]), "=r"(v.w[1]), "=r"(v.w[2]), "=r"(v.w[3]) : "l"(p) : "memory");
+    return v;
+  }
+};
+template <> struct Multimem<__half> {
+  static __device__ __forceinline__ Vec16 ld_reduce(const void* p) {
+    Vec16 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.f16x2 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.w[0]), "=r"(v.w[1]), "=r"(v.w[2]), "=r"(v.w[3]) : "l"(p) : "memory");
+    return v;
+  }
+};
+__device__ __forceinline__ void multimem_st(void* p, const Vec16& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "r"(v.w[0]), "r"(v.w[1]), "r"(v.w[2]), "r"(v.w[3]) : "memory");
+}
+
+template <typename T, bool HAS_PINV>
+__global__ void __launch_bounds__(ADL_THREADS, 1)
+allreduce_nvls_kernel(const ReduceArgs a) {
+  extern __shared__ double s_stats[];                 // [2][n_groups]
+  constexpr int N = VecTraits<T>::N;
+  constexpr int U = 4;
+  smem_stats_zero(s_stats, 2 * a.n_groups);
+  GroupAccum<2> accum;
+  accum.init(s_stats, a.n_groups);
+  const int stride = gridDim.x * blockDim.x;
+  const int first = blockIdx.x * blockDim.x + threadIdx.x;
+  const Vec16* mine = static_cast<const Vec16*>(a.buf[a.rank]);
+
+  const int slice = a.n_vec / a.world;
+  const int iters = (slice + stride * U - 1) / (stride * U);
+  if (a.want_local) {
+    // L += |g_local / P|^2 over the whole bucket. CTA c of this rank reads,
+    // in EVERY slice q, exactly the vectors that CTA c of rank q will later
+    // overwrite -- the per-CTA start barrier below is then enough to order
+    // these reads before the peers' multicast stores.
+    for (int q = 0; q < a.world; ++q) {
+      int cur[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) cur[u] = -1;
+      for (int it = 0; it < iters; ++it) {
+        Vec16 in[U], pv[U];
+        int idx[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          idx[u] = first + (it * U + u) * stride;
+          if (idx[u] < slice) {
+            in[u] = ld_vec(mine + q * slice + idx[u]);
+            if (HAS_PINV) pv[u] = ld_vec(static_cast<const Vec16*>(a.pinv) + q * slice + idx[u]);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          float sq[2] = {0.f, 0.f};
+          int g = -1;
+          if (idx[u] < slice) {
+            const int v = q * slice + idx[u];
+            float x[N], pinv[N];
+            unpack<T>(in[u], x);
+            if (HAS_PINV) unpack<T>(pv[u], pinv);
+#pragma unroll
+            for (int e = 0; e < N; ++e) {
+              const float y = HAS_PINV ? x[e] / pinv[e] : x[e];
+              sq[0] = fmaf(y, y, sq[0]);
+            }
+            if (cur[u] < 0) cur[u] = seg_find(a.segs, v);
+            while (__ldg(a.segs.seg_end + cur[u]) <= v) ++cur[u];
+            g = __ldg(a.segs.seg_group + cur[u]);
+          }
+          accum.add(g, sq);
+        }
+      }
+    }
+    accum.flush_warp();
+  }
+
+  cta_barrier_peers(a, 0);                            // every rank's grads are ready
+
+  const int base = a.rank * slice;
+  Vec16* mc = static_cast<Vec16*>(a.mc_buf);
+  int cur[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) cur[u] = -1;
+  for (int it = 0; it < iters; ++it) {
+    Vec16 in[U], pv[U];
+    int idx[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      idx[u] = first + (it * U + u) * stride;
+      if (idx[u] < slice) {
+        in[u] = Multimem<T>::ld_reduce(mc + base + idx[u]);
+        if (HAS_PINV) pv[u] = ld_vec(static_cast<const Vec16*>(a.pinv) + base + idx[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float sq[2] = {0.f, 0.f};
+      int g = -1;
+      if (idx[u] < slice) {
+        const int v = base + idx[u];
+        float x[N], pinv[N];
+        unpack<T>(in[u], x);
+        if (HAS_PINV) unpack<T>(pv[u], pinv);
+#pragma unroll
+        for (int e = 0; e < N; ++e) {
+          x[e] *= a.scale;
+          const float y = HAS_PINV ? x[e] / pinv[e] : x[e];
+          sq[1] = fmaf(y, y, sq[1]);
+        }
+        multimem_st(mc + v, pack<T>(x));
+        if (cur[u] < 0) cur[u] = seg_find(a.segs, v);
+        while (__ldg(a.segs.seg_end + cur[u]) <= v) ++cur[u];
+        g = __ldg(a.segs.seg_group + cur[u]);
+      }
+      accum.add(g, sq);
+    }
+  }
+  accum.flush_warp();
+  double* outs[2] = {a.want_local ? a.L : nullptr, a.T};
+  smem_stats_flush<2>(s_stats, a.n_groups, outs);
+
+  cta_barrier_peers(a, 1);                            // every slice has landed everywhere
 }
 
 // ---------------------------------------------------------------------------
@@ -552,6 +702,8 @@ static int set_attrs_for() {
   ADL_CHECK(cudaFuncSetAttribute(allreduce_gns_kernel<T, W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
   ADL_AR_ATTR(0) ADL_AR_ATTR(1) ADL_AR_ATTR(2) ADL_AR_ATTR(4) ADL_AR_ATTR(8)
 #undef ADL_AR_ATTR
+  ADL_CHECK(cudaFuncSetAttribute(allreduce_nvls_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+  ADL_CHECK(cudaFuncSetAttribute(allreduce_nvls_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
   ADL_CHECK(cudaFuncSetAttribute(local_kernel<T, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
   ADL_CHECK(cudaFuncSetAttribute(local_kernel<T, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
   ADL_CHECK(cudaFuncSetAttribute(local_kernel<T, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
@@ -605,6 +757,15 @@ int adl_allreduce_gns(const ReduceArgs* args, int dtype, int grid, void* stream)
       default: LAUNCH_AR_W(T, P, 0); break;                    \
     }                                                          \
   } while (0)
+#define LAUNCH_NVLS(T, P) allreduce_nvls_kernel<T, P><<<grid, ADL_THREADS, smem, s>>>(*args)
+  if (args->mc_buf != nullptr && args->world > 1) {
+    if (dtype == 0) { if (pinv) LAUNCH_NVLS(float, true); else LAUNCH_NVLS(float, false); }
+    else if (dtype == 1) { if (pinv) LAUNCH_NVLS(__nv_bfloat16, true); else LAUNCH_NVLS(__nv_bfloat16, false); }
+    else if (dtype == 2) { if (pinv) LAUNCH_NVLS(__half, true); else LAUNCH_NVLS(__half, false); }
+    else return -2;
+    return (int)cudaGetLastError();
+  }
+#undef LAUNCH_NVLS
   if (dtype == 0) { if (pinv) LAUNCH_AR(float, true); else LAUNCH_AR(float, false); }
   else if (dtype == 1) { if (pinv) LAUNCH_AR(__nv_bfloat16, true); else LAUNCH_AR(__nv_bfloat16, false); }
   else if (dtype == 2) { if (pinv) LAUNCH_AR(__half, true); else LAUNCH_AR(__half, false); }

@@ -85,7 +85,8 @@ def main():
                "fused_busbw_GBps": bus / fused / 1e6,
                "nccl_busbw_GBps": bus / nccl / 1e6,
                "fused_frac_of_770": bus / fused / 1e6 / 770.0,
-               "provider": red._provider.name, "ctas": red._reduce_ctas}
+               "provider": red._provider.name, "ctas": red._reduce_ctas,
+               "nvls": bool(getattr(red, "nvls_launches", 0))}
         rows.append(row)
         if rank == 0:
             print(json.dumps(row), flush=True)
