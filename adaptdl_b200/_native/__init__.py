@@ -25,7 +25,7 @@ CSRC = os.path.join(_ROOT, "csrc")
 LIB_PATH = os.path.join(_HERE, "libadl_b200.so")
 STAMP_PATH = os.path.join(_HERE, "libadl_b200.stamp")
 
-SOURCES = ["adl_kernels.cu", "adl_optim.cu", "adl_symm.cpp"]
+SOURCES = ["adl_kernels.cu", "adl_optim.cu", "adl_gemm.cu", "adl_symm.cpp"]
 HEADERS = ["adl_common.cuh"]
 
 NVCC_FLAGS = [
@@ -242,6 +242,10 @@ def _declare(lib):
     lib.adl_mc_bind.argtypes = [c.c_ulonglong, c.c_ulonglong, c.c_size_t]
     lib.adl_fused_optim.argtypes = [c.POINTER(OptimArgs), c.c_int, c.c_int,
                                     c.c_int, c.c_void_p]
+    lib.adl_gemm_bias_act.argtypes = [
+        c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p,
+        c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, c.c_int,
+        c.c_void_p, c.c_void_p]
     for name, struct in (("adl_sizeof_optim_args", OptimArgs),
                          ("adl_sizeof_reduce_args", ReduceArgs),
                          ("adl_sizeof_local_args", LocalArgs),

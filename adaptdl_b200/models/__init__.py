@@ -10,3 +10,5 @@ from .transformer_lm import TransformerModel  # noqa: F401
 from .ncf import NCF  # noqa: F401
 from .dcgan import Generator, Discriminator  # noqa: F401
 from .simple import LinearRegression, MnistNet  # noqa: F401
+from . import cifar_zoo  # noqa: F401,E402
+from .cifar_zoo import get_model  # noqa: F401,E402

@@ -13,6 +13,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from adaptdl_b200.ops.linear_act import linear_act
+
 __all__ = ["BertModel", "MLMTask", "NextSentenceTask", "QuestionAnswerTask",
            "bert_base_mlm"]
 
@@ -63,8 +65,12 @@ class EncoderLayer(nn.Module):
         attn = attn.transpose(1, 2).reshape(n, s, e)
         x = self.norm1(x + F.dropout(self.out_proj(attn), self.drop,
                                      self.training))
-        h = self.linear2(F.dropout(self.activation(self.linear1(x)),
-                                   self.drop, self.training))
+        if self.activation is F.gelu:
+            # bias + GELU fused into the tcgen05 GEMM epilogue on B200
+            h = linear_act(x, self.linear1.weight, self.linear1.bias, "gelu")
+        else:
+            h = self.activation(self.linear1(x))
+        h = self.linear2(F.dropout(h, self.drop, self.training))
         return self.norm2(x + F.dropout(h, self.drop, self.training))
 
 

@@ -4,39 +4,43 @@
 //   (optionally also stores the pre-activation Z for the backward pass)
 //
 // This is the feed-forward up-projection of the BERT / transformer workloads
-// (examples/BERT: 768 -> 3072 + GELU): PyTorch runs it as cuBLAS GEMM + a
-// bias kernel + a GELU kernel, i.e. the [M, 3072] activation makes three
-// extra HBM round trips. Here the epilogue is applied to the accumulator
-// while it is still in tensor memory.
+// (examples/BERT: 768 -> 3072 + GELU): PyTorch runs it as a cuBLASLt GEMM
+// (bias epilogue) + a GELU kernel, i.e. the [M, 3072] pre-activation is
+// written, read back and the activation written again. Here bias + GELU are
+// applied to the accumulator while it is still in tensor memory and both
+// tensors the backward pass needs leave the SM once.
 //
-// Structure (one CTA per 128 x BLOCK_N output tile, 192 threads):
-//   warp 0   TMA producer: cp.async.bulk.tensor loads of the A (128 x 64) and
-//            B (BLOCK_N x 64) K-slices into a STAGES-deep shared-memory ring
-//            (128-byte swizzle), completion on mbarriers (complete_tx::bytes)
-//   warp 1   MMA issuer: one elected lane issues tcgen05.mma.cta_group::1
-//            .kind::f16 (M=128, N=BLOCK_N, K=16) x4 per stage, accumulating in
-//            TMEM; tcgen05.commit releases the smem stage / signals the epilogue
-//            (warp 1 also allocates / frees the TMEM columns)
-//   warps 2-5  epilogue: tcgen05.ld (32 lanes x 32 columns per warp), + bias,
-//            GELU, bf16 pack, 128-bit stores
+// Persistent kernel, one CTA per SM, 320 threads, static round-robin tiles of
+// 128 x BLOCK_N:
+//   warp 0     TMA producer: cp.async.bulk.tensor loads of the A (128 x 64) and
+//              B (BLOCK_N x 64) K-slices into a STAGES-deep shared-memory ring
+//              (128-byte swizzle), completion on mbarriers (complete_tx::bytes);
+//              the ring keeps running across tile boundaries
+//   warp 1     MMA issuer: one elected lane issues tcgen05.mma.cta_group::1
+//              .kind::f16 (M=128, N=BLOCK_N, K=16) x4 per stage into one of TWO
+//              TMEM accumulators; tcgen05.commit frees the smem stage and, after
+//              the last K-slice, hands the accumulator to the epilogue
+//   warps 2-9  epilogue (two warps per 32-lane TMEM quarter, each half of the
+//              columns): tcgen05.ld 32x32b.x32, + bias (smem), GELU, bf16 pack,
+//              128-bit stores; the next tile's MMAs run meanwhile in the other
+//              accumulator
 //
-// Every wait loop is bounded: a stuck pipeline sets an error flag and the CTA
-// exits instead of hanging the GPU.
+// Every wait is bounded: a stuck pipeline raises an error flag and the CTA
+// drains instead of hanging the GPU.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <stdint.h>
-#include <stdio.h>
 
 namespace {
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;                  // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 4;
-constexpr int NUM_THREADS = 192;             // warp0 TMA, warp1 MMA, warps 2..5 epilogue
-constexpr uint32_t SPIN_LIMIT = 1u << 26;
+constexpr int EPI_WARPS = 8;
+constexpr int NUM_THREADS = 64 + EPI_WARPS * 32;
+constexpr uint32_t SPIN_LIMIT = 1u << 22;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -56,7 +60,10 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
                :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// bounded wait; returns false on timeout
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+// bounded wait; false on timeout (the caller abandons its loop)
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, uint32_t* err) {
   const uint32_t addr = smem_u32(bar);
   for (uint32_t spin = 0; spin < SPIN_LIMIT; ++spin) {
@@ -98,7 +105,7 @@ __device__ __forceinline__ void tcgen05_mma_f16(uint32_t tmem_d, uint64_t desc_a
 
 // Shared-memory matrix descriptor, K-major operand, 128-byte swizzle:
 //   bits [ 0,14) start address >> 4        bits [16,30) leading byte offset >> 4 (unused here)
-//   bits [32,46) stride byte offset >> 4   (8 rows x 128 B = 1024 B between core-matrix groups)
+//   bits [32,46) stride byte offset >> 4   (8 rows x 128 B = 1024 B between 8-row groups)
 //   bits [46,48) descriptor version = 1    bits [61,64) layout type: 2 = SWIZZLE_128B
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   uint64_t desc = 0;
@@ -115,8 +122,23 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+// exact-GELU to well below bf16 resolution: erf by Abramowitz-Stegun 7.1.26
+// (|err| < 1.5e-7 + fast-math exp/rcp error), 2 MUFU + ~10 FMA-pipe ops.
 __device__ __forceinline__ float gelu_erf(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = 1.0f - p * t * __expf(-z * z);      // erf(|x|/sqrt2)
+  const float half_x = 0.5f * x;
+  return fmaf(copysignf(e, x), half_x, half_x);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
 }
 
 struct GemmArgs {
@@ -128,93 +150,129 @@ struct GemmArgs {
   uint32_t* err;
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, int STAGES>
+struct SmemLayout {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
+  static constexpr int BIAS_BYTES = EPI_WARPS * (BLOCK_N / 2) * 4;
+  static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
+  static constexpr int TOTAL = 1024 + RING_BYTES + BIAS_BYTES + BAR_BYTES;
+};
+
+template <int BLOCK_N, int STAGES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bias_act_kernel(const __grid_constant__ CUtensorMap map_a,
                      const __grid_constant__ CUtensorMap map_b, const GemmArgs args) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // 1024-byte alignment is required by the 128 B swizzle atoms
+  using L = SmemLayout<BLOCK_N, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  // the 128 B swizzle atoms need 1024-byte alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
-  constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
-  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  float* bias_s = reinterpret_cast<float*>(smem + L::RING_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::RING_BYTES + L::BIAS_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + STAGES;      // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m_blk = blockIdx.y, n_blk = blockIdx.x;
   const int num_k = args.K / BLOCK_K;
+  const int tiles_n = args.N / BLOCK_N;
+  const int tiles_m = (args.M + BLOCK_M - 1) / BLOCK_M;
+  const int num_tiles = tiles_m * tiles_n;
+  constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;        // two accumulators (256 or 512 columns)
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" :: "l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" :: "l"(&map_b) : "memory");
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(tmem_full_bar, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {                      // TMEM: BLOCK_N fp32 columns x 128 lanes
+  if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                 :: "r"(smem_u32(tmem_base_slot)), "r"(BLOCK_N) : "memory");
+                 :: "r"(smem_u32(tmem_base_slot)), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
-  const uint32_t tmem_acc = *reinterpret_cast<volatile uint32_t*>(tmem_base_slot);
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_base_slot);
 
   if (warp == 0) {
     // ===== TMA producer =====
     if (elect_one()) {
-      for (int k = 0; k < num_k; ++k) {
-        const int s = k % STAGES;
-        const uint32_t phase = (k / STAGES) & 1;
-        if (!mbar_wait(&empty_bar[s], phase ^ 1, args.err)) break;
-        uint8_t* a_dst = smem + s * STAGE_BYTES;
-        uint8_t* b_dst = a_dst + A_BYTES;
-        mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-        tma_load_2d(a_dst, &map_a, &full_bar[s], k * BLOCK_K, m_blk * BLOCK_M);
-        tma_load_2d(b_dst, &map_b, &full_bar[s], k * BLOCK_K, n_blk * BLOCK_N);
+      uint32_t it = 0;                               // global K-slice counter -> ring slot/phase
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x) {
+        const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
+        for (int k = 0; k < num_k; ++k, ++it) {
+          const uint32_t s = it % STAGES, phase = (it / STAGES) & 1;
+          if (!mbar_wait(&empty_bar[s], phase ^ 1, args.err)) { ok = false; break; }
+          uint8_t* a_dst = smem + s * L::STAGE_BYTES;
+          mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
+          tma_load_2d(a_dst, &map_a, &full_bar[s], k * BLOCK_K, m_blk * BLOCK_M);
+          tma_load_2d(a_dst + L::A_BYTES, &map_b, &full_bar[s], k * BLOCK_K, n_blk * BLOCK_N);
+        }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N);
-    for (int k = 0; k < num_k; ++k) {
-      const int s = k % STAGES;
-      const uint32_t phase = (k / STAGES) & 1;
-      if (!mbar_wait(&full_bar[s], phase, args.err)) break;
+    uint32_t it = 0, local_tile = 0;
+    bool ok = true;
+    for (int tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x, ++local_tile) {
+      const uint32_t acc = local_tile & 1, acc_phase = (local_tile >> 1) & 1;
+      // the epilogue must have drained this accumulator (passes at once the first two times)
+      if (!mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1, args.err)) break;
       tcgen05_fence_after();
-      if (elect_one()) {
-        const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
-        const uint32_t b_addr = a_addr + A_BYTES;
-        const uint64_t a_desc = make_smem_desc(a_addr);
-        const uint64_t b_desc = make_smem_desc(b_addr);
+      const uint32_t tmem_acc = tmem_base + acc * BLOCK_N;
+      for (int k = 0; k < num_k; ++k, ++it) {
+        const uint32_t s = it % STAGES, phase = (it / STAGES) & 1;
+        if (!mbar_wait(&full_bar[s], phase, args.err)) { ok = false; break; }
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const uint32_t a_addr = smem_u32(smem + s * L::STAGE_BYTES);
+          const uint64_t a_desc = make_smem_desc(a_addr);
+          const uint64_t b_desc = make_smem_desc(a_addr + L::A_BYTES);
 #pragma unroll
-        for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
-          // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in (addr >> 4) units
-          tcgen05_mma_f16(tmem_acc, a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), idesc,
-                          (k > 0 || kk > 0) ? 1u : 0u);
+          for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
+            // +16 bf16 = +32 B inside the 128 B swizzle row: +2 in (addr >> 4) units
+            tcgen05_mma_f16(tmem_acc, a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), idesc,
+                            (k > 0 || kk > 0) ? 1u : 0u);
+          }
+          tcgen05_commit(&empty_bar[s]);               // smem stage reusable once these MMAs retire
+          if (k == num_k - 1) tcgen05_commit(&tmem_full_bar[acc]);
         }
-        tcgen05_commit(&empty_bar[s]);                 // smem stage reusable once the MMAs retire
-        if (k == num_k - 1) tcgen05_commit(tmem_full_bar);
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else {
-    // ===== epilogue warps 2..5: TMEM lanes 32*(warp%4) .. +31 =====
+    // ===== epilogue: TMEM lanes 32*(warp%4) .. +31, columns half (warp-2)/4 =====
     const int lane_grp = warp & 3;
-    if (mbar_wait(tmem_full_bar, 0, args.err)) {
+    const int col_half = (warp - 2) >> 2;
+    constexpr int HALF_N = BLOCK_N / 2;
+    float* my_bias = bias_s + (warp - 2) * HALF_N;
+    uint32_t local_tile = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_tile) {
+      const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
+      const uint32_t acc = local_tile & 1, acc_phase = (local_tile >> 1) & 1;
+      const int col_base = n_blk * BLOCK_N + col_half * HALF_N;
+      // this warp's bias slice -> its private smem (overlaps the wait for the MMAs)
+      __syncwarp();
+      for (int c = lane; c < HALF_N; c += 32) my_bias[c] = args.bias ? __ldg(args.bias + col_base + c) : 0.f;
+      __syncwarp();
+      if (!mbar_wait(&tmem_full_bar[acc], acc_phase, args.err)) break;
       tcgen05_fence_after();
       const int row = m_blk * BLOCK_M + lane_grp * 32 + lane;
-      __nv_bfloat16* y_row = args.y + (size_t)row * args.N + (size_t)n_blk * BLOCK_N;
-      __nv_bfloat16* z_row = args.z ? args.z + (size_t)row * args.N + (size_t)n_blk * BLOCK_N : nullptr;
+      const bool row_ok = row < args.M;
+      const size_t out_off = (size_t)row * args.N + col_base;
+      const uint32_t taddr0 = tmem_base + acc * BLOCK_N + col_half * HALF_N + ((uint32_t)(lane_grp * 32) << 16);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      for (int c0 = 0; c0 < HALF_N; c0 += 32) {
         uint32_t r[32];
-        const uint32_t taddr = tmem_acc + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)c0;
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -223,36 +281,38 @@ gemm_bias_act_kernel(const __grid_constant__ CUtensorMap map_a,
               "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
               "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
               "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-            : "r"(taddr) : "memory");
+            : "r"(taddr0 + (uint32_t)c0) : "memory");
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (row < args.M) {
-          const int col0 = n_blk * BLOCK_N + c0;
+        if (c0 + 32 >= HALF_N) {
+          // accumulator fully read: hand it back so the MMAs of tile+2 can start
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        }
+        if (row_ok) {
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
+            const float4 b0 = *reinterpret_cast<const float4*>(my_bias + c0 + j);
+            const float4 b1 = *reinterpret_cast<const float4*>(my_bias + c0 + j + 4);
             float v[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              v[e] = __uint_as_float(r[j + e]);
-              if (args.bias) v[e] += __ldg(args.bias + col0 + j + e);
-            }
-            if (z_row) {
+            v[0] = __uint_as_float(r[j + 0]) + b0.x; v[1] = __uint_as_float(r[j + 1]) + b0.y;
+            v[2] = __uint_as_float(r[j + 2]) + b0.z; v[3] = __uint_as_float(r[j + 3]) + b0.w;
+            v[4] = __uint_as_float(r[j + 4]) + b1.x; v[5] = __uint_as_float(r[j + 5]) + b1.y;
+            v[6] = __uint_as_float(r[j + 6]) + b1.z; v[7] = __uint_as_float(r[j + 7]) + b1.w;
+            if (args.z) {
               uint4 zp;
-              __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
-              zp.x = *reinterpret_cast<uint32_t*>(&h0); zp.y = *reinterpret_cast<uint32_t*>(&h1);
-              zp.z = *reinterpret_cast<uint32_t*>(&h2); zp.w = *reinterpret_cast<uint32_t*>(&h3);
-              *reinterpret_cast<uint4*>(z_row + c0 + j) = zp;
+              zp.x = pack_bf16(v[0], v[1]); zp.y = pack_bf16(v[2], v[3]);
+              zp.z = pack_bf16(v[4], v[5]); zp.w = pack_bf16(v[6], v[7]);
+              *reinterpret_cast<uint4*>(args.z + out_off + c0 + j) = zp;
             }
             if (args.act == 1) {
 #pragma unroll
               for (int e = 0; e < 8; ++e) v[e] = gelu_erf(v[e]);
             }
             uint4 yp;
-            __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
-            yp.x = *reinterpret_cast<uint32_t*>(&h0); yp.y = *reinterpret_cast<uint32_t*>(&h1);
-            yp.z = *reinterpret_cast<uint32_t*>(&h2); yp.w = *reinterpret_cast<uint32_t*>(&h3);
-            *reinterpret_cast<uint4*>(y_row + c0 + j) = yp;
+            yp.x = pack_bf16(v[0], v[1]); yp.y = pack_bf16(v[2], v[3]);
+            yp.z = pack_bf16(v[4], v[5]); yp.w = pack_bf16(v[6], v[7]);
+            *reinterpret_cast<uint4*>(args.y + out_off + c0 + j) = yp;
           }
         }
       }
@@ -263,7 +323,7 @@ gemm_bias_act_kernel(const __grid_constant__ CUtensorMap map_a,
   __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_acc), "r"(BLOCK_N) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -275,6 +335,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
                                   CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode = nullptr;
+int g_num_sms = 0;
 
 bool load_encode() {
   if (g_encode) return true;
@@ -297,18 +358,20 @@ int make_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, ui
   return (int)r;
 }
 
-template <int BLOCK_N>
-int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& a, cudaStream_t s) {
-  constexpr int smem = STAGES * (BLOCK_M * BLOCK_K * 2 + BLOCK_N * BLOCK_K * 2) + 1024 + 256;
+template <int BLOCK_N, int STAGES>
+int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& a, int max_ctas, cudaStream_t s) {
+  constexpr int smem = SmemLayout<BLOCK_N, STAGES>::TOTAL;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bias_act_kernel<BLOCK_N>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_bias_act_kernel<BLOCK_N, STAGES>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  dim3 grid(a.N / BLOCK_N, (a.M + BLOCK_M - 1) / BLOCK_M);
-  gemm_bias_act_kernel<BLOCK_N><<<grid, NUM_THREADS, smem, s>>>(ma, mb, a);
+  const int tiles = (a.N / BLOCK_N) * ((a.M + BLOCK_M - 1) / BLOCK_M);
+  int grid = tiles < g_num_sms ? tiles : g_num_sms;
+  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+  gemm_bias_act_kernel<BLOCK_N, STAGES><<<grid, NUM_THREADS, smem, s>>>(ma, mb, a);
   return (int)cudaGetLastError();
 }
 
@@ -318,15 +381,23 @@ extern "C" int adl_bind_thread();
 
 extern "C" {
 
-// y[M,N] (and optionally z) = act(x[M,K] @ w[N,K]^T + bias). bf16 row-major; K % 64 == 0,
-// N % 128 == 0. Returns 0, a CUDA error code, or a negative shape/driver error.
+// y[M,N] (and optionally z) = act(x[M,K] @ w[N,K]^T + bias). bf16 row-major, 16-byte aligned
+// rows; K % 64 == 0, N % 128 == 0. block_n: 0 = auto, 128 or 256. Returns 0, a CUDA error
+// code, or a negative shape/driver error.
 int adl_gemm_bias_act(const void* x, const void* w, const float* bias, void* y, void* z, int M, int N,
-                      int K, int act, void* err, void* stream) {
+                      int K, int act, int block_n, int max_ctas, void* err, void* stream) {
   if (K % BLOCK_K != 0 || N % 128 != 0 || M <= 0) return -10;
   if (!load_encode()) return -11;
   if (int rc = adl_bind_thread()) return rc;
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  if (block_n == 0) block_n = (N % 256 == 0) ? 256 : 128;
+  if (block_n != 128 && !(block_n == 256 && N % 256 == 0)) return -12;
   CUtensorMap ma, mb;
-  const int block_n = (N % 256 == 0 && (long long)M * N >= (1ll << 22)) ? 256 : 128;
   if (int rc = make_map(&ma, x, (uint64_t)M, (uint64_t)K, BLOCK_M)) return -100 - rc;
   if (int rc = make_map(&mb, w, (uint64_t)N, (uint64_t)K, (uint32_t)block_n)) return -200 - rc;
   GemmArgs a;
@@ -336,8 +407,8 @@ int adl_gemm_bias_act(const void* x, const void* w, const float* bias, void* y, 
   a.M = M; a.N = N; a.K = K; a.act = act;
   a.err = static_cast<uint32_t*>(err);
   cudaStream_t s = (cudaStream_t)stream;
-  if (block_n == 256) return launch<256>(ma, mb, a, s);
-  return launch<128>(ma, mb, a, s);
+  if (block_n == 256) return launch<256, 4>(ma, mb, a, max_ctas, s);
+  return launch<128, 6>(ma, mb, a, max_ctas, s);
 }
 
 }  // extern "C"

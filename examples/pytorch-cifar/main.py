@@ -26,9 +26,7 @@ from torch.utils.data import TensorDataset  # noqa: E402
 import adaptdl_b200.torch as adl  # noqa: E402
 from adaptdl_b200 import env, models  # noqa: E402
 
-MODELS = {"ResNet18": models.resnet18, "ResNet34": models.resnet34,
-          "ResNet50": models.resnet50, "ResNet101": models.resnet101,
-          "ResNet152": models.resnet152}
+MODELS = models.cifar_zoo.MODELS
 
 
 def load_data(args):

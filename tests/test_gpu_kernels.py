@@ -388,3 +388,58 @@ def test_checkpoint_roundtrip_with_device_engine(tmp_path):
     probe = {}
     net.engine.pull_gns_state(probe)
     np.testing.assert_allclose(probe["sqr_avg"], gns["sqr_avg"])
+
+
+# ---------------------------------------------------------------------------
+# tcgen05 Linear + bias + GELU (csrc/adl_gemm.cu)
+# ---------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("m,n,k,block_n", [
+    (128, 128, 64, 128), (256, 256, 128, 256), (1000, 384, 192, 128),
+    (4096, 3072, 768, 256), (4096, 3072, 768, 128), (77, 512, 1024, 0)])
+def test_tcgen05_linear_gelu_forward(m, n, k, block_n):
+    from adaptdl_b200.ops import check_errors, gemm_bias_act
+    torch.manual_seed(m + n + k)
+    dev = torch.device("cuda:0")
+    x = torch.randn(m, k, device=dev).bfloat16()
+    w = (torch.randn(n, k, device=dev) / k ** 0.5).bfloat16()
+    b = torch.randn(n, device=dev)
+    y, z = gemm_bias_act(x, w, b, "gelu", True, block_n=block_n)
+    torch.cuda.synchronize()
+    check_errors()
+    ref_z = x.float() @ w.float().t() + b
+    ref_y = torch.nn.functional.gelu(ref_z)
+    # bf16 output rounding: 2^-8 relative
+    assert torch.allclose(z.float(), ref_z, rtol=1e-2, atol=2e-2)
+    assert torch.allclose(y.float(), ref_y, rtol=1e-2, atol=2e-2)
+    y2, z2 = gemm_bias_act(x, w, None, "identity", False, block_n=block_n)
+    assert z2 is None
+    assert torch.allclose(y2.float(), x.float() @ w.float().t(),
+                          rtol=1e-2, atol=2e-2)
+    check_errors()
+
+
+@pytest.mark.gpu
+def test_tcgen05_linear_gelu_autograd_matches_torch():
+    from adaptdl_b200.ops import LinearGELU, check_errors
+    torch.manual_seed(3)
+    dev = torch.device("cuda:0")
+    fused = LinearGELU(256, 512).to(dev)
+    plain = torch.nn.Linear(256, 512).to(dev)
+    plain.load_state_dict(fused.state_dict())
+    x1 = torch.randn(4, 96, 256, device=dev, requires_grad=True)
+    x2 = x1.detach().clone().requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y1 = fused(x1)
+        y2 = torch.nn.functional.gelu(plain(x2))
+    assert y1.dtype == torch.bfloat16
+    g = torch.randn_like(y1)
+    y1.backward(g)
+    y2.backward(g)
+    check_errors()
+    assert torch.allclose(y1.float(), y2.float(), rtol=2e-2, atol=2e-2)
+    for a, b in ((x1.grad, x2.grad), (fused.weight.grad, plain.weight.grad),
+                 (fused.bias.grad, plain.bias.grad)):
+        assert a.dtype == b.dtype and a.shape == b.shape
+        scale = b.abs().max().item()
+        assert (a - b).abs().max().item() <= 3e-2 * scale + 1e-3
