@@ -122,23 +122,98 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-// exact-GELU to well below bf16 resolution: erf by Abramowitz-Stegun 7.1.26
-// (|err| < 1.5e-7 + fast-math exp/rcp error), 2 MUFU + ~10 FMA-pipe ops.
-__device__ __forceinline__ float gelu_erf(float x) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float e = 1.0f - p * t * __expf(-z * z);      // erf(|x|/sqrt2)
-  const float half_x = 0.5f * x;
-  return fmaf(copysignf(e, x), half_x, half_x);
+// ---- packed fp32x2 arithmetic (FFMA2 / FMUL2 / FADD2: two lanes per issue slot) ----
+__device__ __forceinline__ uint64_t pk(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t pk_u(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ float fma_sat(float a, float b, float c) {
+  float r;
+  asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+// bf16x2 word: low half = lo, high half = hi
+__device__ __forceinline__ uint32_t pack_bf16(uint64_t v) {
+  float lo, hi;
+  upk(v, lo, hi);
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
 
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
+// GELU(x) = x * Phi(x) for two lanes at once, no MUFU and no branches:
+//   Phi(x) = sat(0.5 + 0.5 * x * Q(x^2)),  x*Q(x^2) ~ erf(x / sqrt 2) on |x| <= 4.2
+// Q is a degree-8 minimax fit; its positive leading coefficient makes x*Q(x^2) run
+// off to +-inf beyond the fit range, so the saturating FMA supplies the exact 0 / 1
+// tails. |Phi error| < 1.4e-5 for every finite x (|GELU error| < 6e-5, i.e. below
+// the bf16 resolution of the output for |y| > 0.015).
+__device__ __forceinline__ uint64_t gelu2(uint64_t x) {
+  const uint64_t s = mul2(x, x);
+  uint64_t q = fma2(s, pk(1.1996946e-10f, 1.1996946e-10f), pk(-1.1267203e-08f, -1.1267203e-08f));
+  q = fma2(q, s, pk(4.6875110e-07f, 4.6875110e-07f));
+  q = fma2(q, s, pk(-1.1521784e-05f, -1.1521784e-05f));
+  q = fma2(q, s, pk(1.8915090e-04f, 1.8915090e-04f));
+  q = fma2(q, s, pk(-2.2283061e-03f, -2.2283061e-03f));
+  q = fma2(q, s, pk(1.9660283e-02f, 1.9660283e-02f));
+  q = fma2(q, s, pk(-1.3272072e-01f, -1.3272072e-01f));
+  q = fma2(q, s, pk(7.9781479e-01f, 7.9781479e-01f));
+  float t0, t1;
+  upk(mul2(x, q), t0, t1);
+  return mul2(x, pk(fma_sat(t0, 0.5f, 0.5f), fma_sat(t1, 0.5f, 0.5f)));
+}
+
+__device__ __forceinline__ void st_global_256(void* p, const uint32_t (&w)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               :: "l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+               : "memory");
+}
+
+// 32 lanes x 32 consecutive fp32 columns of the accumulator -> 32 registers per thread
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+}
+// Wait for this thread's outstanding tcgen05.ld. The registers are in/out operands so
+// that no consumer of r[] can be scheduled above the wait.
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.wait::ld.sync.aligned;"
+      : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+        "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+        "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+        "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+      :: "memory");
 }
 
 struct GemmArgs {
@@ -156,9 +231,8 @@ struct SmemLayout {
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
-  static constexpr int BIAS_BYTES = EPI_WARPS * (BLOCK_N / 2) * 4;
   static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
-  static constexpr int TOTAL = 1024 + RING_BYTES + BIAS_BYTES + BAR_BYTES;
+  static constexpr int TOTAL = 1024 + RING_BYTES + BAR_BYTES;
 };
 
 template <int BLOCK_N, int STAGES>
@@ -169,8 +243,8 @@ gemm_bias_act_kernel(const __grid_constant__ CUtensorMap map_a,
   extern __shared__ uint8_t smem_raw[];
   // the 128 B swizzle atoms need 1024-byte alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float* bias_s = reinterpret_cast<float*>(smem + L::RING_BYTES);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::RING_BYTES + L::BIAS_BYTES);
+  __shared__ __align__(16) float bias_s[EPI_WARPS * (BLOCK_N / 2)];
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::RING_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;      // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
@@ -254,15 +328,21 @@ gemm_bias_act_kernel(const __grid_constant__ CUtensorMap map_a,
     const int lane_grp = warp & 3;
     const int col_half = (warp - 2) >> 2;
     constexpr int HALF_N = BLOCK_N / 2;
-    float* my_bias = bias_s + (warp - 2) * HALF_N;
+    constexpr int NCHUNK = HALF_N / 32;
+    float* my_bias = bias_s + (warp - 2) * HALF_N;     // private to this warp
     uint32_t local_tile = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_tile) {
       const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
       const uint32_t acc = local_tile & 1, acc_phase = (local_tile >> 1) & 1;
       const int col_base = n_blk * BLOCK_N + col_half * HALF_N;
-      // this warp's bias slice -> its private smem (overlaps the wait for the MMAs)
-      __syncwarp();
-      for (int c = lane; c < HALF_N; c += 32) my_bias[c] = args.bias ? __ldg(args.bias + col_base + c) : 0.f;
+      // this warp's bias slice -> smem: all loads in flight first, then the stores
+      float bpre[NCHUNK];
+#pragma unroll
+      for (int i = 0; i < NCHUNK; ++i)
+        bpre[i] = args.bias ? __ldg(args.bias + col_base + i * 32 + lane) : 0.f;
+      __syncwarp();                                    // previous tile's reads are done
+#pragma unroll
+      for (int i = 0; i < NCHUNK; ++i) my_bias[i * 32 + lane] = bpre[i];
       __syncwarp();
       if (!mbar_wait(&tmem_full_bar[acc], acc_phase, args.err)) break;
       tcgen05_fence_after();
@@ -270,20 +350,15 @@ gemm_bias_act_kernel(const __grid_constant__ CUtensorMap map_a,
       const bool row_ok = row < args.M;
       const size_t out_off = (size_t)row * args.N + col_base;
       const uint32_t taddr0 = tmem_base + acc * BLOCK_N + col_half * HALF_N + ((uint32_t)(lane_grp * 32) << 16);
-#pragma unroll 1
-      for (int c0 = 0; c0 < HALF_N; c0 += 32) {
-        uint32_t r[32];
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-              "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-              "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-            : "r"(taddr0 + (uint32_t)c0) : "memory");
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (c0 + 32 >= HALF_N) {
+      uint32_t r[2][32];                               // double-buffered TMEM reads
+      tmem_ld_32x32(taddr0, r[0]);
+#pragma unroll
+      for (int c = 0; c < NCHUNK; ++c) {
+        uint32_t (&cur)[32] = r[c & 1];
+        tmem_ld_wait(cur);
+        if (c + 1 < NCHUNK) {
+          tmem_ld_32x32(taddr0 + (uint32_t)((c + 1) * 32), r[(c + 1) & 1]);
+        } else {
           // accumulator fully read: hand it back so the MMAs of tile+2 can start
           tcgen05_fence_before();
           __syncwarp();
@@ -291,28 +366,27 @@ gemm_bias_act_kernel(const __grid_constant__ CUtensorMap map_a,
         }
         if (row_ok) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            const float4 b0 = *reinterpret_cast<const float4*>(my_bias + c0 + j);
-            const float4 b1 = *reinterpret_cast<const float4*>(my_bias + c0 + j + 4);
-            float v[8];
-            v[0] = __uint_as_float(r[j + 0]) + b0.x; v[1] = __uint_as_float(r[j + 1]) + b0.y;
-            v[2] = __uint_as_float(r[j + 2]) + b0.z; v[3] = __uint_as_float(r[j + 3]) + b0.w;
-            v[4] = __uint_as_float(r[j + 4]) + b1.x; v[5] = __uint_as_float(r[j + 5]) + b1.y;
-            v[6] = __uint_as_float(r[j + 6]) + b1.z; v[7] = __uint_as_float(r[j + 7]) + b1.w;
+          for (int j = 0; j < 32; j += 16) {
+            uint64_t v[8];
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const float4 b = *reinterpret_cast<const float4*>(my_bias + c * 32 + j + q4 * 4);
+              v[2 * q4] = add2(pk_u(cur[j + 4 * q4], cur[j + 4 * q4 + 1]), pk(b.x, b.y));
+              v[2 * q4 + 1] = add2(pk_u(cur[j + 4 * q4 + 2], cur[j + 4 * q4 + 3]), pk(b.z, b.w));
+            }
+            uint32_t w[8];
             if (args.z) {
-              uint4 zp;
-              zp.x = pack_bf16(v[0], v[1]); zp.y = pack_bf16(v[2], v[3]);
-              zp.z = pack_bf16(v[4], v[5]); zp.w = pack_bf16(v[6], v[7]);
-              *reinterpret_cast<uint4*>(args.z + out_off + c0 + j) = zp;
+#pragma unroll
+              for (int e = 0; e < 8; ++e) w[e] = pack_bf16(v[e]);
+              st_global_256(args.z + out_off + c * 32 + j, w);
             }
             if (args.act == 1) {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = gelu_erf(v[e]);
+              for (int e = 0; e < 8; ++e) v[e] = gelu2(v[e]);
             }
-            uint4 yp;
-            yp.x = pack_bf16(v[0], v[1]); yp.y = pack_bf16(v[2], v[3]);
-            yp.z = pack_bf16(v[4], v[5]); yp.w = pack_bf16(v[6], v[7]);
-            *reinterpret_cast<uint4*>(args.y + out_off + c0 + j) = yp;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) w[e] = pack_bf16(v[e]);
+            st_global_256(args.y + out_off + c * 32 + j, w);
           }
         }
       }

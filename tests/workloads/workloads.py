@@ -1,0 +1,154 @@
+"""Cluster / single-box workload suite.
+
+The reference ships its end-to-end tests as shell heredocs piped to the CLI
+(``tests/long-workload/*.sh`` x12, ``tests/short-workload/*.sh`` x2,
+``tests/testworkload.sh``, ``tests/test-localmode2.sh``). Here the same
+workloads are DATA: one table, three ways to use it --
+
+    python tests/workloads/workloads.py list
+    python tests/workloads/workloads.py yaml resnet18-cifar10-elastic       # AdaptDLJob manifest
+    python tests/workloads/workloads.py submit resnet18-cifar10-elastic     # through adaptdl_b200.cli
+    python tests/workloads/workloads.py local transformer-wikitext2-elastic \
+        --gpus 8 --schedule 2,4,8,4 --interval 30                           # no Kubernetes: sched.local
+
+``tests/test_cli.py::test_workload_specs_validate`` runs every manifest
+through the CLI's job preparation and the scheduler's validator on CPU.
+"""
+
+import argparse
+import copy
+import os
+import subprocess
+import sys
+
+import yaml
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(
+    os.path.abspath(__file__))))
+API_VERSION = "adaptdl.petuum.com/v1"
+
+# name -> (suite, script, args, spec overrides)
+WORKLOADS = {
+    "resnet18-cifar10-elastic": (
+        "long", "examples/pytorch-cifar/main.py",
+        ["--model=ResNet18", "--bs=128", "--lr=0.1", "--epochs=60",
+         "--autoscale-bsz"], {}),
+    "resnet18-cifar10-elastic-min-replicas": (
+        "long", "examples/pytorch-cifar/main.py",
+        ["--model=ResNet18", "--bs=128", "--lr=0.1", "--epochs=60",
+         "--autoscale-bsz"], {"minReplicas": 2, "maxReplicas": 4}),
+    "resnet18-cifar10-inelastic": (
+        "long", "examples/pytorch-cifar/main.py",
+        ["--model=ResNet18", "--bs=128", "--lr=0.1", "--epochs=60"],
+        {"minReplicas": 2, "maxReplicas": 2}),
+    "resnet18-cifar10-mixed-precision": (
+        "long", "examples/pytorch-cifar/main.py",
+        ["--model=ResNet18", "--bs=128", "--lr=0.1", "--epochs=60",
+         "--autoscale-bsz", "--mixed-precision"], {}),
+    "densenet121-cifar10": (
+        "long", "examples/pytorch-cifar/main.py",
+        ["--model=DenseNet121", "--bs=128", "--lr=0.1", "--epochs=60",
+         "--autoscale-bsz"], {}),
+    "bert": (
+        "long", "examples/BERT/mlm_task_adaptdl.py",
+        ["--epochs=1", "--batch_size=32", "--bptt=128", "--autoscale-bsz"],
+        {}),
+    "dcgan": (
+        "long", "examples/dcgan/dcgan.py",
+        ["--epochs=5", "--autoscale-bsz"], {}),
+    "ncf": (
+        "long", "examples/NCF/main.py",
+        ["--epochs=20", "--autoscale-bsz"], {}),
+    "ncf-accumulation": (
+        "long", "examples/NCF/main.py",
+        ["--epochs=20", "--autoscale-bsz", "--gradient-accumulation"], {}),
+    "transformer-wikitext2": (
+        "long", "examples/transformer/transformer.py",
+        ["--epochs=3", "--bs=20", "--lr=5.0"], {}),
+    "transformer-wikitext2-elastic": (
+        "long", "examples/transformer/transformer.py",
+        ["--epochs=3", "--bs=20", "--lr=5.0", "--autoscale-bsz"], {}),
+    "lr-elastic-cpu": (
+        "long", "examples/linear_regression/main.py",
+        ["--epochs=90", "--autoscale-bsz"], {"cpu": True}),
+    "resnet18-cifar10-short": (
+        "short", "examples/pytorch-cifar/main.py",
+        ["--model=ResNet18", "--bs=128", "--lr=0.1", "--epochs=2",
+         "--autoscale-bsz", "--synthetic"], {}),
+    "densenet121-cifar10-short": (
+        "short", "examples/pytorch-cifar/main.py",
+        ["--model=DenseNet121", "--bs=128", "--lr=0.1", "--epochs=2",
+         "--autoscale-bsz", "--synthetic"], {}),
+}
+
+
+def manifest(name, image_root="/root"):
+    """The AdaptDLJob object for workload ``name``."""
+    suite, script, args, overrides = WORKLOADS[name]
+    overrides = copy.deepcopy(overrides)
+    cpu = overrides.pop("cpu", False)
+    container = {
+        "name": "main",
+        "command": ["python3", os.path.join(image_root, script)] + list(args),
+        "env": [{"name": "PYTHONUNBUFFERED", "value": "true"}],
+    }
+    if cpu:
+        container["resources"] = {"limits": {"cpu": 1}}
+    else:
+        container["resources"] = {"limits": {"nvidia.com/gpu": 1}}
+    spec = {"template": {"spec": {"containers": [container]}}}
+    spec.update(overrides)
+    return {"apiVersion": API_VERSION, "kind": "AdaptDLJob",
+            "metadata": {"generateName": name + "-"}, "spec": spec}
+
+
+def local_command(name):
+    _, script, args, _ = WORKLOADS[name]
+    return [os.path.join(ROOT, script)] + list(args)
+
+
+def main(argv=None):
+    parser = argparse.ArgumentParser()
+    sub = parser.add_subparsers(dest="verb", required=True)
+    sub.add_parser("list")
+    p = sub.add_parser("yaml")
+    p.add_argument("name")
+    p = sub.add_parser("submit")
+    p.add_argument("name")
+    p.add_argument("--tensorboard", default=None)
+    p = sub.add_parser("local")
+    p.add_argument("name")
+    p.add_argument("--gpus", type=int, default=None)
+    p.add_argument("--schedule", default="")
+    p.add_argument("--interval", type=float, default=30.0)
+    p.add_argument("--adaptive", action="store_true")
+    args = parser.parse_args(argv)
+    if args.verb == "list":
+        for name, (suite, script, wargs, over) in sorted(WORKLOADS.items()):
+            print("{:6s} {:40s} {} {}".format(suite, name, script,
+                                              " ".join(wargs)))
+        return 0
+    if args.verb == "yaml":
+        print(yaml.safe_dump(manifest(args.name), sort_keys=False))
+        return 0
+    if args.verb == "submit":
+        cmd = [sys.executable, "-m", "adaptdl_b200.cli", "submit", ROOT,
+               "-d", os.path.join(ROOT, "examples", "Dockerfile"), "-f", "-",
+               "--checkpoint-storage-size", "1Gi"]
+        if args.tensorboard:
+            cmd += ["--tensorboard", args.tensorboard]
+        return subprocess.run(cmd, input=yaml.safe_dump(
+            manifest(args.name)).encode()).returncode
+    cmd = [sys.executable, "-m", "adaptdl_b200.sched.local"]
+    if args.gpus:
+        cmd += ["--gpus", str(args.gpus)]
+    if args.schedule:
+        cmd += ["--schedule", args.schedule]
+    if args.adaptive:
+        cmd += ["--adaptive"]
+    cmd += ["--interval", str(args.interval)] + local_command(args.name)
+    return subprocess.run(cmd, env=dict(os.environ, PYTHONPATH=ROOT)).returncode
+
+
+if __name__ == "__main__":
+    sys.exit(main())
