@@ -244,7 +244,7 @@ def _declare(lib):
                                     c.c_int, c.c_void_p]
     lib.adl_gemm_bias_act.argtypes = [
         c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p,
-        c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, c.c_int,
+        c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, c.c_int,
         c.c_void_p, c.c_void_p]
     for name, struct in (("adl_sizeof_optim_args", OptimArgs),
                          ("adl_sizeof_reduce_args", ReduceArgs),

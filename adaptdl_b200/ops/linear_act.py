@@ -53,10 +53,11 @@ def supported(x, weight):
 
 
 def gemm_bias_act(x2d, weight, bias, act="gelu", save_preact=True,
-                  block_n=0, max_ctas=0):
+                  block_n=0, cluster_m=0, max_ctas=0):
     """Raw kernel call. ``x2d`` [M, K] bf16, ``weight`` [N, K] bf16, ``bias``
     [N] fp32 or None. Returns ``(y, z)`` (``z`` is None unless
-    ``save_preact``)."""
+    ``save_preact``). ``block_n`` (128/256) and ``cluster_m`` (1/2/4 CTAs
+    sharing a multicast weight tile) default to a shape-based choice."""
     from adaptdl_b200 import _native
     lib = _native.load()
     assert x2d.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16
@@ -75,7 +76,7 @@ def gemm_bias_act(x2d, weight, bias, act="gelu", save_preact=True,
         x2d.data_ptr(), weight.data_ptr(),
         bias.data_ptr() if bias is not None else None,
         y.data_ptr(), z.data_ptr() if z is not None else None,
-        m, n, k, _ACT[act], block_n, max_ctas,
+        m, n, k, _ACT[act], block_n, cluster_m, max_ctas,
         _err_flag(x2d.device).data_ptr(),
         torch.cuda.current_stream(x2d.device).cuda_stream)
     if code < 0:

@@ -21,9 +21,10 @@
 //              TMEM accumulators; tcgen05.commit frees the smem stage and, after
 //              the last K-slice, hands the accumulator to the epilogue
 //   warps 2-9  epilogue (two warps per 32-lane TMEM quarter, each half of the
-//              columns): tcgen05.ld 32x32b.x32, + bias (smem), GELU, bf16 pack,
-//              128-bit stores; the next tile's MMAs run meanwhile in the other
-//              accumulator
+//              columns): tcgen05.ld 32x32b.x32 (double-buffered), + bias (smem),
+//              GELU as a branch-free packed-fp32x2 polynomial, bf16 pack into a
+//              64 B-swizzled smem tile, TMA store (cp.async.bulk.tensor) of Y and Z;
+//              the next tile's MMAs run meanwhile in the other accumulator
 //
 // Every wait is bounded: a stuck pipeline raises an error flag and the CTA
 // drains instead of hanging the GPU.
@@ -84,6 +85,24 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       " [%0], [%1, {%3, %4}], [%2];"
       :: "r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+// the same box delivered to the same smem offset (and signalled on the same barrier offset)
+// of every CTA in cta_mask
+__device__ __forceinline__ void tma_load_2d_mcast(void* smem_dst, const CUtensorMap* map, uint64_t* bar,
+                                                  int c0, int c1, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      :: "r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tcgen05_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }
@@ -93,6 +112,12 @@ __device__ __forceinline__ void tcgen05_fence_after() {
 __device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
                :: "r"(smem_u32(bar)) : "memory");
+}
+// arrive on the barrier at this offset in every CTA of cta_mask once the MMAs retire
+__device__ __forceinline__ void tcgen05_commit_mcast(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      :: "r"(smem_u32(bar)), "h"(cta_mask) : "memory");
 }
 __device__ __forceinline__ void tcgen05_mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
                                                 uint32_t idesc, uint32_t accumulate) {
@@ -186,10 +211,23 @@ __device__ __forceinline__ uint64_t gelu2(uint64_t x) {
   return mul2(x, pk(fma_sat(t0, 0.5f, 0.5f), fma_sat(t1, 0.5f, 0.5f)));
 }
 
-__device__ __forceinline__ void st_global_256(void* p, const uint32_t (&w)[8]) {
-  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
-               :: "l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
-               : "memory");
+__device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// smem tile -> global through the TMA engine (asynchronous, fully coalesced, clips rows >= M)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t saddr, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               :: "l"(map), "r"(saddr), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
 // 32 lanes x 32 consecutive fp32 columns of the accumulator -> 32 registers per thread
@@ -231,20 +269,31 @@ struct SmemLayout {
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
+  // epilogue staging: per warp 2 buffers x {y, z} x (32 rows x 32 bf16 = 2 KB), 64 B swizzle
+  static constexpr int STG_TILE = 32 * 32 * 2;
+  static constexpr int STG_WARP = 2 * 2 * STG_TILE;
+  static constexpr int STG_BYTES = EPI_WARPS * STG_WARP;
   static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
-  static constexpr int TOTAL = 1024 + RING_BYTES + BAR_BYTES;
+  static constexpr int TOTAL = 1024 + RING_BYTES + STG_BYTES + BAR_BYTES;
 };
 
-template <int BLOCK_N, int STAGES>
+// CM = CTAs per cluster along M. The CM CTAs of a cluster work on CM vertically adjacent
+// tiles, which share the B (weight) tile: each CTA fetches 1/CM of it and TMA-multicasts
+// that slice to all of them, cutting the L2 -> SM operand traffic (the actual limiter at
+// 128 x 256 x 64 per stage: 48 KB per 4.2 MFLOP against ~42 B/clk/SM of L2 bandwidth).
+template <int BLOCK_N, int STAGES, int CM>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bias_act_kernel(const __grid_constant__ CUtensorMap map_a,
-                     const __grid_constant__ CUtensorMap map_b, const GemmArgs args) {
+                     const __grid_constant__ CUtensorMap map_b,
+                     const __grid_constant__ CUtensorMap map_y,
+                     const __grid_constant__ CUtensorMap map_z, const GemmArgs args) {
   using L = SmemLayout<BLOCK_N, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   // the 128 B swizzle atoms need 1024-byte alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ __align__(16) float bias_s[EPI_WARPS * (BLOCK_N / 2)];
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::RING_BYTES);
+  uint8_t* staging = smem + L::RING_BYTES;           // 1024-aligned (ring stages are 16 KB multiples)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::RING_BYTES + L::STG_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;      // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
@@ -255,13 +304,18 @@ gemm_bias_act_kernel(const __grid_constant__ CUtensorMap map_a,
   const int num_k = args.K / BLOCK_K;
   const int tiles_n = args.N / BLOCK_N;
   const int tiles_m = (args.M + BLOCK_M - 1) / BLOCK_M;
-  const int num_tiles = tiles_m * tiles_n;
+  const int num_tiles = ((tiles_m + CM - 1) / CM) * tiles_n;   // cluster-level ("super") tiles
+  const int crank = (CM > 1) ? (int)cluster_ctarank() : 0;
+  const int first_tile = blockIdx.x / CM, tile_step = gridDim.x / CM;
+  constexpr uint16_t CMASK = (uint16_t)((1u << CM) - 1);
   constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;        // two accumulators (256 or 512 columns)
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" :: "l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" :: "l"(&map_b) : "memory");
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    asm volatile("prefetch.tensormap [%0];" :: "l"(&map_y) : "memory");
+    if (args.z) asm volatile("prefetch.tensormap [%0];" :: "l"(&map_z) : "memory");
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CM); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -272,6 +326,7 @@ gemm_bias_act_kernel(const __grid_constant__ CUtensorMap map_a,
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (CM > 1) cluster_sync_all();                    // peers' barriers exist before anyone multicasts
   tcgen05_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_base_slot);
 
@@ -280,15 +335,31 @@ gemm_bias_act_kernel(const __grid_constant__ CUtensorMap map_a,
     if (elect_one()) {
       uint32_t it = 0;                               // global K-slice counter -> ring slot/phase
       bool ok = true;
-      for (int tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x) {
-        const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
+      for (int tile = first_tile; tile < num_tiles && ok; tile += tile_step) {
+        const int sm_blk = tile / tiles_n, n_blk = tile - sm_blk * tiles_n;
+        const int m_blk = sm_blk * CM + crank;
         for (int k = 0; k < num_k; ++k, ++it) {
           const uint32_t s = it % STAGES, phase = (it / STAGES) & 1;
+          // with CM > 1 the slot is free only when EVERY CTA of the cluster has consumed it
           if (!mbar_wait(&empty_bar[s], phase ^ 1, args.err)) { ok = false; break; }
           uint8_t* a_dst = smem + s * L::STAGE_BYTES;
           mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
           tma_load_2d(a_dst, &map_a, &full_bar[s], k * BLOCK_K, m_blk * BLOCK_M);
-          tma_load_2d(a_dst + L::A_BYTES, &map_b, &full_bar[s], k * BLOCK_K, n_blk * BLOCK_N);
+          if (CM == 1) {
+            tma_load_2d(a_dst + L::A_BYTES, &map_b, &full_bar[s], k * BLOCK_K, n_blk * BLOCK_N);
+          } else {
+            constexpr int SLICE = BLOCK_N / CM;      // my rows of the shared B tile
+            tma_load_2d_mcast(a_dst + L::A_BYTES + crank * SLICE * BLOCK_K * 2, &map_b, &full_bar[s],
+                              k * BLOCK_K, n_blk * BLOCK_N + crank * SLICE, CMASK);
+          }
+        }
+      }
+      if (CM > 1 && ok) {
+        // tail: every slot I multicast into has been consumed by all peers (and all their
+        // arrivals on my barriers have landed) before this CTA may exit
+        for (int t = 0; t < STAGES; ++t, ++it) {
+          const uint32_t s = it % STAGES, phase = (it / STAGES) & 1;
+          if (!mbar_wait(&empty_bar[s], phase ^ 1, args.err)) break;
         }
       }
     }
@@ -297,7 +368,7 @@ gemm_bias_act_kernel(const __grid_constant__ CUtensorMap map_a,
     constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N);
     uint32_t it = 0, local_tile = 0;
     bool ok = true;
-    for (int tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x, ++local_tile) {
+    for (int tile = first_tile; tile < num_tiles && ok; tile += tile_step, ++local_tile) {
       const uint32_t acc = local_tile & 1, acc_phase = (local_tile >> 1) & 1;
       // the epilogue must have drained this accumulator (passes at once the first two times)
       if (!mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1, args.err)) break;
@@ -317,7 +388,8 @@ gemm_bias_act_kernel(const __grid_constant__ CUtensorMap map_a,
             tcgen05_mma_f16(tmem_acc, a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), idesc,
                             (k > 0 || kk > 0) ? 1u : 0u);
           }
-          tcgen05_commit(&empty_bar[s]);               // smem stage reusable once these MMAs retire
+          // smem stage reusable once these MMAs retire (tell every CTA that multicasts into it)
+          if (CM == 1) tcgen05_commit(&empty_bar[s]); else tcgen05_commit_mcast(&empty_bar[s], CMASK);
           if (k == num_k - 1) tcgen05_commit(&tmem_full_bar[acc]);
         }
         __syncwarp();
@@ -330,30 +402,43 @@ gemm_bias_act_kernel(const __grid_constant__ CUtensorMap map_a,
     constexpr int HALF_N = BLOCK_N / 2;
     constexpr int NCHUNK = HALF_N / 32;
     float* my_bias = bias_s + (warp - 2) * HALF_N;     // private to this warp
-    uint32_t local_tile = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_tile) {
-      const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
-      const uint32_t acc = local_tile & 1, acc_phase = (local_tile >> 1) & 1;
-      const int col_base = n_blk * BLOCK_N + col_half * HALF_N;
-      // this warp's bias slice -> smem: all loads in flight first, then the stores
-      float bpre[NCHUNK];
+    const uint32_t stg0 = smem_u32(staging + (warp - 2) * L::STG_WARP);
+    // 64 B swizzle: the 16-byte chunk index of a row is XORed with (row / 2) % 4
+    const uint32_t row_off = (uint32_t)lane * 64u;
+    const uint32_t swz = (uint32_t)((lane >> 1) & 3);
+    const bool save_z = args.z != nullptr;
+    uint32_t local_tile = 0, chunk_ctr = 0;
+    float bpre[NCHUNK];
+    if (first_tile < num_tiles) {
+      const int n_blk0 = first_tile % tiles_n;
 #pragma unroll
       for (int i = 0; i < NCHUNK; ++i)
-        bpre[i] = args.bias ? __ldg(args.bias + col_base + i * 32 + lane) : 0.f;
+        bpre[i] = args.bias ? __ldg(args.bias + n_blk0 * BLOCK_N + col_half * HALF_N + i * 32 + lane) : 0.f;
+    }
+    for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++local_tile) {
+      const int sm_blk = tile / tiles_n, n_blk = tile - sm_blk * tiles_n;
+      const int m_blk = sm_blk * CM + crank;
+      const uint32_t acc = local_tile & 1, acc_phase = (local_tile >> 1) & 1;
+      const int col_base = n_blk * BLOCK_N + col_half * HALF_N;
+      // this warp's bias slice -> smem, then start fetching the next tile's slice
       __syncwarp();                                    // previous tile's reads are done
 #pragma unroll
       for (int i = 0; i < NCHUNK; ++i) my_bias[i * 32 + lane] = bpre[i];
       __syncwarp();
+      if (tile + tile_step < num_tiles) {
+        const int n_next = (tile + tile_step) % tiles_n;
+#pragma unroll
+        for (int i = 0; i < NCHUNK; ++i)
+          bpre[i] = args.bias ? __ldg(args.bias + n_next * BLOCK_N + col_half * HALF_N + i * 32 + lane) : 0.f;
+      }
       if (!mbar_wait(&tmem_full_bar[acc], acc_phase, args.err)) break;
       tcgen05_fence_after();
-      const int row = m_blk * BLOCK_M + lane_grp * 32 + lane;
-      const bool row_ok = row < args.M;
-      const size_t out_off = (size_t)row * args.N + col_base;
+      const int row0 = m_blk * BLOCK_M + lane_grp * 32;
       const uint32_t taddr0 = tmem_base + acc * BLOCK_N + col_half * HALF_N + ((uint32_t)(lane_grp * 32) << 16);
       uint32_t r[2][32];                               // double-buffered TMEM reads
       tmem_ld_32x32(taddr0, r[0]);
 #pragma unroll
-      for (int c = 0; c < NCHUNK; ++c) {
+      for (int c = 0; c < NCHUNK; ++c, ++chunk_ctr) {
         uint32_t (&cur)[32] = r[c & 1];
         tmem_ld_wait(cur);
         if (c + 1 < NCHUNK) {
@@ -364,37 +449,48 @@ gemm_bias_act_kernel(const __grid_constant__ CUtensorMap map_a,
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
         }
-        if (row_ok) {
+        // staging buffer (chunk_ctr & 1): its previous TMA store must have read it out
+        const uint32_t stg_y = stg0 + (chunk_ctr & 1) * (2 * L::STG_TILE);
+        const uint32_t stg_z = stg_y + L::STG_TILE;
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 32; j += 16) {
-            uint64_t v[8];
+        for (int j = 0; j < 32; j += 16) {
+          uint64_t v[8];
 #pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-              const float4 b = *reinterpret_cast<const float4*>(my_bias + c * 32 + j + q4 * 4);
-              v[2 * q4] = add2(pk_u(cur[j + 4 * q4], cur[j + 4 * q4 + 1]), pk(b.x, b.y));
-              v[2 * q4 + 1] = add2(pk_u(cur[j + 4 * q4 + 2], cur[j + 4 * q4 + 3]), pk(b.z, b.w));
-            }
-            uint32_t w[8];
-            if (args.z) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) w[e] = pack_bf16(v[e]);
-              st_global_256(args.z + out_off + c * 32 + j, w);
-            }
-            if (args.act == 1) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = gelu2(v[e]);
-            }
-#pragma unroll
-            for (int e = 0; e < 8; ++e) w[e] = pack_bf16(v[e]);
-            st_global_256(args.y + out_off + c * 32 + j, w);
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const float4 b = *reinterpret_cast<const float4*>(my_bias + c * 32 + j + q4 * 4);
+            v[2 * q4] = add2(pk_u(cur[j + 4 * q4], cur[j + 4 * q4 + 1]), pk(b.x, b.y));
+            v[2 * q4 + 1] = add2(pk_u(cur[j + 4 * q4 + 2], cur[j + 4 * q4 + 3]), pk(b.z, b.w));
           }
+          // columns j..j+7 are 16-byte chunk j/8 of this row, j+8..j+15 the next one
+          const uint32_t k0 = (((uint32_t)(j >> 3)) ^ swz) << 4, k1 = (((uint32_t)(j >> 3) + 1) ^ swz) << 4;
+          if (save_z) {
+            sts128(stg_z + row_off + k0, pack_bf16(v[0]), pack_bf16(v[1]), pack_bf16(v[2]), pack_bf16(v[3]));
+            sts128(stg_z + row_off + k1, pack_bf16(v[4]), pack_bf16(v[5]), pack_bf16(v[6]), pack_bf16(v[7]));
+          }
+          if (args.act == 1) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = gelu2(v[e]);
+          }
+          sts128(stg_y + row_off + k0, pack_bf16(v[0]), pack_bf16(v[1]), pack_bf16(v[2]), pack_bf16(v[3]));
+          sts128(stg_y + row_off + k1, pack_bf16(v[4]), pack_bf16(v[5]), pack_bf16(v[6]), pack_bf16(v[7]));
+        }
+        fence_proxy_async_smem();                      // generic-proxy writes -> visible to the TMA engine
+        __syncwarp();
+        if (lane == 0 && row0 < args.M) {
+          tma_store_2d(&map_y, stg_y, col_base + c * 32, row0);
+          if (save_z) tma_store_2d(&map_z, stg_z, col_base + c * 32, row0);
+          tma_store_commit();
         }
       }
     }
+    if (lane == 0) tma_store_wait_read<0>();           // smem must outlive the last stores
   }
 
   tcgen05_fence_before();
   __syncthreads();
+  if (CM > 1) cluster_sync_all();
   if (warp == 1) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(TMEM_COLS) : "memory");
@@ -420,33 +516,50 @@ bool load_encode() {
   return g_encode != nullptr;
 }
 
-// row-major [rows, cols] bf16 matrix, box = [box_rows, 64 cols], 128 B swizzle
-int make_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+// row-major [rows, cols] bf16 matrix, box = [box_rows, box_cols]; operands: 64 columns with the
+// 128 B swizzle, outputs: 32 columns with the 64 B swizzle
+int make_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows,
+             uint32_t box_cols, CUtensorMapSwizzle swizzle) {
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {cols * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, box_rows};
+  cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t elem[2] = {1, 1};
   CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box,
-                        elem, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        elem, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return (int)r;
 }
 
-template <int BLOCK_N, int STAGES>
-int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmArgs& a, int max_ctas, cudaStream_t s) {
+template <int BLOCK_N, int STAGES, int CM>
+int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& my, const CUtensorMap& mz,
+           const GemmArgs& a, int max_ctas, cudaStream_t s) {
   constexpr int smem = SmemLayout<BLOCK_N, STAGES>::TOTAL;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bias_act_kernel<BLOCK_N, STAGES>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  auto kernel = gemm_bias_act_kernel<BLOCK_N, STAGES, CM>;
+  static int max_clusters = 0;
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CM; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (max_clusters == 0) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
-    configured = true;
+    int n = 0;
+    cfg.gridDim = dim3(g_num_sms / CM * CM);
+    if (CM > 1 && cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) == cudaSuccess && n > 0) max_clusters = n;
+    else max_clusters = g_num_sms / CM;
+    cudaGetLastError();
   }
-  const int tiles = (a.N / BLOCK_N) * ((a.M + BLOCK_M - 1) / BLOCK_M);
-  int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-  gemm_bias_act_kernel<BLOCK_N, STAGES><<<grid, NUM_THREADS, smem, s>>>(ma, mb, a);
-  return (int)cudaGetLastError();
+  const int tiles_m = (a.M + BLOCK_M - 1) / BLOCK_M;
+  const int super_tiles = ((tiles_m + CM - 1) / CM) * (a.N / BLOCK_N);
+  int clusters = super_tiles < max_clusters ? super_tiles : max_clusters;
+  if (max_ctas > 0 && clusters * CM > max_ctas) clusters = max_ctas / CM > 0 ? max_ctas / CM : 1;
+  cfg.gridDim = dim3(clusters * CM);
+  return (int)cudaLaunchKernelEx(&cfg, kernel, ma, mb, my, mz, a);
 }
 
 }  // namespace
@@ -456,10 +569,10 @@ extern "C" int adl_bind_thread();
 extern "C" {
 
 // y[M,N] (and optionally z) = act(x[M,K] @ w[N,K]^T + bias). bf16 row-major, 16-byte aligned
-// rows; K % 64 == 0, N % 128 == 0. block_n: 0 = auto, 128 or 256. Returns 0, a CUDA error
+// rows; K % 64 == 0, N % 128 == 0. block_n: 0 = auto, 128 or 256; cluster_m: 0 = auto, 1, 2, 4. Returns 0, a CUDA error
 // code, or a negative shape/driver error.
 int adl_gemm_bias_act(const void* x, const void* w, const float* bias, void* y, void* z, int M, int N,
-                      int K, int act, int block_n, int max_ctas, void* err, void* stream) {
+                      int K, int act, int block_n, int cluster_m, int max_ctas, void* err, void* stream) {
   if (K % BLOCK_K != 0 || N % 128 != 0 || M <= 0) return -10;
   if (!load_encode()) return -11;
   if (int rc = adl_bind_thread()) return rc;
@@ -471,9 +584,17 @@ int adl_gemm_bias_act(const void* x, const void* w, const float* bias, void* y, 
   }
   if (block_n == 0) block_n = (N % 256 == 0) ? 256 : 128;
   if (block_n != 128 && !(block_n == 256 && N % 256 == 0)) return -12;
-  CUtensorMap ma, mb;
-  if (int rc = make_map(&ma, x, (uint64_t)M, (uint64_t)K, BLOCK_M)) return -100 - rc;
-  if (int rc = make_map(&mb, w, (uint64_t)N, (uint64_t)K, (uint32_t)block_n)) return -200 - rc;
+  CUtensorMap ma, mb, my, mz;
+  if (int rc = make_map(&ma, x, (uint64_t)M, (uint64_t)K, BLOCK_M, BLOCK_K, CU_TENSOR_MAP_SWIZZLE_128B))
+    return -100 - rc;
+  if (cluster_m == 0) cluster_m = (M > 3 * BLOCK_M) ? 4 : (M > BLOCK_M ? 2 : 1);
+  if (cluster_m != 1 && cluster_m != 2 && cluster_m != 4) return -13;
+  if (int rc = make_map(&mb, w, (uint64_t)N, (uint64_t)K, (uint32_t)(block_n / cluster_m), BLOCK_K,
+                        CU_TENSOR_MAP_SWIZZLE_128B))
+    return -200 - rc;
+  if (int rc = make_map(&my, y, (uint64_t)M, (uint64_t)N, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B)) return -300 - rc;
+  if (int rc = make_map(&mz, z ? z : y, (uint64_t)M, (uint64_t)N, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))
+    return -400 - rc;
   GemmArgs a;
   a.y = static_cast<__nv_bfloat16*>(y);
   a.z = static_cast<__nv_bfloat16*>(z);
@@ -481,8 +602,14 @@ int adl_gemm_bias_act(const void* x, const void* w, const float* bias, void* y, 
   a.M = M; a.N = N; a.K = K; a.act = act;
   a.err = static_cast<uint32_t*>(err);
   cudaStream_t s = (cudaStream_t)stream;
-  if (block_n == 256) return launch<256, 4>(ma, mb, a, max_ctas, s);
-  return launch<128, 6>(ma, mb, a, max_ctas, s);
+  if (block_n == 256) {
+    if (cluster_m == 4) return launch<256, 3, 4>(ma, mb, my, mz, a, max_ctas, s);
+    if (cluster_m == 2) return launch<256, 3, 2>(ma, mb, my, mz, a, max_ctas, s);
+    return launch<256, 3, 1>(ma, mb, my, mz, a, max_ctas, s);
+  }
+  if (cluster_m == 4) return launch<128, 4, 4>(ma, mb, my, mz, a, max_ctas, s);
+  if (cluster_m == 2) return launch<128, 4, 2>(ma, mb, my, mz, a, max_ctas, s);
+  return launch<128, 4, 1>(ma, mb, my, mz, a, max_ctas, s);
 }
 
 }  // extern "C"

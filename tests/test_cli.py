@@ -79,3 +79,34 @@ def test_ls_summary_and_parser():
     assert args.project == "proj" and rest[-2:] == ["--lr", "0.1"]
     args, _ = build_parser().parse_known_args(["tensorboard", "proxy", "x"])
     assert args.tb_command == "proxy" and args.port == 6006
+
+
+def test_workload_specs_validate():
+    """Every workload of the suite (tests/workloads) becomes a job the CLI
+    can prepare and the scheduler's validator accepts."""
+    import asyncio
+    import importlib.util
+    import os
+    from adaptdl_b200.cli import manifests
+    from adaptdl_b200.sched.kube import InMemoryCluster
+    from adaptdl_b200.sched.validator import Validator
+    path = os.path.join(os.path.dirname(__file__), "workloads",
+                        "workloads.py")
+    spec = importlib.util.spec_from_file_location("workloads", path)
+    workloads = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(workloads)
+    assert len(workloads.WORKLOADS) >= 14
+    validator = Validator(InMemoryCluster())
+    for name in workloads.WORKLOADS:
+        resource = workloads.manifest(name)
+        script = resource["spec"]["template"]["spec"]["containers"][0][
+            "command"][1]
+        assert os.path.exists(os.path.join(
+            workloads.ROOT, os.path.relpath(script, "/root"))), script
+        job, pvc = manifests.prepare_job(resource, "registry/img@sha256:0",
+                                         [], name=name)
+        review = {"operation": "CREATE", "namespace": "default",
+                  "uid": "u", "object": job}
+        response = asyncio.run(validator._validate_create(review))
+        assert response["allowed"], (name, response)
+        assert os.path.exists(workloads.local_command(name)[0])

@@ -394,17 +394,20 @@ def test_checkpoint_roundtrip_with_device_engine(tmp_path):
 # tcgen05 Linear + bias + GELU (csrc/adl_gemm.cu)
 # ---------------------------------------------------------------------------
 @pytest.mark.gpu
-@pytest.mark.parametrize("m,n,k,block_n", [
-    (128, 128, 64, 128), (256, 256, 128, 256), (1000, 384, 192, 128),
-    (4096, 3072, 768, 256), (4096, 3072, 768, 128), (77, 512, 1024, 0)])
-def test_tcgen05_linear_gelu_forward(m, n, k, block_n):
+@pytest.mark.parametrize("m,n,k,block_n,cluster_m", [
+    (128, 128, 64, 128, 1), (256, 256, 128, 256, 2), (1000, 384, 192, 128, 4),
+    (4096, 3072, 768, 256, 4), (4096, 3072, 768, 128, 2),
+    (4096, 3072, 768, 256, 1), (77, 512, 1024, 0, 0), (640, 256, 64, 256, 4),
+    (300, 768, 3072, 0, 0)])
+def test_tcgen05_linear_gelu_forward(m, n, k, block_n, cluster_m):
     from adaptdl_b200.ops import check_errors, gemm_bias_act
     torch.manual_seed(m + n + k)
     dev = torch.device("cuda:0")
     x = torch.randn(m, k, device=dev).bfloat16()
     w = (torch.randn(n, k, device=dev) / k ** 0.5).bfloat16()
     b = torch.randn(n, device=dev)
-    y, z = gemm_bias_act(x, w, b, "gelu", True, block_n=block_n)
+    y, z = gemm_bias_act(x, w, b, "gelu", True, block_n=block_n,
+                         cluster_m=cluster_m)
     torch.cuda.synchronize()
     check_errors()
     ref_z = x.float() @ w.float().t() + b
@@ -412,7 +415,8 @@ def test_tcgen05_linear_gelu_forward(m, n, k, block_n):
     # bf16 output rounding: 2^-8 relative
     assert torch.allclose(z.float(), ref_z, rtol=1e-2, atol=2e-2)
     assert torch.allclose(y.float(), ref_y, rtol=1e-2, atol=2e-2)
-    y2, z2 = gemm_bias_act(x, w, None, "identity", False, block_n=block_n)
+    y2, z2 = gemm_bias_act(x, w, None, "identity", False, block_n=block_n,
+                           cluster_m=cluster_m)
     assert z2 is None
     assert torch.allclose(y2.float(), x.float() @ w.float().t(),
                           rtol=1e-2, atol=2e-2)

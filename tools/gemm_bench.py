@@ -43,9 +43,11 @@ def main():
     ap.add_argument("--shapes", default="4096x3072x768,16384x3072x768,"
                     "8192x4096x1024,4096x768x3072,512x3072x768,1000x3072x768")
     ap.add_argument("--block-n", default="128,256")
+    ap.add_argument("--cluster-m", default="1,2,4")
     ap.add_argument("--iters", type=int, default=50)
     args = ap.parse_args()
     block_ns = [int(v) for v in args.block_n.split(",")]
+    cluster_ms = [int(v) for v in args.cluster_m.split(",")]
     ITERS[0] = args.iters
     dev = torch.device("cuda:0")
     torch.manual_seed(0)
@@ -67,19 +69,24 @@ def main():
         ref_y = F.gelu(ref_z)
         row = {"M": m, "N": n, "K": k}
         for bn in block_ns:
-            if n % bn:
-                continue
-            y, z = gemm_bias_act(x, w, b, "gelu", True, block_n=bn)
-            torch.cuda.synchronize()
-            check_errors()
-            row["max_err_y_bn%d" % bn] = (y.float() - ref_y).abs().max().item()
-            row["max_err_z_bn%d" % bn] = (z.float() - ref_z).abs().max().item()
-            row["fused_bn%d_us" % bn] = time_us(
-                lambda: gemm_bias_act(x, w, b, "gelu", True, block_n=bn),
-                flush=flush)
-            row["fused_nosave_bn%d_us" % bn] = time_us(
-                lambda: gemm_bias_act(x, w, b, "gelu", False, block_n=bn),
-                flush=flush)
+            for cm in cluster_ms:
+                if n % bn:
+                    continue
+                tag = "bn%d_cm%d" % (bn, cm)
+                y, z = gemm_bias_act(x, w, b, "gelu", True, block_n=bn,
+                                     cluster_m=cm)
+                torch.cuda.synchronize()
+                check_errors()
+                row["max_err_y_" + tag] = \
+                    (y.float() - ref_y).abs().max().item()
+                row["max_err_z_" + tag] = \
+                    (z.float() - ref_z).abs().max().item()
+                row["fused_%s_us" % tag] = time_us(
+                    lambda: gemm_bias_act(x, w, b, "gelu", True, block_n=bn,
+                                          cluster_m=cm), flush=flush)
+                row["fused_nosave_%s_us" % tag] = time_us(
+                    lambda: gemm_bias_act(x, w, b, "gelu", False, block_n=bn,
+                                          cluster_m=cm), flush=flush)
         bb = b.bfloat16()
         yt = F.gelu(F.linear(x, w, bb))
         row["max_err_torch"] = (yt.float() - ref_y).abs().max().item()
@@ -90,6 +97,8 @@ def main():
         row["flush_only_us"] = time_us(lambda: None, flush=flush)
         best = min(v for k_, v in row.items()
                    if k_.startswith("fused_bn"))
+        row["best"] = min((v, k_) for k_, v in row.items()
+                          if k_.startswith("fused_bn"))[1]
         flops = 2.0 * m * n * k
         row["fused_TFLOPs"] = flops / best / 1e6
         row["torch_TFLOPs"] = flops / row["torch_linear_gelu_us"] / 1e6
