@@ -25,7 +25,8 @@ CSRC = os.path.join(_ROOT, "csrc")
 LIB_PATH = os.path.join(_HERE, "libadl_b200.so")
 STAMP_PATH = os.path.join(_HERE, "libadl_b200.stamp")
 
-SOURCES = ["adl_kernels.cu", "adl_optim.cu", "adl_gemm.cu", "adl_symm.cpp"]
+SOURCES = ["adl_kernels.cu", "adl_optim.cu", "adl_gemm.cu", "adl_bn.cu",
+           "adl_symm.cpp"]
 HEADERS = ["adl_common.cuh"]
 
 NVCC_FLAGS = [
@@ -203,6 +204,22 @@ GNS_TAIL = 8
 (GNS_SQR_UNBIAS, GNS_VAR_UNBIAS, GNS_PROGRESS, GNS_BIASED) = range(4)
 
 
+class BnArgs(ctypes.Structure):
+    _fields_ = [
+        ("x", ctypes.c_void_p), ("res", ctypes.c_void_p),
+        ("y", ctypes.c_void_p), ("dy", ctypes.c_void_p),
+        ("dx", ctypes.c_void_p), ("dres", ctypes.c_void_p),
+        ("gamma", ctypes.c_void_p), ("beta", ctypes.c_void_p),
+        ("mean", ctypes.c_void_p), ("rstd", ctypes.c_void_p),
+        ("running_mean", ctypes.c_void_p), ("running_var", ctypes.c_void_p),
+        ("dgamma", ctypes.c_void_p), ("dbeta", ctypes.c_void_p),
+        ("partial", ctypes.c_void_p), ("coef", ctypes.c_void_p),
+        ("M", ctypes.c_int), ("C", ctypes.c_int),
+        ("n_partial", ctypes.c_int), ("relu", ctypes.c_int),
+        ("eps", ctypes.c_float), ("momentum", ctypes.c_float),
+    ]
+
+
 def _declare(lib):
     c = ctypes
     lib.adl_set_device.argtypes = [c.c_int]
@@ -246,7 +263,10 @@ def _declare(lib):
         c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p,
         c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, c.c_int,
         c.c_void_p, c.c_void_p]
-    for name, struct in (("adl_sizeof_optim_args", OptimArgs),
+    lib.adl_bn_act.argtypes = [c.POINTER(BnArgs), c.c_int, c.c_int, c.c_int,
+                               c.c_void_p]
+    for name, struct in (("adl_sizeof_bn_args", BnArgs),
+                         ("adl_sizeof_optim_args", OptimArgs),
                          ("adl_sizeof_reduce_args", ReduceArgs),
                          ("adl_sizeof_local_args", LocalArgs),
                          ("adl_sizeof_finalize_args", FinalizeArgs),

@@ -3,15 +3,28 @@ reference's ``examples/pytorch-cifar`` workload (ResNet18 =
 BasicBlock x [2, 2, 2, 2], 11.17 M parameters, 62 parameter tensors).
 
 Written for channels-last bf16 autocast on B200: convolutions have no bias
-(BatchNorm follows), the classifier is a single Linear.
+(BatchNorm follows), the classifier is a single Linear. Every
+``bn -> (+ shortcut) -> relu`` group is ONE fused op
+(:class:`adaptdl_b200.ops.BatchNormAct2d`, ``csrc/adl_bn.cu``); parameter
+names and shapes are those of the plain ``nn.BatchNorm2d`` model, so state
+dicts are interchangeable.
 """
 
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from adaptdl_b200.ops.bn_act import BatchNormAct2d
+
 __all__ = ["ResNet", "resnet18", "resnet34", "resnet50", "resnet101",
            "resnet152"]
+
+
+def _shortcut(seq, x):
+    """identity, or conv1x1 -> bn (no activation)"""
+    if len(seq) == 0:
+        return x
+    return seq[1](seq[0](x), relu=False)
 
 
 class BasicBlock(nn.Module):
@@ -20,20 +33,19 @@ class BasicBlock(nn.Module):
     def __init__(self, in_planes, planes, stride=1):
         super().__init__()
         self.conv1 = nn.Conv2d(in_planes, planes, 3, stride, 1, bias=False)
-        self.bn1 = nn.BatchNorm2d(planes)
+        self.bn1 = BatchNormAct2d(planes)
         self.conv2 = nn.Conv2d(planes, planes, 3, 1, 1, bias=False)
-        self.bn2 = nn.BatchNorm2d(planes)
+        self.bn2 = BatchNormAct2d(planes)
         self.shortcut = nn.Sequential()
         if stride != 1 or in_planes != self.expansion * planes:
             self.shortcut = nn.Sequential(
                 nn.Conv2d(in_planes, self.expansion * planes, 1, stride,
                           bias=False),
-                nn.BatchNorm2d(self.expansion * planes))
+                BatchNormAct2d(self.expansion * planes))
 
     def forward(self, x):
-        out = F.relu(self.bn1(self.conv1(x)))
-        out = self.bn2(self.conv2(out))
-        return F.relu(out + self.shortcut(x))
+        out = self.bn1(self.conv1(x))
+        return self.bn2(self.conv2(out), residual=_shortcut(self.shortcut, x))
 
 
 class Bottleneck(nn.Module):
@@ -42,24 +54,23 @@ class Bottleneck(nn.Module):
     def __init__(self, in_planes, planes, stride=1):
         super().__init__()
         self.conv1 = nn.Conv2d(in_planes, planes, 1, bias=False)
-        self.bn1 = nn.BatchNorm2d(planes)
+        self.bn1 = BatchNormAct2d(planes)
         self.conv2 = nn.Conv2d(planes, planes, 3, stride, 1, bias=False)
-        self.bn2 = nn.BatchNorm2d(planes)
+        self.bn2 = BatchNormAct2d(planes)
         self.conv3 = nn.Conv2d(planes, self.expansion * planes, 1,
                                bias=False)
-        self.bn3 = nn.BatchNorm2d(self.expansion * planes)
+        self.bn3 = BatchNormAct2d(self.expansion * planes)
         self.shortcut = nn.Sequential()
         if stride != 1 or in_planes != self.expansion * planes:
             self.shortcut = nn.Sequential(
                 nn.Conv2d(in_planes, self.expansion * planes, 1, stride,
                           bias=False),
-                nn.BatchNorm2d(self.expansion * planes))
+                BatchNormAct2d(self.expansion * planes))
 
     def forward(self, x):
-        out = F.relu(self.bn1(self.conv1(x)))
-        out = F.relu(self.bn2(self.conv2(out)))
-        out = self.bn3(self.conv3(out))
-        return F.relu(out + self.shortcut(x))
+        out = self.bn1(self.conv1(x))
+        out = self.bn2(self.conv2(out))
+        return self.bn3(self.conv3(out), residual=_shortcut(self.shortcut, x))
 
 
 class ResNet(nn.Module):
@@ -67,7 +78,7 @@ class ResNet(nn.Module):
         super().__init__()
         self.in_planes = 64
         self.conv1 = nn.Conv2d(3, 64, 3, 1, 1, bias=False)
-        self.bn1 = nn.BatchNorm2d(64)
+        self.bn1 = BatchNormAct2d(64)
         self.layer1 = self._make_layer(block, 64, num_blocks[0], 1)
         self.layer2 = self._make_layer(block, 128, num_blocks[1], 2)
         self.layer3 = self._make_layer(block, 256, num_blocks[2], 2)
@@ -82,7 +93,7 @@ class ResNet(nn.Module):
         return nn.Sequential(*layers)
 
     def forward(self, x):
-        out = F.relu(self.bn1(self.conv1(x)))
+        out = self.bn1(self.conv1(x))
         out = self.layer4(self.layer3(self.layer2(self.layer1(out))))
         out = F.adaptive_avg_pool2d(out, 1)
         return self.linear(torch.flatten(out, 1))

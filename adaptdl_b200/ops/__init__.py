@@ -1,6 +1,8 @@
-"""Hand-written sm_100a compute ops (tensor-core path)."""
+"""Hand-written sm_100a compute ops."""
 
 from adaptdl_b200.ops.linear_act import (LinearGELU, check_errors,
                                          gemm_bias_act, linear_act)
+from adaptdl_b200.ops.bn_act import BatchNormAct2d, bn_act
 
-__all__ = ["LinearGELU", "linear_act", "gemm_bias_act", "check_errors"]
+__all__ = ["LinearGELU", "linear_act", "gemm_bias_act", "check_errors",
+           "BatchNormAct2d", "bn_act"]

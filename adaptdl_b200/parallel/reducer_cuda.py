@@ -110,7 +110,9 @@ class CudaGradReducer(GradReducer):
         self._grad_mc = {}
         # NVLS: buckets at least this large go through the switch
         self._nvls_min_bytes = int(float(os.environ.get(
-            "ADAPTDL_B200_NVLS_MIN_MB", "1")) * (1 << 20))
+            "ADAPTDL_B200_NVLS_MIN_MB", "2")) * (1 << 20))
+        self._nvls_ctas = max(1, min(int(os.environ.get(
+            "ADAPTDL_B200_NVLS_CTAS", "64")), MAX_CTAS - 1))
         for i, arena in enumerate(self.arenas):
             itemsize = torch.empty((), dtype=arena.dtype).element_size()
             view, ptrs = self._region.carve(
@@ -277,12 +279,16 @@ class CudaGradReducer(GradReducer):
         args.T = self._row(1)
         args.err = self._err.data_ptr()
         args.timeout_ns = _TIMEOUT_NS
+        slice_vec = n_vec // self.world_size
         if self._grad_mc.get(ai) and self.world_size > 1 and \
                 n_vec * layout.VEC_BYTES >= self._nvls_min_bytes:
+            # in-switch reduction: multimem.ld_reduce / multimem.st
             args.mc_buf = self._grad_mc[ai] + off
             self.nvls_launches = getattr(self, "nvls_launches", 0) + 1
-        slice_vec = n_vec // self.world_size
-        if self.world_size > 1:
+            per_cta = 512 * 4
+            grid = max(1, min(self._nvls_ctas,
+                              (slice_vec + per_cta - 1) // per_cta))
+        elif self.world_size > 1:
             # each thread keeps 16/W vectors in flight per iteration
             per_cta = 512 * max(16 // self.world_size, 1)
             grid = max(1, min(self._reduce_ctas,

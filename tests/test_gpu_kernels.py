@@ -447,3 +447,93 @@ def test_tcgen05_linear_gelu_autograd_matches_torch():
         assert a.dtype == b.dtype and a.shape == b.shape
         scale = b.abs().max().item()
         assert (a - b).abs().max().item() <= 3e-2 * scale + 1e-3
+
+
+# ---------------------------------------------------------------------------
+# fused BatchNorm (+ residual) (+ ReLU), channels-last (csrc/adl_bn.cu)
+# ---------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape,residual,relu", [
+    ((32, 64, 16, 16), True, True), ((16, 128, 8, 8), False, True),
+    ((8, 512, 4, 4), True, False), ((7, 256, 5, 3), False, False),
+    ((128, 64, 32, 32), True, True)])
+def test_fused_bn_act_matches_torch(dtype, shape, residual, relu):
+    from adaptdl_b200.ops import BatchNormAct2d
+    from adaptdl_b200.ops.bn_act import supported
+    torch.manual_seed(1)
+    dev = torch.device("cuda:0")
+    c = shape[1]
+    fused = BatchNormAct2d(c).to(dev)
+    with torch.no_grad():
+        fused.weight.uniform_(0.5, 1.5)
+        fused.bias.normal_()
+    plain = torch.nn.BatchNorm2d(c).to(dev)
+    plain.load_state_dict(fused.state_dict())
+    x32 = torch.randn(shape, device=dev) * 2 + 0.5
+    x1 = x32.to(dtype).contiguous(memory_format=torch.channels_last) \
+        .requires_grad_(True)
+    assert supported(x1)
+    x2 = x1.detach().float().requires_grad_(True)
+    r1 = r2 = None
+    if residual:
+        r1 = torch.randn(shape, device=dev).to(dtype).contiguous(
+            memory_format=torch.channels_last).requires_grad_(True)
+        r2 = r1.detach().float().requires_grad_(True)
+    y1 = fused(x1, r1, relu)
+    y2 = plain(x2)                       # fp32 reference of the same op
+    if residual:
+        y2 = y2 + r2
+    if relu:
+        y2 = torch.relu(y2)
+    g = torch.randn(shape, device=dev)
+    y1.backward(g.to(dtype).contiguous(memory_format=torch.channels_last))
+    y2.backward(g.to(dtype).float())
+    tol = 1e-4 if dtype == torch.float32 else 3e-2
+    assert y1.dtype == dtype
+    assert y1.is_contiguous(memory_format=torch.channels_last)
+    assert torch.allclose(y1.float(), y2, rtol=tol, atol=tol)
+    assert torch.allclose(fused.running_mean, plain.running_mean,
+                          rtol=1e-4, atol=1e-4)
+    assert torch.allclose(fused.running_var, plain.running_var,
+                          rtol=1e-3, atol=1e-3)
+    assert int(fused.num_batches_tracked) == 1
+
+    def close(a, b, t):
+        scale = b.abs().max().item() + 1e-6
+        return (a.float() - b).abs().max().item() <= t * scale
+    gtol = 2e-4 if dtype == torch.float32 else 4e-2
+    assert close(x1.grad, x2.grad, gtol)
+    assert close(fused.weight.grad, plain.weight.grad, gtol)
+    assert close(fused.bias.grad, plain.bias.grad, gtol)
+    if residual:
+        assert close(r1.grad, r2.grad, gtol)
+
+
+@pytest.mark.gpu
+def test_fused_bn_resnet_matches_unfused_model():
+    """ResNet-18 with the fused BN kernels vs the same model with the fused
+    path switched off (PyTorch composition): same loss and gradients."""
+    import os
+    from adaptdl_b200.models import resnet18
+    torch.manual_seed(5)
+    dev = torch.device("cuda:0")
+    net = resnet18().to(dev).to(memory_format=torch.channels_last)
+    x = torch.randn(32, 3, 32, 32, device=dev).contiguous(
+        memory_format=torch.channels_last)
+    t = torch.randint(0, 10, (32,), device=dev)
+    results = []
+    for flag in ("1", "0"):
+        os.environ["ADAPTDL_B200_FUSED_BN"] = flag
+        state = {k: v.clone() for k, v in net.state_dict().items()}
+        net.zero_grad(set_to_none=True)
+        loss = torch.nn.functional.cross_entropy(net(x), t)
+        loss.backward()
+        results.append((loss.item(), [p.grad.clone()
+                                      for p in net.parameters()]))
+        net.load_state_dict(state)
+    os.environ.pop("ADAPTDL_B200_FUSED_BN")
+    assert abs(results[0][0] - results[1][0]) < 1e-3
+    for a, b in zip(results[0][1], results[1][1]):
+        assert (a - b).abs().max().item() <= 2e-3 * (b.abs().max().item()
+                                                      + 1e-6)

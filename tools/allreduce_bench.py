@@ -46,6 +46,8 @@ def main():
     ap.add_argument("--out", default=None)
     ap.add_argument("--sizes-mb", default="0.0625,0.25,1,4,16,64,256")
     ap.add_argument("--ctas", default="")
+    ap.add_argument("--sweep", action="store_true",
+                    help="also time the NVLS flavour at 32/64/96 CTAs")
     args = ap.parse_args()
     rank = int(os.environ["RANK"])
     world = int(os.environ["WORLD_SIZE"])
@@ -59,15 +61,37 @@ def main():
         p = torch.nn.Parameter(torch.randn(numel, device=dev))
         if args.ctas:
             os.environ["ADAPTDL_B200_REDUCE_CTAS"] = args.ctas
-        red = CudaGradReducer([{"params": [p]}], world, rank, lambda: True,
-                              bucket_cap_mb=max(2 * mb, 1))
-        arena = red.arenas[0]
-        bucket = arena.buckets[0]
-        arena.grad.normal_()
-        nbytes = bucket.length * 4
         iters = 200 if mb <= 4 else 40
-        fused = timed(lambda: red._reduce(arena, bucket, 1.0 / world, True),
-                      iters, stream=red._comm)
+        variants = {}
+        # the fused kernel in its P2P flavour and its NVLS (multimem)
+        # flavour at several grid sizes; "fused" = what the reducer picks
+        configs = [("fused", {}), ("p2p", {"ADAPTDL_B200_NVLS_MIN_MB": "1e9"})]
+        if args.sweep:
+            configs += [("nvls%d" % c, {"ADAPTDL_B200_NVLS_MIN_MB": "0",
+                                        "ADAPTDL_B200_NVLS_CTAS": str(c)})
+                        for c in (32, 64, 96)]
+        for tag, env in configs:
+            saved = {k: os.environ.get(k) for k in env}
+            os.environ.update(env)
+            red = CudaGradReducer([{"params": [p]}], world, rank,
+                                  lambda: True, bucket_cap_mb=max(2 * mb, 1))
+            for k, v in saved.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+            arena = red.arenas[0]
+            bucket = arena.buckets[0]
+            arena.grad.normal_()
+            nbytes = bucket.length * 4
+            variants[tag] = timed(
+                lambda: red._reduce(arena, bucket, 1.0 / world, True),
+                iters, stream=red._comm) * 1e3
+            if tag == "fused":
+                used_nvls = bool(getattr(red, "nvls_launches", 0))
+                provider, ctas = red._provider.name, red._reduce_ctas
+            del red, arena, bucket
+        fused = variants["fused"] / 1e3
         flat = torch.randn(bucket.length, device=dev)
         nccl = timed(lambda: dist.all_reduce(flat), iters)
 
@@ -85,12 +109,11 @@ def main():
                "fused_busbw_GBps": bus / fused / 1e6,
                "nccl_busbw_GBps": bus / nccl / 1e6,
                "fused_frac_of_770": bus / fused / 1e6 / 770.0,
-               "provider": red._provider.name, "ctas": red._reduce_ctas,
-               "nvls": bool(getattr(red, "nvls_launches", 0))}
+               "provider": provider, "ctas": ctas, "nvls": used_nvls,
+               "variants_us": variants}
         rows.append(row)
         if rank == 0:
             print(json.dumps(row), flush=True)
-        del red
     if rank == 0 and args.out:
         os.makedirs(os.path.dirname(os.path.abspath(args.out)),
                     exist_ok=True)
