@@ -213,7 +213,8 @@ class BnArgs(ctypes.Structure):
         ("mean", ctypes.c_void_p), ("rstd", ctypes.c_void_p),
         ("running_mean", ctypes.c_void_p), ("running_var", ctypes.c_void_p),
         ("dgamma", ctypes.c_void_p), ("dbeta", ctypes.c_void_p),
-        ("partial", ctypes.c_void_p), ("coef", ctypes.c_void_p),
+        ("partial", ctypes.c_void_p), ("counters", ctypes.c_void_p),
+        ("cb", ctypes.c_int), ("coef", ctypes.c_void_p),
         ("M", ctypes.c_int), ("C", ctypes.c_int),
         ("n_partial", ctypes.c_int), ("relu", ctypes.c_int),
         ("eps", ctypes.c_float), ("momentum", ctypes.c_float),
@@ -264,7 +265,7 @@ def _declare(lib):
         c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, c.c_int,
         c.c_void_p, c.c_void_p]
     lib.adl_bn_act.argtypes = [c.POINTER(BnArgs), c.c_int, c.c_int, c.c_int,
-                               c.c_void_p]
+                               c.c_int, c.c_void_p]
     for name, struct in (("adl_sizeof_bn_args", BnArgs),
                          ("adl_sizeof_optim_args", OptimArgs),
                          ("adl_sizeof_reduce_args", ReduceArgs),

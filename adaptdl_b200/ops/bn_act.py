@@ -46,23 +46,53 @@ def supported(x):
         return False
     c = x.shape[1]
     vec = 4 if x.dtype == torch.float32 else 8
-    if c % vec:
+    cb = min(c, 64)
+    if c % vec or c % cb or cb % vec:
         return False
     tpr = c // vec
-    return tpr <= 256 and 256 % tpr == 0 and x.numel() > 0
+    return tpr <= 256 and 256 % tpr == 0 and 256 % (cb // vec) == 0 and \
+        x.numel() > 0
 
 
-def _grid(device, m, c, vec, unroll):
+def _grid(device, m, c, vec, unroll, waves=8):
+    """CTAs of the elementwise pass (a row holds C / vec threads)."""
     rpi = 256 // (c // vec)
     need = (m + rpi * unroll - 1) // (rpi * unroll)
-    return max(1, min(need, 4 * _sm_count(device)))
+    return max(1, min(need, waves * _sm_count(device)))
 
 
-def _launch(args, dtype, backward, grid, device):
+def _reduce_grid(device, m, c, vec, unroll):
+    """(channels per CTA, row chunks) of the reduction: ~2 CTAs per SM."""
+    cb = min(c, 64)
+    rpi = 256 // (cb // vec)
+    need = (m + rpi * unroll - 1) // (rpi * unroll)
+    return cb, max(1, min(need, 2 * _sm_count(device) // (c // cb)))
+
+
+_TICKETS = {}
+
+
+def _tickets(device, n):
+    """``n`` zeroed int32 ticket counters. They live in a per-device ring:
+    the kernels leave them at zero, and consecutive calls take different
+    slots so two launches in flight never share one."""
+    state = _TICKETS.get(device.index)
+    if state is None:
+        state = [torch.zeros(4096, dtype=torch.int32, device=device), 0]
+        _TICKETS[device.index] = state
+    if state[1] + n > state[0].numel():
+        state[1] = 0
+    ptr = state[0].data_ptr() + 4 * state[1]
+    state[1] += n
+    return ptr
+
+
+def _launch(args, dtype, backward, grid, grid_apply, device):
     from adaptdl_b200 import _native
     lib = _native.load()
     lib.adl_set_device(device.index)
     code = lib.adl_bn_act(ctypes.byref(args), _DTYPES[dtype], backward, grid,
+                          grid_apply,
                           torch.cuda.current_stream(device).cuda_stream)
     if code < 0:
         raise RuntimeError("adl_bn_act rejected the call (code {})".format(
@@ -94,7 +124,7 @@ class _BnAct(torch.autograd.Function):
         y = torch.empty_like(x)           # preserve_format: channels-last
         mean = torch.empty(c, dtype=torch.float32, device=dev)
         rstd = torch.empty(c, dtype=torch.float32, device=dev)
-        grid = _grid(dev, m, c, vec, 4)
+        cb, grid = _reduce_grid(dev, m, c, vec, 4)
         scratch = torch.empty((grid + 1) * 2 * c, dtype=torch.float32,
                               device=dev)
         gamma = weight.float() if weight is not None else \
@@ -109,8 +139,9 @@ class _BnAct(torch.autograd.Function):
         a.partial = scratch.data_ptr()
         a.coef = scratch.data_ptr() + grid * 2 * c * 4
         a.M, a.C, a.n_partial, a.relu = m, c, grid, int(relu)
+        a.cb, a.counters = cb, _tickets(dev, c // cb)
         a.eps, a.momentum = eps, momentum
-        _launch(a, x.dtype, 0, grid, dev)
+        _launch(a, x.dtype, 0, grid, _grid(dev, m, c, vec, 4), dev)
         ctx.save_for_backward(x, y if relu else None, gamma, mean, rstd)
         ctx.relu = bool(relu)
         ctx.has_res = residual is not None
@@ -131,7 +162,7 @@ class _BnAct(torch.autograd.Function):
         dres = torch.empty_like(x) if ctx.has_res else None
         dgamma = torch.empty(c, dtype=torch.float32, device=dev)
         dbeta = torch.empty(c, dtype=torch.float32, device=dev)
-        grid = _grid(dev, m, c, vec, 2)
+        cb, grid = _reduce_grid(dev, m, c, vec, 2)
         scratch = torch.empty((grid + 1) * 2 * c, dtype=torch.float32,
                               device=dev)
         a = BnArgs()
@@ -143,7 +174,8 @@ class _BnAct(torch.autograd.Function):
         a.partial = scratch.data_ptr()
         a.coef = scratch.data_ptr() + grid * 2 * c * 4
         a.M, a.C, a.n_partial, a.relu = m, c, grid, int(ctx.relu)
-        _launch(a, x.dtype, 1, grid, dev)
+        a.cb, a.counters = cb, _tickets(dev, c // cb)
+        _launch(a, x.dtype, 1, grid, _grid(dev, m, c, vec, 2), dev)
         if not ctx.relu and ctx.has_res:
             dres = dy                      # identity: d(residual) = dy
         return (dx, dgamma if ctx.has_affine[0] else None,

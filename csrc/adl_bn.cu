@@ -37,7 +37,9 @@ struct BnArgs {
   float* running_var;   // [C] (or null)
   float* dgamma;        // [C]
   float* dbeta;         // [C]
-  float* partial;       // [grid, 2, C] scratch
+  float* partial;       // [C / cb, grid.y, 2, cb] scratch
+  int* counters;        // [C / cb] zero-initialised tickets (left zero again)
+  int cb;               // channels per reduce CTA (<= 64)
   float* coef;          // [2, C] scratch: forward (scale, shift); backward (s1/M, s2/M)
   int M, C;
   int n_partial;
@@ -45,16 +47,25 @@ struct BnArgs {
   float eps, momentum;
 };
 
-// sum over rows of two per-channel quantities, K in {fwd: x, x^2 ; bwd: g, g*xhat}
+// Per-channel sums over the rows of two quantities (forward: x, x^2; backward: g, g*xhat),
+// then the per-channel terms, in ONE launch:
+//   grid.x = channel blocks of `cb` channels, grid.y = row chunks. Every CTA writes its
+//   partial sums; the LAST CTA to finish in a channel block (ticket counter, self-resetting)
+//   folds that block's grid.y partials in a fixed order (deterministic) and derives
+//   mean / rstd / scale / shift (forward) or dgamma / dbeta / s1/M / s2/M (backward).
 template <typename T, bool BWD>
 __global__ void __launch_bounds__(BN_THREADS)
 bn_reduce_kernel(const BnArgs a) {
   constexpr int V = VecTraits<T>::N;
   constexpr int BN_UNROLL = BnUnroll<BWD>::U;
-  extern __shared__ float red[];                 // [2][rows_per_iter][C]
-  const int tpr = a.C / V;                       // threads per row
+  __shared__ float red[2 * 32 * 64];             // [2][rows_per_iter][cb]
+  __shared__ int is_last;
+  const int cb = a.cb;
+  const int tpr = cb / V;                        // threads per row
   const int rpi = BN_THREADS / tpr;              // rows per iteration
-  const int my_c = (threadIdx.x % tpr) * V;
+  const int c0 = blockIdx.x * cb;
+  const int lc = (threadIdx.x % tpr) * V;        // channel within the block
+  const int my_c = c0 + lc;
   const int my_r = threadIdx.x / tpr;
   float s0[V], s1[V];
 #pragma unroll
@@ -64,8 +75,8 @@ bn_reduce_kernel(const BnArgs a) {
 #pragma unroll
     for (int e = 0; e < V; ++e) { mu[e] = a.mean[my_c + e]; rs[e] = a.rstd[my_c + e]; }
   }
-  const long long stride = (long long)gridDim.x * rpi;
-  for (long long r0 = (long long)blockIdx.x * rpi + my_r; r0 < a.M; r0 += stride * BN_UNROLL) {
+  const long long stride = (long long)gridDim.y * rpi;
+  for (long long r0 = (long long)blockIdx.y * rpi + my_r; r0 < a.M; r0 += stride * BN_UNROLL) {
     Vec16 vx[BN_UNROLL], vg[BN_UNROLL], vy[BN_UNROLL];
 #pragma unroll
     for (int u = 0; u < BN_UNROLL; ++u) {
@@ -103,52 +114,80 @@ bn_reduce_kernel(const BnArgs a) {
     }
   }
   float* r0s = red;
-  float* r1s = red + rpi * a.C;
+  float* r1s = red + rpi * cb;
 #pragma unroll
   for (int e = 0; e < V; ++e) {
-    r0s[my_r * a.C + my_c + e] = s0[e];
-    r1s[my_r * a.C + my_c + e] = s1[e];
+    r0s[my_r * cb + lc + e] = s0[e];
+    r1s[my_r * cb + lc + e] = s1[e];
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < 2 * a.C; c += BN_THREADS) {
-    const float* src = (c < a.C) ? (r0s + c) : (r1s + (c - a.C));
+  float* mine = a.partial + ((size_t)blockIdx.x * gridDim.y + blockIdx.y) * 2 * cb;
+  for (int c = threadIdx.x; c < 2 * cb; c += BN_THREADS) {
+    const float* src = (c < cb) ? (r0s + c) : (r1s + (c - cb));
     float t = 0.f;
-    for (int r = 0; r < rpi; ++r) t += src[r * a.C];
-    a.partial[(size_t)blockIdx.x * 2 * a.C + c] = t;
+    for (int r = 0; r < rpi; ++r) t += src[r * cb];
+    mine[c] = t;
   }
-}
-
-// one thread per channel: fold the partials (fixed order) and derive the per-channel terms
-template <bool BWD>
-__global__ void bn_finalize_kernel(const BnArgs a) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= a.C) return;
-  double t0 = 0.0, t1 = 0.0;
-  for (int p = 0; p < a.n_partial; ++p) {
-    t0 += (double)a.partial[(size_t)p * 2 * a.C + c];
-    t1 += (double)a.partial[(size_t)p * 2 * a.C + a.C + c];
+  // ---- last CTA of this channel block finalizes ----
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(a.counters + blockIdx.x, 1) == (int)gridDim.y - 1);
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  // fold the grid.y partials of this channel block: warp w takes partials w, w+8, ...,
+  // lane l the l-th float4 of the 2*cb values; then the 8 warp sums are added in order
+  const int nv4 = 2 * cb / 4;                    // float4s per partial (<= 32)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (lane < nv4) {
+    const float4* base = reinterpret_cast<const float4*>(a.partial + (size_t)blockIdx.x * gridDim.y * 2 * cb) + lane;
+    const int gy = (int)gridDim.y;
+    int p = warp;
+    for (; p + 24 < gy; p += 32) {
+      const float4 t0 = __ldcg(base + (size_t)p * nv4), t1 = __ldcg(base + (size_t)(p + 8) * nv4);
+      const float4 t2 = __ldcg(base + (size_t)(p + 16) * nv4), t3 = __ldcg(base + (size_t)(p + 24) * nv4);
+      acc.x += (t0.x + t1.x) + (t2.x + t3.x); acc.y += (t0.y + t1.y) + (t2.y + t3.y);
+      acc.z += (t0.z + t1.z) + (t2.z + t3.z); acc.w += (t0.w + t1.w) + (t2.w + t3.w);
+    }
+    for (; p < gy; p += 8) {
+      const float4 t = __ldcg(base + (size_t)p * nv4);
+      acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+    }
   }
-  const double inv_m = 1.0 / (double)a.M;
+  __syncthreads();                               // everyone is done with `red`
+  if (lane < nv4) reinterpret_cast<float4*>(red)[warp * nv4 + lane] = acc;
+  __syncthreads();
+  float* tot = red + 8 * 2 * cb;                 // [2][cb]
+  if (threadIdx.x < 2 * cb) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < BN_THREADS / 32; ++w) t += (double)red[w * 2 * cb + threadIdx.x];
+    tot[threadIdx.x] = (float)(t / (double)a.M);  // mean-like quantities from here on
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) a.counters[blockIdx.x] = 0;
+  if (threadIdx.x >= cb) return;
+  const int c = c0 + threadIdx.x;
+  const float m0 = tot[threadIdx.x], m1 = tot[cb + threadIdx.x];
   if (!BWD) {
-    const double mean = t0 * inv_m;
-    double var = t1 * inv_m - mean * mean;
-    if (var < 0.0) var = 0.0;
-    const float rstd = (float)(1.0 / sqrt(var + (double)a.eps));
-    a.mean[c] = (float)mean;
+    const float var = fmaxf(m1 - m0 * m0, 0.f);
+    const float rstd = rsqrtf(var + a.eps);
+    a.mean[c] = m0;
     a.rstd[c] = rstd;
     const float scale = a.gamma[c] * rstd;
     a.coef[c] = scale;
-    a.coef[a.C + c] = a.beta[c] - (float)mean * scale;
+    a.coef[a.C + c] = a.beta[c] - m0 * scale;
     if (a.running_mean != nullptr) {
-      const double unbiased = a.M > 1 ? var * (double)a.M / (double)(a.M - 1) : var;
-      a.running_mean[c] = (1.f - a.momentum) * a.running_mean[c] + a.momentum * (float)mean;
-      a.running_var[c] = (1.f - a.momentum) * a.running_var[c] + a.momentum * (float)unbiased;
+      const float unbiased = a.M > 1 ? var * ((float)a.M / (float)(a.M - 1)) : var;
+      a.running_mean[c] = (1.f - a.momentum) * a.running_mean[c] + a.momentum * m0;
+      a.running_var[c] = (1.f - a.momentum) * a.running_var[c] + a.momentum * unbiased;
     }
   } else {
-    a.dbeta[c] = (float)t0;
-    a.dgamma[c] = (float)t1;
-    a.coef[c] = (float)(t0 * inv_m);
-    a.coef[a.C + c] = (float)(t1 * inv_m);
+    a.dbeta[c] = m0 * (float)a.M;
+    a.dgamma[c] = m1 * (float)a.M;
+    a.coef[c] = m0;
+    a.coef[a.C + c] = m1;
   }
 }
 
@@ -230,20 +269,14 @@ bn_apply_kernel(const BnArgs a) {
 }
 
 template <typename T>
-int run(const BnArgs& a, int backward, int grid, cudaStream_t s) {
-  constexpr int V = VecTraits<T>::N;
-  const int tpr = a.C / V;
-  const int rpi = BN_THREADS / tpr;
-  const size_t smem = (size_t)2 * rpi * a.C * sizeof(float);
-  const int fin_blocks = (a.C + 127) / 128;
+int run(const BnArgs& a, int backward, int grid_y, int grid_apply, cudaStream_t s) {
+  const dim3 grid(a.C / a.cb, grid_y);
   if (!backward) {
-    bn_reduce_kernel<T, false><<<grid, BN_THREADS, smem, s>>>(a);
-    bn_finalize_kernel<false><<<fin_blocks, 128, 0, s>>>(a);
-    bn_apply_kernel<T, false><<<grid, BN_THREADS, 0, s>>>(a);
+    bn_reduce_kernel<T, false><<<grid, BN_THREADS, 0, s>>>(a);
+    bn_apply_kernel<T, false><<<grid_apply, BN_THREADS, 0, s>>>(a);
   } else {
-    bn_reduce_kernel<T, true><<<grid, BN_THREADS, smem, s>>>(a);
-    bn_finalize_kernel<true><<<fin_blocks, 128, 0, s>>>(a);
-    bn_apply_kernel<T, true><<<grid, BN_THREADS, 0, s>>>(a);
+    bn_reduce_kernel<T, true><<<grid, BN_THREADS, 0, s>>>(a);
+    bn_apply_kernel<T, true><<<grid_apply, BN_THREADS, 0, s>>>(a);
   }
   return (int)cudaGetLastError();
 }
@@ -257,20 +290,22 @@ extern "C" {
 int adl_sizeof_bn_args() { return (int)sizeof(BnArgs); }
 
 // dtype: 0 fp32, 1 bf16, 2 fp16. Requirements (checked by the caller too): C a multiple of
-// the vector width (4 / 8), C / width a divisor of 256, a.n_partial == grid.
-int adl_bn_act(const void* args, int dtype, int backward, int grid, void* stream) {
+// the vector width (4 / 8) and of cb, cb <= 64, C / width and cb / width divisors of 256,
+// a.n_partial == grid (row chunks of the reduction).
+int adl_bn_act(const void* args, int dtype, int backward, int grid, int grid_apply, void* stream) {
   const BnArgs* a = static_cast<const BnArgs*>(args);
   if (int rc = adl_bind_thread()) return rc;
   const int v = dtype == 0 ? 4 : 8;
   if (a->C % v != 0) return -20;
   const int tpr = a->C / v;
   if (tpr > BN_THREADS || BN_THREADS % tpr != 0) return -21;
-  if (grid <= 0 || a->n_partial != grid) return -22;
+  if (grid <= 0 || grid_apply <= 0 || a->n_partial != grid) return -22;
+  if (a->cb <= 0 || a->cb > 64 || a->C % a->cb != 0 || a->cb % v != 0 || BN_THREADS % (a->cb / v) != 0) return -24;
   cudaStream_t s = (cudaStream_t)stream;
   switch (dtype) {
-    case 0: return run<float>(*a, backward, grid, s);
-    case 1: return run<__nv_bfloat16>(*a, backward, grid, s);
-    case 2: return run<__half>(*a, backward, grid, s);
+    case 0: return run<float>(*a, backward, grid, grid_apply, s);
+    case 1: return run<__nv_bfloat16>(*a, backward, grid, grid_apply, s);
+    case 2: return run<__half>(*a, backward, grid, grid_apply, s);
   }
   return -23;
 }

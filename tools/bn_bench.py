@@ -18,8 +18,19 @@ from adaptdl_b200.ops import BatchNormAct2d  # noqa: E402
 
 
 def time_us(fn, iters=30, warmup=5, flush=None):
-    for _ in range(warmup):
+    """Device time of ``fn`` replayed as a CUDA graph (no CPU launch cost)."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(warmup):
+            fn()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
         fn()
+    fn = graph.replay
+    fn()
     torch.cuda.synchronize()
     total = 0.0
     for _ in range(iters):
