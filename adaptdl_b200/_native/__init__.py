@@ -263,7 +263,7 @@ def _declare(lib):
     lib.adl_gemm_bias_act.argtypes = [
         c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p,
         c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, c.c_int,
-        c.c_void_p, c.c_void_p]
+        c.c_void_p, c.c_void_p, c.c_void_p]
     lib.adl_bn_act.argtypes = [c.POINTER(BnArgs), c.c_int, c.c_int, c.c_int,
                                c.c_int, c.c_void_p]
     for name, struct in (("adl_sizeof_bn_args", BnArgs),

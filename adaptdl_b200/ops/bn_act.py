@@ -22,6 +22,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from adaptdl_b200.ops import _count
+
 _DTYPES = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
 _SM = {}
 
@@ -98,6 +100,7 @@ def _launch(args, dtype, backward, grid, grid_apply, device):
         raise RuntimeError("adl_bn_act rejected the call (code {})".format(
             code))
     _native.check(code, "adl_bn_act")
+    _count.add(2)                     # reduce(+finalize) and apply
 
 
 def _ptr(t):

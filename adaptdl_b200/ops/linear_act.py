@@ -20,6 +20,8 @@ import os
 import torch
 import torch.nn.functional as F
 
+from adaptdl_b200.ops import _count
+
 _ERR = {}            # device index -> int32 error flag tensor
 _ACT = {None: 0, "identity": 0, "gelu": 1}
 
@@ -53,11 +55,15 @@ def supported(x, weight):
 
 
 def gemm_bias_act(x2d, weight, bias, act="gelu", save_preact=True,
-                  block_n=0, cluster_m=0, max_ctas=0):
+                  block_n=0, cluster_m=0, max_ctas=0, trace=None):
     """Raw kernel call. ``x2d`` [M, K] bf16, ``weight`` [N, K] bf16, ``bias``
     [N] fp32 or None. Returns ``(y, z)`` (``z`` is None unless
     ``save_preact``). ``block_n`` (128/256) and ``cluster_m`` (1/2/4 CTAs
-    sharing a multicast weight tile) default to a shape-based choice."""
+    sharing a multicast weight tile, or 22 = CTA pair issuing 2-SM
+    ``tcgen05.mma.cta_group::2``) default to a shape-based choice.
+    ``trace``: optional int64 ``[3, 256]`` tensor that receives SM-clock
+    stamps of CTA 0's pipeline (TMA issue, MMA wait begin / end per
+    K-slice)."""
     from adaptdl_b200 import _native
     lib = _native.load()
     assert x2d.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16
@@ -76,14 +82,17 @@ def gemm_bias_act(x2d, weight, bias, act="gelu", save_preact=True,
         x2d.data_ptr(), weight.data_ptr(),
         bias.data_ptr() if bias is not None else None,
         y.data_ptr(), z.data_ptr() if z is not None else None,
-        m, n, k, _ACT[act], block_n, cluster_m, max_ctas,
+        m, n, k, _ACT[act] if isinstance(act, (str, type(None))) else int(act),
+        block_n, cluster_m, max_ctas,
         _err_flag(x2d.device).data_ptr(),
+        trace.data_ptr() if trace is not None else None,
         torch.cuda.current_stream(x2d.device).cuda_stream)
     if code < 0:
         raise RuntimeError(
             "adl_gemm_bias_act rejected M={} N={} K={} (code {})".format(
                 m, n, k, code))
     _native.check(code, "adl_gemm_bias_act")
+    _count.add(1)
     return y, z
 
 

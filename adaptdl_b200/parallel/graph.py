@@ -23,6 +23,8 @@ import logging
 
 import torch
 
+from adaptdl_b200.ops import _count as _ops_count
+
 from adaptdl_b200.torch.data import current_dataloader
 
 LOG = logging.getLogger(__name__)
@@ -31,7 +33,8 @@ __all__ = ["GraphedTrainStep"]
 
 
 class _Captured(object):
-    __slots__ = ("graph", "inputs", "loss", "launches", "n_rows")
+    __slots__ = ("graph", "inputs", "loss", "launches", "ops_launches",
+                 "n_rows")
 
 
 class GraphedTrainStep(object):
@@ -154,12 +157,14 @@ class GraphedTrainStep(object):
         net.gns._flush()
         net.engine.sync_hyper()
         launches0 = red.launches
+        ops0 = _ops_count.total()
         steps0 = red._steps
         torch.cuda.synchronize(dev)
         cap.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(cap.graph, capture_error_mode="thread_local"):
             cap.loss = self._body(*cap.inputs)
         cap.launches = red.launches - launches0
+        cap.ops_launches = _ops_count.total() - ops0
         cap.n_rows = None
         # the capture ran the step's host bookkeeping but no kernels: replay
         # once so the device actually performs this step
@@ -188,5 +193,6 @@ class GraphedTrainStep(object):
         if sync:
             net.engine._opt_steps_host += 1
         red.launches += cap.launches
+        _ops_count.add(cap.ops_launches)
         self.replays += 1
         return cap.loss

@@ -78,12 +78,18 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, uint32
   atomicOr(err, 2u);
   return false;
 }
+// L2 eviction-priority descriptors (the encodings createpolicy.fractional produces): operands
+// are re-read by other tiles -> keep; the outputs stream out once -> evict first
+constexpr uint64_t L2_EVICT_FIRST = 0x12F0000000000000ull;
+constexpr uint64_t L2_EVICT_LAST = 0x14F0000000000000ull;
+
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar,
                                             int c0, int c1) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4}], [%2];"
-      :: "r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      :: "r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(L2_EVICT_LAST)
+      : "memory");
 }
 // the same box delivered to the same smem offset (and signalled on the same barrier offset)
 // of every CTA in cta_mask
@@ -91,8 +97,28 @@ __device__ __forceinline__ void tma_load_2d_mcast(void* smem_dst, const CUtensor
                                                   int c0, int c1, uint16_t cta_mask) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%3, %4}], [%2], %5;"
-      :: "r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask) : "memory");
+      ".L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5, %6;"
+      :: "r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask),
+         "l"(L2_EVICT_LAST) : "memory");
+}
+// cta_group::2 flavour: issued by both CTAs of a pair for their own smem, completion bytes are
+// credited to the barrier `bar_cluster_addr` (a shared::cluster address: the leader CTA's)
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, uint32_t bar_cluster_addr,
+                                                int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      ".L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+      :: "r"(smem_u32(smem_dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "l"(L2_EVICT_LAST)
+      : "memory");
+}
+// shared::cluster address of `smem_addr` (a shared::cta address of this CTA) in CTA `rank`
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(bar_cluster_addr) : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -118,6 +144,20 @@ __device__ __forceinline__ void tcgen05_commit_mcast(uint64_t* bar, uint16_t cta
   asm volatile(
       "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
       :: "r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+// the pair flavours: one thread of the leader CTA drives the tensor cores of both SMs
+__device__ __forceinline__ void tcgen05_commit_2sm_mcast(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      :: "r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_f16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                                    uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void tcgen05_mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
                                                 uint32_t idesc, uint32_t accumulate) {
@@ -216,8 +256,8 @@ __device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, u
 }
 // smem tile -> global through the TMA engine (asynchronous, fully coalesced, clips rows >= M)
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t saddr, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-               :: "l"(map), "r"(saddr), "r"(c0), "r"(c1) : "memory");
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;"
+               :: "l"(map), "r"(saddr), "r"(c0), "r"(c1), "l"(L2_EVICT_FIRST) : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -259,14 +299,18 @@ struct GemmArgs {
   __nv_bfloat16* z;            // [M, N] pre-activation (may be nullptr)
   const float* bias;           // [N] (may be nullptr)
   int M, N, K;
-  int act;                     // 0 = identity, 1 = GELU (erf)
+  int act;                     // 0 = identity, 1 = GELU (erf); diagnostic bits (timing experiments
+                               // only, results are wrong): 8 = no TMA stores, 16 = no epilogue
+                               // math, 32 = no proxy fence, 64 = no TMEM loads
   uint32_t* err;
+  long long* trace;            // optional [3][256] SM-clock stamps of CTA 0 (pipeline diagnosis)
 };
 
-template <int BLOCK_N, int STAGES>
+// B_ROWS = rows of the weight tile resident in ONE CTA (BLOCK_N, or BLOCK_N / 2 for 2-SM MMAs)
+template <int B_ROWS, int STAGES>
 struct SmemLayout {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
-  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int B_BYTES = B_ROWS * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
   // epilogue staging: per warp 2 buffers x {y, z} x (32 rows x 32 bf16 = 2 KB), 64 B swizzle
@@ -277,17 +321,23 @@ struct SmemLayout {
   static constexpr int TOTAL = 1024 + RING_BYTES + STG_BYTES + BAR_BYTES;
 };
 
+// TWO_SM (needs CM == 2): the pair runs ONE tcgen05.mma.cta_group::2 of M = 256: each CTA
+// keeps its 128 rows of A and only HALF of the weight tile in shared memory, the leader
+// CTA's elected thread issues the MMAs for both SMs, each SM accumulates its 128 rows in
+// its own TMEM. Per-SM shared-memory fill traffic drops from 48 KB to 32 KB per K-slice,
+// which is what bounds the 1-SM kernel.
 // CM = CTAs per cluster along M. The CM CTAs of a cluster work on CM vertically adjacent
 // tiles, which share the B (weight) tile: each CTA fetches 1/CM of it and TMA-multicasts
 // that slice to all of them, cutting the L2 -> SM operand traffic (the actual limiter at
 // 128 x 256 x 64 per stage: 48 KB per 4.2 MFLOP against ~42 B/clk/SM of L2 bandwidth).
-template <int BLOCK_N, int STAGES, int CM>
+template <int BLOCK_N, int STAGES, int CM, bool TWO_SM>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bias_act_kernel(const __grid_constant__ CUtensorMap map_a,
                      const __grid_constant__ CUtensorMap map_b,
                      const __grid_constant__ CUtensorMap map_y,
                      const __grid_constant__ CUtensorMap map_z, const GemmArgs args) {
-  using L = SmemLayout<BLOCK_N, STAGES>;
+  static_assert(!TWO_SM || CM == 2, "2-SM MMAs need a cluster of two CTAs");
+  using L = SmemLayout<TWO_SM ? BLOCK_N / 2 : BLOCK_N, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   // the 128 B swizzle atoms need 1024-byte alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -315,14 +365,25 @@ gemm_bias_act_kernel(const __grid_constant__ CUtensorMap map_a,
     asm volatile("prefetch.tensormap [%0];" :: "l"(&map_b) : "memory");
     asm volatile("prefetch.tensormap [%0];" :: "l"(&map_y) : "memory");
     if (args.z) asm volatile("prefetch.tensormap [%0];" :: "l"(&map_z) : "memory");
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CM); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], EPI_WARPS); }
+    // 2-SM: one multicast commit frees a slot in both CTAs; the leader's accumulator barrier
+    // collects the epilogue warps of both CTAs
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], TWO_SM ? 1 : CM); }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], TWO_SM ? 2 * EPI_WARPS : EPI_WARPS);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                 :: "r"(smem_u32(tmem_base_slot)), "r"(TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (TWO_SM) {                                     // same warp of both CTAs
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                   :: "r"(smem_u32(tmem_base_slot)), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                   :: "r"(smem_u32(tmem_base_slot)), "r"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -343,6 +404,16 @@ gemm_bias_act_kernel(const __grid_constant__ CUtensorMap map_a,
           // with CM > 1 the slot is free only when EVERY CTA of the cluster has consumed it
           if (!mbar_wait(&empty_bar[s], phase ^ 1, args.err)) { ok = false; break; }
           uint8_t* a_dst = smem + s * L::STAGE_BYTES;
+          if (args.trace && blockIdx.x == 0 && it < 256) args.trace[it] = clock64();
+          if (TWO_SM) {
+            // both CTAs fill their own slot; all bytes are credited to the LEADER's barrier
+            const uint32_t leader_full = mapa_u32(smem_u32(&full_bar[s]), 0);
+            if (crank == 0) mbar_expect_tx(&full_bar[s], 2 * L::STAGE_BYTES);
+            tma_load_2d_2sm(a_dst, &map_a, leader_full, k * BLOCK_K, m_blk * BLOCK_M);
+            tma_load_2d_2sm(a_dst + L::A_BYTES, &map_b, leader_full, k * BLOCK_K,
+                            n_blk * BLOCK_N + crank * (BLOCK_N / 2));
+            continue;
+          }
           mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
           tma_load_2d(a_dst, &map_a, &full_bar[s], k * BLOCK_K, m_blk * BLOCK_M);
           if (CM == 1) {
@@ -365,9 +436,9 @@ gemm_bias_act_kernel(const __grid_constant__ CUtensorMap map_a,
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N);
+    constexpr uint32_t idesc = make_idesc(TWO_SM ? 2 * BLOCK_M : BLOCK_M, BLOCK_N);
     uint32_t it = 0, local_tile = 0;
-    bool ok = true;
+    bool ok = !(TWO_SM && crank != 0);               // 2-SM: only the leader CTA issues MMAs
     for (int tile = first_tile; tile < num_tiles && ok; tile += tile_step, ++local_tile) {
       const uint32_t acc = local_tile & 1, acc_phase = (local_tile >> 1) & 1;
       // the epilogue must have drained this accumulator (passes at once the first two times)
@@ -376,7 +447,9 @@ gemm_bias_act_kernel(const __grid_constant__ CUtensorMap map_a,
       const uint32_t tmem_acc = tmem_base + acc * BLOCK_N;
       for (int k = 0; k < num_k; ++k, ++it) {
         const uint32_t s = it % STAGES, phase = (it / STAGES) & 1;
+        if (args.trace && blockIdx.x == 0 && it < 256 && lane == 0) args.trace[256 + it] = clock64();
         if (!mbar_wait(&full_bar[s], phase, args.err)) { ok = false; break; }
+        if (args.trace && blockIdx.x == 0 && it < 256 && lane == 0) args.trace[512 + it] = clock64();
         tcgen05_fence_after();
         if (elect_one()) {
           const uint32_t a_addr = smem_u32(smem + s * L::STAGE_BYTES);
@@ -385,12 +458,21 @@ gemm_bias_act_kernel(const __grid_constant__ CUtensorMap map_a,
 #pragma unroll
           for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
             // +16 bf16 = +32 B inside the 128 B swizzle row: +2 in (addr >> 4) units
-            tcgen05_mma_f16(tmem_acc, a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), idesc,
-                            (k > 0 || kk > 0) ? 1u : 0u);
+            if (TWO_SM)
+              tcgen05_mma_f16_2sm(tmem_acc, a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), idesc,
+                                  (k > 0 || kk > 0) ? 1u : 0u);
+            else
+              tcgen05_mma_f16(tmem_acc, a_desc + (uint64_t)(kk * 2), b_desc + (uint64_t)(kk * 2), idesc,
+                              (k > 0 || kk > 0) ? 1u : 0u);
           }
-          // smem stage reusable once these MMAs retire (tell every CTA that multicasts into it)
-          if (CM == 1) tcgen05_commit(&empty_bar[s]); else tcgen05_commit_mcast(&empty_bar[s], CMASK);
-          if (k == num_k - 1) tcgen05_commit(&tmem_full_bar[acc]);
+          // smem stage reusable once these MMAs retire (tell every CTA that fills / multicasts into it)
+          if (TWO_SM) tcgen05_commit_2sm_mcast(&empty_bar[s], CMASK);
+          else if (CM == 1) tcgen05_commit(&empty_bar[s]);
+          else tcgen05_commit_mcast(&empty_bar[s], CMASK);
+          if (k == num_k - 1) {
+            if (TWO_SM) tcgen05_commit_2sm_mcast(&tmem_full_bar[acc], CMASK);
+            else tcgen05_commit(&tmem_full_bar[acc]);
+          }
         }
         __syncwarp();
       }
@@ -442,12 +524,15 @@ gemm_bias_act_kernel(const __grid_constant__ CUtensorMap map_a,
         uint32_t (&cur)[32] = r[c & 1];
         tmem_ld_wait(cur);
         if (c + 1 < NCHUNK) {
-          tmem_ld_32x32(taddr0 + (uint32_t)((c + 1) * 32), r[(c + 1) & 1]);
+          if (!(args.act & 64)) tmem_ld_32x32(taddr0 + (uint32_t)((c + 1) * 32), r[(c + 1) & 1]);
         } else {
           // accumulator fully read: hand it back so the MMAs of tile+2 can start
           tcgen05_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+          if (lane == 0) {
+            if (TWO_SM) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[acc]), 0));
+            else mbar_arrive(&tmem_empty_bar[acc]);
+          }
         }
         // staging buffer (chunk_ctr & 1): its previous TMA store must have read it out
         const uint32_t stg_y = stg0 + (chunk_ctr & 1) * (2 * L::STG_TILE);
@@ -469,16 +554,16 @@ gemm_bias_act_kernel(const __grid_constant__ CUtensorMap map_a,
             sts128(stg_z + row_off + k0, pack_bf16(v[0]), pack_bf16(v[1]), pack_bf16(v[2]), pack_bf16(v[3]));
             sts128(stg_z + row_off + k1, pack_bf16(v[4]), pack_bf16(v[5]), pack_bf16(v[6]), pack_bf16(v[7]));
           }
-          if (args.act == 1) {
+          if ((args.act & 1) && !(args.act & 16)) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[e] = gelu2(v[e]);
           }
           sts128(stg_y + row_off + k0, pack_bf16(v[0]), pack_bf16(v[1]), pack_bf16(v[2]), pack_bf16(v[3]));
           sts128(stg_y + row_off + k1, pack_bf16(v[4]), pack_bf16(v[5]), pack_bf16(v[6]), pack_bf16(v[7]));
         }
-        fence_proxy_async_smem();                      // generic-proxy writes -> visible to the TMA engine
+        if (!(args.act & 32)) fence_proxy_async_smem(); // generic-proxy writes -> visible to the TMA engine
         __syncwarp();
-        if (lane == 0 && row0 < args.M) {
+        if (lane == 0 && row0 < args.M && !(args.act & 8)) {
           tma_store_2d(&map_y, stg_y, col_base + c * 32, row0);
           if (save_z) tma_store_2d(&map_z, stg_z, col_base + c * 32, row0);
           tma_store_commit();
@@ -493,7 +578,10 @@ gemm_bias_act_kernel(const __grid_constant__ CUtensorMap map_a,
   if (CM > 1) cluster_sync_all();
   if (warp == 1) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    if (TWO_SM)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -530,11 +618,11 @@ int make_map(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, ui
   return (int)r;
 }
 
-template <int BLOCK_N, int STAGES, int CM>
+template <int BLOCK_N, int STAGES, int CM, bool TWO_SM>
 int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& my, const CUtensorMap& mz,
            const GemmArgs& a, int max_ctas, cudaStream_t s) {
-  constexpr int smem = SmemLayout<BLOCK_N, STAGES>::TOTAL;
-  auto kernel = gemm_bias_act_kernel<BLOCK_N, STAGES, CM>;
+  constexpr int smem = SmemLayout<TWO_SM ? BLOCK_N / 2 : BLOCK_N, STAGES>::TOTAL;
+  auto kernel = gemm_bias_act_kernel<BLOCK_N, STAGES, CM, TWO_SM>;
   static int max_clusters = 0;
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute attr[1];
@@ -572,7 +660,8 @@ extern "C" {
 // rows; K % 64 == 0, N % 128 == 0. block_n: 0 = auto, 128 or 256; cluster_m: 0 = auto, 1, 2, 4. Returns 0, a CUDA error
 // code, or a negative shape/driver error.
 int adl_gemm_bias_act(const void* x, const void* w, const float* bias, void* y, void* z, int M, int N,
-                      int K, int act, int block_n, int cluster_m, int max_ctas, void* err, void* stream) {
+                      int K, int act, int block_n, int cluster_m, int max_ctas, void* err, void* trace,
+                      void* stream) {
   if (K % BLOCK_K != 0 || N % 128 != 0 || M <= 0) return -10;
   if (!load_encode()) return -11;
   if (int rc = adl_bind_thread()) return rc;
@@ -587,9 +676,12 @@ int adl_gemm_bias_act(const void* x, const void* w, const float* bias, void* y, 
   CUtensorMap ma, mb, my, mz;
   if (int rc = make_map(&ma, x, (uint64_t)M, (uint64_t)K, BLOCK_M, BLOCK_K, CU_TENSOR_MAP_SWIZZLE_128B))
     return -100 - rc;
-  if (cluster_m == 0) cluster_m = (M > 3 * BLOCK_M) ? 4 : (M > BLOCK_M ? 2 : 1);
-  if (cluster_m != 1 && cluster_m != 2 && cluster_m != 4) return -13;
-  if (int rc = make_map(&mb, w, (uint64_t)N, (uint64_t)K, (uint32_t)(block_n / cluster_m), BLOCK_K,
+  // cluster_m: 1, 2, 4 = CTAs sharing a multicast weight tile (1-SM MMAs); 22 = CTA pair with
+  // 2-SM MMAs (cta_group::2)
+  if (cluster_m == 0) cluster_m = (M > BLOCK_M && block_n == 256) ? 22 : 1;
+  if (cluster_m != 1 && cluster_m != 2 && cluster_m != 4 && !(cluster_m == 22 && block_n == 256)) return -13;
+  const uint32_t b_box_rows = (uint32_t)(cluster_m == 22 ? block_n / 2 : block_n / cluster_m);
+  if (int rc = make_map(&mb, w, (uint64_t)N, (uint64_t)K, b_box_rows, BLOCK_K,
                         CU_TENSOR_MAP_SWIZZLE_128B))
     return -200 - rc;
   if (int rc = make_map(&my, y, (uint64_t)M, (uint64_t)N, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B)) return -300 - rc;
@@ -601,15 +693,17 @@ int adl_gemm_bias_act(const void* x, const void* w, const float* bias, void* y, 
   a.bias = bias;
   a.M = M; a.N = N; a.K = K; a.act = act;
   a.err = static_cast<uint32_t*>(err);
+  a.trace = static_cast<long long*>(trace);
   cudaStream_t s = (cudaStream_t)stream;
   if (block_n == 256) {
-    if (cluster_m == 4) return launch<256, 3, 4>(ma, mb, my, mz, a, max_ctas, s);
-    if (cluster_m == 2) return launch<256, 3, 2>(ma, mb, my, mz, a, max_ctas, s);
-    return launch<256, 3, 1>(ma, mb, my, mz, a, max_ctas, s);
+    if (cluster_m == 22) return launch<256, 4, 2, true>(ma, mb, my, mz, a, max_ctas, s);
+    if (cluster_m == 4) return launch<256, 3, 4, false>(ma, mb, my, mz, a, max_ctas, s);
+    if (cluster_m == 2) return launch<256, 3, 2, false>(ma, mb, my, mz, a, max_ctas, s);
+    return launch<256, 3, 1, false>(ma, mb, my, mz, a, max_ctas, s);
   }
-  if (cluster_m == 4) return launch<128, 4, 4>(ma, mb, my, mz, a, max_ctas, s);
-  if (cluster_m == 2) return launch<128, 4, 2>(ma, mb, my, mz, a, max_ctas, s);
-  return launch<128, 4, 1>(ma, mb, my, mz, a, max_ctas, s);
+  if (cluster_m == 4) return launch<128, 4, 4, false>(ma, mb, my, mz, a, max_ctas, s);
+  if (cluster_m == 2) return launch<128, 4, 2, false>(ma, mb, my, mz, a, max_ctas, s);
+  return launch<128, 4, 1, false>(ma, mb, my, mz, a, max_ctas, s);
 }
 
 }  // extern "C"

@@ -398,7 +398,8 @@ def test_checkpoint_roundtrip_with_device_engine(tmp_path):
     (128, 128, 64, 128, 1), (256, 256, 128, 256, 2), (1000, 384, 192, 128, 4),
     (4096, 3072, 768, 256, 4), (4096, 3072, 768, 128, 2),
     (4096, 3072, 768, 256, 1), (77, 512, 1024, 0, 0), (640, 256, 64, 256, 4),
-    (300, 768, 3072, 0, 0)])
+    (300, 768, 3072, 0, 0), (4096, 3072, 768, 256, 22), (256, 256, 64, 256, 22),
+    (1000, 512, 192, 256, 22), (128, 256, 128, 256, 22)])
 def test_tcgen05_linear_gelu_forward(m, n, k, block_n, cluster_m):
     from adaptdl_b200.ops import check_errors, gemm_bias_act
     torch.manual_seed(m + n + k)
