@@ -90,9 +90,10 @@ def main():
             if tag == "fused":
                 used_nvls = bool(getattr(red, "nvls_launches", 0))
                 provider, ctas = red._provider.name, red._reduce_ctas
+            length = bucket.length
             del red, arena, bucket
         fused = variants["fused"] / 1e3
-        flat = torch.randn(bucket.length, device=dev)
+        flat = torch.randn(length, device=dev)
         nccl = timed(lambda: dist.all_reduce(flat), iters)
 
         def reference_like():
