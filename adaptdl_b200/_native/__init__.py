@@ -191,6 +191,7 @@ class OptimArgs(ctypes.Structure):
         ("step_ctr", ctypes.c_void_p),
         ("step_offset", ctypes.c_void_p),
         ("n_groups", ctypes.c_int),
+        ("master", ctypes.c_void_p),
     ]
 
 
@@ -212,6 +213,7 @@ class BnArgs(ctypes.Structure):
         ("gamma", ctypes.c_void_p), ("beta", ctypes.c_void_p),
         ("mean", ctypes.c_void_p), ("rstd", ctypes.c_void_p),
         ("running_mean", ctypes.c_void_p), ("running_var", ctypes.c_void_p),
+        ("num_batches_tracked", ctypes.c_void_p),
         ("dgamma", ctypes.c_void_p), ("dbeta", ctypes.c_void_p),
         ("partial", ctypes.c_void_p), ("counters", ctypes.c_void_p),
         ("cb", ctypes.c_int), ("coef", ctypes.c_void_p),

@@ -15,14 +15,26 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from adaptdl_b200.models import resnet as _resnet
+from adaptdl_b200.ops.bn_act import BatchNormAct2d
+
+
+class ConvBN(nn.Module):
+    """conv (no bias) -> BatchNorm (-> ReLU); the normalisation and the
+    activation are one fused kernel on B200 (``ops.BatchNormAct2d``)."""
+
+    def __init__(self, cin, cout, k=3, stride=1, groups=1, act=True):
+        super().__init__()
+        self.conv = nn.Conv2d(cin, cout, k, stride, padding=k // 2,
+                              groups=groups, bias=False)
+        self.bn = BatchNormAct2d(cout)
+        self.act = act
+
+    def forward(self, x, residual=None):
+        return self.bn(self.conv(x), residual, self.act)
 
 
 def conv_bn(cin, cout, k=3, stride=1, groups=1, act=True):
-    layers = [nn.Conv2d(cin, cout, k, stride, padding=k // 2, groups=groups,
-                        bias=False), nn.BatchNorm2d(cout)]
-    if act:
-        layers.append(nn.ReLU(inplace=True))
-    return nn.Sequential(*layers)
+    return ConvBN(cin, cout, k, stride, groups, act)
 
 
 class _Head(nn.Module):

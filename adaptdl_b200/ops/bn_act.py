@@ -117,7 +117,7 @@ def _like(x, ref):
 class _BnAct(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, running_mean, running_var, residual,
-                relu, momentum, eps):
+                relu, momentum, eps, num_batches_tracked=None):
         from adaptdl_b200._native import BnArgs
         dev, c = x.device, x.shape[1]
         m = x.numel() // c
@@ -139,6 +139,7 @@ class _BnAct(torch.autograd.Function):
         a.gamma, a.beta = gamma.data_ptr(), beta.data_ptr()
         a.mean, a.rstd = mean.data_ptr(), rstd.data_ptr()
         a.running_mean, a.running_var = _ptr(running_mean), _ptr(running_var)
+        a.num_batches_tracked = _ptr(num_batches_tracked)
         a.partial = scratch.data_ptr()
         a.coef = scratch.data_ptr() + grid * 2 * c * 4
         a.M, a.C, a.n_partial, a.relu = m, c, grid, int(relu)
@@ -149,8 +150,9 @@ class _BnAct(torch.autograd.Function):
         ctx.relu = bool(relu)
         ctx.has_res = residual is not None
         ctx.has_affine = (weight is not None, bias is not None)
-        ctx.mark_non_differentiable(*[t for t in (running_mean, running_var)
-                                      if t is not None])
+        ctx.mark_non_differentiable(*[
+            t for t in (running_mean, running_var, num_batches_tracked)
+            if t is not None])
         return y
 
     @staticmethod
@@ -183,16 +185,21 @@ class _BnAct(torch.autograd.Function):
             dres = dy                      # identity: d(residual) = dy
         return (dx, dgamma if ctx.has_affine[0] else None,
                 dbeta if ctx.has_affine[1] else None, None, None, dres,
-                None, None, None)
+                None, None, None, None)
 
 
 def bn_act(x, weight, bias, running_mean=None, running_var=None,
-           residual=None, relu=True, training=True, momentum=0.1, eps=1e-5):
-    """``act(batch_norm(x) + residual)`` (``act`` = ReLU or identity)."""
+           residual=None, relu=True, training=True, momentum=0.1, eps=1e-5,
+           num_batches_tracked=None):
+    """``act(batch_norm(x) + residual)`` (``act`` = ReLU or identity).
+    ``num_batches_tracked`` (int64 scalar tensor) is incremented if given."""
     if training and supported(x) and \
             (residual is None or residual.shape == x.shape):
         return _BnAct.apply(x, weight, bias, running_mean, running_var,
-                            residual, relu, momentum, eps)
+                            residual, relu, momentum, eps,
+                            num_batches_tracked)
+    if num_batches_tracked is not None:
+        num_batches_tracked.add_(1)
     out = F.batch_norm(x, running_mean, running_var, weight, bias, training,
                        momentum, eps)
     if residual is not None:
@@ -205,19 +212,17 @@ class BatchNormAct2d(nn.BatchNorm2d):
     State-dict compatible with ``nn.BatchNorm2d``."""
 
     def forward(self, x, residual=None, relu=True):
-        if self.training and self.track_running_stats:
-            if self.num_batches_tracked is not None:
-                self.num_batches_tracked.add_(1)
-            if self.momentum is None:       # cumulative average: not fused
-                out = super().forward(x)
-                self.num_batches_tracked.sub_(1)
-                if residual is not None:
-                    out = out + residual
-                return F.relu(out) if relu else out
+        tracking = self.training and self.track_running_stats
+        if tracking and self.momentum is None:   # cumulative average: not fused
+            out = super().forward(x)
+            if residual is not None:
+                out = out + residual
+            return F.relu(out) if relu else out
         use_batch = self.training or self.running_mean is None
         return bn_act(
             x, self.weight, self.bias,
             self.running_mean if self.track_running_stats else None,
             self.running_var if self.track_running_stats else None,
             residual, relu, use_batch,
-            self.momentum if self.momentum is not None else 0.1, self.eps)
+            self.momentum if self.momentum is not None else 0.1, self.eps,
+            self.num_batches_tracked if tracking else None)

@@ -136,16 +136,26 @@ class DeviceEngine(object):
                                       dtype=torch.int32, device=dev),
             "param_ptr": torch.tensor([p.data_ptr() for p in params],
                                       dtype=torch.int64, device=dev),
-            "state0": None, "state1": None,
+            "state0": None, "state1": None, "master": None,
         }
+        # 16-bit parameters are trained in mixed precision: fp32 master
+        # weights and fp32 optimizer state in flat arenas, the fused kernel
+        # writes the rounded 16-bit weights the forward pass reads
+        wide = arena.dtype in (torch.bfloat16, torch.float16)
+        state_dtype = torch.float32 if wide else arena.dtype
         needs0 = self.kind == "adam" or any(
             g.get("momentum", 0) != 0 for g in self.optimizer.param_groups)
         if needs0:
-            t["state0"] = torch.zeros(max(arena.total, 1), dtype=arena.dtype,
+            t["state0"] = torch.zeros(max(arena.total, 1), dtype=state_dtype,
                                       device=dev)
         if self.kind == "adam":
-            t["state1"] = torch.zeros(max(arena.total, 1), dtype=arena.dtype,
+            t["state1"] = torch.zeros(max(arena.total, 1), dtype=state_dtype,
                                       device=dev)
+        if wide:
+            t["master"] = torch.zeros(max(arena.total, 1),
+                                      dtype=torch.float32, device=dev)
+            for view, p in zip(self._state_views(t, "master"), params):
+                view.copy_(p.detach())
         return t
 
     def _state_views(self, table, key):
@@ -156,6 +166,47 @@ class DeviceEngine(object):
             out.append(piece.as_strided(p.shape, p.stride())
                        if not p.is_contiguous() else piece.view(p.shape))
         return out
+
+    def wide_state(self):
+        """fp32 master weights + optimizer state of the 16-bit arenas, keyed
+        by (arena index, segment index): what a checkpoint must carry on top
+        of ``optimizer.state_dict()`` (whose loader rounds state tensors to
+        the parameter dtype)."""
+        out = {}
+        for ai, table in enumerate(self._tables):
+            if table["master"] is None:
+                continue
+            for key in ("master", "state0", "state1"):
+                if table[key] is not None:
+                    for si, view in enumerate(self._state_views(table, key)):
+                        out[(ai, si, key)] = view.detach().cpu().clone()
+        return out
+
+    def load_wide_state(self, saved):
+        for ai, table in enumerate(self._tables):
+            if table["master"] is None:
+                continue
+            for key in ("master", "state0", "state1"):
+                if table[key] is None:
+                    continue
+                views = self._state_views(table, key)
+                for si, view in enumerate(views):
+                    src = saved.get((ai, si, key))
+                    if src is not None and src.shape == view.shape:
+                        view.copy_(src)
+            # the 16-bit weights are the rounded masters
+            for view, p in zip(self._state_views(table, "master"),
+                               table["params"]):
+                p.data.copy_(view)
+
+    def resync_master(self):
+        """Re-derive the masters from the (just loaded / broadcast) 16-bit
+        parameters -- used when no saved master is available."""
+        for table in self._tables:
+            if table["master"] is not None:
+                for view, p in zip(self._state_views(table, "master"),
+                                   table["params"]):
+                    view.copy_(p.detach())
 
     def adopt_optimizer_state(self):
         """Move whatever state the torch optimizer holds (fresh, or just
@@ -183,6 +234,8 @@ class DeviceEngine(object):
                             views[i].data_ptr():
                         views[i].copy_(old)
                     st[name] = views[i]
+                if table["master"] is not None:
+                    st["master_param"] = self._master_views(table)[i]
                 if self.kind == "adam":
                     step = st.get("step")
                     if step is not None:
@@ -192,6 +245,13 @@ class DeviceEngine(object):
         if self.kind == "adam" and loaded_step is not None:
             self.opt_steps.fill_(loaded_step)
             self._opt_steps_host = loaded_step
+
+    def _master_views(self, table):
+        cached = table.get("_master_views")
+        if cached is None:
+            cached = self._state_views(table, "master")
+            table["_master_views"] = cached
+        return cached
 
     def refresh_param_pointers(self):
         for table in self._tables:
@@ -311,6 +371,8 @@ class DeviceEngine(object):
             args.step_ctr = self.opt_steps.data_ptr()
             args.step_offset = self._one().data_ptr()
             args.n_groups = self.num_groups
+            args.master = table["master"].data_ptr() \
+                if table["master"] is not None else None
             grid = max(1, min(2 * red._sm_count,
                               (table["n_vec"] + 2 * 512 - 1) // (2 * 512)))
             check(self._lib.adl_fused_optim(

@@ -22,7 +22,7 @@ from adaptdl_b200.utils import parse_version, pick_unused_port
 from .epoch import current_epoch, finished_epochs, remaining_epochs_until
 from .data import (current_dataloader, AdaptiveDataLoader, ElasticSampler,
                    DevicePrefetcher)
-from .parallel import AdaptiveDataParallel
+from .parallel import AdaptiveDataParallel, mixed_precision_params
 from .accumulator import Accumulator
 from adaptdl_b200.parallel.graph import GraphedTrainStep
 
@@ -40,6 +40,7 @@ __all__ = [
     "Accumulator",
     "DevicePrefetcher",
     "GraphedTrainStep",
+    "mixed_precision_params",
 ]
 
 

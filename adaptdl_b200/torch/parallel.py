@@ -110,11 +110,17 @@ class AdaptiveDataParallel(torch.nn.Module):
 
         self._state = _AdaptiveDataParallelState(
             model, optimizer, lr_scheduler, mp_scaler, name, self._engine)
-        checkpoint.load_state(self._state)
+        loaded = checkpoint.load_state(self._state)
         if self._engine is not None:
             self._engine.adopt_optimizer_state()
             self._engine.push_gns_state(optimizer.state["gns"])
+            if self._state.wide_state is not None:
+                # exact fp32 masters / optimizer state of 16-bit parameters
+                self._engine.load_wide_state(self._state.wide_state)
+                self._state.wide_state = None
         self._sync_module_states()
+        if self._engine is not None and not loaded:
+            self._engine.resync_master()     # masters = the broadcast weights
 
     # ------------------------------------------------------------------
 
@@ -261,6 +267,22 @@ class AdaptiveDataParallel(torch.nn.Module):
                           global_step)
 
 
+def mixed_precision_params(model, dtype=torch.bfloat16, min_dim=2):
+    """Store the matrix-like parameters of ``model`` (``dim >= min_dim``:
+    convolution / linear / embedding weights) in ``dtype`` -- call it BEFORE
+    building the optimizer. With :class:`AdaptiveDataParallel`'s device
+    engine the fused optimizer keeps fp32 master weights and fp32 momentum /
+    Adam moments for them and writes the rounded 16-bit weights itself, so a
+    bf16-autocast step runs without a single cast kernel: the forward reads
+    the 16-bit weights directly, weight gradients arrive (and are
+    all-reduced) in 16 bits. Normalisation parameters and biases stay fp32.
+    Returns ``model``."""
+    for p in model.parameters():
+        if p.dim() >= min_dim and p.is_floating_point():
+            p.data = p.data.to(dtype)
+    return model
+
+
 class _AdaptiveDataParallelState(checkpoint.State):
     """``torch.save(([model_sd, optim_sd, sched_sd|None, scaler_sd|None],
     gain, lr_factor))`` -- the reference's layout (App. B); the GNS running
@@ -276,6 +298,7 @@ class _AdaptiveDataParallelState(checkpoint.State):
         self.mp_scaler = mp_scaler
         self.gain = 1.0
         self.lr_factor = 1.0
+        self.wide_state = None       # loaded, not yet applied to the engine
 
     def sync(self):
         # device-resident estimator / Adam step counters -> host dicts
@@ -291,6 +314,13 @@ class _AdaptiveDataParallelState(checkpoint.State):
             self.mp_scaler.state_dict()
             if self.mp_scaler is not None else None,
         ]
+        if self.engine is not None and self.engine.enabled:
+            wide = self.engine.wide_state()
+            if wide:
+                # fifth entry (ignored by the reference's loader): fp32
+                # masters + optimizer state of bf16/fp16 parameters, which
+                # Optimizer.load_state_dict would round to the param dtype
+                state_dicts.append(wide)
         torch.save((state_dicts, self.gain, self.lr_factor), fileobj)
 
     def load(self, fileobj):
@@ -303,3 +333,5 @@ class _AdaptiveDataParallelState(checkpoint.State):
             self.lr_scheduler.load_state_dict(state_dicts[2])
         if state_dicts[3] is not None and self.mp_scaler is not None:
             self.mp_scaler.load_state_dict(state_dicts[3])
+        if len(state_dicts) > 4 and state_dicts[4]:
+            self.wide_state = state_dicts[4]

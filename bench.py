@@ -51,6 +51,10 @@ def parse_args():
                          "needs torchtext)")
     ap.add_argument("--device", default="cuda")
     ap.add_argument("--reducer", default="auto")
+    ap.add_argument("--param-dtype", default="bf16", choices=["bf16", "fp32"],
+                    help="own arm: store conv/linear weights in bf16 with "
+                         "fp32 masters inside the fused optimizer (default) "
+                         "or keep fp32 weights + autocast casts")
     ap.add_argument("--no-graph", action="store_true",
                     help="own arm: eager step instead of the CUDA-graph step")
     return ap.parse_args()
@@ -309,6 +313,9 @@ def build_program(args, adl, device, world, workload):
     model = workload.model().to(device)
     if device.type == "cuda" and workload.channels_last:
         model = model.to(memory_format=torch.channels_last)
+    if workload.own and device.type == "cuda" and args.param_dtype == "bf16" \
+            and not args.no_graph:
+        adl.mixed_precision_params(model)
     optimizer, scheduler = workload.optimizer(model)
     kwargs = {}
     if workload.own and args.reducer != "auto":
@@ -481,6 +488,11 @@ def run(args, rank, world, local_rank):
                 "adaptive": "autoscale_batch_size(max=32x, local 32..1024)",
                 "memory_format": ("channels_last, " if workload.channels_last
                                   else "") + "bf16 autocast",
+                "params": ("bf16 weights, fp32 masters + fp32 optimizer "
+                           "state in the fused optimizer"
+                           if (own and args.param_dtype == "bf16"
+                               and not args.no_graph and device.type == "cuda")
+                           else "fp32 weights (autocast casts per step)"),
                 "l2": "working set > L2 (activations of a 128-sample batch "
                       "exceed 126 MB) and a fresh batch every e2e step",
                 "step": ("eager" if (not own or args.no_graph)

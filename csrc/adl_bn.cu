@@ -35,6 +35,7 @@ struct BnArgs {
   float* rstd;          // [C]  saved 1/sqrt(var + eps)
   float* running_mean;  // [C] (or null)
   float* running_var;   // [C] (or null)
+  long long* num_batches_tracked;  // scalar counter of nn.BatchNorm (or null): +1 per forward
   float* dgamma;        // [C]
   float* dbeta;         // [C]
   float* partial;       // [C / cb, grid.y, 2, cb] scratch
@@ -166,7 +167,10 @@ bn_reduce_kernel(const BnArgs a) {
     tot[threadIdx.x] = (float)(t / (double)a.M);  // mean-like quantities from here on
   }
   __syncthreads();
-  if (threadIdx.x == 0) a.counters[blockIdx.x] = 0;
+  if (threadIdx.x == 0) {
+    a.counters[blockIdx.x] = 0;
+    if (!BWD && blockIdx.x == 0 && a.num_batches_tracked != nullptr) *a.num_batches_tracked += 1;
+  }
   if (threadIdx.x >= cb) return;
   const int c = c0 + threadIdx.x;
   const float m0 = tot[threadIdx.x], m1 = tot[cb + threadIdx.x];

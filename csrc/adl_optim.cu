@@ -8,6 +8,12 @@
 // (momentum / Adam moments) lives in flat arenas whose views are exposed to
 // torch as optimizer.state[...] for checkpoint compatibility.
 //
+// 16-bit parameters (bf16 / fp16 arenas) are updated in MIXED PRECISION: an fp32 master copy
+// of the weights and fp32 optimizer state live in flat arenas of the same layout (`master`,
+// state0/state1 then hold floats); the kernel reads the 16-bit gradient, updates master and
+// state in fp32 and writes the rounded 16-bit parameter the forward pass uses -- no per-tensor
+// cast kernels anywhere in the step.
+//
 // The learning rate of group g is  hyper[g].lr * lr_factor[g]  where
 // lr_factor is written ON THE DEVICE by the gradient-noise-scale estimator
 // (adl_finalize_stats) -- the AdaScale gain never round-trips through Python,
@@ -32,6 +38,7 @@ struct OptimArgs {
   const uint32_t* step_ctr;              // optimizer steps finalized (Adam bias correction)
   const int* step_offset;                // device int: adam_step = *step_ctr + *step_offset
   int n_groups;
+  float* master;                         // fp32 master weights, arena layout (16-bit arenas only)
 };
 
 template <typename T> __device__ __forceinline__ float to_f(T x);
@@ -43,8 +50,21 @@ template <> __device__ __forceinline__ float from_f<float>(float x) { return x; 
 template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float x) { return __float2bfloat16_rn(x); }
 template <> __device__ __forceinline__ __half from_f<__half>(float x) { return __float2half_rn(x); }
 
-// ADAM: 0 = SGD(momentum, nesterov), 1 = Adam / AdamW
-template <typename T, int ADAM>
+// N consecutive floats of a flat fp32 array starting at element e0 (e0 % N == 0)
+template <int N>
+__device__ __forceinline__ void ld_f32(const float* base, int e0, float* out) {
+#pragma unroll
+  for (int i = 0; i < N; i += 4) unpack<float>(ld_vec(base + e0 + i), out + i);
+}
+template <int N>
+__device__ __forceinline__ void st_f32(float* base, int e0, const float* in) {
+#pragma unroll
+  for (int i = 0; i < N; i += 4) st_vec(base + e0 + i, pack<float>(in + i));
+}
+
+// ADAM: 0 = SGD(momentum, nesterov), 1 = Adam / AdamW. WIDE: fp32 master weights + fp32 state
+// next to 16-bit parameters / gradients.
+template <typename T, int ADAM, bool WIDE>
 __global__ void __launch_bounds__(ADL_THREADS, 2) fused_optim_kernel(const OptimArgs a) {
   constexpr int N = VecTraits<T>::N;
   if (a.lr_factor && a.lr_factor[a.n_groups] == 0.f) return;   // non-finite gradients: skip
@@ -71,13 +91,20 @@ __global__ void __launch_bounds__(ADL_THREADS, 2) fused_optim_kernel(const Optim
 
     float gr[N], p[N], s0[N], s1[N];
     unpack<T>(ld_vec(static_cast<const Vec16*>(a.grad) + v), gr);
-    if (a.state0) unpack<T>(ld_vec(static_cast<const Vec16*>(a.state0) + v), s0);
-    else {
+    if (a.state0) {
+      if (WIDE) ld_f32<N>(static_cast<const float*>(a.state0), e0, s0);
+      else unpack<T>(ld_vec(static_cast<const Vec16*>(a.state0) + v), s0);
+    } else {
 #pragma unroll
       for (int e = 0; e < N; ++e) s0[e] = 0.f;
     }
-    if (ADAM) unpack<T>(ld_vec(static_cast<const Vec16*>(a.state1) + v), s1);
-    if (vec_ok) {
+    if (ADAM) {
+      if (WIDE) ld_f32<N>(static_cast<const float*>(a.state1), e0, s1);
+      else unpack<T>(ld_vec(static_cast<const Vec16*>(a.state1) + v), s1);
+    }
+    if (WIDE) {
+      ld_f32<N>(a.master, e0, p);
+    } else if (vec_ok) {
       unpack<T>(*reinterpret_cast<const Vec16*>(pbase), p);
     } else {
 #pragma unroll
@@ -114,6 +141,7 @@ __global__ void __launch_bounds__(ADL_THREADS, 2) fused_optim_kernel(const Optim
         p[e] = fmaf(-step_size, s0[e] / denom, p[e]);
       }
     }
+    if (WIDE) st_f32<N>(a.master, e0, p);
     if (vec_ok) {
       *reinterpret_cast<Vec16*>(pbase) = pack<T>(p);
     } else {
@@ -122,7 +150,13 @@ __global__ void __launch_bounds__(ADL_THREADS, 2) fused_optim_kernel(const Optim
     }
     // state arenas share the gradient arena's layout (padding included)
     if (!ADAM) {
-      if (h[1] != 0.f && a.state0) st_vec(static_cast<Vec16*>(a.state0) + v, pack<T>(s0));
+      if (h[1] != 0.f && a.state0) {
+        if (WIDE) st_f32<N>(static_cast<float*>(a.state0), e0, s0);
+        else st_vec(static_cast<Vec16*>(a.state0) + v, pack<T>(s0));
+      }
+    } else if (WIDE) {
+      st_f32<N>(static_cast<float*>(a.state0), e0, s0);
+      st_f32<N>(static_cast<float*>(a.state1), e0, s1);
     } else {
       st_vec(static_cast<Vec16*>(a.state0) + v, pack<T>(s0));
       st_vec(static_cast<Vec16*>(a.state1) + v, pack<T>(s1));
@@ -137,14 +171,16 @@ extern "C" {
 int adl_fused_optim(const OptimArgs* args, int adam, int dtype, int grid, void* stream) {
   if (int rc = adl_bind_thread()) return rc;
   cudaStream_t s = (cudaStream_t)stream;
-#define LAUNCH_O(T)                                                              \
-  do {                                                                           \
-    if (adam) fused_optim_kernel<T, 1><<<grid, ADL_THREADS, 0, s>>>(*args);      \
-    else fused_optim_kernel<T, 0><<<grid, ADL_THREADS, 0, s>>>(*args);           \
+#define LAUNCH_O(T, WIDE)                                                              \
+  do {                                                                                 \
+    if (adam) fused_optim_kernel<T, 1, WIDE><<<grid, ADL_THREADS, 0, s>>>(*args);      \
+    else fused_optim_kernel<T, 0, WIDE><<<grid, ADL_THREADS, 0, s>>>(*args);           \
   } while (0)
-  if (dtype == 0) LAUNCH_O(float);
-  else if (dtype == 1) LAUNCH_O(__nv_bfloat16);
-  else if (dtype == 2) LAUNCH_O(__half);
+  const bool wide = args->master != nullptr;
+  if (wide && dtype == 0) return -3;
+  if (dtype == 0) LAUNCH_O(float, false);
+  else if (dtype == 1) { if (wide) LAUNCH_O(__nv_bfloat16, true); else LAUNCH_O(__nv_bfloat16, false); }
+  else if (dtype == 2) { if (wide) LAUNCH_O(__half, true); else LAUNCH_O(__half, false); }
   else return -2;
 #undef LAUNCH_O
   return (int)cudaGetLastError();

@@ -13,6 +13,8 @@ to a 1-D ``torch.save``d LongTensor.
         --interval 20 examples/transformer/transformer.py --epochs 3
 """
 import argparse
+import faulthandler
+import signal
 import math
 import os
 import sys
@@ -37,6 +39,9 @@ def token_stream(n, seed):
     # Zipf-like: exponentiate a uniform variate
     u = torch.rand(n, generator=gen)
     return (NTOKENS ** u).long().clamp_(0, NTOKENS - 1)
+
+
+faulthandler.register(signal.SIGUSR1)   # kill -USR1 <pid>: thread dump
 
 
 def main():

@@ -232,7 +232,7 @@ def _single_process_runtime():
 
 
 def _train(adl, make_opt, rule_fn, fused, graphed, steps=14, accum=False,
-           model_fn=None, lag=None):
+           model_fn=None, lag=None, autocast=None):
     """Train a small model through the public API; returns (params, gns
     dict, net)."""
     dev = torch.device("cuda", 0)
@@ -269,7 +269,7 @@ def _train(adl, make_opt, rule_fn, fused, graphed, steps=14, accum=False,
         helper._sync_local_bsz = fixed
     trainer = adl.GraphedTrainStep(
         net, opt, lambda n, x, y: torch.nn.functional.cross_entropy(n(x), y),
-        warmup=2, enabled=graphed)
+        warmup=2, enabled=graphed, autocast_dtype=autocast)
     losses = []
     for epoch in adl.remaining_epochs_until(adl.finished_epochs() + 1):
         for i, (x, y) in enumerate(loader):
@@ -388,6 +388,73 @@ def test_checkpoint_roundtrip_with_device_engine(tmp_path):
     probe = {}
     net.engine.pull_gns_state(probe)
     np.testing.assert_allclose(probe["sqr_avg"], gns["sqr_avg"])
+
+
+@pytest.mark.parametrize("opt_name", ["sgd", "adamw"])
+def test_mixed_precision_params_follow_fp32_training(opt_name, tmp_path):
+    """bf16-stored weights + fp32 masters inside the fused optimizer train like
+    fp32 weights under bf16 autocast (same rounded weights in every forward),
+    and a checkpoint restores the masters exactly."""
+    adl = _single_process_runtime()
+    from adaptdl_b200.torch.scaling_rules import LinearScale
+
+    def mlp():
+        return torch.nn.Sequential(
+            torch.nn.Linear(32, 64), torch.nn.ReLU(),
+            torch.nn.Linear(64, 64), torch.nn.Tanh(),
+            torch.nn.Linear(64, 10))
+
+    def mlp16():
+        return adl.mixed_precision_params(mlp())
+
+    def make(model):
+        if opt_name == "sgd":
+            return _sgd(model)
+        return torch.optim.AdamW(model.parameters(), lr=2e-3,
+                                 weight_decay=1e-2)
+    pa, _, net_a, _, la = _train(adl, make, LinearScale, True, False,
+                                 steps=12, model_fn=mlp16,
+                                 autocast=torch.bfloat16)
+    pb, _, net_b, _, lb = _train(adl, make, LinearScale, True, False,
+                                 steps=12, model_fn=mlp,
+                                 autocast=torch.bfloat16)
+    weights = [p for p in net_a.module.parameters() if p.dim() >= 2]
+    assert all(p.dtype == torch.bfloat16 for p in weights)
+    assert all(p.grad.dtype == torch.bfloat16 for p in weights)
+    masters = torch.cat([
+        net_a._state.optimizer.state[p]["master_param"].reshape(-1)
+        if p.dim() >= 2 else p.detach().reshape(-1)
+        for p in net_a.module.parameters()])
+    assert masters.dtype == torch.float32
+    torch.testing.assert_close(la, lb, rtol=2e-2, atol=2e-2)
+    torch.testing.assert_close(masters, pb, rtol=2e-2, atol=2e-3)
+    # the 16-bit weights are the rounded masters
+    for p in weights:
+        m = net_a._state.optimizer.state[p]["master_param"]
+        assert torch.equal(p.detach(), m.to(torch.bfloat16))
+        assert (m - p.detach().float()).abs().max() > 0   # masters carry more
+    # checkpoint: masters survive exactly (Optimizer.load_state_dict alone
+    # would round them to bf16)
+    import io
+    buf = io.BytesIO()
+    net_a._state.sync()
+    net_a._state.save(buf)
+    before = masters.clone()
+    with torch.no_grad():
+        for p in weights:
+            net_a._state.optimizer.state[p]["master_param"].add_(1.0)
+            p.add_(1.0)
+    net_a._state.load(io.BytesIO(buf.getvalue()))
+    net_a.engine.adopt_optimizer_state()
+    net_a.engine.load_wide_state(net_a._state.wide_state)
+    after = torch.cat([
+        net_a._state.optimizer.state[p]["master_param"].reshape(-1)
+        if p.dim() >= 2 else p.detach().reshape(-1)
+        for p in net_a.module.parameters()])
+    assert torch.equal(before, after)
+    for p in weights:
+        m = net_a._state.optimizer.state[p]["master_param"]
+        assert torch.equal(p.detach(), m.to(torch.bfloat16))
 
 
 # ---------------------------------------------------------------------------
