@@ -101,6 +101,22 @@ class BertModel(nn.Module):
         return x
 
 
+def aligned_linear(x, weight, bias, multiple=64):
+    """``F.linear`` for an output width that is not a multiple of 8 (the
+    28 996-token vocabulary of the MLM head): cuBLAS falls back to sm_80
+    ``mma.sync`` kernels for such shapes (3x slower forward, dgrad and wgrad
+    on B200). Zero rows are appended to the weight so that all three GEMMs
+    take the tcgen05 path; the extra logits are dropped again."""
+    n = weight.shape[0]
+    pad = (-n) % multiple
+    if pad == 0 or not x.is_cuda:
+        return F.linear(x, weight, bias)
+    weight = F.pad(weight, (0, 0, 0, pad))
+    if bias is not None:
+        bias = F.pad(bias, (0, pad))
+    return F.linear(x, weight, bias)[..., :n].contiguous()
+
+
 class MLMTask(nn.Module):
     """Encoder + masked-language-model head (untied)."""
 
@@ -116,7 +132,7 @@ class MLMTask(nn.Module):
     def forward(self, src, token_type_input=None):
         out = self.bert_model(src, token_type_input)
         out = self.norm_layer(F.gelu(self.mlm_span(out)))
-        return self.mlm_head(out)
+        return aligned_linear(out, self.mlm_head.weight, self.mlm_head.bias)
 
 
 class NextSentenceTask(nn.Module):

@@ -73,6 +73,9 @@ def main():
             dist.all_gather_object(gathered, (sa.local_sqr.tobytes(),
                                               sa.total_sqr.tobytes()))
             assert all(g == gathered[0] for g in gathered)
+        if os.environ.get("ADAPTDL_EXPECT_NVLS") == "1":
+            assert getattr(ra, "nvls_launches", 0) > 0, \
+                "NVLS flavour was requested but never launched"
         # every rank ends with the same averaged gradients
         flat = torch.cat([p.grad.reshape(-1).float() for p in pa])
         ref = flat.clone()

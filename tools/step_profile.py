@@ -27,6 +27,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--out", default=None)
     ap.add_argument("--top", type=int, default=25)
+    ap.add_argument("--bf16-params", action="store_true",
+                    help="store conv/linear weights in bf16 (no autocast "
+                         "cast kernels); plain torch SGD, no masters")
     args = ap.parse_args()
     from adaptdl_b200 import models
     dev = torch.device("cuda:0")
@@ -47,6 +50,9 @@ def main():
             memory_format=torch.channels_last)
         t = torch.randint(0, 10, (args.batch,), device=dev)
         loss_fn = torch.nn.functional.cross_entropy
+    if args.bf16_params:
+        from adaptdl_b200.torch import mixed_precision_params
+        mixed_precision_params(net)
     opt = torch.optim.SGD(net.parameters(), lr=0.01, momentum=0.9)
 
     def step():
