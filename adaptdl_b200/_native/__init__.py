@@ -26,7 +26,7 @@ LIB_PATH = os.path.join(_HERE, "libadl_b200.so")
 STAMP_PATH = os.path.join(_HERE, "libadl_b200.stamp")
 
 SOURCES = ["adl_kernels.cu", "adl_optim.cu", "adl_gemm.cu", "adl_bn.cu",
-           "adl_symm.cpp"]
+           "adl_ln.cu", "adl_symm.cpp"]
 HEADERS = ["adl_common.cuh"]
 
 NVCC_FLAGS = [
@@ -223,6 +223,21 @@ class BnArgs(ctypes.Structure):
     ]
 
 
+class LnArgs(ctypes.Structure):
+    _fields_ = [
+        ("x", ctypes.c_void_p), ("h", ctypes.c_void_p),
+        ("mask", ctypes.c_void_p), ("y", ctypes.c_void_p),
+        ("z", ctypes.c_void_p), ("dh", ctypes.c_void_p),
+        ("gamma", ctypes.c_void_p), ("beta", ctypes.c_void_p),
+        ("mean", ctypes.c_void_p), ("rstd", ctypes.c_void_p),
+        ("partial", ctypes.c_void_p),
+        ("dgamma", ctypes.c_void_p), ("dbeta", ctypes.c_void_p),
+        ("M", ctypes.c_int), ("D", ctypes.c_int),
+        ("n_partial", ctypes.c_int),
+        ("scale", ctypes.c_float), ("eps", ctypes.c_float),
+    ]
+
+
 def _declare(lib):
     c = ctypes
     lib.adl_set_device.argtypes = [c.c_int]
@@ -268,7 +283,10 @@ def _declare(lib):
         c.c_void_p, c.c_void_p, c.c_void_p]
     lib.adl_bn_act.argtypes = [c.POINTER(BnArgs), c.c_int, c.c_int, c.c_int,
                                c.c_int, c.c_void_p]
+    lib.adl_dropout_add_ln.argtypes = [c.POINTER(LnArgs), c.c_int, c.c_int,
+                                       c.c_int, c.c_void_p]
     for name, struct in (("adl_sizeof_bn_args", BnArgs),
+                         ("adl_sizeof_ln_args", LnArgs),
                          ("adl_sizeof_optim_args", OptimArgs),
                          ("adl_sizeof_reduce_args", ReduceArgs),
                          ("adl_sizeof_local_args", LocalArgs),

@@ -13,6 +13,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from adaptdl_b200.ops.layer_norm import dropout_add_layer_norm
 from adaptdl_b200.ops.linear_act import linear_act
 
 __all__ = ["BertModel", "MLMTask", "NextSentenceTask", "QuestionAnswerTask",
@@ -63,15 +64,19 @@ class EncoderLayer(nn.Module):
             q, k, v, attn_mask=attn_mask, is_causal=is_causal,
             dropout_p=self.drop if self.training else 0.0)
         attn = attn.transpose(1, 2).reshape(n, s, e)
-        x = self.norm1(x + F.dropout(self.out_proj(attn), self.drop,
-                                     self.training))
+        # dropout + residual + LayerNorm: one fused kernel per direction
+        x = dropout_add_layer_norm(x, self.out_proj(attn), self.norm1.weight,
+                                   self.norm1.bias, self.drop, self.training,
+                                   self.norm1.eps)
         if self.activation is F.gelu:
             # bias + GELU fused into the tcgen05 GEMM epilogue on B200
             h = linear_act(x, self.linear1.weight, self.linear1.bias, "gelu")
         else:
             h = self.activation(self.linear1(x))
         h = self.linear2(F.dropout(h, self.drop, self.training))
-        return self.norm2(x + F.dropout(h, self.drop, self.training))
+        return dropout_add_layer_norm(x, h, self.norm2.weight,
+                                      self.norm2.bias, self.drop,
+                                      self.training, self.norm2.eps)
 
 
 class BertModel(nn.Module):

@@ -1,0 +1,287 @@
+// adaptdl_b200 -- fused dropout + residual add + LayerNorm, forward and backward (sm_100a).
+//
+// The transformer workloads (examples/BERT, examples/transformer) close every sub-layer with
+//     y = LayerNorm(x + dropout(h))
+// Stock PyTorch runs it as dropout, add, layer_norm forward and layer_norm_grad_input,
+// GammaBetaBackward, masked_scale, add backward: seven launches and ~36 bytes per element
+// of HBM traffic per sub-layer. Here: ONE forward kernel (reads x, h and the keep-mask, writes
+// y and the pre-norm sum z), ONE backward kernel (reads dy, z, mask; writes dx and dh and the
+// per-CTA partial sums of dgamma / dbeta) and a small column reduction.
+//
+// One warp owns a row at a time: the row lives in registers between the statistics and the
+// normalisation (two-pass variance), 16-byte vectors, lanes keep the same columns for every
+// row they visit so the dgamma / dbeta partials accumulate in registers.
+#include "adl_common.cuh"
+
+namespace {
+
+constexpr int LN_THREADS = 256;
+constexpr int LN_WARPS = LN_THREADS / 32;
+constexpr int LN_MAXV = 4;            // 16-byte vectors per lane (template NV <= 4): D <= 32 * 4 * (4 | 8)
+
+struct LnArgs {
+  const void* x;        // [M, D] residual input
+  const void* h;        // [M, D] sub-layer output (dropout applies to it)        | backward: dy
+  const uint8_t* mask;  // [M, D] 1 = keep (or null: no dropout)
+  void* y;              // [M, D] LayerNorm output                               | backward: dx
+  void* z;              // [M, D] x + dropout(h), saved for the backward pass     | backward: z (input)
+  void* dh;             // backward: [M, D] gradient of h
+  const float* gamma;   // [D]
+  const float* beta;    // [D]
+  float* mean;          // [M]
+  float* rstd;          // [M]
+  float* partial;       // backward: [grid, 2, D] (dgamma, dbeta) partial sums
+  float* dgamma;        // [D]
+  float* dbeta;         // [D]
+  int M, D;
+  int n_partial;
+  float scale;          // 1 / (1 - p)
+  float eps;
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// keep-mask bytes of one vector (V = 4 or 8 elements)
+template <int V>
+__device__ __forceinline__ void ld_mask(const uint8_t* p, float* keep) {
+  if (V == 8) {
+    const uint2 m = *reinterpret_cast<const uint2*>(p);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      keep[e] = (float)((m.x >> (8 * e)) & 0xffu);
+      keep[4 + e] = (float)((m.y >> (8 * e)) & 0xffu);
+    }
+  } else {
+    const uint32_t m = *reinterpret_cast<const uint32_t*>(p);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) keep[e] = (float)((m >> (8 * e)) & 0xffu);
+  }
+}
+
+template <typename T, int NV>
+__global__ void __launch_bounds__(LN_THREADS)
+ln_fwd_kernel(const LnArgs a) {
+  constexpr int V = VecTraits<T>::N;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nvec = a.D / V;
+  const float inv_d = 1.f / (float)a.D;
+  for (int row = blockIdx.x * LN_WARPS + warp; row < a.M; row += gridDim.x * LN_WARPS) {
+    const size_t base = (size_t)row * a.D;
+    float zr[NV][V];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nvec) {
+        const size_t off = base + (size_t)v * V;
+        float fx[V], fh[V];
+        unpack<T>(ld_vec(static_cast<const T*>(a.x) + off), fx);
+        if (a.h != nullptr) {
+          unpack<T>(ld_vec(static_cast<const T*>(a.h) + off), fh);
+          if (a.mask != nullptr) {
+            float keep[V];
+            ld_mask<V>(a.mask + off, keep);
+#pragma unroll
+            for (int e = 0; e < V; ++e) fh[e] *= keep[e] * a.scale;
+          }
+#pragma unroll
+          for (int e = 0; e < V; ++e) fx[e] += fh[e];
+        }
+        // the sum is what the backward pass sees: round it like the stored copy
+        const Vec16 packed = pack<T>(fx);
+        if (a.z != nullptr) st_vec(static_cast<T*>(a.z) + off, packed);
+        unpack<T>(packed, zr[i]);
+#pragma unroll
+        for (int e = 0; e < V; ++e) sum += zr[i][e];
+      }
+    }
+    const float mean = warp_sum(sum) * inv_d;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (lane + 32 * i < nvec) {
+#pragma unroll
+        for (int e = 0; e < V; ++e) { const float d = zr[i][e] - mean; sq = fmaf(d, d, sq); }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) * inv_d + a.eps);
+    if (lane == 0) { a.mean[row] = mean; a.rstd[row] = rstd; }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nvec) {
+        float out[V];
+#pragma unroll
+        for (int e = 0; e < V; ++e)
+          out[e] = fmaf((zr[i][e] - mean) * rstd, __ldg(a.gamma + v * V + e), __ldg(a.beta + v * V + e));
+        st_vec(static_cast<T*>(a.y) + base + (size_t)v * V, pack<T>(out));
+      }
+    }
+  }
+}
+
+// dz = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma
+// dx = dz,  dh = dz * keep * scale;  partial dgamma += dy * xhat, dbeta += dy
+template <typename T, int NV>
+__global__ void __launch_bounds__(LN_THREADS)
+ln_bwd_kernel(const LnArgs a) {
+  constexpr int V = VecTraits<T>::N;
+  __shared__ float acc[2 * 32 * LN_MAXV * 8];          // [2][D], D <= 1024
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nvec = a.D / V;
+  const float inv_d = 1.f / (float)a.D;
+  float dg[NV][V], db[NV][V];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+#pragma unroll
+    for (int e = 0; e < V; ++e) { dg[i][e] = 0.f; db[i][e] = 0.f; }
+  }
+  for (int row = blockIdx.x * LN_WARPS + warp; row < a.M; row += gridDim.x * LN_WARPS) {
+    const size_t base = (size_t)row * a.D;
+    const float mean = a.mean[row], rstd = a.rstd[row];
+    float xh[NV][V], g[NV][V];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nvec) {
+        const size_t off = base + (size_t)v * V;
+        float fz[V], fdy[V];
+        unpack<T>(ld_vec(static_cast<const T*>(a.z) + off), fz);
+        unpack<T>(ld_vec(static_cast<const T*>(a.h) + off), fdy);   // a.h carries dy
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+          xh[i][e] = (fz[e] - mean) * rstd;
+          g[i][e] = fdy[e] * __ldg(a.gamma + v * V + e);
+          s1 += g[i][e];
+          s2 = fmaf(g[i][e], xh[i][e], s2);
+          dg[i][e] = fmaf(fdy[e], xh[i][e], dg[i][e]);
+          db[i][e] += fdy[e];
+        }
+      }
+    }
+    const float c1 = warp_sum(s1) * inv_d, c2 = warp_sum(s2) * inv_d;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nvec) {
+        const size_t off = base + (size_t)v * V;
+        float dz[V];
+#pragma unroll
+        for (int e = 0; e < V; ++e) dz[e] = rstd * (g[i][e] - c1 - xh[i][e] * c2);
+        st_vec(static_cast<T*>(a.y) + off, pack<T>(dz));              // a.y carries dx
+        if (a.dh != nullptr) {
+          if (a.mask != nullptr) {
+            float keep[V];
+            ld_mask<V>(a.mask + off, keep);
+#pragma unroll
+            for (int e = 0; e < V; ++e) dz[e] *= keep[e] * a.scale;
+          }
+          st_vec(static_cast<T*>(a.dh) + off, pack<T>(dz));
+        }
+      }
+    }
+  }
+  // fold the eight warps' partials in a fixed order and store this CTA's row of partial sums
+  for (int idx = threadIdx.x; idx < 2 * a.D; idx += LN_THREADS) acc[idx] = 0.f;
+  __syncthreads();
+  for (int w = 0; w < LN_WARPS; ++w) {
+    if (warp == w) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int v = lane + 32 * i;
+        if (v < nvec) {
+#pragma unroll
+          for (int e = 0; e < V; ++e) {
+            acc[v * V + e] += dg[i][e];
+            acc[a.D + v * V + e] += db[i][e];
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  float* out = a.partial + (size_t)blockIdx.x * 2 * a.D;
+  for (int idx = threadIdx.x; idx < 2 * a.D; idx += LN_THREADS) out[idx] = acc[idx];
+}
+
+// column sums of the per-CTA partials: CTA = 32 columns, warp w takes partials w, w+8, ...
+__global__ void __launch_bounds__(LN_THREADS)
+ln_param_grad_kernel(const LnArgs a) {
+  __shared__ float red[2][LN_WARPS][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + lane;
+  float tg = 0.f, tb = 0.f;
+  if (col < a.D) {
+    for (int p = warp; p < a.n_partial; p += LN_WARPS) {
+      tg += a.partial[(size_t)p * 2 * a.D + col];
+      tb += a.partial[(size_t)p * 2 * a.D + a.D + col];
+    }
+  }
+  red[0][warp][lane] = tg;
+  red[1][warp][lane] = tb;
+  __syncthreads();
+  if (warp == 0 && col < a.D) {
+    float g = 0.f, b = 0.f;
+#pragma unroll
+    for (int w = 0; w < LN_WARPS; ++w) { g += red[0][w][lane]; b += red[1][w][lane]; }
+    a.dgamma[col] = g;
+    a.dbeta[col] = b;
+  }
+}
+
+template <typename T, int NV>
+void launch(const LnArgs& a, int backward, int grid, cudaStream_t s) {
+  if (!backward) {
+    ln_fwd_kernel<T, NV><<<grid, LN_THREADS, 0, s>>>(a);
+  } else {
+    ln_bwd_kernel<T, NV><<<grid, LN_THREADS, 0, s>>>(a);
+    ln_param_grad_kernel<<<(a.D + 31) / 32, LN_THREADS, 0, s>>>(a);
+  }
+}
+
+template <typename T>
+int run(const LnArgs& a, int backward, int grid, cudaStream_t s) {
+  const int nv = (a.D / VecTraits<T>::N + 31) / 32;    // vectors per lane
+  switch (nv) {
+    case 1: launch<T, 1>(a, backward, grid, s); break;
+    case 2: launch<T, 2>(a, backward, grid, s); break;
+    case 3: launch<T, 3>(a, backward, grid, s); break;
+    case 4: launch<T, 4>(a, backward, grid, s); break;
+    default: return -33;
+  }
+  return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+extern "C" int adl_bind_thread();
+
+extern "C" {
+
+int adl_sizeof_ln_args() { return (int)sizeof(LnArgs); }
+
+// dtype: 0 fp32, 1 bf16, 2 fp16. D must be a multiple of the vector width (4 / 8) and at most
+// 32 * 4 vectors (D <= 1024 for bf16 / fp16, 512 for fp32); backward: n_partial == grid.
+int adl_dropout_add_ln(const void* args, int dtype, int backward, int grid, void* stream) {
+  const LnArgs* a = static_cast<const LnArgs*>(args);
+  if (int rc = adl_bind_thread()) return rc;
+  const int v = dtype == 0 ? 4 : 8;
+  if (a->D % v != 0 || a->D / v > 32 * LN_MAXV) return -30;
+  if (grid <= 0 || (backward && a->n_partial != grid)) return -31;
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (dtype) {
+    case 0: return run<float>(*a, backward, grid, s);
+    case 1: return run<__nv_bfloat16>(*a, backward, grid, s);
+    case 2: return run<__half>(*a, backward, grid, s);
+  }
+  return -32;
+}
+
+}  // extern "C"

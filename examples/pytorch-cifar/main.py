@@ -68,6 +68,9 @@ def main():
     parser.add_argument("--mixed-precision", action="store_true",
                         help="fp16 autocast + GradScaler (reference flag); "
                              "default is bf16 autocast on CUDA")
+    parser.add_argument("--bf16-params", action="store_true",
+                        help="keep conv/linear weights in bf16; the fused "
+                             "optimizer holds fp32 masters (no cast kernels)")
     parser.add_argument("--no-graph", action="store_true")
     parser.add_argument("--synthetic", action="store_true")
     parser.add_argument("--synthetic-size", default=12800, type=int)
@@ -90,6 +93,8 @@ def main():
     if cuda:
         net = net.to(memory_format=torch.channels_last)
         torch.backends.cudnn.benchmark = True
+        if args.bf16_params and not args.mixed_precision:
+            adl.mixed_precision_params(net)     # before the optimizer exists
     criterion = nn.CrossEntropyLoss()
     optimizer = torch.optim.SGD([{"params": [p]} for p in net.parameters()],
                                 lr=args.lr, momentum=0.9, weight_decay=5e-4)

@@ -617,3 +617,68 @@ def test_fused_bn_resnet_matches_unfused_model():
     # elements; compare in norm
     for a, b in zip(results[0][1], results[1][1]):
         assert (a - b).norm().item() <= 1e-2 * (b.norm().item() + 1e-6)
+
+
+# ---------------------------------------------------------------------------
+# fused dropout + residual + LayerNorm (csrc/adl_ln.cu)
+# ---------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape,p", [((4, 128, 768), 0.1), ((37, 200), 0.2),
+                                     ((3, 5, 1024), 0.0), ((16, 8), 0.5),
+                                     ((512, 512), 0.1)])
+def test_fused_dropout_add_layer_norm(dtype, shape, p):
+    from adaptdl_b200.ops import dropout_add_layer_norm
+    from adaptdl_b200.ops.layer_norm import supported
+    torch.manual_seed(7)
+    dev = torch.device("cuda:0")
+    d = shape[-1]
+    if dtype == torch.float32 and d > 512:
+        pytest.skip("fp32 rows wider than 512 use the PyTorch composition")
+    w = (torch.rand(d, device=dev) + 0.5).requires_grad_(True)
+    b = torch.randn(d, device=dev).requires_grad_(True)
+    w2 = w.detach().clone().requires_grad_(True)
+    b2 = b.detach().clone().requires_grad_(True)
+    x1 = (torch.randn(shape, device=dev) * 2).to(dtype).requires_grad_(True)
+    h1 = torch.randn(shape, device=dev).to(dtype).requires_grad_(True)
+    assert supported(h1)
+    x2 = x1.detach().float().requires_grad_(True)
+    h2 = h1.detach().float().requires_grad_(True)
+    mask = (torch.rand(shape, device=dev) > p).to(torch.uint8)
+    y1 = dropout_add_layer_norm(x1, h1, w, b, p, True, 1e-5, mask=mask)
+    z2 = x2 + (h2 * mask.float() / (1 - p) if p > 0 else h2)
+    z2 = z2.to(dtype).float() + (z2 - z2.detach())   # the kernel rounds z
+    y2 = torch.nn.functional.layer_norm(z2, (d,), w2, b2, 1e-5)
+    g = torch.randn(shape, device=dev)
+    y1.backward(g.to(dtype))
+    y2.backward(g.to(dtype).float())
+    tol = 2e-4 if dtype == torch.float32 else 3e-2
+    assert y1.dtype == dtype and y1.shape == tuple(shape)
+    assert torch.allclose(y1.float(), y2, rtol=tol, atol=tol)
+
+    def close(a, c, t):
+        return (a.float() - c).abs().max().item() <= \
+            t * (c.abs().max().item() + 1e-6)
+    gtol = 5e-4 if dtype == torch.float32 else 4e-2
+    assert close(x1.grad, x2.grad, gtol)
+    assert close(h1.grad, h2.grad, gtol)
+    assert close(w.grad, w2.grad, gtol)
+    assert close(b.grad, b2.grad, gtol)
+
+
+@pytest.mark.gpu
+def test_fused_dropout_add_layer_norm_random_mask_and_eval():
+    from adaptdl_b200.ops import dropout_add_layer_norm
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    x = torch.randn(64, 256, device=dev)
+    h = torch.randn(64, 256, device=dev)
+    w = torch.ones(256, device=dev)
+    b = torch.zeros(256, device=dev)
+    ref = torch.nn.functional.layer_norm(x + h, (256,), w, b, 1e-5)
+    out = dropout_add_layer_norm(x, h, w, b, 0.3, False)
+    assert torch.allclose(out, ref, rtol=1e-4, atol=1e-4)
+    a = dropout_add_layer_norm(x, h, w, b, 0.3, True)
+    c = dropout_add_layer_norm(x, h, w, b, 0.3, True)
+    assert not torch.equal(a, c)            # fresh keep-mask per call
+    assert torch.isfinite(a).all()
