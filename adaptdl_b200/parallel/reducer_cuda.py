@@ -108,11 +108,13 @@ class CudaGradReducer(GradReducer):
                 offsets["staging"], _STAGING_BYTES)
         self._grad_ptrs = {}
         self._grad_mc = {}
-        # NVLS: buckets at least this large go through the switch
+        # NVLS: buckets at least this large go through the switch. Measured
+        # at N=8 (profiles/r1_n8_final/allreduce_n8.json): the P2P flavour
+        # wins up to 64 MB, multimem with 96 CTAs wins at 256 MB
         self._nvls_min_bytes = int(float(os.environ.get(
-            "ADAPTDL_B200_NVLS_MIN_MB", "2")) * (1 << 20))
+            "ADAPTDL_B200_NVLS_MIN_MB", "128")) * (1 << 20))
         self._nvls_ctas = max(1, min(int(os.environ.get(
-            "ADAPTDL_B200_NVLS_CTAS", "64")), MAX_CTAS - 1))
+            "ADAPTDL_B200_NVLS_CTAS", "96")), MAX_CTAS - 1))
         for i, arena in enumerate(self.arenas):
             itemsize = torch.empty((), dtype=arena.dtype).element_size()
             view, ptrs = self._region.carve(

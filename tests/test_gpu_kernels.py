@@ -627,7 +627,8 @@ def test_fused_bn_resnet_matches_unfused_model():
 @pytest.mark.parametrize("shape,p", [((4, 128, 768), 0.1), ((37, 200), 0.2),
                                      ((3, 5, 1024), 0.0), ((16, 8), 0.5),
                                      ((512, 512), 0.1)])
-def test_fused_dropout_add_layer_norm(dtype, shape, p):
+def test_fused_dropout_add_layer_norm(dtype, shape, p, monkeypatch):
+    monkeypatch.setenv("ADAPTDL_B200_FUSED_LN", "1")     # opt-in op
     from adaptdl_b200.ops import dropout_add_layer_norm
     from adaptdl_b200.ops.layer_norm import supported
     torch.manual_seed(7)
@@ -667,7 +668,8 @@ def test_fused_dropout_add_layer_norm(dtype, shape, p):
 
 
 @pytest.mark.gpu
-def test_fused_dropout_add_layer_norm_random_mask_and_eval():
+def test_fused_dropout_add_layer_norm_random_mask_and_eval(monkeypatch):
+    monkeypatch.setenv("ADAPTDL_B200_FUSED_LN", "1")
     from adaptdl_b200.ops import dropout_add_layer_norm
     dev = torch.device("cuda:0")
     torch.manual_seed(0)
