@@ -620,8 +620,18 @@ def test_fused_bn_resnet_matches_unfused_model():
 
 
 # ---------------------------------------------------------------------------
-# fused dropout + residual + LayerNorm (csrc/adl_ln.cu)
+# fused dropout + residual + LayerNorm (csrc/adl_ln.cu) -- opt-in op, written
+# after round 1's GPU budget was spent: the tests exist but have never run on
+# hardware, so they only run on request (first thing to do next round):
+#   ADAPTDL_B200_TEST_EXPERIMENTAL=1 python -m pytest tests -m gpu -k layer_norm
 # ---------------------------------------------------------------------------
+_EXPERIMENTAL = pytest.mark.skipif(
+    os.environ.get("ADAPTDL_B200_TEST_EXPERIMENTAL") != "1",
+    reason="experimental op, not validated on hardware yet "
+           "(set ADAPTDL_B200_TEST_EXPERIMENTAL=1)")
+
+
+@_EXPERIMENTAL
 @pytest.mark.gpu
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("shape,p", [((4, 128, 768), 0.1), ((37, 200), 0.2),
@@ -667,6 +677,7 @@ def test_fused_dropout_add_layer_norm(dtype, shape, p, monkeypatch):
     assert close(b.grad, b2.grad, gtol)
 
 
+@_EXPERIMENTAL
 @pytest.mark.gpu
 def test_fused_dropout_add_layer_norm_random_mask_and_eval(monkeypatch):
     monkeypatch.setenv("ADAPTDL_B200_FUSED_LN", "1")
