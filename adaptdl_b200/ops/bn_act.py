@@ -77,7 +77,9 @@ _TICKETS = {}
 def _tickets(device, n):
     """``n`` zeroed int32 ticket counters. They live in a per-device ring:
     the kernels leave them at zero, and consecutive calls take different
-    slots so two launches in flight never share one."""
+    slots, so launches that overlap on different streams only share a
+    counter if they are a full trip around the ring (>= 512 calls) apart;
+    launches on one stream are ordered anyway."""
     state = _TICKETS.get(device.index)
     if state is None:
         state = [torch.zeros(4096, dtype=torch.int32, device=device), 0]
@@ -164,7 +166,8 @@ class _BnAct(torch.autograd.Function):
         vec = 4 if x.dtype == torch.float32 else 8
         dy = _like(dy.to(x.dtype), x)
         dx = torch.empty_like(x)
-        dres = torch.empty_like(x) if ctx.has_res else None
+        # without an activation the residual's gradient is dy itself
+        dres = torch.empty_like(x) if (ctx.has_res and ctx.relu) else None
         dgamma = torch.empty(c, dtype=torch.float32, device=dev)
         dbeta = torch.empty(c, dtype=torch.float32, device=dev)
         cb, grid = _reduce_grid(dev, m, c, vec, 2)
@@ -181,8 +184,8 @@ class _BnAct(torch.autograd.Function):
         a.M, a.C, a.n_partial, a.relu = m, c, grid, int(ctx.relu)
         a.cb, a.counters = cb, _tickets(dev, c // cb)
         _launch(a, x.dtype, 1, grid, _grid(dev, m, c, vec, 2), dev)
-        if not ctx.relu and ctx.has_res:
-            dres = dy                      # identity: d(residual) = dy
+        if ctx.has_res and not ctx.relu:
+            dres = dy
         return (dx, dgamma if ctx.has_affine[0] else None,
                 dbeta if ctx.has_affine[1] else None, None, None, dres,
                 None, None, None, None)

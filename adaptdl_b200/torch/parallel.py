@@ -107,6 +107,7 @@ class AdaptiveDataParallel(torch.nn.Module):
         self.gns.add_backward_listener(self._on_backward_end)
         self.scaling_rule.initialize(self, optimizer, patch_optimizer=True)
         self._engine = self._make_engine(optimizer, mp_scaler, fused_step)
+        self._warn_if_unmastered_16bit(optimizer)
 
         self._state = _AdaptiveDataParallelState(
             model, optimizer, lr_scheduler, mp_scaler, name, self._engine)
@@ -151,6 +152,18 @@ class AdaptiveDataParallel(torch.nn.Module):
             return None
         self.gns.attach_engine(engine)
         return engine
+
+    def _warn_if_unmastered_16bit(self, optimizer):
+        if self._engine is not None:
+            return
+        narrow = [p for g in optimizer.param_groups for p in g["params"]
+                  if p.dtype in (torch.bfloat16, torch.float16)]
+        if narrow:
+            LOG.warning(
+                "%d parameters are stored in 16 bits but the device engine "
+                "(fp32 master weights in the fused optimizer) is not "
+                "active: the optimizer updates them in 16-bit precision",
+                len(narrow))
 
     def _sync_engine_ctrl(self):
         engine = self._engine
