@@ -19,6 +19,12 @@ This tool replays the same experiment against THIS repo's scheduler stack
 * **static** (baseline): every job asks for a fixed number of GPUs and keeps
   its initial batch size; FIFO with backfilling, no pre-emption.
 
+Reported per load level: average / p90 job completion time, restarts per job,
+GPU-hours and node-hours held (what an autoscaled cloud cluster would bill: the
+policy sizes the cluster to a utilisation band, ``pollux.py`` MIN/MAX_UTIL, so
+it deliberately leaves nodes empty when the jobs' speedups have saturated),
+and the policy's wall-clock cost per optimisation cycle.
+
     python tools/sched_sim.py --nodes 16 --gpus-per-node 4 --hours 8 \
         --rates 3,7,10,15 --out profiles/sched_sim.json
 """
@@ -141,6 +147,8 @@ def simulate(rate_per_hour, args, adaptive, seed):
     now, pending, active = 0.0, collections.deque(jobs), []
     dt = args.interval
     policy_seconds = 0.0
+    gpu_seconds = 0.0            # GPU time held by jobs (what a cloud bills)
+    nodes_seconds = 0.0          # nodes with at least one replica
     while (pending or active) and now < horizon * 6:
         while pending and pending[0].arrival <= now:
             active.append(pending.popleft())
@@ -183,6 +191,8 @@ def simulate(rate_per_hour, args, adaptive, seed):
                         free[node] -= 1
                     j.allocation = got
                     j.penalty_until = now + RESTART_SECONDS
+        gpu_seconds += dt * sum(len(j.allocation) for j in active)
+        nodes_seconds += dt * len({n for j in active for n in j.allocation})
         for j in list(active):
             run = max(0.0, now + dt - max(now, j.penalty_until))
             j.progress += j.rate(adaptive) * run
@@ -202,6 +212,10 @@ def simulate(rate_per_hour, args, adaptive, seed):
         if done else None,
         "restarts_per_job": float(np.mean([j.restarts for j in jobs]))
         if jobs else 0.0,
+        "gpu_hours": gpu_seconds / 3600.0,
+        "node_hours": nodes_seconds / 3600.0,
+        "single_gpu_hours_of_work": float(sum(j.single_gpu_hours
+                                              for j in jobs)),
         "policy_seconds_per_cycle": policy_seconds / max(now / dt, 1.0),
     }
 
@@ -228,6 +242,9 @@ def main():
         a, s = row["adaptive"]["avg_jct_hours"], row["static"]["avg_jct_hours"]
         row["avg_jct_ratio_static_over_adaptive"] = \
             (s / a) if (a and s) else None
+        row["node_hours_ratio_static_over_adaptive"] = \
+            row["static"]["node_hours"] / max(row["adaptive"]["node_hours"],
+                                              1e-9)
         rows.append(row)
         print(json.dumps(row), flush=True)
     if args.out:
