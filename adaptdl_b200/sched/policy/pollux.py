@@ -355,8 +355,43 @@ class PolluxPolicy(object):
                           values[i].tolist(), utilities[i], state)
         if idx is None:
             return {}, desired
-        return self._state_to_allocations(states[idx][:, :N], jobs,
-                                          nodes), desired
+        allocations = self._state_to_allocations(states[idx][:, :N], jobs,
+                                                 nodes)
+        self._place_starved(allocations, jobs, nodes)
+        return allocations, desired
+
+    @staticmethod
+    def _place_starved(allocations, jobs, nodes):
+        """No job waits while capacity sits idle. The genetic search limits
+        itself to the desired cluster size (utilisation band), which on a
+        busy, fixed-size cluster can leave recently arrived jobs without a
+        single replica next to free GPUs. Give each such job its minimum
+        (at least one replica) on one node, preferring nodes that are already
+        in use so that empty nodes stay releasable. This goes beyond the
+        reference policy (``pollux.py:200-215`` returns the selected state
+        as is); a job at one replica has speedup 1 instead of 0 and nobody
+        else's allocation changes, so the cycle's utility only improves."""
+        free = {key: dict(node.resources) for key, node in nodes.items()}
+        for key, placement in allocations.items():
+            for node in placement:
+                for rtype, amount in jobs[key].resources.items():
+                    free[node][rtype] = free[node].get(rtype, 0) - amount
+        in_use = {node for placement in allocations.values()
+                  for node in placement}
+        for key, job in jobs.items():           # policy order (FIFO inside)
+            if allocations.get(key):
+                continue
+            want = max(job.min_replicas, 1)
+            for name in sorted(free, key=lambda n: n not in in_use):
+                fits = min((free[name].get(rtype, 0) // amount
+                            for rtype, amount in job.resources.items()
+                            if amount > 0), default=0)
+                if fits >= want:
+                    allocations[key] = [name] * want
+                    for rtype, amount in job.resources.items():
+                        free[name][rtype] -= amount * want
+                    in_use.add(name)
+                    break
 
 
 _ = copy

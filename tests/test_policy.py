@@ -200,3 +200,23 @@ def test_non_preemptible_jobs_keep_their_allocation(num_nodes,
         victim = random.choice(sorted(allocations))
         (fixed if victim in fixed else preemptible).remove(victim)
         prev.pop(victim)
+
+
+def test_starved_jobs_get_their_minimum_next_to_idle_capacity():
+    from adaptdl_b200.sched.policy import JobInfo, NodeInfo, PolluxPolicy
+    gpu = "nvidia.com/gpu"
+    nodes = {"a": NodeInfo({gpu: 4, "pods": 8}, False),
+             "b": NodeInfo({gpu: 4, "pods": 8}, False)}
+    mk = lambda t, lo=0: JobInfo({gpu: 1, "pods": 1}, lambda n, r: r, t, lo, 8)
+    jobs = {"old": mk(0), "new": mk(1), "pair": mk(2, lo=2), "big": mk(3, lo=4)}
+    alloc = {"old": ["a", "a", "a"], "new": [], "pair": [], "big": []}
+    PolluxPolicy._place_starved(alloc, jobs, nodes)
+    assert alloc["old"] == ["a", "a", "a"]          # untouched
+    assert alloc["new"] == ["a"]                      # packs onto the used node
+    assert alloc["pair"] == ["b", "b"]                # minimum, on one node
+    assert alloc["big"] == []                         # 4 do not fit anywhere
+    used = {}
+    for placement in alloc.values():
+        for node in placement:
+            used[node] = used.get(node, 0) + 1
+    assert all(used[n] <= nodes[n].resources[gpu] for n in used)

@@ -16,8 +16,10 @@ This tool replays the same experiment against THIS repo's scheduler stack
 * **adaptive**: every ``--interval`` seconds the policy re-allocates GPUs from
   the jobs' speedup functions; a job that is re-allocated pays a restart
   penalty; it trains at the batch size that maximises its goodput;
-* **static** (baseline): every job asks for a fixed number of GPUs and keeps
-  its initial batch size; FIFO with backfilling, no pre-emption.
+* **static** (baseline): every job asks for a fixed, per-model TUNED number of
+  GPUs and keeps its initial batch size; FIFO with backfilling, no
+  pre-emption. **static_whole_node**: the same scheduler when every user
+  simply asks for one whole node (the untuned habit).
 
 Reported per load level: average / p90 job completion time, restarts per job,
 GPU-hours and node-hours held (what an autoscaled cloud cluster would bill: the
@@ -124,7 +126,7 @@ class SimJob(object):
         return float(fn.evaluate(nodes, n, atomic, 0))
 
 
-def simulate(rate_per_hour, args, adaptive, seed):
+def simulate(rate_per_hour, args, adaptive, seed, static_gpus=None):
     rng = np.random.default_rng(seed)
     kinds = list(ZOO)
     weights = np.array([0.5, 0.1, 0.2, 0.2])
@@ -138,6 +140,9 @@ def simulate(rate_per_hour, args, adaptive, seed):
     jobs = [SimJob("job-{}".format(i), kinds[rng.choice(len(kinds),
                                                         p=weights)], a, rng)
             for i, a in enumerate(arrivals)]
+    if static_gpus is not None:          # every user asks for the same size
+        for j in jobs:
+            j.static_gpus = static_gpus
     nodes = {"node-{:02d}".format(i): NodeInfo({GPU: args.gpus_per_node,
                                                 "pods": 32}, False)
              for i in range(args.nodes)}
@@ -237,11 +242,17 @@ def main():
     rows = []
     for rate in (float(r) for r in args.rates.split(",")):
         row = {"jobs_per_hour": rate}
-        for name, adaptive in (("static", False), ("adaptive", True)):
-            row[name] = simulate(rate, args, adaptive, args.seed)
+        for name, adaptive, fixed in (
+                ("static", False, None),
+                ("static_whole_node", False, args.gpus_per_node),
+                ("adaptive", True, None)):
+            row[name] = simulate(rate, args, adaptive, args.seed, fixed)
         a, s = row["adaptive"]["avg_jct_hours"], row["static"]["avg_jct_hours"]
         row["avg_jct_ratio_static_over_adaptive"] = \
             (s / a) if (a and s) else None
+        w = row["static_whole_node"]["avg_jct_hours"]
+        row["avg_jct_ratio_whole_node_over_adaptive"] = \
+            (w / a) if (a and w) else None
         row["node_hours_ratio_static_over_adaptive"] = \
             row["static"]["node_hours"] / max(row["adaptive"]["node_hours"],
                                               1e-9)
