@@ -111,7 +111,8 @@ class AdaptiveDataParallel(torch.nn.Module):
 
         self._state = _AdaptiveDataParallelState(
             model, optimizer, lr_scheduler, mp_scaler, name, self._engine)
-        loaded = checkpoint.load_state(self._state)
+        checkpoint.load_state(self._state)
+        exact_masters = False
         if self._engine is not None:
             self._engine.adopt_optimizer_state()
             self._engine.push_gns_state(optimizer.state["gns"])
@@ -119,9 +120,12 @@ class AdaptiveDataParallel(torch.nn.Module):
                 # exact fp32 masters / optimizer state of 16-bit parameters
                 self._engine.load_wide_state(self._state.wide_state)
                 self._state.wide_state = None
+                exact_masters = True
         self._sync_module_states()
-        if self._engine is not None and not loaded:
-            self._engine.resync_master()     # masters = the broadcast weights
+        if self._engine is not None and not exact_masters:
+            # fresh start, or a checkpoint written without the engine: the
+            # masters are the (broadcast / loaded) 16-bit weights
+            self._engine.resync_master()
 
     # ------------------------------------------------------------------
 
