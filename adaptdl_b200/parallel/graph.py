@@ -25,7 +25,6 @@ import torch
 
 from adaptdl_b200.ops import _count as _ops_count
 
-from adaptdl_b200.torch.data import current_dataloader
 
 LOG = logging.getLogger(__name__)
 
@@ -106,6 +105,8 @@ class GraphedTrainStep(object):
 
     def _key(self, inputs):
         net = self.net
+        # imported here: adaptdl_b200.torch imports this module
+        from adaptdl_b200.torch.data import current_dataloader
         dataloader = current_dataloader()
         if dataloader is not None and dataloader.training:
             sync = dataloader.is_optim_step()
