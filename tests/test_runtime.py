@@ -226,3 +226,18 @@ def test_fd_exchange_between_processes():
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
+
+
+def test_modules_import_standalone():
+    """Each sub-package can be the FIRST thing a program imports (no import
+    cycles hidden by importing ``adaptdl_b200.torch`` first)."""
+    import subprocess
+    import sys
+    mods = ["adaptdl_b200.parallel.graph", "adaptdl_b200.parallel.engine",
+            "adaptdl_b200.ops", "adaptdl_b200.models",
+            "adaptdl_b200.torch.parallel", "adaptdl_b200.sched.local"]
+    procs = [subprocess.Popen([sys.executable, "-c", "import " + m],
+                              stderr=subprocess.PIPE) for m in mods]
+    for m, proc in zip(mods, procs):
+        _, err = proc.communicate(timeout=300)
+        assert proc.returncode == 0, (m, err.decode()[-800:])
