@@ -10,6 +10,10 @@ workloads are DATA: one table, three ways to use it --
     python tests/workloads/workloads.py submit resnet18-cifar10-elastic     # through adaptdl_b200.cli
     python tests/workloads/workloads.py local transformer-wikitext2-elastic \
         --gpus 8 --schedule 2,4,8,4 --interval 30                           # no Kubernetes: sched.local
+    python tests/workloads/workloads.py soak --jobs 6                       # keep 6 random jobs alive on the cluster
+                                                                            # (reference tests/testworkload.sh)
+    python tests/workloads/workloads.py standalone3                         # three independent single-replica jobs on this
+                                                                            # box (reference tests/test-localmode2.sh)
 
 ``tests/test_cli.py::test_workload_specs_validate`` runs every manifest
 through the CLI's job preparation and the scheduler's validator on CPU.
@@ -107,6 +111,52 @@ def local_command(name):
     return [os.path.join(ROOT, script)] + list(args)
 
 
+def active_jobs():
+    """Names of AdaptDLJobs that have not reached a final phase."""
+    import json
+    out = subprocess.run(["kubectl", "get", "adaptdljobs", "-o", "json"],
+                         stdout=subprocess.PIPE, check=True).stdout
+    items = json.loads(out).get("items", [])
+    return [item["metadata"]["name"] for item in items
+            if (item.get("status") or {}).get("phase")
+            not in ("Succeeded", "Failed")]
+
+
+def soak(args):
+    """Keep ``--jobs`` randomly chosen workloads of a suite alive: whenever
+    fewer are active, submit more (scheduler soak test)."""
+    import random
+    import time
+    names = [n for n, w in WORKLOADS.items() if w[0] == args.suite]
+    rounds = 0
+    while args.rounds == 0 or rounds < args.rounds:
+        missing = args.jobs - len(active_jobs())
+        for _ in range(max(missing, 0)):
+            name = random.choice(names)
+            print("submitting", name, flush=True)
+            main(["submit", name])
+        rounds += 1
+        time.sleep(args.period)
+    return 0
+
+
+def standalone(names):
+    """Independent single-replica jobs side by side on this machine, each with
+    its own checkpoint directory (standalone mode, no scheduler)."""
+    import tempfile
+    procs = []
+    for i, name in enumerate(names):
+        env = dict(os.environ, PYTHONPATH=ROOT,
+                   ADAPTDL_CHECKPOINT_PATH=tempfile.mkdtemp(
+                       prefix="adaptdl-b200-standalone-"),
+                   ADAPTDL_JOB_ID="standalone/{}-{}".format(name, i))
+        cmd = [sys.executable] + local_command(name)
+        procs.append(subprocess.Popen(cmd, env=env))
+    codes = [p.wait() for p in procs]
+    print("exit codes:", codes)
+    return 0 if all(c == 0 for c in codes) else 1
+
+
 def main(argv=None):
     parser = argparse.ArgumentParser()
     sub = parser.add_subparsers(dest="verb", required=True)
@@ -122,7 +172,19 @@ def main(argv=None):
     p.add_argument("--schedule", default="")
     p.add_argument("--interval", type=float, default=30.0)
     p.add_argument("--adaptive", action="store_true")
+    p = sub.add_parser("soak")
+    p.add_argument("--jobs", type=int, default=4)
+    p.add_argument("--suite", default="short")
+    p.add_argument("--period", type=float, default=60.0)
+    p.add_argument("--rounds", type=int, default=0, help="0 = forever")
+    p = sub.add_parser("standalone3")
+    p.add_argument("--names", default="lr-elastic-cpu,lr-elastic-cpu,"
+                                      "lr-elastic-cpu")
     args = parser.parse_args(argv)
+    if args.verb == "soak":
+        return soak(args)
+    if args.verb == "standalone3":
+        return standalone(args.names.split(","))
     if args.verb == "list":
         for name, (suite, script, wargs, over) in sorted(WORKLOADS.items()):
             print("{:6s} {:40s} {} {}".format(suite, name, script,
