@@ -56,8 +56,11 @@ def _network_time(p, num_nodes, num_replicas):
 
 def _log_optim_time(gamma, accum_time, network_time):
     # log of the gamma-norm, via log-sum-exp for stability at large gamma.
-    return np.logaddexp(gamma * np.log(accum_time),
-                        gamma * np.log(network_time)) / gamma
+    # Perfectly free communication (fitted alpha = beta = 0) is clamped to
+    # _EPS seconds instead of taking log(0).
+    return np.logaddexp(gamma * np.log(np.maximum(accum_time, _EPS)),
+                        gamma * np.log(np.maximum(network_time, _EPS))) \
+        / gamma
 
 
 class GoodputFunction(object):

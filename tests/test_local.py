@@ -1,0 +1,76 @@
+"""Single-box elastic launcher (``adaptdl_b200.sched.local``): hint-driven
+replica choice, the embedded supervisor, and a real 1 -> 2 replica rescale of a
+training script on CPU/gloo (SIGTERM -> checkpoint -> exit 143 -> restart)."""
+
+import json
+import os
+import sys
+import urllib.request
+
+from adaptdl_b200.sched import local
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _hints(alpha_n=0.0, max_profiled=4, var=1.0):
+    return {
+        "perfParams": {"alpha_c": 0.1, "beta_c": 0.01, "alpha_n": alpha_n,
+                       "beta_n": 0.0, "alpha_r": alpha_n, "beta_r": 0.0,
+                       "gamma": 1.0},
+        "gradParams": {"norm": 0.01, "var": var},
+        "initBatchSize": 128, "maxBatchSize": 4096,
+        "localBszBounds": [32, 256], "gradientAccumulation": False,
+        "maxProfiledReplicas": max_profiled,
+    }
+
+
+def test_best_replicas_follows_the_speedup_function():
+    # noisy gradients + free communication: more replicas pay off
+    assert local.best_replicas(_hints(), 8, 1) == 8
+    # exploration is capped at twice the largest profiled replica count
+    assert local.best_replicas(_hints(max_profiled=1), 8, 1) == 2
+    # nothing known yet: stay
+    assert local.best_replicas(None, 8, 3) == 3
+    assert local.best_replicas({"initBatchSize": 128}, 8, 3) == 3
+    # crushing communication cost: one replica is best
+    assert local.best_replicas(_hints(alpha_n=50.0), 8, 1) == 1
+    # hysteresis: a marginal win does not trigger a restart
+    assert local.best_replicas(_hints(alpha_n=50.0), 8, 2,
+                               hysteresis=1e9) == 2
+
+
+def test_hints_server_round_trip():
+    server = local.HintsServer()
+    try:
+        server.replicas = 3
+        with urllib.request.urlopen(
+                server.url + "/discover/ns/job/0?replicas=3") as resp:
+            assert json.loads(resp.read()) == ["127.0.0.1"] * 3
+        body = json.dumps(dict(_hints(), ignored="x")).encode()
+        req = urllib.request.Request(server.url + "/hints/ns/job",
+                                     data=body, method="PUT")
+        with urllib.request.urlopen(req) as resp:
+            assert resp.status == 200
+        assert server.hints["initBatchSize"] == 128
+        assert "ignored" not in server.hints
+    finally:
+        server.close()
+
+
+def test_rescale_a_running_job_1_to_2_replicas(tmp_path):
+    script = os.path.join(ROOT, "examples", "linear_regression", "main.py")
+    env = {"PYTHONPATH": ROOT, "CUDA_VISIBLE_DEVICES": "",
+           "OMP_NUM_THREADS": "1"}
+    job = local.LocalElasticJob(
+        [sys.executable, script, "--epochs", "400", "--size", "4000"], 2,
+        checkpoint_dir=str(tmp_path), env=env)
+    state = job.run(schedule=[1, 2], interval=8.0, stop_after=22.0)
+    events = [(what, detail) for _, what, detail in job.events]
+    started = [d["replicas"] for w, d in events if w == "started"]
+    assert started[:2] == [1, 2], events
+    rescaled = [d for w, d in events if w == "rescaled"]
+    assert rescaled and rescaled[0]["replicas"] == 2
+    assert state in ("stopped", "finished")
+    # the second generation resumed from the first one's checkpoint
+    assert any(name.startswith("checkpoint-")
+               for name in os.listdir(str(tmp_path)))
