@@ -68,7 +68,7 @@ class AdaptiveDataParallel(torch.nn.Module):
         self._key = id(self)
         self.require_backward_grad_sync = True
         self.broadcast_buffers = kwargs.pop("broadcast_buffers", True)
-        bucket_cap_mb = kwargs.pop("bucket_cap_mb", None) or 25
+        bucket_cap_mb = kwargs.pop("bucket_cap_mb", None)
         process_group = kwargs.pop("process_group", None)
         backend = kwargs.pop("reducer", "auto")
         fused_step = kwargs.pop("fused_step", None)
