@@ -189,7 +189,9 @@ def load_state(state):
         return False
     path = os.path.join(ckpt, _REGISTRY.name_of(state))
     if not os.path.isfile(path):
-        LOG.warning("state file %s not found", path)
+        # normal for states created after the checkpoint was written (e.g. a
+        # new epoch's Accumulator): they simply start fresh
+        LOG.debug("state file %s not found", path)
         return False
     with open(path, "rb") as f:
         state.load(f)

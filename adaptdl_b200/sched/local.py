@@ -135,8 +135,13 @@ class LocalElasticJob(object):
         self.events.append((time.time(), what, detail))
         LOG.info("%s %s", what, detail)
 
-    def start(self, replicas):
+    def start(self, replicas, gpu_ids=None):
+        """Start a generation with ``replicas`` processes; ``gpu_ids``
+        (optional) are the device indices of this generation's replicas."""
         assert not self.procs
+        if gpu_ids is not None:
+            assert len(gpu_ids) >= replicas
+            self.gpu_ids = list(gpu_ids)
         port = pick_unused_port()
         self.replicas = self.server.replicas = replicas
         for rank in range(replicas):
@@ -191,10 +196,10 @@ class LocalElasticJob(object):
             p.wait()
         self.procs = []
 
-    def rescale(self, replicas, timeout=300.0):
+    def rescale(self, replicas, timeout=300.0, gpu_ids=None):
         """SIGTERM -> wait for the checkpoint exit -> start the next
-        generation. Returns the state (``"running"`` / ``"finished"`` /
-        ``"failed"``)."""
+        generation (``replicas == 0``: stay stopped). Returns the state
+        (``"running"`` / ``"stopped"`` / ``"finished"`` / ``"failed"``)."""
         t0 = time.time()
         self.signal_stop()
         deadline = t0 + timeout
@@ -210,7 +215,10 @@ class LocalElasticJob(object):
         if state != "preempted":
             return state
         self.num_restarts += 1
-        self.start(replicas)
+        if replicas == 0:
+            self.replicas = 0
+            return "stopped"
+        self.start(replicas, gpu_ids)
         self._log("rescaled", replicas=replicas,
                   seconds=time.time() - t0)
         return "running"

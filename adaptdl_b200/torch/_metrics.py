@@ -15,6 +15,7 @@ blocking ``event.synchronize()`` the reference needs every step.
 
 import collections
 import pickle
+import os
 import time
 
 import numpy as np
@@ -24,7 +25,9 @@ from adaptdl_b200.goodput import GoodputFunction, fit_perf_params
 from adaptdl_b200.sched_hints import SCHED_HINTS, PERF_PARAMS, \
     post_sched_hints
 
-REPORT_PERIOD_S = 30.0
+# seconds between performance fits / scheduling-hint reports (reference: 30 s,
+# torch/_metrics.py:63); overridable for tests and short jobs
+REPORT_PERIOD_S = float(os.environ.get("ADAPTDL_REPORT_PERIOD", "30"))
 
 
 class _MetricsState(checkpoint.State):

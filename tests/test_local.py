@@ -74,3 +74,40 @@ def test_rescale_a_running_job_1_to_2_replicas(tmp_path):
     # the second generation resumed from the first one's checkpoint
     assert any(name.startswith("checkpoint-")
                for name in os.listdir(str(tmp_path)))
+
+
+def test_two_jobs_share_a_box_under_the_pollux_policy(tmp_path):
+    """The multi-job single-box scheduler: two elastic jobs, three "GPUs"
+    (CPU/gloo processes here), Pollux decides who gets how many replicas;
+    both jobs finish and the box is never over-committed."""
+    from adaptdl_b200.sched.local_cluster import LocalCluster
+    from adaptdl_b200.sched.policy import PolluxPolicy
+    script = os.path.join(ROOT, "examples", "linear_regression", "main.py")
+    env = {"PYTHONPATH": ROOT, "CUDA_VISIBLE_DEVICES": "",
+           "OMP_NUM_THREADS": "1", "ADAPTDL_REPORT_PERIOD": "2"}
+    jobs = [{"name": "a", "env": env, "command": [
+                sys.executable, script, "--epochs", "250", "--size", "4000",
+                "--autoscale-bsz"]},
+            {"name": "b", "env": env, "max_replicas": 2, "command": [
+                sys.executable, script, "--epochs", "120", "--size", "4000",
+                "--autoscale-bsz"]}]
+    cluster = LocalCluster(jobs, 3, str(tmp_path),
+                           policy=PolluxPolicy(pop_size=20, generations=10,
+                                               seed=0))
+    held = []
+    orig = cluster.step
+
+    def step():
+        alive = orig()
+        held.append({n: list(d) for n, d in cluster.devices.items()})
+        return alive
+    cluster.step = step
+    done = cluster.run(interval=5.0, timeout=240.0)
+    assert done == {"a": "finished", "b": "finished"}, (done, cluster.events)
+    for snapshot in held:
+        devices = [d for ids in snapshot.values() for d in ids]
+        assert len(devices) == len(set(devices)) <= 3     # no double booking
+        assert len(snapshot["b"]) <= 2
+    allocs = [(d["job"], d["replicas"]) for _, w, d in cluster.events
+              if w == "allocate"]
+    assert ("a", 1) in allocs and ("b", 1) in allocs     # both got started
