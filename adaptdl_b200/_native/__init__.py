@@ -216,6 +216,7 @@ class BnArgs(ctypes.Structure):
         ("num_batches_tracked", ctypes.c_void_p),
         ("dgamma", ctypes.c_void_p), ("dbeta", ctypes.c_void_p),
         ("partial", ctypes.c_void_p), ("counters", ctypes.c_void_p),
+        ("mask", ctypes.c_void_p),
         ("cb", ctypes.c_int), ("coef", ctypes.c_void_p),
         ("M", ctypes.c_int), ("C", ctypes.c_int),
         ("n_partial", ctypes.c_int), ("relu", ctypes.c_int),

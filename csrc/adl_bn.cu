@@ -40,6 +40,9 @@ struct BnArgs {
   float* dbeta;         // [C]
   float* partial;       // [C / cb, grid.y, 2, cb] scratch
   int* counters;        // [C / cb] zero-initialised tickets (left zero again)
+  uint8_t* mask;        // optional [M * C / V] ReLU keep-bits, one byte per 16-byte vector:
+                        // written by the forward pass, read by the backward pass INSTEAD of y
+                        // (1/16 of the bytes)
   int cb;               // channels per reduce CTA (<= 64)
   float* coef;          // [2, C] scratch: forward (scale, shift); backward (s1/M, s2/M)
   int M, C;
@@ -87,7 +90,10 @@ bn_reduce_kernel(const BnArgs a) {
         vx[u] = ld_vec(static_cast<const char*>(a.x) + off);
         if (BWD) {
           vg[u] = ld_vec(static_cast<const char*>(a.dy) + off);
-          if (a.relu) vy[u] = ld_vec(static_cast<const char*>(a.y) + off);
+          if (a.relu) {
+            if (a.mask != nullptr) vy[u].w[0] = a.mask[((size_t)r * a.C + my_c) / V];
+            else vy[u] = ld_vec(static_cast<const char*>(a.y) + off);
+          }
         }
       }
     }
@@ -103,7 +109,14 @@ bn_reduce_kernel(const BnArgs a) {
         } else {
           float fg[V], fy[V];
           unpack<T>(vg[u], fg);
-          if (a.relu) unpack<T>(vy[u], fy);
+          if (a.relu) {
+            if (a.mask != nullptr) {
+#pragma unroll
+              for (int e = 0; e < V; ++e) fy[e] = (float)((vy[u].w[0] >> e) & 1u);
+            } else {
+              unpack<T>(vy[u], fy);
+            }
+          }
 #pragma unroll
           for (int e = 0; e < V; ++e) {
             const float g = (a.relu && !(fy[e] > 0.f)) ? 0.f : fg[e];
@@ -234,7 +247,10 @@ bn_apply_kernel(const BnArgs a) {
           if (a.res) vb[u] = ld_vec(static_cast<const char*>(a.res) + off);
         } else {
           vb[u] = ld_vec(static_cast<const char*>(a.dy) + off);
-          if (a.relu) vy[u] = ld_vec(static_cast<const char*>(a.y) + off);
+          if (a.relu) {
+            if (a.mask != nullptr) vy[u].w[0] = a.mask[((size_t)r * a.C + my_c) / V];
+            else vy[u] = ld_vec(static_cast<const char*>(a.y) + off);
+          }
         }
       }
     }
@@ -254,10 +270,23 @@ bn_apply_kernel(const BnArgs a) {
             out[e] = a.relu ? fmaxf(v, 0.f) : v;
           }
           st_vec(static_cast<char*>(a.y) + off, pack<T>(out));
+          if (a.relu && a.mask != nullptr) {
+            uint32_t bits = 0;
+#pragma unroll
+            for (int e = 0; e < V; ++e) bits |= (out[e] > 0.f ? 1u : 0u) << e;
+            a.mask[((size_t)r * a.C + my_c) / V] = (uint8_t)bits;
+          }
         } else {
           float fy[V], g[V];
           unpack<T>(vb[u], fb);
-          if (a.relu) unpack<T>(vy[u], fy);
+          if (a.relu) {
+            if (a.mask != nullptr) {
+#pragma unroll
+              for (int e = 0; e < V; ++e) fy[e] = (float)((vy[u].w[0] >> e) & 1u);
+            } else {
+              unpack<T>(vy[u], fy);
+            }
+          }
 #pragma unroll
           for (int e = 0; e < V; ++e) {
             g[e] = (a.relu && !(fy[e] > 0.f)) ? 0.f : fb[e];

@@ -525,6 +525,15 @@ def test_tcgen05_linear_gelu_autograd_matches_torch():
         assert (a - b).abs().max().item() <= 3e-2 * scale + 1e-3
 
 
+# experimental code paths: written after round 1's GPU budget was spent, so
+# their tests have never run on hardware and only run on request:
+#   ADAPTDL_B200_TEST_EXPERIMENTAL=1 python -m pytest tests -m gpu -k "layer_norm or bitmask"
+_EXPERIMENTAL = pytest.mark.skipif(
+    os.environ.get("ADAPTDL_B200_TEST_EXPERIMENTAL") != "1",
+    reason="experimental op, not validated on hardware yet "
+           "(set ADAPTDL_B200_TEST_EXPERIMENTAL=1)")
+
+
 # ---------------------------------------------------------------------------
 # fused BatchNorm (+ residual) (+ ReLU), channels-last (csrc/adl_bn.cu)
 # ---------------------------------------------------------------------------
@@ -586,6 +595,30 @@ def test_fused_bn_act_matches_torch(dtype, shape, residual, relu):
         assert close(r1.grad, r2.grad, gtol)
 
 
+@_EXPERIMENTAL
+@pytest.mark.gpu
+def test_fused_bn_act_bitmask_backward_matches_y_backward(monkeypatch):
+    """ADAPTDL_B200_BN_BITMASK=1 (one saved ReLU bit per element instead of
+    re-reading y) gives bit-identical gradients."""
+    from adaptdl_b200.ops import BatchNormAct2d
+    dev = torch.device("cuda:0")
+    grads = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("ADAPTDL_B200_BN_BITMASK", flag)
+        torch.manual_seed(11)
+        bn = BatchNormAct2d(128).to(dev)
+        x = torch.randn(16, 128, 8, 8, device=dev).bfloat16().contiguous(
+            memory_format=torch.channels_last).requires_grad_(True)
+        r = torch.randn(16, 128, 8, 8, device=dev).bfloat16().contiguous(
+            memory_format=torch.channels_last).requires_grad_(True)
+        y = bn(x, r, True)
+        y.backward(torch.ones_like(y))
+        grads.append((y.detach().clone(), x.grad.clone(), r.grad.clone(),
+                      bn.weight.grad.clone(), bn.bias.grad.clone()))
+    for a, b in zip(*grads):
+        assert torch.equal(a, b)
+
+
 @pytest.mark.gpu
 def test_fused_bn_resnet_matches_unfused_model():
     """ResNet-18 with the fused BN kernels vs the same model with the fused
@@ -625,12 +658,6 @@ def test_fused_bn_resnet_matches_unfused_model():
 # hardware, so they only run on request (first thing to do next round):
 #   ADAPTDL_B200_TEST_EXPERIMENTAL=1 python -m pytest tests -m gpu -k layer_norm
 # ---------------------------------------------------------------------------
-_EXPERIMENTAL = pytest.mark.skipif(
-    os.environ.get("ADAPTDL_B200_TEST_EXPERIMENTAL") != "1",
-    reason="experimental op, not validated on hardware yet "
-           "(set ADAPTDL_B200_TEST_EXPERIMENTAL=1)")
-
-
 @_EXPERIMENTAL
 @pytest.mark.gpu
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
