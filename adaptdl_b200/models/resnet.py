@@ -10,6 +10,8 @@ names and shapes are those of the plain ``nn.BatchNorm2d`` model, so state
 dicts are interchangeable.
 """
 
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -92,8 +94,25 @@ class ResNet(nn.Module):
             self.in_planes = planes * block.expansion
         return nn.Sequential(*layers)
 
+    def _stem(self, x):
+        # Experimental (ADAPTDL_B200_PAD_STEM=1, not timed on hardware yet):
+        # cuDNN has no tensor-core kernels for 3 input channels; zero-padding
+        # image and filter to 8 channels is the same convolution on the fast
+        # path. The parameter keeps its [64, 3, 3, 3] shape.
+        if x.is_cuda and os.environ.get("ADAPTDL_B200_PAD_STEM", "0") == "1":
+            pad = (-x.shape[1]) % 8
+            w = self.conv1.weight
+            if x.is_contiguous(memory_format=torch.channels_last):
+                x = F.pad(x.permute(0, 2, 3, 1), (0, pad)).permute(0, 3, 1, 2)
+                w = F.pad(w.permute(0, 2, 3, 1), (0, pad)).permute(0, 3, 1, 2)
+            else:
+                x = F.pad(x, (0, 0, 0, 0, 0, pad))
+                w = F.pad(w, (0, 0, 0, 0, 0, pad))
+            return F.conv2d(x, w, None, self.conv1.stride, self.conv1.padding)
+        return self.conv1(x)
+
     def forward(self, x):
-        out = self.bn1(self.conv1(x))
+        out = self.bn1(self._stem(x))
         out = self.layer4(self.layer3(self.layer2(self.layer1(out))))
         out = F.adaptive_avg_pool2d(out, 1)
         return self.linear(torch.flatten(out, 1))
