@@ -75,6 +75,23 @@ class Bottleneck(nn.Module):
         return self.bn3(self.conv3(out), residual=_shortcut(self.shortcut, x))
 
 
+def padded_channels_conv2d(x, conv, multiple=8):
+    """``conv(x)`` computed on input / filter zero-padded to a multiple of
+    ``multiple`` input channels (identical result, tensor-core eligible)."""
+    pad = (-x.shape[1]) % multiple
+    w = conv.weight
+    if pad:
+        if x.is_contiguous(memory_format=torch.channels_last):
+            # channels are the innermost dimension: pad there, keep the format
+            x = F.pad(x.permute(0, 2, 3, 1), (0, pad)).permute(0, 3, 1, 2)
+            w = F.pad(w.permute(0, 2, 3, 1), (0, pad)).permute(0, 3, 1, 2)
+        else:
+            x = F.pad(x, (0, 0, 0, 0, 0, pad))
+            w = F.pad(w, (0, 0, 0, 0, 0, pad))
+    return F.conv2d(x, w, conv.bias, conv.stride, conv.padding,
+                    conv.dilation, conv.groups)
+
+
 class ResNet(nn.Module):
     def __init__(self, block, num_blocks, num_classes=10):
         super().__init__()
@@ -100,15 +117,7 @@ class ResNet(nn.Module):
         # image and filter to 8 channels is the same convolution on the fast
         # path. The parameter keeps its [64, 3, 3, 3] shape.
         if x.is_cuda and os.environ.get("ADAPTDL_B200_PAD_STEM", "0") == "1":
-            pad = (-x.shape[1]) % 8
-            w = self.conv1.weight
-            if x.is_contiguous(memory_format=torch.channels_last):
-                x = F.pad(x.permute(0, 2, 3, 1), (0, pad)).permute(0, 3, 1, 2)
-                w = F.pad(w.permute(0, 2, 3, 1), (0, pad)).permute(0, 3, 1, 2)
-            else:
-                x = F.pad(x, (0, 0, 0, 0, 0, pad))
-                w = F.pad(w, (0, 0, 0, 0, 0, pad))
-            return F.conv2d(x, w, None, self.conv1.stride, self.conv1.padding)
+            return padded_channels_conv2d(x, self.conv1)
         return self.conv1(x)
 
     def forward(self, x):
