@@ -157,3 +157,42 @@ def test_gemm_epilogue_gelu_polynomial_meets_its_error_bound():
     # exact tails: identity for large x, zero for very negative x
     assert np.all(y[xd > 6] == xd[xd > 6])
     assert np.all(y[xd < -6] == 0.0)
+
+
+def test_bn_launch_geometry(monkeypatch):
+    """Host-side launch arithmetic of the fused BN kernels for the layer
+    shapes of the model zoo (no GPU needed: the SM count is injected)."""
+    import importlib
+    bn_act = importlib.import_module("adaptdl_b200.ops.bn_act")
+    dev = torch.device("cuda", 0)
+    monkeypatch.setitem(bn_act._SM, 0, 148)
+    for m, c, vec in ((131072, 64, 8), (32768, 128, 8), (8192, 256, 8),
+                      (2048, 512, 8), (2048, 512, 4), (7, 16, 8),
+                      (100000, 32, 4), (64, 2048, 8)):
+        cb, gy = bn_act._reduce_grid(dev, m, c, vec, 4)
+        assert cb == min(c, 64) and c % cb == 0
+        assert 256 % (cb // vec) == 0           # threads per row divide the CTA
+        assert 1 <= gy and gy * (c // cb) <= 2 * 148 + (c // cb)
+        rows_per_cta_iter = (256 // (cb // vec)) * 4
+        assert gy <= max(1, -(-m // rows_per_cta_iter))    # no idle CTAs
+        ga = bn_act._grid(dev, m, c, vec, 4)
+        assert 1 <= ga <= 8 * 148
+
+
+def test_ln_and_gemm_support_predicates():
+    import importlib
+    layer_norm = importlib.import_module("adaptdl_b200.ops.layer_norm")
+    linear_act = importlib.import_module("adaptdl_b200.ops.linear_act")
+    cpu = torch.randn(4, 768)
+    assert not layer_norm.supported(cpu)        # CPU -> PyTorch composition
+    assert not linear_act.supported(cpu, torch.randn(3072, 768))
+    # shape rules of the GEMM kernel (checked before any device work)
+    class Fake(object):
+        is_cuda = True
+        shape = (16, 768)
+
+        def numel(self):
+            return 16 * 768
+    assert linear_act.supported(Fake(), torch.empty(3072, 768))
+    assert not linear_act.supported(Fake(), torch.empty(3000, 768))   # N % 128
+    assert not linear_act.supported(Fake(), torch.empty(3072, 700))   # K mismatch
