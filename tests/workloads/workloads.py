@@ -195,7 +195,7 @@ def main(argv=None):
         return 0
     if args.verb == "submit":
         cmd = [sys.executable, "-m", "adaptdl_b200.cli", "submit", ROOT,
-               "-d", os.path.join(ROOT, "examples", "Dockerfile"), "-f", "-",
+               "-d", os.path.join(ROOT, "deploy", "docker", "Dockerfile.trainer"), "-f", "-",
                "--checkpoint-storage-size", "1Gi"]
         if args.tensorboard:
             cmd += ["--tensorboard", args.tensorboard]
