@@ -102,7 +102,7 @@ def test_workload_specs_validate():
         script = resource["spec"]["template"]["spec"]["containers"][0][
             "command"][1]
         assert os.path.exists(os.path.join(
-            workloads.ROOT, os.path.relpath(script, "/root"))), script
+            workloads.ROOT, os.path.relpath(script, workloads.IMAGE_ROOT))), script
         job, pvc = manifests.prepare_job(resource, "registry/img@sha256:0",
                                          [], name=name)
         review = {"operation": "CREATE", "namespace": "default",

@@ -30,6 +30,7 @@ import yaml
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(
     os.path.abspath(__file__))))
 API_VERSION = "adaptdl.petuum.com/v1"
+IMAGE_ROOT = "/opt/adaptdl_b200"      # WORKDIR of deploy/docker/Dockerfile.trainer
 
 # name -> (suite, script, args, spec overrides)
 WORKLOADS = {
@@ -86,7 +87,7 @@ WORKLOADS = {
 }
 
 
-def manifest(name, image_root="/root"):
+def manifest(name, image_root=IMAGE_ROOT):
     """The AdaptDLJob object for workload ``name``."""
     suite, script, args, overrides = WORKLOADS[name]
     overrides = copy.deepcopy(overrides)
