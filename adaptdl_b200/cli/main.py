@@ -33,7 +33,10 @@ def _create(obj):
 
 
 def _load_yaml(path):
+    """Job manifest from a file, or from stdin for ``-f -``."""
     import yaml
+    if path == "-":
+        return yaml.safe_load(sys.stdin)
     with open(path) as f:
         return yaml.safe_load(f)
 

@@ -110,3 +110,10 @@ def test_workload_specs_validate():
         response = asyncio.run(validator._validate_create(review))
         assert response["allowed"], (name, response)
         assert os.path.exists(workloads.local_command(name)[0])
+
+
+def test_jobfile_from_stdin(monkeypatch):
+    import io
+    from adaptdl_b200.cli import main as cli
+    monkeypatch.setattr("sys.stdin", io.StringIO("kind: AdaptDLJob\nspec: {}\n"))
+    assert cli._load_yaml("-") == {"kind": "AdaptDLJob", "spec": {}}
