@@ -158,7 +158,8 @@ def tensorboard(args, remaining):
         classes = json.loads(_kubectl("get", "storageclass", "-o",
                                       "json"))["items"]
         sc = manifests.choose_storageclass(classes, args.storage_class)
-        for obj in manifests.tensorboard_manifests(args.name, sc, args.size):
+        for obj in manifests.tensorboard_manifests(args.name, sc, args.size,
+                                                   nodeport=args.nodeport):
             _create(obj)
     elif args.tb_command == "delete":
         full = manifests.TENSORBOARD_PREFIX + args.name
@@ -205,6 +206,8 @@ def build_parser():
     c.add_argument("name")
     c.add_argument("--storage-class")
     c.add_argument("--size", default="1Gi")
+    c.add_argument("--nodeport", action="store_true",
+                   help="expose TensorBoard on a node port")
     for verb in ("delete", "proxy"):
         c = tb.add_parser(verb)
         c.add_argument("name")

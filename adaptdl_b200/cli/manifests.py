@@ -114,8 +114,11 @@ def copy_pod_manifest(pvc_name, uid):
 
 
 def tensorboard_manifests(name, storage_class, size="1Gi",
-                          image="tensorflow/tensorflow:latest"):
-    """Deployment + Service + PVC of a named TensorBoard instance."""
+                          image="tensorflow/tensorflow:latest",
+                          nodeport=False):
+    """Deployment + Service + PVC of a named TensorBoard instance
+    (``nodeport``: expose the service on a node port instead of ClusterIP,
+    reference ``adaptdl tensorboard create --nodeport``)."""
     full = TENSORBOARD_PREFIX + name
     labels = {"app": "adaptdl-tensorboard", "adaptdl/tensorboard": name}
     deployment = {
@@ -138,6 +141,8 @@ def tensorboard_manifests(name, storage_class, size="1Gi",
                "spec": {"selector": labels,
                         "ports": [{"name": "http", "port": 6006,
                                    "targetPort": 6006}]}}
+    if nodeport:
+        service["spec"]["type"] = "NodePort"
     return [pvc_manifest(full, storage_class, size), deployment, service]
 
 
