@@ -51,6 +51,9 @@ def parse_args():
                          "needs torchtext)")
     ap.add_argument("--device", default="cuda")
     ap.add_argument("--reducer", default="auto")
+    ap.add_argument("--bucket-cap-mb", type=float, default=None,
+                    help="own arm: gradient bucket cap (default: the "
+                         "reducer's own, 4 MB for the fused kernels)")
     ap.add_argument("--param-dtype", default="bf16", choices=["bf16", "fp32"],
                     help="own arm: store conv/linear weights in bf16 with "
                          "fp32 masters inside the fused optimizer (default) "
@@ -320,6 +323,8 @@ def build_program(args, adl, device, world, workload):
     kwargs = {}
     if workload.own and args.reducer != "auto":
         kwargs["reducer"] = args.reducer
+    if workload.own and args.bucket_cap_mb:
+        kwargs["bucket_cap_mb"] = args.bucket_cap_mb
     if workload.name == "ncf":
         kwargs["find_unused_parameters"] = True
     net = adl.AdaptiveDataParallel(model, optimizer, scheduler, **kwargs)
