@@ -1,0 +1,93 @@
+"""Model-based replay of the reference's batch-size chart
+(``docs/README.rst:79-80``: ResNet-18 time-to-train at fixed batch sizes
+128 ... 4096 vs AdaptDL's automatic batch size; auto ~ best hand-tuned, ~1.95x
+faster than 128).
+
+Uses this repo's :class:`GoodputFunction` only (no GPU): throughput from a
+performance model, statistical efficiency from a gradient-noise trajectory
+that grows as training converges. For every fixed global batch size the job
+runs at that size from start to finish; "auto" re-optimises the batch size
+(and gradient accumulation) as the noise scale changes, exactly as
+``AdaptiveDataLoader.autoscale_batch_size`` does from its fitted model.
+
+    python tools/autobsz_sim.py --replicas 8 --out profiles/autobsz_sim.json
+"""
+
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from adaptdl_b200.goodput import (GoodputFunction, GradParams,  # noqa: E402
+                                  PerfParams)
+
+
+def time_to_train(perf, init_bsz, target, noise, replicas, nodes, bsz=None,
+                  max_bsz=4096, bounds=(32, 1024), dt_progress=0.002):
+    """Seconds to accumulate ``target`` scale-invariant samples."""
+    t, progress, trace = 0.0, 0.0, []
+    while progress < target:
+        f = progress / target
+        fn = GoodputFunction(perf, noise(f), init_bsz)
+        if bsz is None:
+            goodput, atomic, accum = fn.optimize(nodes, replicas, max_bsz,
+                                                 bounds, accumulation=True)
+            atomic, accum = int(atomic), int(accum)
+        else:
+            atomic = max(bsz // replicas, 1)
+            accum = 0
+            while atomic > bounds[1]:              # needs accumulation
+                accum += 1
+                atomic = max(bsz // (replicas * (accum + 1)), 1)
+            goodput = float(fn.evaluate(nodes, replicas, atomic, accum))
+        step = dt_progress * target
+        t += step / float(goodput)
+        progress += step
+        trace.append(replicas * atomic * (accum + 1))
+    return t, trace
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--replicas", type=int, default=8)
+    ap.add_argument("--nodes", type=int, default=1)
+    ap.add_argument("--epochs", type=float, default=60)
+    ap.add_argument("--out", default=None)
+    args = ap.parse_args()
+    # ResNet-18 / CIFAR on B200: ~1.2 ms fixed + 6.5 us per sample per step
+    # (2.0 ms at 128), intra-node sync ~0.15 ms (profiles/README.md section 1)
+    perf = PerfParams(1.2e-3, 6.5e-6, 2.0e-4, 4.0e-5, 1.5e-4, 3.0e-6, 1.3)
+    init_bsz = 128
+    target = args.epochs * 50000.0
+
+    def noise(f):           # |g|^2 shrinks, variance grows: the noise scale
+        sqr = 0.0014 * (1 - f) + 0.00012 * f        # rises ~25x over training
+        var = 0.0005 * (1 - f) + 0.0012 * f
+        return GradParams(sqr, var)
+    rows = {}
+    for bsz in (128, 256, 512, 1024, 2048, 4096):
+        t, _ = time_to_train(perf, init_bsz, target, noise, args.replicas,
+                             args.nodes, bsz)
+        rows[str(bsz)] = t
+    t_auto, trace = time_to_train(perf, init_bsz, target, noise,
+                                  args.replicas, args.nodes, None)
+    rows["auto"] = t_auto
+    best = min(v for k, v in rows.items() if k != "auto")
+    out = {
+        "replicas": args.replicas, "seconds": rows,
+        "auto_vs_best_fixed": best / t_auto,
+        "auto_vs_128": rows["128"] / t_auto,
+        "auto_batch_size_start_mid_end": [trace[0], trace[len(trace) // 2],
+                                          trace[-1]],
+    }
+    print(json.dumps(out, indent=1))
+    if args.out:
+        with open(args.out, "w") as f:
+            json.dump(out, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
