@@ -1,0 +1,51 @@
+"""Smoke tests of the CPU-only tools (they produce numbers quoted in
+profiles/README.md, so they must keep running)."""
+
+import importlib.util
+import os
+import types
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _load(name):
+    spec = importlib.util.spec_from_file_location(
+        name, os.path.join(ROOT, "tools", name + ".py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_scheduler_simulation_runs_and_conserves_work():
+    sim = _load("sched_sim")
+    args = types.SimpleNamespace(nodes=2, gpus_per_node=4, hours=0.5,
+                                 interval=60.0, pop=12, generations=6)
+    for adaptive, fixed in ((False, None), (False, 4), (True, None)):
+        out = sim.simulate(8.0, args, adaptive, seed=1, static_gpus=fixed)
+        assert out["jobs"] > 0 and out["finished"] == out["jobs"]
+        assert out["avg_jct_hours"] > 0
+        assert out["gpu_hours"] >= out["node_hours"] > 0
+        # nobody can hold more than the cluster has
+        assert out["gpu_hours"] <= 8 * out["makespan_hours"] + 1e-6
+    # same seed, same workload in all arms
+    a = sim.simulate(8.0, args, False, seed=1)
+    b = sim.simulate(8.0, args, True, seed=1)
+    assert a["single_gpu_hours_of_work"] == b["single_gpu_hours_of_work"]
+
+
+def test_auto_batch_size_replay_is_u_shaped():
+    sim = _load("autobsz_sim")
+    from adaptdl_b200.goodput import GradParams, PerfParams
+    perf = PerfParams(1.2e-3, 6.5e-6, 2.0e-4, 4.0e-5, 1.5e-4, 3.0e-6, 1.3)
+
+    def noise(f):
+        return GradParams(0.0014 * (1 - f) + 0.00012 * f,
+                          0.0005 * (1 - f) + 0.0012 * f)
+    times = {b: sim.time_to_train(perf, 128, 3e5, noise, 8, 1, b,
+                                  dt_progress=0.05)[0]
+             for b in (128, 512, 4096)}
+    auto, trace = sim.time_to_train(perf, 128, 3e5, noise, 8, 1, None,
+                                    dt_progress=0.05)
+    assert times[512] < times[128] and times[512] < times[4096]
+    assert auto <= min(times.values()) * 1.01
+    assert trace[-1] > trace[0]          # batch size grows with the noise
