@@ -22,57 +22,61 @@ __all__ = ["ResNet", "resnet18", "resnet34", "resnet50", "resnet101",
            "resnet152"]
 
 
-def _shortcut(seq, x):
-    """identity, or conv1x1 -> bn (no activation)"""
-    if len(seq) == 0:
-        return x
-    return seq[1](seq[0](x), relu=False)
+class ResidualBlock(nn.Module):
+    """One residual unit, plain (two 3x3 convolutions) or bottleneck (1x1,
+    3x3, 1x1 with a 4x wider output). Sub-module names follow the usual
+    CIFAR ResNet checkpoints: ``conv{i}`` / ``bn{i}`` for the main path and
+    ``shortcut.0`` / ``shortcut.1`` for the projection (empty when the
+    input can be added as is).
 
+    Every ``bn -> (+ shortcut) -> relu`` group is one fused op
+    (:class:`BatchNormAct2d`): the last normalisation of the main path takes
+    the shortcut as its residual input."""
 
-class BasicBlock(nn.Module):
-    expansion = 1
-
-    def __init__(self, in_planes, planes, stride=1):
+    def __init__(self, in_planes, planes, stride, bottleneck):
         super().__init__()
-        self.conv1 = nn.Conv2d(in_planes, planes, 3, stride, 1, bias=False)
-        self.bn1 = BatchNormAct2d(planes)
-        self.conv2 = nn.Conv2d(planes, planes, 3, 1, 1, bias=False)
-        self.bn2 = BatchNormAct2d(planes)
+        self.expansion = 4 if bottleneck else 1
+        out_planes = planes * self.expansion
+        # (kernel, in, out, stride) of the main path
+        if bottleneck:
+            plan = [(1, in_planes, planes, 1), (3, planes, planes, stride),
+                    (1, planes, out_planes, 1)]
+        else:
+            plan = [(3, in_planes, planes, stride), (3, planes, planes, 1)]
+        self.depth = len(plan)
+        for i, (k, cin, cout, s) in enumerate(plan, start=1):
+            setattr(self, "conv{}".format(i),
+                    nn.Conv2d(cin, cout, k, s, k // 2, bias=False))
+            setattr(self, "bn{}".format(i), BatchNormAct2d(cout))
         self.shortcut = nn.Sequential()
-        if stride != 1 or in_planes != self.expansion * planes:
+        if stride != 1 or in_planes != out_planes:
             self.shortcut = nn.Sequential(
-                nn.Conv2d(in_planes, self.expansion * planes, 1, stride,
-                          bias=False),
-                BatchNormAct2d(self.expansion * planes))
+                nn.Conv2d(in_planes, out_planes, 1, stride, bias=False),
+                BatchNormAct2d(out_planes))
 
     def forward(self, x):
-        out = self.bn1(self.conv1(x))
-        return self.bn2(self.conv2(out), residual=_shortcut(self.shortcut, x))
+        skip = x
+        if len(self.shortcut):                   # 1x1 projection, no ReLU
+            skip = self.shortcut[1](self.shortcut[0](x), relu=False)
+        out = x
+        for i in range(1, self.depth + 1):
+            conv = getattr(self, "conv{}".format(i))
+            norm = getattr(self, "bn{}".format(i))
+            last = i == self.depth
+            out = norm(conv(out), residual=skip if last else None)
+        return out
 
 
-class Bottleneck(nn.Module):
-    expansion = 4
+def BasicBlock(in_planes, planes, stride=1):
+    return ResidualBlock(in_planes, planes, stride, bottleneck=False)
 
-    def __init__(self, in_planes, planes, stride=1):
-        super().__init__()
-        self.conv1 = nn.Conv2d(in_planes, planes, 1, bias=False)
-        self.bn1 = BatchNormAct2d(planes)
-        self.conv2 = nn.Conv2d(planes, planes, 3, stride, 1, bias=False)
-        self.bn2 = BatchNormAct2d(planes)
-        self.conv3 = nn.Conv2d(planes, self.expansion * planes, 1,
-                               bias=False)
-        self.bn3 = BatchNormAct2d(self.expansion * planes)
-        self.shortcut = nn.Sequential()
-        if stride != 1 or in_planes != self.expansion * planes:
-            self.shortcut = nn.Sequential(
-                nn.Conv2d(in_planes, self.expansion * planes, 1, stride,
-                          bias=False),
-                BatchNormAct2d(self.expansion * planes))
 
-    def forward(self, x):
-        out = self.bn1(self.conv1(x))
-        out = self.bn2(self.conv2(out))
-        return self.bn3(self.conv3(out), residual=_shortcut(self.shortcut, x))
+def Bottleneck(in_planes, planes, stride=1):
+    return ResidualBlock(in_planes, planes, stride, bottleneck=True)
+
+
+BasicBlock.expansion = 1
+Bottleneck.expansion = 4
 
 
 def padded_channels_conv2d(x, conv, multiple=8):
@@ -93,23 +97,26 @@ def padded_channels_conv2d(x, conv, multiple=8):
 
 
 class ResNet(nn.Module):
+    """Stem (3x3, 64 channels) -> four stages of residual units at widths
+    64 / 128 / 256 / 512 (the first unit of stages 2-4 halves the
+    resolution) -> global average pool -> linear classifier."""
+
+    WIDTHS = (64, 128, 256, 512)
+
     def __init__(self, block, num_blocks, num_classes=10):
         super().__init__()
-        self.in_planes = 64
         self.conv1 = nn.Conv2d(3, 64, 3, 1, 1, bias=False)
         self.bn1 = BatchNormAct2d(64)
-        self.layer1 = self._make_layer(block, 64, num_blocks[0], 1)
-        self.layer2 = self._make_layer(block, 128, num_blocks[1], 2)
-        self.layer3 = self._make_layer(block, 256, num_blocks[2], 2)
-        self.layer4 = self._make_layer(block, 512, num_blocks[3], 2)
-        self.linear = nn.Linear(512 * block.expansion, num_classes)
-
-    def _make_layer(self, block, planes, count, stride):
-        layers = []
-        for s in [stride] + [1] * (count - 1):
-            layers.append(block(self.in_planes, planes, s))
-            self.in_planes = planes * block.expansion
-        return nn.Sequential(*layers)
+        channels = 64
+        for stage, (width, count) in enumerate(zip(self.WIDTHS, num_blocks),
+                                               start=1):
+            units = []
+            for unit in range(count):
+                stride = 2 if (unit == 0 and stage > 1) else 1
+                units.append(block(channels, width, stride))
+                channels = width * block.expansion
+            setattr(self, "layer{}".format(stage), nn.Sequential(*units))
+        self.linear = nn.Linear(channels, num_classes)
 
     def _stem(self, x):
         # Experimental (ADAPTDL_B200_PAD_STEM=1, not timed on hardware yet):
@@ -122,7 +129,8 @@ class ResNet(nn.Module):
 
     def forward(self, x):
         out = self.bn1(self._stem(x))
-        out = self.layer4(self.layer3(self.layer2(self.layer1(out))))
+        for stage in (self.layer1, self.layer2, self.layer3, self.layer4):
+            out = stage(out)
         out = F.adaptive_avg_pool2d(out, 1)
         return self.linear(torch.flatten(out, 1))
 
