@@ -1,21 +1,32 @@
 """Step profiler, performance-model fitting and scheduler hints.
 
-The profile is a table keyed by ``(num_nodes, num_replicas, atomic_bsz)`` with
-counters ``accum_step_time / accum_count / optim_step_time / optim_sync_time /
-optim_count`` (parity: reference ``torch/_metrics.py:29-199``). It survives
-restarts (so measurements at several replica counts accumulate) and feeds
-:func:`adaptdl_b200.goodput.fit_perf_params`.
+Three small pieces:
 
-B200 difference: step and sync durations may be supplied by the on-device
-timer (``%globaltimer`` stamps written by the fused reducer; see
-``parallel/reducer_cuda.py``) through :func:`profile_step_commit`'s
-``step_time`` argument instead of host wall-clock, which removes the
-blocking ``event.synchronize()`` the reference needs every step.
+``_MetricsState``
+    the checkpointed record: a profile table keyed by ``(num_nodes,
+    num_replicas, atomic_bsz)`` whose rows count ``accum_step_time /
+    accum_count / optim_step_time / optim_sync_time / optim_count``, the
+    fitted performance parameters, the latest gradient statistics, the batch
+    size configuration and the job's scale-invariant progress. It survives
+    restarts, so measurements taken at different replica counts accumulate
+    (on-disk layout: Appendix B of SURVEY.md, eight consecutive pickles).
+``_OpenStep``
+    the measurements of the iteration in flight (not checkpointed).
+module functions
+    the semi-public API the data loader, the data-parallel wrapper and the
+    Ray integration call (same names as the reference's
+    ``torch/_metrics.py:29-199``).
+
+B200 difference: step and sync durations may come from the on-device timer
+(``%globaltimer`` stamps written by the fused reducer, see
+``parallel/reducer_cuda.py``) via ``profile_step_commit(step_time=...)``
+instead of the host clock, which removes the blocking event synchronisation
+the reference pays every step.
 """
 
 import collections
-import pickle
 import os
+import pickle
 import time
 
 import numpy as np
@@ -31,33 +42,43 @@ REPORT_PERIOD_S = float(os.environ.get("ADAPTDL_REPORT_PERIOD", "30"))
 
 
 class _MetricsState(checkpoint.State):
+    # attribute -> default; also the order of the pickles on disk
+    _LAYOUT = (("profile", None), ("perf_params", None),
+               ("grad_params", None), ("init_batch_size", None),
+               ("max_batch_size", None), ("local_bsz_bounds", None),
+               ("gradient_accumulation", False), ("progress", 0.0))
+
     def __init__(self):
         super().__init__("adaptdl-metrics")
+        for name, default in self._LAYOUT:
+            setattr(self, name, default)
         self.profile = collections.defaultdict(collections.Counter)
-        self.perf_params = None
-        self.grad_params = None
-        self.init_batch_size = None
-        self.max_batch_size = None
-        self.local_bsz_bounds = None
-        self.gradient_accumulation = False
-        self.progress = 0.0      # scale-invariant iterations completed
 
-    _FIELDS = ("profile", "perf_params", "grad_params", "init_batch_size",
-               "max_batch_size", "local_bsz_bounds", "gradient_accumulation",
-               "progress")
-
-    def save(self, fileobj):     # 8 consecutive pickles (App. B)
-        for name in self._FIELDS:
+    def save(self, fileobj):
+        for name, _ in self._LAYOUT:
             pickle.dump(getattr(self, name), fileobj)
 
     def load(self, fileobj):
-        for name in self._FIELDS:
+        for name, _ in self._LAYOUT:
             setattr(self, name, pickle.load(fileobj))
 
 
-_METRICS_STATE = None
-_PREV_REPORT = None
-_GRAD_PARAM_DICT = {}
+class _OpenStep(object):
+    """Clock and counters of the iteration between ``profile_step_start``
+    and ``profile_step_commit``."""
+
+    __slots__ = ("atomic_bsz", "began", "sync_time")
+
+    def __init__(self, atomic_bsz):
+        self.atomic_bsz = atomic_bsz
+        self.began = time.time()
+        self.sync_time = 0.0
+
+
+_METRICS_STATE = None        # the singleton record (lazily loaded)
+_OPEN_STEP = None            # iteration in flight
+_PREV_REPORT = None          # host time of the last hints report
+_GRAD_PARAM_DICT = {}        # data-parallel instance -> (sqr, var)
 
 
 def _metrics_state():
@@ -68,52 +89,63 @@ def _metrics_state():
     return _METRICS_STATE
 
 
+# ---------------------------------------------------------------------------
+# profiling one iteration
+# ---------------------------------------------------------------------------
+
 def profile_step_start(atomic_bsz):
-    state = _metrics_state()
-    state.atomic_bsz = atomic_bsz
-    state.step_start = time.time()
-    state.sync_time = 0.0
+    global _OPEN_STEP
+    _metrics_state()                       # make sure the record exists
+    _OPEN_STEP = _OpenStep(atomic_bsz)
 
 
 def profile_sync_time(sync_time):
-    _metrics_state().sync_time += sync_time
+    _OPEN_STEP.sync_time += sync_time
 
 
 def profile_step_commit(accumulation_step=False, step_time=None):
-    """Commit the measurements of the step opened by
-    :func:`profile_step_start`. ``step_time`` overrides the host wall-clock
-    (device-timed steps)."""
-    global _PREV_REPORT
-    state = _metrics_state()
-    if step_time is None:
-        step_time = time.time() - state.step_start
-    key = (env.num_nodes(), env.num_replicas(), state.atomic_bsz)
-    row = state.profile[key]
+    """Book the iteration opened by :func:`profile_step_start` into the
+    profile. ``step_time`` (seconds) replaces the host wall-clock for
+    device-timed steps. Rank 0 re-fits the performance model and reports
+    scheduling hints every ``REPORT_PERIOD_S`` seconds."""
+    global _OPEN_STEP
+    step, _OPEN_STEP = _OPEN_STEP, None
+    elapsed = (time.time() - step.began) if step_time is None else step_time
+    row = _metrics_state().profile[
+        (env.num_nodes(), env.num_replicas(), step.atomic_bsz)]
+    kind = "accum" if accumulation_step else "optim"
+    row[kind + "_step_time"] += elapsed
+    row[kind + "_count"] += 1
     if accumulation_step:
-        row["accum_step_time"] += step_time
-        row["accum_count"] += 1
-    else:
-        row["optim_step_time"] += step_time
-        row["optim_sync_time"] += state.sync_time
-        row["optim_count"] += 1
-    del state.atomic_bsz, state.step_start, state.sync_time
-    if not accumulation_step:
-        now = time.time()
-        if _PREV_REPORT is None:
-            _PREV_REPORT = now
-        if env.replica_rank() == 0 and now - _PREV_REPORT > REPORT_PERIOD_S:
-            _fit_perf_params()
-            _report_sched_hints()
-            _PREV_REPORT = time.time()
+        return
+    row["optim_sync_time"] += step.sync_time
+    _maybe_report()
 
+
+def _maybe_report():
+    global _PREV_REPORT
+    now = time.time()
+    if _PREV_REPORT is None:
+        _PREV_REPORT = now
+    due = now - _PREV_REPORT > REPORT_PERIOD_S
+    if due and env.replica_rank() == 0:
+        _fit_perf_params()
+        _report_sched_hints()
+        _PREV_REPORT = time.time()
+
+
+# ---------------------------------------------------------------------------
+# statistics and configuration pushed in by the trainer
+# ---------------------------------------------------------------------------
 
 def update_grad_params(edp_key, grad_norm_sqr, grad_variance):
-    """Record one data-parallel instance's (sqr, var); instances are summed
-    (e.g. GAN generator + discriminator)."""
-    _GRAD_PARAM_DICT[edp_key] = np.asarray([grad_norm_sqr, grad_variance],
-                                           dtype=float)
-    total = sum(_GRAD_PARAM_DICT.values())
-    _metrics_state().grad_params = (float(total[0]), float(total[1]))
+    """Latest ``(|g|^2, variance)`` of one data-parallel instance. A job may
+    hold several (GAN generator + discriminator): the job-level statistic is
+    their sum."""
+    _GRAD_PARAM_DICT[edp_key] = (float(grad_norm_sqr), float(grad_variance))
+    sqr = sum(pair[0] for pair in _GRAD_PARAM_DICT.values())
+    var = sum(pair[1] for pair in _GRAD_PARAM_DICT.values())
+    _metrics_state().grad_params = (sqr, var)
 
 
 def update_progress(progress):
@@ -126,73 +158,77 @@ def get_progress():
 
 def set_batch_size(init_batch_size, max_batch_size, local_bsz_bounds,
                    gradient_accumulation):
-    state = _metrics_state()
-    state.init_batch_size = init_batch_size
-    state.max_batch_size = max_batch_size
-    state.local_bsz_bounds = local_bsz_bounds
-    state.gradient_accumulation = gradient_accumulation
+    record = _metrics_state()
+    record.init_batch_size, record.max_batch_size = \
+        init_batch_size, max_batch_size
+    record.local_bsz_bounds = local_bsz_bounds
+    record.gradient_accumulation = gradient_accumulation
 
 
 def get_goodput_fn():
-    state = _metrics_state()
-    if state.grad_params is None or state.perf_params is None:
+    """The job's current goodput model, or ``None`` until both a performance
+    fit and gradient statistics exist."""
+    record = _metrics_state()
+    if record.perf_params is None or record.grad_params is None:
         return None
-    return GoodputFunction(state.perf_params, state.grad_params,
-                           state.init_batch_size)
+    return GoodputFunction(record.perf_params, record.grad_params,
+                           record.init_batch_size)
 
+
+# ---------------------------------------------------------------------------
+# performance fit and scheduler hints
+# ---------------------------------------------------------------------------
 
 def _fit_perf_params():
-    state = _metrics_state()
-    profile = {k: v for k, v in state.profile.items() if v.get("optim_count")}
-    if not profile:
+    """Turn the profile table into per-configuration mean step times and fit
+    the throughput model to them."""
+    record = _metrics_state()
+    table = [(key, row) for key, row in record.profile.items()
+             if row.get("optim_count")]
+    if not table:
         return
-    num_nodes, num_replicas, atomic_bsz = (
-        np.array(col) for col in zip(*profile.keys()))
-    rows = list(profile.values())
+    nodes, replicas, atomic = (np.array(col) for col in
+                               zip(*(key for key, _ in table)))
 
-    def column(name, dtype=float):
-        return np.array([row.get(name, 0) for row in rows], dtype=dtype)
-
-    accum_step_time = column("accum_step_time")
-    accum_count = column("accum_count")
-    optim_step_time = column("optim_step_time")
-    optim_sync_time = column("optim_sync_time")
-    optim_count = column("optim_count")
-    assert np.all(optim_count > 0)
-    # the model requires step time >= sync time (device-timed sync can
-    # exceed a wall-clock step by jitter; clamp instead of asserting)
-    optim_sync_time = np.minimum(optim_sync_time, optim_step_time)
-    # The non-sync part of an optimisation step costs about as much as an
-    # accumulation step; pool the two kinds of sample.
-    accum_step_time = (accum_step_time + optim_step_time - optim_sync_time) \
-        / (accum_count + optim_count)
-    optim_step_time = optim_step_time / optim_count
-    state.perf_params = fit_perf_params(num_nodes, num_replicas, atomic_bsz,
-                                        accum_step_time, optim_step_time)
+    def col(name):
+        return np.array([row.get(name, 0) for _, row in table], dtype=float)
+    optim_total, optim_n = col("optim_step_time"), col("optim_count")
+    accum_total, accum_n = col("accum_step_time"), col("accum_count")
+    # device-timed sync can exceed a wall-clock step by jitter: clamp (the
+    # model needs step >= sync)
+    sync_total = np.minimum(col("optim_sync_time"), optim_total)
+    # an optimisation step minus its synchronisation costs about what an
+    # accumulation step costs: pool both kinds of sample for the local time
+    local_mean = (accum_total + optim_total - sync_total) / (accum_n + optim_n)
+    record.perf_params = fit_perf_params(nodes, replicas, atomic, local_mean,
+                                         optim_total / optim_n)
 
 
 def _get_sched_hints():
-    state = _metrics_state()
-    if len(state.profile) == 0:
+    """(Ray integration) the record with a fresh fit, or ``None`` before the
+    first committed step."""
+    record = _metrics_state()
+    if not record.profile:
         return None
     _fit_perf_params()
-    return _metrics_state()
+    return record
 
 
 def _build_sched_hints():
-    state = _metrics_state()
+    record = _metrics_state()
     hints = dict(SCHED_HINTS)
-    if state.perf_params is not None:
-        hints["perfParams"] = {k: float(v) for k, v in
-                               zip(PERF_PARAMS.keys(), state.perf_params)}
-    hints["maxBatchSize"] = state.max_batch_size
-    hints["localBszBounds"] = state.local_bsz_bounds
-    hints["initBatchSize"] = state.init_batch_size
-    if state.grad_params:
-        hints["gradParams"] = {"norm": float(state.grad_params[0]),
-                               "var": float(state.grad_params[1])}
-    hints["maxProfiledReplicas"] = max(key[1] for key in state.profile)
-    hints["gradientAccumulation"] = state.gradient_accumulation
+    hints.update(
+        initBatchSize=record.init_batch_size,
+        maxBatchSize=record.max_batch_size,
+        localBszBounds=record.local_bsz_bounds,
+        gradientAccumulation=record.gradient_accumulation,
+        maxProfiledReplicas=max(key[1] for key in record.profile))
+    if record.perf_params is not None:
+        hints["perfParams"] = dict(zip(
+            PERF_PARAMS.keys(), (float(v) for v in record.perf_params)))
+    if record.grad_params:
+        sqr, var = record.grad_params
+        hints["gradParams"] = {"norm": float(sqr), "var": float(var)}
     return hints
 
 
@@ -202,7 +238,6 @@ def _report_sched_hints():
 
 
 def _reset_for_tests():
-    global _METRICS_STATE, _PREV_REPORT
-    _METRICS_STATE = None
-    _PREV_REPORT = None
+    global _METRICS_STATE, _OPEN_STEP, _PREV_REPORT
+    _METRICS_STATE = _OPEN_STEP = _PREV_REPORT = None
     _GRAD_PARAM_DICT.clear()
