@@ -153,57 +153,37 @@ class AdaptiveDataLoaderHelper(object):
         self._accum_count = 0
         self._step_time_source = None   # optional device-side step timer
 
-    # -- positions -----------------------------------------------------
+    # -- positions and batch sizes (views of the checkpointed record) ------
 
-    @property
-    def current_index(self):
-        """Samples processed so far in the current loop by all replicas
-        (``None`` unless this loader is being iterated)."""
-        if AdaptiveDataLoaderHelper._current is not self:
-            return None
-        return self._state.current_index
+    def _is_current(self):
+        return AdaptiveDataLoaderHelper._current is self
 
-    @current_index.setter
-    def current_index(self, index):
-        if AdaptiveDataLoaderHelper._current is not self:
-            return
-        self._state.current_index = index
-
-    @property
-    def end_index(self):
-        return self._state.end_index
-
-    @end_index.setter
-    def end_index(self, index):
-        self._state.end_index = index
-
-    # -- batch size ----------------------------------------------------
-
-    @property
-    def max_batch_size(self):
-        """Upper bound of the adaptive global batch size (``None`` when
-        adaptive batch size is off)."""
-        return self._max_batch_size
-
-    @property
-    def local_bsz_bounds(self):
-        """``(min_local_bsz, max_local_bsz)`` per replica."""
-        return self._local_bsz_bounds
-
-    @property
-    def current_local_bsz(self):
-        """Per-replica micro-batch size currently in use."""
-        return self._state.current_local_bsz
-
-    @property
-    def accumulation_steps(self):
-        """Extra micro-batches accumulated before each optimizer step."""
-        return self._state.accumulation_steps
+    #: samples consumed so far in the running loop, over all replicas; reads
+    #: as ``None`` and ignores writes unless THIS loader is being iterated
+    current_index = property(
+        lambda self: self._state.current_index if self._is_current()
+        else None,
+        lambda self, value: setattr(self._state, "current_index", value)
+        if self._is_current() else None)
+    #: free slot for custom loaders (e.g. the end of a BPTT stream)
+    end_index = property(
+        lambda self: self._state.end_index,
+        lambda self, value: setattr(self._state, "end_index", value))
+    #: largest adaptive global batch size, ``None`` while adaptation is off
+    max_batch_size = property(lambda self: self._max_batch_size)
+    #: ``(min, max)`` micro-batch size per replica
+    local_bsz_bounds = property(lambda self: self._local_bsz_bounds)
+    #: micro-batch size per replica in use
+    current_local_bsz = property(lambda self: self._state.current_local_bsz)
+    #: additional micro-batches accumulated into every optimizer step
+    accumulation_steps = property(
+        lambda self: self._state.accumulation_steps)
 
     @property
     def current_batch_size(self):
-        return (self.current_local_bsz * (self.accumulation_steps + 1)
-                * env.num_replicas())
+        """Samples per optimizer step over the whole job."""
+        micro_steps = self.accumulation_steps + 1
+        return env.num_replicas() * micro_steps * self.current_local_bsz
 
     def is_accum_step(self):
         """This step's gradient is only accumulated (no sync, no update)."""
@@ -318,19 +298,22 @@ class AdaptiveDataLoaderHelper(object):
     @contextmanager
     def context(self):
         """Wrap a whole loader iteration (one ``for batch in loader``)."""
+        cls = AdaptiveDataLoaderHelper
+        if cls._current is not None:
+            raise RuntimeError("a data loader is already being iterated: "
+                               "loops over adaptive loaders cannot nest")
         epoch = current_epoch()
+        cls._current = self
         try:
-            if AdaptiveDataLoaderHelper._current is not None:
-                raise RuntimeError("overlapping dataloader iterations "
-                                   "detected")
-            AdaptiveDataLoaderHelper._current = self
             yield
         finally:
-            self._state.current_index = 0
-            self._state.end_index = 0
-            self._state.last_position[epoch] = self._position[epoch]
-            self._position[epoch] += 1
-            AdaptiveDataLoaderHelper._current = None
+            # the loop (finished or abandoned) is over: rewind, and remember
+            # its position so that a restarted job can skip it
+            record = self._state
+            record.current_index = record.end_index = 0
+            record.last_position[epoch] = cls._position[epoch]
+            cls._position[epoch] += 1
+            cls._current = None
 
     def skipdone(self):
         """Call right after entering :meth:`context`: True if this loop had
@@ -346,14 +329,11 @@ class AdaptiveDataLoaderHelper(object):
 
     def to_tensorboard(self, writer, global_step, tag_prefix=""):
         """Write batch-size metrics to a TensorBoard ``SummaryWriter``."""
-        if tag_prefix and not tag_prefix.endswith("/"):
-            tag_prefix += "/"
-        writer.add_scalar(tag_prefix + "Total_Batch_Size",
-                          self.current_batch_size, global_step)
-        writer.add_scalar(tag_prefix + "Local_Batch_Size",
-                          self.current_local_bsz, global_step)
-        writer.add_scalar(tag_prefix + "Accumulation_Steps",
-                          self.accumulation_steps, global_step)
+        prefix = tag_prefix.rstrip("/") + "/" if tag_prefix else ""
+        for tag, value in (("Total_Batch_Size", self.current_batch_size),
+                           ("Local_Batch_Size", self.current_local_bsz),
+                           ("Accumulation_Steps", self.accumulation_steps)):
+            writer.add_scalar(prefix + tag, value, global_step)
 
 
 class AdaptiveDataLoaderMixin(object):
@@ -364,35 +344,36 @@ class AdaptiveDataLoaderMixin(object):
     def __init__(self, batch_size):
         self._elastic = AdaptiveDataLoaderHelper(batch_size)
 
-    def autoscale_batch_size(self, max_batch_size, local_bsz_bounds=None,
-                             gradient_accumulation=False):
-        self._elastic.autoscale_batch_size(max_batch_size, local_bsz_bounds,
-                                           gradient_accumulation)
-    autoscale_batch_size.__doc__ = \
-        AdaptiveDataLoaderHelper.autoscale_batch_size.__doc__
-
     def _iterating(self):
-        return AdaptiveDataLoaderHelper._current is self._elastic
+        return self._elastic._is_current()
 
-    @property
-    def current_local_bsz(self):
-        return self._elastic.current_local_bsz if self._iterating() else None
 
-    @property
-    def accumulation_steps(self):
-        return self._elastic.accumulation_steps
+def _forward_to_helper(cls):
+    """Re-export the helper's user-facing methods and read-only views on the
+    mix-in; the batch sizes only mean something while the loader runs."""
+    def method(name):
+        def call(self, *args, **kwargs):
+            return getattr(self._elastic, name)(*args, **kwargs)
+        call.__name__ = name
+        call.__doc__ = getattr(AdaptiveDataLoaderHelper, name).__doc__
+        return call
 
-    @property
-    def training(self):
-        return self._elastic.training
+    def view(name, only_while_iterating):
+        def read(self):
+            if only_while_iterating and not self._iterating():
+                return None
+            return getattr(self._elastic, name)
+        return property(read)
+    for name in ("autoscale_batch_size", "to_tensorboard"):
+        setattr(cls, name, method(name))
+    for name, gated in (("current_local_bsz", True),
+                        ("current_batch_size", True),
+                        ("accumulation_steps", False), ("training", False)):
+        setattr(cls, name, view(name, gated))
+    return cls
 
-    @property
-    def current_batch_size(self):
-        return self._elastic.current_batch_size if self._iterating() else None
 
-    def to_tensorboard(self, writer, global_step, tag_prefix=""):
-        self._elastic.to_tensorboard(writer, global_step, tag_prefix)
-    to_tensorboard.__doc__ = AdaptiveDataLoaderHelper.to_tensorboard.__doc__
+_forward_to_helper(AdaptiveDataLoaderMixin)
 
 
 def _worker_init_wrapper(worker_init_fn, num_workers):
