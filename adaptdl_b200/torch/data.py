@@ -16,7 +16,6 @@ semantics and checkpoint format). B200 additions: :class:`DevicePrefetcher`
 """
 
 import collections
-import functools
 import logging
 import math
 import pickle
@@ -320,12 +319,13 @@ class AdaptiveDataLoaderHelper(object):
         already completed before the last restart (and must be skipped)."""
         epoch = current_epoch()
         position = self._position[epoch]
-        if position <= self._state.last_position.get(epoch, -1):
-            LOG.info("skipping %s loop at position %s in epoch %s",
-                     self.__class__.__name__, position, epoch)
-            self._position[epoch] += 1
-            return True
-        return False
+        finished_before = self._state.last_position.get(epoch, -1)
+        if position > finished_before:
+            return False
+        LOG.info("epoch %s: loop #%s of %s completed before the restart, "
+                 "skipping it", epoch, position, type(self).__name__)
+        self._position[epoch] += 1
+        return True
 
     def to_tensorboard(self, writer, global_step, tag_prefix=""):
         """Write batch-size metrics to a TensorBoard ``SummaryWriter``."""
@@ -376,19 +376,23 @@ def _forward_to_helper(cls):
 _forward_to_helper(AdaptiveDataLoaderMixin)
 
 
-def _worker_init_wrapper(worker_init_fn, num_workers):
-    """Give every (replica, worker) pair distinct python/numpy/torch seeds."""
-    workers = num_workers or 1
+class _SeededWorkerInit(object):
+    """``worker_init_fn`` that first gives the (replica, worker) pair its own
+    python / numpy / torch seed -- torch's per-worker base seed is the same
+    on every replica -- and then runs the user's function, if any. A class
+    (not a closure) so that it pickles for spawn-based workers."""
 
-    @functools.wraps(worker_init_fn)
-    def wrapper(worker_id):
-        seed = torch.initial_seed() + env.replica_rank() * workers
-        torch.manual_seed(seed)
-        np.random.seed(seed % 2 ** 32)
+    def __init__(self, user_fn, num_workers):
+        self.user_fn = user_fn
+        self.stride = max(int(num_workers or 0), 1)
+
+    def __call__(self, worker_id):
+        seed = env.replica_rank() * self.stride + torch.initial_seed()
         random.seed(seed)
-        if worker_init_fn is not None:
-            return worker_init_fn(worker_id)
-    return wrapper
+        np.random.seed(seed % (1 << 32))
+        torch.manual_seed(seed)
+        if self.user_fn is not None:
+            return self.user_fn(worker_id)
 
 
 class AdaptiveDataLoader(DataLoader, AdaptiveDataLoaderMixin):
@@ -407,14 +411,19 @@ class AdaptiveDataLoader(DataLoader, AdaptiveDataLoaderMixin):
     """
 
     def __init__(self, dataset, batch_size=1, shuffle=False, **kwargs):
-        if kwargs.get("batch_sampler") is not None \
-                or kwargs.get("sampler") is not None:
-            raise ValueError("AdaptiveDataLoader does not support "
-                             "custom 'sampler' or 'batch_sampler'")
-        kwargs["sampler"] = ElasticSampler(dataset, shuffle=shuffle)
-        kwargs["worker_init_fn"] = _worker_init_wrapper(
-            kwargs.get("worker_init_fn"), kwargs.get("num_workers"))
-        super().__init__(dataset, batch_size, shuffle=False, **kwargs)
+        for reserved in ("sampler", "batch_sampler"):
+            if kwargs.get(reserved) is not None:
+                raise ValueError(
+                    "{!r} cannot be passed to AdaptiveDataLoader: it "
+                    "partitions and re-partitions the dataset across "
+                    "replicas with its own ElasticSampler".format(reserved))
+        loader_kwargs = dict(
+            kwargs, sampler=ElasticSampler(dataset, shuffle=shuffle),
+            worker_init_fn=_SeededWorkerInit(kwargs.get("worker_init_fn"),
+                                             kwargs.get("num_workers")))
+        # the sampler shuffles; DataLoader itself must not
+        DataLoader.__init__(self, dataset, batch_size, shuffle=False,
+                            **loader_kwargs)
         AdaptiveDataLoaderMixin.__init__(self, batch_size)
 
     def _set_local_batch_size(self, local_bsz):
