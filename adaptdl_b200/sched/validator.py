@@ -1,16 +1,24 @@
 """Admission webhook for AdaptDLJob objects.
 
-``POST /validate`` receives an ``AdmissionReview``: on CREATE the pod
-template is dry-run-created against the API server and
-``maxReplicas >= minReplicas`` is enforced; on UPDATE any change of
-``spec`` is refused (jobs are immutable; the scheduler only writes
-``status``). Parity: reference ``sched/adaptdl_sched/validator.py:30-134``.
+Kubernetes sends every CREATE / UPDATE of an AdaptDLJob to ``POST /validate``
+as an ``AdmissionReview`` and acts on the verdict:
+
+* CREATE -- the job's pod template must be something the API server would
+  accept (checked with a dry-run pod creation, so image pull secrets, volume
+  references, resource syntax, ... fail at submission time instead of when
+  the scheduler first starts the job), and ``maxReplicas`` must not be
+  smaller than ``minReplicas``;
+* UPDATE -- a job's ``spec`` is immutable; only ``status`` (written by the
+  scheduler) and metadata may change.
+
+The rules are plain functions (:func:`verdict_for_create`,
+:func:`verdict_for_update`) wrapped by a small aiohttp application
+(capabilities of the reference's ``sched/adaptdl_sched/validator.py:30-134``).
 """
 
 import argparse
 import logging
 import ssl
-import sys
 from http import HTTPStatus
 
 from aiohttp import web
@@ -19,22 +27,57 @@ from adaptdl_b200.sched.kube import ApiError
 
 LOG = logging.getLogger(__name__)
 
+ALLOW = {"allowed": True}
 
-def _deny(reason, message):
-    return {"allowed": False,
-            "status": {"code": int(HTTPStatus.UNPROCESSABLE_ENTITY),
-                       "reason": reason, "message": message}}
+
+def refuse(reason, message):
+    """An admission response that rejects the request (HTTP 422)."""
+    status = {"code": HTTPStatus.UNPROCESSABLE_ENTITY.value,
+              "reason": reason, "message": message}
+    return {"allowed": False, "status": status}
+
+
+def pod_of_template(job):
+    """A stand-alone Pod object made from the job's pod template."""
+    template = job["spec"].get("template") or {}
+    metadata = dict(template.get("metadata") or {})
+    metadata["name"] = "spec.template"       # shows up in API error messages
+    return {"apiVersion": "v1", "kind": "Pod", "metadata": metadata,
+            "spec": template.get("spec") or {}}
+
+
+async def verdict_for_create(cluster, namespace, job):
+    try:
+        await cluster.create_pod(namespace, pod_of_template(job),
+                                 dry_run=True)
+    except ApiError as exc:
+        return refuse("Invalid", str(exc))
+    spec = job["spec"]
+    lowest = spec.get("minReplicas", 0)
+    highest = spec.get("maxReplicas")
+    if highest is not None and highest < lowest:
+        return refuse("Invalid", "spec.maxReplicas ({}) is smaller than "
+                                 "spec.minReplicas ({})".format(highest,
+                                                                lowest))
+    return dict(ALLOW)
+
+
+def verdict_for_update(old_job, new_job):
+    if old_job["spec"] == new_job["spec"]:
+        return dict(ALLOW)
+    return refuse("Forbidden", "the spec of an AdaptDLJob cannot be changed "
+                               "after creation")
 
 
 class Validator(object):
+    """The webhook server. ``cluster`` is a :mod:`adaptdl_b200.sched.kube`
+    backend (only ``create_pod(..., dry_run=True)`` is used)."""
 
     def __init__(self, cluster):
         self._cluster = cluster
         self._app = web.Application()
-        self._app.add_routes([
-            web.get("/healthz", self._handle_healthz),
-            web.post("/validate", self._handle_validate),
-        ])
+        self._app.router.add_get("/healthz", self._healthz)
+        self._app.router.add_post("/validate", self._validate)
 
     def get_app(self):
         return self._app
@@ -42,63 +85,47 @@ class Validator(object):
     def run(self, host, port, ssl_context=None):
         web.run_app(self._app, host=host, port=port, ssl_context=ssl_context)
 
-    async def _handle_healthz(self, request):
-        return web.Response()
-
-    async def _handle_validate(self, request):
-        review = (await request.json())["request"]
-        operation = review["operation"]
-        if operation == "CREATE":
-            response = await self._validate_create(review)
-        elif operation == "UPDATE":
-            response = self._validate_update(review)
-        else:
-            response = {"allowed": True}
-        LOG.info("%s %s/%s: %s", operation, review.get("namespace"),
-                 review.get("name", "<none>"), response)
-        response["uid"] = review["uid"]
-        return web.json_response({"apiVersion": "admission.k8s.io/v1",
-                                  "kind": "AdmissionReview",
-                                  "response": response})
-
+    # kept as methods: tests and the CLI's manifest check call them directly
     async def _validate_create(self, review):
-        job = review["object"]
-        template = job["spec"].get("template") or {}
-        pod = {"apiVersion": "v1", "kind": "Pod",
-               "metadata": dict(template.get("metadata") or {},
-                                name="spec.template"),
-               "spec": template.get("spec") or {}}
-        try:
-            await self._cluster.create_pod(review["namespace"], pod,
-                                           dry_run=True)
-        except ApiError as exc:
-            return _deny("Invalid", str(exc))
-        if job["spec"].get("maxReplicas", sys.maxsize) < \
-                job["spec"].get("minReplicas", 0):
-            return _deny("Invalid", "spec.maxReplicas must be greater than "
-                                    "or equal to spec.minReplicas")
-        return {"allowed": True}
+        return await verdict_for_create(self._cluster, review["namespace"],
+                                        review["object"])
 
     @staticmethod
     def _validate_update(review):
-        if review["object"]["spec"] != review["oldObject"]["spec"]:
-            return _deny("Forbidden", "updates to job spec are forbidden")
-        return {"allowed": True}
+        return verdict_for_update(review["oldObject"], review["object"])
+
+    async def _healthz(self, request):
+        return web.Response()
+
+    async def _validate(self, request):
+        review = (await request.json())["request"]
+        kind = review["operation"]
+        if kind == "CREATE":
+            verdict = await self._validate_create(review)
+        elif kind == "UPDATE":
+            verdict = self._validate_update(review)
+        else:                                  # DELETE / CONNECT: not ours
+            verdict = dict(ALLOW)
+        LOG.info("%s of %s/%s -> %s", kind, review.get("namespace"),
+                 review.get("name", "<new>"), verdict)
+        return web.json_response({
+            "apiVersion": "admission.k8s.io/v1", "kind": "AdmissionReview",
+            "response": dict(verdict, uid=review["uid"])})
 
 
 def main(argv=None):
     from adaptdl_b200.sched.kube import KubernetesCluster
-    parser = argparse.ArgumentParser()
+    parser = argparse.ArgumentParser(description=__doc__.split("\n")[0])
     parser.add_argument("--host", default="0.0.0.0")
     parser.add_argument("--port", type=int, default=8080)
-    parser.add_argument("--tls-crt")
-    parser.add_argument("--tls-key")
+    parser.add_argument("--tls-crt", help="server certificate (PEM)")
+    parser.add_argument("--tls-key", help="private key (PEM)")
     args = parser.parse_args(argv)
-    context = None
+    tls = None
     if args.tls_crt and args.tls_key:
-        context = ssl.SSLContext(ssl.PROTOCOL_TLS_SERVER)
-        context.load_cert_chain(args.tls_crt, args.tls_key)
-    Validator(KubernetesCluster()).run(args.host, args.port, context)
+        tls = ssl.SSLContext(ssl.PROTOCOL_TLS_SERVER)
+        tls.load_cert_chain(args.tls_crt, args.tls_key)
+    Validator(KubernetesCluster()).run(args.host, args.port, tls)
 
 
 if __name__ == "__main__":
