@@ -1,13 +1,20 @@
-"""Speedup of a job as a function of (nodes, replicas), relative to one
-replica, each at its own best batch size:
+"""Speedup of a job as a function of its allocation.
 
-    speedup(n, r) = max_bsz goodput(n, r, bsz) / max_bsz goodput(1, 1, bsz)
+``SpeedupFunction(goodput_fn, ...)(num_nodes, num_replicas)`` is the job's
+best achievable goodput on that allocation (batch size and gradient
+accumulation re-optimised for it) divided by its best goodput on a single
+replica, so ``speedup(1, 1) == 1`` and an empty allocation is worth 0.
 
-Evaluations are memoised in a small dense table because the policy's genetic
-search asks the same few hundred questions thousands of times (parity:
-reference ``policy/speedup.py:18-70``)."""
+The genetic search in ``pollux.py`` evaluates the same few hundred
+allocations tens of thousands of times per cycle, so results are kept in a
+dense ``[nodes, replicas]`` table (allocations beyond the table are computed
+on demand and not stored). Capabilities of the reference's
+``policy/speedup.py:18-70``.
+"""
 
 import numpy as np
+
+_UNKNOWN = -1.0
 
 
 class SpeedupFunction(object):
@@ -15,39 +22,55 @@ class SpeedupFunction(object):
     def __init__(self, goodput_fn, max_batch_size=None, atomic_bsz_range=None,
                  accumulation=False, mem_size=32):
         self._goodput_fn = goodput_fn
-        self._kwargs = dict(max_batch_size=max_batch_size,
-                            atomic_bsz_range=atomic_bsz_range,
-                            accumulation=accumulation)
-        self._mem_size = mem_size
-        self._base_goodput, _, _ = goodput_fn.optimize(
-            num_nodes=1, num_replicas=1, **self._kwargs)
-        self._table = np.full((mem_size, mem_size), -1.0)
-        self._table[0, 0] = 0.0          # nothing allocated, no progress
+        self._search = {"max_batch_size": max_batch_size,
+                        "atomic_bsz_range": atomic_bsz_range,
+                        "accumulation": accumulation}
+        self._limit = mem_size
+        self._cache = np.full((mem_size, mem_size), _UNKNOWN)
+        self._cache[0, 0] = 0.0                  # nothing allocated
+        self._unit = self._best_goodput(1, 1)    # the denominator
+
+    def _best_goodput(self, nodes, replicas):
+        best, _atomic_bsz, _accum_steps = self._goodput_fn.optimize(
+            nodes, replicas, **self._search)
+        return best
+
+    def _lookup(self, nodes, replicas):
+        """Cached speedups for flat integer arrays (``_UNKNOWN`` where the
+        table has no answer yet or cannot hold one)."""
+        found = np.full(nodes.shape, _UNKNOWN)
+        inside = replicas < self._limit
+        found[inside] = self._cache[nodes[inside], replicas[inside]]
+        return found
+
+    def _compute(self, nodes, replicas):
+        """Speedups of the DISTINCT allocations among the arguments, written
+        back to the table where they fit; returns one value per argument."""
+        distinct, where = np.unique(np.stack([nodes, replicas]), axis=1,
+                                    return_inverse=True)
+        n, r = distinct
+        speedup = np.asarray(self._best_goodput(n, r), dtype=float) \
+            / self._unit
+        storable = r < self._limit
+        self._cache[n[storable], r[storable]] = speedup[storable]
+        return speedup[np.asarray(where).reshape(-1)]
 
     def __call__(self, num_nodes, num_replicas):
-        assert np.all(np.less_equal(0, num_nodes))
-        assert np.all(np.less_equal(num_nodes, num_replicas))
-        assert np.all((np.asarray(num_nodes) > 0)
-                      == (np.asarray(num_replicas) > 0))
-        scalar = np.isscalar(num_nodes) and np.isscalar(num_replicas)
-        shape = np.broadcast(num_nodes, num_replicas).shape
-        nodes = np.broadcast_to(num_nodes, shape).reshape(-1).astype(int)
-        repl = np.broadcast_to(num_replicas, shape).reshape(-1).astype(int)
-        out = np.full(nodes.shape, -1.0)
-        small = repl < self._mem_size
-        out[small] = self._table[nodes[small], repl[small]]
-        todo = out < 0
-        if np.any(todo):
-            pairs, inverse = np.unique(
-                np.stack([nodes[todo], repl[todo]]), axis=1,
-                return_inverse=True)
-            inverse = np.asarray(inverse).reshape(-1)
-            goodput, _, _ = self._goodput_fn.optimize(
-                pairs[0], pairs[1], **self._kwargs)
-            speedup = np.asarray(goodput, dtype=float) / self._base_goodput
-            keep = pairs[1] < self._mem_size
-            self._table[pairs[0][keep], pairs[1][keep]] = speedup[keep]
-            out[todo] = speedup[inverse]
-        assert np.all(out >= 0)
-        out = out.reshape(shape)
-        return out.item() if scalar else out
+        nodes_in, replicas_in = np.asarray(num_nodes), np.asarray(num_replicas)
+        if np.any(nodes_in < 0) or np.any(nodes_in > replicas_in) or \
+                np.any((nodes_in > 0) != (replicas_in > 0)):
+            raise AssertionError(
+                "an allocation needs 0 <= nodes <= replicas, and replicas "
+                "exactly when it has nodes")
+        shape = np.broadcast(nodes_in, replicas_in).shape
+        nodes = np.broadcast_to(nodes_in, shape).astype(int).ravel()
+        replicas = np.broadcast_to(replicas_in, shape).astype(int).ravel()
+        result = self._lookup(nodes, replicas)
+        missing = result == _UNKNOWN
+        if missing.any():
+            result[missing] = self._compute(nodes[missing], replicas[missing])
+        if np.any(result < 0):
+            raise AssertionError("negative speedup from the goodput model")
+        if np.isscalar(num_nodes) and np.isscalar(num_replicas):
+            return float(result[0])
+        return result.reshape(shape)
