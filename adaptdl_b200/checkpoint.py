@@ -17,6 +17,7 @@ intact.
 
 import logging
 import os
+import pickle
 import shutil
 import weakref
 
@@ -90,6 +91,39 @@ class State(object):
         """Remove from the registry (extension: lets long-lived processes
         and tests drop states; the reference leaks them)."""
         _REGISTRY.discard(self)
+
+
+class PickledFields(State):
+    """A :class:`State` whose payload is a fixed list of attributes, pickled
+    in one of the three layouts the checkpoint format uses:
+
+    ``"value"``     a single attribute, pickled bare;
+    ``"tuple"``     one pickle holding the tuple of attributes;
+    ``"sequence"``  one pickle per attribute, back to back.
+    """
+
+    FIELDS = ()
+    LAYOUT = "tuple"
+
+    def save(self, fileobj):
+        values = tuple(getattr(self, name) for name in self.FIELDS)
+        if self.LAYOUT == "value":
+            pickle.dump(values[0], fileobj)
+        elif self.LAYOUT == "tuple":
+            pickle.dump(values, fileobj)
+        else:
+            for value in values:
+                pickle.dump(value, fileobj)
+
+    def load(self, fileobj):
+        if self.LAYOUT == "value":
+            values = (pickle.load(fileobj),)
+        elif self.LAYOUT == "tuple":
+            values = pickle.load(fileobj)
+        else:
+            values = [pickle.load(fileobj) for _ in self.FIELDS]
+        for name, value in zip(self.FIELDS, values):
+            setattr(self, name, value)
 
 
 def _staging_dir(root):

@@ -26,7 +26,6 @@ the reference pays every step.
 
 import collections
 import os
-import pickle
 import time
 
 import numpy as np
@@ -41,26 +40,20 @@ from adaptdl_b200.sched_hints import SCHED_HINTS, PERF_PARAMS, \
 REPORT_PERIOD_S = float(os.environ.get("ADAPTDL_REPORT_PERIOD", "30"))
 
 
-class _MetricsState(checkpoint.State):
-    # attribute -> default; also the order of the pickles on disk
-    _LAYOUT = (("profile", None), ("perf_params", None),
-               ("grad_params", None), ("init_batch_size", None),
-               ("max_batch_size", None), ("local_bsz_bounds", None),
-               ("gradient_accumulation", False), ("progress", 0.0))
+class _MetricsState(checkpoint.PickledFields):
+    # the order of the eight pickles on disk
+    FIELDS = ("profile", "perf_params", "grad_params", "init_batch_size",
+              "max_batch_size", "local_bsz_bounds", "gradient_accumulation",
+              "progress")
+    LAYOUT = "sequence"
 
     def __init__(self):
         super().__init__("adaptdl-metrics")
-        for name, default in self._LAYOUT:
-            setattr(self, name, default)
+        for name in self.FIELDS:
+            setattr(self, name, None)
         self.profile = collections.defaultdict(collections.Counter)
-
-    def save(self, fileobj):
-        for name, _ in self._LAYOUT:
-            pickle.dump(getattr(self, name), fileobj)
-
-    def load(self, fileobj):
-        for name, _ in self._LAYOUT:
-            setattr(self, name, pickle.load(fileobj))
+        self.gradient_accumulation = False
+        self.progress = 0.0
 
 
 class _OpenStep(object):

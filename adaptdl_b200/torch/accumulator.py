@@ -19,7 +19,6 @@ import collections
 import collections.abc
 import contextlib
 import copy
-import pickle
 
 from adaptdl_b200 import checkpoint, collective
 from adaptdl_b200.torch.data import current_dataloader
@@ -34,27 +33,30 @@ def _dict_iadd(a, b):
     return a
 
 
-class _AccumulatorState(checkpoint.State):
+class _AccumulatorState(checkpoint.PickledFields):
+    """What an :class:`Accumulator` persists: the totals of the current epoch
+    and, per epoch, the history of synchronised snapshots (replayed after a
+    restart). Pending local updates are not persisted -- they are summed into
+    the totals before every save."""
+
+    FIELDS = ("results_history", "results")
+    LAYOUT = "tuple"
     init_count = collections.Counter()   # epoch -> accumulators created
 
     def __init__(self, *args, **kwargs):
         if current_dataloader() is not None:
-            raise RuntimeError("accumulator may not be initialized during "
-                               "dataloader iteration")
+            raise RuntimeError("an Accumulator must be created outside of "
+                               "data-loader loops (every replica has to "
+                               "create the same accumulators in the same "
+                               "order)")
         epoch = current_epoch()
-        ordinal = _AccumulatorState.init_count[epoch]
-        super().__init__("adaptdl-accumulator-epoch{}-{}".format(epoch,
-                                                                 ordinal))
-        _AccumulatorState.init_count[epoch] += 1
-        self.results_history = collections.defaultdict(list)
-        self.results = dict(*args, **kwargs)
+        counter = _AccumulatorState.init_count
+        super().__init__("adaptdl-accumulator-epoch{}-{}".format(
+            epoch, counter[epoch]))
+        counter[epoch] += 1
         self.updates = {}
-
-    def save(self, fileobj):
-        pickle.dump((self.results_history, self.results), fileobj)
-
-    def load(self, fileobj):
-        self.results_history, self.results = pickle.load(fileobj)
+        self.results = dict(*args, **kwargs)
+        self.results_history = collections.defaultdict(list)
 
     def sync(self):
         """Sum the pending updates of all replicas into ``results``."""

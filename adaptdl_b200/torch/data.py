@@ -18,7 +18,6 @@ semantics and checkpoint format). B200 additions: :class:`DevicePrefetcher`
 import collections
 import logging
 import math
-import pickle
 import random
 import sys
 from contextlib import contextmanager
@@ -97,33 +96,29 @@ def current_dataloader():
     return AdaptiveDataLoaderHelper._current
 
 
-class _AdaptiveDataLoaderState(checkpoint.State):
+class _AdaptiveDataLoaderState(checkpoint.PickledFields):
+    FIELDS = ("current_index", "end_index", "last_position")
+    LAYOUT = "tuple"
+
     # Loaders are created in the same order on every replica; the name is
     # derived from (epoch at creation, creation ordinal within that epoch).
     init_count = collections.Counter()
 
     def __init__(self):
         if current_dataloader() is not None:
-            raise RuntimeError("dataloader may not be initialized during "
-                               "dataloader iteration")
+            raise RuntimeError("a data loader must be created outside of "
+                               "data-loader loops (replicas create their "
+                               "loaders in the same order)")
         epoch = current_epoch()
-        ordinal = _AdaptiveDataLoaderState.init_count[epoch]
-        super().__init__("adaptdl-dataloader-epoch{}-{}".format(epoch,
-                                                                ordinal))
-        _AdaptiveDataLoaderState.init_count[epoch] += 1
+        counter = _AdaptiveDataLoaderState.init_count
+        super().__init__("adaptdl-dataloader-epoch{}-{}".format(
+            epoch, counter[epoch]))
+        counter[epoch] += 1
         self.current_index = 0    # samples consumed in the current loop
         self.end_index = 0        # optional, for custom loaders
         self.last_position = {}   # epoch -> position of last finished loop
         self.current_local_bsz = 0
         self.accumulation_steps = 0
-
-    def save(self, fileobj):
-        pickle.dump((self.current_index, self.end_index,
-                     self.last_position), fileobj)
-
-    def load(self, fileobj):
-        self.current_index, self.end_index, self.last_position = \
-            pickle.load(fileobj)
 
 
 class AdaptiveDataLoaderHelper(object):

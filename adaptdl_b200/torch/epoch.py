@@ -15,7 +15,6 @@ restarts outside of epoch/dataloader loops must be safe to replay::
 """
 
 import logging
-import pickle
 
 from adaptdl_b200 import checkpoint
 
@@ -24,17 +23,17 @@ LOG = logging.getLogger(__name__)
 __all__ = ["remaining_epochs_until", "current_epoch", "finished_epochs"]
 
 
-class _EpochState(checkpoint.State):
+class _EpochState(checkpoint.PickledFields):
+    """Epochs completed so far (checkpointed) and the epoch of the loop that
+    is running now (not checkpointed: a restart re-enters the loop)."""
+
+    FIELDS = ("finished_epochs",)
+    LAYOUT = "value"
+
     def __init__(self):
         super().__init__(".adaptdl-epoch")
-        self.finished_epochs = 0
         self.current_epoch = None
-
-    def save(self, fileobj):
-        pickle.dump(self.finished_epochs, fileobj)
-
-    def load(self, fileobj):
-        self.finished_epochs = pickle.load(fileobj)
+        self.finished_epochs = 0
 
 
 _EPOCH_STATE = None
