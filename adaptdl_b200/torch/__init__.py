@@ -103,25 +103,29 @@ def init_process_group(backend, init_method=None, world_size=None,
     """
     _adopt_torchrun_env()
     if env.from_ray():
+        # Ray Tune hands the rendezvous over explicitly; mirror it into the
+        # environment the rest of the library reads
+        if None in (init_method, world_size, rank):
+            raise ValueError("under Ray, init_method, world_size and rank "
+                             "must all be given")
         from adaptdl_b200.ray.utils import unique_nodes_pg
-        assert init_method is not None
-        assert world_size is not None
-        assert rank is not None
-        os.environ["ADAPTDL_NUM_NODES"] = str(unique_nodes_pg())
-        os.environ["ADAPTDL_REPLICA_RANK"] = str(rank)
-        os.environ["ADAPTDL_NUM_REPLICAS"] = str(world_size)
+        os.environ.update(ADAPTDL_NUM_REPLICAS=str(world_size),
+                          ADAPTDL_REPLICA_RANK=str(rank),
+                          ADAPTDL_NUM_NODES=str(unique_nodes_pg()))
+    if rank is None:
+        rank = env.replica_rank()
+    if world_size is None:
+        world_size = env.num_replicas()
 
-    url = env.supervisor_url()
+    # where rank 0 listens: explicit URL > supervisor discovery > environment
     master_port = env.master_port()
-    rank = env.replica_rank() if rank is None else rank
-    world_size = env.num_replicas() if world_size is None else world_size
-
+    supervisor = env.supervisor_url()
     if init_method is not None:
-        _, master_addr, port = init_method.split(":")
-        master_addr = master_addr[2:]
+        scheme, _, location = init_method.partition("://")
+        master_addr, _, port = location.rpartition(":")
         master_port = int(port)
-    elif url:
-        master_addr = _discover_master(url)
+    elif supervisor:
+        master_addr = _discover_master(supervisor)
     else:
         master_addr = env.master_addr()
 

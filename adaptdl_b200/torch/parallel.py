@@ -265,23 +265,18 @@ class AdaptiveDataParallel(torch.nn.Module):
 
     def to_tensorboard(self, writer, global_step, tag_prefix=""):
         """Write gradient statistics to a TensorBoard ``SummaryWriter``."""
-        if tag_prefix and not tag_prefix.endswith("/"):
-            tag_prefix += "/"
+        prefix = tag_prefix.rstrip("/") + "/" if tag_prefix else ""
         gns = self.gns
-        writer.add_scalar(tag_prefix + "Gradient_Norm_Sqr", gns.sqr_avg(),
-                          global_step)
-        writer.add_scalar(tag_prefix + "Gradient_Variance", gns.var_avg(),
-                          global_step)
-        writer.add_scalar(tag_prefix + "Gain", self._state.gain, global_step)
-        writer.add_scalar(tag_prefix + "Learning_Rate_Factor",
-                          self._state.lr_factor, global_step)
-        writer.add_scalar(tag_prefix + "Accum_Scale", gns.accum_scale,
-                          global_step)
+        scalars = [("Gradient_Norm_Sqr", gns.sqr_avg()),
+                   ("Gradient_Variance", gns.var_avg()),
+                   ("Gain", self._state.gain),
+                   ("Learning_Rate_Factor", self._state.lr_factor),
+                   ("Accum_Scale", gns.accum_scale),
+                   ("Progress", gns.get_progress())]
         if gns.accum_count > 0:
-            writer.add_scalar(tag_prefix + "Accum_Count", gns.accum_count,
-                              global_step)
-        writer.add_scalar(tag_prefix + "Progress", gns.get_progress(),
-                          global_step)
+            scalars.append(("Accum_Count", gns.accum_count))
+        for tag, value in scalars:
+            writer.add_scalar(prefix + tag, value, global_step)
 
 
 def mixed_precision_params(model, dtype=torch.bfloat16, min_dim=2):
