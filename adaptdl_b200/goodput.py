@@ -68,34 +68,49 @@ class GoodputFunction(object):
     accum_steps) and searches for the best batch-size configuration."""
 
     def __init__(self, perf_params, grad_params, init_batch_size):
-        self._perf_params = PerfParams(*perf_params)
-        self._grad_params = GradParams(*grad_params)
+        self._perf = PerfParams(*perf_params)
+        self._grad = GradParams(*grad_params)
         self._init_batch_size = init_batch_size
 
-    def __call__(self, num_nodes, num_replicas, atomic_bsz, accum_steps):
-        return self.evaluate(num_nodes, num_replicas, atomic_bsz, accum_steps)
+    # kept for callers that reach into the model
+    _perf_params = property(lambda self: self._perf)
+    _grad_params = property(lambda self: self._grad)
 
-    def evaluate(self, num_nodes, num_replicas, atomic_bsz, accum_steps):
-        batch_size = num_replicas * atomic_bsz * (accum_steps + 1)
-        assert np.all(self._init_batch_size <= batch_size)
-        return (self.throughput(num_nodes, num_replicas, atomic_bsz,
-                                accum_steps) * self.efficiency(batch_size))
+    @staticmethod
+    def _batch_size(num_replicas, atomic_bsz, accum_steps):
+        return num_replicas * atomic_bsz * (accum_steps + 1)
 
     def throughput(self, num_nodes, num_replicas, atomic_bsz, accum_steps):
-        p = self._perf_params
-        accum = _accum_time(p, atomic_bsz)
-        network = _network_time(p, num_nodes, num_replicas)
-        optim = np.exp(_log_optim_time(p.gamma, accum, network))
-        batch_size = num_replicas * atomic_bsz * (accum_steps + 1)
-        return batch_size / (accum_steps * accum + optim)
+        """Samples per second: ``accum_steps`` local micro-steps followed by
+        one step that also synchronises (gamma-norm of compute and network
+        time: they overlap partially)."""
+        local = _accum_time(self._perf, atomic_bsz)
+        network = _network_time(self._perf, num_nodes, num_replicas)
+        last = np.exp(_log_optim_time(self._perf.gamma, local, network))
+        samples = self._batch_size(num_replicas, atomic_bsz, accum_steps)
+        return samples / (accum_steps * local + last)
 
     def efficiency(self, batch_size):
-        sqr, var = self._grad_params
+        """Statistical efficiency relative to the initial batch size: how
+        much progress one sample makes at ``batch_size`` (gain / scale)."""
+        sqr, var = self._grad
         scale = batch_size / self._init_batch_size
-        denom = var / scale + sqr
-        gain = np.where(denom > 0, (var + sqr) / np.where(denom > 0, denom, 1),
+        noise = var / scale + sqr
+        usable = noise > 0
+        gain = np.where(usable, (var + sqr) / np.where(usable, noise, 1.0),
                         1.0)
         return gain / scale
+
+    def evaluate(self, num_nodes, num_replicas, atomic_bsz, accum_steps):
+        """Goodput = throughput x efficiency (useful samples per second)."""
+        samples = self._batch_size(num_replicas, atomic_bsz, accum_steps)
+        if np.any(samples < self._init_batch_size):
+            raise AssertionError("batch size below the initial batch size")
+        speed = self.throughput(num_nodes, num_replicas, atomic_bsz,
+                                accum_steps)
+        return speed * self.efficiency(samples)
+
+    __call__ = evaluate
 
     def optimize(self, num_nodes, num_replicas, max_batch_size=None,
                  atomic_bsz_range=None, accumulation=False):
