@@ -40,28 +40,30 @@ def datasets():
 
 
 def train(model, device, train_loader, optimizer, epoch):
+    """One pass over the training loader (plain supervised step)."""
     model.train()
-    for batch_idx, (data, target) in enumerate(train_loader):
-        data, target = data.to(device), target.to(device)
+    for step, (images, labels) in enumerate(train_loader):
+        images = images.to(device)
+        labels = labels.to(device)
         optimizer.zero_grad()
-        loss = F.nll_loss(model(data), target)
-        loss.backward()
+        nll = F.nll_loss(model(images), labels)
+        nll.backward()
         optimizer.step()
-        if batch_idx % 10 == 0:
-            print("Train epoch {} batch {} loss {:.4f}".format(
-                epoch, batch_idx, loss.item()))
+        if step % 10 == 0:
+            print("epoch {:3d}  step {:4d}  train loss {:.4f}".format(
+                epoch, step, nll.item()))
 
 def test(model, device, test_loader):
     model.eval()
     stats = adl.Accumulator()
     with torch.no_grad():
-        for data, target in test_loader:
-            data, target = data.to(device), target.to(device)
-            output = model(data)
-            stats["loss_sum"] += F.nll_loss(output, target,
+        for images, labels in test_loader:
+            images, labels = images.to(device), labels.to(device)
+            scores = model(images)
+            stats["loss_sum"] += F.nll_loss(scores, labels,
                                             reduction="sum").item()
-            stats["correct"] += output.argmax(1).eq(target).sum().item()
-            stats["total"] += len(target)
+            stats["correct"] += scores.argmax(1).eq(labels).sum().item()
+            stats["total"] += len(labels)
     with stats.synchronized():
         print("Test set: average loss {:.4f}, accuracy {}/{}".format(
             stats["loss_sum"] / stats["total"], stats["correct"],
