@@ -57,7 +57,7 @@ struct BnArgs {
 //   partial sums; the LAST CTA to finish in a channel block (ticket counter, self-resetting)
 //   folds that block's grid.y partials in a fixed order (deterministic) and derives
 //   mean / rstd / scale / shift (forward) or dgamma / dbeta / s1/M / s2/M (backward).
-template <typename T, bool BWD>
+template <typename T, bool BWD, bool MASK>
 __global__ void __launch_bounds__(BN_THREADS)
 bn_reduce_kernel(const BnArgs a) {
   constexpr int V = VecTraits<T>::N;
@@ -91,7 +91,7 @@ bn_reduce_kernel(const BnArgs a) {
         if (BWD) {
           vg[u] = ld_vec(static_cast<const char*>(a.dy) + off);
           if (a.relu) {
-            if (a.mask != nullptr) vy[u].w[0] = a.mask[((size_t)r * a.C + my_c) / V];
+            if (MASK) vy[u].w[0] = a.mask[((size_t)r * a.C + my_c) / V];
             else vy[u] = ld_vec(static_cast<const char*>(a.y) + off);
           }
         }
@@ -110,7 +110,7 @@ bn_reduce_kernel(const BnArgs a) {
           float fg[V], fy[V];
           unpack<T>(vg[u], fg);
           if (a.relu) {
-            if (a.mask != nullptr) {
+            if (MASK) {
 #pragma unroll
               for (int e = 0; e < V; ++e) fy[e] = (float)((vy[u].w[0] >> e) & 1u);
             } else {
@@ -210,7 +210,7 @@ bn_reduce_kernel(const BnArgs a) {
 
 // forward:  y  = act(x * scale + shift + res)
 // backward: dx = gamma * rstd * (g - s1/M - xhat * s2/M),  dres = g,  g = dy * [y > 0]
-template <typename T, bool BWD>
+template <typename T, bool BWD, bool MASK>
 __global__ void __launch_bounds__(BN_THREADS)
 bn_apply_kernel(const BnArgs a) {
   constexpr int V = VecTraits<T>::N;
@@ -248,7 +248,7 @@ bn_apply_kernel(const BnArgs a) {
         } else {
           vb[u] = ld_vec(static_cast<const char*>(a.dy) + off);
           if (a.relu) {
-            if (a.mask != nullptr) vy[u].w[0] = a.mask[((size_t)r * a.C + my_c) / V];
+            if (MASK) vy[u].w[0] = a.mask[((size_t)r * a.C + my_c) / V];
             else vy[u] = ld_vec(static_cast<const char*>(a.y) + off);
           }
         }
@@ -270,7 +270,7 @@ bn_apply_kernel(const BnArgs a) {
             out[e] = a.relu ? fmaxf(v, 0.f) : v;
           }
           st_vec(static_cast<char*>(a.y) + off, pack<T>(out));
-          if (a.relu && a.mask != nullptr) {
+          if (MASK && a.relu) {
             uint32_t bits = 0;
 #pragma unroll
             for (int e = 0; e < V; ++e) bits |= (out[e] > 0.f ? 1u : 0u) << e;
@@ -280,7 +280,7 @@ bn_apply_kernel(const BnArgs a) {
           float fy[V], g[V];
           unpack<T>(vb[u], fb);
           if (a.relu) {
-            if (a.mask != nullptr) {
+            if (MASK) {
 #pragma unroll
               for (int e = 0; e < V; ++e) fy[e] = (float)((vy[u].w[0] >> e) & 1u);
             } else {
@@ -301,17 +301,25 @@ bn_apply_kernel(const BnArgs a) {
   }
 }
 
-template <typename T>
-int run(const BnArgs& a, int backward, int grid_y, int grid_apply, cudaStream_t s) {
+template <typename T, bool MASK>
+int run_masked(const BnArgs& a, int backward, int grid_y, int grid_apply, cudaStream_t s) {
   const dim3 grid(a.C / a.cb, grid_y);
   if (!backward) {
-    bn_reduce_kernel<T, false><<<grid, BN_THREADS, 0, s>>>(a);
-    bn_apply_kernel<T, false><<<grid_apply, BN_THREADS, 0, s>>>(a);
+    bn_reduce_kernel<T, false, false><<<grid, BN_THREADS, 0, s>>>(a);   // never reads the mask
+    bn_apply_kernel<T, false, MASK><<<grid_apply, BN_THREADS, 0, s>>>(a);
   } else {
-    bn_reduce_kernel<T, true><<<grid, BN_THREADS, 0, s>>>(a);
-    bn_apply_kernel<T, true><<<grid_apply, BN_THREADS, 0, s>>>(a);
+    bn_reduce_kernel<T, true, MASK><<<grid, BN_THREADS, 0, s>>>(a);
+    bn_apply_kernel<T, true, MASK><<<grid_apply, BN_THREADS, 0, s>>>(a);
   }
   return (int)cudaGetLastError();
+}
+
+// The ReLU bit mask is a compile-time variant so that the default path (mask == null) keeps
+// the register footprint -- and with it the occupancy -- of the kernels without it.
+template <typename T>
+int run(const BnArgs& a, int backward, int grid_y, int grid_apply, cudaStream_t s) {
+  return (a.mask != nullptr && a.relu) ? run_masked<T, true>(a, backward, grid_y, grid_apply, s)
+                                       : run_masked<T, false>(a, backward, grid_y, grid_apply, s);
 }
 
 }  // namespace
