@@ -4,11 +4,14 @@ memory, topology discovery, CUDA-graph step capture."""
 
 
 # Default bucket caps. The fused kernels cost ~20 us per bucket on the comm
-# stream (nothing on the host inside a CUDA graph), so small buckets are cheap
-# and what matters is how little is left to reduce when backward ends: with
-# DDP's 25 MB, ResNet-18's 22 MB of bf16 gradients are one bucket that only
-# completes with the first layer, i.e. the whole all-reduce is exposed.
-CUDA_BUCKET_CAP_MB = 4
+# stream (nothing on the host inside a CUDA graph), so smaller buckets than
+# DDP's are plausible: with 25 MB, ResNet-18's 22 MB of bf16 gradients are one
+# bucket that only completes with the first layer, i.e. the whole all-reduce
+# (~50 us at N=8) is exposed. Smaller buckets overlap it with backward but put
+# flag-spinning CTAs next to the backward kernels; that trade has not been
+# measured yet (ROUND2_PLAN.md, `bench.py --bucket-cap-mb 4`), so the default
+# stays at the value every published number was taken with.
+CUDA_BUCKET_CAP_MB = 25
 TORCH_BUCKET_CAP_MB = 25
 
 
@@ -17,8 +20,8 @@ def make_reducer(param_groups, world_size, rank, should_sync,
                  name="reducer"):
     """Pick the gradient reducer for this process.
 
-    ``bucket_cap_mb``: ``None`` = the reducer's own default (4 MB for the
-    fused kernels, DDP's 25 MB for torch collectives).
+    ``bucket_cap_mb``: ``None`` = the reducer's own default (``CUDA_BUCKET_CAP_MB`` /
+    ``TORCH_BUCKET_CAP_MB``).
 
     ``backend``: ``"cuda"`` = fused sm_100a kernels (raises if unavailable),
     ``"torch"`` = stock torch collectives, ``"auto"`` = fused kernels when the

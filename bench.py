@@ -53,7 +53,7 @@ def parse_args():
     ap.add_argument("--reducer", default="auto")
     ap.add_argument("--bucket-cap-mb", type=float, default=None,
                     help="own arm: gradient bucket cap (default: the "
-                         "reducer's own, 4 MB for the fused kernels)")
+                         "reducer's own, 25 MB)")
     ap.add_argument("--param-dtype", default="bf16", choices=["bf16", "fp32"],
                     help="own arm: store conv/linear weights in bf16 with "
                          "fp32 masters inside the fused optimizer (default) "

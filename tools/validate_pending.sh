@@ -21,7 +21,7 @@ echo "== 2. full GPU suite (defaults)"
 timeout 900 python -m pytest tests -q -m gpu > "$OUT/pytest_gpu.log" 2>&1
 tail -3 "$OUT/pytest_gpu.log"
 
-echo "== 3. headline bench: defaults (4 MB buckets) vs 25 MB buckets vs padded stem vs BN bit-mask"
+echo "== 3. headline bench: defaults vs padded stem vs BN bit-mask"
 timeout 300 python bench.py --steps 40 --warmup 8 > "$OUT/bench_n1_default.log" 2>&1
 ADAPTDL_B200_PAD_STEM=1 timeout 300 python bench.py --steps 40 --warmup 8 > "$OUT/bench_n1_padstem.log" 2>&1
 ADAPTDL_B200_BN_BITMASK=1 timeout 300 python bench.py --steps 40 --warmup 8 > "$OUT/bench_n1_bitmask.log" 2>&1
@@ -54,13 +54,13 @@ ADAPTDL_B200_BN_BITMASK=1 timeout 200 python tools/bn_bench.py --out "$OUT/bn_be
 grep -h fused_fwd_bwd_us "$OUT"/bn_bench_*.log | cut -c1-200
 
 if [ "$NGPU" -ge 2 ]; then
-  echo "== 6. N=2 headline: 4 MB (default) vs 25 MB buckets"
+  echo "== 6. N=2 headline: 25 MB (default) vs 4 MB buckets"
   timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
       --master-port 29521 bench.py --gpus 2 --steps 40 --warmup 8 > "$OUT/bench_n2_default.log" 2>&1
   tail -1 "$OUT/bench_n2_default.log" | cut -c1-160
   timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
-      --master-port 29524 bench.py --gpus 2 --steps 40 --warmup 8 --bucket-cap-mb 25 > "$OUT/bench_n2_cap25.log" 2>&1
-  tail -1 "$OUT/bench_n2_cap25.log" | cut -c1-160
+      --master-port 29524 bench.py --gpus 2 --steps 40 --warmup 8 --bucket-cap-mb 4 > "$OUT/bench_n2_cap4.log" 2>&1
+  tail -1 "$OUT/bench_n2_cap4.log" | cut -c1-160
   echo "== 7. all-reduce stress (P2P and multimem flavours)"
   timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
       --master-port 29522 tools/allreduce_stress.py --iters 5000 > "$OUT/stress_p2p.log" 2>&1
