@@ -31,6 +31,8 @@ def main(argv=None):
     elif role == "allocator":
         from adaptdl_b200.sched.allocator import AdaptDLAllocator
         from adaptdl_b200.sched.cluster_expander import ClusterExpander
+        from adaptdl_b200.sched import metrics
+        metrics.serve(9092)              # per-cycle and per-job series
         expander = ClusterExpander(cluster)
         allocator = AdaptDLAllocator(cluster, expander)
 

@@ -21,7 +21,7 @@ import logging
 import time
 
 from adaptdl_b200.goodput import GoodputFunction, GradParams, PerfParams
-from adaptdl_b200.sched import config
+from adaptdl_b200.sched import config, metrics
 from adaptdl_b200.sched.kube import NotFound
 from adaptdl_b200.sched.policy import (JobInfo, NodeInfo, PolluxPolicy,
                                        SpeedupFunction)
@@ -81,6 +81,7 @@ class AdaptDLAllocator(object):
         self._policy = policy or PolluxPolicy()
         self._period = period
         self._lock = asyncio.Lock()
+        self._desired_nodes = None
 
     async def run(self):
         await asyncio.gather(self._allocate_one_loop(),
@@ -131,10 +132,15 @@ class AdaptDLAllocator(object):
         nodes, template = await self.find_nodes(
             pod_label_selector="!adaptdl/job")
         jobs, previous = await self.find_jobs_and_allocations()
+        known = list(jobs)
         start = time.time()
         allocations = self.allocate(jobs, nodes, previous, template)
-        LOG.info("allocations (%.3f s): %s", time.time() - start, allocations)
+        elapsed = time.time() - start
+        LOG.info("allocations (%.3f s): %s", elapsed, allocations)
         await self.update_allocations(allocations)
+        metrics.observe_cycle(allocations, nodes, seconds=elapsed,
+                              desired_nodes=self._desired_nodes,
+                              known_jobs=known)
         return allocations
 
     async def find_nodes(self, pod_label_selector=None):
@@ -179,9 +185,11 @@ class AdaptDLAllocator(object):
                 LOG.warning("job %s cannot be scheduled on any node", key)
                 jobs.pop(key)
         allocations, active = {}, []
+        self._desired_nodes = None
         if jobs and nodes:
             allocations, desired = self._policy.optimize(
                 jobs, nodes, previous, template)
+            self._desired_nodes = desired
             if desired < len(nodes):
                 used = [set(a) for a in allocations.values() if a]
                 active = sorted(set().union(*used)) if used else []

@@ -7,6 +7,9 @@
 * ``PUT  /hints/{namespace}/{name}`` -- scheduling hints from rank 0, stored
   in the job's ``status.train`` (only recognised keys are kept).
 * ``GET  /healthz``
+* ``GET  /metrics`` -- Prometheus series derived from the hints (per-job
+  batch sizes, gradient statistics, fitted parameters, predicted speedups:
+  ``sched/metrics.py``)
 
 Parity: reference ``sched/adaptdl_sched/supervisor.py:27-99``; here over the
 backend abstraction, polling the pod list instead of holding a K8s watch.
@@ -18,7 +21,7 @@ import time
 
 from aiohttp import web
 
-from adaptdl_b200.sched import config
+from adaptdl_b200.sched import config, metrics
 from adaptdl_b200.sched_hints import SCHED_HINTS
 
 LOG = logging.getLogger(__name__)
@@ -38,6 +41,7 @@ class Supervisor(object):
             web.get("/discover/{namespace}/{name}/{group}",
                     self._handle_discover),
             web.put("/hints/{namespace}/{name}", self._handle_report),
+            web.get("/metrics", self._handle_metrics),
         ])
 
     async def _handle_healthz(self, request):
@@ -80,8 +84,16 @@ class Supervisor(object):
         patched = await self._cluster.patch_job_status(
             info["namespace"], info["name"], {"status": {"train": hints}})
         if patched is None:
+            metrics.forget_job(info["namespace"], info["name"])
             return web.Response(status=404)
+        metrics.observe_hints(info["namespace"], info["name"], hints)
         return web.Response()
+
+    async def _handle_metrics(self, request):
+        """Prometheus exposition of the per-job series (sched/metrics.py)."""
+        body, content_type = metrics.render()
+        return web.Response(body=body,
+                            headers={"Content-Type": content_type})
 
     def run(self):
         web.run_app(self.app, host=self._host, port=self._port)

@@ -12,7 +12,7 @@ from adaptdl_b200.sched.cluster_expander import ClusterExpander
 from adaptdl_b200.sched.controller import (AdaptDLController, build_pod,
                                            reconcile, detect_completion)
 from adaptdl_b200.sched.kube import InMemoryCluster
-from adaptdl_b200.sched.policy import PolluxPolicy
+from adaptdl_b200.sched.policy import NodeInfo, PolluxPolicy
 from adaptdl_b200.sched.supervisor import Supervisor
 from adaptdl_b200.sched.validator import Validator
 
@@ -358,7 +358,37 @@ def test_supervisor_endpoints():
             assert "bogus" not in train and train["initBatchSize"] == 128
             resp = await client.put("/hints/ns/missing", json=HINTS)
             assert resp.status == 404
+            # the hints became Prometheus series
+            text = await (await client.get("/metrics")).text()
+            assert 'adaptdl_job_batch_size{job="job",kind="init",' \
+                'namespace="ns"} 128.0' in text
+            assert 'adaptdl_job_speedup_predict{job="job",namespace="ns",' \
+                'replicas="1"} 1.0' in text
+            assert 'job="missing"' not in text
     run(scenario())
+
+
+def test_scheduler_metrics():
+    from adaptdl_b200.sched import metrics
+    predicted = metrics.speedup_predictions(HINTS)
+    assert predicted[1] == 1.0
+    assert 1.0 < predicted[2] < 2.0 and predicted[2] <= predicted[8]
+    assert metrics.speedup_predictions({"initBatchSize": 128}) == {}
+    nodes = {"n0": NodeInfo({"nvidia.com/gpu": 4}, False),
+             "n1": NodeInfo({"nvidia.com/gpu": 4}, False)}
+    metrics.observe_cycle({("ns", "m1"): ["n0", "n0", "n1"]}, nodes,
+                          seconds=0.5, desired_nodes=2,
+                          known_jobs=[("ns", "m1"), ("ns", "m2")])
+    text = metrics.render()[0].decode()
+    assert 'adaptdl_job_replicas{job="m1",namespace="ns"} 3.0' in text
+    assert 'adaptdl_job_nodes{job="m1",namespace="ns"} 2.0' in text
+    assert 'adaptdl_job_replicas{job="m2",namespace="ns"} 0.0' in text
+    assert 'adaptdl_sched_cluster_gpus{state="total"} 8.0' in text
+    assert 'adaptdl_sched_cluster_gpus{state="allocated"} 3.0' in text
+    assert "adaptdl_sched_desired_nodes 2.0" in text
+    metrics.forget_job("ns", "m1")
+    text = metrics.render()[0].decode()
+    assert 'job="m1"' not in text and 'job="m2"' in text
 
 
 def test_validator_webhook():
@@ -398,3 +428,32 @@ def test_validator_webhook():
                 "DELETE", good))).json()
             assert out["response"]["allowed"] is True
     run(scenario())
+
+
+def test_dashboard_only_plots_series_the_code_exports():
+    """The reference's Grafana dashboard went stale (none of its series is
+    exported any more); ours must track the code."""
+    import os
+    import re
+    from adaptdl_b200.sched import metrics
+    from adaptdl_b200.sched import controller
+    controller.JOB_COMPLETION_TIME.labels(status="Succeeded").observe(1.0)
+    metrics.observe_hints("ns", "dash", HINTS)
+    metrics.observe_cycle({("ns", "dash"): ["n0"]},
+                          {"n0": NodeInfo({"nvidia.com/gpu": 1}, False)},
+                          seconds=0.1, desired_nodes=1)
+    import prometheus_client
+    exported = set()
+    for family in prometheus_client.REGISTRY.collect():
+        for sample in family.samples:
+            exported.add(sample.name)
+    path = os.path.join(os.path.dirname(os.path.dirname(
+        os.path.abspath(__file__))), "deploy", "grafana", "dashboard.json")
+    with open(path) as f:
+        dashboard = json.load(f)
+    plotted = set()
+    for panel in dashboard["panels"]:
+        for target in panel["targets"]:
+            plotted.update(re.findall(r"adaptdl_[a-z_]+", target["expr"]))
+    assert plotted and plotted <= exported, plotted - exported
+    metrics.forget_job("ns", "dash")
