@@ -41,8 +41,9 @@ EXIT_PREEMPTED = 143
 
 
 class HintsServer(object):
-    """Tiny supervisor: ``PUT /hints/<job>`` and ``GET /discover/...`` (all
-    replicas are local, so discovery always answers 127.0.0.1)."""
+    """Tiny supervisor: ``PUT /hints/<job>``, ``GET /discover/...`` (all
+    replicas are local, so discovery always answers 127.0.0.1) and
+    ``GET /metrics`` (Prometheus series derived from the hints)."""
 
     def __init__(self):
         from http.server import BaseHTTPRequestHandler, ThreadingHTTPServer
@@ -58,6 +59,10 @@ class HintsServer(object):
                 if self.path.startswith("/discover/"):
                     body = json.dumps(["127.0.0.1"] * outer.replicas)
                     self._reply(200, body)
+                elif self.path == "/metrics":     # same series as the
+                    from adaptdl_b200.sched import metrics  # K8s supervisor
+                    body, ctype = metrics.render()
+                    self._reply(200, body.decode(), ctype)
                 else:
                     self._reply(200, "")
 
@@ -68,13 +73,16 @@ class HintsServer(object):
                     outer.hints = {k: hints[k] for k in SCHED_HINTS
                                    if k in hints}
                     self._reply(200, "")
+                    from adaptdl_b200.sched import metrics
+                    metrics.observe_hints(
+                        "local", self.path.rsplit("/", 1)[-1], outer.hints)
                 except ValueError:
                     self._reply(400, "")
 
-            def _reply(self, code, body):
+            def _reply(self, code, body, ctype="application/json"):
                 data = body.encode()
                 self.send_response(code)
-                self.send_header("Content-Type", "application/json")
+                self.send_header("Content-Type", ctype)
                 self.send_header("Content-Length", str(len(data)))
                 self.end_headers()
                 self.wfile.write(data)

@@ -53,6 +53,10 @@ def test_hints_server_round_trip():
             assert resp.status == 200
         assert server.hints["initBatchSize"] == 128
         assert "ignored" not in server.hints
+        with urllib.request.urlopen(server.url + "/metrics") as resp:
+            text = resp.read().decode()
+        assert 'adaptdl_job_batch_size{job="job",kind="init",' \
+            'namespace="local"} 128.0' in text
     finally:
         server.close()
 
