@@ -1,9 +1,10 @@
 """Tune trial scheduler / trial / trainable for elastic trials.
 
 * ``AdaptDLTrainableCreator(train_fn, num_workers=...)`` wraps a training
-  function into a Tune trainable whose workers call
-  ``adaptdl_b200.torch.init_process_group`` with Tune's rendezvous (sets
-  ``ADAPTDL_TUNE_TRIAL_SCHED`` so checkpoints go through Tune).
+  function into a Tune trainable whose replicas are Ray actors forming an
+  ordinary adaptdl_b200 job (``workers.py`` / ``trainable.py``); its
+  checkpoints are in-memory objects, so a clone on another placement group
+  resumes with a different replica count.
 * ``AdaptDLTrial`` = a Tune ``Trial`` that can be *cloned onto a new
   placement group* and restored from an in-memory checkpoint (= rescale).
 * ``AdaptDLScheduler`` (a ``TrialScheduler``) calls the allocator every
@@ -136,19 +137,13 @@ def _build():
         def debug_string(self):
             return "AdaptDLScheduler (adaptdl_b200)"
 
-    def AdaptDLTrainableCreator(func, num_workers=1, group=0,
-                                num_cpus_per_worker=1, num_workers_per_host=None,
-                                backend="gloo", timeout_s=1800, use_gpu=None):
-        """Wrap ``func(config, checkpoint_dir=None)`` as an elastic Tune
-        trainable."""
-        import os
-
-        def wrapped(config, checkpoint_dir=None):
-            os.environ["ADAPTDL_TUNE_TRIAL_SCHED"] = "true"
-            return func(config, checkpoint_dir=checkpoint_dir)
-        return tune.with_resources(
-            wrapped, ray_utils.allocation_to_pgf(
-                ["virtual-{}".format(i) for i in range(num_workers)]))
+    def AdaptDLTrainableCreator(func, num_workers=1,
+                                resources_per_replica=None, **_ignored):
+        """Wrap ``func(config, report)`` -- an adaptdl_b200 training loop
+        that calls ``report(**metrics)`` -- as an elastic Tune trainable
+        whose replicas run as Ray actors (``trainable.py``)."""
+        from adaptdl_b200.ray.tune.trainable import make_trainable
+        return make_trainable(func, num_workers, resources_per_replica)
 
     _CLASSES.update(AdaptDLTrial=AdaptDLTrial,
                     AdaptDLScheduler=AdaptDLScheduler,
