@@ -49,3 +49,16 @@ def test_auto_batch_size_replay_is_u_shaped():
     assert times[512] < times[128] and times[512] < times[4096]
     assert auto <= min(times.values()) * 1.01
     assert trace[-1] > trace[0]          # batch size grows with the noise
+
+
+def test_docs_reference_existing_paths():
+    check_docs = _load("check_docs")
+    problems = []
+    for path in check_docs.markdown_files():
+        problems.extend(check_docs.check_file(path))
+    assert not problems, "\n".join(problems)
+    assert check_docs.repo_path("adaptdl_b200/ops/bn_act.py:12") == \
+        "adaptdl_b200/ops/bn_act.py"
+    assert check_docs.repo_path("tests/test_ops.py::test_x") == \
+        "tests/test_ops.py"
+    assert check_docs.repo_path("torch/data.py") is None
