@@ -21,7 +21,11 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(os.path.dirname(_HERE))
+# a source checkout keeps the kernels in <repo>/csrc; an installed package
+# (sdist / wheel) carries a copy next to this file (setup.py: BuildPyWithCsrc)
 CSRC = os.path.join(_ROOT, "csrc")
+if not os.path.isdir(CSRC):
+    CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libadl_b200.so")
 STAMP_PATH = os.path.join(_HERE, "libadl_b200.stamp")
 

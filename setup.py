@@ -3,8 +3,11 @@ in-tree by ``adaptdl_b200._native.build()`` (plain nvcc, sm_100a) so the same
 ``.so`` ships with a repo snapshot; ``python setup.py build_native`` runs it."""
 import os
 
+import shutil
+
 import setuptools
 from setuptools import Command
+from setuptools.command.build_py import build_py
 
 
 class BuildNative(Command):
@@ -22,6 +25,22 @@ class BuildNative(Command):
         sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
         from adaptdl_b200 import _native
         print(_native.build(force=True))
+
+
+class BuildPyWithCsrc(build_py):
+    """Installed packages carry the CUDA sources (``csrc/``) inside
+    ``adaptdl_b200/_native/csrc`` so ``adaptdl_b200._native.build()`` can
+    compile them on the target machine."""
+
+    def run(self):
+        super().run()
+        here = os.path.dirname(os.path.abspath(__file__))
+        target = os.path.join(self.build_lib, "adaptdl_b200", "_native",
+                              "csrc")
+        os.makedirs(target, exist_ok=True)
+        for name in sorted(os.listdir(os.path.join(here, "csrc"))):
+            if name.endswith((".cu", ".cuh", ".cpp", ".h")):
+                shutil.copy2(os.path.join(here, "csrc", name), target)
 
 
 setuptools.setup(
@@ -46,5 +65,5 @@ setuptools.setup(
         "adaptdl-b200-local-cluster=adaptdl_b200.sched.local_cluster:main",
         "adaptdl-b200-on-ray-aws=adaptdl_b200.ray.aws.launch_job:main",
     ]},
-    cmdclass={"build_native": BuildNative},
+    cmdclass={"build_native": BuildNative, "build_py": BuildPyWithCsrc},
 )

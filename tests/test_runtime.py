@@ -241,3 +241,16 @@ def test_modules_import_standalone():
     for m, proc in zip(mods, procs):
         _, err = proc.communicate(timeout=300)
         assert proc.returncode == 0, (m, err.decode()[-800:])
+
+
+def test_print_exc_shows_tracebacks_of_hook_exceptions(capsys):
+    from adaptdl_b200.utils import print_exc
+
+    @print_exc
+    def hook(x):
+        raise KeyError("lost in autograd")
+
+    with pytest.raises(KeyError):
+        hook(1)
+    assert "lost in autograd" in capsys.readouterr().err
+    assert hook.__name__ == "hook"
