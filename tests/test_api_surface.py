@@ -1,0 +1,110 @@
+"""The public API checklist of SURVEY.md §2.6: every name a user of the
+reference imports must exist here with a compatible signature."""
+import importlib
+import inspect
+
+import pytest
+
+SURFACE = {
+    "adaptdl_b200.env": [
+        "checkpoint_path", "share_path", "job_id", "master_addr",
+        "master_port", "replica_rank", "num_nodes", "num_replicas",
+        "num_restarts", "adaptdl_sched_version", "supervisor_url",
+        "from_ray"],
+    "adaptdl_b200.checkpoint": [
+        "State", "save_all_states", "save_state", "load_state"],
+    "adaptdl_b200.collective": [
+        "initialize", "allreduce", "allreduce_async", "broadcast",
+        "teardown"],
+    "adaptdl_b200.goodput": [
+        "PerfParams", "GradParams", "GoodputFunction", "fit_perf_params"],
+    "adaptdl_b200.sched_hints": [
+        "SCHED_HINTS", "PERF_PARAMS", "post_sched_hints"],
+    "adaptdl_b200.torch": [
+        "init_process_group", "AdaptiveDataParallel", "AdaptiveDataLoader",
+        "ElasticSampler", "current_dataloader", "Accumulator",
+        "remaining_epochs_until", "current_epoch", "finished_epochs"],
+    "adaptdl_b200.torch.data": [
+        "AdaptiveDataLoaderHelper", "AdaptiveDataLoaderMixin",
+        "AdaptiveDataLoader", "ElasticSampler", "current_dataloader"],
+    "adaptdl_b200.torch.iterator": ["AdaptiveBPTTIterator"],
+    "adaptdl_b200.torch.scaling_rules": [
+        "ScalingRuleBase", "AdaScale", "AdamScale", "LinearScale",
+        "SqrtScale", "LEGWScale"],
+    "adaptdl_b200.torch.gradient_noise_scale": [
+        "GradientNoiseScale", "AdamGradientNoiseScale"],
+    "adaptdl_b200.torch._metrics": [
+        "profile_step_start", "profile_step_commit", "profile_sync_time",
+        "update_grad_params", "update_progress", "get_progress",
+        "set_batch_size", "get_goodput_fn", "_fit_perf_params",
+        "_get_sched_hints", "_metrics_state"],
+    "adaptdl_b200.sched.policy": [
+        "PolluxPolicy", "JobInfo", "NodeInfo", "SpeedupFunction"],
+}
+
+MEMBERS = {
+    ("adaptdl_b200.checkpoint", "State"): ["save", "load", "sync"],
+    ("adaptdl_b200.goodput", "GoodputFunction"): [
+        "__call__", "evaluate", "throughput", "efficiency", "optimize"],
+    ("adaptdl_b200.torch", "AdaptiveDataParallel"): [
+        "forward", "gain", "to_tensorboard", "zero_grad"],
+    ("adaptdl_b200.torch", "AdaptiveDataLoader"): [
+        "autoscale_batch_size", "current_local_bsz", "current_batch_size",
+        "accumulation_steps", "training", "to_tensorboard"],
+    ("adaptdl_b200.torch", "ElasticSampler"): [
+        "__iter__", "__len__", "set_epoch"],
+    ("adaptdl_b200.torch", "Accumulator"): [
+        "__iadd__", "__isub__", "update", "subtract", "synchronized",
+        "__getitem__", "__setitem__", "__iter__", "__len__"],
+    ("adaptdl_b200.torch.scaling_rules", "ScalingRuleBase"): [
+        "scale_lr", "initialize", "step", "zero_grad"],
+    ("adaptdl_b200.torch.gradient_noise_scale", "GradientNoiseScale"): [
+        "sqr_avg", "var_avg", "gain", "get_progress", "set_progress",
+        "set_accum_scale", "reset_accumulation", "should_zero_grad",
+        "accum_scale", "accum_count", "raw_sqr_avg", "raw_var_avg"],
+    ("adaptdl_b200.torch.data", "AdaptiveDataLoaderHelper"): [
+        "autoscale_batch_size", "profile", "context", "skipdone",
+        "is_optim_step", "is_accum_step", "train", "to_tensorboard",
+        "current_local_bsz", "current_batch_size", "accumulation_steps",
+        "max_batch_size", "local_bsz_bounds", "current_index", "end_index"],
+}
+
+SIGNATURES = {
+    ("adaptdl_b200.torch", "init_process_group"):
+        ["backend", "init_method", "world_size", "rank"],
+    ("adaptdl_b200.torch", "AdaptiveDataParallel"):
+        ["model", "optimizer", "lr_scheduler", "mp_scaler", "scaling_rule",
+         "name"],
+    ("adaptdl_b200.checkpoint", "save_state"): ["state", "checkpoint_dir",
+                                                "sync"],
+    ("adaptdl_b200.collective", "initialize"):
+        ["master_addr", "master_port", "replica_rank", "num_replicas"],
+    ("adaptdl_b200.goodput", "GoodputFunction"):
+        ["perf_params", "grad_params", "init_batch_size"],
+    ("adaptdl_b200.sched_hints", "post_sched_hints"):
+        ["sched_hints", "job_key"],
+}
+
+
+@pytest.mark.parametrize("module", sorted(SURFACE))
+def test_module_exports(module):
+    mod = importlib.import_module(module)
+    missing = [name for name in SURFACE[module] if not hasattr(mod, name)]
+    assert not missing, (module, missing)
+
+
+@pytest.mark.parametrize("owner", sorted(MEMBERS))
+def test_class_members(owner):
+    cls = getattr(importlib.import_module(owner[0]), owner[1])
+    missing = [name for name in MEMBERS[owner] if not hasattr(cls, name)]
+    assert not missing, (owner, missing)
+
+
+@pytest.mark.parametrize("owner", sorted(SIGNATURES))
+def test_leading_parameters(owner):
+    obj = getattr(importlib.import_module(owner[0]), owner[1])
+    target = obj.__init__ if inspect.isclass(obj) else obj
+    params = [p for p in inspect.signature(target).parameters
+              if p != "self"]
+    want = SIGNATURES[owner]
+    assert params[:len(want)] == want, (owner, params)
