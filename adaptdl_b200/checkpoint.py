@@ -22,6 +22,7 @@ import shutil
 import weakref
 
 from adaptdl_b200 import env
+from adaptdl_b200.utils.trace import traced
 
 LOG = logging.getLogger(__name__)
 
@@ -158,6 +159,7 @@ def _resolve_checkpoint_dir(for_save):
     return env.checkpoint_path()
 
 
+@traced("checkpoint_save")
 def save_all_states():
     """Checkpoint every registered :class:`State`: ``sync()`` on all
     replicas, ``save()`` on rank 0 into a staging dir which is then renamed

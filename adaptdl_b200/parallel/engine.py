@@ -33,6 +33,7 @@ from adaptdl_b200._native import (
     CTL_RULE, CTL_RULE_ARG, CTL_ENABLED, RULE_ADASCALE, RULE_ADAMSCALE,
     RULE_LINEAR, RULE_SQRT, RULE_LEGW, check)
 from adaptdl_b200.parallel import layout
+from adaptdl_b200.utils.trace import traced
 
 _DTYPE_CODE = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
 
@@ -347,6 +348,7 @@ class DeviceEngine(object):
     # the fused optimizer step
     # ------------------------------------------------------------------
 
+    @traced("optimizer_step")
     def optimizer_step(self):
         self.sync_hyper()
         red = self.reducer

@@ -24,6 +24,7 @@ import logging
 import torch
 
 from adaptdl_b200.ops import _count as _ops_count
+from adaptdl_b200.utils.trace import traced
 
 
 LOG = logging.getLogger(__name__)
@@ -120,6 +121,7 @@ class GraphedTrainStep(object):
 
     # ------------------------------------------------------------------
 
+    @traced("graphed_step")
     def __call__(self, *inputs):
         if not self._can_graph():
             self.eager_steps += 1

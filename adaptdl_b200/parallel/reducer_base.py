@@ -38,6 +38,7 @@ from torch.autograd import Variable
 
 from adaptdl_b200.parallel import layout
 from adaptdl_b200.utils import print_exc
+from adaptdl_b200.utils.trace import traced
 
 LOG = logging.getLogger(__name__)
 
@@ -222,6 +223,7 @@ class GradReducer(object):
         """Forget the previous-step gradient (after a non-finite step)."""
         self._prev_valid = False
 
+    @traced("pop_stats")
     def pop_stats(self):
         """Statistics of the last synchronised backward (blocks until the
         device has produced them), or ``None``."""
@@ -262,6 +264,7 @@ class GradReducer(object):
         Variable._execution_engine.queue_callback(self._end_backward)
 
     @print_exc
+    @traced("backward_end")
     def _end_backward(self):
         # buckets whose parameters did not all receive gradients (unused
         # parameters) are flushed here, in order.
@@ -279,6 +282,7 @@ class GradReducer(object):
         if self._on_backward_end is not None:
             self._on_backward_end(self._sync)
 
+    @traced("bucket")
     def _process_bucket(self, arena, b):
         arena.done[b] = True
         bucket = arena.buckets[b]

@@ -28,6 +28,7 @@ from adaptdl_b200.torch.gradient_noise_scale import (
     AdamGradientNoiseScale, GradientNoiseScale)
 from adaptdl_b200.torch.scaling_rules import (
     AdaScale, AdamScale, ScalingRuleBase)
+from adaptdl_b200.utils.trace import traced
 
 LOG = logging.getLogger(__name__)
 
@@ -207,6 +208,7 @@ class AdaptiveDataParallel(torch.nn.Module):
             self.gns.set_accum_scale(accum_scale)
         self._sync_engine_ctrl()
 
+    @traced("forward")
     def forward(self, *args, **kwargs):
         self._pre_forward()
         if self.broadcast_buffers and self._world_size > 1 \

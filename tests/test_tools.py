@@ -62,3 +62,32 @@ def test_docs_reference_existing_paths():
     assert check_docs.repo_path("tests/test_ops.py::test_x") == \
         "tests/test_ops.py"
     assert check_docs.repo_path("torch/data.py") is None
+
+
+def test_host_trace_of_a_training_run(tmp_path):
+    """ADAPTDL_B200_TRACE writes a Chrome trace with the step-path spans;
+    without it the decorators are the identity."""
+    import json
+    import subprocess
+    import sys
+    from adaptdl_b200.utils import trace
+    assert not trace.ENABLED
+
+    def plain():
+        pass
+    assert trace.traced("x")(plain) is plain
+    assert trace.span("x") is trace.span("y")          # shared no-op
+
+    script = os.path.join(ROOT, "examples", "linear_regression", "main.py")
+    env = dict(os.environ, PYTHONPATH=ROOT, CUDA_VISIBLE_DEVICES="",
+               ADAPTDL_B200_TRACE=str(tmp_path / "trace"),
+               ADAPTDL_CHECKPOINT_PATH=str(tmp_path))
+    subprocess.run([sys.executable, script, "--epochs", "2", "--size",
+                    "512"], env=env, check=True, timeout=240,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    with open(str(tmp_path / "trace") + ".rank0.json") as f:
+        events = json.load(f)["traceEvents"]
+    names = {e["name"] for e in events if e["ph"] == "X"}
+    assert {"forward", "backward_end"} <= names, names
+    spans = [e for e in events if e["name"] == "forward"]
+    assert len(spans) >= 4 and all(e["dur"] >= 0 for e in spans)
