@@ -62,15 +62,33 @@ def _rank_and_crowding(F):
     return rank, crowd
 
 
+_HASH_SEED = np.random.default_rng(0x5EED)
+
+
+def _row_keys(X):
+    """One 64-bit key per row: a random linear form over the integers mod
+    2**64 (rows are ~100 KB at cluster scale, so hashing their bytes in
+    Python dominated the generation loop). Different rows collide with
+    probability ~2**-64."""
+    global _HASH_VECTOR
+    width = X.shape[1]
+    if _HASH_VECTOR is None or len(_HASH_VECTOR) < width:
+        _HASH_VECTOR = _HASH_SEED.integers(
+            1, np.iinfo(np.int64).max, size=max(width, 1024), dtype=np.int64)
+    with np.errstate(over="ignore"):
+        return X.astype(np.int64, copy=False) @ _HASH_VECTOR[:width]
+
+
+_HASH_VECTOR = None
+
+
 def _unique_rows(X, against=None):
     """Boolean mask of rows of ``X`` that are new (not in ``against`` and
     not repeated earlier in ``X``)."""
-    seen = set()
-    if against is not None:
-        seen.update(row.tobytes() for row in against)
+    seen = set(_row_keys(against).tolist()) if against is not None \
+        and len(against) else set()
     keep = np.zeros(len(X), dtype=bool)
-    for i, row in enumerate(X):
-        key = row.tobytes()
+    for i, key in enumerate(_row_keys(X).tolist()):
         if key not in seen:
             seen.add(key)
             keep[i] = True

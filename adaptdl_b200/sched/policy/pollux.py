@@ -30,6 +30,9 @@ POP_SIZE = 100
 GENERATIONS = 100
 RESTART_PENALTY = 0.1
 MIN_UTIL, MAX_UTIL = 0.35, 0.65
+# replica counts per (job, node): the population tensor is the bulk of the
+# memory traffic of a cycle, resource arithmetic is done in int64
+STATE_DTYPE = np.int32
 
 
 def _sorted_nodes(nodes):
@@ -41,8 +44,10 @@ def _sorted_nodes(nodes):
 class ClusterProblem(object):
     """Objectives and genetic operators for one optimisation cycle."""
 
-    def __init__(self, jobs, nodes, base_state, restart_penalty=RESTART_PENALTY):
+    def __init__(self, jobs, nodes, base_state,
+                 restart_penalty=RESTART_PENALTY, rng=None):
         assert base_state.shape == (len(jobs), len(nodes))
+        self._rng = np.random.default_rng() if rng is None else rng
         self.jobs, self.nodes = jobs, nodes
         self.base = base_state
         self.restart_penalty = restart_penalty
@@ -91,8 +96,12 @@ class ClusterProblem(object):
 
     def speedups(self, states):
         nodes_used = np.count_nonzero(states, axis=2)
-        replicas = states.sum(axis=2)
-        cols = [job.speedup_fn(nodes_used[:, j], replicas[:, j])
+        replicas = states.sum(axis=2, dtype=np.int64)
+        # SpeedupFunction objects answer from their table without the
+        # argument checking of the public call (tens of thousands of calls
+        # per cycle); any other callable is called as is
+        cols = [getattr(job.speedup_fn, "lookup", job.speedup_fn)(
+                    nodes_used[:, j], replicas[:, j])
                 for j, job in enumerate(self.jobs)]
         return np.stack(cols, axis=1).astype(float)
 
@@ -147,51 +156,90 @@ class ClusterProblem(object):
         """Re-draw a few entries within their feasible range; zero and
         non-zero entries of a row are equally likely to be touched."""
         states = np.asarray(states)
-        nonzero = np.count_nonzero(states, axis=2, keepdims=True)
-        zero = states.shape[2] - nonzero
-        with np.errstate(divide="ignore"):
-            prob = 1.0 / np.where(states > 0, nonzero, zero)
-        hit = rng.random(states.shape) < prob
+        width = states.shape[2]
+        positive = states > 0
+        nonzero = positive.sum(axis=2, keepdims=True, dtype=np.int32)
+        with np.errstate(divide="ignore"):            # per-row thresholds
+            p_nonzero = (1.0 / nonzero).astype(np.float32)
+            p_zero = (1.0 / (width - nonzero)).astype(np.float32)
+        hit = rng.random(states.shape, dtype=np.float32) < \
+            np.where(positive, p_nonzero, p_zero)
         # a mutation grows the cluster by a geometrically distributed number
         # of nodes (usually one): unrestricted hits in far columns would erase
         # every small-cluster candidate and the Pareto front would lose the
         # sizes that fit the real nodes
-        limit = self.cluster_sizes(states) + rng.geometric(
-            0.5, size=len(states))
-        hit &= np.arange(states.shape[2])[None, None, :] < \
-            limit[:, None, None]
-        draw = rng.integers(self.min_fill, self.max_fit + 1,
-                            size=states.shape)
-        out = np.where(hit, draw, states)
-        return np.maximum(out, self.min_fill)
+        ordinal = np.arange(width)
+        size = np.where(positive.any(axis=1), ordinal + 1, 0).max(axis=1)
+        limit = size + rng.geometric(0.5, size=len(states))
+        hit &= (ordinal[None, :] < limit[:, None])[:, None, :]
+        # new values are drawn only where a mutation happens (a few entries
+        # per row), not for the whole population tensor
+        p, j, n = np.nonzero(hit)
+        out = np.array(states, dtype=STATE_DTYPE, copy=True)
+        out[p, j, n] = rng.integers(self.min_fill[j, n],
+                                    self.max_fit[j, n] + 1)
+        return np.maximum(out, self.min_fill, out=out)
 
     def repair(self, states):
-        states = np.array(states, dtype=np.int64, copy=True)
-        P, J, N = states.shape
+        """Make every candidate feasible. The population tensor is
+        ``[P, J, N]`` with thousands of jobs x nodes entries per candidate
+        and this runs once per generation, so each rule touches only what it
+        must (rows over their cap, resources somebody requests) and works
+        resource by resource instead of on a ``[P, J, N, R]`` tensor."""
+        states = np.array(states, dtype=STATE_DTYPE, copy=True)
         # 1. non-preemptible jobs that already run keep their placement
         if len(self.pinned):
             states[:, self.pinned] = self.base[self.pinned]
-        # 2. a node hosts at most one multi-node job (first in job order)
-        spread = np.count_nonzero(states, axis=2) > 1          # [P, J]
-        on_node = (states > 0) & spread[:, :, None]
-        extra = on_node.cumsum(axis=1) > 1
-        states[extra & on_node] = 0
-        # 3. no more than max_replicas per job (trim in random node order)
-        order = np.argsort(np.random.random(states.shape), axis=2)
-        shuffled = np.take_along_axis(states, order, axis=2)
-        capped = np.minimum(shuffled.cumsum(axis=2), self.max_replicas)
-        shuffled = np.diff(capped, axis=2, prepend=0)
-        states = np.take_along_axis(shuffled, np.argsort(order, axis=2),
-                                    axis=2)
-        # 4. node capacities: jobs claim resources in priority order
-        demand = states[:, :, :, None] * self.job_res[None, :, None, :]
-        granted = np.minimum(demand.cumsum(axis=1), self.node_res)
-        granted = np.diff(granted, axis=1, prepend=0)          # [P,J,N,R]
-        per_type = np.where(self.job_res[None, :, None, :] > 0,
-                            granted // np.maximum(
-                                self.job_res[None, :, None, :], 1),
-                            np.iinfo(np.int64).max)
-        states = np.minimum(per_type.min(axis=3), states)
+        # 2. a node hosts at most one multi-node job (first in job order);
+        #    only nodes with several of them are looked at
+        positive = states > 0
+        spread = positive.sum(axis=2, dtype=np.int32) > 1       # [P, J]
+        positive &= spread[:, :, None]
+        crowd_p, crowd_n = np.nonzero(
+            positive.sum(axis=1, dtype=np.int32) > 1)
+        if len(crowd_p):
+            cols = positive[crowd_p, :, crowd_n]                # [K, J]
+            later = cols & (np.cumsum(cols, axis=1, dtype=np.int32) > 1)
+            kept = states[crowd_p, :, crowd_n]
+            kept[later] = 0
+            states[crowd_p, :, crowd_n] = kept
+        # 3. no more than max_replicas per job: rows above their cap are
+        #    trimmed in a random node order
+        over_p, over_j = np.nonzero(
+            states.sum(axis=2) > self.max_replicas[:, 0])
+        if len(over_p):
+            rows = states[over_p, over_j]                       # [K, N]
+            order = np.argsort(self._rng.random(rows.shape), axis=1)
+            shuffled = np.take_along_axis(rows, order, axis=1)
+            capped = np.minimum(shuffled.cumsum(axis=1),
+                                self.max_replicas[over_j])
+            trimmed = np.empty_like(rows)
+            np.put_along_axis(trimmed, order,
+                              np.diff(capped, axis=1, prepend=0), axis=1)
+            states[over_p, over_j] = trimmed
+        # 4. node capacities, one resource after the other: on every
+        #    oversubscribed (candidate, node) the jobs claim the resource in
+        #    priority order and keep what it can still grant. Columns within
+        #    capacity (most of them for every resource but the scarcest) are
+        #    not touched.
+        for r in range(self.job_res.shape[1]):
+            need = self.job_res[:, r]
+            if not need.any():
+                continue
+            capacity = self.node_res[:, r]
+            used = np.einsum("pjn,j->pn", states, need)
+            over_p, over_n = np.nonzero(used > capacity)
+            if not len(over_p):
+                continue
+            cols = states[over_p, :, over_n]                    # [K, J]
+            claim = cols * need
+            np.cumsum(claim, axis=1, out=claim)
+            np.minimum(claim, capacity[over_n][:, None], out=claim)
+            granted = np.diff(claim, axis=1, prepend=0)
+            granted //= np.maximum(need, 1)
+            states[over_p, :, over_n] = np.where(need > 0,
+                                                np.minimum(cols, granted),
+                                                cols)
         # 5. all-or-nothing below min_replicas
         short = states.sum(axis=2) < self.min_replicas
         states[short] = 0
@@ -338,7 +386,7 @@ class PolluxPolicy(object):
                                       base[None]])
         problem = ClusterProblem(list(jobs.values()),
                                  list(nodes.values()) + [node_template] * N,
-                                 base)
+                                 base, rng=self._rng)
         states, values = nsga2.minimize(problem, initial, self._pop_size,
                                         self._generations, self._rng)
         self._prev_states = states.copy()

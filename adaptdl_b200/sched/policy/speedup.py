@@ -55,6 +55,16 @@ class SpeedupFunction(object):
         self._cache[n[storable], r[storable]] = speedup[storable]
         return speedup[np.asarray(where).reshape(-1)]
 
+    def lookup(self, nodes, replicas):
+        """Speedups for flat integer arrays of VALID allocations (what the
+        policy's inner loop has): the table answer, computing what is
+        missing, without the checks and broadcasting of ``__call__``."""
+        result = self._lookup(nodes, replicas)
+        missing = result == _UNKNOWN
+        if missing.any():
+            result[missing] = self._compute(nodes[missing], replicas[missing])
+        return result
+
     def __call__(self, num_nodes, num_replicas):
         nodes_in, replicas_in = np.asarray(num_nodes), np.asarray(num_replicas)
         if np.any(nodes_in < 0) or np.any(nodes_in > replicas_in) or \

@@ -220,3 +220,100 @@ def test_starved_jobs_get_their_minimum_next_to_idle_capacity():
         for node in placement:
             used[node] = used.get(node, 0) + 1
     assert all(used[n] <= nodes[n].resources[gpu] for n in used)
+
+
+def _repair_oracle(problem, candidate):
+    """Straightforward per-candidate version of ClusterProblem.repair
+    (without the max_replicas rule, whose trimming order is random)."""
+    state = np.array(candidate, dtype=np.int64)
+    J, N = state.shape
+    for j in problem.pinned:
+        state[j] = problem.base[j]
+    multi = [np.count_nonzero(state[j]) > 1 for j in range(J)]
+    for n in range(N):
+        taken = False
+        for j in range(J):
+            if multi[j] and state[j, n] > 0:
+                if taken:
+                    state[j, n] = 0
+                taken = True
+    for r in range(problem.job_res.shape[1]):
+        for n in range(N):
+            need = problem.job_res[:, r]
+            if (state[:, n] * need).sum() <= problem.node_res[n, r]:
+                continue
+            left = problem.node_res[n, r]
+            for j in range(J):
+                if need[j] == 0:
+                    continue
+                grant = min(state[j, n] * need[j], left)
+                left -= grant
+                state[j, n] = min(state[j, n], grant // need[j])
+    for j in range(J):
+        if state[j].sum() < problem.min_replicas[j]:
+            state[j] = 0
+    return state
+
+
+def test_vectorised_repair_matches_a_plain_loop():
+    from adaptdl_b200.sched.policy.pollux import ClusterProblem
+    rng = np.random.default_rng(7)
+    J, N = 9, 6
+    jobs = [JobInfo({"gpu": int(rng.integers(1, 3)), "pods": 1,
+                     "mem": int(rng.integers(0, 3)) * (1 << 33)},
+                    lambda n, r: r, j, int(rng.integers(0, 3)), 1000,
+                    preemptible=bool(j % 4))
+            for j in range(J)]
+    nodes = [NodeInfo({"gpu": int(rng.integers(2, 9)), "pods": 5,
+                       "mem": 6 << 33}, False) for _ in range(N)]
+    base = np.zeros((J, N), dtype=np.int64)
+    base[0, 0] = 1                     # job 0 is not preemptible: pinned
+    problem = ClusterProblem(jobs, nodes, base, rng=rng)
+    assert list(problem.pinned) == [0]
+    population = rng.integers(0, 5, size=(40, J, N)) * \
+        (rng.random((40, J, N)) < 0.5)
+    fixed = problem.repair(population)
+    assert fixed.shape == population.shape
+    for got, candidate in zip(fixed, population):
+        np.testing.assert_array_equal(got, _repair_oracle(problem, candidate))
+    # idempotent, and every resource within capacity
+    np.testing.assert_array_equal(problem.repair(fixed), fixed)
+    use = np.einsum("pjn,jr->pnr", fixed, problem.job_res)
+    assert (use <= problem.node_res[None]).all()
+
+
+def test_repair_trims_rows_over_max_replicas():
+    from adaptdl_b200.sched.policy.pollux import ClusterProblem
+    rng = np.random.default_rng(3)
+    jobs = [JobInfo({"gpu": 1}, lambda n, r: r, j, 0, 3 + j) for j in range(4)]
+    nodes = [NodeInfo({"gpu": 64}, False) for _ in range(5)]
+    problem = ClusterProblem(jobs, nodes, np.zeros((4, 5), dtype=np.int64),
+                             rng=rng)
+    population = rng.integers(0, 4, size=(30, 4, 5))
+    fixed = problem.repair(population)
+    assert (fixed <= population).all() and (fixed >= 0).all()
+    caps = np.array([3, 4, 5, 6])
+    multi_node_rule = population.copy()          # rule 2 may empty entries
+    assert (fixed.sum(axis=2) <= caps).all()
+    # rows already within their cap and alone on their nodes are untouched
+    ok = population.sum(axis=2) <= caps
+    single = np.count_nonzero(population, axis=2) <= 1
+    keep = ok & single
+    np.testing.assert_array_equal(fixed[keep], multi_node_rule[keep])
+
+
+def test_speedup_lookup_equals_call():
+    fn = _speedup_fn()
+    nodes = np.array([1, 1, 2, 2, 4])
+    replicas = np.array([1, 3, 2, 8, 70])       # 70 is beyond the table
+    np.testing.assert_allclose(fn.lookup(nodes, replicas),
+                               fn(nodes, replicas))
+
+
+def test_row_keys_distinguish_rows():
+    rng = np.random.default_rng(0)
+    X = rng.integers(0, 9, size=(300, 500)).astype(np.int32)
+    X[17] = X[3]
+    keep = nsga2._unique_rows(X)
+    assert keep.sum() == 299 and not keep[17]
+    assert not nsga2._unique_rows(X[:5], against=X).any()

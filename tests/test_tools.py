@@ -91,3 +91,11 @@ def test_host_trace_of_a_training_run(tmp_path):
     assert {"forward", "backward_end"} <= names, names
     spans = [e for e in events if e["name"] == "forward"]
     assert len(spans) >= 4 and all(e["dur"] >= 0 for e in spans)
+
+
+def test_policy_bench_smoke():
+    bench = _load("policy_bench")
+    row = bench.run(num_jobs=6, num_nodes=2, gpus_per_node=4, cycles=2,
+                    seed=0)
+    assert row["gpus_allocated"] <= 8 and row["jobs_running"] >= 1
+    assert len(row["cycle_seconds"]) == 2 and row["sum_speedup"] > 0
