@@ -25,7 +25,9 @@ the reference pays every step.
 """
 
 import collections
+import logging
 import os
+import threading
 import time
 
 import numpy as np
@@ -38,6 +40,13 @@ from adaptdl_b200.sched_hints import SCHED_HINTS, PERF_PARAMS, \
 # seconds between performance fits / scheduling-hint reports (reference: 30 s,
 # torch/_metrics.py:63); overridable for tests and short jobs
 REPORT_PERIOD_S = float(os.environ.get("ADAPTDL_REPORT_PERIOD", "30"))
+# The periodic fit (an L-BFGS solve, ~0.2 s) and the hints PUT (up to its 10 s
+# timeout against a slow supervisor) run on a background thread so that
+# telemetry never stalls the step loop; ADAPTDL_ASYNC_REPORT=0 restores the
+# reference's inline behaviour.
+ASYNC_REPORT = os.environ.get("ADAPTDL_ASYNC_REPORT", "1") != "0"
+
+LOG = logging.getLogger(__name__)
 
 
 class _MetricsState(checkpoint.PickledFields):
@@ -71,6 +80,7 @@ class _OpenStep(object):
 _METRICS_STATE = None        # the singleton record (lazily loaded)
 _OPEN_STEP = None            # iteration in flight
 _PREV_REPORT = None          # host time of the last hints report
+_REPORT_THREAD = None        # background fit + report in flight
 _GRAD_PARAM_DICT = {}        # data-parallel instance -> (sqr, var)
 
 
@@ -121,10 +131,45 @@ def _maybe_report():
     if _PREV_REPORT is None:
         _PREV_REPORT = now
     due = now - _PREV_REPORT > REPORT_PERIOD_S
-    if due and env.replica_rank() == 0:
+    if not (due and env.replica_rank() == 0):
+        return
+    if ASYNC_REPORT:
+        _PREV_REPORT = now
+        _report_in_background()
+    else:
         _fit_perf_params()
         _report_sched_hints()
         _PREV_REPORT = time.time()
+
+
+def _report_in_background():
+    """Fit and report from a snapshot of the profile on a daemon thread; a
+    report still in flight (slow supervisor) is not doubled up."""
+    global _REPORT_THREAD
+    if _REPORT_THREAD is not None and _REPORT_THREAD.is_alive():
+        return
+    table = _profile_snapshot()
+    job = env.job_id()
+
+    def work():
+        try:
+            params = _fit_from(table)
+            if params is not None:
+                _metrics_state().perf_params = params
+            post_sched_hints(_build_sched_hints(
+                [key for key, _ in table]), job)
+        except Exception:  # noqa: BLE001 - telemetry must not kill a job
+            LOG.exception("background performance fit / report failed")
+    _REPORT_THREAD = threading.Thread(target=work, daemon=True,
+                                      name="adaptdl-report")
+    _REPORT_THREAD.start()
+
+
+def wait_for_report(timeout=None):
+    """Join the background report, if any (tests, orderly shutdown)."""
+    thread = _REPORT_THREAD
+    if thread is not None:
+        thread.join(timeout)
 
 
 # ---------------------------------------------------------------------------
@@ -172,14 +217,18 @@ def get_goodput_fn():
 # performance fit and scheduler hints
 # ---------------------------------------------------------------------------
 
-def _fit_perf_params():
-    """Turn the profile table into per-configuration mean step times and fit
-    the throughput model to them."""
-    record = _metrics_state()
-    table = [(key, row) for key, row in record.profile.items()
-             if row.get("optim_count")]
+def _profile_snapshot():
+    """``[(key, counters)]`` of every configuration with at least one
+    optimisation step, copied so that it can be read off-thread."""
+    return [(key, dict(row)) for key, row in
+            list(_metrics_state().profile.items()) if row.get("optim_count")]
+
+
+def _fit_from(table):
+    """Turn a profile snapshot into per-configuration mean step times and
+    fit the throughput model to them (``None`` for an empty table)."""
     if not table:
-        return
+        return None
     nodes, replicas, atomic = (np.array(col) for col in
                                zip(*(key for key, _ in table)))
 
@@ -193,8 +242,14 @@ def _fit_perf_params():
     # an optimisation step minus its synchronisation costs about what an
     # accumulation step costs: pool both kinds of sample for the local time
     local_mean = (accum_total + optim_total - sync_total) / (accum_n + optim_n)
-    record.perf_params = fit_perf_params(nodes, replicas, atomic, local_mean,
-                                         optim_total / optim_n)
+    return fit_perf_params(nodes, replicas, atomic, local_mean,
+                           optim_total / optim_n)
+
+
+def _fit_perf_params():
+    params = _fit_from(_profile_snapshot())
+    if params is not None:
+        _metrics_state().perf_params = params
 
 
 def _get_sched_hints():
@@ -207,15 +262,17 @@ def _get_sched_hints():
     return record
 
 
-def _build_sched_hints():
+def _build_sched_hints(profile_keys=None):
     record = _metrics_state()
+    if profile_keys is None:
+        profile_keys = list(record.profile)
     hints = dict(SCHED_HINTS)
     hints.update(
         initBatchSize=record.init_batch_size,
         maxBatchSize=record.max_batch_size,
         localBszBounds=record.local_bsz_bounds,
         gradientAccumulation=record.gradient_accumulation,
-        maxProfiledReplicas=max(key[1] for key in record.profile))
+        maxProfiledReplicas=max(key[1] for key in profile_keys))
     if record.perf_params is not None:
         hints["perfParams"] = dict(zip(
             PERF_PARAMS.keys(), (float(v) for v in record.perf_params)))
@@ -232,5 +289,8 @@ def _report_sched_hints():
 
 def _reset_for_tests():
     global _METRICS_STATE, _OPEN_STEP, _PREV_REPORT
+    wait_for_report(5.0)
+    if _METRICS_STATE is not None:
+        _METRICS_STATE.unregister()
     _METRICS_STATE = _OPEN_STEP = _PREV_REPORT = None
     _GRAD_PARAM_DICT.clear()

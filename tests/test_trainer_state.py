@@ -345,3 +345,48 @@ def test_bptt_iterator():
         # rows 10..98 in windows of 5 shared by 2 replicas -> 9 steps each
         assert idx == 8 and seen == 9
     return 0
+
+
+def test_periodic_report_does_not_stall_the_step_loop(monkeypatch):
+    """The fit and the hints PUT run off-thread: a slow supervisor must not
+    cost the training loop anything (the reference does both inline)."""
+    import time
+    from adaptdl_b200 import checkpoint
+    from adaptdl_b200.torch import _metrics
+    _metrics._reset_for_tests()
+    stale = checkpoint._NAMES_TO_STATES.get("adaptdl-metrics")
+    if stale is not None:          # left behind by an in-process test
+        stale.unregister()
+    posted = []
+
+    def slow_post(hints, job):
+        time.sleep(0.5)
+        posted.append(hints)
+    monkeypatch.setattr(_metrics, "post_sched_hints", slow_post)
+    monkeypatch.setattr(_metrics, "REPORT_PERIOD_S", 0.0)
+    monkeypatch.setattr(_metrics, "ASYNC_REPORT", True)
+    _metrics.set_batch_size(32, 256, (8, 64), False)
+    _metrics.update_grad_params("k", 1.0, 2.0)
+    try:
+        slowest = 0.0
+        for step in range(6):
+            _metrics.profile_step_start(16)
+            began = time.time()
+            _metrics.profile_step_commit(step_time=0.01)
+            slowest = max(slowest, time.time() - began)
+            time.sleep(0.01)
+        assert slowest < 0.25, slowest          # never waited for the PUT
+        _metrics.wait_for_report(10.0)
+        assert posted and posted[0]["initBatchSize"] == 32
+        assert posted[0]["maxProfiledReplicas"] == 1
+        assert _metrics._metrics_state().perf_params is not None
+        assert len(posted) <= 2                  # in-flight reports not doubled
+        # the inline mode still works
+        monkeypatch.setattr(_metrics, "ASYNC_REPORT", False)
+        count = len(posted)
+        _metrics.profile_step_start(16)
+        _metrics.profile_step_commit(step_time=0.01)
+        assert len(posted) == count + 1
+    finally:
+        _metrics.wait_for_report(10.0)
+        _metrics._reset_for_tests()
