@@ -31,7 +31,6 @@ def _build():
         return _CLASSES
     from adaptdl_b200.ray import require_ray
     require_ray()
-    from ray import tune
     from ray.tune.experiment import Trial
     from ray.tune.schedulers import TrialScheduler
 

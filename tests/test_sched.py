@@ -4,8 +4,6 @@ endpoints, cluster expander."""
 import asyncio
 import json
 
-import pytest
-
 from adaptdl_b200.sched import resources
 from adaptdl_b200.sched.allocator import AdaptDLAllocator, job_info_from
 from adaptdl_b200.sched.cluster_expander import ClusterExpander
