@@ -17,6 +17,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from adaptdl_b200.ops.bn_act import BatchNormAct2d
+from adaptdl_b200.ops.strided_conv import strided_conv3x3
 
 __all__ = ["ResNet", "resnet18", "resnet34", "resnet50", "resnet101",
            "resnet152"]
@@ -63,7 +64,11 @@ class ResidualBlock(nn.Module):
             conv = getattr(self, "conv{}".format(i))
             norm = getattr(self, "bn{}".format(i))
             last = i == self.depth
-            out = norm(conv(out), residual=skip if last else None)
+            # stride-2 3x3: optional phase-decomposed data gradient
+            # (ops/strided_conv.py, ADAPTDL_B200_PHASE_DGRAD=1)
+            out = strided_conv3x3(out, conv) if conv.stride == (2, 2) \
+                else conv(out)
+            out = norm(out, residual=skip if last else None)
         return out
 
 

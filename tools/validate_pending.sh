@@ -25,7 +25,8 @@ echo "== 3. headline bench: defaults vs padded stem vs BN bit-mask"
 timeout 300 python bench.py --steps 40 --warmup 8 > "$OUT/bench_n1_default.log" 2>&1
 ADAPTDL_B200_PAD_STEM=1 timeout 300 python bench.py --steps 40 --warmup 8 > "$OUT/bench_n1_padstem.log" 2>&1
 ADAPTDL_B200_BN_BITMASK=1 timeout 300 python bench.py --steps 40 --warmup 8 > "$OUT/bench_n1_bitmask.log" 2>&1
-for f in default padstem bitmask; do
+ADAPTDL_B200_PHASE_DGRAD=1 timeout 300 python bench.py --steps 40 --warmup 8 > "$OUT/bench_n1_phasedgrad.log" 2>&1
+for f in default padstem bitmask phasedgrad; do
   python - "$OUT/bench_n1_$f.log" <<'PY'
 import json, sys
 for line in open(sys.argv[1]):
