@@ -527,7 +527,7 @@ def test_tcgen05_linear_gelu_autograd_matches_torch():
 
 # experimental code paths: written after round 1's GPU budget was spent, so
 # their tests have never run on hardware and only run on request:
-#   ADAPTDL_B200_TEST_EXPERIMENTAL=1 python -m pytest tests -m gpu -k "layer_norm or bitmask"
+#   ADAPTDL_B200_TEST_EXPERIMENTAL=1 python -m pytest tests -m gpu -k "layer_norm or bitmask or phase_dgrad"
 _EXPERIMENTAL = pytest.mark.skipif(
     os.environ.get("ADAPTDL_B200_TEST_EXPERIMENTAL") != "1",
     reason="experimental op, not validated on hardware yet "
@@ -722,3 +722,45 @@ def test_fused_dropout_add_layer_norm_random_mask_and_eval(monkeypatch):
     c = dropout_add_layer_norm(x, h, w, b, 0.3, True)
     assert not torch.equal(a, c)            # fresh keep-mask per call
     assert torch.isfinite(a).all()
+
+
+# Phase-decomposed strided data gradient (ops/strided_conv.py): PyTorch-level
+# (four cuDNN convolutions), verified on CPU; gated until it has run on a GPU.
+#   ADAPTDL_B200_TEST_EXPERIMENTAL=1 python -m pytest tests -m gpu -k phase_dgrad
+@_EXPERIMENTAL
+@pytest.mark.gpu
+def test_phase_dgrad_on_gpu_eager_and_graph_captured(monkeypatch):
+    from adaptdl_b200.ops import strided_conv
+    monkeypatch.setenv("ADAPTDL_B200_PHASE_DGRAD", "1")
+    dev = torch.device("cuda:0")
+    torch.manual_seed(5)
+    conv = torch.nn.Conv2d(64, 128, 3, 2, 1, bias=False).to(dev).to(
+        memory_format=torch.channels_last)
+    x = torch.randn(32, 64, 32, 32, device=dev).contiguous(
+        memory_format=torch.channels_last).requires_grad_(True)
+
+    def step(fn):
+        x.grad = conv.weight.grad = None
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = fn(x)
+        out.float().square().mean().backward()
+        return x.grad.clone(), conv.weight.grad.clone()
+
+    want = step(conv)
+    got = step(lambda t: strided_conv.strided_conv3x3(t, conv))
+    for a, b in zip(got, want):
+        assert (a - b).norm() <= 2e-2 * b.norm()
+    # the backward must be capturable (no host-side index tensors)
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            step(lambda t: strided_conv.strided_conv3x3(t, conv))
+        graph = torch.cuda.CUDAGraph()
+        x.grad = conv.weight.grad = None
+        with torch.cuda.graph(graph, stream=side):
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                out = strided_conv.strided_conv3x3(x, conv)
+            out.float().square().mean().backward()
+        graph.replay()
+    torch.cuda.synchronize()
+    assert (x.grad - want[0]).norm() <= 2e-2 * want[0].norm()

@@ -14,7 +14,7 @@ NGPU=$(python -c "import torch; print(torch.cuda.device_count())")
 
 echo "== 1. experimental numerics tests (LayerNorm op, BN bit-mask)"
 ADAPTDL_B200_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_kernels.py -q -m gpu \
-    -k "layer_norm or bitmask" > "$OUT/experimental_tests.log" 2>&1
+    -k "layer_norm or bitmask or phase_dgrad" > "$OUT/experimental_tests.log" 2>&1
 tail -3 "$OUT/experimental_tests.log"
 
 echo "== 2. full GPU suite (defaults)"
