@@ -3,6 +3,10 @@ sm_100a kernel over NVLink peer memory, or stock torch collectives), symmetric
 memory, topology discovery, CUDA-graph step capture."""
 
 
+import logging
+
+LOG = logging.getLogger(__name__)
+
 # Default bucket caps. The fused kernels cost ~20 us per bucket on the comm
 # stream (nothing on the host inside a CUDA graph), so smaller buckets than
 # DDP's are plausible: with 25 MB, ResNet-18's 22 MB of bf16 gradients are one
@@ -13,6 +17,54 @@ memory, topology discovery, CUDA-graph step capture."""
 # stays at the value every published number was taken with.
 CUDA_BUCKET_CAP_MB = 25
 TORCH_BUCKET_CAP_MB = 25
+
+
+def choose_backend(backend, device_type, num_nodes, force_torch=False):
+    """``"cuda"`` or ``"torch"`` for a ``backend`` request (see
+    :func:`make_reducer`). The fused kernels reduce through peer-mapped
+    memory, which exists inside one NVLink / NVSwitch domain only: a job whose
+    replicas span several nodes (``ADAPTDL_NUM_NODES`` > 1, as the cluster
+    scheduler may well allocate) uses NCCL through the torch reducer in
+    ``auto`` mode. (A two-level reducer -- fused inside the node, NCCL across
+    -- is the planned successor.)"""
+    if backend == "torch":
+        return "torch"
+    if backend == "cuda":
+        if num_nodes > 1:
+            raise ValueError(
+                "reducer='cuda' needs all replicas in one NVLink domain, "
+                "but the job spans {} nodes".format(num_nodes))
+        return "cuda"
+    if backend != "auto":
+        raise ValueError("unknown reducer backend {!r}".format(backend))
+    if device_type != "cuda" or force_torch:
+        return "torch"
+    if num_nodes > 1:
+        LOG.info("replicas span %d nodes: gradients are reduced with NCCL "
+                 "(the fused peer-memory kernels are single-node)", num_nodes)
+        return "torch"
+    return "cuda"
+
+
+def hosts_spanned(world_size, process_group=None):
+    """How many hosts the replicas run on: ``ADAPTDL_NUM_NODES`` when the
+    launcher states it (the cluster scheduler, the local launchers and
+    ``bench.py`` all do), otherwise the number of distinct host names among
+    the ranks (the reference's default of "one node per replica" would send
+    every hand-launched single-box job to NCCL)."""
+    import os
+    stated = os.environ.get("ADAPTDL_NUM_NODES")
+    if stated:
+        return int(stated)
+    if world_size <= 1:
+        return 1
+    import socket
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return 1
+    names = [None] * dist.get_world_size(process_group)
+    dist.all_gather_object(names, socket.gethostname(), group=process_group)
+    return len(set(names))
 
 
 def make_reducer(param_groups, world_size, rank, should_sync,
@@ -36,9 +88,10 @@ def make_reducer(param_groups, world_size, rank, should_sync,
             break
         if device is not None:
             break
-    want_cuda = backend == "cuda" or (
-        backend == "auto" and device is not None and device.type == "cuda"
-        and not env.force_torch_reducer())
+    want_cuda = choose_backend(
+        backend, device.type if device is not None else None,
+        hosts_spanned(world_size, process_group),
+        env.force_torch_reducer()) == "cuda"
     if want_cuda:
         try:
             from adaptdl_b200.parallel.reducer_cuda import CudaGradReducer

@@ -95,6 +95,7 @@ def main():
 
     # end-to-end through the public API
     os.environ["ADAPTDL_NUM_REPLICAS"] = str(world)
+    os.environ["ADAPTDL_NUM_NODES"] = "1"
     os.environ["ADAPTDL_REPLICA_RANK"] = str(rank)
     import adaptdl_b200.torch as adl
     from adaptdl_b200 import collective

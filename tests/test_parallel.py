@@ -184,3 +184,29 @@ def test_accumulation_through_dataloader():
     assert updates == 3
     assert net.gns._state["biased"] is False
     return 0
+
+
+def test_reducer_backend_choice():
+    from adaptdl_b200.parallel import choose_backend
+    assert choose_backend("auto", "cuda", 1) == "cuda"
+    assert choose_backend("auto", "cpu", 1) == "torch"
+    assert choose_backend("auto", "cuda", 1, force_torch=True) == "torch"
+    # peer-mapped memory stops at the node boundary
+    assert choose_backend("auto", "cuda", 2) == "torch"
+    assert choose_backend("torch", "cuda", 1) == "torch"
+    assert choose_backend("cuda", "cuda", 1) == "cuda"
+    with pytest.raises(ValueError, match="spans 4 nodes"):
+        choose_backend("cuda", "cuda", 4)
+    with pytest.raises(ValueError, match="unknown"):
+        choose_backend("nccl", "cuda", 1)
+
+
+def test_hosts_spanned(monkeypatch):
+    from adaptdl_b200.parallel import hosts_spanned
+    monkeypatch.setenv("ADAPTDL_NUM_NODES", "3")
+    assert hosts_spanned(8) == 3
+    monkeypatch.delenv("ADAPTDL_NUM_NODES")
+    assert hosts_spanned(1) == 1
+    # no launcher statement, no process group yet: assume one box instead of
+    # the reference's "one node per replica"
+    assert hosts_spanned(4) == 1
