@@ -40,24 +40,31 @@ def choose_backend(backend, device_type, num_nodes, force_torch=False):
     if device_type != "cuda" or force_torch:
         return "torch"
     if num_nodes > 1:
-        LOG.info("replicas span %d nodes: gradients are reduced with NCCL "
-                 "(the fused peer-memory kernels are single-node)", num_nodes)
+        LOG.info("replicas run in %d separate hosts / containers: gradients "
+                 "are reduced with NCCL (the fused peer-memory kernels need "
+                 "all ranks in one)", num_nodes)
         return "torch"
     return "cuda"
 
 
 def hosts_spanned(world_size, process_group=None):
-    """How many hosts the replicas run on: ``ADAPTDL_NUM_NODES`` when the
-    launcher states it (the cluster scheduler, the local launchers and
-    ``bench.py`` all do), otherwise the number of distinct host names among
-    the ranks (the reference's default of "one node per replica" would send
-    every hand-launched single-box job to NCCL)."""
+    """How many separate memory-sharing domains the replicas run in (1 =
+    the fused peer-memory path is possible).
+
+    Peer mappings are set up by passing file descriptors between the rank
+    processes over unix sockets, so the ranks must share a host AND a
+    container: ``ADAPTDL_NUM_NODES`` > 1 settles it; otherwise the ranks
+    compare host names (every Kubernetes pod has its own, even on one node --
+    one-GPU pods therefore reduce with NCCL; run one multi-GPU pod per node,
+    or the single-box launchers, to get the fused path). The reference's
+    default of "one node per replica" when the variable is unset is NOT used:
+    it would send every hand-launched single-box job to NCCL."""
     import os
-    stated = os.environ.get("ADAPTDL_NUM_NODES")
-    if stated:
-        return int(stated)
+    stated = int(os.environ.get("ADAPTDL_NUM_NODES") or 0)
     if world_size <= 1:
         return 1
+    if stated > 1:
+        return stated
     import socket
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()):

@@ -205,8 +205,28 @@ def test_hosts_spanned(monkeypatch):
     from adaptdl_b200.parallel import hosts_spanned
     monkeypatch.setenv("ADAPTDL_NUM_NODES", "3")
     assert hosts_spanned(8) == 3
+    assert hosts_spanned(1) == 1
+    monkeypatch.setenv("ADAPTDL_NUM_NODES", "1")
+    assert hosts_spanned(4) == 1           # no process group: nothing to ask
     monkeypatch.delenv("ADAPTDL_NUM_NODES")
     assert hosts_spanned(1) == 1
     # no launcher statement, no process group yet: assume one box instead of
     # the reference's "one node per replica"
     assert hosts_spanned(4) == 1
+
+
+@elastic_multiprocessing
+def test_ranks_compare_host_names_before_choosing_the_fused_path():
+    import socket
+    import adaptdl_b200.torch as adl
+    from adaptdl_b200 import env
+    from adaptdl_b200.parallel import choose_backend, hosts_spanned
+    if env.num_restarts() == 0:
+        return 2
+    adl.init_process_group("gloo")
+    assert hosts_spanned(2) == 1                 # same box, same container
+    if env.replica_rank() == 1:                  # "another pod"
+        socket.gethostname = lambda: "job-0-1"
+    assert hosts_spanned(2) == 2
+    assert choose_backend("auto", "cuda", hosts_spanned(2)) == "torch"
+    return 0
