@@ -134,7 +134,11 @@ class AdaptDLAllocator(object):
         jobs, previous = await self.find_jobs_and_allocations()
         known = list(jobs)
         start = time.time()
-        allocations = self.allocate(jobs, nodes, previous, template)
+        # the genetic search takes seconds on a big cluster: keep it off the
+        # event loop so that watches, the fast path's API calls and the
+        # cluster expander keep being served meanwhile
+        allocations = await asyncio.get_running_loop().run_in_executor(
+            None, self.allocate, jobs, nodes, previous, template)
         elapsed = time.time() - start
         LOG.info("allocations (%.3f s): %s", elapsed, allocations)
         await self.update_allocations(allocations)

@@ -455,3 +455,33 @@ def test_dashboard_only_plots_series_the_code_exports():
             plotted.update(re.findall(r"adaptdl_[a-z_]+", target["expr"]))
     assert plotted and plotted <= exported, plotted - exported
     metrics.forget_job("ns", "dash")
+
+
+def test_allocation_cycle_does_not_block_the_event_loop():
+    import time
+
+    class SlowPolicy(object):
+        def optimize(self, jobs, nodes, previous, template):
+            time.sleep(0.6)                       # a big cluster's search
+            return {key: [next(iter(nodes))] for key in jobs}, 1
+
+    async def scenario():
+        cluster = InMemoryCluster()
+        cluster.add_node("n0", {"nvidia.com/gpu": 4, "pods": 32})
+        cluster.add_job("ns", "a", {"template": TEMPLATE, "maxReplicas": 4})
+        alloc = AdaptDLAllocator(cluster, None, SlowPolicy())
+        ticks = []
+
+        async def heartbeat():
+            while True:
+                ticks.append(time.time())
+                await asyncio.sleep(0.05)
+        beat = asyncio.ensure_future(heartbeat())
+        began = time.time()
+        allocations = await alloc.optimize_all()
+        took = time.time() - began
+        beat.cancel()
+        assert allocations == {("ns", "a"): ["n0"]}
+        during = [t for t in ticks if began < t < began + took]
+        assert took >= 0.6 and len(during) >= 5, (took, len(during))
+    run(scenario())
