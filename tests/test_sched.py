@@ -467,7 +467,8 @@ def test_allocation_cycle_does_not_block_the_event_loop():
 
     async def scenario():
         cluster = InMemoryCluster()
-        cluster.add_node("n0", {"nvidia.com/gpu": 4, "pods": 32})
+        cluster.add_node("n0", {"nvidia.com/gpu": 4, "pods": 32,
+                                "cpu": "16", "memory": "64Gi"})
         cluster.add_job("ns", "a", {"template": TEMPLATE, "maxReplicas": 4})
         alloc = AdaptDLAllocator(cluster, None, SlowPolicy())
         ticks = []
