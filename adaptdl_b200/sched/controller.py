@@ -27,7 +27,8 @@ from datetime import datetime, timezone
 
 from adaptdl_b200.sched import config, k8s_templates as templates
 from adaptdl_b200.sched.kube import ApiError, NotFound
-from adaptdl_b200.sched.resources import set_default_resources
+from adaptdl_b200.sched.resources import (scale_container_resources,
+                                          set_default_resources)
 
 LOG = logging.getLogger(__name__)
 
@@ -89,6 +90,42 @@ def _exited_143(pod):
     return False
 
 
+def _local_replicas(pod):
+    """Replicas hosted by ``pod`` (1 unless the job uses one pod per node)."""
+    return int(pod["metadata"].get("annotations", {}).get(
+        "adaptdl/local-replicas", 1))
+
+
+def count_replicas(pods):
+    return sum(_local_replicas(pod) for pod in pods)
+
+
+def canonical_allocation(allocation, pod_per_node=False):
+    """The allocation in rank order. With one pod per node the replicas of
+    a node take consecutive ranks (nodes in order of first appearance), so
+    that each pod hosts one contiguous rank range."""
+    if not pod_per_node:
+        return list(allocation)
+    order = {}
+    for node in allocation:
+        order.setdefault(node, len(order))
+    return sorted(allocation, key=order.__getitem__)
+
+
+def plan_pods(allocation, pod_per_node=False):
+    """``[(first_rank, node, replicas)]``, one entry per pod to create."""
+    ranked = canonical_allocation(allocation, pod_per_node)
+    if not pod_per_node:
+        return [(rank, node, 1) for rank, node in enumerate(ranked)]
+    plan = []
+    for rank, node in enumerate(ranked):
+        if plan and plan[-1][1] == node:
+            plan[-1] = (plan[-1][0], node, plan[-1][2] + 1)
+        else:
+            plan.append((rank, node, 1))
+    return plan
+
+
 def validate_pods(pods):
     """``None`` if the job's pods form one consistent group, else the
     failure message."""
@@ -98,7 +135,7 @@ def validate_pods(pods):
         try:
             groups.add(int(_ann(pod, "group")))
             replicas.add(int(_ann(pod, "replicas")))
-            ranks.append(int(_ann(pod, "rank")))
+            ranks.append(int(_ann(pod, "rank")) + _local_replicas(pod) - 1)
             node = _ann(pod, "node")
         except (KeyError, ValueError):
             return "invalid annotations for pod {}".format(name)
@@ -118,7 +155,8 @@ def detect_completion(pods, preemptible):
     if not pods:
         return {}
     want = {int(_ann(p, "replicas")) for p in pods}
-    if all(_phase(p) == "Succeeded" for p in pods) and want == {len(pods)}:
+    if all(_phase(p) == "Succeeded" for p in pods) and \
+            want == {count_replicas(pods)}:
         return {"phase": "Succeeded"}
     for pod in pods:
         if _phase(pod) == "Unknown":
@@ -137,13 +175,18 @@ def detect_completion(pods, preemptible):
     return {}
 
 
-def detect_restart(pods, allocation):
+def detect_restart(pods, allocation, pod_per_node=False):
     """True if the running pods no longer match ``status.allocation``."""
+    ranked = canonical_allocation(allocation, pod_per_node)
     for pod in pods:
         replicas, rank = int(_ann(pod, "replicas")), int(_ann(pod, "rank"))
-        if replicas != len(allocation) or _ann(pod, "node") != \
-                allocation[rank]:
+        hosted = ranked[rank:rank + _local_replicas(pod)] \
+            if replicas == len(ranked) else []
+        if len(hosted) != _local_replicas(pod) or \
+                any(node != _ann(pod, "node") for node in hosted):
             return True
+        if pod_per_node and ranked.count(_ann(pod, "node")) != len(hosted):
+            return True                  # the node's share changed
     return False
 
 
@@ -184,10 +227,16 @@ def _apply_json_patch(doc, patch):
 
 
 def build_pod(job_metadata, pod_template, allocation, group, rank,
-              node_hostname):
-    """Manifest of replica ``rank`` of restart generation ``group``: pinned
-    to its node, memory-backed ``/dev/shm``, and the ``ADAPTDL_*``
-    environment the trainer reads (``adaptdl_b200.env``)."""
+              node_hostname, local_replicas=1):
+    """Manifest of the pod hosting replicas ``rank .. rank+local_replicas-1``
+    of restart generation ``group``: pinned to its node, memory-backed
+    ``/dev/shm``, and the ``ADAPTDL_*`` environment the trainer reads
+    (``adaptdl_b200.env``). With ``local_replicas`` > 1 (``spec.podPerNode``)
+    every container's requests and limits are multiplied and
+    ``ADAPTDL_LOCAL_REPLICAS`` tells ``python -m adaptdl_b200.launch`` how
+    many rank processes to start -- all the job's GPUs on the node are then
+    inside ONE container, which is what the peer-memory gradient reducer
+    needs (one-GPU pods fall back to NCCL)."""
     pod = copy.deepcopy(pod_template)
     pod["apiVersion"], pod["kind"] = "v1", "Pod"
     meta = pod.setdefault("metadata", {})
@@ -201,6 +250,8 @@ def build_pod(job_metadata, pod_template, allocation, group, rank,
         "adaptdl/replicas": str(len(allocation)),
         "adaptdl/group": str(group), "adaptdl/rank": str(rank),
         "adaptdl/node": allocation[rank]})
+    if local_replicas != 1:
+        meta["annotations"]["adaptdl/local-replicas"] = str(local_replicas)
     spec = pod["spec"]
     spec["hostname"] = "{}-{}-{}".format(job_metadata["name"], group, rank)
     spec.setdefault("nodeSelector", {})["kubernetes.io/hostname"] = \
@@ -220,7 +271,10 @@ def build_pod(job_metadata, pod_template, allocation, group, rank,
         ("ADAPTDL_SUPERVISOR_URL", config.get_supervisor_url()),
         ("ADAPTDL_SCHED_VERSION", config.get_adaptdl_version()),
     ]
+    if local_replicas != 1:
+        env.append(("ADAPTDL_LOCAL_REPLICAS", str(local_replicas)))
     for container in spec["containers"]:
+        scale_container_resources(container, local_replicas)
         container.setdefault("volumeMounts", []).append(
             {"name": "adaptdl-shm", "mountPath": "/dev/shm"})
         cenv = container.setdefault("env", [])
@@ -262,6 +316,8 @@ def reconcile(job, pods, now=None):
     phase = new.setdefault("phase", "Pending")
     replicas = new.get("replicas") or 0
     preemptible = job["spec"].get("preemptible", True)
+    per_node = bool(job["spec"].get("podPerNode", False))
+    want_pods = len(plan_pods(allocation, per_node))
     completion = detect_completion(pods, preemptible) \
         if phase not in ("Succeeded", "Failed") else {}
     if completion:
@@ -275,18 +331,19 @@ def reconcile(job, pods, now=None):
         if allocation and not pods:
             new["phase"] = "Starting"
     elif phase == "Starting":
-        if not allocation or (count_scheduled_pods(pods) != replicas
-                              and detect_restart(pods, allocation)):
+        if not allocation or (count_scheduled_pods(pods) != want_pods
+                              and detect_restart(pods, allocation,
+                                                 per_node)):
             new["phase"] = "Stopping"
         elif not pods:
             new["group"] = new.get("group", -1) + 1
             actions.append(("create_pods", new["group"], list(allocation)))
-        elif len(pods) != replicas:
+        elif len(pods) != want_pods:
             new["phase"] = "Stopping"
-        elif count_ready_pods(pods) == replicas:
+        elif count_ready_pods(pods) == want_pods:
             new["phase"] = "Running"
     elif phase == "Running":
-        if not pods or detect_restart(pods, allocation):
+        if not pods or detect_restart(pods, allocation, per_node):
             new["phase"] = "Stopping"
     elif phase == "Stopping":
         if pods:
@@ -295,7 +352,8 @@ def reconcile(job, pods, now=None):
             new["phase"] = "Pending"
     if allocation:
         new["replicas"] = len(allocation)
-        new["readyReplicas"] = count_ready_pods(pods)
+        new["readyReplicas"] = count_replicas(
+            [p for p in pods if count_ready_pods([p])])
     else:
         new["allocation"] = new["replicas"] = new["readyReplicas"] = None
     patch = {k: v for k, v in new.items() if old.get(k) != v}
@@ -369,12 +427,14 @@ class AdaptDLController(object):
         meta = job["metadata"]
         created = []
         try:
-            for rank in range(len(allocation)):
-                node = await self._cluster.read_node(allocation[rank])
+            per_node = bool(job["spec"].get("podPerNode", False))
+            ranked = canonical_allocation(allocation, per_node)
+            for rank, node_name, count in plan_pods(allocation, per_node):
+                node = await self._cluster.read_node(node_name)
                 hostname = node["metadata"].get("labels", {}).get(
                     "kubernetes.io/hostname", node["metadata"]["name"])
-                pod = build_pod(meta, job["spec"]["template"], allocation,
-                                group, rank, hostname)
+                pod = build_pod(meta, job["spec"]["template"], ranked,
+                                group, rank, hostname, count)
                 created.append(await self._cluster.create_pod(
                     meta["namespace"], pod))
         except (ApiError, NotFound) as exc:

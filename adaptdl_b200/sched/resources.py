@@ -41,6 +41,26 @@ def discretize_resource(name, value):
 _discretize_resource = discretize_resource     # reference name
 
 
+def scale_quantity(name, value, factor):
+    """``factor`` times a Kubernetes quantity, as a quantity string (CPU in
+    milli-cores, everything else in base units) -- the resources of a pod
+    that hosts several replicas."""
+    total = discretize_resource(name, value) * int(factor)
+    return "{}m".format(total) if name == "cpu" else str(total)
+
+
+def scale_container_resources(container, factor):
+    """Multiply every request and limit of ``container`` (in place)."""
+    if factor == 1:
+        return container
+    resources = container.get("resources") or {}
+    for kind in ("requests", "limits"):
+        for key, val in list((resources.get(kind) or {}).items()):
+            if val is not None:
+                resources[kind][key] = scale_quantity(key, val, factor)
+    return container
+
+
 def _as_dict(obj):
     return obj if isinstance(obj, dict) else obj.to_dict()
 

@@ -59,7 +59,10 @@ class Supervisor(object):
                 int(ann["adaptdl/rank"])
             if ips is None:
                 ips = [None] * replicas
-            ips[rank] = (pod.get("status") or {}).get("podIP")
+            # a node pod (spec.podPerNode) hosts a range of ranks
+            hosted = int(ann.get("adaptdl/local-replicas", 1))
+            for local in range(hosted):
+                ips[rank + local] = (pod.get("status") or {}).get("podIP")
         return ips
 
     async def _handle_discover(self, request):

@@ -60,7 +60,8 @@ def test_crd_matches_what_controller_and_cli_use():
     assert "status" in version["subresources"]      # patch_job_status
     spec = version["schema"]["openAPIV3Schema"]["properties"]["spec"]
     assert set(spec["properties"]) == {"maxReplicas", "minReplicas",
-                                       "preemptible", "template"}
+                                       "preemptible", "template",
+                                       "podPerNode"}
     assert spec["properties"]["maxReplicas"]["minimum"] == 1
     columns = [c["name"] for c in version["additionalPrinterColumns"]]
     assert columns == ["Ready", "Replicas", "Restarts", "Status", "Age"]

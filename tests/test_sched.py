@@ -486,3 +486,95 @@ def test_allocation_cycle_does_not_block_the_event_loop():
         during = [t for t in ticks if began < t < began + took]
         assert took >= 0.6 and len(during) >= 5, (took, len(during))
     run(scenario())
+
+
+# ------------------------------------------------------- one pod per node
+
+def test_plan_pods_and_canonical_allocation():
+    from adaptdl_b200.sched.controller import (canonical_allocation,
+                                               plan_pods)
+    alloc = ["n1", "n0", "n1", "n1", "n0"]
+    assert plan_pods(alloc) == [(0, "n1", 1), (1, "n0", 1), (2, "n1", 1),
+                                (3, "n1", 1), (4, "n0", 1)]
+    assert canonical_allocation(alloc, True) == ["n1", "n1", "n1", "n0", "n0"]
+    assert plan_pods(alloc, True) == [(0, "n1", 3), (3, "n0", 2)]
+    assert plan_pods([], True) == []
+
+
+def test_node_pod_manifest_scales_resources(monkeypatch):
+    monkeypatch.setenv("ADAPTDL_SUPERVISOR_URL", "http://sup:8080")
+    monkeypatch.delenv("ADAPTDL_JOB_DEFAULT_RESOURCES", raising=False)
+    template = {"spec": {"containers": [{
+        "name": "main", "image": "img",
+        "resources": {"requests": {"cpu": "500m", "memory": "1Gi"},
+                      "limits": {"nvidia.com/gpu": 1}}}]}}
+    meta = {"namespace": "ns", "name": "job", "uid": "u"}
+    pod = build_pod(meta, template, ["n0", "n0", "n0", "n1"], 2, 0, "host0",
+                    local_replicas=3)
+    ann = pod["metadata"]["annotations"]
+    assert ann["adaptdl/local-replicas"] == "3" and ann["adaptdl/rank"] == "0"
+    res = pod["spec"]["containers"][0]["resources"]
+    assert res["limits"]["nvidia.com/gpu"] == "3"
+    assert res["requests"] == {"cpu": "1500m", "memory": str(3 << 30)}
+    env = {e["name"]: e["value"] for e in pod["spec"]["containers"][0]["env"]}
+    assert env["ADAPTDL_LOCAL_REPLICAS"] == "3"
+    assert env["ADAPTDL_REPLICA_RANK"] == "0"
+    assert env["ADAPTDL_NUM_REPLICAS"] == "4" and env["ADAPTDL_NUM_NODES"] == "2"
+    # the template itself is untouched, one-replica pods are unchanged
+    assert template["spec"]["containers"][0]["resources"]["limits"] == \
+        {"nvidia.com/gpu": 1}
+    single = build_pod(meta, template, ["n0", "n1"], 0, 1, "host1")
+    assert "adaptdl/local-replicas" not in single["metadata"]["annotations"]
+    assert single["spec"]["containers"][0]["resources"]["limits"] == \
+        {"nvidia.com/gpu": 1}
+
+
+def test_pod_per_node_lifecycle_and_discovery():
+    async def scenario():
+        cluster = InMemoryCluster()
+        for n in ("n0", "n1"):
+            cluster.add_node(n, {"nvidia.com/gpu": 8, "pods": 32})
+        cluster.add_job("ns", "job", {"template": TEMPLATE, "maxReplicas": 8,
+                                      "podPerNode": True},
+                        {"allocation": ["n0", "n1", "n0", "n0"]})
+        ctl = AdaptDLController(cluster)
+        await ctl.sync_job("ns", "job")                    # -> Starting
+        await ctl.sync_job("ns", "job")                    # creates pods
+        pods = await cluster.list_pods("ns")
+        assert len(pods) == 2
+        by_node = {p["metadata"]["annotations"]["adaptdl/node"]: p
+                   for p in pods}
+        ann0 = by_node["n0"]["metadata"]["annotations"]
+        ann1 = by_node["n1"]["metadata"]["annotations"]
+        assert (ann0["adaptdl/rank"], ann0["adaptdl/local-replicas"]) == \
+            ("0", "3")
+        assert ann1["adaptdl/rank"] == "3" and \
+            "adaptdl/local-replicas" not in ann1
+        for pod in pods:
+            cluster.set_pod_status(
+                "ns", pod["metadata"]["name"], phase="Running",
+                podIP="10.0.0." + pod["metadata"]["annotations"][
+                    "adaptdl/rank"],
+                containerStatuses=[{"ready": True}],
+                conditions=[{"type": "PodScheduled", "status": "True"}])
+        await ctl.sync_job("ns", "job")
+        status = (await cluster.get_job("ns", "job"))["status"]
+        assert status["phase"] == "Running"
+        assert status["replicas"] == 4 and status["readyReplicas"] == 4
+        # rendezvous: one address per RANK
+        sup = Supervisor(cluster, port=0, poll=0.01)
+        async with _client(sup.app) as client:
+            resp = await client.get("/discover/ns/job/0?timeout=1")
+            assert await resp.json() == ["10.0.0.0"] * 3 + ["10.0.0.3"]
+        # same allocation in another order is not a restart; a new share is
+        await cluster.patch_job_status(
+            "ns", "job", {"status": {"allocation": ["n0", "n0", "n0", "n1"]}})
+        await ctl.sync_job("ns", "job")
+        assert (await cluster.get_job("ns", "job"))["status"]["phase"] == \
+            "Running"
+        await cluster.patch_job_status(
+            "ns", "job", {"status": {"allocation": ["n0", "n0", "n1", "n1"]}})
+        await ctl.sync_job("ns", "job")
+        assert (await cluster.get_job("ns", "job"))["status"]["phase"] == \
+            "Stopping"
+    run(scenario())
