@@ -99,8 +99,11 @@ def test_workload_specs_validate():
     validator = Validator(InMemoryCluster())
     for name in workloads.WORKLOADS:
         resource = workloads.manifest(name)
-        script = resource["spec"]["template"]["spec"]["containers"][0][
-            "command"][1]
+        command = resource["spec"]["template"]["spec"]["containers"][0][
+            "command"]
+        script = next(part for part in command if part.endswith(".py"))
+        assert ("adaptdl_b200.launch" in command) == bool(
+            resource["spec"].get("podPerNode"))
         assert os.path.exists(os.path.join(
             workloads.ROOT, os.path.relpath(script, workloads.IMAGE_ROOT))), script
         job, pvc = manifests.prepare_job(resource, "registry/img@sha256:0",

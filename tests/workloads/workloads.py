@@ -50,6 +50,12 @@ WORKLOADS = {
         "long", "examples/pytorch-cifar/main.py",
         ["--model=ResNet18", "--bs=128", "--lr=0.1", "--epochs=60",
          "--autoscale-bsz", "--mixed-precision"], {}),
+    # one pod per node: all replicas of a node in one container, so the
+    # peer-memory reducer is used (docs/commandline.md)
+    "resnet18-cifar10-elastic-node-pods": (
+        "long", "examples/pytorch-cifar/main.py",
+        ["--model=ResNet18", "--bs=128", "--lr=0.1", "--epochs=60",
+         "--autoscale-bsz"], {"podPerNode": True, "maxReplicas": 8}),
     "densenet121-cifar10": (
         "long", "examples/pytorch-cifar/main.py",
         ["--model=DenseNet121", "--bs=128", "--lr=0.1", "--epochs=60",
@@ -92,9 +98,12 @@ def manifest(name, image_root=IMAGE_ROOT):
     suite, script, args, overrides = WORKLOADS[name]
     overrides = copy.deepcopy(overrides)
     cpu = overrides.pop("cpu", False)
+    launcher = ["-m", "adaptdl_b200.launch"] \
+        if overrides.get("podPerNode") else []
     container = {
         "name": "main",
-        "command": ["python3", os.path.join(image_root, script)] + list(args),
+        "command": ["python3"] + launcher
+        + [os.path.join(image_root, script)] + list(args),
         "env": [{"name": "PYTHONUNBUFFERED", "value": "true"}],
     }
     if cpu:
