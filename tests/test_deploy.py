@@ -68,16 +68,23 @@ def test_crd_matches_what_controller_and_cli_use():
 
 
 def test_plain_manifests_parse():
-    for rel in ("deploy/cluster-autoscaler.yaml", "deploy/eks-cluster.yaml",
+    for rel in ("deploy/cluster-autoscaler-values.yaml",
+                "deploy/eks-cluster.yaml",
                 "examples/ray/aws/cluster.yaml", "tutorial/adaptdljob.yaml",
                 ".github/workflows/test.yaml",
                 ".github/workflows/docs.yaml",
                 ".github/workflows/release.yaml"):
         docs = [d for d in yaml.safe_load_all(_read(ROOT, rel)) if d]
         assert docs, rel
-    kinds = [d["kind"] for d in yaml.safe_load_all(
-        _read(ROOT, "deploy", "cluster-autoscaler.yaml"))]
-    assert kinds.count("Deployment") == 1 and "ClusterRole" in kinds
+    # the autoscaler discovers exactly the node groups eksctl tags
+    values = yaml.safe_load(_read(ROOT, "deploy",
+                                  "cluster-autoscaler-values.yaml"))
+    eks = yaml.safe_load(_read(ROOT, "deploy", "eks-cluster.yaml"))
+    assert values["autoDiscovery"]["clusterName"] == eks["metadata"]["name"]
+    tagged = [group for group in eks["nodeGroups"]
+              if all(tag in (group.get("tags") or {})
+                     for tag in values["autoDiscovery"]["tags"])]
+    assert [group["name"] for group in tagged] == ["gpu"]
 
 
 def test_tutorial_job_goes_through_the_submit_path():
