@@ -70,7 +70,7 @@ def test_crd_matches_what_controller_and_cli_use():
 def test_plain_manifests_parse():
     for rel in ("deploy/cluster-autoscaler-values.yaml",
                 "deploy/eks-cluster.yaml",
-                "examples/ray/aws/cluster.yaml", "tutorial/adaptdljob.yaml",
+                "examples/ray/aws/cluster.yaml", "tutorial/mnist-job.yaml",
                 ".github/workflows/test.yaml",
                 ".github/workflows/docs.yaml",
                 ".github/workflows/release.yaml"):
@@ -89,7 +89,7 @@ def test_plain_manifests_parse():
 
 def test_tutorial_job_goes_through_the_submit_path():
     from adaptdl_b200.cli import manifests
-    resource = yaml.safe_load(_read(ROOT, "tutorial", "adaptdljob.yaml"))
+    resource = yaml.safe_load(_read(ROOT, "tutorial", "mnist-job.yaml"))
     job, pvc = manifests.prepare_job(resource, "registry/img@sha256:0", [],
                                      name="tutorial")
     container = job["spec"]["template"]["spec"]["containers"][0]
@@ -98,7 +98,7 @@ def test_tutorial_job_goes_through_the_submit_path():
     assert env["ADAPTDL_CHECKPOINT_PATH"] == manifests.CHECKPOINT_MOUNT
     assert job["spec"]["maxReplicas"] >= job["spec"]["minReplicas"]
     assert pvc.startswith("adaptdl-pvc-")
-    script = container["command"][1]
+    script = next(c for c in container["command"] if c.endswith(".py"))
     assert os.path.exists(os.path.join(ROOT, script))
 
 
