@@ -18,8 +18,10 @@ semantics and checkpoint format). B200 additions: :class:`DevicePrefetcher`
 import collections
 import logging
 import math
+import os
 import random
 import sys
+import time
 from contextlib import contextmanager
 
 import numpy as np
@@ -34,6 +36,74 @@ from adaptdl_b200.torch.epoch import current_epoch
 LOG = logging.getLogger(__name__)
 
 EXIT_CODE_PREEMPTED = 143     # the contract with the job controller
+
+
+class _PreemptionBeat(object):
+    """Exit-flag consensus of the replicas, off the step path.
+
+    The reference OR-reduces the flag over its TCP reducer on EVERY training
+    iteration (``torch/data.py:311-334``): a host-side barrier per step whose
+    messages all pass through a Python thread on rank 0 -- irrelevant at its
+    100 ms steps, a real cost at the 2 ms steps of a graph-replayed B200 job
+    (8 replicas = 8000 messages/s on rank 0's interpreter). Here a round is
+    started only every ``interval`` iterations, with ``interval`` chosen so
+    that rounds are about ``ADAPTDL_HEARTBEAT_PERIOD`` seconds apart (default
+    0.1; ``0`` = every iteration, as the reference). The interval must be the
+    same on every replica, so it travels WITH the consensus: each round
+    reduces ``(flag, rank 0's suggestion for the next interval)``, and every
+    replica resolves round k and starts round k+1 at the same iteration. A
+    signal is therefore acted upon within two rounds (~0.2 s) -- far inside
+    any preemption grace period.
+
+    One instance per process: rounds continue across data loaders (training
+    and validation loops alternate), so short loops cannot starve it.
+    """
+
+    MAX_INTERVAL = 1000
+
+    def __init__(self):
+        self.reset()
+
+    def reset(self):
+        self.pending = None          # future of the round in flight
+        self.interval = 1            # iterations between round starts
+        self.countdown = 0           # iterations until the next round start
+        self.started = None          # host time the pending round started
+
+    @staticmethod
+    def period():
+        return float(os.environ.get("ADAPTDL_HEARTBEAT_PERIOD", "0.1"))
+
+    def _suggestion(self, now):
+        """Interval that would have put the rounds ``period`` apart at the
+        pace of the iterations since the last round started."""
+        period = self.period()
+        if period <= 0 or self.started is None:
+            return 1
+        per_iteration = max(now - self.started, 1e-6) / self.interval
+        return int(min(max(period / per_iteration, 1), self.MAX_INTERVAL))
+
+    def beat(self):
+        """Call once per training iteration on every replica."""
+        if self.countdown > 0:
+            self.countdown -= 1
+            return
+        now = time.monotonic()
+        suggestion = self._suggestion(now)
+        if self.pending is not None:
+            flagged, self.interval = self.pending.result()
+            if flagged:
+                checkpoint.save_all_states()
+                sys.exit(EXIT_CODE_PREEMPTED)
+        # rank 0 is the left-most operand of the fold: its suggestion wins
+        self.pending = collective.allreduce_async(
+            (bool(get_exit_flag()), suggestion),
+            lambda a, b: (a[0] or b[0], a[1]))
+        self.started = now
+        self.countdown = self.interval - 1
+
+
+_PREEMPTION = _PreemptionBeat()
 
 
 def _shuffle_seed(epoch, pass_index):
@@ -141,7 +211,6 @@ class AdaptiveDataLoaderHelper(object):
         self._state = _AdaptiveDataLoaderState()
         checkpoint.load_state(self._state)
         self.batch_size = batch_size
-        self.future_exit = None
         self._gradient_accumulation = False
         self._speedup_threshold = self.SPEEDUP_THRESHOLD
         self._accum_count = 0
@@ -269,15 +338,11 @@ class AdaptiveDataLoaderHelper(object):
         """Wrap every training iteration. Must be entered the same number
         of times on every replica.
 
-        Resolves the exit-flag consensus launched one iteration earlier: if
-        any replica was signalled, *all* replicas checkpoint now and exit
-        with code 143.
+        Takes part in the exit-flag consensus (:class:`_PreemptionBeat`): if
+        any replica was signalled, *all* replicas checkpoint at the same
+        iteration and exit with code 143.
         """
-        if self.future_exit is not None and self.future_exit.result():
-            checkpoint.save_all_states()
-            sys.exit(EXIT_CODE_PREEMPTED)
-        self.future_exit = collective.allreduce_async(
-            get_exit_flag(), lambda a, b: a or b)
+        _PREEMPTION.beat()
         _metrics.profile_step_start(self.current_local_bsz)
         yield
         if commit:
@@ -529,3 +594,4 @@ def _reset_for_tests():
     AdaptiveDataLoaderHelper._training = None
     AdaptiveDataLoaderHelper._current = None
     _AdaptiveDataLoaderState.init_count = collections.Counter()
+    _PREEMPTION.reset()

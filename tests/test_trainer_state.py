@@ -3,6 +3,7 @@ restarts at changing replica counts (ideas from the reference's
 torch/*_test.py, run on the local elastic harness)."""
 import collections
 import math
+import os
 
 import pytest
 import torch
@@ -390,3 +391,60 @@ def test_periodic_report_does_not_stall_the_step_loop(monkeypatch):
     finally:
         _metrics.wait_for_report(10.0)
         _metrics._reset_for_tests()
+
+
+def _beat_loop(iterations, signal_at, period, pause=0.001):
+    """Run the preemption beat like a training loop does; returns what each
+    replica saw: (iteration of the exit, consensus rounds started)."""
+    import time
+    from adaptdl_b200 import _signal, collective, env
+    from adaptdl_b200.torch import data
+    os.environ["ADAPTDL_HEARTBEAT_PERIOD"] = str(period)
+    collective.initialize(env.master_addr(), env.master_port(),
+                          env.replica_rank(), env.num_replicas())
+    beat = data._PREEMPTION
+    rounds, launch = [0], collective.allreduce_async
+
+    def counting(*args, **kwargs):
+        rounds[0] += 1
+        return launch(*args, **kwargs)
+    data.collective.allreduce_async = counting
+    try:
+        for iteration in range(iterations):
+            if iteration == signal_at and env.replica_rank() == 1:
+                _signal.set_exit_flag(True)          # only ONE replica
+            try:
+                beat.beat()
+            except SystemExit as stop:
+                assert stop.code == 143
+                return iteration, rounds[0]
+            time.sleep(pause)
+        return None, rounds[0]
+    finally:
+        data.collective.allreduce_async = launch
+
+
+@elastic_multiprocessing
+def test_preemption_beat_every_iteration_like_the_reference():
+    from adaptdl_b200 import env
+    if env.num_restarts() == 0:
+        return 2
+    stopped_at, rounds = _beat_loop(40, signal_at=10, period=0)
+    # flagged in round 10, resolved by everyone in iteration 11
+    assert stopped_at == 11 and rounds == 11, (stopped_at, rounds)
+    return 0
+
+
+@elastic_multiprocessing
+def test_preemption_beat_leaves_the_step_path_but_stays_in_lockstep():
+    from adaptdl_b200 import collective, env
+    if env.num_restarts() == 0:
+        return 2
+    stopped_at, rounds = _beat_loop(3000, signal_at=600, period=0.05)
+    assert stopped_at is not None and 600 < stopped_at < 900, stopped_at
+    # ~1 ms iterations, a round every ~50 ms: far fewer rounds than iterations
+    assert rounds < stopped_at / 5, (rounds, stopped_at)
+    # every replica left at the SAME iteration
+    both = collective.allreduce([stopped_at], lambda a, b: a + b)
+    assert both[0] == both[1], both
+    return 0
