@@ -448,3 +448,36 @@ def test_preemption_beat_leaves_the_step_path_but_stays_in_lockstep():
     both = collective.allreduce([stopped_at], lambda a, b: a + b)
     assert both[0] == both[1], both
     return 0
+
+
+@elastic_multiprocessing
+def test_tensor_dataset_batches_are_fetched_whole():
+    """In-memory TensorDatasets take the batched fast path; the batches are
+    exactly what the per-sample path produces."""
+    from adaptdl_b200.torch import data
+    from adaptdl_b200.torch.data import AdaptiveDataLoader
+    torch.manual_seed(0)
+    x, y = torch.randn(50, 3, 4), torch.arange(50)
+
+    def batches(flag):
+        os.environ["ADAPTDL_B200_BATCHED_TENSOR_DATASET"] = flag
+        loader = AdaptiveDataLoader(TensorDataset(x, y), batch_size=8,
+                                    shuffle=True)
+        assert isinstance(loader.dataset,
+                          data._BatchedTensorDataset) == (flag == "1")
+        sampler = loader.batch_sampler.sampler
+        sampler.set_epoch(0)
+        return [loader.collate_fn(
+                    loader.dataset.__getitems__(idx) if flag == "1"
+                    else [loader.dataset[i] for i in idx])
+                for idx in loader.batch_sampler]
+    fast, slow = batches("1"), batches("0")
+    assert len(fast) == len(slow) == 7
+    for a, b in zip(fast, slow):
+        assert type(a) is type(b) is list and len(a) == 2
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    # a custom collate_fn or a dataset subclass keeps the generic path
+    loader = AdaptiveDataLoader(TensorDataset(x, y), batch_size=8,
+                                collate_fn=lambda samples: samples)
+    assert type(loader.dataset) is TensorDataset
+    return 0
