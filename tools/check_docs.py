@@ -20,6 +20,8 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 TOP_LEVEL = ("adaptdl_b200", "csrc", "tools", "tests", "docs", "deploy",
              "examples", "tutorial", "profiles", "baseline")
+# created by the offline reference install, not tracked
+GENERATED = ("baseline/_ref",)
 # files that quote paths of OTHER trees (the reference, retrieved snippets)
 SKIP = {"SURVEY.md", "PAPERS.md", "SNIPPETS.md", "BASELINE.md", "VERDICT.md",
         "ADVICE.md"}
@@ -49,6 +51,8 @@ def repo_path(token):
         token = token[2:]
     head = token.split("/")[0]
     if "/" not in token or head not in TOP_LEVEL:
+        return None
+    if token.startswith(GENERATED):       # git-ignored, absent from a clone
         return None
     if any(ch in token for ch in "<>{}$|") or "..." in token or \
             "…" in token:
