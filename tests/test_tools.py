@@ -99,3 +99,16 @@ def test_policy_bench_smoke():
                     seed=0)
     assert row["gpus_allocated"] <= 8 and row["jobs_running"] >= 1
     assert len(row["cycle_seconds"]) == 2 and row["sum_speedup"] > 0
+
+
+def test_conv_bench_plumbing_on_cpu():
+    bench = _load("conv_bench")
+    measure = bench.timer(__import__("torch").device("cpu"), 1, 0)
+    import torch
+    rows = [bench.bench_layer(spec, 2, torch.device("cpu"), torch.float32,
+                              measure)
+            for spec in bench.RESNET18_CONVS[:3]]
+    assert "fprop_padded_us" in rows[0]            # 3-channel stem
+    assert "dgrad_phase_us" in rows[2]             # stride-2 3x3
+    assert "dgrad_phase_us" not in rows[1]
+    assert all(r["fprop_us"] > 0 and r["gflop"] > 0 for r in rows)

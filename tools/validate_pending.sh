@@ -36,6 +36,9 @@ for line in open(sys.argv[1]):
 PY
 done
 
+timeout 300 python tools/conv_bench.py --out "$OUT/conv_bench.json" > "$OUT/conv_bench.log" 2>&1
+tail -1 "$OUT/conv_bench.log"
+
 echo "== 4. BERT with and without the fused LayerNorm op"
 timeout 300 python bench.py --workload bert --steps 20 --warmup 5 > "$OUT/bench_bert_default.log" 2>&1
 ADAPTDL_B200_FUSED_LN=1 timeout 300 python bench.py --workload bert --steps 20 --warmup 5 > "$OUT/bench_bert_fused_ln.log" 2>&1
