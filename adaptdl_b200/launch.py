@@ -83,9 +83,9 @@ def run(command, environ=None, poll=0.2):
                 except subprocess.TimeoutExpired:
                     proc.kill()
         codes = [proc.wait() for proc in procs]
-        return exit_code(failed + [c for c in codes if c in
-                                   (0, EXIT_PREEMPTED)]) if failed \
-            else exit_code(codes)
+        # the replicas we terminated report the signal, not a verdict: the
+        # group's code is that of the replica that failed on its own
+        return exit_code(failed or codes)
     finally:
         for sig, handler in previous.items():
             signal.signal(sig, handler)
