@@ -122,7 +122,7 @@ class SimJob(object):
                                         accumulation=True)
             return float(goodput)
         # static: fixed global batch = initial batch (split over the GPUs)
-        atomic = max(self.init_bsz // n, 1)
+        atomic = max(-(-self.init_bsz // n), 1)       # ceil: never below it
         return float(fn.evaluate(nodes, n, atomic, 0))
 
 
