@@ -52,6 +52,10 @@ class _HookedOptimizerMethods(object):
         # bound methods (torch's LR schedulers re-wrap ``optimizer.step`` and
         # expect ``step.__func__``)
         def step(_optimizer, *args, **kwargs):
+            # what torch's LR-scheduler wrapper records on every call (its
+            # "scheduler.step() before optimizer.step()" check); the fused
+            # device step does not go through that wrapper
+            _optimizer._opt_called = True
             return rule.step(*args, **kwargs)
 
         def zero_grad(_optimizer, *args, **kwargs):
@@ -61,6 +65,11 @@ class _HookedOptimizerMethods(object):
             mine.__name__ = getattr(real, "__name__", mine.__name__)
             mine.__doc__ = getattr(real, "__doc__", None)
             mine.__wrapped__ = real
+        # an LR scheduler built before the wrapper marked the step it saw;
+        # carry the mark over, or every scheduler.step() warns that
+        # optimizer.step() "has been overridden after initialization"
+        if hasattr(self.real_step, "_wrapped_by_lr_sched"):
+            step._wrapped_by_lr_sched = True
         self.optimizer.step = types.MethodType(step, self.optimizer)
         self.optimizer.zero_grad = types.MethodType(zero_grad,
                                                     self.optimizer)

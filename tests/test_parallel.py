@@ -39,12 +39,19 @@ def test_single_replica_parallel():
     schedule = torch.optim.lr_scheduler.MultiStepLR(sgd, [50])
     model = adl.AdaptiveDataParallel(model, sgd, schedule)
     loss = torch.nn.MSELoss()
-    for epoch in adl.remaining_epochs_until(100):
-        for inputs, targets in dataloader:
-            sgd.zero_grad()
-            loss(model(inputs), targets).backward()
-            sgd.step()
-        schedule.step()
+    import warnings
+    with warnings.catch_warnings(record=True) as caught:
+        warnings.simplefilter("always")
+        for epoch in adl.remaining_epochs_until(100):
+            for inputs, targets in dataloader:
+                sgd.zero_grad()
+                loss(model(inputs), targets).backward()
+                sgd.step()
+            schedule.step()
+    # patching optimizer.step() after the scheduler was built must not trip
+    # torch's "overridden after initialization" / "called before" checks
+    assert not [w for w in caught if "optimizer.step()" in str(w.message)], \
+        [str(w.message) for w in caught]
     got = np.asarray([float(p.detach()) for p in params])
     assert np.all(np.isclose(got, true_values, atol=0.1)), got
     assert model.gain >= 1.0 - 1e-6
