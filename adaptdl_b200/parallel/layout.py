@@ -20,6 +20,7 @@ Pure Python / no torch dependency: unit-testable on its own.
 """
 
 import collections
+import math
 
 VEC_BYTES = 16
 BUCKET_ALIGN_BYTES = 512
@@ -57,8 +58,11 @@ def plan_arena(numels, groups, itemsize, bucket_cap_bytes,
     """
     assert len(numels) == len(groups)
     vec = VEC_BYTES // itemsize
-    bucket_align = max(BUCKET_ALIGN_BYTES // itemsize, vec * world_size)
-    bucket_align = _round_up(bucket_align, vec * world_size)
+    # a common multiple of both requirements (for world sizes that are not
+    # powers of two -- an elastic job may run on 3, 5, 6, 7 GPUs -- rounding
+    # one up to the other would break the 512-byte starts)
+    bucket_align = math.lcm(max(BUCKET_ALIGN_BYTES // itemsize, 1),
+                            vec * world_size)
     if first_bucket_cap_bytes is None:
         first_bucket_cap_bytes = bucket_cap_bytes
     first_bucket_cap_bytes = min(first_bucket_cap_bytes, bucket_cap_bytes)

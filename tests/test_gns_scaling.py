@@ -357,3 +357,49 @@ def test_unused_parameters_do_not_stall():
         stats = red.pop_stats()
         assert stats.total_sqr == pytest.approx([12.0])
         assert float(unused.grad.abs().sum()) == 0.0
+
+
+def test_layout_invariants_hold_for_arbitrary_models():
+    """Property test of the flat-gradient planner: whatever the parameter
+    sizes, groups, dtype width, bucket cap and world size, the plan keeps the
+    alignment contract the sm_100a kernels rely on."""
+    from hypothesis import given, settings, strategies as st
+    from adaptdl_b200.parallel import layout
+
+    @settings(max_examples=200, deadline=None)
+    @given(numels=st.lists(st.integers(1, 5000), min_size=1, max_size=40),
+           itemsize=st.sampled_from([2, 4]),
+           cap=st.integers(64, 20000), first=st.integers(64, 20000),
+           world=st.integers(1, 8), data=st.data())
+    def check(numels, itemsize, cap, first, world, data):
+        groups = [data.draw(st.integers(0, 5)) for _ in numels]
+        total, buckets = layout.plan_arena(numels, groups, itemsize, cap,
+                                           first, world)
+        vec = layout.VEC_BYTES // itemsize
+        seen, cursor = [], 0
+        for index, bucket in enumerate(buckets):
+            assert bucket.index == index and bucket.start == cursor
+            assert bucket.start * itemsize % layout.BUCKET_ALIGN_BYTES == 0
+            assert bucket.length % (vec * world) == 0    # whole rank slices
+            previous_end = bucket.start
+            for seg in bucket.segments:
+                assert seg.start % vec == 0              # 16-byte aligned
+                assert seg.start >= previous_end          # no overlap
+                assert seg.length == numels[seg.param_index]
+                assert seg.group == groups[seg.param_index]
+                previous_end = seg.start + seg.length
+                seen.append(seg.param_index)
+            assert previous_end <= bucket.start + bucket.length
+            payload = sum(s.length for s in bucket.segments) * itemsize
+            limit = min(first, cap) if index == 0 else cap
+            # the cap is soft only for a single oversized parameter
+            assert payload <= limit or len(bucket.segments) == 1
+            rows = layout.segment_table(bucket, vec)
+            assert all(a < b for a, b, _ in rows)
+            assert all(rows[i][1] <= rows[i + 1][0]
+                       for i in range(len(rows) - 1))
+            cursor = bucket.start + bucket.length
+        assert total == cursor
+        # every parameter exactly once, in reverse registration order
+        assert seen == list(reversed(range(len(numels))))
+    check()
