@@ -146,7 +146,9 @@ class ElasticSampler(Sampler):
         base = self.index % len(self.dataset)
         mine = order[base + self.rank::self.num_replicas]
         if len(mine) < len(self):       # pad so all replicas are equal
-            mine.append(order[self.rank])
+            # (modulo: a dataset smaller than the replica count -- a tiny
+            # validation set on many GPUs -- must not index past its end)
+            mine.append(order[self.rank % len(order)])
         assert len(mine) == len(self)
         return iter(mine)
 

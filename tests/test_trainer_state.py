@@ -481,3 +481,34 @@ def test_tensor_dataset_batches_are_fetched_whole():
                                 collate_fn=lambda samples: samples)
     assert type(loader.dataset) is TensorDataset
     return 0
+
+
+def test_sampler_partition_properties():
+    """Property test: for any dataset size, replica count and resume index,
+    the replicas' shares have equal length, only valid indices, and together
+    cover exactly the rest of the pass (plus at most one pad each)."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=300, deadline=None)
+    @given(n=st.integers(1, 60), replicas=st.integers(1, 12),
+           passes=st.integers(0, 2), offset=st.integers(0, 59),
+           shuffle=st.booleans(), epoch=st.integers(0, 3))
+    def check(n, replicas, passes, offset, shuffle, epoch):
+        index = passes * n + offset % n
+        shares = []
+        for rank in range(replicas):
+            sampler = ElasticSampler(list(range(n)), shuffle=shuffle)
+            sampler.num_replicas, sampler.rank = replicas, rank
+            sampler.set_epoch(epoch, index)
+            share = list(sampler)
+            assert len(share) == len(sampler)
+            assert all(0 <= i < n for i in share)
+            shares.append(share)
+        assert len({len(s) for s in shares}) == 1
+        order = shares and ElasticSampler(list(range(n)), shuffle=shuffle)
+        order.set_epoch(epoch, index)
+        rest = order._order()[index % n:]
+        real = [s[:len(rest[r::replicas])] for r, s in enumerate(shares)]
+        merged = sorted(i for s in real for i in s)
+        assert merged == sorted(rest)
+    check()
