@@ -317,3 +317,38 @@ def test_row_keys_distinguish_rows():
     keep = nsga2._unique_rows(X)
     assert keep.sum() == 299 and not keep[17]
     assert not nsga2._unique_rows(X[:5], against=X).any()
+
+
+def test_non_dominated_sorting_properties():
+    from hypothesis import given, settings, strategies as st
+
+    def dominates(a, b):
+        return all(x <= y for x, y in zip(a, b)) and \
+            any(x < y for x, y in zip(a, b))
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.lists(st.tuples(st.integers(0, 6), st.integers(0, 6)),
+                    min_size=1, max_size=25))
+    def check(points):
+        F = np.array(points, dtype=float)
+        fronts = nsga2.non_dominated_fronts(F)
+        flat = sorted(int(i) for front in fronts for i in front)
+        assert flat == list(range(len(points)))          # a partition
+        rank = {int(i): r for r, front in enumerate(fronts) for i in front}
+        for i, a in enumerate(points):
+            for j, b in enumerate(points):
+                if dominates(a, b):
+                    assert rank[i] < rank[j]
+            # every point outside front 0 is dominated by someone one front up
+            if rank[i] > 0:
+                assert any(dominates(points[j], a) and rank[j] == rank[i] - 1
+                           for j in range(len(points)))
+        for front in fronts:
+            dist = nsga2.crowding_distance(F[front])
+            assert (dist >= 0).all()
+            if len(front) > 2:
+                for k in range(F.shape[1]):
+                    col = F[front, k]
+                    assert np.isinf(dist[np.argmin(col)]) or \
+                        np.isinf(dist).sum() >= 2
+    check()

@@ -578,3 +578,45 @@ def test_pod_per_node_lifecycle_and_discovery():
         assert (await cluster.get_job("ns", "job"))["status"]["phase"] == \
             "Stopping"
     run(scenario())
+
+
+def test_pod_plans_cover_every_rank_once():
+    from hypothesis import given, settings, strategies as st
+    from adaptdl_b200.sched.controller import (canonical_allocation,
+                                               plan_pods)
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.lists(st.sampled_from(["n0", "n1", "n2", "n3"]), max_size=24),
+           st.booleans())
+    def check(allocation, per_node):
+        ranked = canonical_allocation(allocation, per_node)
+        assert sorted(ranked) == sorted(allocation)
+        plan = plan_pods(allocation, per_node)
+        covered = []
+        for first, node, count in plan:
+            assert count >= 1
+            assert ranked[first:first + count] == [node] * count
+            covered.extend(range(first, first + count))
+        assert covered == list(range(len(allocation)))
+        if per_node:
+            assert len(plan) == len(set(allocation))
+        else:
+            assert len(plan) == len(allocation)
+    check()
+
+
+def test_quantity_scaling_roundtrip():
+    from hypothesis import given, settings, strategies as st
+    from adaptdl_b200.sched.resources import (discretize_resource,
+                                              scale_quantity)
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.sampled_from(["cpu", "memory", "nvidia.com/gpu"]),
+           st.sampled_from(["1", "2", "500m", "1Gi", "3Mi", "2k", "1.5",
+                            "250m", "8"]),
+           st.integers(1, 16))
+    def check(name, quantity, factor):
+        scaled = scale_quantity(name, quantity, factor)
+        assert discretize_resource(name, scaled) == \
+            discretize_resource(name, quantity) * factor
+    check()
