@@ -170,3 +170,33 @@ def test_fit_single_replica_pins_network_terms():
     # single batch size: alpha_c pinned to half the mean accum time
     fit = fit_perf_params([1], [1], [64.], [0.2], [0.2])
     assert fit.alpha_c == pytest.approx(0.1)
+
+
+def test_fit_is_robust_to_arbitrary_small_profiles():
+    """Whatever (few, noisy, degenerate) measurements a job has collected,
+    the fit returns finite parameters inside their bounds."""
+    from hypothesis import given, settings, strategies as st
+
+    row = st.tuples(st.integers(1, 4), st.integers(1, 8),
+                    st.integers(1, 512),
+                    st.floats(1e-4, 10.0), st.floats(0.0, 5.0))
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.lists(row, min_size=1, max_size=8))
+    def check(rows):
+        nodes = np.array([min(r[0], r[1]) for r in rows])
+        replicas = np.array([r[1] for r in rows])
+        bsz = np.array([r[2] for r in rows])
+        accum = np.array([r[3] for r in rows])
+        optim = accum + np.array([r[4] for r in rows])   # step >= local time
+        params = fit_perf_params(nodes, replicas, bsz, accum, optim)
+        values = np.array(params, dtype=float)
+        assert np.isfinite(values).all(), params
+        assert (values[:6] >= 0).all() and 1.0 <= params.gamma <= 10.0
+        fn = GoodputFunction(params, GradParams(1.0, 1.0), 32)
+        goodput, atomic, accum_steps = fn.optimize(
+            1, 2, max_batch_size=1024, atomic_bsz_range=(8, 256),
+            accumulation=True)
+        assert np.isfinite(goodput) and goodput >= 0
+        assert 8 <= atomic <= 256 and accum_steps >= 0
+    check()

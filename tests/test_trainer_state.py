@@ -512,3 +512,36 @@ def test_sampler_partition_properties():
         merged = sorted(i for s in real for i in s)
         assert merged == sorted(rest)
     check()
+
+
+@elastic_multiprocessing
+def test_dataloader_visits_every_sample_for_arbitrary_sizes():
+    """Property test (single replica): for any dataset size, batch size and
+    drop_last, one epoch visits every sample once (or drops only a final
+    partial batch), in batches no larger than asked for."""
+    from hypothesis import given, settings, strategies as st
+    import adaptdl_b200.torch as adl
+    adl.init_process_group("gloo")
+    seen_epochs = []
+
+    @settings(max_examples=40, deadline=None)
+    @given(n=st.integers(1, 70), batch=st.integers(1, 20),
+           drop_last=st.booleans(), shuffle=st.booleans())
+    def check(n, batch, drop_last, shuffle):
+        data = TensorDataset(torch.arange(n))
+        loader = AdaptiveDataLoader(data, batch_size=batch, shuffle=shuffle,
+                                    drop_last=drop_last)
+        epoch = len(seen_epochs)
+        seen_epochs.append(epoch)
+        for _ in adl.remaining_epochs_until(epoch + 1):
+            got = []
+            for (values,) in loader:
+                assert 1 <= len(values) <= batch
+                got.extend(values.tolist())
+        if drop_last:
+            assert len(got) == n // batch * batch
+            assert len(set(got)) == len(got) and set(got) <= set(range(n))
+        else:
+            assert sorted(got) == list(range(n))
+    check()
+    return 0
