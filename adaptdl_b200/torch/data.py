@@ -56,10 +56,15 @@ class _PreemptionBeat(object):
     any preemption grace period.
 
     One instance per process: rounds continue across data loaders (training
-    and validation loops alternate), so short loops cannot starve it.
+    and validation loops alternate), so short loops cannot starve it. The
+    interval is only trusted while the pace is: every ``for batch in loader``
+    loop starts over at one iteration per round (its batch size, model mode
+    or dataset may differ from the previous loop's), and the interval never
+    exceeds ``MAX_INTERVAL`` iterations, so that a sudden slow-down cannot
+    push the reaction time towards a preemption grace period.
     """
 
-    MAX_INTERVAL = 1000
+    MAX_INTERVAL = 64
 
     def __init__(self):
         self.reset()
@@ -69,6 +74,7 @@ class _PreemptionBeat(object):
         self.interval = 1            # iterations between round starts
         self.countdown = 0           # iterations until the next round start
         self.started = None          # host time the pending round started
+        self.relearn = False
 
     @staticmethod
     def period():
@@ -83,6 +89,14 @@ class _PreemptionBeat(object):
         per_iteration = max(now - self.started, 1e-6) / self.interval
         return int(min(max(period / per_iteration, 1), self.MAX_INTERVAL))
 
+    def new_loop(self):
+        """A data-loader loop begins (same iteration on every replica): the
+        next beat resolves the round in flight and the pace is re-learned."""
+        self.countdown = 0
+        self.interval = 1
+        self.started = None
+        self.relearn = True      # the round in flight carries the OLD pace
+
     def beat(self):
         """Call once per training iteration on every replica."""
         if self.countdown > 0:
@@ -91,10 +105,12 @@ class _PreemptionBeat(object):
         now = time.monotonic()
         suggestion = self._suggestion(now)
         if self.pending is not None:
-            flagged, self.interval = self.pending.result()
+            flagged, agreed = self.pending.result()
             if flagged:
                 checkpoint.save_all_states()
                 sys.exit(EXIT_CODE_PREEMPTED)
+            self.interval = 1 if self.relearn else agreed
+        self.relearn = False
         # rank 0 is the left-most operand of the fold: its suggestion wins
         self.pending = collective.allreduce_async(
             (bool(get_exit_flag()), suggestion),
@@ -365,6 +381,7 @@ class AdaptiveDataLoaderHelper(object):
                                "loops over adaptive loaders cannot nest")
         epoch = current_epoch()
         cls._current = self
+        _PREEMPTION.new_loop()
         try:
             yield
         finally:

@@ -545,3 +545,28 @@ def test_dataloader_visits_every_sample_for_arbitrary_sizes():
             assert sorted(got) == list(range(n))
     check()
     return 0
+
+
+@elastic_multiprocessing
+def test_preemption_beat_relearns_its_pace_in_every_loop():
+    import time
+    from adaptdl_b200 import collective, env
+    from adaptdl_b200.torch import data
+    if env.num_restarts() == 0:
+        return 2
+    os.environ["ADAPTDL_HEARTBEAT_PERIOD"] = "0.05"
+    collective.initialize(env.master_addr(), env.master_port(),
+                          env.replica_rank(), env.num_replicas())
+    beat = data._PREEMPTION
+    for _ in range(400):                       # a fast loop: interval grows
+        beat.beat()
+        time.sleep(0.0005)
+    assert 4 < beat.interval <= beat.MAX_INTERVAL
+    beat.new_loop()                            # e.g. the validation loop
+    beat.beat()
+    assert beat.interval == 1 and beat.countdown == 0
+    for _ in range(3):                         # slow iterations: stays at 1
+        time.sleep(0.06)
+        beat.beat()
+        assert beat.interval == 1
+    return 0
