@@ -620,3 +620,36 @@ def test_quantity_scaling_roundtrip():
         assert discretize_resource(name, scaled) == \
             discretize_resource(name, quantity) * factor
     check()
+
+
+def test_json_patches_from_helm_values_are_applied(monkeypatch):
+    """job.patch.pods / job.patch.containers of the chart (RFC 6902 subset:
+    add / replace / remove, ``~1`` escapes, ``-`` appends)."""
+    from adaptdl_b200.sched.controller import _apply_json_patch
+    doc = {"metadata": {"annotations": {"a": "1"}},
+           "env": [{"name": "X", "value": "1"}], "keep": True}
+    patched = _apply_json_patch(doc, [
+        {"op": "add", "path": "/metadata/annotations/k8s.v1.cni.cncf.io~1networks",
+         "value": "macvlan-conf"},
+        {"op": "add", "path": "/env/0", "value": {"name": "FIRST"}},
+        {"op": "add", "path": "/env/-", "value": {"name": "LAST"}},
+        {"op": "replace", "path": "/metadata/annotations/a", "value": "2"},
+        {"op": "remove", "path": "/keep"},
+        {"op": "add", "path": "/spec/new/nested", "value": 5}])
+    assert patched["metadata"]["annotations"] == {
+        "a": "2", "k8s.v1.cni.cncf.io/networks": "macvlan-conf"}
+    assert [e["name"] for e in patched["env"]] == ["FIRST", "X", "LAST"]
+    assert "keep" not in patched and patched["spec"]["new"]["nested"] == 5
+    assert doc["env"] == [{"name": "X", "value": "1"}] and doc["keep"]
+    # end to end: the controller stamps them onto every job pod / container
+    monkeypatch.setenv("ADAPTDL_SUPERVISOR_URL", "http://sup:8080")
+    monkeypatch.setenv("ADAPTDL_JOB_PATCH_PODS", json.dumps([
+        {"op": "add", "path": "/metadata/annotations/net", "value": "ib0"}]))
+    monkeypatch.setenv("ADAPTDL_JOB_PATCH_CONTAINERS", json.dumps([
+        {"op": "add", "path": "/env/-",
+         "value": {"name": "NCCL_SOCKET_IFNAME", "value": "net1"}}]))
+    pod = build_pod({"namespace": "ns", "name": "j", "uid": "u"}, TEMPLATE,
+                    ["n0"], 0, 0, "host0")
+    assert pod["metadata"]["annotations"]["net"] == "ib0"
+    env = pod["spec"]["containers"][0]["env"]
+    assert env[-1] == {"name": "NCCL_SOCKET_IFNAME", "value": "net1"}
