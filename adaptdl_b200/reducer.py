@@ -113,13 +113,20 @@ class _Server(threading.Thread):
         return clients
 
     def run(self):
+        clients = []
         try:
             clients = self._accept_all()
             sel = selectors.DefaultSelector()
             for rank, conn in enumerate(clients):
                 sel.register(conn, selectors.EVENT_READ, rank)
             pending = {}                         # key -> {rank: obj}
+            dead = set()                         # ranks that hung up
             alive = self._replicas
+
+            def doomed(slot):
+                """A reduction some departed replica never contributed to
+                can never complete."""
+                return any(rank not in slot for rank in dead)
             while alive and not self._stop_event.is_set():
                 for skey, _ in sel.select(timeout=0.5):
                     conn, rank = skey.fileobj, skey.data
@@ -128,12 +135,21 @@ class _Server(threading.Thread):
                     except (ConnectionError, OSError):
                         sel.unregister(conn)
                         alive -= 1
+                        dead.add(rank)
+                        if any(doomed(slot) for slot in pending.values()):
+                            raise ConnectionError(
+                                "replica {} left in the middle of a "
+                                "collective".format(rank))
                         continue
                     slot = pending.setdefault(key, {})
                     slot[rank] = obj
                     if len(slot) == self._replicas:
                         del pending[key]
                         self._finish(key, slot, clients)
+                    elif doomed(slot):
+                        raise ConnectionError(
+                            "replica(s) {} are gone: the collective cannot "
+                            "complete".format(sorted(dead)))
         except Exception as exc:  # noqa: BLE001 - surfaced to clients
             if not self._stop_event.is_set():
                 self.error = exc
@@ -143,6 +159,14 @@ class _Server(threading.Thread):
                 self._listener.close()
             except OSError:
                 pass
+            if self.error is not None:
+                # fail fast: everybody blocked on a result gets a
+                # ConnectionError instead of waiting for a replica that died
+                for conn in clients:
+                    try:
+                        conn.shutdown(socket.SHUT_RDWR)
+                    except OSError:
+                        pass
 
     def _finish(self, key, slot, clients):
         with self._lock:

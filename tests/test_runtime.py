@@ -254,3 +254,38 @@ def test_print_exc_shows_tracebacks_of_hook_exceptions(capsys):
         hook(1)
     assert "lost in autograd" in capsys.readouterr().err
     assert hook.__name__ == "hook"
+
+
+def _fail_fast_worker(rank, port, out):
+    from adaptdl_b200.reducer import Reducer
+    reducer = Reducer(rank, 3, "127.0.0.1", port)
+    assert reducer.allreduce(1) == 3                  # everybody is there
+    if rank == 2:
+        os._exit(7)                                   # dies without a word
+    try:
+        reducer.allreduce(1)                          # can never complete
+        out.put((rank, "completed"))
+    except ConnectionError as exc:
+        out.put((rank, "ConnectionError"))
+    except Exception as exc:  # noqa: BLE001
+        out.put((rank, repr(exc)))
+
+
+def test_a_replica_dying_mid_job_fails_the_others_fast():
+    """The reference's reducer waits forever for a replica that is gone;
+    here the survivors get a ConnectionError within moments."""
+    import multiprocessing as mp
+    import time
+    from adaptdl_b200.utils import pick_unused_port
+    ctx = mp.get_context("fork")
+    out, port = ctx.Queue(), pick_unused_port()
+    procs = [ctx.Process(target=_fail_fast_worker, args=(r, port, out))
+             for r in range(3)]
+    began = time.time()
+    for proc in procs:
+        proc.start()
+    results = dict(out.get(timeout=60) for _ in range(2))
+    assert results == {0: "ConnectionError", 1: "ConnectionError"}, results
+    assert time.time() - began < 30
+    for proc in procs:
+        proc.join(10)
