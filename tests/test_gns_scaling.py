@@ -403,3 +403,61 @@ def test_layout_invariants_hold_for_arbitrary_models():
         # every parameter exactly once, in reverse registration order
         assert seen == list(reversed(range(len(numels))))
     check()
+
+
+def test_reducer_results_do_not_depend_on_bucketing():
+    """Property test (one replica, torch reducer): whatever the parameter
+    shapes, groups, unused parameters, accumulation pattern and bucket cap,
+    gradients and statistics equal a plain autograd reference."""
+    from hypothesis import given, settings, strategies as st
+    from adaptdl_b200.parallel.reducer_torch import TorchGradReducer
+
+    shape = st.lists(st.integers(1, 6), min_size=1, max_size=3)
+
+    @settings(max_examples=40, deadline=None)
+    @given(shapes=st.lists(shape, min_size=1, max_size=7),
+           cap=st.sampled_from([1e-5, 1e-4, 1e-3, 25.0]),
+           accum=st.integers(0, 2), seed=st.integers(0, 1000),
+           data=st.data())
+    def check(shapes, cap, accum, seed, data):
+        torch.manual_seed(seed)
+        params = [torch.nn.Parameter(torch.randn(s)) for s in shapes]
+        n_groups = data.draw(st.integers(1, min(3, len(params))))
+        member = [data.draw(st.integers(0, n_groups - 1)) for _ in params]
+        for g in range(n_groups):                  # no empty group
+            if g not in member:
+                member[g % len(params)] = g
+        if len(set(member)) < n_groups:
+            return
+        used = [data.draw(st.booleans()) for _ in params]
+        if not any(used):
+            used[0] = True
+        groups = [{"params": [p for p, m in zip(params, member) if m == g]}
+                  for g in range(n_groups)]
+        syncing = [True]
+        red = TorchGradReducer(groups, 1, 0, lambda: syncing[0],
+                               bucket_cap_mb=cap)
+        weights = [[torch.randn(s) for s in shapes]
+                   for _ in range(accum + 1)]
+
+        def loss(step):
+            return sum((p * w).sum() * (step + 1)
+                       for p, w, u in zip(params, weights[step], used) if u)
+        red.zero()
+        for step in range(accum + 1):
+            syncing[0] = step == accum
+            loss(step).backward()
+        stats = red.pop_stats()
+        # reference: the mean of the micro-step gradients
+        want = [sum(w[i] * (k + 1) for k, w in enumerate(weights))
+                / (accum + 1) if used[i] else torch.zeros(shapes[i])
+                for i in range(len(params))]
+        for p, w in zip(params, want):
+            torch.testing.assert_close(p.grad, w, rtol=1e-5, atol=1e-6)
+        total = [sum(float((want[i].double() ** 2).sum())
+                     for i in range(len(params)) if member[i] == g)
+                 for g in range(n_groups)]
+        assert stats.count == accum + 1
+        assert stats.total_sqr == pytest.approx(total, rel=1e-4, abs=1e-8)
+        red.detach()
+    check()
