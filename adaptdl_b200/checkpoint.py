@@ -127,6 +127,9 @@ class PickledFields(State):
             setattr(self, name, value)
 
 
+_REPLACED = ".replaced"
+
+
 def _staging_dir(root):
     path = os.path.join(root, _STAGING)
     os.makedirs(path, exist_ok=True)
@@ -139,13 +142,21 @@ def _generation_dirs(root):
         names = os.listdir(root)
     except FileNotFoundError:
         return out
+    replaced = {}
     for name in names:
         if name.startswith(CKPT_DIR_PREFIX):
+            stem = name[len(CKPT_DIR_PREFIX):]
+            target = out
+            if stem.endswith(_REPLACED):     # see save_all_states
+                stem, target = stem[:-len(_REPLACED)], replaced
             try:
-                out[int(name[len(CKPT_DIR_PREFIX):])] = \
-                    os.path.join(root, name)
+                target[int(stem)] = os.path.join(root, name)
             except ValueError:
                 continue
+    # a generation whose re-save died between its two renames survives as
+    # its previous copy
+    for gen, path in replaced.items():
+        out.setdefault(gen, path)
     return out
 
 
@@ -174,12 +185,17 @@ def save_all_states():
         return None
     final = os.path.join(root, CKPT_DIR_PREFIX + str(env.num_restarts()))
     staging = _staging_dir(root)
-    if os.path.isdir(final):       # re-save within the same generation
-        shutil.rmtree(final)
+    if os.path.isdir(final):       # re-save within the same generation:
+        # move the old copy aside instead of deleting it first, so that a
+        # crash at any point leaves one complete checkpoint on disk
+        aside = final + _REPLACED
+        shutil.rmtree(aside, ignore_errors=True)
+        os.rename(final, aside)
     os.rename(staging, final)      # atomic publish
     for path in _generation_dirs(root).values():
         if path != final:
             shutil.rmtree(path, ignore_errors=True)
+    shutil.rmtree(final + _REPLACED, ignore_errors=True)
     return root
 
 

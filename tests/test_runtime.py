@@ -289,3 +289,47 @@ def test_a_replica_dying_mid_job_fails_the_others_fast():
     assert time.time() - began < 30
     for proc in procs:
         proc.join(10)
+
+
+def test_resaving_a_generation_never_leaves_the_disk_without_a_checkpoint(
+        tmp_path, monkeypatch):
+    """Periodic saves inside one restart generation replace
+    ``checkpoint-N``; a crash between the two renames must leave the previous
+    copy loadable (the reference deletes first and renames second)."""
+    from adaptdl_b200 import checkpoint
+    checkpoint._reset_registry_for_tests()
+    monkeypatch.setenv("ADAPTDL_CHECKPOINT_PATH", str(tmp_path))
+    monkeypatch.setenv("ADAPTDL_NUM_RESTARTS", "0")
+
+    class Counter(checkpoint.State):
+        value = 0
+
+        def save(self, f):
+            pickle.dump(self.value, f)
+
+        def load(self, f):
+            self.value = pickle.load(f)
+    state = Counter("counter")
+    state.value = 1
+    checkpoint.save_all_states()
+    state.value = 2
+    real_rename, calls = os.rename, []
+
+    def crashing_rename(src, dst):
+        calls.append((src, dst))
+        if len(calls) == 2:                      # staging -> final
+            raise OSError("power cut")
+        return real_rename(src, dst)
+    monkeypatch.setattr(os, "rename", crashing_rename)
+    with pytest.raises(OSError):
+        checkpoint.save_all_states()
+    monkeypatch.setattr(os, "rename", real_rename)
+    # "restart": the previous copy of generation 0 is still found and loads
+    monkeypatch.setenv("ADAPTDL_NUM_RESTARTS", "1")
+    state.value = None
+    assert checkpoint.load_state(state) and state.value == 1
+    # and a later successful save cleans everything up
+    state.value = 3
+    checkpoint.save_all_states()
+    assert sorted(os.listdir(tmp_path)) == ["checkpoint-1"]
+    checkpoint._reset_registry_for_tests()
