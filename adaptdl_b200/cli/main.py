@@ -88,6 +88,8 @@ def submit(args, remaining):
         resource, image, remaining, name=args.name,
         pull_secret=os.getenv("ADAPTDL_SUBMIT_REPO_CREDS"),
         tensorboard=args.tensorboard)
+    if args.pod_per_node:
+        manifests.use_node_pods(job)
     created = _create(job)
     classes = json.loads(_kubectl("get", "storageclass", "-o",
                                   "json"))["items"]
@@ -190,6 +192,10 @@ def build_parser():
     p.add_argument("--tensorboard")
     p.add_argument("--checkpoint-storage-class")
     p.add_argument("--checkpoint-storage-size", default="1Gi")
+    p.add_argument("--pod-per-node", action="store_true",
+                   help="one pod per node hosting all of the job's replicas "
+                        "there (fused peer-memory reducer); wraps python "
+                        "commands in the replica launcher")
     p.set_defaults(handler=submit)
     p = sub.add_parser("logs", help="stream a job's logs")
     p.add_argument("jobname")

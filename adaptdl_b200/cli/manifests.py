@@ -9,6 +9,7 @@
 """
 
 import copy
+import os
 import uuid
 
 TENSORBOARD_PREFIX = "adaptdl-tensorboard-"
@@ -57,6 +58,25 @@ def prepare_job(resource, image, args, name=None, pull_secret=None,
     volumes.append({"name": PVC_VOLUME,
                     "persistentVolumeClaim": {"claimName": pvc_name}})
     return job, pvc_name
+
+
+LAUNCHER = ["-m", "adaptdl_b200.launch"]
+
+
+def use_node_pods(job):
+    """Turn a one-GPU-per-pod job into a one-pod-per-node job (in place):
+    ``spec.podPerNode`` plus the replica launcher in front of every
+    container command that starts a Python interpreter
+    (``python train.py`` -> ``python -m adaptdl_b200.launch train.py``).
+    Containers with another entry point are left alone -- they must start
+    ``ADAPTDL_LOCAL_REPLICAS`` processes themselves."""
+    job["spec"]["podPerNode"] = True
+    for container in job["spec"]["template"]["spec"]["containers"]:
+        command = container.get("command") or []
+        if command and os.path.basename(command[0]).startswith("python") \
+                and command[1:3] != LAUNCHER:
+            container["command"] = [command[0]] + LAUNCHER + command[1:]
+    return job
 
 
 def choose_storageclass(storage_classes, name=None):

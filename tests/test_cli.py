@@ -120,3 +120,24 @@ def test_jobfile_from_stdin(monkeypatch):
     from adaptdl_b200.cli import main as cli
     monkeypatch.setattr("sys.stdin", io.StringIO("kind: AdaptDLJob\nspec: {}\n"))
     assert cli._load_yaml("-") == {"kind": "AdaptDLJob", "spec": {}}
+
+
+def test_pod_per_node_flag_wraps_python_commands():
+    from adaptdl_b200.cli import manifests
+    from adaptdl_b200.cli.main import build_parser
+    args, rest = build_parser().parse_known_args(
+        ["submit", ".", "--pod-per-node"])
+    assert args.pod_per_node
+    job = {"spec": {"template": {"spec": {"containers": [
+        {"name": "main", "command": ["python3", "train.py", "--x"]},
+        {"name": "side", "command": ["/bin/sidecar"]},
+        {"name": "img-entrypoint"}]}}}}
+    manifests.use_node_pods(job)
+    manifests.use_node_pods(job)                       # idempotent
+    containers = job["spec"]["template"]["spec"]["containers"]
+    assert job["spec"]["podPerNode"] is True
+    assert containers[0]["command"] == ["python3", "-m",
+                                        "adaptdl_b200.launch", "train.py",
+                                        "--x"]
+    assert containers[1]["command"] == ["/bin/sidecar"]
+    assert "command" not in containers[2]
