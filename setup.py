@@ -61,6 +61,7 @@ setuptools.setup(
     },
     entry_points={"console_scripts": [
         "adaptdl-b200=adaptdl_b200.cli.main:main",
+        "adaptdl-b200-launch=adaptdl_b200.launch:main",
         "adaptdl-b200-local=adaptdl_b200.sched.local:main",
         "adaptdl-b200-local-cluster=adaptdl_b200.sched.local_cluster:main",
         "adaptdl-b200-on-ray-aws=adaptdl_b200.ray.aws.launch_job:main",
