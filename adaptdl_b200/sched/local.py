@@ -181,6 +181,7 @@ class LocalElasticJob(object):
         codes = [p.poll() for p in self.procs]
         if any(c is None for c in codes):
             if any(c not in (None, 0, EXIT_PREEMPTED) for c in codes):
+                self._log("replica_failed", exit_codes=codes)
                 self.kill()
                 return "failed"
             return None
@@ -189,6 +190,7 @@ class LocalElasticJob(object):
             return "finished"
         if all(c in (0, EXIT_PREEMPTED) for c in codes):
             return "preempted"
+        self._log("replica_failed", exit_codes=codes)
         return "failed"
 
     def signal_stop(self):
