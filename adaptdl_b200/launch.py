@@ -46,6 +46,8 @@ def replica_environments(environ=None):
 
 def exit_code(codes):
     """Code of the group from the replicas' codes (see module docstring)."""
+    # killed by SIGTERM before the handler was installed = preempted early
+    codes = [EXIT_PREEMPTED if c == -signal.SIGTERM else c for c in codes]
     failures = [c for c in codes if c not in (0, EXIT_PREEMPTED)]
     if failures:
         return failures[0] if failures[0] > 0 else 128 - failures[0]
@@ -67,8 +69,8 @@ def run(command, environ=None, poll=0.2):
     try:
         while True:
             codes = [proc.poll() for proc in procs]
-            failed = [c for c in codes
-                      if c is not None and c not in (0, EXIT_PREEMPTED)]
+            failed = [c for c in codes if c is not None and
+                      c not in (0, EXIT_PREEMPTED, -signal.SIGTERM)]
             if failed or all(c is not None for c in codes):
                 break
             time.sleep(poll)

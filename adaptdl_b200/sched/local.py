@@ -178,7 +178,12 @@ class LocalElasticJob(object):
     def poll(self):
         """``None`` while running; else ``"finished"`` / ``"preempted"`` /
         ``"failed"`` once every replica has exited."""
-        codes = [p.poll() for p in self.procs]
+        # a replica that receives SIGTERM before its interpreter has installed
+        # the handler (still importing torch) dies of the signal: it had
+        # nothing to checkpoint yet, which is a preemption, not a failure
+        # (Kubernetes reports the same case as exit code 143)
+        codes = [EXIT_PREEMPTED if c == -signal.SIGTERM else c
+                 for c in (p.poll() for p in self.procs)]
         if any(c is None for c in codes):
             if any(c not in (None, 0, EXIT_PREEMPTED) for c in codes):
                 self._log("replica_failed", exit_codes=codes)

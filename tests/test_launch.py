@@ -29,6 +29,7 @@ def test_exit_code_rules():
     assert launch.exit_code([0, 143]) == 143
     assert launch.exit_code([143, 3, 143]) == 3
     assert launch.exit_code([-9, 0]) == 137          # killed by a signal
+    assert launch.exit_code([-15, 143]) == 143       # SIGTERM before the handler
 
 
 def _launch(code, tmp_path, replicas=3, **popen):

@@ -5,6 +5,7 @@ training script on CPU/gloo (SIGTERM -> checkpoint -> exit 143 -> restart)."""
 import json
 import os
 import sys
+import time
 import urllib.request
 
 from adaptdl_b200.sched import local
@@ -128,3 +129,22 @@ def test_two_jobs_share_a_box_under_the_pollux_policy(tmp_path):
     allocs = [(d["job"], d["replicas"]) for _, w, d in cluster.events
               if w == "allocate"]
     assert ("a", 1) in allocs and ("b", 1) in allocs     # both got started
+
+
+def test_sigterm_during_startup_counts_as_preemption(tmp_path):
+    """A replica signalled before its interpreter installed the SIGTERM
+    handler dies of the signal (exit code -15). That is a preemption with
+    nothing to save, not a failure -- it used to fail whole jobs when two
+    rescales came close together."""
+    job = local.LocalElasticJob(
+        [sys.executable, "-c", "import time; time.sleep(60)"], 2,
+        checkpoint_dir=str(tmp_path), env={"PYTHONPATH": ROOT})
+    job.start(2)
+    time.sleep(0.3)                  # plain `sleep` has no handler at all
+    job.signal_stop()
+    deadline = time.time() + 30
+    state = None
+    while state is None and time.time() < deadline:
+        state = job.poll()
+        time.sleep(0.1)
+    assert state == "preempted", (state, job.events)
