@@ -15,6 +15,11 @@
 import logging
 import os
 
+# First of all: the SIGTERM / SIGINT handlers. Importing torch takes seconds,
+# and a replica that is preempted during that window would die of the signal
+# instead of leaving through the checkpoint-and-exit-143 path.
+from adaptdl_b200 import _signal  # noqa: F401  (isort: skip)
+
 import torch.distributed
 
 from adaptdl_b200 import __version__, collective, env
