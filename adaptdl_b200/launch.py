@@ -2,6 +2,7 @@
 
     python -m adaptdl_b200.launch train.py --epochs 10
     python -m adaptdl_b200.launch -m package.module --flag
+    python -m adaptdl_b200.launch --replicas 8 train.py      # by hand, one box
 
 Under the cluster scheduler a job normally gets one pod per replica. With
 ``spec.podPerNode: true`` it gets ONE pod per node holding all of the job's
@@ -34,6 +35,13 @@ def replica_environments(environ=None):
     environ = dict(os.environ if environ is None else environ)
     count = int(environ.get("ADAPTDL_LOCAL_REPLICAS") or 1)
     first = int(environ.get("ADAPTDL_REPLICA_RANK") or 0)
+    if "ADAPTDL_NUM_REPLICAS" not in environ:
+        # started by hand on one box (no scheduler): these replicas are the
+        # whole job
+        from adaptdl_b200.utils import pick_unused_port
+        environ.update(ADAPTDL_NUM_REPLICAS=str(count), ADAPTDL_NUM_NODES="1",
+                       ADAPTDL_MASTER_ADDR="127.0.0.1")
+        environ.setdefault("ADAPTDL_MASTER_PORT", str(pick_unused_port()))
     out = []
     for local in range(count):
         env = dict(environ)
@@ -98,9 +106,13 @@ def main(argv=None):
     if not argv or argv[0] in ("-h", "--help"):
         print(__doc__)
         return 0 if argv else 2
-    if argv[0] == "--":
+    environ = None
+    if argv[0] == "--replicas":          # by hand: N replicas on this box
+        environ = dict(os.environ, ADAPTDL_LOCAL_REPLICAS=argv[1])
+        argv = argv[2:]
+    if argv and argv[0] == "--":
         argv = argv[1:]
-    sys.exit(run([sys.executable] + argv))
+    sys.exit(run([sys.executable] + argv, environ))
 
 
 if __name__ == "__main__":

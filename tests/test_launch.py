@@ -91,3 +91,23 @@ def test_two_replicas_of_a_real_job_in_one_container(tmp_path):
          "2", "--size", "512"], env=env, timeout=240,
         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert done.returncode == 0, done.stdout[-2000:]
+
+
+def test_replicas_flag_runs_a_whole_job_by_hand(tmp_path):
+    """``--replicas N`` without a scheduler: the launcher supplies the
+    job-level variables itself (N replicas, one node, a free port)."""
+    script = os.path.join(ROOT, "examples", "linear_regression", "main.py")
+    env = dict(os.environ, PYTHONPATH=ROOT, CUDA_VISIBLE_DEVICES="",
+               OMP_NUM_THREADS="1", ADAPTDL_CHECKPOINT_PATH=str(tmp_path))
+    for stale in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "ADAPTDL_NUM_REPLICAS",
+                  "ADAPTDL_LOCAL_REPLICAS", "ADAPTDL_REPLICA_RANK",
+                  "ADAPTDL_MASTER_PORT"):
+        env.pop(stale, None)
+    done = subprocess.run(
+        [sys.executable, "-m", "adaptdl_b200.launch", "--replicas", "2",
+         script, "--epochs", "2", "--size", "512"], env=env, timeout=240,
+        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert done.returncode == 0, done.stdout[-2000:]
+    envs = launch.replica_environments({"ADAPTDL_LOCAL_REPLICAS": "3"})
+    assert {e["ADAPTDL_NUM_REPLICAS"] for e in envs} == {"3"}
+    assert len({e["ADAPTDL_MASTER_PORT"] for e in envs}) == 1
