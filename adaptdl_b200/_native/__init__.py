@@ -123,6 +123,11 @@ class ReduceArgs(ctypes.Structure):
         ("err", ctypes.c_void_p),
         ("timeout_ns", ctypes.c_ulonglong),
         ("mc_buf", ctypes.c_void_p),
+        ("pinv_mode", ctypes.c_int), ("pinv_wide", ctypes.c_int),
+        ("pinv_coef", ctypes.c_void_p),
+        ("stage", ctypes.c_void_p * MAX_RANKS),
+        ("fuse_fin", ctypes.c_int),
+        ("ticket", ctypes.c_void_p),
     ]
 
 
@@ -137,6 +142,10 @@ class LocalArgs(ctypes.Structure):
         ("s2", ctypes.c_void_p),
         ("flag", ctypes.c_int),
         ("flag_ptr", ctypes.c_void_p),
+        ("pinv_mode", ctypes.c_int), ("pinv_wide", ctypes.c_int),
+        ("pinv_coef", ctypes.c_void_p),
+        ("fuse_fin", ctypes.c_int),
+        ("ticket", ctypes.c_void_p),
     ]
 
 
@@ -164,6 +173,9 @@ class FinalizeArgs(ctypes.Structure):
         ("lr_factor", ctypes.c_void_p),
         ("err", ctypes.c_void_p),
         ("timeout_ns", ctypes.c_ulonglong),
+        ("last_stamp", ctypes.c_void_p),
+        ("clock", ctypes.c_void_p),
+        ("amp_scale", ctypes.c_void_p),
     ]
 
 
@@ -196,10 +208,21 @@ class OptimArgs(ctypes.Structure):
         ("step_offset", ctypes.c_void_p),
         ("n_groups", ctypes.c_int),
         ("master", ctypes.c_void_p),
+        ("grad_scale", ctypes.c_void_p),
+        ("pinv_coef", ctypes.c_void_p),
     ]
 
 
-MBOX_HDR = 8
+MBOX_HDR = 16           # mailbox header doubles (adl_kernels.cu ADL_MBOX_HDR)
+XCHG_TAIL = 4           # timing doubles after the statistic rows of an exchange record
+CLOCK_DOUBLES = 4
+# mailbox header fields
+(MB_SEQ, MB_FINITE, MB_GAIN, MB_PROGRESS, MB_SYNC_NS, MB_ERR, MB_SCALE,
+ MB_NROWS, MB_STEP_NS, MB_ACCUM_NS, MB_ACCUM_COUNT, MB_AMP_SCALE) = range(12)
+# reduce flavours (adl_allreduce_gns)
+(FLAVOUR_TWOSHOT, FLAVOUR_ONESHOT, FLAVOUR_NVLS) = range(3)
+# preconditioner modes of the statistics kernels
+(PINV_NONE, PINV_FLAT, PINV_ADAM) = range(3)
 SITES_PER_STEP = 1024
 HYPER_STRIDE = 8
 (RULE_ADASCALE, RULE_ADAMSCALE, RULE_LINEAR, RULE_SQRT, RULE_LEGW) = range(5)
@@ -249,12 +272,15 @@ def _declare(lib):
     lib.adl_error_string.restype = c.c_char_p
     lib.adl_error_string.argtypes = [c.c_int]
     lib.adl_sm_count.argtypes = [c.c_int]
-    lib.adl_allreduce_gns.argtypes = [c.POINTER(ReduceArgs), c.c_int,
-                                      c.c_int, c.c_void_p]
-    lib.adl_local.argtypes = [c.POINTER(LocalArgs), c.c_int, c.c_int,
-                              c.c_int, c.c_void_p]
+    lib.adl_allreduce_gns.argtypes = [c.POINTER(ReduceArgs),
+                                      c.POINTER(FinalizeArgs), c.c_int,
+                                      c.c_int, c.c_int, c.c_void_p]
+    lib.adl_local.argtypes = [c.POINTER(LocalArgs), c.POINTER(FinalizeArgs),
+                              c.c_int, c.c_int, c.c_int, c.c_void_p]
     lib.adl_finalize_stats.argtypes = [c.POINTER(FinalizeArgs), c.c_void_p]
     lib.adl_stamp.argtypes = [c.c_void_p, c.c_void_p]
+    lib.adl_step_mark.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p]
+    lib.adl_optim_advance.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p]
     lib.adl_bcast_pull.argtypes = [c.POINTER(BcastArgs), c.c_int,
                                    c.c_void_p]
     lib.adl_symm_last_error.restype = c.c_char_p
@@ -302,6 +328,8 @@ def _declare(lib):
             raise RuntimeError(
                 "ABI mismatch for {}: C {} vs ctypes {}".format(
                     struct.__name__, got, c.sizeof(struct)))
+    if lib.adl_mbox_hdr() != MBOX_HDR or lib.adl_xchg_tail() != XCHG_TAIL:
+        raise RuntimeError("ABI mismatch: mailbox / exchange layout")
     return lib
 
 

@@ -226,7 +226,8 @@ def fit_perf_params(num_nodes, num_replicas, atomic_bsz,
     Parameters that the data cannot identify are pinned (single batch size
     -> alpha_c; no multi-node / multi-replica / N>2 data -> the matching
     network terms), and without multi-node data the inter-node terms are
-    kept >= 1.1x the intra-node ones.
+    kept >= 1.1x the intra-node ones. Returns ``None`` when the objective is
+    not finite at the solution (degenerate measurements).
     """
     num_nodes = np.asarray(num_nodes)
     num_replicas = np.asarray(num_replicas)
@@ -256,6 +257,10 @@ def fit_perf_params(num_nodes, num_replicas, atomic_bsz,
         _objective, x0, args=args, jac=True, method="L-BFGS-B",
         bounds=scipy.optimize.Bounds(lower, upper, keep_feasible=True))
     params = np.array(result.x, dtype=float)
+    if not (np.all(np.isfinite(params)) and np.isfinite(result.fun)):
+        # L-BFGS silently hands back its starting point when the objective
+        # is not finite there: that is not a fit
+        return None
     if not np.any(num_nodes > 1):
         params[2] = max(params[2], params[4] * 1.1)
         params[3] = max(params[3], params[5] * 1.1)

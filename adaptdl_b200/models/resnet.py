@@ -17,7 +17,6 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from adaptdl_b200.ops.bn_act import BatchNormAct2d
-from adaptdl_b200.ops.strided_conv import strided_conv3x3
 
 __all__ = ["ResNet", "resnet18", "resnet34", "resnet50", "resnet101",
            "resnet152"]
@@ -64,11 +63,7 @@ class ResidualBlock(nn.Module):
             conv = getattr(self, "conv{}".format(i))
             norm = getattr(self, "bn{}".format(i))
             last = i == self.depth
-            # stride-2 3x3: optional phase-decomposed data gradient
-            # (ops/strided_conv.py, ADAPTDL_B200_PHASE_DGRAD=1)
-            out = strided_conv3x3(out, conv) if conv.stride == (2, 2) \
-                else conv(out)
-            out = norm(out, residual=skip if last else None)
+            out = norm(conv(out), residual=skip if last else None)
         return out
 
 
@@ -84,21 +79,6 @@ BasicBlock.expansion = 1
 Bottleneck.expansion = 4
 
 
-def padded_channels_conv2d(x, conv, multiple=8):
-    """``conv(x)`` computed on input / filter zero-padded to a multiple of
-    ``multiple`` input channels (identical result, tensor-core eligible)."""
-    pad = (-x.shape[1]) % multiple
-    w = conv.weight
-    if pad:
-        if x.is_contiguous(memory_format=torch.channels_last):
-            # channels are the innermost dimension: pad there, keep the format
-            x = F.pad(x.permute(0, 2, 3, 1), (0, pad)).permute(0, 3, 1, 2)
-            w = F.pad(w.permute(0, 2, 3, 1), (0, pad)).permute(0, 3, 1, 2)
-        else:
-            x = F.pad(x, (0, 0, 0, 0, 0, pad))
-            w = F.pad(w, (0, 0, 0, 0, 0, pad))
-    return F.conv2d(x, w, conv.bias, conv.stride, conv.padding,
-                    conv.dilation, conv.groups)
 
 
 class ResNet(nn.Module):
@@ -123,17 +103,8 @@ class ResNet(nn.Module):
             setattr(self, "layer{}".format(stage), nn.Sequential(*units))
         self.linear = nn.Linear(channels, num_classes)
 
-    def _stem(self, x):
-        # Experimental (ADAPTDL_B200_PAD_STEM=1, not timed on hardware yet):
-        # cuDNN has no tensor-core kernels for 3 input channels; zero-padding
-        # image and filter to 8 channels is the same convolution on the fast
-        # path. The parameter keeps its [64, 3, 3, 3] shape.
-        if x.is_cuda and os.environ.get("ADAPTDL_B200_PAD_STEM", "0") == "1":
-            return padded_channels_conv2d(x, self.conv1)
-        return self.conv1(x)
-
     def forward(self, x):
-        out = self.bn1(self._stem(x))
+        out = self.bn1(self.conv1(x))
         for stage in (self.layer1, self.layer2, self.layer3, self.layer4):
             out = stage(out)
         out = F.adaptive_avg_pool2d(out, 1)

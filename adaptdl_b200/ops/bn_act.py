@@ -147,15 +147,8 @@ class _BnAct(torch.autograd.Function):
         a.M, a.C, a.n_partial, a.relu = m, c, grid, int(relu)
         a.cb, a.counters = cb, _tickets(dev, c // cb)
         a.eps, a.momentum = eps, momentum
-        # experimental (not yet validated on hardware): keep one ReLU bit per
-        # element for the backward pass instead of re-reading y
-        bits = None
-        if relu and os.environ.get("ADAPTDL_B200_BN_BITMASK", "0") == "1":
-            bits = torch.empty(m * c // vec, dtype=torch.uint8, device=dev)
-            a.mask = bits.data_ptr()
         _launch(a, x.dtype, 0, grid, _grid(dev, m, c, vec, 4), dev)
-        ctx.save_for_backward(x, y if (relu and bits is None) else None,
-                              gamma, mean, rstd, bits)
+        ctx.save_for_backward(x, y if relu else None, gamma, mean, rstd)
         ctx.relu = bool(relu)
         ctx.has_res = residual is not None
         ctx.has_affine = (weight is not None, bias is not None)
@@ -167,7 +160,7 @@ class _BnAct(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         from adaptdl_b200._native import BnArgs
-        x, y, gamma, mean, rstd, bits = ctx.saved_tensors
+        x, y, gamma, mean, rstd = ctx.saved_tensors
         dev, c = x.device, x.shape[1]
         m = x.numel() // c
         vec = 4 if x.dtype == torch.float32 else 8
@@ -182,7 +175,6 @@ class _BnAct(torch.autograd.Function):
                               device=dev)
         a = BnArgs()
         a.x, a.y, a.dy = x.data_ptr(), _ptr(y), dy.data_ptr()
-        a.mask = _ptr(bits)
         a.dx, a.dres = dx.data_ptr(), _ptr(dres)
         a.gamma, a.mean, a.rstd = gamma.data_ptr(), mean.data_ptr(), \
             rstd.data_ptr()

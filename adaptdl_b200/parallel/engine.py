@@ -28,7 +28,8 @@ import torch
 
 from adaptdl_b200 import _native
 from adaptdl_b200._native import (
-    OptimArgs, HYPER_STRIDE, MBOX_HDR, GNS_TAIL, GNS_SQR_UNBIAS,
+    OptimArgs, HYPER_STRIDE, MBOX_HDR, MB_ERR, MB_PROGRESS, GNS_TAIL,
+    GNS_SQR_UNBIAS,
     GNS_VAR_UNBIAS, GNS_PROGRESS, GNS_BIASED, CTL_ACCUM_SCALE, CTL_SMOOTHING,
     CTL_RULE, CTL_RULE_ARG, CTL_ENABLED, RULE_ADASCALE, RULE_ADAMSCALE,
     RULE_LINEAR, RULE_SQRT, RULE_LEGW, check)
@@ -72,7 +73,8 @@ def supported_optimizer(optimizer):
 
 class DeviceEngine(object):
 
-    def __init__(self, reducer, optimizer, rule, gns_state):
+    def __init__(self, reducer, optimizer, rule, gns_state,
+                 precondition_stats=False, mp_scaler=None):
         self.reducer = reducer
         self.optimizer = optimizer
         self.rule = rule
@@ -81,6 +83,13 @@ class DeviceEngine(object):
         if self.kind is None or self.rule_code is None:
             raise ValueError("optimizer / scaling rule not supported by the "
                              "device engine")
+        if precondition_stats and self.kind != "adam":
+            raise ValueError("Adam-preconditioned statistics need Adam / "
+                             "AdamW")
+        # statistics of g / (sqrt(v_hat) + eps): the bucket kernels read the
+        # fused optimizer's second-moment arena in place
+        self.precondition_stats = bool(precondition_stats)
+        self.mp_scaler = None
         self._lib = _native.load()
         dev = reducer.device
         G = reducer.num_groups
@@ -98,7 +107,9 @@ class DeviceEngine(object):
                                        dtype=torch.float32).pin_memory()
         self._hyper_last = None
         self.opt_steps = torch.zeros(1, dtype=torch.int32, device=dev)
-        self._one_i32 = torch.ones(1, dtype=torch.int32, device=dev)
+        self._zero_i32 = torch.zeros(1, dtype=torch.int32, device=dev)
+        # per group: (rsqrt(1 - beta2^t) or 0 = no preconditioning, eps)
+        self.pinv_coef = torch.zeros(G, 2, dtype=torch.float32, device=dev)
         self._opt_steps_host = 0
         self._consumed = -1          # last optimizer step mirrored on host
         self._tables = []
@@ -106,6 +117,46 @@ class DeviceEngine(object):
             self._tables.append(self._build_tables(arena))
         self.push_gns_state(gns_state)
         reducer.engine = self
+        if mp_scaler is not None:
+            self.attach_scaler(mp_scaler)
+
+    # ------------------------------------------------------------------
+    # AMP loss scaling without host synchronisation
+    # ------------------------------------------------------------------
+
+    def attach_scaler(self, scaler):
+        """Keep the step host-sync free under ``torch.amp.GradScaler``: the
+        scaler hands ``optimizer.grad_scale`` (a device tensor) to optimizers
+        that declare ``_step_supports_amp_scaling`` instead of unscaling and
+        checking for infs with a blocking ``.item()``. The estimator divides
+        the scale out of the statistics on the device, flags non-finite
+        gradients (``lr_factor[G]``) and the fused optimizer unscales /
+        skips accordingly."""
+        if not scaler.is_enabled():
+            return
+        dev = self.reducer.device
+        if scaler._scale is None:
+            scaler._lazy_init_scale_growth_tracker(dev)
+        self.mp_scaler = scaler
+        self.reducer.set_amp_scale(scaler._scale)
+        self.optimizer._step_supports_amp_scaling = True
+
+    def second_moments(self, arena_index):
+        """``(flat exp_avg_sq arena, is_fp32_next_to_16bit_grads)``."""
+        table = self._tables[arena_index]
+        return table["state1"], table["master"] is not None
+
+    def reset_adam_state(self):
+        """What the reference does when the batch-size scale changes
+        (``gradient_noise_scale.py:313-330`` with step=0: the moments are
+        zeroed and the step count restarts), on the device."""
+        for table in self._tables:
+            for key in ("state0", "state1"):
+                if table[key] is not None:
+                    table[key].zero_()
+        self.opt_steps.zero_()
+        self.pinv_coef[:, 0].zero_()
+        self._opt_steps_host = 0
 
     # ------------------------------------------------------------------
     # layout tables + optimizer state arenas
@@ -246,6 +297,16 @@ class DeviceEngine(object):
         if self.kind == "adam" and loaded_step is not None:
             self.opt_steps.fill_(loaded_step)
             self._opt_steps_host = loaded_step
+        if self.kind == "adam":
+            self._init_pinv_coef(loaded_step or 0)
+
+    def _init_pinv_coef(self, step):
+        rows = []
+        for g in self.optimizer.param_groups:
+            beta2, eps = float(g["betas"][1]), float(g["eps"])
+            coef = (1.0 - beta2 ** step) ** -0.5 if step >= 5 else 0.0
+            rows.append((coef, eps))
+        self.pinv_coef.copy_(torch.tensor(rows, dtype=torch.float32))
 
     def _master_views(self, table):
         cached = table.get("_master_views")
@@ -353,6 +414,18 @@ class DeviceEngine(object):
         self.sync_hyper()
         red = self.reducer
         stream = torch.cuda.current_stream(red.device).cuda_stream
+        grad_scale = None
+        if self.mp_scaler is not None:
+            # handed over by GradScaler.step (None = already unscaled)
+            grad_scale = getattr(self.optimizer, "grad_scale", None)
+        G = self.num_groups
+        if self.kind == "adam":
+            # the step count advances only when the update is applied
+            check(self._lib.adl_optim_advance(
+                self.opt_steps.data_ptr(),
+                self.lr_factor.data_ptr() + 4 * G, stream),
+                "adl_optim_advance")
+            red.launches += 1
         for arena, table in zip(red.arenas, self._tables):
             args = OptimArgs()
             args.grad = arena.grad.data_ptr()
@@ -369,25 +442,24 @@ class DeviceEngine(object):
             args.n_vec = table["n_vec"]
             args.hyper = self.hyper.data_ptr()
             args.lr_factor = self.lr_factor.data_ptr()
-            # adam step = opt_steps (device) + 1, via step_ctr/step_offset
+            # adam step = opt_steps (device), advanced just above
             args.step_ctr = self.opt_steps.data_ptr()
-            args.step_offset = self._one().data_ptr()
+            args.step_offset = self._zero_i32.data_ptr()
             args.n_groups = self.num_groups
             args.master = table["master"].data_ptr() \
                 if table["master"] is not None else None
+            if grad_scale is not None:
+                args.grad_scale = grad_scale.data_ptr()
+            if self.kind == "adam" and self.precondition_stats:
+                args.pinv_coef = self.pinv_coef.data_ptr()
             grid = max(1, min(2 * red._sm_count,
                               (table["n_vec"] + 2 * 512 - 1) // (2 * 512)))
             check(self._lib.adl_fused_optim(
                 ctypes.byref(args), 1 if self.kind == "adam" else 0,
                 _DTYPE_CODE[arena.dtype], grid, stream), "adl_fused_optim")
             red.launches += 1
-        if self.kind == "adam":
-            self.opt_steps.add_(self._one())
         self._opt_steps_host += 1
         self.optimizer._opt_called = True    # keep LR schedulers quiet
-
-    def _one(self):
-        return self._one_i32
 
     # ------------------------------------------------------------------
     # host mirror of the device statistics
@@ -403,13 +475,13 @@ class DeviceEngine(object):
             return None
         arr = red.read_slot(target)
         self._consumed = target
-        if int(arr[5]) != 0:
+        if int(arr[MB_ERR]) != 0:
             raise RuntimeError("fused all-reduce timed out waiting for a "
-                               "peer (error word {})".format(int(arr[5])))
+                               "peer (error word {})".format(int(arr[MB_ERR])))
         G = self.num_groups
         gns_dict["sqr_avg"] = np.array(arr[MBOX_HDR:MBOX_HDR + G])
         gns_dict["var_avg"] = np.array(arr[MBOX_HDR + G:MBOX_HDR + 2 * G])
-        gns_dict["progress"] = float(arr[3])
+        gns_dict["progress"] = float(arr[MB_PROGRESS])
         return np.array(arr[:MBOX_HDR])
 
 

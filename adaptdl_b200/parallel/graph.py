@@ -43,6 +43,9 @@ class GraphedTrainStep(object):
         optimizer: the optimizer passed to ``net`` (patched by it).
         loss_fn: ``loss_fn(net, *inputs) -> scalar loss tensor``.
         autocast_dtype: e.g. ``torch.bfloat16`` (``None`` = no autocast).
+        grad_scaler: the ``torch.amp.GradScaler`` given to ``net`` (fp16
+            training); the device engine keeps it host-sync free, so the
+            scaled step is captured like any other.
         warmup: eager steps per configuration before capturing.
         enabled: ``False`` forces the eager path (same call signature).
 
@@ -54,10 +57,14 @@ class GraphedTrainStep(object):
     """
 
     def __init__(self, net, optimizer, loss_fn, autocast_dtype=None,
-                 warmup=3, enabled=True, channels_last=False):
+                 warmup=3, enabled=True, channels_last=False,
+                 grad_scaler=None):
         self.net = net
         self.optimizer = optimizer
         self.loss_fn = loss_fn
+        # torch.amp.GradScaler (the one passed to ``net`` as ``mp_scaler``):
+        # the step becomes scale(loss).backward(); step(optimizer); update()
+        self.grad_scaler = grad_scaler
         self.autocast_dtype = autocast_dtype
         self.warmup = max(1, int(warmup))
         self.enabled = enabled
@@ -80,8 +87,14 @@ class GraphedTrainStep(object):
                 loss = self.loss_fn(self.net, *inputs)
         else:
             loss = self.loss_fn(self.net, *inputs)
-        loss.backward()
-        self.optimizer.step()
+        scaler = self.grad_scaler
+        if scaler is not None and scaler.is_enabled():
+            scaler.scale(loss).backward()
+            scaler.step(self.optimizer)
+            scaler.update()
+        else:
+            loss.backward()
+            self.optimizer.step()
         return loss.detach()
 
     def _wants_nhwc(self, t):
@@ -158,6 +171,7 @@ class GraphedTrainStep(object):
         # the capture starts (no pinned allocations / H2D copies inside)
         net._pre_forward()
         net.gns._flush()
+        net.gns.before_captured_step(key[0], key[2])
         net.engine.sync_hyper()
         launches0 = red.launches
         ops0 = _ops_count.total()
@@ -188,6 +202,7 @@ class GraphedTrainStep(object):
         # host prologue: what zero_grad()/forward() do on the host
         net.gns._flush()
         net._pre_forward()
+        net.gns.before_captured_step(sync, k_before)
         net.engine.sync_hyper()
         cap.graph.replay()
         # host epilogue: what the backward hooks / optimizer.step() record

@@ -39,7 +39,8 @@ def _round_up(x, m):
 
 
 def plan_arena(numels, groups, itemsize, bucket_cap_bytes,
-               first_bucket_cap_bytes=None, world_size=1):
+               first_bucket_cap_bytes=None, world_size=1,
+               last_bucket_cap_bytes=None):
     """Plan one arena.
 
     Arguments:
@@ -52,6 +53,11 @@ def plan_arena(numels, groups, itemsize, bucket_cap_bytes,
             backward (small, so communication starts early); defaults to
             ``bucket_cap_bytes``.
         world_size: replicas sharing each bucket (slice alignment).
+        last_bucket_cap_bytes: if given, the parameters backward reaches
+            last (the first ones registered) are split off into a final
+            bucket of at most this payload (at least one parameter): that
+            bucket's reduction cannot overlap with backward, so it is kept
+            latency-sized.
 
     Returns ``(total_elements, buckets)``; ``buckets[i].segments`` are in
     arena order, and ``buckets`` is in expected completion order.
@@ -66,6 +72,20 @@ def plan_arena(numels, groups, itemsize, bucket_cap_bytes,
     if first_bucket_cap_bytes is None:
         first_bucket_cap_bytes = bucket_cap_bytes
     first_bucket_cap_bytes = min(first_bucket_cap_bytes, bucket_cap_bytes)
+
+    # index of the first parameter (in walk order = reverse registration)
+    # of the tail bucket: the longest run of first-registered parameters
+    # whose payload fits the cap
+    tail_from = -1
+    if last_bucket_cap_bytes is not None and len(numels) > 1:
+        payload = 0
+        for pidx in range(len(numels)):
+            payload += numels[pidx] * itemsize
+            if payload > last_bucket_cap_bytes and pidx > 0:
+                break
+            tail_from = pidx
+        if tail_from == len(numels) - 1:
+            tail_from = -1      # everything fits: no separate tail
 
     buckets = []
     cursor = 0            # arena cursor in elements
@@ -88,7 +108,8 @@ def plan_arena(numels, groups, itemsize, bucket_cap_bytes,
     for pidx in reversed(range(len(numels))):
         n = numels[pidx]
         cap = first_bucket_cap_bytes if not buckets else bucket_cap_bytes
-        if cur_segments and (cur_payload + n * itemsize) > cap:
+        if cur_segments and ((cur_payload + n * itemsize) > cap
+                             or pidx == tail_from):
             close_bucket()
         start = _round_up(cursor, vec)
         cur_segments.append(Segment(pidx, start, n, groups[pidx]))

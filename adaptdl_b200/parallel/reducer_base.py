@@ -91,6 +91,10 @@ class GradReducer(object):
     """
 
     FIRST_BUCKET_BYTES = 1 << 20
+    # The parameters backward reaches LAST (the first layers) get a small
+    # bucket of their own: its reduction is the only one that cannot overlap
+    # with backward, so it should be latency- not bandwidth-sized.
+    LAST_BUCKET_BYTES = 64 << 10
 
     def __init__(self, param_groups, world_size, rank, should_sync,
                  bucket_cap_mb=25, name="reducer"):
@@ -110,6 +114,7 @@ class GradReducer(object):
         self._hooks = []
         self._on_backward_end = None   # callable(sync: bool)
         self._sync_t0 = None
+        self._n_done = 0
         self.launches = 0            # fused-primitive launches (telemetry)
         self.device = None
 
@@ -140,7 +145,8 @@ class GradReducer(object):
             itemsize = torch.empty((), dtype=arena.dtype).element_size()
             arena.total, arena.buckets = layout.plan_arena(
                 [p.numel() for p in arena.params], arena.groups, itemsize,
-                self._bucket_cap, self.FIRST_BUCKET_BYTES, self.world_size)
+                self._bucket_cap, self.FIRST_BUCKET_BYTES, self.world_size,
+                last_bucket_cap_bytes=self.LAST_BUCKET_BYTES)
             for b in arena.buckets:
                 for seg in b.segments:
                     arena.bucket_of[seg.param_index] = b.index
@@ -258,7 +264,8 @@ class GradReducer(object):
         self._in_backward = True
         self._sync = bool(self._should_sync())
         self._k_before = self._accum_count
-        if self._precond_fn is not None:
+        self._n_done = 0
+        if self._precond_fn is not None and not self._device_preconditioner():
             self._refresh_preconditioner()
         self._on_begin_backward()
         Variable._execution_engine.queue_callback(self._end_backward)
@@ -268,7 +275,6 @@ class GradReducer(object):
     def _end_backward(self):
         # buckets whose parameters did not all receive gradients (unused
         # parameters) are flushed here, in order.
-        self._mark_sync_start()
         for arena in self.arenas:
             for b in range(len(arena.buckets)):
                 if not arena.done[b]:
@@ -278,6 +284,8 @@ class GradReducer(object):
         self._accum_count += 1
         if self._sync:
             self._stats_ready = self._finalize_step()
+        else:
+            self._mark_accum_step()
         self._in_backward = False
         if self._on_backward_end is not None:
             self._on_backward_end(self._sync)
@@ -286,17 +294,29 @@ class GradReducer(object):
     def _process_bucket(self, arena, b):
         arena.done[b] = True
         bucket = arena.buckets[b]
+        self._n_done += 1
+        # the step's last bucket: everything after it (statistics exchange,
+        # estimator, optimizer) is on the critical path, so the subclass may
+        # fold the finalize into this launch
+        last = self._sync and self._n_done == self.num_buckets
+        if last:
+            # "end of the local backward" for the sync-time measurement
+            self._mark_sync_start()
         if not self._sync:
             self._fold_acc(arena, bucket)
         elif self._k_before > 0:
             self._fold_final(arena, bucket)
             scale = 1.0 / (self.world_size * (self._k_before + 1))
-            self._reduce(arena, bucket, scale, want_local=False)
+            self._reduce(arena, bucket, scale, want_local=False, last=last)
         elif self.world_size > 1:
             self._reduce(arena, bucket, 1.0 / self.world_size,
-                         want_local=True)
+                         want_local=True, last=last)
         else:
-            self._pair(arena, bucket)
+            self._pair(arena, bucket, last=last)
+
+    @property
+    def num_buckets(self):
+        return sum(len(arena.buckets) for arena in self.arenas)
 
     def _refresh_preconditioner(self):
         for arena in self.arenas:
@@ -330,8 +350,16 @@ class GradReducer(object):
     def _on_begin_backward(self):
         pass
 
+    def _device_preconditioner(self):
+        """True if the kernels derive the preconditioner themselves (no
+        per-parameter refresh on the host)."""
+        return False
+
     def _mark_sync_start(self):
         self._sync_t0 = time.time()
+
+    def _mark_accum_step(self):
+        """End of an accumulation micro-step (no synchronisation)."""
 
     def _reset_partials(self):
         raise NotImplementedError
@@ -342,10 +370,10 @@ class GradReducer(object):
     def _fold_final(self, arena, bucket):
         raise NotImplementedError
 
-    def _reduce(self, arena, bucket, scale, want_local):
+    def _reduce(self, arena, bucket, scale, want_local, last=False):
         raise NotImplementedError
 
-    def _pair(self, arena, bucket):
+    def _pair(self, arena, bucket, last=False):
         raise NotImplementedError
 
     def _finalize_step(self):

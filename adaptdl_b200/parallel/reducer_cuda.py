@@ -8,6 +8,13 @@ all-reduces, ~10 element-wise/reduction launches per parameter, a second
 NCCL all-reduce for the statistics, one full fp32 copy of the gradients and
 ``1 + num_param_groups`` host synchronisations.
 
+Three flavours of the bucket kernel, chosen per bucket when the reducer is
+built (all ranks derive the same choice from the bucket plan): one-shot push
+for latency-bound buckets, NVLS (``multimem``) for the largest ones, two-shot
+P2P in between. The kernel of the step's LAST bucket also runs the statistics
+exchange and the noise-scale estimator in its last CTA (``fuse_fin``), so the
+exposed tail of a step is one small launch with two flag rounds.
+
 Stream plumbing: every primitive runs on a dedicated high-priority
 communication stream, ordered after the producing backward kernels by an
 event; the compute stream waits for the communication stream once, at the
@@ -26,7 +33,10 @@ import torch.distributed as dist
 from adaptdl_b200 import _native
 from adaptdl_b200._native import (ReduceArgs, LocalArgs, FinalizeArgs,
                                   BcastArgs, MAX_RANKS, MAX_CTAS, MBOX_HDR,
-                                  SITES_PER_STEP, check)
+                                  XCHG_TAIL, CLOCK_DOUBLES, SITES_PER_STEP,
+                                  FLAVOUR_TWOSHOT, FLAVOUR_ONESHOT,
+                                  FLAVOUR_NVLS, PINV_FLAT, PINV_ADAM,
+                                  MB_SYNC_NS, MB_ERR, check)
 from adaptdl_b200.parallel import layout, symm
 from adaptdl_b200.parallel.reducer_base import GradReducer, GradStats
 
@@ -82,7 +92,7 @@ class CudaGradReducer(GradReducer):
             raise ValueError("too many param groups for the fused "
                              "statistics kernels ({} > {})".format(
                                  G, self._lib.adl_max_groups()))
-        self._xchg_bytes = _round_up(2 * 4 * G * 8, _ALIGN)
+        self._xchg_bytes = _round_up(2 * (4 * G + XCHG_TAIL) * 8, _ALIGN)
         offsets, cursor = {}, 0
         offsets["pad"] = cursor
         cursor += _round_up(_PAD_BYTES, _ALIGN)
@@ -94,6 +104,29 @@ class CudaGradReducer(GradReducer):
             offsets[("grad", i)] = cursor
             itemsize = torch.empty((), dtype=arena.dtype).element_size()
             cursor += _round_up(max(arena.total, 1) * itemsize, _ALIGN)
+        # NVLS: buckets at least this large go through the switch
+        # (profiles/README.md: all-reduce sweep at N=8)
+        self._nvls_min_bytes = int(float(os.environ.get(
+            "ADAPTDL_B200_NVLS_MIN_MB", "16")) * (1 << 20))
+        self._nvls_ctas = max(1, min(int(os.environ.get(
+            "ADAPTDL_B200_NVLS_CTAS", "64")), MAX_CTAS - 1))
+        # one-shot push: buckets whose pushed bytes ((N-1) x bucket) stay
+        # below this are latency-bound; each gets N lanes of staging
+        self._oneshot_push_bytes = int(float(os.environ.get(
+            "ADAPTDL_B200_ONESHOT_KB", "1024")) * 1024)
+        self._flavour = {}
+        for i, arena in enumerate(self.arenas):
+            itemsize = torch.empty((), dtype=arena.dtype).element_size()
+            for b in arena.buckets:
+                nbytes = b.length * itemsize
+                if self.world_size > 1 and \
+                        (self.world_size - 1) * nbytes <= \
+                        self._oneshot_push_bytes:
+                    self._flavour[(i, b.index)] = FLAVOUR_ONESHOT
+                    offsets[("stage", i, b.index)] = cursor
+                    cursor += _round_up(self.world_size * nbytes, _ALIGN)
+                else:
+                    self._flavour[(i, b.index)] = FLAVOUR_TWOSHOT
         self._provider = symm.make_provider(
             self._pg if self._pg is not None else
             (dist.group.WORLD if self.world_size > 1 else None),
@@ -108,13 +141,14 @@ class CudaGradReducer(GradReducer):
                 offsets["staging"], _STAGING_BYTES)
         self._grad_ptrs = {}
         self._grad_mc = {}
-        # NVLS: buckets at least this large go through the switch. Measured
-        # at N=8 (profiles/r1_n8_final/allreduce_n8.json): the P2P flavour
-        # wins up to 64 MB, multimem with 96 CTAs wins at 256 MB
-        self._nvls_min_bytes = int(float(os.environ.get(
-            "ADAPTDL_B200_NVLS_MIN_MB", "128")) * (1 << 20))
-        self._nvls_ctas = max(1, min(int(os.environ.get(
-            "ADAPTDL_B200_NVLS_CTAS", "96")), MAX_CTAS - 1))
+        self._stage_ptrs = {}
+        for key, off in offsets.items():
+            if isinstance(key, tuple) and key[0] == "stage":
+                _, ai, bi = key
+                arena = self.arenas[ai]
+                itemsize = torch.empty((), dtype=arena.dtype).element_size()
+                nbytes = self.world_size * arena.buckets[bi].length * itemsize
+                _, self._stage_ptrs[(ai, bi)] = self._region.carve(off, nbytes)
         for i, arena in enumerate(self.arenas):
             itemsize = torch.empty((), dtype=arena.dtype).element_size()
             view, ptrs = self._region.carve(
@@ -124,6 +158,11 @@ class CudaGradReducer(GradReducer):
             self._grad_ptrs[i] = ptrs
             self._grad_mc[i] = (self._region.mc_ptr + offsets[("grad", i)]
                                 if self._region.mc_ptr else 0)
+            for b in arena.buckets:
+                if self._grad_mc[i] and self.world_size > 1 and \
+                        self._flavour[(i, b.index)] == FLAVOUR_TWOSHOT and \
+                        b.length * itemsize >= self._nvls_min_bytes:
+                    self._flavour[(i, b.index)] = FLAVOUR_NVLS
         # statistics, error word, timers, mailbox
         self._stats = torch.zeros(4, G, dtype=torch.float64, device=dev)
         self._result = torch.zeros(4, G, dtype=torch.float64, device=dev)
@@ -131,7 +170,19 @@ class CudaGradReducer(GradReducer):
         self._t_start = torch.zeros(1, dtype=torch.int64, device=dev)
         self._step_ctr = torch.zeros(1, dtype=torch.int32, device=dev)
         self._pair_state = torch.zeros(1, dtype=torch.int32, device=dev)
-        self._ring = 8
+        # step clock: %globaltimer of the previous step mark + the running
+        # accumulation-step totals (adl_kernels.cu, finalize_body)
+        self._last_stamp = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._clock = torch.zeros(CLOCK_DOUBLES, dtype=torch.float64,
+                                  device=dev)
+        self._ticket = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._amp_scale = None      # device float tensor (GradScaler._scale)
+        self._fin_fused = False
+        self.fuse_finalize = os.environ.get(
+            "ADAPTDL_B200_FUSE_FINALIZE", "1") != "0"
+        self.oneshot_launches = 0
+        self.nvls_launches = 0
+        self._ring = 16
         self._slot = MBOX_HDR + 4 * G
         self._mailbox = torch.zeros(self._ring * self._slot,
                                     dtype=torch.float64).pin_memory()
@@ -203,15 +254,32 @@ class CudaGradReducer(GradReducer):
             args.a = self._ensure(arena, "acc").data_ptr() + off
         if mode == 2:
             args.pv = self._ensure(arena, "prev").data_ptr() + off
-        args.pinv = (arena.pinv.data_ptr() + off) \
-            if (self._precond_fn is not None and arena.pinv is not None) \
-            else None
+        self._set_pinv(args, arena, ai, bucket.start, itemsize)
         args.n_vec = n_vec
         args.segs.seg_end = ends.data_ptr()
         args.segs.seg_group = groups.data_ptr()
         args.segs.n_seg = ends.numel()
         args.n_groups = self.num_groups
         return args, n_vec
+
+    def _set_pinv(self, args, arena, ai, start_elem, itemsize):
+        """Preconditioner of the squared norms: the device engine's Adam
+        second moments (read in place, no copies), or the host path's flat
+        divisor arena, or none."""
+        engine = self.engine
+        if engine is not None and engine.enabled and \
+                engine.precondition_stats:
+            moments, wide = engine.second_moments(ai)
+            args.pinv = moments.data_ptr() + \
+                start_elem * moments.element_size()
+            args.pinv_mode = PINV_ADAM
+            args.pinv_wide = int(wide)
+            args.pinv_coef = engine.pinv_coef.data_ptr()
+        elif self._precond_fn is not None and arena.pinv is not None:
+            args.pinv = arena.pinv.data_ptr() + start_elem * itemsize
+            args.pinv_mode = PINV_FLAT
+        else:
+            args.pinv = None
 
     def _row(self, r):
         return self._stats.data_ptr() + r * self.num_groups * 8
@@ -225,13 +293,39 @@ class CudaGradReducer(GradReducer):
     def _on_begin_backward(self):
         self._had_pair = False
 
+    def _device_preconditioner(self):
+        engine = self.engine
+        return engine is not None and engine.enabled and \
+            engine.precondition_stats
+
     def _mark_sync_start(self):
         check(self._lib.adl_stamp(
             self._t_start.data_ptr(),
             torch.cuda.current_stream(self.device).cuda_stream), "adl_stamp")
         self.launches += 1
 
-    def _launch_local(self, arena, bucket, mode, flag=0):
+    def _mark_accum_step(self):
+        # after this micro-step's folds, on the communication stream
+        self._order_after_compute()
+        check(self._lib.adl_step_mark(
+            self._last_stamp.data_ptr(), self._clock.data_ptr(),
+            self._comm.cuda_stream), "adl_step_mark")
+        self.launches += 1
+
+    def reset_step_clock(self):
+        """Forget the previous step mark: the next step's interval is not
+        measured (start of a training loop, after evaluation / a
+        checkpoint)."""
+        with torch.cuda.stream(self._comm):
+            self._last_stamp.zero_()
+            self._clock.zero_()
+
+    def set_amp_scale(self, scale_tensor):
+        """Device tensor holding the AMP loss scale the gradients carry
+        (``GradScaler._scale``); the device estimator divides it out."""
+        self._amp_scale = scale_tensor
+
+    def _launch_local(self, arena, bucket, mode, flag=0, last=False):
         args, n_vec = self._local_args(arena, bucket, mode)
         args.s0 = self._row(1) if mode == 2 else self._row(0)
         args.s1 = self._row(2)
@@ -239,9 +333,18 @@ class CudaGradReducer(GradReducer):
         args.flag = flag
         if mode == 2 and self.engine is not None and self.engine.enabled:
             args.flag_ptr = self._pair_state.data_ptr()
+        fin = None
+        if last and mode == 2 and self.fuse_finalize:
+            if flag:
+                self._had_pair = True
+            fin = self._finalize_args()
+            args.fuse_fin = 1
+            args.ticket = self._ticket.data_ptr()
+            self._fin_fused = True
         self._order_after_compute()
         check(self._lib.adl_local(
-            ctypes.byref(args), mode, _DTYPE_CODE[arena.dtype],
+            ctypes.byref(args), ctypes.byref(fin) if fin is not None else None,
+            mode, _DTYPE_CODE[arena.dtype],
             self._local_grid(n_vec), self._comm.cuda_stream), "adl_local")
         self.launches += 1
 
@@ -251,11 +354,12 @@ class CudaGradReducer(GradReducer):
     def _fold_final(self, arena, bucket):
         self._launch_local(arena, bucket, 1)
 
-    def _pair(self, arena, bucket):
-        self._launch_local(arena, bucket, 2, flag=int(self._prev_valid))
+    def _pair(self, arena, bucket, last=False):
+        self._launch_local(arena, bucket, 2, flag=int(self._prev_valid),
+                           last=last)
         self._had_pair = self._had_pair or self._prev_valid
 
-    def _reduce(self, arena, bucket, scale, want_local):
+    def _reduce(self, arena, bucket, scale, want_local, last=False):
         ai = self._arena_index(arena)
         ends, groups, n_vec, vec = self._seg[(ai, bucket.index)]
         itemsize = layout.VEC_BYTES // vec
@@ -274,32 +378,46 @@ class CudaGradReducer(GradReducer):
         args.segs.seg_group = groups.data_ptr()
         args.segs.n_seg = ends.numel()
         args.n_groups = self.num_groups
-        args.pinv = (arena.pinv.data_ptr() + off) \
-            if (self._precond_fn is not None and arena.pinv is not None) \
-            else None
+        self._set_pinv(args, arena, ai, bucket.start, itemsize)
         args.L = self._row(0)
         args.T = self._row(1)
         args.err = self._err.data_ptr()
         args.timeout_ns = _TIMEOUT_NS
         slice_vec = n_vec // self.world_size
-        if self._grad_mc.get(ai) and self.world_size > 1 and \
-                n_vec * layout.VEC_BYTES >= self._nvls_min_bytes:
+        flavour = self._flavour.get((ai, bucket.index), FLAVOUR_TWOSHOT) \
+            if self.world_size > 1 else FLAVOUR_TWOSHOT
+        if flavour == FLAVOUR_NVLS:
             # in-switch reduction: multimem.ld_reduce / multimem.st
             args.mc_buf = self._grad_mc[ai] + off
-            self.nvls_launches = getattr(self, "nvls_launches", 0) + 1
-            per_cta = 512 * 4
+            self.nvls_launches += 1
+            per_cta = 512 * 8
             grid = max(1, min(self._nvls_ctas,
                               (slice_vec + per_cta - 1) // per_cta))
+        elif flavour == FLAVOUR_ONESHOT:
+            for p in range(self.world_size):
+                args.stage[p] = self._stage_ptrs[(ai, bucket.index)][p]
+            self.oneshot_launches += 1
+            grid = max(1, min(self._reduce_ctas, (n_vec + 511) // 512))
         elif self.world_size > 1:
-            # each thread keeps 16/W vectors in flight per iteration
-            per_cta = 512 * max(16 // self.world_size, 1)
+            # each thread keeps 16/W vectors in flight per iteration; a CTA
+            # moves >= 64 KB of its slice so that small buckets leave the
+            # SMs to backward
+            per_cta = max(512 * max(16 // self.world_size, 1),
+                          (64 << 10) // layout.VEC_BYTES)
             grid = max(1, min(self._reduce_ctas,
                               (slice_vec + per_cta - 1) // per_cta))
         else:
             grid = self._local_grid(n_vec)
+        fin = None
+        if last and self.fuse_finalize:
+            fin = self._finalize_args()
+            args.fuse_fin = 1
+            args.ticket = self._ticket.data_ptr()
+            self._fin_fused = True
         self._order_after_compute()
         check(self._lib.adl_allreduce_gns(
-            ctypes.byref(args), _DTYPE_CODE[arena.dtype], grid,
+            ctypes.byref(args), ctypes.byref(fin) if fin is not None else None,
+            _DTYPE_CODE[arena.dtype], flavour, grid,
             self._comm.cuda_stream), "adl_allreduce_gns")
         self.launches += 1
 
@@ -309,7 +427,9 @@ class CudaGradReducer(GradReducer):
             raise RuntimeError("too many fused launches in one step")
         return self._site
 
-    def _finalize_step(self):
+    def _finalize_args(self):
+        """Arguments of this step's finalize (stand-alone launch, or fused
+        into the last bucket's kernel)."""
         pair_mode = self.world_size == 1 and self._k_before == 0
         engine = self.engine if (self.engine is not None
                                  and self.engine.enabled) else None
@@ -317,8 +437,7 @@ class CudaGradReducer(GradReducer):
             n_rows = 4 if pair_mode else 2
         else:
             n_rows = 4 if (pair_mode and self._had_pair) else 2
-        if pair_mode:
-            self._prev_valid = True
+        self._fin_rows = n_rows
         G = self.num_groups
         args = FinalizeArgs()
         for p in range(self.world_size):
@@ -332,7 +451,7 @@ class CudaGradReducer(GradReducer):
         for r in range(4):
             args.rows[r] = self._row(r)
         args.sum_mask = 0b0011 if self.world_size > 1 else 0
-        args.micro_steps = self._accum_count
+        args.micro_steps = self._k_before + 1
         args.pair_mode = int(pair_mode)
         args.pair_flag = int(self._had_pair)
         args.pair_state = self._pair_state.data_ptr()
@@ -346,11 +465,27 @@ class CudaGradReducer(GradReducer):
             args.lr_factor = engine.lr_factor.data_ptr()
         args.err = self._err.data_ptr()
         args.timeout_ns = _TIMEOUT_NS
-        self._order_after_compute()
-        check(self._lib.adl_finalize_stats(ctypes.byref(args),
-                                           self._comm.cuda_stream),
-              "adl_finalize_stats")
-        self.launches += 1
+        args.last_stamp = self._last_stamp.data_ptr()
+        args.clock = self._clock.data_ptr()
+        if self._amp_scale is not None:
+            args.amp_scale = self._amp_scale.data_ptr()
+        return args
+
+    def _finalize_step(self):
+        if self._fin_fused:
+            # the last bucket's kernel already carried the finalize
+            self._fin_fused = False
+            n_rows = self._fin_rows
+        else:
+            args = self._finalize_args()
+            n_rows = self._fin_rows
+            self._order_after_compute()
+            check(self._lib.adl_finalize_stats(ctypes.byref(args),
+                                               self._comm.cuda_stream),
+                  "adl_finalize_stats")
+            self.launches += 1
+        if self.world_size == 1 and self._k_before == 0:
+            self._prev_valid = True
         done = torch.cuda.Event()
         done.record(self._comm)
         # the optimizer (compute stream) must see the reduced gradients
@@ -400,20 +535,31 @@ class CudaGradReducer(GradReducer):
                 time.sleep(0)
         return arr
 
+    def peek_slot(self, step):
+        """Non-blocking :meth:`read_slot`: the slot's numpy view if the
+        device has published optimizer step ``step``, ``None`` if not yet,
+        ``False`` if the ring has already moved past it."""
+        lo = (step % self._ring) * self._slot
+        arr = self._mailbox.numpy()[lo:lo + self._slot]
+        seq = int(arr[0])
+        if seq == step + 1:
+            return arr
+        return False if seq > step + 1 else None
+
     def _resolve_stats(self, handle):
         step, done, count, n_rows = handle
         arr = self.read_slot(step, wait_event=done)
         G = self.num_groups
-        if int(arr[5]) != 0:
+        if int(arr[MB_ERR]) != 0:
             raise RuntimeError(
                 "fused all-reduce timed out waiting for a peer "
-                "(error word {})".format(int(arr[5])))
+                "(error word {})".format(int(arr[MB_ERR])))
         n = n_rows * G
         rows = np.array(arr[MBOX_HDR:MBOX_HDR + n],
                         dtype=np.float64).reshape(n_rows, G)
         pair = (rows[2], rows[3]) if n_rows == 4 else None
         return GradStats(rows[0], rows[1], count, pair,
-                         sync_time=float(arr[4]) * 1e-9)
+                         sync_time=float(arr[MB_SYNC_NS]) * 1e-9)
 
     # -- broadcast -----------------------------------------------------------
 

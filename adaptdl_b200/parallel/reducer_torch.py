@@ -115,7 +115,7 @@ class TorchGradReducer(GradReducer):
         g.add_(a)
         a.zero_()
 
-    def _reduce(self, arena, bucket, scale, want_local):
+    def _reduce(self, arena, bucket, scale, want_local, last=False):
         g = self._slice(arena, bucket, "grad")
         if want_local:
             self._add_norms(self._L, arena, bucket, g)
@@ -125,7 +125,7 @@ class TorchGradReducer(GradReducer):
             g.mul_(scale)
         self._add_norms(self._T, arena, bucket, g)
 
-    def _pair(self, arena, bucket):
+    def _pair(self, arena, bucket, last=False):
         g = self._slice(arena, bucket, "grad")
         pv = self._slice(arena, bucket, "prev")
         self._add_norms(self._T, arena, bucket, g)

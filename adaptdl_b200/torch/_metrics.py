@@ -65,6 +65,11 @@ class _MetricsState(checkpoint.PickledFields):
         self.progress = 0.0
 
 
+    def sync(self):
+        # before a checkpoint: book every step the device has timed
+        _book_device_records(wait=True)
+
+
 class _OpenStep(object):
     """Clock and counters of the iteration between ``profile_step_start``
     and ``profile_step_commit``."""
@@ -78,6 +83,7 @@ class _OpenStep(object):
 
 
 _METRICS_STATE = None        # the singleton record (lazily loaded)
+_DEVICE_TIMER = None         # weakref to a parallel.timer.DeviceStepTimer
 _OPEN_STEP = None            # iteration in flight
 _PREV_REPORT = None          # host time of the last hints report
 _REPORT_THREAD = None        # background fit + report in flight
@@ -103,6 +109,8 @@ def profile_step_start(atomic_bsz):
 
 
 def profile_sync_time(sync_time):
+    if device_timer() is not None:
+        return               # booked from the device record of the step
     _OPEN_STEP.sync_time += sync_time
 
 
@@ -123,6 +131,67 @@ def profile_step_commit(accumulation_step=False, step_time=None):
         return
     row["optim_sync_time"] += step.sync_time
     _maybe_report()
+
+
+# ---------------------------------------------------------------------------
+# device-timed steps (parallel/timer.py)
+# ---------------------------------------------------------------------------
+
+def set_device_timer(timer):
+    """Install the on-device step timer (``None`` removes it). Only the
+    first data-parallel instance of a process registers one: with several
+    (a GAN's generator and discriminator) its finalize-to-finalize interval
+    is the whole iteration."""
+    global _DEVICE_TIMER
+    import weakref
+    _DEVICE_TIMER = weakref.ref(timer) if timer is not None else None
+
+
+def device_timer():
+    """The active device timer, or ``None`` (host clocks are used)."""
+    timer = _DEVICE_TIMER() if _DEVICE_TIMER is not None else None
+    return timer if (timer is not None and timer.active()) else None
+
+
+def device_timer_reset():
+    timer = device_timer()
+    if timer is not None:
+        timer.reset()
+
+
+def _book_device_records(wait=False):
+    timer = device_timer()
+    if timer is None:
+        return 0
+    profile = _metrics_state().profile
+    records = timer.drain(wait=wait)
+    for rec in records:
+        row = profile[rec.key]
+        row["optim_step_time"] += rec.step_time
+        row["optim_sync_time"] += rec.sync_time
+        row["optim_count"] += 1
+        if rec.accum_count:
+            row["accum_step_time"] += rec.accum_time
+            row["accum_count"] += rec.accum_count
+    return len(records)
+
+
+def profile_step_commit_device(accumulation_step, commit):
+    """:func:`profile_step_commit` when the device times the steps: the
+    iteration is only *noted* here; it is booked (with the device's numbers)
+    once the GPU has published them, one or two iterations later, so the host
+    never waits. Accumulation micro-steps arrive with the optimizer step that
+    closes them."""
+    global _OPEN_STEP
+    step, _OPEN_STEP = _OPEN_STEP, None
+    timer = device_timer()
+    if not accumulation_step:
+        key = (env.num_nodes(), env.num_replicas(), step.atomic_bsz) \
+            if (commit and step is not None) else None
+        timer.note(key)
+    _book_device_records()
+    if commit and not accumulation_step:
+        _maybe_report()
 
 
 def _maybe_report():
@@ -236,14 +305,24 @@ def _fit_from(table):
         return np.array([row.get(name, 0) for _, row in table], dtype=float)
     optim_total, optim_n = col("optim_step_time"), col("optim_count")
     accum_total, accum_n = col("accum_step_time"), col("accum_count")
-    # device-timed sync can exceed a wall-clock step by jitter: clamp (the
+    # a measured sync can reach a step's duration by jitter: clamp (the
     # model needs step >= sync)
     sync_total = np.minimum(col("optim_sync_time"), optim_total)
     # an optimisation step minus its synchronisation costs about what an
     # accumulation step costs: pool both kinds of sample for the local time
     local_mean = (accum_total + optim_total - sync_total) / (accum_n + optim_n)
-    return fit_perf_params(nodes, replicas, atomic, local_mean,
-                           optim_total / optim_n)
+    optim_mean = optim_total / optim_n
+    # a row whose sync ate the whole step would put log(0) into the fit
+    # (the reference asserts here): keep the local time strictly positive
+    local_mean = np.maximum(local_mean, 1e-3 * optim_mean)
+    local_mean = np.maximum(local_mean, 1e-7)
+    params = fit_perf_params(nodes, replicas, atomic, local_mean, optim_mean)
+    if params is None or not np.all(np.isfinite(np.array(params,
+                                                          dtype=float))):
+        LOG.warning("performance fit did not converge to finite parameters; "
+                    "keeping the previous ones")
+        return None
+    return params
 
 
 def _fit_perf_params():
@@ -294,3 +373,4 @@ def _reset_for_tests():
         _METRICS_STATE.unregister()
     _METRICS_STATE = _OPEN_STEP = _PREV_REPORT = None
     _GRAD_PARAM_DICT.clear()
+    set_device_timer(None)

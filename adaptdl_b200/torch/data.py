@@ -363,7 +363,10 @@ class AdaptiveDataLoaderHelper(object):
         _PREEMPTION.beat()
         _metrics.profile_step_start(self.current_local_bsz)
         yield
-        if commit:
+        if _metrics.device_timer() is not None:
+            # steps are timed on the device and booked asynchronously
+            _metrics.profile_step_commit_device(self.is_accum_step(), commit)
+        elif commit:
             step_time = None
             if self._step_time_source is not None:
                 step_time = self._step_time_source()
@@ -382,6 +385,7 @@ class AdaptiveDataLoaderHelper(object):
         epoch = current_epoch()
         cls._current = self
         _PREEMPTION.new_loop()
+        _metrics.device_timer_reset()     # no step interval across loops
         try:
             yield
         finally:

@@ -230,6 +230,9 @@ class GradientNoiseScale(object):
     def _before_update(self):
         pass
 
+    def before_captured_step(self, sync, k_before):
+        pass
+
     _pending = False
 
     def _flush(self):
@@ -338,6 +341,9 @@ class AdamGradientNoiseScale(GradientNoiseScale):
     def _reset_adam_state(self, step=0):
         # NOTE (reference quirk, App. D3): with step=0 the factors are
         # (1-beta^0)/(1-beta^t) = 0, i.e. the moments are zeroed.
+        if self._engine is not None and self._engine.enabled and step == 0:
+            self._engine.reset_adam_state()      # same thing on the device
+            return
         for group in self._optimizer.param_groups:
             beta1, beta2 = group["betas"]
             for param in group["params"]:
@@ -357,6 +363,17 @@ class AdamGradientNoiseScale(GradientNoiseScale):
 
     def _before_update(self):
         scale = self._accum_scale * self.accum_count
+        if not np.isclose(scale, self._state["prev_scale"]):
+            self._reset_adam_state()
+            self._state["prev_scale"] = scale
+
+    def before_captured_step(self, sync, k_before):
+        """A CUDA-graph replay runs the optimizer inside the graph, i.e.
+        before the backward-end callback: do the scale-change reset ahead of
+        the replay."""
+        if not sync:
+            return
+        scale = self._accum_scale * (k_before + 1)
         if not np.isclose(scale, self._state["prev_scale"]):
             self._reset_adam_state()
             self._state["prev_scale"] = scale

@@ -112,6 +112,7 @@ class AdaptiveDataParallel(torch.nn.Module):
 
         self._state = _AdaptiveDataParallelState(
             model, optimizer, lr_scheduler, mp_scaler, name, self._engine)
+        self._state.adp = self
         checkpoint.load_state(self._state)
         exact_masters = False
         if self._engine is not None:
@@ -143,19 +144,29 @@ class AdaptiveDataParallel(torch.nn.Module):
         import os
         if fused_step is None:
             fused_step = os.environ.get("ADAPTDL_B200_FUSED", "1") != "0"
-        if not fused_step or mp_scaler is not None \
-                or isinstance(self.gns, AdamGradientNoiseScale) \
+        if not fused_step \
                 or type(self._reducer).__name__ != "CudaGradReducer":
             return None
         from adaptdl_b200.parallel.engine import DeviceEngine
         try:
-            engine = DeviceEngine(self._reducer, optimizer, self.scaling_rule,
-                                  optimizer.state["gns"])
+            engine = DeviceEngine(
+                self._reducer, optimizer, self.scaling_rule,
+                optimizer.state["gns"],
+                precondition_stats=isinstance(self.gns,
+                                              AdamGradientNoiseScale),
+                mp_scaler=mp_scaler)
         except ValueError as exc:
             LOG.info("device engine unavailable (%s); using the host path",
                      exc)
             return None
         self.gns.attach_engine(engine)
+        if _metrics.device_timer() is None:
+            # step / sync durations of the goodput profile come from the
+            # device's %globaltimer stamps (reference: host clocks,
+            # torch/_metrics.py:43-59)
+            from adaptdl_b200.parallel.timer import DeviceStepTimer
+            self._step_timer = DeviceStepTimer(self._reducer)
+            _metrics.set_device_timer(self._step_timer)
         return engine
 
     def _warn_if_unmastered_16bit(self, optimizer):
@@ -191,6 +202,37 @@ class AdaptiveDataParallel(torch.nn.Module):
                     if torch.is_tensor(b) and b.numel() > 0]
         return tensors
 
+    def _split_buffers(self):
+        """``(eager, deferred)`` buffers for ``broadcast_buffers``.
+
+        DDP (and the reference on top of it) re-broadcasts rank 0's buffers
+        before every training forward. For normalisation layers that track
+        running statistics the training forward only *updates* those buffers
+        (``r <- (1-m) r + m batch``), it never feeds them into the output, and
+        rank 0's sequence of values does not depend on the other ranks'. So
+        broadcasting rank 0's running statistics right before they are first
+        *used* -- the next evaluation-mode / no-grad forward -- leaves every
+        rank with exactly the values the per-step broadcast would have given
+        it, without two peer barriers and three launches on every step's
+        critical path. Buffers of any other module are broadcast every
+        forward, as before. ``ADAPTDL_B200_EAGER_BUFFER_BCAST=1`` restores
+        the per-forward broadcast for everything."""
+        import os
+        from torch.nn.modules.batchnorm import _NormBase
+        eager, deferred = [], []
+        lazy_ok = os.environ.get("ADAPTDL_B200_EAGER_BUFFER_BCAST",
+                                 "0") != "1"
+        seen = set()
+        for mod in self.module.modules():
+            is_norm = isinstance(mod, _NormBase) and mod.track_running_stats
+            for buf in mod.buffers(recurse=False):
+                if not torch.is_tensor(buf) or buf.numel() == 0 \
+                        or id(buf) in seen:
+                    continue
+                seen.add(id(buf))
+                (deferred if (is_norm and lazy_ok) else eager).append(buf)
+        return eager, deferred
+
     def _sync_module_states(self):
         """Rank 0's parameters and buffers win (construction and after every
         elastic restart)."""
@@ -211,13 +253,34 @@ class AdaptiveDataParallel(torch.nn.Module):
     @traced("forward")
     def forward(self, *args, **kwargs):
         self._pre_forward()
-        if self.broadcast_buffers and self._world_size > 1 \
-                and self.require_backward_grad_sync \
-                and torch.is_grad_enabled():
+        if self.broadcast_buffers and self._world_size > 1:
+            training = self.module.training and torch.is_grad_enabled()
+            if training and self.require_backward_grad_sync:
+                eager, deferred = self._split_buffers()
+                if eager:
+                    self._reducer.broadcast_parameters(eager)
+                self._deferred_buffers_stale = bool(deferred)
+            elif not training and self._deferred_buffers_stale:
+                self.sync_buffers()
+        return self.module(*args, **kwargs)
+
+    _deferred_buffers_stale = False
+
+    def train(self, mode=True):
+        # leaving training mode (``net.eval()``, called on every replica):
+        # the deferred running statistics are about to be used
+        if not mode and self._deferred_buffers_stale:
+            self.sync_buffers()
+        return super().train(mode)
+
+    def sync_buffers(self):
+        """Give every replica rank 0's buffers now (what the next
+        evaluation-mode forward does on its own)."""
+        if self._world_size > 1:
             buffers = self._module_tensors(buffers_only=True)
             if buffers:
                 self._reducer.broadcast_parameters(buffers)
-        return self.module(*args, **kwargs)
+        self._deferred_buffers_stale = False
 
     @contextlib.contextmanager
     def no_sync(self):
@@ -313,8 +376,12 @@ class _AdaptiveDataParallelState(checkpoint.State):
         self.gain = 1.0
         self.lr_factor = 1.0
         self.wide_state = None       # loaded, not yet applied to the engine
+        self.adp = None              # set by AdaptiveDataParallel
 
     def sync(self):
+        # called on every replica before a checkpoint is written
+        if self.adp is not None and self.adp._deferred_buffers_stale:
+            self.adp.sync_buffers()
         # device-resident estimator / Adam step counters -> host dicts
         if self.engine is not None and self.engine.enabled:
             self.engine.pull_gns_state(self.optimizer.state["gns"])

@@ -40,9 +40,8 @@ struct BnArgs {
   float* dbeta;         // [C]
   float* partial;       // [C / cb, grid.y, 2, cb] scratch
   int* counters;        // [C / cb] zero-initialised tickets (left zero again)
-  uint8_t* mask;        // optional [M * C / V] ReLU keep-bits, one byte per 16-byte vector:
-                        // written by the forward pass, read by the backward pass INSTEAD of y
-                        // (1/16 of the bytes)
+  uint8_t* mask;        // unused (kept for ABI stability; a 1-bit ReLU mask replacing the y read of
+                        // the backward pass was measured and was SLOWER: profiles/r2_validate)
   int cb;               // channels per reduce CTA (<= 64)
   float* coef;          // [2, C] scratch: forward (scale, shift); backward (s1/M, s2/M)
   int M, C;
@@ -57,7 +56,7 @@ struct BnArgs {
 //   partial sums; the LAST CTA to finish in a channel block (ticket counter, self-resetting)
 //   folds that block's grid.y partials in a fixed order (deterministic) and derives
 //   mean / rstd / scale / shift (forward) or dgamma / dbeta / s1/M / s2/M (backward).
-template <typename T, bool BWD, bool MASK>
+template <typename T, bool BWD>
 __global__ void __launch_bounds__(BN_THREADS)
 bn_reduce_kernel(const BnArgs a) {
   constexpr int V = VecTraits<T>::N;
@@ -90,10 +89,7 @@ bn_reduce_kernel(const BnArgs a) {
         vx[u] = ld_vec(static_cast<const char*>(a.x) + off);
         if (BWD) {
           vg[u] = ld_vec(static_cast<const char*>(a.dy) + off);
-          if (a.relu) {
-            if (MASK) vy[u].w[0] = a.mask[((size_t)r * a.C + my_c) / V];
-            else vy[u] = ld_vec(static_cast<const char*>(a.y) + off);
-          }
+          if (a.relu) vy[u] = ld_vec(static_cast<const char*>(a.y) + off);
         }
       }
     }
@@ -109,14 +105,7 @@ bn_reduce_kernel(const BnArgs a) {
         } else {
           float fg[V], fy[V];
           unpack<T>(vg[u], fg);
-          if (a.relu) {
-            if (MASK) {
-#pragma unroll
-              for (int e = 0; e < V; ++e) fy[e] = (float)((vy[u].w[0] >> e) & 1u);
-            } else {
-              unpack<T>(vy[u], fy);
-            }
-          }
+          if (a.relu) unpack<T>(vy[u], fy);
 #pragma unroll
           for (int e = 0; e < V; ++e) {
             const float g = (a.relu && !(fy[e] > 0.f)) ? 0.f : fg[e];
@@ -210,7 +199,7 @@ bn_reduce_kernel(const BnArgs a) {
 
 // forward:  y  = act(x * scale + shift + res)
 // backward: dx = gamma * rstd * (g - s1/M - xhat * s2/M),  dres = g,  g = dy * [y > 0]
-template <typename T, bool BWD, bool MASK>
+template <typename T, bool BWD>
 __global__ void __launch_bounds__(BN_THREADS)
 bn_apply_kernel(const BnArgs a) {
   constexpr int V = VecTraits<T>::N;
@@ -247,10 +236,7 @@ bn_apply_kernel(const BnArgs a) {
           if (a.res) vb[u] = ld_vec(static_cast<const char*>(a.res) + off);
         } else {
           vb[u] = ld_vec(static_cast<const char*>(a.dy) + off);
-          if (a.relu) {
-            if (MASK) vy[u].w[0] = a.mask[((size_t)r * a.C + my_c) / V];
-            else vy[u] = ld_vec(static_cast<const char*>(a.y) + off);
-          }
+          if (a.relu) vy[u] = ld_vec(static_cast<const char*>(a.y) + off);
         }
       }
     }
@@ -270,23 +256,10 @@ bn_apply_kernel(const BnArgs a) {
             out[e] = a.relu ? fmaxf(v, 0.f) : v;
           }
           st_vec(static_cast<char*>(a.y) + off, pack<T>(out));
-          if (MASK && a.relu) {
-            uint32_t bits = 0;
-#pragma unroll
-            for (int e = 0; e < V; ++e) bits |= (out[e] > 0.f ? 1u : 0u) << e;
-            a.mask[((size_t)r * a.C + my_c) / V] = (uint8_t)bits;
-          }
         } else {
           float fy[V], g[V];
           unpack<T>(vb[u], fb);
-          if (a.relu) {
-            if (MASK) {
-#pragma unroll
-              for (int e = 0; e < V; ++e) fy[e] = (float)((vy[u].w[0] >> e) & 1u);
-            } else {
-              unpack<T>(vy[u], fy);
-            }
-          }
+          if (a.relu) unpack<T>(vy[u], fy);
 #pragma unroll
           for (int e = 0; e < V; ++e) {
             g[e] = (a.relu && !(fy[e] > 0.f)) ? 0.f : fb[e];
@@ -301,25 +274,17 @@ bn_apply_kernel(const BnArgs a) {
   }
 }
 
-template <typename T, bool MASK>
-int run_masked(const BnArgs& a, int backward, int grid_y, int grid_apply, cudaStream_t s) {
-  const dim3 grid(a.C / a.cb, grid_y);
-  if (!backward) {
-    bn_reduce_kernel<T, false, false><<<grid, BN_THREADS, 0, s>>>(a);   // never reads the mask
-    bn_apply_kernel<T, false, MASK><<<grid_apply, BN_THREADS, 0, s>>>(a);
-  } else {
-    bn_reduce_kernel<T, true, MASK><<<grid, BN_THREADS, 0, s>>>(a);
-    bn_apply_kernel<T, true, MASK><<<grid_apply, BN_THREADS, 0, s>>>(a);
-  }
-  return (int)cudaGetLastError();
-}
-
-// The ReLU bit mask is a compile-time variant so that the default path (mask == null) keeps
-// the register footprint -- and with it the occupancy -- of the kernels without it.
 template <typename T>
 int run(const BnArgs& a, int backward, int grid_y, int grid_apply, cudaStream_t s) {
-  return (a.mask != nullptr && a.relu) ? run_masked<T, true>(a, backward, grid_y, grid_apply, s)
-                                       : run_masked<T, false>(a, backward, grid_y, grid_apply, s);
+  const dim3 grid(a.C / a.cb, grid_y);
+  if (!backward) {
+    bn_reduce_kernel<T, false><<<grid, BN_THREADS, 0, s>>>(a);
+    bn_apply_kernel<T, false><<<grid_apply, BN_THREADS, 0, s>>>(a);
+  } else {
+    bn_reduce_kernel<T, true><<<grid, BN_THREADS, 0, s>>>(a);
+    bn_apply_kernel<T, true><<<grid_apply, BN_THREADS, 0, s>>>(a);
+  }
+  return (int)cudaGetLastError();
 }
 
 }  // namespace

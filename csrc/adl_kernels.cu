@@ -3,29 +3,62 @@
 //
 //   adl_fold_acc       A += G ; L += |G/P|^2 ; G = 0
 //   adl_fold_final     L += |G/P|^2 ; G += A ; A = 0
-//   adl_allreduce_gns  fused two-shot all-reduce over NVLink peer mappings:
+//   adl_allreduce_gns  fused all-reduce over NVLink peer mappings:
 //                      G <- s * sum_r G_r (in place on every rank) with
 //                      L += sum_r |G_r/P|^2 and T += |G/P|^2 from the same
-//                      registers (reference call sites K1-K6)
+//                      registers (reference call sites K1-K6).
+//                      Three flavours, picked per bucket by the host:
+//                        two-shot P2P  (rank r reduces slice r from the peers'
+//                                       arenas and stores it back to all of them)
+//                        one-shot push (small buckets: every rank pushes its
+//                                       bucket into the peers' staging lanes,
+//                                       ONE flag round, local reduction)
+//                        NVLS          (multimem.ld_reduce / multimem.st: the
+//                                       NVSwitch reduces and multicasts)
+//                      The kernel of the LAST bucket of a step also runs the
+//                      statistics exchange + estimator (finalize) in its last
+//                      CTA: one launch and one peer barrier fewer per step.
 //   adl_pair_norm      T=|G/P|^2, Pp=|Pv/P|^2, Pa=|(G+Pv)/2P|^2 ; Pv = G
 //   adl_finalize_stats sum per-rank partial statistics over ranks through a
-//                      peer-mapped pad, publish to a pinned host mailbox with
-//                      %globaltimer stamps, reset the partials
+//                      peer-mapped pad, run the gradient-noise-scale estimator,
+//                      publish to a pinned host mailbox with %globaltimer
+//                      stamps (step and sync durations, max over ranks), reset
+//                      the partials
+//   adl_step_mark      %globaltimer interval of an accumulation micro-step
 //   adl_bcast_pull     rank src's staging buffer -> every rank
 //   adl_stamp          write %globaltimer to device memory
 //
 // No tensor cores: these are bandwidth / latency kernels. sm_100a specifics:
 // 128-bit L1-bypassing vector accesses, .sys-scope release/acquire flags on
-// NVLink-mapped signal pads, %globaltimer stamps, grids sized to leave SMs to
-// the concurrently running backward pass.
+// NVLink-mapped signal pads, multimem.* through the NVSwitch, %globaltimer
+// stamps, grids sized to leave SMs to the concurrently running backward pass.
+//
+// Synchronisation protocol of one optimizer step (all on the comm stream):
+//   * every bucket kernel has ONE peer barrier, at its start ("this rank's
+//     gradients of the bucket are final"); its own remote stores are fenced
+//     (fence.sys) before the kernel ends but nobody waits for them there;
+//   * the finalize (stand-alone kernel, or the last CTA of the last bucket
+//     kernel) has the step's only other barrier: a rank sends its flag after
+//     ALL its bucket kernels have completed, so passing it means every peer's
+//     stores have landed in this rank's arenas AND every peer has finished
+//     reading this rank's arenas -- the optimizer may read the gradients and
+//     the next backward may overwrite them.
 #include "adl_common.cuh"
 
 #include <stdio.h>
+#include <string.h>
 
 // error word bits (device -> host, sticky)
 #define ADL_ERR_TIMEOUT 1u
 #define ADL_MAX_STAT_SMEM (96 * 1024)
 
+// preconditioner modes (template parameter PINV)
+//   0 none
+//   1 `pinv` is a flat element-wise divisor in the gradient dtype (host path)
+//   2 `pinv` are Adam's second moments (exp_avg_sq) in the arena layout, fp32
+//     when `pinv_wide` (16-bit gradients with fp32 optimizer state) else in
+//     the gradient dtype; divisor = sqrt(v) * coef[g][0] + coef[g][1], and
+//     coef[g][0] == 0 switches preconditioning off (Adam warm-up).
 struct ReduceArgs {
   void* buf[ADL_MAX_RANKS];        // bucket start in every rank's G arena
   uint32_t* pad[ADL_MAX_RANKS];    // signal pad of every rank
@@ -37,16 +70,24 @@ struct ReduceArgs {
   int want_local;
   SegTable segs;
   int n_groups;
-  const void* pinv;                // local preconditioner slice or nullptr
+  const void* pinv;                // see the PINV modes above (or nullptr)
   double* L;                       // [n_groups] partial: sum_r |G_r/P|^2
   double* T;                       // [n_groups] partial: |G/P|^2
   uint32_t* err;                   // sticky error word (device)
   unsigned long long timeout_ns;
   void* mc_buf;                    // NVLS: multicast address of the bucket (or nullptr)
+  int pinv_mode;
+  int pinv_wide;
+  const float* pinv_coef;          // mode 2: [n_groups][2]
+  void* stage[ADL_MAX_RANKS];      // one-shot: every rank's staging area of this bucket
+                                   // ([world][n_vec] vectors, lane r written by rank r)
+  int fuse_fin;                    // the last CTA to finish runs the finalize
+  uint32_t* ticket;                // device: CTA completion counter (fuse_fin)
 };
 
 __device__ __forceinline__ bool wait_flag(const uint32_t* p, uint32_t epoch,
                                           unsigned long long timeout_ns, uint32_t* err) {
+  if ((int32_t)(ld_acquire_sys(p) - epoch) >= 0) return true;
   const uint64_t t0 = globaltimer_ns();
   uint32_t spins = 0;
   while ((int32_t)(ld_acquire_sys(p) - epoch) < 0) {
@@ -60,9 +101,9 @@ __device__ __forceinline__ bool wait_flag(const uint32_t* p, uint32_t epoch,
 }
 
 // Flag values ("epochs") are derived on the device: step counter (bumped by
-// the finalize kernel once per optimizer step) * ADL_SITES_PER_STEP + the
-// launch's ordinal within the step. Nothing launch-specific is baked into
-// kernel arguments, so a captured CUDA graph can be replayed step after step.
+// the finalize once per optimizer step) * ADL_SITES_PER_STEP + the launch's
+// ordinal within the step. Nothing launch-specific is baked into kernel
+// arguments, so a captured CUDA graph can be replayed step after step.
 #define ADL_SITES_PER_STEP 1024u
 __device__ __forceinline__ uint32_t launch_epoch(const uint32_t* step_ctr, uint32_t site) {
   return (*reinterpret_cast<const volatile uint32_t*>(step_ctr)) * ADL_SITES_PER_STEP + site;
@@ -81,355 +122,56 @@ __device__ __forceinline__ void cta_barrier_peers(const ReduceArgs& a, int phase
 }
 
 // ---------------------------------------------------------------------------
-// fused two-shot all-reduce + gradient-noise-scale statistics
+// element-wise reciprocal preconditioner of one 16-byte gradient vector
 // ---------------------------------------------------------------------------
-// W > 0: world size known at compile time (2, 4, 8): the per-peer loads are a
-// fully unrolled register array and each thread keeps U = 16/W vectors in
-// flight (16 independent 16-byte requests per thread; with 32 CTAs x 512
-// threads that is ~4 MB outstanding, enough to cover the ~2-3 us NVLink
-// round trip at full link bandwidth). W == 0: generic fallback, runtime world.
-template <int W> struct ReduceUnroll { static constexpr int U = 16 / W; };
-template <> struct ReduceUnroll<0> { static constexpr int U = 1; };
-template <> struct ReduceUnroll<1> { static constexpr int U = 8; };
-
-template <typename T, int W, bool HAS_PINV>
-__global__ void __launch_bounds__(ADL_THREADS, 1)
-allreduce_gns_kernel(const ReduceArgs a) {
-  extern __shared__ double s_stats[];                 // [2][n_groups]
-  constexpr int N = VecTraits<T>::N;
-  constexpr int U = ReduceUnroll<W>::U;
-  constexpr int WMAX = (W > 0) ? W : ADL_MAX_RANKS;
-  smem_stats_zero(s_stats, 2 * a.n_groups);
-  GroupAccum<2> accum;
-  accum.init(s_stats, a.n_groups);
-
-  const int world = (W > 0) ? W : a.world;
-  if (world > 1) cta_barrier_peers(a, 0);             // every rank's grads are ready
-
-  const int slice = a.n_vec / world;
-  const int base = a.rank * slice;
-  const int stride = gridDim.x * blockDim.x;
-  const int first = blockIdx.x * blockDim.x + threadIdx.x;
-  const int iters = (slice + stride * U - 1) / (stride * U);   // same for every lane
-  int cur[U];
-#pragma unroll
-  for (int u = 0; u < U; ++u) cur[u] = -1;
-
-  // peer order rotated so that rank r starts with its own copy and the ranks
-  // do not all hammer the same peer at once
-  const Vec16* src[WMAX];
-  Vec16* dst[WMAX];
-#pragma unroll
-  for (int p = 0; p < WMAX; ++p) {
-    const int q = (p < world) ? (a.rank + p) % world : a.rank;
-    src[p] = static_cast<const Vec16*>(a.buf[q]);
-    dst[p] = static_cast<Vec16*>(a.buf[q]);
-  }
-
-  for (int it = 0; it < iters; ++it) {
-    Vec16 in[U][WMAX];
-    Vec16 pv[U];
-    int idx[U];
-    bool active[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      idx[u] = first + (it * U + u) * stride;
-      active[u] = idx[u] < slice;
-      if (active[u]) {
-#pragma unroll
-        for (int p = 0; p < WMAX; ++p)
-          if (p < world) in[u][p] = ld_vec(src[p] + base + idx[u]);
-        if (HAS_PINV) pv[u] = ld_vec(static_cast<const Vec16*>(a.pinv) + base + idx[u]);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      float sq[2] = {0.f, 0.f};
-      int g = -1;
-      if (active[u]) {
-        const int v = base + idx[u];
-        float sum[N], pinv[N];
-        if (HAS_PINV) {
-          unpack<T>(pv[u], pinv);
-#pragma unroll
-          for (int e = 0; e < N; ++e) pinv[e] = 1.0f / pinv[e];
-        }
-#pragma unroll
-        for (int e = 0; e < N; ++e) sum[e] = 0.f;
-#pragma unroll
-        for (int p = 0; p < WMAX; ++p) {
-          if (p < world) {
-            float x[N];
-            unpack<T>(in[u][p], x);
-#pragma unroll
-            for (int e = 0; e < N; ++e) {
-              sum[e] += x[e];
-              const float y = HAS_PINV ? x[e] * pinv[e] : x[e];
-              sq[0] = fmaf(y, y, sq[0]);
-            }
-          }
-        }
-#pragma unroll
-        for (int e = 0; e < N; ++e) {
-          sum[e] *= a.scale;
-          const float y = HAS_PINV ? sum[e] * pinv[e] : sum[e];
-          sq[1] = fmaf(y, y, sq[1]);
-        }
-        const Vec16 out = pack<T>(sum);
-#pragma unroll
-        for (int p = 0; p < WMAX; ++p)
-          if (p < world) st_vec(dst[p] + v, out);
-        if (cur[u] < 0) cur[u] = seg_find(a.segs, v);
-        while (__ldg(a.segs.seg_end + cur[u]) <= v) ++cur[u];
-        g = __ldg(a.segs.seg_group + cur[u]);
-        if (!a.want_local) sq[0] = 0.f;
-      }
-      accum.add(g, sq);
-    }
-  }
-  accum.flush_warp();
-  double* outs[2] = {a.want_local ? a.L : nullptr, a.T};
-  smem_stats_flush<2>(s_stats, a.n_groups, outs);
-
-  if (world > 1) cta_barrier_peers(a, 1);             // every slice has landed everywhere
-}
-
-// ---------------------------------------------------------------------------
-// NVLS flavour: the NVSwitch reduces. `multimem.ld_reduce` on the multicast
-// address returns sum_r g_r of a vector in ONE load (the switch pulls every
-// GPU's copy and adds in flight), `multimem.st` writes the mean into every
-// GPU's arena with ONE store. Per GPU that is ~B out + ~B(1+1/W) in instead
-// of 2(W-1)/W*B each way, and W times fewer load instructions.
-// The switch hides the per-replica values, so sum_r |g_r|^2 comes from a local
-// pass over this rank's own bucket (HBM speed, before the start barrier --
-// peers may only overwrite it after they have seen this rank's start flag);
-// the per-rank partials are summed by the finalize kernel like all others.
-// ---------------------------------------------------------------------------
-template <typename T> struct Multimem;
-template <> struct Multimem<float> {
-  static __device__ __forceinline__ Vec16 ld_reduce(const void* p) {
-    Vec16 v;
-    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(v.w[0]), "=r"(v.w[1]), "=r"(v.w[2]), "=r"(v.w[3]) : "l"(p) : "memory");
-    return v;
-  }
-};
-template <> struct Multimem<__nv_bfloat16> {
-  static __device__ __forceinline__ Vec16 ld_reduce(const void* p) {
-    Vec16 v;
-    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(v.w[0]), "=r"(v.w[1]), "=r"(v.w[2]), "=r"(v.w[3]) : "l"(p) : "memory");
-    return v;
-  }
-};
-template <> struct Multimem<__half> {
-  static __device__ __forceinline__ Vec16 ld_reduce(const void* p) {
-    Vec16 v;
-    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.f16x2 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(v.w[0]), "=r"(v.w[1]), "=r"(v.w[2]), "=r"(v.w[3]) : "l"(p) : "memory");
-    return v;
-  }
-};
-__device__ __forceinline__ void multimem_st(void* p, const Vec16& v) {
-  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
-               :: "l"(p), "r"(v.w[0]), "r"(v.w[1]), "r"(v.w[2]), "r"(v.w[3]) : "memory");
-}
-
-template <typename T, bool HAS_PINV>
-__global__ void __launch_bounds__(ADL_THREADS, 1)
-allreduce_nvls_kernel(const ReduceArgs a) {
-  extern __shared__ double s_stats[];                 // [2][n_groups]
-  constexpr int N = VecTraits<T>::N;
-  constexpr int U = 4;
-  smem_stats_zero(s_stats, 2 * a.n_groups);
-  GroupAccum<2> accum;
-  accum.init(s_stats, a.n_groups);
-  const int stride = gridDim.x * blockDim.x;
-  const int first = blockIdx.x * blockDim.x + threadIdx.x;
-  const Vec16* mine = static_cast<const Vec16*>(a.buf[a.rank]);
-
-  const int slice = a.n_vec / a.world;
-  const int iters = (slice + stride * U - 1) / (stride * U);
-  if (a.want_local) {
-    // L += |g_local / P|^2 over the whole bucket. CTA c of this rank reads,
-    // in EVERY slice q, exactly the vectors that CTA c of rank q will later
-    // overwrite -- the per-CTA start barrier below is then enough to order
-    // these reads before the peers' multicast stores.
-    for (int q = 0; q < a.world; ++q) {
-      int cur[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) cur[u] = -1;
-      for (int it = 0; it < iters; ++it) {
-        Vec16 in[U], pv[U];
-        int idx[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          idx[u] = first + (it * U + u) * stride;
-          if (idx[u] < slice) {
-            in[u] = ld_vec(mine + q * slice + idx[u]);
-            if (HAS_PINV) pv[u] = ld_vec(static_cast<const Vec16*>(a.pinv) + q * slice + idx[u]);
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          float sq[2] = {0.f, 0.f};
-          int g = -1;
-          if (idx[u] < slice) {
-            const int v = q * slice + idx[u];
-            float x[N], pinv[N];
-            unpack<T>(in[u], x);
-            if (HAS_PINV) unpack<T>(pv[u], pinv);
-#pragma unroll
-            for (int e = 0; e < N; ++e) {
-              const float y = HAS_PINV ? x[e] / pinv[e] : x[e];
-              sq[0] = fmaf(y, y, sq[0]);
-            }
-            if (cur[u] < 0) cur[u] = seg_find(a.segs, v);
-            while (__ldg(a.segs.seg_end + cur[u]) <= v) ++cur[u];
-            g = __ldg(a.segs.seg_group + cur[u]);
-          }
-          accum.add(g, sq);
-        }
-      }
-    }
-    accum.flush_warp();
-  }
-
-  cta_barrier_peers(a, 0);                            // every rank's grads are ready
-
-  const int base = a.rank * slice;
-  Vec16* mc = static_cast<Vec16*>(a.mc_buf);
-  int cur[U];
-#pragma unroll
-  for (int u = 0; u < U; ++u) cur[u] = -1;
-  for (int it = 0; it < iters; ++it) {
-    Vec16 in[U], pv[U];
-    int idx[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      idx[u] = first + (it * U + u) * stride;
-      if (idx[u] < slice) {
-        in[u] = Multimem<T>::ld_reduce(mc + base + idx[u]);
-        if (HAS_PINV) pv[u] = ld_vec(static_cast<const Vec16*>(a.pinv) + base + idx[u]);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      float sq[2] = {0.f, 0.f};
-      int g = -1;
-      if (idx[u] < slice) {
-        const int v = base + idx[u];
-        float x[N], pinv[N];
-        unpack<T>(in[u], x);
-        if (HAS_PINV) unpack<T>(pv[u], pinv);
-#pragma unroll
-        for (int e = 0; e < N; ++e) {
-          x[e] *= a.scale;
-          const float y = HAS_PINV ? x[e] / pinv[e] : x[e];
-          sq[1] = fmaf(y, y, sq[1]);
-        }
-        multimem_st(mc + v, pack<T>(x));
-        if (cur[u] < 0) cur[u] = seg_find(a.segs, v);
-        while (__ldg(a.segs.seg_end + cur[u]) <= v) ++cur[u];
-        g = __ldg(a.segs.seg_group + cur[u]);
-      }
-      accum.add(g, sq);
-    }
-  }
-  accum.flush_warp();
-  double* outs[2] = {a.want_local ? a.L : nullptr, a.T};
-  smem_stats_flush<2>(s_stats, a.n_groups, outs);
-
-  cta_barrier_peers(a, 1);                            // every slice has landed everywhere
-}
-
-// ---------------------------------------------------------------------------
-// local folds (gradient accumulation) and the single-replica pair norm
-// ---------------------------------------------------------------------------
-struct LocalArgs {
-  void* g; void* a; void* pv; const void* pinv;
-  int n_vec;
-  SegTable segs;
-  int n_groups;
-  double* s0; double* s1; double* s2;   // statistic outputs (see kernels)
-  int flag;                             // MODE 2: previous-step stash is valid
-  const int* flag_ptr;                  // if non-null, overrides `flag` (device-resident state)
-};
-
-// MODE 0: fold_acc   (a += g ; s0 += |g|^2 ; g = 0)
-// MODE 1: fold_final (s0 += |g|^2 ; g += a ; a = 0)
-// MODE 2: pair       (s0 += |g|^2 ; if flag: s1 += |pv|^2, s2 += |(g+pv)/2|^2 ; pv = g)
-template <typename T, int MODE, bool HAS_PINV>
-__global__ void __launch_bounds__(ADL_THREADS, 2)
-local_kernel(const LocalArgs a) {
-  extern __shared__ double s_stats[];                 // [3][n_groups]
-  constexpr int N = VecTraits<T>::N;
-  constexpr int K = 3;
-  smem_stats_zero(s_stats, K * a.n_groups);
-  GroupAccum<K> accum;
-  accum.init(s_stats, a.n_groups);
-  const int stride = gridDim.x * blockDim.x;
-  const int first = blockIdx.x * blockDim.x + threadIdx.x;
-  const int iters = (a.n_vec + stride - 1) / stride;
-  const bool have_prev = a.flag_ptr ? (*a.flag_ptr != 0) : (a.flag != 0);
-  int cur = -1;
-  for (int it = 0; it < iters; ++it) {
-    const int v = first + it * stride;
-    const bool active = v < a.n_vec;
-    float sq[K] = {0.f, 0.f, 0.f};
-    int grp = -1;
-    if (active) {
-      float g[N], o[N], pinv[N];
-      const Vec16 gv = ld_vec(static_cast<const Vec16*>(a.g) + v);
-      Vec16 ov;
-      if (MODE == 2) ov = ld_vec(static_cast<const Vec16*>(a.pv) + v);
-      else ov = ld_vec(static_cast<const Vec16*>(a.a) + v);
-      if (HAS_PINV) {
-        const Vec16 pvv = ld_vec(static_cast<const Vec16*>(a.pinv) + v);
-        unpack<T>(pvv, pinv);
-#pragma unroll
-        for (int e = 0; e < N; ++e) pinv[e] = 1.0f / pinv[e];
-      }
-      unpack<T>(gv, g);
-      unpack<T>(ov, o);
-#pragma unroll
-      for (int e = 0; e < N; ++e) {
-        const float y = HAS_PINV ? g[e] * pinv[e] : g[e];
-        sq[0] = fmaf(y, y, sq[0]);
-      }
-      if (MODE == 0) {
-#pragma unroll
-        for (int e = 0; e < N; ++e) o[e] += g[e];
-        st_vec(static_cast<Vec16*>(a.a) + v, pack<T>(o));
-        Vec16 z; z.w[0] = z.w[1] = z.w[2] = z.w[3] = 0u;
-        st_vec(static_cast<Vec16*>(a.g) + v, z);
-      } else if (MODE == 1) {
-#pragma unroll
-        for (int e = 0; e < N; ++e) g[e] += o[e];
-        st_vec(static_cast<Vec16*>(a.g) + v, pack<T>(g));
-        Vec16 z; z.w[0] = z.w[1] = z.w[2] = z.w[3] = 0u;
-        st_vec(static_cast<Vec16*>(a.a) + v, z);
+// `v` is the vector index relative to the bucket, `g` its statistics group.
+template <typename T, int PINV>
+struct Precond {
+  static constexpr int N = VecTraits<T>::N;
+  Vec16 raw[2];
+  __device__ __forceinline__ void issue(const void* pinv, int wide, int v) {
+    if (PINV == 1) {
+      raw[0] = ld_vec(static_cast<const Vec16*>(pinv) + v);
+    } else if (PINV == 2) {
+      if (wide && N == 8) {
+        raw[0] = ld_vec(static_cast<const Vec16*>(pinv) + 2 * (size_t)v);
+        raw[1] = ld_vec(static_cast<const Vec16*>(pinv) + 2 * (size_t)v + 1);
       } else {
-        if (have_prev) {
-#pragma unroll
-          for (int e = 0; e < N; ++e) {
-            const float p = HAS_PINV ? o[e] * pinv[e] : o[e];
-            const float m = 0.5f * ((HAS_PINV ? g[e] * pinv[e] : g[e]) + p);
-            sq[1] = fmaf(p, p, sq[1]);
-            sq[2] = fmaf(m, m, sq[2]);
-          }
-        }
-        st_vec(static_cast<Vec16*>(a.pv) + v, gv);
+        raw[0] = ld_vec(static_cast<const Vec16*>(pinv) + v);
       }
-      if (cur < 0) cur = seg_find(a.segs, v);
-      while (__ldg(a.segs.seg_end + cur) <= v) ++cur;
-      grp = __ldg(a.segs.seg_group + cur);
     }
-    accum.add(grp, sq);
   }
-  accum.flush_warp();
-  double* outs[K] = {a.s0, a.s1, a.s2};
-  smem_stats_flush<K>(s_stats, a.n_groups, outs);
+  // out[e] = 1 / divisor
+  __device__ __forceinline__ void finish(const float* coef, int wide, int g, float* out) const {
+    if (PINV == 1) {
+      unpack<T>(raw[0], out);
+#pragma unroll
+      for (int e = 0; e < N; ++e) out[e] = 1.0f / out[e];
+    } else if (PINV == 2) {
+      const float c = (g >= 0) ? __ldg(coef + 2 * g) : 0.f;
+      if (c == 0.f) {
+#pragma unroll
+        for (int e = 0; e < N; ++e) out[e] = 1.0f;
+        return;
+      }
+      const float eps = __ldg(coef + 2 * g + 1);
+      if (wide && N == 8) {
+        unpack<float>(raw[0], out);
+        unpack<float>(raw[1], out + 4);
+      } else {
+        unpack<T>(raw[0], out);
+      }
+#pragma unroll
+      for (int e = 0; e < N; ++e) out[e] = 1.0f / fmaf(sqrtf(out[e]), c, eps);
+    }
+  }
+};
+
+// statistics group of bucket-relative vector v (monotone cursor per lane)
+__device__ __forceinline__ int group_of(const SegTable& segs, int v, int& cur) {
+  if (cur < 0) cur = seg_find(segs, v);
+  while (__ldg(segs.seg_end + cur) <= v) ++cur;
+  return __ldg(segs.seg_group + cur);
 }
 
 // ---------------------------------------------------------------------------
@@ -445,15 +187,26 @@ enum { CTL_ACCUM_SCALE = 0, CTL_SMOOTHING = 1, CTL_RULE = 2, CTL_RULE_ARG = 3, C
 enum { RULE_ADASCALE = 0, RULE_ADAMSCALE = 1, RULE_LINEAR = 2, RULE_SQRT = 3, RULE_LEGW = 4 };
 // Mailbox slot (doubles): header then payload.
 //   0 seq  1 finite  2 gain  3 progress  4 sync_ns  5 err  6 scale  7 n_rows
-//   host mode   : 8.. raw rows [n_rows][G]
-//   device mode : 8.. sqr_avg[G], var_avg[G], lr_factor[G]
-#define ADL_MBOX_HDR 8
+//   8 step_ns  9 accum_ns  10 accum_count  11 amp_scale  12..15 reserved
+//   host mode   : 16.. raw rows [n_rows][G]
+//   device mode : 16.. sqr_avg[G], var_avg[G], lr_factor[G]
+// step_ns  = max over ranks of the interval between this finalize and the
+//            previous step mark (0 right after a clock reset),
+// sync_ns  = max over ranks of (finalize entry - end of the local backward)
+//            + this rank's time inside the finalize,
+// accum_ns / accum_count = accumulation micro-steps since the previous
+//            finalize (adl_step_mark); accum_ns is the max over ranks.
+#define ADL_MBOX_HDR 16
+// per-parity exchange record: [4][G] statistic rows + ADL_XCHG_TAIL timing doubles
+#define ADL_XCHG_TAIL 4
+// step clock (device doubles): 0 accum_ns  1 accum_count
+#define ADL_CLOCK_DOUBLES 4
 
 struct FinalizeArgs {
-  double* xchg[ADL_MAX_RANKS];     // every rank's exchange buffer [2][4*n_groups]
+  double* xchg[ADL_MAX_RANKS];     // every rank's exchange buffer [2][4*n_groups + ADL_XCHG_TAIL]
   uint32_t* pad[ADL_MAX_RANKS];
   int rank, world;
-  uint32_t* step_ctr;              // device; bumped at the end of this kernel
+  uint32_t* step_ctr;              // device; bumped at the end of the finalize
   uint32_t site;
   int n_rows;                      // statistic rows in use (2, or 4 in pair mode)
   int n_groups;
@@ -465,37 +218,58 @@ struct FinalizeArgs {
   int* pair_state;                 // device-mode: stash validity (read, then updated)
   double* mailbox;                 // pinned host ring: [ring][slot_doubles]
   int ring, slot_doubles;
-  double* result;                  // device copy of the summed rows (may be nullptr)
+  double* result;                  // device copy of the summed rows
   unsigned long long* t_start;     // device: %globaltimer at end of local backward
   double* gns_state;               // device estimator state or nullptr (host mode)
   const double* gns_ctrl;          // host-written control block (device memory)
-  float* lr_factor;                // [n_groups] out (device mode)
+  float* lr_factor;                // [n_groups + 1] out (device mode); last = finite flag
   uint32_t* err;
   unsigned long long timeout_ns;
+  unsigned long long* last_stamp;  // device: %globaltimer of the previous step mark (0 = none)
+  double* clock;                   // device step clock (ADL_CLOCK_DOUBLES)
+  const float* amp_scale;          // device: AMP loss scale the gradients carry (or nullptr)
 };
 
+// all threads of the CTA; blockDim.x a power of two <= ADL_THREADS
 __device__ __forceinline__ double block_sum(double x, double* scratch) {
-  // blockDim.x == 256
   __syncthreads();
   scratch[threadIdx.x] = x;
   __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
+  for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
     if ((int)threadIdx.x < o) scratch[threadIdx.x] += scratch[threadIdx.x + o];
     __syncthreads();
   }
   return scratch[0];
 }
 
-__global__ void __launch_bounds__(256, 1) finalize_stats_kernel(const FinalizeArgs a) {
-  __shared__ double scratch[256];
+// Executed by ONE CTA (all of its threads) once every bucket kernel of the
+// step has completed on this rank.
+__device__ __noinline__ void finalize_body(const FinalizeArgs& a) {
+  __shared__ double scratch[ADL_THREADS];
+  __shared__ double sh_t[3];                 // step_ns, sync_entry_ns, accum_ns (max over ranks)
+  __shared__ unsigned long long sh_entry;
   const int G = a.n_groups;
   const int n = a.n_rows * G;
+  const int XS = 4 * G + ADL_XCHG_TAIL;
   const uint32_t step = *reinterpret_cast<volatile uint32_t*>(a.step_ctr);
   const int parity = step & 1;
-  double* mine = a.xchg[a.rank] + (size_t)parity * 4 * G;
+  double* mine = a.xchg[a.rank] + (size_t)parity * XS;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const int r = i / G;
-    mine[i] = a.rows[r][i - r * G];
+    mine[i] = __ldcg(a.rows[r] + (i - r * G));
+  }
+  if (threadIdx.x == 0) {
+    const unsigned long long now = globaltimer_ns();
+    const unsigned long long last = a.last_stamp ? *a.last_stamp : 0ull;
+    const unsigned long long t0 = a.t_start ? *a.t_start : now;
+    if (a.last_stamp) *a.last_stamp = now;
+    double accum_ns = 0.0, accum_cnt = 0.0;
+    if (a.clock) { accum_ns = a.clock[0]; accum_cnt = a.clock[1]; a.clock[0] = 0.0; a.clock[1] = 0.0; }
+    mine[4 * G + 0] = (last != 0ull && now > last) ? (double)(now - last) : 0.0;
+    mine[4 * G + 1] = now > t0 ? (double)(now - t0) : 0.0;
+    mine[4 * G + 2] = accum_ns;
+    mine[4 * G + 3] = accum_cnt;
+    sh_entry = now;
   }
   if (a.world > 1) {
     __syncthreads();
@@ -506,8 +280,8 @@ __global__ void __launch_bounds__(256, 1) finalize_stats_kernel(const FinalizeAr
       st_release_sys(pad_slot(a.pad[peer], 0, ADL_MAX_CTAS - 1, a.rank), epoch);
       wait_flag(pad_slot(a.pad[a.rank], 0, ADL_MAX_CTAS - 1, peer), epoch, a.timeout_ns, a.err);
     }
-    __syncthreads();
   }
+  __syncthreads();
   double* slot = a.mailbox + (size_t)(step % a.ring) * a.slot_doubles;
   double* summed = a.result;                 // [4][G] device scratch (always provided)
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -516,17 +290,28 @@ __global__ void __launch_bounds__(256, 1) finalize_stats_kernel(const FinalizeAr
     if (a.world > 1 && ((a.sum_mask >> r) & 1)) {
       x = 0.0;
       for (int p = 0; p < a.world; ++p)       // fixed order: identical on all ranks
-        x += *reinterpret_cast<volatile double*>(a.xchg[p] + (size_t)parity * 4 * G + i);
+        x += *reinterpret_cast<volatile double*>(a.xchg[p] + (size_t)parity * XS + i);
     } else {
       x = mine[i];
     }
     summed[i] = x;
     a.rows[r][i - r * G] = 0.0;               // partials restart from zero
   }
+  if (threadIdx.x < 3) {                      // timings: max over ranks
+    double x = mine[4 * G + threadIdx.x];
+    for (int p = 0; p < a.world; ++p) {
+      if (p == a.rank) continue;
+      const double y = *reinterpret_cast<volatile double*>(
+          a.xchg[p] + (size_t)parity * XS + 4 * G + threadIdx.x);
+      x = fmax(x, y);
+    }
+    sh_t[threadIdx.x] = x;
+  }
   __syncthreads();
 
   const bool device_mode = a.gns_state != nullptr && a.gns_ctrl[CTL_ENABLED] != 0.0;
   double finite_flag = 1.0, gain = 1.0, progress = 0.0, scale_out = 0.0;
+  const double amp = a.amp_scale ? (double)(*a.amp_scale) : 1.0;
   if (!device_mode) {
     for (int i = threadIdx.x; i < n; i += blockDim.x) slot[ADL_MBOX_HDR + i] = summed[i];
   } else {
@@ -535,6 +320,7 @@ __global__ void __launch_bounds__(256, 1) finalize_stats_kernel(const FinalizeAr
     const double accum_scale = a.gns_ctrl[CTL_ACCUM_SCALE];
     const double smoothing = a.gns_ctrl[CTL_SMOOTHING];
     const int rule = (int)a.gns_ctrl[CTL_RULE];
+    const double inv_amp2 = 1.0 / (amp * amp);  // the statistics are of amp-scaled gradients
     const double* L = summed;
     const double* T = summed + G;
     // non-finite gradients: skip the statistics update (and the progress)
@@ -573,11 +359,12 @@ __global__ void __launch_bounds__(256, 1) finalize_stats_kernel(const FinalizeAr
       for (int g = threadIdx.x; g < G; g += blockDim.x) {
         double local, total, cnt, sc;
         if (count > 1) {
-          local = L[g] / count; total = T[g]; cnt = count; sc = scale;
+          local = L[g] * inv_amp2 / count; total = T[g] * inv_amp2; cnt = count; sc = scale;
         } else {
           const double* Pp = summed + 2 * G;
           const double* Pa = summed + 3 * G;
-          local = 0.5 * (Pp[g] + T[g]); total = Pa[g]; cnt = 2.0; sc = 2.0 * accum_scale;
+          local = 0.5 * (Pp[g] + T[g]) * inv_amp2; total = Pa[g] * inv_amp2;
+          cnt = 2.0; sc = 2.0 * accum_scale;
         }
         const double grad_sqr = (cnt * total - local) / (cnt - 1.0);
         const double grad_var = (local - total) * sc / (cnt - 1.0);
@@ -622,9 +409,12 @@ __global__ void __launch_bounds__(256, 1) finalize_stats_kernel(const FinalizeAr
       slot[ADL_MBOX_HDR + 2 * G + g] = f;
     }
     __syncthreads();
-    if (threadIdx.x == 0 && finite) {         // progress advances with every update
-      progress += gain;
-      tail[GNS_PROGRESS] = progress;
+    if (threadIdx.x == 0) {
+      a.lr_factor[G] = finite ? 1.f : 0.f;    // the fused optimizer skips non-finite steps
+      if (finite) {                           // progress advances with every update
+        progress += gain;
+        tail[GNS_PROGRESS] = progress;
+      }
     }
     scale_out = lr_scale;
   }
@@ -632,21 +422,511 @@ __global__ void __launch_bounds__(256, 1) finalize_stats_kernel(const FinalizeAr
   __syncthreads();
   if (threadIdx.x == 0) {
     const unsigned long long now = globaltimer_ns();
-    const unsigned long long t0 = a.t_start ? *a.t_start : now;
     slot[1] = finite_flag;
     slot[2] = gain;
     slot[3] = progress;
-    slot[4] = (double)(now > t0 ? now - t0 : 0ull);
+    slot[4] = sh_t[1] + (double)(now > sh_entry ? now - sh_entry : 0ull);
     slot[5] = (double)(*a.err);
     slot[6] = scale_out;
     slot[7] = (double)a.n_rows;
+    slot[8] = sh_t[0];
+    slot[9] = sh_t[2];
+    slot[10] = mine[4 * G + 3];
+    slot[11] = amp;
     __threadfence_system();
     *reinterpret_cast<volatile double*>(slot) = (double)(step + 1);   // publish last
     *a.step_ctr = step + 1;                                           // next optimizer step
   }
 }
 
+// Tail of every statistics-producing kernel. All threads of all CTAs call it
+// after their last global access. With `fuse`, the last CTA of the grid to
+// get here runs the step's finalize.
+__device__ __forceinline__ void kernel_tail(bool fuse, uint32_t* ticket, const FinalizeArgs& f) {
+  __threadfence_system();                     // this thread's (remote) stores and atomics have landed
+  if (!fuse) return;
+  __shared__ int s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(ticket, 1u);
+    s_last = (t == gridDim.x - 1);
+    if (s_last) *ticket = 0u;                 // everybody else has drawn: reset for the next step
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    finalize_body(f);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// two-shot P2P flavour
+// ---------------------------------------------------------------------------
+// W > 0: world size known at compile time (2, 4, 8): the per-peer loads are a
+// fully unrolled register array and each thread keeps U = 16/W vectors in
+// flight (16 independent 16-byte requests per thread; with 32 CTAs x 512
+// threads that is ~4 MB outstanding, enough to cover the ~2-3 us NVLink
+// round trip at full link bandwidth). W == 0: generic fallback, runtime world.
+template <int W> struct ReduceUnroll { static constexpr int U = 16 / W; };
+template <> struct ReduceUnroll<0> { static constexpr int U = 1; };
+template <> struct ReduceUnroll<1> { static constexpr int U = 8; };
+
+template <typename T, int W, int PINV>
+__global__ void __launch_bounds__(ADL_THREADS, 1)
+allreduce_gns_kernel(const ReduceArgs a, const FinalizeArgs f) {
+  extern __shared__ double s_stats[];                 // [2][n_groups]
+  constexpr int N = VecTraits<T>::N;
+  constexpr int U = ReduceUnroll<W>::U;
+  constexpr int WMAX = (W > 0) ? W : ADL_MAX_RANKS;
+  smem_stats_zero(s_stats, 2 * a.n_groups);
+  GroupAccum<2> accum;
+  accum.init(s_stats, a.n_groups);
+
+  const int world = (W > 0) ? W : a.world;
+  if (world > 1) cta_barrier_peers(a, 0);             // every rank's grads are ready
+
+  const int slice = a.n_vec / world;
+  const int base = a.rank * slice;
+  const int stride = gridDim.x * blockDim.x;
+  const int first = blockIdx.x * blockDim.x + threadIdx.x;
+  const int iters = (slice + stride * U - 1) / (stride * U);   // same for every lane
+  int cur[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) cur[u] = -1;
+
+  // peer order rotated so that rank r starts with its own copy and the ranks
+  // do not all hammer the same peer at once
+  const Vec16* src[WMAX];
+  Vec16* dst[WMAX];
+#pragma unroll
+  for (int p = 0; p < WMAX; ++p) {
+    const int q = (p < world) ? (a.rank + p) % world : a.rank;
+    src[p] = static_cast<const Vec16*>(a.buf[q]);
+    dst[p] = static_cast<Vec16*>(a.buf[q]);
+  }
+
+  for (int it = 0; it < iters; ++it) {
+    Vec16 in[U][WMAX];
+    Precond<T, PINV> pc[U];
+    int idx[U];
+    bool active[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      idx[u] = first + (it * U + u) * stride;
+      active[u] = idx[u] < slice;
+      if (active[u]) {
+#pragma unroll
+        for (int p = 0; p < WMAX; ++p)
+          if (p < world) in[u][p] = ld_vec(src[p] + base + idx[u]);
+        pc[u].issue(a.pinv, a.pinv_wide, base + idx[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float sq[2] = {0.f, 0.f};
+      int g = -1;
+      if (active[u]) {
+        const int v = base + idx[u];
+        g = group_of(a.segs, v, cur[u]);
+        float sum[N], pinv[N];
+        if (PINV) pc[u].finish(a.pinv_coef, a.pinv_wide, g, pinv);
+#pragma unroll
+        for (int e = 0; e < N; ++e) sum[e] = 0.f;
+#pragma unroll
+        for (int p = 0; p < WMAX; ++p) {
+          if (p < world) {
+            float x[N];
+            unpack<T>(in[u][p], x);
+#pragma unroll
+            for (int e = 0; e < N; ++e) {
+              sum[e] += x[e];
+              const float y = PINV ? x[e] * pinv[e] : x[e];
+              sq[0] = fmaf(y, y, sq[0]);
+            }
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < N; ++e) {
+          sum[e] *= a.scale;
+          const float y = PINV ? sum[e] * pinv[e] : sum[e];
+          sq[1] = fmaf(y, y, sq[1]);
+        }
+        const Vec16 out = pack<T>(sum);
+#pragma unroll
+        for (int p = 0; p < WMAX; ++p)
+          if (p < world) st_vec(dst[p] + v, out);
+        if (!a.want_local) sq[0] = 0.f;
+      }
+      accum.add(g, sq);
+    }
+  }
+  accum.flush_warp();
+  double* outs[2] = {a.want_local ? a.L : nullptr, a.T};
+  smem_stats_flush<2>(s_stats, a.n_groups, outs);
+  kernel_tail(a.fuse_fin != 0, a.ticket, f);
+}
+
+// ---------------------------------------------------------------------------
+// one-shot push flavour (latency-bound buckets)
+// ---------------------------------------------------------------------------
+// Every rank copies its bucket into lane `rank` of every peer's staging area,
+// fences, raises ONE flag per peer; once all flags are in, the whole
+// reduction is local (HBM / L2 reads of the W lanes). Compared with the
+// two-shot flavour that is one NVLink round trip instead of two, at (W-1)
+// times the bytes -- the host picks it for buckets where latency dominates.
+// Statistics: rank r accumulates the vectors of "its" slice only (the same
+// partition as the two-shot flavour), so the cross-rank sum of the partials
+// is unchanged.
+template <typename T, int W, int PINV>
+__global__ void __launch_bounds__(ADL_THREADS, 1)
+allreduce_oneshot_kernel(const ReduceArgs a, const FinalizeArgs f) {
+  extern __shared__ double s_stats[];                 // [2][n_groups]
+  constexpr int N = VecTraits<T>::N;
+  constexpr int WMAX = (W > 0) ? W : ADL_MAX_RANKS;
+  smem_stats_zero(s_stats, 2 * a.n_groups);
+  GroupAccum<2> accum;
+  accum.init(s_stats, a.n_groups);
+  const int world = (W > 0) ? W : a.world;
+  const int stride = gridDim.x * blockDim.x;
+  const int first = blockIdx.x * blockDim.x + threadIdx.x;
+  Vec16* mine = static_cast<Vec16*>(a.buf[a.rank]);
+  const int iters = (a.n_vec + stride - 1) / stride;
+
+  // push: lane `rank` of every peer's staging area (the own lane is read in place)
+  for (int it = 0; it < iters; ++it) {
+    const int v = first + it * stride;
+    if (v < a.n_vec) {
+      const Vec16 x = ld_vec(mine + v);
+#pragma unroll
+      for (int p = 1; p < WMAX; ++p) {
+        if (p < world) {
+          const int q = (a.rank + p) % world;
+          st_vec(static_cast<Vec16*>(a.stage[q]) + (size_t)a.rank * a.n_vec + v, x);
+        }
+      }
+    }
+  }
+  cta_barrier_peers(a, 0);             // every peer's push of this CTA's vectors has landed
+
+  const Vec16* lanes = static_cast<const Vec16*>(a.stage[a.rank]);
+  const int slice = a.n_vec / world;
+  int cur = -1;
+  for (int it = 0; it < iters; ++it) {
+    const int v = first + it * stride;
+    float sq[2] = {0.f, 0.f};
+    int g = -1;
+    if (v < a.n_vec) {
+      Vec16 in[WMAX];                  // indexed by RANK: the sum order is the same on every rank
+      Precond<T, PINV> pc;
+#pragma unroll
+      for (int r = 0; r < WMAX; ++r) {
+        if (r < world)
+          in[r] = (r == a.rank) ? ld_vec(mine + v) : ld_vec(lanes + (size_t)r * a.n_vec + v);
+      }
+      pc.issue(a.pinv, a.pinv_wide, v);
+      g = group_of(a.segs, v, cur);
+      float sum[N], pinv[N];
+      if (PINV) pc.finish(a.pinv_coef, a.pinv_wide, g, pinv);
+#pragma unroll
+      for (int e = 0; e < N; ++e) sum[e] = 0.f;
+#pragma unroll
+      for (int r = 0; r < WMAX; ++r) {
+        if (r < world) {
+          float x[N];
+          unpack<T>(in[r], x);
+#pragma unroll
+          for (int e = 0; e < N; ++e) {
+            sum[e] += x[e];
+            const float y = PINV ? x[e] * pinv[e] : x[e];
+            sq[0] = fmaf(y, y, sq[0]);
+          }
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < N; ++e) {
+        sum[e] *= a.scale;
+        const float y = PINV ? sum[e] * pinv[e] : sum[e];
+        sq[1] = fmaf(y, y, sq[1]);
+      }
+      st_vec(mine + v, pack<T>(sum));
+      const bool owned = (v / slice) == a.rank;
+      if (!owned) { sq[0] = 0.f; sq[1] = 0.f; g = -1; }
+      if (!a.want_local) sq[0] = 0.f;
+    }
+    accum.add(g, sq);
+  }
+  accum.flush_warp();
+  double* outs[2] = {a.want_local ? a.L : nullptr, a.T};
+  smem_stats_flush<2>(s_stats, a.n_groups, outs);
+  kernel_tail(a.fuse_fin != 0, a.ticket, f);
+}
+
+// ---------------------------------------------------------------------------
+// NVLS flavour: the NVSwitch reduces. `multimem.ld_reduce` on the multicast
+// address returns sum_r g_r of a vector in ONE load (the switch pulls every
+// GPU's copy and adds in flight), `multimem.st` writes the mean into every
+// GPU's arena with ONE store. Per GPU that is ~B(1+1/W) each way instead of
+// 2(W-1)/W*B, and W times fewer load instructions.
+// The switch hides the per-replica values, so sum_r |g_r|^2 comes from this
+// rank's own copy: the own slice is read next to the multimem load in the
+// main loop; a foreign slice q is read BEFORE this rank tells rank q that its
+// gradients are ready (per-peer start flags, released slice by slice), because
+// rank q's multimem.st will overwrite it. CTA c reads, in every slice, exactly
+// the vectors CTA c of the owning rank will write.
+// ---------------------------------------------------------------------------
+template <typename T> struct Multimem;
+template <> struct Multimem<float> {
+  static __device__ __forceinline__ Vec16 ld_reduce(const void* p) {
+    Vec16 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.w[0]), "=r"(v.w[1]), "=r"(v.w[2]), "=r"(v.w[3]) : "l"(p) : "memory");
+    return v;
+  }
+};
+template <> struct Multimem<__nv_bfloat16> {
+  static __device__ __forceinline__ Vec16 ld_reduce(const void* p) {
+    Vec16 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.w[0]), "=r"(v.w[1]), "=r"(v.w[2]), "=r"(v.w[3]) : "l"(p) : "memory");
+    return v;
+  }
+};
+template <> struct Multimem<__half> {
+  static __device__ __forceinline__ Vec16 ld_reduce(const void* p) {
+    Vec16 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.f16x2 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.w[0]), "=r"(v.w[1]), "=r"(v.w[2]), "=r"(v.w[3]) : "l"(p) : "memory");
+    return v;
+  }
+};
+__device__ __forceinline__ void multimem_st(void* p, const Vec16& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "r"(v.w[0]), "r"(v.w[1]), "r"(v.w[2]), "r"(v.w[3]) : "memory");
+}
+
+template <typename T, int PINV>
+__global__ void __launch_bounds__(ADL_THREADS, 1)
+allreduce_nvls_kernel(const ReduceArgs a, const FinalizeArgs f) {
+  extern __shared__ double s_stats[];                 // [2][n_groups]
+  constexpr int N = VecTraits<T>::N;
+  constexpr int U = 8;
+  smem_stats_zero(s_stats, 2 * a.n_groups);
+  GroupAccum<2> accum;
+  accum.init(s_stats, a.n_groups);
+  const int stride = gridDim.x * blockDim.x;
+  const int first = blockIdx.x * blockDim.x + threadIdx.x;
+  const Vec16* mine = static_cast<const Vec16*>(a.buf[a.rank]);
+  const uint32_t epoch = launch_epoch(a.step_ctr, a.site);
+
+  const int slice = a.n_vec / a.world;
+  const int iters = (slice + stride * U - 1) / (stride * U);
+  // foreign slices: local statistic first, then this rank's "ready" flag to the owner
+  for (int k = 1; k < a.world; ++k) {
+    const int q = (a.rank + k) % a.world;
+    if (a.want_local) {
+      int cur[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) cur[u] = -1;
+      for (int it = 0; it < iters; ++it) {
+        Vec16 in[U];
+        Precond<T, PINV> pc[U];
+        int idx[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          idx[u] = first + (it * U + u) * stride;
+          if (idx[u] < slice) {
+            in[u] = ld_vec(mine + q * slice + idx[u]);
+            pc[u].issue(a.pinv, a.pinv_wide, q * slice + idx[u]);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          float sq[2] = {0.f, 0.f};
+          int g = -1;
+          if (idx[u] < slice) {
+            const int v = q * slice + idx[u];
+            g = group_of(a.segs, v, cur[u]);
+            float x[N], pinv[N];
+            unpack<T>(in[u], x);
+            if (PINV) pc[u].finish(a.pinv_coef, a.pinv_wide, g, pinv);
+#pragma unroll
+            for (int e = 0; e < N; ++e) {
+              const float y = PINV ? x[e] * pinv[e] : x[e];
+              sq[0] = fmaf(y, y, sq[0]);
+            }
+          }
+          accum.add(g, sq);
+        }
+      }
+    }
+    __syncthreads();                                  // every lane has consumed its loads of slice q
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      st_release_sys(pad_slot(a.pad[q], 0, blockIdx.x, a.rank), epoch);
+    }
+  }
+  if (threadIdx.x > 0 && (int)threadIdx.x < a.world) {
+    const int peer = (a.rank + threadIdx.x) % a.world;
+    wait_flag(pad_slot(a.pad[a.rank], 0, blockIdx.x, peer), epoch, a.timeout_ns, a.err);
+  }
+  __syncthreads();                                    // every rank's grads are ready
+
+  const int base = a.rank * slice;
+  Vec16* mc = static_cast<Vec16*>(a.mc_buf);
+  int cur[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) cur[u] = -1;
+  for (int it = 0; it < iters; ++it) {
+    Vec16 in[U], own[U];
+    Precond<T, PINV> pc[U];
+    int idx[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      idx[u] = first + (it * U + u) * stride;
+      if (idx[u] < slice) {
+        in[u] = Multimem<T>::ld_reduce(mc + base + idx[u]);
+        if (a.want_local) own[u] = ld_vec(mine + base + idx[u]);
+        pc[u].issue(a.pinv, a.pinv_wide, base + idx[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float sq[2] = {0.f, 0.f};
+      int g = -1;
+      if (idx[u] < slice) {
+        const int v = base + idx[u];
+        g = group_of(a.segs, v, cur[u]);
+        float x[N], pinv[N];
+        if (PINV) pc[u].finish(a.pinv_coef, a.pinv_wide, g, pinv);
+        if (a.want_local) {
+          unpack<T>(own[u], x);
+#pragma unroll
+          for (int e = 0; e < N; ++e) {
+            const float y = PINV ? x[e] * pinv[e] : x[e];
+            sq[0] = fmaf(y, y, sq[0]);
+          }
+        }
+        unpack<T>(in[u], x);
+#pragma unroll
+        for (int e = 0; e < N; ++e) {
+          x[e] *= a.scale;
+          const float y = PINV ? x[e] * pinv[e] : x[e];
+          sq[1] = fmaf(y, y, sq[1]);
+        }
+        multimem_st(mc + v, pack<T>(x));
+      }
+      accum.add(g, sq);
+    }
+  }
+  accum.flush_warp();
+  double* outs[2] = {a.want_local ? a.L : nullptr, a.T};
+  smem_stats_flush<2>(s_stats, a.n_groups, outs);
+  kernel_tail(a.fuse_fin != 0, a.ticket, f);
+}
+
+// ---------------------------------------------------------------------------
+// local folds (gradient accumulation) and the single-replica pair norm
+// ---------------------------------------------------------------------------
+struct LocalArgs {
+  void* g; void* a; void* pv; const void* pinv;
+  int n_vec;
+  SegTable segs;
+  int n_groups;
+  double* s0; double* s1; double* s2;   // statistic outputs (see kernels)
+  int flag;                             // MODE 2: previous-step stash is valid
+  const int* flag_ptr;                  // if non-null, overrides `flag` (device-resident state)
+  int pinv_mode;
+  int pinv_wide;
+  const float* pinv_coef;
+  int fuse_fin;
+  uint32_t* ticket;
+};
+
+// MODE 0: fold_acc   (a += g ; s0 += |g|^2 ; g = 0)
+// MODE 1: fold_final (s0 += |g|^2 ; g += a ; a = 0)
+// MODE 2: pair       (s0 += |g|^2 ; if flag: s1 += |pv|^2, s2 += |(g+pv)/2|^2 ; pv = g)
+template <typename T, int MODE, int PINV>
+__global__ void __launch_bounds__(ADL_THREADS, 2)
+local_kernel(const LocalArgs a, const FinalizeArgs f) {
+  extern __shared__ double s_stats[];                 // [3][n_groups]
+  constexpr int N = VecTraits<T>::N;
+  constexpr int K = 3;
+  smem_stats_zero(s_stats, K * a.n_groups);
+  GroupAccum<K> accum;
+  accum.init(s_stats, a.n_groups);
+  const int stride = gridDim.x * blockDim.x;
+  const int first = blockIdx.x * blockDim.x + threadIdx.x;
+  const int iters = (a.n_vec + stride - 1) / stride;
+  const bool have_prev = a.flag_ptr ? (*a.flag_ptr != 0) : (a.flag != 0);
+  int cur = -1;
+  for (int it = 0; it < iters; ++it) {
+    const int v = first + it * stride;
+    const bool active = v < a.n_vec;
+    float sq[K] = {0.f, 0.f, 0.f};
+    int grp = -1;
+    if (active) {
+      float g[N], o[N], pinv[N];
+      const Vec16 gv = ld_vec(static_cast<const Vec16*>(a.g) + v);
+      Vec16 ov;
+      if (MODE == 2) ov = ld_vec(static_cast<const Vec16*>(a.pv) + v);
+      else ov = ld_vec(static_cast<const Vec16*>(a.a) + v);
+      Precond<T, PINV> pc;
+      pc.issue(a.pinv, a.pinv_wide, v);
+      grp = group_of(a.segs, v, cur);
+      if (PINV) pc.finish(a.pinv_coef, a.pinv_wide, grp, pinv);
+      unpack<T>(gv, g);
+      unpack<T>(ov, o);
+#pragma unroll
+      for (int e = 0; e < N; ++e) {
+        const float y = PINV ? g[e] * pinv[e] : g[e];
+        sq[0] = fmaf(y, y, sq[0]);
+      }
+      if (MODE == 0) {
+#pragma unroll
+        for (int e = 0; e < N; ++e) o[e] += g[e];
+        st_vec(static_cast<Vec16*>(a.a) + v, pack<T>(o));
+        Vec16 z; z.w[0] = z.w[1] = z.w[2] = z.w[3] = 0u;
+        st_vec(static_cast<Vec16*>(a.g) + v, z);
+      } else if (MODE == 1) {
+#pragma unroll
+        for (int e = 0; e < N; ++e) g[e] += o[e];
+        st_vec(static_cast<Vec16*>(a.g) + v, pack<T>(g));
+        Vec16 z; z.w[0] = z.w[1] = z.w[2] = z.w[3] = 0u;
+        st_vec(static_cast<Vec16*>(a.a) + v, z);
+      } else {
+        if (have_prev) {
+#pragma unroll
+          for (int e = 0; e < N; ++e) {
+            const float p = PINV ? o[e] * pinv[e] : o[e];
+            const float m = 0.5f * ((PINV ? g[e] * pinv[e] : g[e]) + p);
+            sq[1] = fmaf(p, p, sq[1]);
+            sq[2] = fmaf(m, m, sq[2]);
+          }
+        }
+        st_vec(static_cast<Vec16*>(a.pv) + v, gv);
+      }
+    }
+    accum.add(grp, sq);
+  }
+  accum.flush_warp();
+  double* outs[K] = {a.s0, a.s1, a.s2};
+  smem_stats_flush<K>(s_stats, a.n_groups, outs);
+  if (MODE == 2) kernel_tail(a.fuse_fin != 0, a.ticket, f);
+}
+
+__global__ void __launch_bounds__(256, 1) finalize_stats_kernel(const FinalizeArgs a) {
+  finalize_body(a);
+}
+
 __global__ void stamp_kernel(unsigned long long* dst) { *dst = globaltimer_ns(); }
+
+// accumulation micro-step: add the interval since the previous mark to the step clock
+__global__ void step_mark_kernel(unsigned long long* last_stamp, double* clock) {
+  const unsigned long long now = globaltimer_ns();
+  const unsigned long long last = *last_stamp;
+  if (last != 0ull && now > last) { clock[0] += (double)(now - last); clock[1] += 1.0; }
+  *last_stamp = now;
+}
 
 // ---------------------------------------------------------------------------
 // broadcast: every non-source rank pulls the source's staging buffer
@@ -694,24 +974,50 @@ static int g_device = -1;
 
 // Raise the dynamic shared memory limit of every statistics kernel ONCE (not
 // per launch: launches may happen under CUDA-graph capture).
-template <typename T>
-static int set_attrs_for() {
-  const int lim = ADL_MAX_STAT_SMEM;
-#define ADL_AR_ATTR(W)                                                                                          \
-  ADL_CHECK(cudaFuncSetAttribute(allreduce_gns_kernel<T, W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim)); \
-  ADL_CHECK(cudaFuncSetAttribute(allreduce_gns_kernel<T, W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
-  ADL_AR_ATTR(0) ADL_AR_ATTR(1) ADL_AR_ATTR(2) ADL_AR_ATTR(4) ADL_AR_ATTR(8)
-#undef ADL_AR_ATTR
-  ADL_CHECK(cudaFuncSetAttribute(allreduce_nvls_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
-  ADL_CHECK(cudaFuncSetAttribute(allreduce_nvls_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
-  ADL_CHECK(cudaFuncSetAttribute(local_kernel<T, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
-  ADL_CHECK(cudaFuncSetAttribute(local_kernel<T, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
-  ADL_CHECK(cudaFuncSetAttribute(local_kernel<T, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
-  ADL_CHECK(cudaFuncSetAttribute(local_kernel<T, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
-  ADL_CHECK(cudaFuncSetAttribute(local_kernel<T, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
-  ADL_CHECK(cudaFuncSetAttribute(local_kernel<T, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+#define ADL_SMEM_ATTR(...) \
+  ADL_CHECK(cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributeMaxDynamicSharedMemorySize, ADL_MAX_STAT_SMEM))
+template <typename T, int PINV>
+static int set_attrs_for_p() {
+  ADL_SMEM_ATTR(allreduce_gns_kernel<T, 0, PINV>);
+  ADL_SMEM_ATTR(allreduce_gns_kernel<T, 1, PINV>);
+  ADL_SMEM_ATTR(allreduce_gns_kernel<T, 2, PINV>);
+  ADL_SMEM_ATTR(allreduce_gns_kernel<T, 4, PINV>);
+  ADL_SMEM_ATTR(allreduce_gns_kernel<T, 8, PINV>);
+  ADL_SMEM_ATTR(allreduce_oneshot_kernel<T, 0, PINV>);
+  ADL_SMEM_ATTR(allreduce_oneshot_kernel<T, 2, PINV>);
+  ADL_SMEM_ATTR(allreduce_oneshot_kernel<T, 4, PINV>);
+  ADL_SMEM_ATTR(allreduce_oneshot_kernel<T, 8, PINV>);
+  ADL_SMEM_ATTR(allreduce_nvls_kernel<T, PINV>);
+  ADL_SMEM_ATTR(local_kernel<T, 0, PINV>);
+  ADL_SMEM_ATTR(local_kernel<T, 1, PINV>);
+  ADL_SMEM_ATTR(local_kernel<T, 2, PINV>);
   return 0;
 }
+template <typename T>
+static int set_attrs_for() {
+  if (int rc = set_attrs_for_p<T, 0>()) return rc;
+  if (int rc = set_attrs_for_p<T, 1>()) return rc;
+  if (int rc = set_attrs_for_p<T, 2>()) return rc;
+  return 0;
+}
+
+// dispatch helper: dtype code x preconditioner mode -> template instance
+#define ADL_DISPATCH_TP(dtype, pinv, CALL)                                         \
+  do {                                                                             \
+    if ((pinv) < 0 || (pinv) > 2) return -5;                                       \
+    switch ((dtype) * 3 + (pinv)) {                                                \
+      case 0: CALL(float, 0); break;                                               \
+      case 1: CALL(float, 1); break;                                               \
+      case 2: CALL(float, 2); break;                                               \
+      case 3: CALL(__nv_bfloat16, 0); break;                                       \
+      case 4: CALL(__nv_bfloat16, 1); break;                                       \
+      case 5: CALL(__nv_bfloat16, 2); break;                                       \
+      case 6: CALL(__half, 0); break;                                              \
+      case 7: CALL(__half, 1); break;                                              \
+      case 8: CALL(__half, 2); break;                                              \
+      default: return -2;                                                          \
+    }                                                                              \
+  } while (0)
 
 extern "C" {
 
@@ -740,62 +1046,78 @@ int adl_sm_count(int dev) {
 }
 
 // dtype: 0 = fp32, 1 = bf16, 2 = fp16
-int adl_allreduce_gns(const ReduceArgs* args, int dtype, int grid, void* stream) {
+// flavour: 0 = two-shot P2P, 1 = one-shot push (args->stage), 2 = NVLS (args->mc_buf)
+// fin: finalize arguments when args->fuse_fin (else ignored; may be nullptr)
+int adl_allreduce_gns(const ReduceArgs* args, const FinalizeArgs* fin, int dtype, int flavour,
+                      int grid, void* stream) {
   if (g_device >= 0) ADL_CHECK(cudaSetDevice(g_device));
   const size_t smem = sizeof(double) * 2 * args->n_groups;
   if (smem > ADL_MAX_STAT_SMEM) return -4;
-  const bool pinv = args->pinv != nullptr;
+  if (dtype < 0 || dtype > 2) return -2;
+  if (args->fuse_fin && fin == nullptr) return -6;
+  FinalizeArgs none;
+  memset(&none, 0, sizeof(none));
+  const FinalizeArgs& f = args->fuse_fin ? *fin : none;
+  const int pinv = args->pinv != nullptr ? args->pinv_mode : 0;
   cudaStream_t s = (cudaStream_t)stream;
-#define LAUNCH_AR_W(T, P, W) allreduce_gns_kernel<T, W, P><<<grid, ADL_THREADS, smem, s>>>(*args)
-#define LAUNCH_AR(T, P)                                        \
-  do {                                                         \
-    switch (args->world) {                                     \
-      case 1: LAUNCH_AR_W(T, P, 1); break;                     \
-      case 2: LAUNCH_AR_W(T, P, 2); break;                     \
-      case 4: LAUNCH_AR_W(T, P, 4); break;                     \
-      case 8: LAUNCH_AR_W(T, P, 8); break;                     \
-      default: LAUNCH_AR_W(T, P, 0); break;                    \
-    }                                                          \
-  } while (0)
-#define LAUNCH_NVLS(T, P) allreduce_nvls_kernel<T, P><<<grid, ADL_THREADS, smem, s>>>(*args)
-  if (args->mc_buf != nullptr && args->world > 1) {
-    if (dtype == 0) { if (pinv) LAUNCH_NVLS(float, true); else LAUNCH_NVLS(float, false); }
-    else if (dtype == 1) { if (pinv) LAUNCH_NVLS(__nv_bfloat16, true); else LAUNCH_NVLS(__nv_bfloat16, false); }
-    else if (dtype == 2) { if (pinv) LAUNCH_NVLS(__half, true); else LAUNCH_NVLS(__half, false); }
-    else return -2;
+  if (args->world > 1 && flavour == 2) {
+    if (args->mc_buf == nullptr) return -7;
+#define CALL_NVLS(T, P) allreduce_nvls_kernel<T, P><<<grid, ADL_THREADS, smem, s>>>(*args, f)
+    ADL_DISPATCH_TP(dtype, pinv, CALL_NVLS);
+#undef CALL_NVLS
     return (int)cudaGetLastError();
   }
-#undef LAUNCH_NVLS
-  if (dtype == 0) { if (pinv) LAUNCH_AR(float, true); else LAUNCH_AR(float, false); }
-  else if (dtype == 1) { if (pinv) LAUNCH_AR(__nv_bfloat16, true); else LAUNCH_AR(__nv_bfloat16, false); }
-  else if (dtype == 2) { if (pinv) LAUNCH_AR(__half, true); else LAUNCH_AR(__half, false); }
-  else return -2;
-#undef LAUNCH_AR
-#undef LAUNCH_AR_W
+  if (args->world > 1 && flavour == 1) {
+#define CALL_OS(T, P)                                                                                  \
+  do {                                                                                                 \
+    switch (args->world) {                                                                             \
+      case 2: allreduce_oneshot_kernel<T, 2, P><<<grid, ADL_THREADS, smem, s>>>(*args, f); break;      \
+      case 4: allreduce_oneshot_kernel<T, 4, P><<<grid, ADL_THREADS, smem, s>>>(*args, f); break;      \
+      case 8: allreduce_oneshot_kernel<T, 8, P><<<grid, ADL_THREADS, smem, s>>>(*args, f); break;      \
+      default: allreduce_oneshot_kernel<T, 0, P><<<grid, ADL_THREADS, smem, s>>>(*args, f); break;     \
+    }                                                                                                  \
+  } while (0)
+    ADL_DISPATCH_TP(dtype, pinv, CALL_OS);
+#undef CALL_OS
+    return (int)cudaGetLastError();
+  }
+#define CALL_AR(T, P)                                                                              \
+  do {                                                                                             \
+    switch (args->world) {                                                                         \
+      case 1: allreduce_gns_kernel<T, 1, P><<<grid, ADL_THREADS, smem, s>>>(*args, f); break;      \
+      case 2: allreduce_gns_kernel<T, 2, P><<<grid, ADL_THREADS, smem, s>>>(*args, f); break;      \
+      case 4: allreduce_gns_kernel<T, 4, P><<<grid, ADL_THREADS, smem, s>>>(*args, f); break;      \
+      case 8: allreduce_gns_kernel<T, 8, P><<<grid, ADL_THREADS, smem, s>>>(*args, f); break;      \
+      default: allreduce_gns_kernel<T, 0, P><<<grid, ADL_THREADS, smem, s>>>(*args, f); break;     \
+    }                                                                                              \
+  } while (0)
+  ADL_DISPATCH_TP(dtype, pinv, CALL_AR);
+#undef CALL_AR
   return (int)cudaGetLastError();
 }
 
 // mode: 0 fold_acc, 1 fold_final, 2 pair
-int adl_local(const LocalArgs* args, int mode, int dtype, int grid, void* stream) {
+int adl_local(const LocalArgs* args, const FinalizeArgs* fin, int mode, int dtype, int grid,
+              void* stream) {
   if (g_device >= 0) ADL_CHECK(cudaSetDevice(g_device));
   const size_t smem = sizeof(double) * 3 * args->n_groups;
   if (smem > ADL_MAX_STAT_SMEM) return -4;
-  const bool pinv = args->pinv != nullptr;
+  if (dtype < 0 || dtype > 2) return -2;
+  if (args->fuse_fin && (fin == nullptr || mode != 2)) return -6;
+  FinalizeArgs none;
+  memset(&none, 0, sizeof(none));
+  const FinalizeArgs& f = args->fuse_fin ? *fin : none;
+  const int pinv = args->pinv != nullptr ? args->pinv_mode : 0;
   cudaStream_t s = (cudaStream_t)stream;
-#define LAUNCH_L(T, M, P) local_kernel<T, M, P><<<grid, ADL_THREADS, smem, s>>>(*args)
-#define LAUNCH_LM(T)                                                                         \
+#define CALL_L(T, P)                                                                         \
   do {                                                                                       \
-    if (mode == 0) { if (pinv) LAUNCH_L(T, 0, true); else LAUNCH_L(T, 0, false); }           \
-    else if (mode == 1) { if (pinv) LAUNCH_L(T, 1, true); else LAUNCH_L(T, 1, false); }      \
-    else if (mode == 2) { if (pinv) LAUNCH_L(T, 2, true); else LAUNCH_L(T, 2, false); }      \
+    if (mode == 0) local_kernel<T, 0, P><<<grid, ADL_THREADS, smem, s>>>(*args, f);          \
+    else if (mode == 1) local_kernel<T, 1, P><<<grid, ADL_THREADS, smem, s>>>(*args, f);     \
+    else if (mode == 2) local_kernel<T, 2, P><<<grid, ADL_THREADS, smem, s>>>(*args, f);     \
     else return -3;                                                                          \
   } while (0)
-  if (dtype == 0) LAUNCH_LM(float);
-  else if (dtype == 1) LAUNCH_LM(__nv_bfloat16);
-  else if (dtype == 2) LAUNCH_LM(__half);
-  else return -2;
-#undef LAUNCH_LM
-#undef LAUNCH_L
+  ADL_DISPATCH_TP(dtype, pinv, CALL_L);
+#undef CALL_L
   return (int)cudaGetLastError();
 }
 
@@ -811,6 +1133,12 @@ int adl_stamp(unsigned long long* dst, void* stream) {
   return (int)cudaGetLastError();
 }
 
+int adl_step_mark(unsigned long long* last_stamp, double* clock, void* stream) {
+  if (g_device >= 0) ADL_CHECK(cudaSetDevice(g_device));
+  step_mark_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(last_stamp, clock);
+  return (int)cudaGetLastError();
+}
+
 int adl_bcast_pull(const BcastArgs* args, int grid, void* stream) {
   if (g_device >= 0) ADL_CHECK(cudaSetDevice(g_device));
   bcast_pull_kernel<<<grid, ADL_THREADS, 0, (cudaStream_t)stream>>>(*args);
@@ -821,5 +1149,7 @@ int adl_sizeof_reduce_args() { return (int)sizeof(ReduceArgs); }
 int adl_sizeof_local_args() { return (int)sizeof(LocalArgs); }
 int adl_sizeof_finalize_args() { return (int)sizeof(FinalizeArgs); }
 int adl_sizeof_bcast_args() { return (int)sizeof(BcastArgs); }
+int adl_mbox_hdr() { return ADL_MBOX_HDR; }
+int adl_xchg_tail() { return ADL_XCHG_TAIL; }
 
 }  // extern "C"

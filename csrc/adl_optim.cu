@@ -39,6 +39,9 @@ struct OptimArgs {
   const int* step_offset;                // device int: adam_step = *step_ctr + *step_offset
   int n_groups;
   float* master;                         // fp32 master weights, arena layout (16-bit arenas only)
+  const float* grad_scale;               // device: AMP loss scale carried by the gradients (or nullptr)
+  float* pinv_coef;                      // Adam: [n_groups][2] preconditioner coefficients for the NEXT
+                                         // backward's statistics (adl_kernels.cu PINV mode 2), or nullptr
 };
 
 template <typename T> __device__ __forceinline__ float to_f(T x);
@@ -72,6 +75,17 @@ __global__ void __launch_bounds__(ADL_THREADS, 2) fused_optim_kernel(const Optim
   float bc1 = 1.f, bc2_rsqrt = 1.f;
   float step = 0.f;
   if (ADAM) step = (float)((long long)(*a.step_ctr) + (long long)(*a.step_offset));
+  const float inv_gs = a.grad_scale ? 1.f / *a.grad_scale : 1.f;
+  if (ADAM && a.pinv_coef && blockIdx.x == 0) {
+    // Adam-preconditioned gradient statistics (reference gradient_noise_scale.py:289-311):
+    // after `step` updates the divisor is sqrt(v / (1 - beta2^step)) + eps, and none for
+    // the first five steps
+    for (int g = threadIdx.x; g < a.n_groups; g += blockDim.x) {
+      const float* h = a.hyper + g * ADL_HYPER_STRIDE;
+      a.pinv_coef[2 * g] = step >= 5.f ? rsqrtf(1.f - powf(h[4], step)) : 0.f;
+      a.pinv_coef[2 * g + 1] = h[5];
+    }
+  }
   int cur = -1;
   for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < a.n_vec; v += stride) {
     if (cur < 0) cur = seg_find(a.segs, v);
@@ -91,6 +105,10 @@ __global__ void __launch_bounds__(ADL_THREADS, 2) fused_optim_kernel(const Optim
 
     float gr[N], p[N], s0[N], s1[N];
     unpack<T>(ld_vec(static_cast<const Vec16*>(a.grad) + v), gr);
+    if (a.grad_scale) {
+#pragma unroll
+      for (int e = 0; e < N; ++e) gr[e] *= inv_gs;
+    }
     if (a.state0) {
       if (WIDE) ld_f32<N>(static_cast<const float*>(a.state0), e0, s0);
       else unpack<T>(ld_vec(static_cast<const Vec16*>(a.state0) + v), s0);
@@ -183,6 +201,17 @@ int adl_fused_optim(const OptimArgs* args, int adam, int dtype, int grid, void* 
   else if (dtype == 2) { if (wide) LAUNCH_O(__half, true); else LAUNCH_O(__half, false); }
   else return -2;
 #undef LAUNCH_O
+  return (int)cudaGetLastError();
+}
+
+// Adam's step counter advances only on finite (applied) updates
+__global__ void optim_advance_kernel(int* steps, const float* finite) {
+  if (finite == nullptr || *finite != 0.f) *steps += 1;
+}
+
+int adl_optim_advance(int* steps, const float* finite, void* stream) {
+  if (int rc = adl_bind_thread()) return rc;
+  optim_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(steps, finite);
   return (int)cudaGetLastError();
 }
 

@@ -239,7 +239,7 @@ def _single_process_runtime():
 
 
 def _train(adl, make_opt, rule_fn, fused, graphed, steps=14, accum=False,
-           model_fn=None, lag=None, autocast=None):
+           model_fn=None, lag=None, autocast=None, scaler=None):
     """Train a small model through the public API; returns (params, gns
     dict, net)."""
     dev = torch.device("cuda", 0)
@@ -254,6 +254,7 @@ def _train(adl, make_opt, rule_fn, fused, graphed, steps=14, accum=False,
     opt = make_opt(model)
     _COUNTER[0] += 1
     net = adl.AdaptiveDataParallel(model, opt, scaling_rule=rule_fn(),
+                                   mp_scaler=scaler,
                                    name="t{}".format(_COUNTER[0]),
                                    fused_step=fused)
     assert (net.engine is not None) == bool(fused)
@@ -276,7 +277,8 @@ def _train(adl, make_opt, rule_fn, fused, graphed, steps=14, accum=False,
         helper._sync_local_bsz = fixed
     trainer = adl.GraphedTrainStep(
         net, opt, lambda n, x, y: torch.nn.functional.cross_entropy(n(x), y),
-        warmup=2, enabled=graphed, autocast_dtype=autocast)
+        warmup=2, enabled=graphed, autocast_dtype=autocast,
+        grad_scaler=scaler)
     losses = []
     for epoch in adl.remaining_epochs_until(adl.finished_epochs() + 1):
         for i, (x, y) in enumerate(loader):
@@ -316,6 +318,100 @@ def test_device_engine_matches_host_path(accum):
     for key in ("sqr_avg", "var_avg", "progress"):
         np.testing.assert_allclose(ga[key], gb[key], rtol=2e-3, atol=1e-9)
     assert ga["progress"] > 0
+
+
+@pytest.mark.parametrize("graphed", [False, True])
+def test_device_engine_adam_preconditioned_statistics(graphed):
+    """``scaling_rule=AdamScale()`` (Adam-preconditioned gradient statistics,
+    reference gradient_noise_scale.py:289-330) stays on the device engine:
+    the bucket kernels read the fused optimizer's second moments in place.
+    Same trajectory as the host estimator + torch Adam."""
+    adl = _single_process_runtime()
+    from adaptdl_b200.torch.scaling_rules import AdamScale
+
+    def make(model):
+        return torch.optim.Adam([{"params": [p]} for p in model.parameters()],
+                                lr=2e-3, betas=(0.9, 0.98))
+    pa, ga, net_a, tr, la = _train(adl, make, AdamScale, True, graphed,
+                                   steps=16)
+    pb, gb, net_b, _, lb = _train(adl, make, AdamScale, False, False,
+                                  steps=16)
+    assert net_a.engine is not None and net_a.engine.precondition_stats
+    assert net_b.engine is None
+    if graphed:
+        assert tr.replays > 0
+    torch.testing.assert_close(la, lb, rtol=2e-3, atol=2e-4)
+    torch.testing.assert_close(pa, pb, rtol=2e-3, atol=2e-4)
+    for key in ("sqr_avg", "var_avg", "progress"):
+        np.testing.assert_allclose(ga[key], gb[key], rtol=1e-2, atol=1e-7)
+    assert ga["progress"] > 0
+
+
+@pytest.mark.parametrize("graphed", [False, True])
+def test_device_engine_with_grad_scaler(graphed):
+    """fp16 autocast + ``GradScaler``: the engine stays on (no blocking
+    ``.item()`` in ``scaler.step``), non-finite steps are skipped on the
+    device, the statistics are divided by the loss scale. Same trajectory as
+    the host path (which synchronises every step)."""
+    adl = _single_process_runtime()
+    from adaptdl_b200.torch.scaling_rules import AdaScale
+
+    def run(fused, graph):
+        # a large initial scale overflows fp16 in the first steps: both
+        # paths must skip exactly those updates
+        scaler = torch.amp.GradScaler("cuda", init_scale=2.0 ** 22,
+                                      growth_interval=4)
+        out = _train(adl, _sgd, AdaScale, fused, graph, steps=16,
+                     autocast=torch.float16, scaler=scaler)
+        return out + (scaler,)
+    pa, ga, net_a, tr, la, sa = run(True, graphed)
+    pb, gb, net_b, _, lb, sb = run(False, False)
+    assert net_a.engine is not None and net_b.engine is None
+    if graphed:
+        assert tr.replays > 0
+    assert sa.get_scale() == sb.get_scale() < 2.0 ** 22
+    torch.testing.assert_close(la, lb, rtol=5e-3, atol=5e-3)
+    torch.testing.assert_close(pa, pb, rtol=5e-3, atol=5e-4)
+    for key in ("sqr_avg", "var_avg", "progress"):
+        np.testing.assert_allclose(ga[key], gb[key], rtol=5e-2, atol=1e-7)
+    assert ga["progress"] > 0
+
+
+def test_step_profile_comes_from_device_stamps():
+    """The goodput profile's step / sync durations are the finalize
+    kernel's %globaltimer stamps (not host clocks), booked asynchronously;
+    reference: torch/_metrics.py:43-59,104-127."""
+    adl = _single_process_runtime()
+    from adaptdl_b200.torch import _metrics
+    from adaptdl_b200.torch.scaling_rules import AdaScale
+    _metrics._reset_for_tests()
+    _, _, net, _, _ = _train(adl, _sgd, AdaScale, True, True, steps=20)
+    timer = _metrics.device_timer()
+    assert timer is not None and timer.reducer is net.reducer
+    _metrics._book_device_records(wait=True)
+    assert timer.booked >= 10 and timer.dropped == 0
+    rows = [r for r in _metrics._metrics_state().profile.values()
+            if r.get("optim_count")]
+    assert rows
+    for row in rows:
+        mean_step = row["optim_step_time"] / row["optim_count"]
+        mean_sync = row["optim_sync_time"] / row["optim_count"]
+        # a device-timed step of this toy model: tens of microseconds to a
+        # few milliseconds, never the host's python loop time
+        assert 5e-6 < mean_step < 2e-2, mean_step
+        assert 0 < mean_sync <= mean_step
+    # accumulation micro-steps arrive with the optimizer step closing them
+    _metrics._reset_for_tests()
+    _, _, net2, _, _ = _train(adl, _sgd, AdaScale, True, False, steps=8,
+                              accum=True)
+    _metrics._book_device_records(wait=True)
+    rows = [r for r in _metrics._metrics_state().profile.values()
+            if r.get("optim_count")]
+    assert rows and any(r.get("accum_count", 0) > 0 for r in rows)
+    for row in rows:
+        if row.get("accum_count"):
+            assert row["accum_step_time"] > 0
+    _metrics._reset_for_tests()
 
 
 @pytest.mark.parametrize("opt_name", ["adam", "adamw", "sgd_plain"])
@@ -525,15 +621,6 @@ def test_tcgen05_linear_gelu_autograd_matches_torch():
         assert (a - b).abs().max().item() <= 3e-2 * scale + 1e-3
 
 
-# experimental code paths: written after round 1's GPU budget was spent, so
-# their tests have never run on hardware and only run on request:
-#   ADAPTDL_B200_TEST_EXPERIMENTAL=1 python -m pytest tests -m gpu -k "layer_norm or bitmask or phase_dgrad"
-_EXPERIMENTAL = pytest.mark.skipif(
-    os.environ.get("ADAPTDL_B200_TEST_EXPERIMENTAL") != "1",
-    reason="experimental op, not validated on hardware yet "
-           "(set ADAPTDL_B200_TEST_EXPERIMENTAL=1)")
-
-
 # ---------------------------------------------------------------------------
 # fused BatchNorm (+ residual) (+ ReLU), channels-last (csrc/adl_bn.cu)
 # ---------------------------------------------------------------------------
@@ -595,28 +682,6 @@ def test_fused_bn_act_matches_torch(dtype, shape, residual, relu):
         assert close(r1.grad, r2.grad, gtol)
 
 
-@_EXPERIMENTAL
-@pytest.mark.gpu
-def test_fused_bn_act_bitmask_backward_matches_y_backward(monkeypatch):
-    """ADAPTDL_B200_BN_BITMASK=1 (one saved ReLU bit per element instead of
-    re-reading y) gives bit-identical gradients."""
-    from adaptdl_b200.ops import BatchNormAct2d
-    dev = torch.device("cuda:0")
-    grads = []
-    for flag in ("0", "1"):
-        monkeypatch.setenv("ADAPTDL_B200_BN_BITMASK", flag)
-        torch.manual_seed(11)
-        bn = BatchNormAct2d(128).to(dev)
-        x = torch.randn(16, 128, 8, 8, device=dev).bfloat16().contiguous(
-            memory_format=torch.channels_last).requires_grad_(True)
-        r = torch.randn(16, 128, 8, 8, device=dev).bfloat16().contiguous(
-            memory_format=torch.channels_last).requires_grad_(True)
-        y = bn(x, r, True)
-        y.backward(torch.ones_like(y))
-        grads.append((y.detach().clone(), x.grad.clone(), r.grad.clone(),
-                      bn.weight.grad.clone(), bn.bias.grad.clone()))
-    for a, b in zip(*grads):
-        assert torch.equal(a, b)
 
 
 @pytest.mark.gpu
@@ -653,12 +718,8 @@ def test_fused_bn_resnet_matches_unfused_model():
 
 
 # ---------------------------------------------------------------------------
-# fused dropout + residual + LayerNorm (csrc/adl_ln.cu) -- opt-in op, written
-# after round 1's GPU budget was spent: the tests exist but have never run on
-# hardware, so they only run on request (first thing to do next round):
-#   ADAPTDL_B200_TEST_EXPERIMENTAL=1 python -m pytest tests -m gpu -k layer_norm
+# fused dropout + residual + LayerNorm (csrc/adl_ln.cu)
 # ---------------------------------------------------------------------------
-@_EXPERIMENTAL
 @pytest.mark.gpu
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("shape,p", [((4, 128, 768), 0.1), ((37, 200), 0.2),
@@ -685,7 +746,8 @@ def test_fused_dropout_add_layer_norm(dtype, shape, p, monkeypatch):
     mask = (torch.rand(shape, device=dev) > p).to(torch.uint8)
     y1 = dropout_add_layer_norm(x1, h1, w, b, p, True, 1e-5, mask=mask)
     z2 = x2 + (h2 * mask.float() / (1 - p) if p > 0 else h2)
-    z2 = z2.to(dtype).float() + (z2 - z2.detach())   # the kernel rounds z
+    # the kernel rounds z to the storage dtype (straight-through: gradient 1)
+    z2 = z2 + (z2.to(dtype).float() - z2).detach()
     y2 = torch.nn.functional.layer_norm(z2, (d,), w2, b2, 1e-5)
     g = torch.randn(shape, device=dev)
     y1.backward(g.to(dtype))
@@ -704,7 +766,6 @@ def test_fused_dropout_add_layer_norm(dtype, shape, p, monkeypatch):
     assert close(b.grad, b2.grad, gtol)
 
 
-@_EXPERIMENTAL
 @pytest.mark.gpu
 def test_fused_dropout_add_layer_norm_random_mask_and_eval(monkeypatch):
     monkeypatch.setenv("ADAPTDL_B200_FUSED_LN", "1")
@@ -724,43 +785,3 @@ def test_fused_dropout_add_layer_norm_random_mask_and_eval(monkeypatch):
     assert torch.isfinite(a).all()
 
 
-# Phase-decomposed strided data gradient (ops/strided_conv.py): PyTorch-level
-# (four cuDNN convolutions), verified on CPU; gated until it has run on a GPU.
-#   ADAPTDL_B200_TEST_EXPERIMENTAL=1 python -m pytest tests -m gpu -k phase_dgrad
-@_EXPERIMENTAL
-@pytest.mark.gpu
-def test_phase_dgrad_on_gpu_eager_and_graph_captured(monkeypatch):
-    from adaptdl_b200.ops import strided_conv
-    monkeypatch.setenv("ADAPTDL_B200_PHASE_DGRAD", "1")
-    dev = torch.device("cuda:0")
-    torch.manual_seed(5)
-    conv = torch.nn.Conv2d(64, 128, 3, 2, 1, bias=False).to(dev).to(
-        memory_format=torch.channels_last)
-    x = torch.randn(32, 64, 32, 32, device=dev).contiguous(
-        memory_format=torch.channels_last).requires_grad_(True)
-
-    def step(fn):
-        x.grad = conv.weight.grad = None
-        with torch.autocast("cuda", dtype=torch.bfloat16):
-            out = fn(x)
-        out.float().square().mean().backward()
-        return x.grad.clone(), conv.weight.grad.clone()
-
-    want = step(conv)
-    got = step(lambda t: strided_conv.strided_conv3x3(t, conv))
-    for a, b in zip(got, want):
-        assert (a - b).norm() <= 2e-2 * b.norm()
-    # the backward must be capturable (no host-side index tensors)
-    side = torch.cuda.Stream()
-    with torch.cuda.stream(side):
-        for _ in range(3):
-            step(lambda t: strided_conv.strided_conv3x3(t, conv))
-        graph = torch.cuda.CUDAGraph()
-        x.grad = conv.weight.grad = None
-        with torch.cuda.graph(graph, stream=side):
-            with torch.autocast("cuda", dtype=torch.bfloat16):
-                out = strided_conv.strided_conv3x3(x, conv)
-            out.float().square().mean().backward()
-        graph.replay()
-    torch.cuda.synchronize()
-    assert (x.grad - want[0]).norm() <= 2e-2 * want[0].norm()

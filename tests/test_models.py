@@ -42,21 +42,3 @@ def test_parameter_counts(name, params_m):
     assert abs(n - params_m) / params_m < 0.08, n
 
 
-@pytest.mark.parametrize("channels_last", [False, True])
-def test_padded_stem_convolution_is_the_same_convolution(channels_last):
-    from adaptdl_b200.models.resnet import padded_channels_conv2d
-    torch.manual_seed(0)
-    conv = torch.nn.Conv2d(3, 16, 3, 1, 1, bias=False)
-    x = torch.randn(2, 3, 8, 8)
-    if channels_last:
-        x = x.contiguous(memory_format=torch.channels_last)
-        conv = conv.to(memory_format=torch.channels_last)
-    a = padded_channels_conv2d(x, conv)
-    b = conv(x)
-    assert torch.allclose(a, b, atol=1e-6)
-    a.sum().backward()
-    g = conv.weight.grad.clone()
-    conv.weight.grad = None
-    b.sum().backward()
-    assert torch.allclose(g, conv.weight.grad, atol=1e-5)
-    assert g.shape == (16, 3, 3, 3)

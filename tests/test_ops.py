@@ -200,71 +200,7 @@ def test_ln_and_gemm_support_predicates():
     assert not linear_act.supported(Fake(), torch.empty(3072, 700))   # K mismatch
 
 
-@pytest.mark.parametrize("channels_last", [False, True])
-def test_phase_dgrad_matches_autograd(channels_last):
-    from adaptdl_b200.ops.strided_conv import phase_dgrad
-    torch.manual_seed(0)
-    x = torch.randn(3, 5, 8, 12, dtype=torch.float64, requires_grad=True)
-    w = torch.randn(7, 5, 3, 3, dtype=torch.float64)
-    y = torch.nn.functional.conv2d(x, w, None, 2, 1)
-    dy = torch.randn_like(y)
-    if channels_last:
-        dy = dy.contiguous(memory_format=torch.channels_last)
-    want, = torch.autograd.grad(y, x, dy)
-    got = phase_dgrad(dy, w, x.shape)
-    assert got.shape == want.shape
-    assert got.is_contiguous(memory_format=torch.channels_last) == \
-        channels_last or not channels_last
-    torch.testing.assert_close(got, want, rtol=1e-10, atol=1e-10)
 
 
-def test_strided_conv_module_path(monkeypatch):
-    from adaptdl_b200.ops import strided_conv
-    torch.manual_seed(1)
-    conv = torch.nn.Conv2d(4, 6, 3, 2, 1, bias=False).double()
-    x = torch.randn(2, 4, 6, 6, dtype=torch.float64, requires_grad=True)
-    ref = conv(x)
-    gx, gw = torch.autograd.grad(ref.square().sum(), [x, conv.weight])
-    monkeypatch.setenv("ADAPTDL_B200_PHASE_DGRAD", "1")
-    assert strided_conv.supported(x, conv)
-    out = strided_conv.strided_conv3x3(x, conv)
-    assert out.grad_fn.name().startswith("_PhaseDgradConv")
-    torch.testing.assert_close(out, ref)
-    hx, hw = torch.autograd.grad(out.square().sum(), [x, conv.weight])
-    torch.testing.assert_close(hx, gx, rtol=1e-10, atol=1e-10)
-    torch.testing.assert_close(hw, gw, rtol=1e-10, atol=1e-10)
-    # unsupported shapes and the default (flag off) fall back to the module
-    odd = torch.randn(2, 4, 5, 6, dtype=torch.float64)
-    assert not strided_conv.supported(odd, conv)
-    monkeypatch.setenv("ADAPTDL_B200_PHASE_DGRAD", "0")
-    assert strided_conv.strided_conv3x3(x, conv).grad_fn.name() != \
-        out.grad_fn.name()
 
 
-def test_resnet_with_phase_dgrad_matches_default(monkeypatch):
-    """Same model, same batch: gradients with the phase-decomposed strided
-    data gradient equal the default ones (fp32), and track them under bf16
-    autocast."""
-    from adaptdl_b200.models import resnet18
-    torch.manual_seed(0)
-    model = resnet18().train()
-    x = torch.randn(4, 3, 32, 32)
-    y = torch.randint(0, 10, (4,))
-
-    def grads(flag, autocast):
-        monkeypatch.setenv("ADAPTDL_B200_PHASE_DGRAD", flag)
-        model.zero_grad(set_to_none=True)
-        with torch.autocast("cpu", dtype=torch.bfloat16, enabled=autocast):
-            loss = F.cross_entropy(model(x).float(), y)
-        loss.backward()
-        return {n: p.grad.clone() for n, p in model.named_parameters()}
-
-    base, phased = grads("0", False), grads("1", False)
-    for name in base:
-        torch.testing.assert_close(phased[name], base[name], rtol=2e-4,
-                                   atol=2e-5, msg=name)
-    base, phased = grads("0", True), grads("1", True)
-    num = sum((phased[n] - base[n]).square().sum() for n in base)
-    den = sum(base[n].square().sum() for n in base)
-    assert float(num / den) ** 0.5 < 0.05
-    assert all(phased[n].dtype == torch.float32 for n in phased)

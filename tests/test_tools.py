@@ -108,7 +108,5 @@ def test_conv_bench_plumbing_on_cpu():
     rows = [bench.bench_layer(spec, 2, torch.device("cpu"), torch.float32,
                               measure)
             for spec in bench.RESNET18_CONVS[:3]]
-    assert "fprop_padded_us" in rows[0]            # 3-channel stem
-    assert "dgrad_phase_us" in rows[2]             # stride-2 3x3
-    assert "dgrad_phase_us" not in rows[1]
+    assert {"fprop_us", "dgrad_us", "wgrad_us"} <= set(rows[0])
     assert all(r["fprop_us"] > 0 and r["gflop"] > 0 for r in rows)

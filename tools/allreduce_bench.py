@@ -4,10 +4,24 @@
     torchrun --nproc-per-node N tools/allreduce_bench.py [--out f.json]
 
 For each bucket size: device time (CUDA events, max over ranks) of
-(a) ``adl_allreduce_gns`` (in-place mean + both GNS statistics), (b)
-``dist.all_reduce`` alone, (c) what the reference does around it for the same
-result (all-reduce + per-bucket norm kernels). Bus bandwidth =
-``2 (N-1)/N * bytes / time``; roofline = measured 770 GB/s per direction.
+(a) ``adl_allreduce_gns`` (in-place mean + both GNS statistics) in each of
+its flavours (two-shot P2P, one-shot push, NVLS), (b) ``dist.all_reduce``
+alone, (c) what the reference does around it for the same result (all-reduce
++ per-bucket norm kernels).
+
+Two timings per flavour:
+
+``isolated``   one bucket = one optimizer step: the bucket kernel carries the
+               fused finalize (statistics exchange + the step's closing peer
+               barrier), i.e. a COMPLETE all-reduce whose result is visible on
+               every rank when the kernel ends -- the number to hold against
+               NCCL and the roofline;
+``pipelined``  eight bucket kernels back to back + one closing kernel, per
+               kernel: what a bucket costs in the middle of a backward pass.
+
+Roofline: bytes each GPU must receive over NVLink / 770 GB/s (measured peer
+copy; 900 nominal): two-shot 2(N-1)/N x B, NVLS (1 + 1/N) x B, one-shot
+(N-1) x B.
 """
 import argparse
 import json
@@ -45,9 +59,11 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=None)
     ap.add_argument("--sizes-mb", default="0.0625,0.25,1,4,16,64,256")
+    ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--ctas", default="")
+    ap.add_argument("--nvls-ctas", default="32,64,96")
     ap.add_argument("--sweep", action="store_true",
-                    help="also time the NVLS flavour at 32/64/96 CTAs")
+                    help="also time the NVLS flavour at several grid sizes")
     args = ap.parse_args()
     rank = int(os.environ["RANK"])
     world = int(os.environ["WORLD_SIZE"])
@@ -55,21 +71,35 @@ def main():
     torch.cuda.set_device(dev)
     dist.init_process_group("nccl", device_id=dev)
     from adaptdl_b200.parallel.reducer_cuda import CudaGradReducer
+    from adaptdl_b200._native import (FLAVOUR_NVLS, FLAVOUR_ONESHOT,
+                                      FLAVOUR_TWOSHOT)
+    names = {FLAVOUR_TWOSHOT: "twoshot", FLAVOUR_ONESHOT: "oneshot",
+             FLAVOUR_NVLS: "nvls"}
+    dtype = torch.float32 if args.dtype == "fp32" else torch.bfloat16
+    itemsize = 4 if args.dtype == "fp32" else 2
+    peak = 770.0     # GB/s per direction, measured peer copy
     rows = []
     for mb in [float(x) for x in args.sizes_mb.split(",")]:
-        numel = int(mb * (1 << 20) / 4)
-        p = torch.nn.Parameter(torch.randn(numel, device=dev))
+        numel = int(mb * (1 << 20) / itemsize)
+        p = torch.nn.Parameter(torch.randn(numel, device=dev).to(dtype))
         if args.ctas:
             os.environ["ADAPTDL_B200_REDUCE_CTAS"] = args.ctas
         iters = 200 if mb <= 4 else 40
         variants = {}
-        # the fused kernel in its P2P flavour and its NVLS (multimem)
-        # flavour at several grid sizes; "fused" = what the reducer picks
-        configs = [("fused", {}), ("p2p", {"ADAPTDL_B200_NVLS_MIN_MB": "1e9"})]
-        if args.sweep:
+        configs = [("auto", {}),
+                   ("twoshot", {"ADAPTDL_B200_NVLS_MIN_MB": "1e9",
+                                "ADAPTDL_B200_ONESHOT_KB": "0"})]
+        if mb <= 8:
+            configs.append(("oneshot", {"ADAPTDL_B200_NVLS_MIN_MB": "1e9",
+                                        "ADAPTDL_B200_ONESHOT_KB": "1e9"}))
+        nvls_grids = [int(c) for c in args.nvls_ctas.split(",")] \
+            if args.sweep else [64]
+        if world > 2 or args.sweep:
             configs += [("nvls%d" % c, {"ADAPTDL_B200_NVLS_MIN_MB": "0",
+                                        "ADAPTDL_B200_ONESHOT_KB": "0",
                                         "ADAPTDL_B200_NVLS_CTAS": str(c)})
-                        for c in (32, 64, 96)]
+                        for c in nvls_grids]
+        picked = None
         for tag, env in configs:
             saved = {k: os.environ.get(k) for k in env}
             os.environ.update(env)
@@ -83,18 +113,34 @@ def main():
             arena = red.arenas[0]
             bucket = arena.buckets[0]
             arena.grad.normal_()
-            nbytes = bucket.length * 4
-            variants[tag] = timed(
-                lambda: red._reduce(arena, bucket, 1.0 / world, True),
-                iters, stream=red._comm) * 1e3
-            if tag == "fused":
-                used_nvls = bool(getattr(red, "nvls_launches", 0))
+            nbytes = bucket.length * itemsize
+            flavour = names[red._flavour[(0, bucket.index)]]
+            if tag.startswith("nvls") and flavour != "nvls":
+                del red, arena, bucket      # no multicast on this box
+                continue
+            red._k_before, red._accum_count = 0, 1
+
+            def isolated():
+                red._mark_sync_start()
+                red._reduce(arena, bucket, 1.0 / world, True, last=True)
+                red._finalize_step()
+
+            def pipelined():
+                for _ in range(8):
+                    red._reduce(arena, bucket, 1.0 / world, True)
+                isolated()
+            t_iso = timed(isolated, iters, stream=red._comm) * 1e3
+            t_pipe = timed(pipelined, max(iters // 8, 5),
+                           stream=red._comm) * 1e3 / 9
+            variants[tag] = {"flavour": flavour, "isolated_us": t_iso,
+                             "pipelined_us": t_pipe}
+            if tag == "auto":
+                picked = flavour
                 provider, ctas = red._provider.name, red._reduce_ctas
             length = bucket.length
             del red, arena, bucket
-        fused = variants["fused"] / 1e3
-        flat = torch.randn(length, device=dev)
-        nccl = timed(lambda: dist.all_reduce(flat), iters)
+        flat = torch.randn(length, device=dev).to(dtype)
+        nccl = timed(lambda: dist.all_reduce(flat), iters) * 1e3
 
         def reference_like():
             local = flat.float().pow(2).sum(dtype=torch.float64)
@@ -102,16 +148,23 @@ def main():
             flat.div_(world)
             total = flat.float().pow(2).sum(dtype=torch.float64)
             return local, total
-        ref = timed(reference_like, iters)
-        bus = 2 * (world - 1) / world * nbytes
-        row = {"MB": nbytes / 2 ** 20, "world": world,
-               "fused_us": fused * 1e3, "nccl_us": nccl * 1e3,
-               "nccl_plus_norms_us": ref * 1e3,
-               "fused_busbw_GBps": bus / fused / 1e6,
-               "nccl_busbw_GBps": bus / nccl / 1e6,
-               "fused_frac_of_770": bus / fused / 1e6 / 770.0,
-               "provider": provider, "ctas": ctas, "nvls": used_nvls,
-               "variants_us": variants}
+        ref = timed(reference_like, iters) * 1e3
+        need = {"twoshot": 2.0 * (world - 1) / world * nbytes,
+                "nvls": (1.0 + 1.0 / world) * nbytes,
+                "oneshot": (world - 1.0) * nbytes}
+        for tag, v in variants.items():
+            floor_us = need[v["flavour"]] / (peak * 1e3)
+            v["roofline_us"] = floor_us
+            v["isolated_frac_of_770"] = floor_us / v["isolated_us"]
+            v["pipelined_frac_of_770"] = floor_us / v["pipelined_us"]
+        best = min(variants, key=lambda t: variants[t]["isolated_us"])
+        row = {"MB": nbytes / 2 ** 20, "world": world, "dtype": args.dtype,
+               "picked": picked, "best": best,
+               "fused_us": variants["auto"]["isolated_us"],
+               "nccl_us": nccl, "nccl_plus_norms_us": ref,
+               "nccl_busbw_GBps": need["twoshot"] / nccl / 1e3,
+               "provider": provider, "ctas": ctas,
+               "variants": variants}
         rows.append(row)
         if rank == 0:
             print(json.dumps(row), flush=True)

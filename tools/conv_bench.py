@@ -7,16 +7,14 @@ For every distinct convolution of ResNet-18 / CIFAR shape (batch 128,
 channels-last bf16) the forward, data-gradient and weight-gradient kernels
 are timed SEPARATELY (``aten::convolution_backward`` with an output mask),
 each replayed as a CUDA graph with an L2 flush in between, and reported with
-the TFLOP/s they reach. Extra rows:
+the TFLOP/s they reach.
 
-* ``dgrad_phase``  -- the stride-2 3x3 data gradient as four stride-1 phase
-  convolutions (``adaptdl_b200.ops.strided_conv.phase_dgrad``);
-* ``fprop_padded`` -- the 3-channel stem on 8 zero-padded channels
-  (``adaptdl_b200.models.resnet.padded_channels_conv2d``).
-
-The step profile (``profiles/r1_bn/step_profile_resnet_bf16.log``) says where
-to look: 2 x 98 us of ``implicit_gemm_strided_dgrad`` and ~117 us of
-non-tensor-core stem kernels in a 2 ms step. On a machine without a GPU the
+The step profile (``profiles/r2_validate/step_profile_resnet_bf16.log``) says
+where to look: 2 x 98 us of ``implicit_gemm_strided_dgrad`` and ~117 us of
+non-tensor-core stem kernels in a 2 ms step. Two PyTorch-level workarounds
+(the stride-2 data gradient as four stride-1 phase convolutions; the stem on
+8 zero-padded input channels) were measured in round 2 and removed: whole-step
+time 2.108 ms and 1.991 ms against 1.994 ms (``profiles/r2_validate``). On a machine without a GPU the
 tool runs tiny shapes on the CPU (a smoke test of the plumbing, the numbers
 mean nothing).
 """
@@ -31,8 +29,6 @@ import torch
 import torch.nn.functional as F
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from adaptdl_b200.models.resnet import padded_channels_conv2d  # noqa: E402
-from adaptdl_b200.ops.strided_conv import phase_dgrad  # noqa: E402
 
 # (name, count in the model, C_in, C_out, input H=W, kernel, stride)
 RESNET18_CONVS = [
@@ -113,12 +109,6 @@ def bench_layer(spec, batch, device, dtype, measure):
         "dgrad": backward((True, False, False)),
         "wgrad": backward((False, True, False)),
     }
-    if k == 3 and stride == 2:
-        candidates["dgrad_phase"] = lambda: phase_dgrad(dy, w, x.shape)
-    if cin % 8:
-        conv = torch.nn.Conv2d(cin, cout, k, stride, pad, bias=False)
-        conv.weight = torch.nn.Parameter(w)
-        candidates["fprop_padded"] = lambda: padded_channels_conv2d(x, conv)
     with torch.no_grad():
         for key, fn in candidates.items():
             micros = measure(fn)
