@@ -274,7 +274,7 @@ def _declare(lib):
     lib.adl_sm_count.argtypes = [c.c_int]
     lib.adl_allreduce_gns.argtypes = [c.POINTER(ReduceArgs),
                                       c.POINTER(FinalizeArgs), c.c_int,
-                                      c.c_int, c.c_int, c.c_void_p]
+                                      c.c_int, c.c_int, c.c_int, c.c_void_p]
     lib.adl_local.argtypes = [c.POINTER(LocalArgs), c.POINTER(FinalizeArgs),
                               c.c_int, c.c_int, c.c_int, c.c_void_p]
     lib.adl_finalize_stats.argtypes = [c.POINTER(FinalizeArgs), c.c_void_p]
@@ -314,6 +314,11 @@ def _declare(lib):
         c.c_void_p, c.c_void_p, c.c_void_p]
     lib.adl_bn_act.argtypes = [c.POINTER(BnArgs), c.c_int, c.c_int, c.c_int,
                                c.c_int, c.c_void_p]
+    lib.adl_bn_act_fused.argtypes = [c.POINTER(BnArgs), c.c_int, c.c_int,
+                                     c.c_int, c.c_void_p]
+    lib.adl_bn_config.argtypes = [c.c_int]
+    lib.adl_bn_config.restype = None
+    lib.adl_bn_fused_max_grid.argtypes = [c.c_int]
     lib.adl_dropout_add_ln.argtypes = [c.POINTER(LnArgs), c.c_int, c.c_int,
                                        c.c_int, c.c_void_p]
     for name, struct in (("adl_sizeof_bn_args", BnArgs),

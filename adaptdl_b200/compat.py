@@ -1,0 +1,70 @@
+"""Import aliases: ``import adaptdl`` (and ``adaptdl_sched`` / ``adaptdl_ray``
+/ ``adaptdl_cli``) resolve to this framework, so that training scripts
+written against petuum/adaptdl run unmodified::
+
+    import adaptdl
+    import adaptdl.torch as adl            # -> adaptdl_b200.torch
+    from adaptdl.torch.data import current_dataloader
+
+The four top-level packages in the repository root (three lines each) call
+:func:`alias`; nothing is copied or re-exported by hand -- a meta-path finder
+maps every ``<alias>.x.y`` to ``<target>.x.y`` and registers the *same*
+module object under both names (so module-level state, e.g. the current data
+loader, is shared no matter which name imported it).
+"""
+
+import importlib
+import importlib.abc
+import importlib.machinery
+import importlib.util
+import sys
+
+__all__ = ["alias"]
+
+_INSTALLED = {}
+
+
+class _AliasFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+
+    def __init__(self, name, target):
+        self.name, self.target = name, target
+
+    def _real_name(self, fullname):
+        if fullname == self.name:
+            return self.target
+        if fullname.startswith(self.name + "."):
+            return self.target + fullname[len(self.name):]
+        return None
+
+    def find_spec(self, fullname, path=None, target=None):
+        real = self._real_name(fullname)
+        if real is None:
+            return None
+        try:
+            spec = importlib.util.find_spec(real)
+        except (ImportError, ValueError):
+            return None
+        if spec is None:
+            return None
+        return importlib.machinery.ModuleSpec(
+            fullname, self, is_package=spec.submodule_search_locations
+            is not None)
+
+    def create_module(self, spec):
+        # the real module object itself: one module, two names
+        return importlib.import_module(self._real_name(spec.name))
+
+    def exec_module(self, module):
+        pass
+
+
+def alias(name, target):
+    """Make ``import <name>[.sub]`` return ``<target>[.sub]``."""
+    if _INSTALLED.get(name) == target:
+        return sys.modules.get(name)
+    finder = _AliasFinder(name, target)
+    sys.meta_path.insert(0, finder)
+    _INSTALLED[name] = target
+    module = importlib.import_module(target)
+    sys.modules[name] = module
+    return module

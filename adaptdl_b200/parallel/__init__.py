@@ -7,15 +7,14 @@ import logging
 
 LOG = logging.getLogger(__name__)
 
-# Default bucket caps. The fused kernels cost ~20 us per bucket on the comm
-# stream (nothing on the host inside a CUDA graph), so smaller buckets than
-# DDP's are plausible: with 25 MB, ResNet-18's 22 MB of bf16 gradients are one
-# bucket that only completes with the first layer, i.e. the whole all-reduce
-# (~50 us at N=8) is exposed. Smaller buckets overlap it with backward but put
-# flag-spinning CTAs next to the backward kernels; that trade has not been
-# measured yet (ROUND2_PLAN.md, `bench.py --bucket-cap-mb 4`), so the default
-# stays at the value every published number was taken with.
-CUDA_BUCKET_CAP_MB = 25
+# Default bucket caps. A fused bucket kernel costs ~10-20 us on the comm
+# stream (nothing on the host inside a CUDA graph), so buckets smaller than
+# DDP's 25 MB pay off: they start reducing while backward is still producing
+# gradients and keep the un-overlappable tail short. Measured on ResNet-18 at
+# N = 2 (profiles/r2_n2): 25 MB 2.110 ms/step, 8 MB 2.084, 4 MB 2.100,
+# 2 MB 2.124. The first and the last bucket have their own small caps
+# (reducer_base.FIRST_BUCKET_BYTES / LAST_BUCKET_BYTES).
+CUDA_BUCKET_CAP_MB = 8
 TORCH_BUCKET_CAP_MB = 25
 
 

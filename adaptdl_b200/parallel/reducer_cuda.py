@@ -110,6 +110,11 @@ class CudaGradReducer(GradReducer):
             "ADAPTDL_B200_NVLS_MIN_MB", "16")) * (1 << 20))
         self._nvls_ctas = max(1, min(int(os.environ.get(
             "ADAPTDL_B200_NVLS_CTAS", "64")), MAX_CTAS - 1))
+        # the switch moves (1 + 1/N) B per GPU against 2 (N-1)/N B for the
+        # two-shot flavour: no gain at N = 2 (measured 2x slower), 1.55x
+        # fewer bytes at N = 8
+        self._nvls_min_world = int(os.environ.get(
+            "ADAPTDL_B200_NVLS_MIN_WORLD", "4"))
         # one-shot push: buckets whose pushed bytes ((N-1) x bucket) stay
         # below this are latency-bound; each gets N lanes of staging
         self._oneshot_push_bytes = int(float(os.environ.get(
@@ -159,7 +164,8 @@ class CudaGradReducer(GradReducer):
             self._grad_mc[i] = (self._region.mc_ptr + offsets[("grad", i)]
                                 if self._region.mc_ptr else 0)
             for b in arena.buckets:
-                if self._grad_mc[i] and self.world_size > 1 and \
+                if self._grad_mc[i] and \
+                        self.world_size >= self._nvls_min_world and \
                         self._flavour[(i, b.index)] == FLAVOUR_TWOSHOT and \
                         b.length * itemsize >= self._nvls_min_bytes:
                     self._flavour[(i, b.index)] = FLAVOUR_NVLS
@@ -191,6 +197,12 @@ class CudaGradReducer(GradReducer):
         self._reduce_ctas = int(os.environ.get(
             "ADAPTDL_B200_REDUCE_CTAS", "32"))
         self._reduce_ctas = max(1, min(self._reduce_ctas, MAX_CTAS - 1))
+        # CTA size of the bucket kernels that run next to backward (two-shot
+        # and one-shot flavours): 256 threads keep half of an SM's registers
+        # and warp slots free for the backward kernels; NVLS-sized buckets
+        # are bandwidth-bound and keep 512
+        self._reduce_threads = int(os.environ.get(
+            "ADAPTDL_B200_REDUCE_THREADS", "256"))
         super()._attach()
         for i, arena in enumerate(self.arenas):
             self._build_seg_tables(i, arena)
@@ -390,23 +402,28 @@ class CudaGradReducer(GradReducer):
             # in-switch reduction: multimem.ld_reduce / multimem.st
             args.mc_buf = self._grad_mc[ai] + off
             self.nvls_launches += 1
-            per_cta = 512 * 8
+            threads = 512
+            per_cta = threads * 8
             grid = max(1, min(self._nvls_ctas,
                               (slice_vec + per_cta - 1) // per_cta))
         elif flavour == FLAVOUR_ONESHOT:
             for p in range(self.world_size):
                 args.stage[p] = self._stage_ptrs[(ai, bucket.index)][p]
             self.oneshot_launches += 1
-            grid = max(1, min(self._reduce_ctas, (n_vec + 511) // 512))
+            threads = self._reduce_threads
+            grid = max(1, min(self._reduce_ctas,
+                              (n_vec + threads - 1) // threads))
         elif self.world_size > 1:
             # each thread keeps 16/W vectors in flight per iteration; a CTA
             # moves >= 64 KB of its slice so that small buckets leave the
             # SMs to backward
-            per_cta = max(512 * max(16 // self.world_size, 1),
+            threads = self._reduce_threads
+            per_cta = max(threads * max(16 // self.world_size, 1),
                           (64 << 10) // layout.VEC_BYTES)
             grid = max(1, min(self._reduce_ctas,
                               (slice_vec + per_cta - 1) // per_cta))
         else:
+            threads = 512
             grid = self._local_grid(n_vec)
         fin = None
         if last and self.fuse_finalize:
@@ -417,7 +434,7 @@ class CudaGradReducer(GradReducer):
         self._order_after_compute()
         check(self._lib.adl_allreduce_gns(
             ctypes.byref(args), ctypes.byref(fin) if fin is not None else None,
-            _DTYPE_CODE[arena.dtype], flavour, grid,
+            _DTYPE_CODE[arena.dtype], flavour, grid, threads,
             self._comm.cuda_stream), "adl_allreduce_gns")
         self.launches += 1
 

@@ -10,10 +10,11 @@ back to everyone. Futures may be waited out of order.
 Capabilities match the reference's ``adaptdl/adaptdl/reducer.py:30-160``
 (allreduce / allreduce_async / broadcast, local mode with port 0, connect
 retries); the design differs: length-prefixed frames instead of streaming
-``pickle.load``, a selector-driven server that accepts contributions in any
-arrival order (so no reply-ordering trick is needed to dodge GIL deadlocks),
-an event instead of sleep-polling for local-mode port discovery, and a real
-``close``.
+``pickle.load``, a fully non-blocking selector-driven server (per-connection
+input buffers and output queues: contributions are accepted in any arrival
+order and several large asynchronous all-reduces may be in flight without
+the send/receive deadlock a blocking server has), an event instead of
+sleep-polling for local-mode port discovery, and a real ``close``.
 
 All replicas must invoke collectives in the same order.
 """
@@ -113,43 +114,15 @@ class _Server(threading.Thread):
         return clients
 
     def run(self):
-        clients = []
+        conns = []
         try:
-            clients = self._accept_all()
+            conns = [_Conn(rank, sock)
+                     for rank, sock in enumerate(self._accept_all())]
             sel = selectors.DefaultSelector()
-            for rank, conn in enumerate(clients):
-                sel.register(conn, selectors.EVENT_READ, rank)
-            pending = {}                         # key -> {rank: obj}
-            dead = set()                         # ranks that hung up
-            alive = self._replicas
-
-            def doomed(slot):
-                """A reduction some departed replica never contributed to
-                can never complete."""
-                return any(rank not in slot for rank in dead)
-            while alive and not self._stop_event.is_set():
-                for skey, _ in sel.select(timeout=0.5):
-                    conn, rank = skey.fileobj, skey.data
-                    try:
-                        key, obj = _recv_frame(conn)
-                    except (ConnectionError, OSError):
-                        sel.unregister(conn)
-                        alive -= 1
-                        dead.add(rank)
-                        if any(doomed(slot) for slot in pending.values()):
-                            raise ConnectionError(
-                                "replica {} left in the middle of a "
-                                "collective".format(rank))
-                        continue
-                    slot = pending.setdefault(key, {})
-                    slot[rank] = obj
-                    if len(slot) == self._replicas:
-                        del pending[key]
-                        self._finish(key, slot, clients)
-                    elif doomed(slot):
-                        raise ConnectionError(
-                            "replica(s) {} are gone: the collective cannot "
-                            "complete".format(sorted(dead)))
+            for conn in conns:
+                conn.sock.setblocking(False)
+                sel.register(conn.sock, selectors.EVENT_READ, conn)
+            self._loop(sel, conns)
         except Exception as exc:  # noqa: BLE001 - surfaced to clients
             if not self._stop_event.is_set():
                 self.error = exc
@@ -162,28 +135,155 @@ class _Server(threading.Thread):
             if self.error is not None:
                 # fail fast: everybody blocked on a result gets a
                 # ConnectionError instead of waiting for a replica that died
-                for conn in clients:
+                for conn in conns:
                     try:
-                        conn.shutdown(socket.SHUT_RDWR)
+                        conn.sock.shutdown(socket.SHUT_RDWR)
                     except OSError:
                         pass
 
-    def _finish(self, key, slot, clients):
+    def _loop(self, sel, conns):
+        """Event loop. Nothing in here blocks on one client: frames are
+        parsed out of per-connection input buffers as bytes arrive and
+        replies leave through per-connection output queues, so a replica
+        that is still busy sending (several large asynchronous all-reduces
+        in flight) cannot stall the replies the others -- or itself -- are
+        waiting for (the reference's blocking server deadlocks there)."""
+        pending = {}                         # key -> {rank: obj}
+        dead = set()                         # ranks that hung up
+        alive = self._replicas
+        held_for_rank0 = []                  # see _finish
+
+        def doomed(slot):
+            """A reduction some departed replica never contributed to can
+            never complete."""
+            return any(rank not in slot for rank in dead)
+
+        def want_write(conn):
+            events = selectors.EVENT_READ if not conn.closed else 0
+            if conn.out:
+                events |= selectors.EVENT_WRITE
+            if events:
+                sel.modify(conn.sock, events, conn)
+
+        drain_deadline = None
+        while alive:
+            if self._stop_event.is_set():
+                # orderly shutdown: flush what is already queued, briefly
+                if drain_deadline is None:
+                    drain_deadline = time.time() + 5.0
+                if not any(c.out for c in conns) and not held_for_rank0 \
+                        or time.time() > drain_deadline:
+                    break
+            for skey, events in sel.select(timeout=0.2):
+                conn = skey.data
+                if events & selectors.EVENT_WRITE:
+                    conn.flush()
+                    want_write(conn)
+                if not events & selectors.EVENT_READ:
+                    continue
+                try:
+                    frames = conn.read_frames()
+                except (ConnectionError, OSError):
+                    conn.closed = True
+                    if conn.out:
+                        want_write(conn)
+                    else:
+                        sel.unregister(conn.sock)
+                    alive -= 1
+                    dead.add(conn.rank)
+                    if any(doomed(slot) for slot in pending.values()):
+                        raise ConnectionError(
+                            "replica {} left in the middle of a "
+                            "collective".format(conn.rank))
+                    continue
+                for key, obj in frames:
+                    slot = pending.setdefault(key, {})
+                    slot[conn.rank] = obj
+                    if len(slot) == self._replicas:
+                        del pending[key]
+                        frame = self._finish(key, slot)
+                        for other in conns[1:]:
+                            if not other.closed:
+                                other.out.append(memoryview(frame))
+                                want_write(other)
+                        held_for_rank0.append(frame)
+                    elif doomed(slot):
+                        raise ConnectionError(
+                            "replica(s) {} are gone: the collective cannot "
+                            "complete".format(sorted(dead)))
+            # Rank 0 is answered last: it hosts this thread, and once it has
+            # its result it may run ahead and even exit; by then every other
+            # replica's reply must have left.
+            if held_for_rank0 and not any(c.out for c in conns[1:]):
+                if not conns[0].closed:
+                    conns[0].out.extend(memoryview(f)
+                                        for f in held_for_rank0)
+                    want_write(conns[0])
+                held_for_rank0 = []
+
+    def _finish(self, key, slot):
         with self._lock:
             reduce_fn = self._reduce_fns.pop(key)
         result = slot[0]
         for rank in range(1, self._replicas):
             result = reduce_fn(result, slot[rank])
         payload = pickle.dumps(result, protocol=pickle.HIGHEST_PROTOCOL)
-        frame = _HDR.pack(key, len(payload)) + payload
-        # Rank 0 is answered last: it hosts this thread, and once it has its
-        # result it may run ahead and even exit; by then every other
-        # replica's reply is already in its socket buffer.
-        for conn in reversed(clients):
+        return _HDR.pack(key, len(payload)) + payload
+
+
+class _Conn(object):
+    """Server side of one replica's connection (non-blocking)."""
+
+    CHUNK = 1 << 20
+
+    def __init__(self, rank, sock):
+        self.rank = rank
+        self.sock = sock
+        self.inbuf = bytearray()
+        self.out = []               # memoryviews still to be sent, in order
+        self.closed = False
+
+    def read_frames(self):
+        """Drain the socket; returns the complete ``(key, obj)`` frames."""
+        while True:
             try:
-                conn.sendall(frame)
+                chunk = self.sock.recv(self.CHUNK)
+            except (BlockingIOError, InterruptedError):
+                break
+            if not chunk:
+                raise ConnectionError("peer closed the connection")
+            self.inbuf += chunk
+            if len(chunk) < self.CHUNK:
+                break
+        frames = []
+        view = self.inbuf
+        offset = 0
+        while len(view) - offset >= _HDR.size:
+            key, length = _HDR.unpack_from(view, offset)
+            end = offset + _HDR.size + length
+            if len(view) < end:
+                break
+            frames.append((key, pickle.loads(
+                bytes(view[offset + _HDR.size:end]))))
+            offset = end
+        if offset:
+            del self.inbuf[:offset]
+        return frames
+
+    def flush(self):
+        while self.out:
+            head = self.out[0]
+            try:
+                sent = self.sock.send(head)
+            except (BlockingIOError, InterruptedError):
+                return
             except OSError:
-                pass
+                self.out = []       # the peer is gone
+                return
+            if sent < len(head):
+                self.out[0] = head[sent:]
+                return
+            self.out.pop(0)
 
 
 class Reducer(object):

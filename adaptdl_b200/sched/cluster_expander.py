@@ -53,7 +53,6 @@ class ClusterExpander(object):
         self._owner_reference = owner_reference
         self._active_nodes = set()
         self._allocations = set()
-        self._serial = 0
 
     def fit(self, active_nodes):
         """``active_nodes``: names of the nodes to keep plus one ``"~k"``
@@ -84,10 +83,12 @@ class ClusterExpander(object):
         LOG.info("placeholders: want %d, have %d", expected, len(live))
         if expected > len(live):
             for _ in range(expected - len(live)):
+                # no explicit name: the API server derives a unique one
+                # from the template's generateName, so placeholders that
+                # survived a scheduler restart can never collide (409) with
+                # new ones
                 pod = placeholder_pod(self._owner_reference)
-                self._serial += 1
-                pod["metadata"]["name"] = "adaptdl-placeholder-{}".format(
-                    self._serial)
+                pod["metadata"].pop("name", None)
                 await self._cluster.create_pod(self._namespace, pod)
         elif expected < len(live):
             for pod in live[:len(live) - expected]:

@@ -59,6 +59,33 @@ def _phase(pod):
     return (pod.get("status") or {}).get("phase")
 
 
+def _parse_time(stamp):
+    import datetime
+    if isinstance(stamp, datetime.datetime):
+        return stamp
+    try:
+        return datetime.datetime.fromisoformat(
+            str(stamp).replace("Z", "+00:00"))
+    except ValueError:
+        return None
+
+
+def _job_duration_seconds(job, patch):
+    """completionTimestamp - metadata.creationTimestamp (0 if unknown)."""
+    import datetime
+    created = _parse_time((job.get("metadata") or {})
+                          .get("creationTimestamp"))
+    done = _parse_time(patch.get("completionTimestamp")) or \
+        datetime.datetime.now(datetime.timezone.utc)
+    if created is None:
+        return 0.0
+    if created.tzinfo is None:
+        created = created.replace(tzinfo=datetime.timezone.utc)
+    if done.tzinfo is None:
+        done = done.replace(tzinfo=datetime.timezone.utc)
+    return max((done - created).total_seconds(), 0.0)
+
+
 def _deleting(pod):
     return pod["metadata"].get("deletionTimestamp") is not None
 
@@ -410,7 +437,12 @@ class AdaptDLController(object):
             LOG.info("Patch AdaptDLJob %s: %s", name, patch)
             if JOB_COMPLETION_TIME is not None and \
                     patch.get("phase") in ("Succeeded", "Failed"):
-                JOB_COMPLETION_TIME.labels(patch["phase"]).observe(0)
+                JOB_COMPLETION_TIME.labels(patch["phase"]).observe(
+                    _job_duration_seconds(job, patch))
+            if JOB_SUBMISSION_COUNT is not None and \
+                    patch.get("phase") == "Pending" and \
+                    not (job.get("status") or {}).get("phase"):
+                JOB_SUBMISSION_COUNT.inc()       # first time we see the job
             await cluster.patch_job_status(namespace, name, {"status": patch})
         return patch
 

@@ -136,6 +136,14 @@ class InMemoryCluster(object):
             return copy.deepcopy(pod)
         pod = copy.deepcopy(pod)
         pod["metadata"]["namespace"] = namespace
+        if not pod["metadata"].get("name"):
+            # what the API server does with metadata.generateName
+            import uuid
+            pod["metadata"]["name"] = \
+                pod["metadata"].get("generateName", "pod-") \
+                + uuid.uuid4().hex[:5]
+        elif (namespace, pod["metadata"]["name"]) in self.pods:
+            raise ApiError(409, "pod already exists")
         pod.setdefault("status", {"phase": "Pending"})
         self.pods[(namespace, pod["metadata"]["name"])] = pod
         self._notify("pod", pod)

@@ -1,24 +1,31 @@
-"""Replica- and restart-consistent metric accumulation.
+"""Metric accumulation that is consistent across replicas and restarts.
 
-An :class:`Accumulator` looks like a ``dict`` with two modes:
+``Accumulator`` is the user-facing object of the reference's
+``adaptdl/adaptdl/torch/accumulator.py`` (same constructor, ``+=`` / ``-=``
+/ ``update`` / ``subtract`` / ``synchronized()`` behaviour, same checkpoint
+file contents); the machinery below is this repo's own:
 
-* **accumulation mode** (default): ``accum[k] += v`` / ``accum.update(k=v)``
-  record *local* additive updates, lazily summed over replicas; reads behave
-  like an empty dict.
-* **synchronized mode** (``with accum.synchronized():``): pending updates of
-  all replicas are summed in, every replica sees the same contents and may
-  use the object like a normal ``dict`` (writes must be identical everywhere).
+* local updates are an append-only **delta log** of ``(key, amount)``
+  entries -- ``accum[k] += v`` builds an immutable :class:`_Delta` through
+  the ``__getitem__`` / ``__add__`` / ``__setitem__`` protocol and logs it;
+* a **ledger** (the checkpointed :class:`~adaptdl_b200.checkpoint.State`)
+  holds the job-wide totals and the snapshots that must be replayed after a
+  restart, indexed by *loop position* ``(epoch, n-th synchronisation of that
+  epoch outside data-loader loops)``;
+* ``synchronized()`` opens a **session**: the compacted delta logs of all
+  replicas are summed over the control plane into the totals (or, if this
+  loop position was already passed before the last restart, the recorded
+  snapshot is served instead and the local log is dropped), and while the
+  session is open the accumulator is an ordinary ``dict`` view of the totals.
 
-Results of synchronisations that happened outside of data-loader loops are
-remembered per epoch and *replayed* after a restart, so code that already ran
-before the checkpoint observes the same values when the script is re-executed
-(parity: reference ``torch/accumulator.py:27-312``).
+Outside a session reads see an empty mapping: local partial sums are never
+observable, which is what makes results independent of the replica count.
 """
 
 import collections
 import collections.abc
-import contextlib
 import copy
+import pickle
 
 from adaptdl_b200 import checkpoint, collective
 from adaptdl_b200.torch.data import current_dataloader
@@ -27,74 +34,161 @@ from adaptdl_b200.torch.epoch import current_epoch
 __all__ = ["Accumulator"]
 
 
-def _dict_iadd(a, b):
-    for k, v in b.items():
-        a[k] = a[k] + v if k in a else v
-    return a
+def _merge_sums(total, part):
+    """``total[k] += part[k]`` (keys missing from ``total`` start at the
+    addend itself, so any type with ``+`` works)."""
+    for key, amount in part.items():
+        total[key] = (total[key] + amount) if key in total else amount
+    return total
 
 
-class _AccumulatorState(checkpoint.PickledFields):
-    """What an :class:`Accumulator` persists: the totals of the current epoch
-    and, per epoch, the history of synchronised snapshots (replayed after a
-    restart). Pending local updates are not persisted -- they are summed into
-    the totals before every save."""
+class _Delta(object):
+    """The pending effect of ``accum[key] <op>= amount``. Immutable: every
+    ``+`` / ``-`` gives a new delta, so a stray reference can never change
+    what was logged."""
 
-    FIELDS = ("results_history", "results")
-    LAYOUT = "tuple"
-    init_count = collections.Counter()   # epoch -> accumulators created
+    __slots__ = ("owner", "key", "amount")
 
-    def __init__(self, *args, **kwargs):
+    def __init__(self, owner, key, amount=0):
+        object.__setattr__(self, "owner", owner)
+        object.__setattr__(self, "key", key)
+        object.__setattr__(self, "amount", amount)
+
+    def __setattr__(self, name, value):
+        raise AttributeError("_Delta is immutable")
+
+    def _shifted(self, amount, sign):
+        if isinstance(amount, _Delta):
+            raise TypeError("an accumulator entry cannot be added to "
+                            "another one; add plain values")
+        return _Delta(self.owner, self.key,
+                      self.amount + amount if sign > 0
+                      else self.amount - amount)
+
+    def __add__(self, amount):
+        return self._shifted(amount, +1)
+
+    __radd__ = __add__
+
+    def __sub__(self, amount):
+        return self._shifted(amount, -1)
+
+
+class _Ledger(checkpoint.State):
+    """Checkpointed part of an accumulator: the replica-independent totals
+    and the snapshots to replay, keyed by loop position."""
+
+    _created = collections.Counter()      # epoch -> ledgers created in it
+
+    def __init__(self, initial):
         if current_dataloader() is not None:
-            raise RuntimeError("an Accumulator must be created outside of "
-                               "data-loader loops (every replica has to "
-                               "create the same accumulators in the same "
-                               "order)")
+            raise RuntimeError(
+                "create Accumulators before entering a data-loader loop: "
+                "all replicas must create the same ones in the same order")
         epoch = current_epoch()
-        counter = _AccumulatorState.init_count
-        super().__init__("adaptdl-accumulator-epoch{}-{}".format(
-            epoch, counter[epoch]))
-        counter[epoch] += 1
-        self.updates = {}
-        self.results = dict(*args, **kwargs)
-        self.results_history = collections.defaultdict(list)
+        index = _Ledger._created[epoch]
+        _Ledger._created[epoch] += 1
+        # the name doubles as the file name inside a checkpoint
+        super().__init__("adaptdl-accumulator-epoch{}-{}".format(epoch,
+                                                                 index))
+        self.totals = dict(initial)
+        self.snapshots = {}               # (epoch, ordinal) -> dict
+        self.log = []                     # local (key, amount) entries
+
+    # -- local log ---------------------------------------------------------
+
+    def record(self, key, amount):
+        self.log.append((key, amount))
+
+    def compact(self):
+        """Collapse the log into one amount per key (and empty it)."""
+        sums = {}
+        for key, amount in self.log:
+            sums[key] = (sums[key] + amount) if key in sums else amount
+        self.log = []
+        return sums
+
+    def settle(self):
+        """Sum every replica's log into the totals (a collective)."""
+        combined = collective.allreduce(self.compact(), _merge_sums)
+        _merge_sums(self.totals, combined)
+
+    # -- checkpoint.State --------------------------------------------------
 
     def sync(self):
-        """Sum the pending updates of all replicas into ``results``."""
-        updates = collective.allreduce(self.updates, _dict_iadd)
-        _dict_iadd(self.results, updates)
-        self.updates.clear()
+        self.settle()
+
+    def save(self, fileobj):
+        # on-disk layout of the reference (SURVEY App. B): one pickle of
+        # (history: {epoch: [snapshot, ...]}, results)
+        history = collections.defaultdict(list)
+        for (epoch, ordinal) in sorted(
+                self.snapshots, key=lambda k: (k[0] is not None, k[0] or 0,
+                                               k[1])):
+            history[epoch].append(self.snapshots[(epoch, ordinal)])
+        pickle.dump((history, self.totals), fileobj)
+
+    def load(self, fileobj):
+        history, self.totals = pickle.load(fileobj)
+        self.snapshots = {}
+        for epoch, rows in history.items():
+            for ordinal, snap in enumerate(rows):
+                self.snapshots[(epoch, ordinal)] = snap
+
+    def forget_before(self, epoch):
+        """Snapshots of finished epochs can never be asked for again."""
+        if epoch is None:
+            return
+        for position in [p for p in self.snapshots
+                         if p[0] is not None and p[0] < epoch]:
+            del self.snapshots[position]
 
 
-class _Pending(object):
-    """What ``accum[key]`` returns in accumulation mode: captures the
-    ``+ v`` / ``- v`` of an in-place update so ``__setitem__`` can record
-    it."""
+class _Session(object):
+    """``with accum.synchronized():`` -- re-entrant; the outermost entry
+    decides what the accumulator shows."""
 
-    __slots__ = ("accum", "key", "update")
-
-    def __init__(self, accum, key):
+    def __init__(self, accum):
         self.accum = accum
-        self.key = key
-        self.update = 0
 
-    def __add__(self, update):
-        if isinstance(update, _Pending):
-            raise TypeError("invalid update type: {}".format(type(update)))
-        self.update += update
-        return self
+    def __enter__(self):
+        accum = self.accum
+        accum._depth += 1
+        if accum._depth > 1:
+            return accum
+        ledger = accum._ledger
+        if current_dataloader() is not None:
+            # inside a data-loader loop: such code is skipped, never
+            # re-executed, after a restart -- nothing to replay or record
+            ledger.settle()
+            accum._visible = ledger.totals
+            return accum
+        epoch = current_epoch()
+        ledger.forget_before(epoch)
+        position = (epoch, accum._visits[epoch])   # n-th out-of-loop session
+        accum._visits[epoch] += 1
+        if position in ledger.snapshots:
+            # this loop position was passed before the last restart: show
+            # what was shown then; whatever was logged on the way here is a
+            # repetition of work already counted
+            ledger.log = []
+            accum._visible = ledger.snapshots[position]
+        else:
+            ledger.settle()
+            ledger.snapshots[position] = copy.deepcopy(ledger.totals)
+            accum._visible = ledger.totals
+        return accum
 
-    def __sub__(self, update):
-        if isinstance(update, _Pending):
-            raise TypeError("invalid update type: {}".format(type(update)))
-        self.update -= update
-        return self
-
-
-_Value = _Pending   # reference name
+    def __exit__(self, *exc):
+        accum = self.accum
+        accum._depth -= 1
+        if accum._depth == 0:
+            accum._visible = None
+        return False
 
 
 class Accumulator(collections.abc.MutableMapping):
-    """See the module docstring. Example::
+    """A ``dict``-like metric accumulator. Example::
 
         accum = Accumulator()
         for epoch in remaining_epochs_until(60):
@@ -105,107 +199,88 @@ class Accumulator(collections.abc.MutableMapping):
                 print(accum["loss_sum"] / accum["total"])
                 accum.clear()
 
+    In *accumulation mode* (the default) only additive updates are allowed
+    (``+=``, ``-=``, :meth:`update`, :meth:`subtract`); they stay local
+    until the next ``synchronized()`` block, inside which every replica sees
+    the same job-wide sums and may treat the object as a plain ``dict``
+    (writes there must be identical on every replica).
+
     Arguments: same as ``dict``.
     """
 
     def __init__(self, *args, **kwargs):
-        self._sync_count = collections.Counter()
-        self._synchronized = None
-        self._state = _AccumulatorState(*args, **kwargs)
-        checkpoint.load_state(self._state)
+        self._visits = collections.Counter()   # epoch -> sessions opened
+        self._depth = 0
+        self._visible = None                   # dict shown inside a session
+        self._ledger = _Ledger(dict(*args, **kwargs))
+        checkpoint.load_state(self._ledger)
 
-    @contextlib.contextmanager
     def synchronized(self):
-        """Enter synchronized mode. A distributed synchronisation point: all
-        replicas must enter it at the same place."""
-        if self._synchronized is not None:      # re-entrant
-            yield self
-            return
-        epoch = current_epoch()
-        history = self._state.results_history
-        for key in list(history.keys()):        # finished epochs never replay
-            if key is not None and epoch is not None and key < epoch:
-                history.pop(key)
-        ordinal = self._sync_count[epoch]
-        self._sync_count[epoch] += 1
-        saved = history[epoch]
-        assert ordinal <= len(saved)
-        if ordinal < len(saved):
-            # this synchronisation already happened before the restart
-            self._synchronized = saved[ordinal]
-            self._state.updates.clear()
-        else:
-            self._state.sync()
-            if current_dataloader() is None:
-                # code inside loader loops is not replayed, so only
-                # out-of-loop results need remembering
-                saved.append(copy.deepcopy(self._state.results))
-            self._synchronized = self._state.results
-        try:
-            yield self
-        finally:
-            self._synchronized = None
+        """Context manager entering synchronized mode. A collective: every
+        replica must open the session at the same point of the program."""
+        return _Session(self)
+
+    # -- additive updates ------------------------------------------------------
 
     def update(self, *args, **kwargs):
-        """*Additively* apply key/update pairs (unlike ``dict.update``)."""
-        for key, val in dict(*args, **kwargs).items():
-            self[key] += val
+        """Add the given amounts key by key (NOT ``dict.update``)."""
+        for key, amount in dict(*args, **kwargs).items():
+            self[key] += amount
 
     def subtract(self, *args, **kwargs):
-        """Subtract key/update pairs."""
-        for key, val in dict(*args, **kwargs).items():
-            self[key] -= val
+        """Subtract the given amounts key by key."""
+        for key, amount in dict(*args, **kwargs).items():
+            self[key] -= amount
 
     def __iadd__(self, other):
-        """``accum += {k: v}`` == ``accum.update({k: v})``."""
         self.update(other)
         return self
 
     def __isub__(self, other):
-        """``accum -= {k: v}`` == ``accum.subtract({k: v})``."""
         self.subtract(other)
         return self
 
+    # -- mapping protocol ------------------------------------------------------
+
     def __getitem__(self, key):
-        """Read access is meaningful in synchronized mode only; in
-        accumulation mode this supports ``accum[key] += v``."""
-        if self._synchronized is not None:
-            return self._synchronized[key]
-        return _Pending(self, key)
+        if self._visible is not None:
+            return self._visible[key]
+        # accumulation mode: ``accum[key] += v`` evaluates to
+        # ``accum[key] = accum[key] + v``; hand out a delta to carry ``v``
+        return _Delta(self, key)
 
     def __setitem__(self, key, value):
-        if self._synchronized is not None:
-            self._synchronized[key] = value
+        if self._visible is not None:
+            self._visible[key] = value
             return
-        # ``a[k] += v`` is  tmp = a[k]; tmp += v; a[k] = tmp  -- tmp is the
-        # _Pending returned by __getitem__, carrying v.
-        if not isinstance(value, _Pending):
-            raise TypeError("invalid value type: {}".format(type(value)))
-        if value.accum is not self:
-            raise ValueError("incompatible {}".format(type(self).__name__))
-        if key != value.key:
-            raise ValueError("incompatible key: {}".format(value.key))
-        updates = self._state.updates
-        updates[key] = updates.get(key, 0) + value.update
+        if not isinstance(value, _Delta):
+            raise TypeError(
+                "outside synchronized() an Accumulator only takes additive "
+                "updates (accum[k] += v), not assignment of {}".format(
+                    type(value).__name__))
+        if value.owner is not self or value.key != key:
+            raise ValueError("the update was built from a different "
+                             "accumulator entry ({!r})".format(value.key))
+        self._ledger.record(key, value.amount)
 
-    def _view(self):
-        return self._synchronized if self._synchronized is not None else {}
-
-    def __contains__(self, key):
-        return key in self._view()
+    def _shown(self):
+        return self._visible if self._visible is not None else {}
 
     def __delitem__(self, key):
-        del self._view()[key]
+        del self._shown()[key]
+
+    def __contains__(self, key):
+        return key in self._shown()
 
     def __iter__(self):
-        return iter(self._view())
+        return iter(self._shown())
 
     def __len__(self):
-        return len(self._view())
+        return len(self._shown())
 
     def __repr__(self):
-        return repr(self._view())
+        return "Accumulator({!r})".format(self._shown())
 
 
 def _reset_for_tests():
-    _AccumulatorState.init_count = collections.Counter()
+    _Ledger._created = collections.Counter()

@@ -15,12 +15,20 @@ autoscale_batch_size, bf16 autocast, channels-last) through each framework's
 public API; only the framework under the loop differs.
 
 Weak scaling: the per-GPU batch is fixed (default 128), global batch =
-128 x N. Two timed regions per run, each W warm-up + K timed steps bracketed by
-barrier + synchronize, CUDA events on the launching stream, max over ranks:
+128 x N. Two kinds of timed region, each W warm-up + EXACTLY K timed steps
+bracketed by barrier + synchronize, CUDA events on the launching stream, max
+over ranks:
 
   e2e    every step copies its batch host(pinned)->device and reads the loss
          back device->host (4 B, async into pinned memory);
   value  the same loop with the batch already resident on the device.
+
+K steps of a 2 ms step are 40 ms of device work -- too little to resolve a few
+per cent. So each kind of region is repeated as R separately bracketed
+windows of K steps until at least 0.5 s of device time has been measured
+(R is agreed across ranks after the first window); the reported numbers are
+totals over the windows (samples / time), `ms_per_step` their mean, and the
+per-window times are listed under "windows".
 """
 
 import argparse
@@ -47,8 +55,9 @@ def parse_args():
                     choices=["resnet18", "ncf", "bert"],
                     help="resnet18 = the headline config (default); ncf = "
                          "small-model/latency path; bert = BERT-base MLM "
-                         "bf16 (own arm only: the reference's BERT model "
-                         "needs torchtext)")
+                         "bf16 (reference arm: the same model in stock "
+                         "PyTorch modules, baseline/models/bert_plain.py, "
+                         "under the reference's AdaptiveDataParallel)")
     ap.add_argument("--device", default="cuda")
     ap.add_argument("--reducer", default="auto")
     ap.add_argument("--bucket-cap-mb", type=float, default=None,
@@ -60,6 +69,13 @@ def parse_args():
                          "or keep fp32 weights + autocast casts")
     ap.add_argument("--no-graph", action="store_true",
                     help="own arm: eager step instead of the CUDA-graph step")
+    ap.add_argument("--min-timed-ms", type=float, default=500.0,
+                    help="repeat the K-step window until this much device "
+                         "time has been measured per region (0 = one window)")
+    ap.add_argument("--max-windows", type=int, default=40)
+    ap.add_argument("--no-fp32-variant", action="store_true",
+                    help="own arm: skip the extra fp32-parameter / "
+                         "fp32-gradient measurement")
     return ap.parse_args()
 
 
@@ -255,7 +271,14 @@ class Workload(object):
                 from ncf_model import NCF
             return NCF(SyntheticNCF.USERS, SyntheticNCF.ITEMS, 32, 3, 0.0,
                        "NeuMF-end")
-        from adaptdl_b200.models import bert_base_mlm
+        if self.own:
+            from adaptdl_b200.models import bert_base_mlm
+        else:
+            # the reference's examples/BERT/model.py needs torchtext.nn and
+            # a pre-2.0 nn.TransformerEncoder: BASELINE.md section 2 defines
+            # the baseline as the same model (stock PyTorch modules) under
+            # the reference's unmodified AdaptiveDataParallel
+            from models.bert_plain import bert_base_mlm
         return bert_base_mlm(SyntheticMLM.NTOKEN, max_len=SyntheticMLM.SEQ)
 
     def optimizer(self, model):
@@ -286,6 +309,15 @@ class Workload(object):
         return lambda net, x, y: ce(
             net(x).view(-1, SyntheticMLM.NTOKEN), y.view(-1))
 
+    def l2_note(self):
+        if self.name == "ncf":
+            return ("latency-bound config: parameters + optimizer state "
+                    "(26 MB) fit the 126 MB L2, no flush between steps; a "
+                    "fresh batch every e2e step")
+        return ("working set > L2 (the step's activations + weights + "
+                "optimizer state exceed 126 MB) and a fresh batch every "
+                "e2e step")
+
     def describe(self):
         return {
             "resnet18": ("ResNet-18 (pytorch-cifar, 3x32x32, 10 classes, "
@@ -307,12 +339,15 @@ def warmup_steps(args):
     return max(args.warmup, 6)
 
 
-def build_program(args, adl, device, world, workload):
+def build_program(args, adl, device, world, workload, param_dtype=None,
+                  name=None):
     """The user program (identical for both arms)."""
     import torch
+    param_dtype = param_dtype or args.param_dtype
     local_bsz = args.local_bsz or workload.default_local_bsz
     global_bsz = local_bsz * world
-    total_steps = 2 * (warmup_steps(args) + args.steps) + 4
+    # one pass over the dataset = one timed window (W warm-up + K steps)
+    total_steps = warmup_steps(args) + args.steps + 2
     dataset = workload.dataset(global_bsz * total_steps,
                                pin=device.type == "cuda")
     loader = adl.AdaptiveDataLoader(dataset, batch_size=global_bsz,
@@ -324,11 +359,13 @@ def build_program(args, adl, device, world, workload):
     model = workload.model().to(device)
     if device.type == "cuda" and workload.channels_last:
         model = model.to(memory_format=torch.channels_last)
-    if workload.own and device.type == "cuda" and args.param_dtype == "bf16" \
+    if workload.own and device.type == "cuda" and param_dtype == "bf16" \
             and not args.no_graph:
         adl.mixed_precision_params(model)
     optimizer, scheduler = workload.optimizer(model)
     kwargs = {}
+    if name is not None:
+        kwargs["name"] = name
     if workload.own and args.reducer != "auto":
         kwargs["reducer"] = args.reducer
     if workload.own and args.bucket_cap_mb:
@@ -339,37 +376,31 @@ def build_program(args, adl, device, world, workload):
     return dataset, loader, net, optimizer, global_bsz
 
 
-def run(args, rank, world, local_rank):
+class Region(object):
+    """Timed windows of one kind ("e2e" or "device") for one program."""
+
+    def __init__(self, name):
+        self.name = name
+        self.ms = []            # device ms per window (this rank)
+        self.wall_ms = []
+        self.samples = 0        # local samples inside timed windows
+        self.target = None      # windows to run (agreed after the first)
+        self.launches = 0
+
+    def done(self):
+        return self.target is not None and len(self.ms) >= self.target
+
+
+def run_program(args, adl, device, rank, world, local_rank, workload,
+                param_dtype, regions, name=None, sample_clocks=True):
+    """Build the user program once and run the requested regions on it.
+    Returns a dict of per-region totals plus bookkeeping."""
+    import math
     import torch
     import torch.distributed as dist
-    own = args.impl == "own"
-    if args.device == "cuda" and not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (use --device cpu "
-                         "only for plumbing checks)")
-    device = torch.device("cuda", local_rank) if args.device == "cuda" \
-        else torch.device("cpu")
-    if device.type == "cuda":
-        torch.cuda.set_device(device)
-        torch.backends.cudnn.benchmark = True
-
-    if own:
-        sys.path.insert(0, ROOT)
-        import adaptdl_b200.torch as adl
-        from adaptdl_b200.ops import launch_count as ops_launch_count
-    else:
-        import numpy as np
-        if not hasattr(np, "int"):       # numpy >= 1.24 dropped the aliases
-            np.int, np.float = int, float
-        sys.path.insert(0, os.path.join(ROOT, "baseline", "shims"))
-        sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref"))
-        sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref",
-                                        "_ref_examples"))
-        import adaptdl.torch as adl
-
-    adl.init_process_group("nccl" if device.type == "cuda" else "gloo")
-    workload = Workload(args.workload, own)
+    own = workload.own
     dataset, loader, net, optimizer, global_bsz = build_program(
-        args, adl, device, world, workload)
+        args, adl, device, world, workload, param_dtype, name)
     loss_fn = workload.loss_fn()
     cl = device.type == "cuda" and workload.channels_last
     W, K = warmup_steps(args), args.steps
@@ -377,6 +408,8 @@ def run(args, rank, world, local_rank):
     loss_host = torch.zeros(W + K + 8, dtype=torch.float32)
     if device.type == "cuda":
         loss_host = loss_host.pin_memory()
+    if own:
+        from adaptdl_b200.ops import launch_count as ops_launch_count
 
     def barrier():
         if world > 1:
@@ -407,89 +440,180 @@ def run(args, rank, world, local_rank):
             loss_host[slot].copy_(loss.detach(), non_blocking=True)
         return loss
 
-    results = {}
-    launches = {}
+    def on_device(t, blocking):
+        t = t.to(device, non_blocking=not blocking)
+        if cl and t.dim() == 4:
+            t = t.contiguous(memory_format=torch.channels_last)
+        return t
+
+    def launches_now():
+        return net.reducer.launches + ops_launch_count() if own else 0
+
+    todo = [Region(r) for r in regions]
     clocks = None
     resident = None
     h2d_bytes = 0
-    for phase, epochs_until in (("e2e", 1), ("device", 2)):
-        for _ in adl.remaining_epochs_until(epochs_until):
-            t_wall = ev0 = ev1 = None
-            sampler = None
-            for step, batch in enumerate(loader):
-                if step == W:
-                    barrier()
-                    sampler = ClockSampler(
-                        rank == 0 and device.type == "cuda"
-                        and phase == "device", local_rank)
-                    if device.type == "cuda":
-                        ev0 = torch.cuda.Event(enable_timing=True)
-                        ev1 = torch.cuda.Event(enable_timing=True)
-                        ev0.record()
-                    t_wall = time.perf_counter()
-                    if own:
-                        launches[phase] = net.reducer.launches + \
-                            ops_launch_count()
-                if step == W + K:
-                    if device.type == "cuda":
-                        ev1.record()
-                        torch.cuda.synchronize()
-                        ms = ev0.elapsed_time(ev1)
-                    else:
-                        ms = (time.perf_counter() - t_wall) * 1e3
-                    wall_ms = (time.perf_counter() - t_wall) * 1e3
-                    barrier()
-                    results[phase] = (ms, wall_ms)
-                    if own:
-                        launches[phase] = net.reducer.launches + \
-                            ops_launch_count() - launches[phase]
-                    if sampler is not None:
-                        got = sampler.stop()
-                        clocks = got or clocks
-                    break
-                def on_device(t, blocking):
-                    t = t.to(device, non_blocking=not blocking)
-                    if cl and t.dim() == 4:
-                        t = t.contiguous(memory_format=torch.channels_last)
-                    return t
-                if phase == "e2e":
-                    h2d_bytes = sum(t.numel() * t.element_size()
-                                    for t in batch)
-                    if trainer is not None:
-                        # pinned host tensors go straight into the step
-                        # (copied H2D into the graph's static inputs)
-                        train_step(batch, step, read_back=True)
-                    else:
-                        train_step([on_device(t, False) for t in batch],
-                                   step, read_back=True)
+    epochs = adl.remaining_epochs_until(10 ** 6)
+    for _ in epochs:
+        region = next((r for r in todo if not r.done()), None)
+        if region is None:
+            epochs.close()       # leave the epoch loop cleanly
+            break
+        # the first window of a region gets the full warm-up (cuDNN
+        # autotuning, graph capture); later ones the recipe's minimum
+        w = W if not region.ms else 3
+        t_wall = ev0 = ev1 = None
+        sampler = None
+        n0 = 0
+        for step, batch in enumerate(loader):
+            if step == w:
+                barrier()
+                sampler = ClockSampler(
+                    sample_clocks and rank == 0 and device.type == "cuda"
+                    and region.name == "device", local_rank)
+                if device.type == "cuda":
+                    ev0 = torch.cuda.Event(enable_timing=True)
+                    ev1 = torch.cuda.Event(enable_timing=True)
+                    ev0.record()
+                t_wall = time.perf_counter()
+                n0 = launches_now()
+            if step == w + K:
+                if device.type == "cuda":
+                    ev1.record()
+                    torch.cuda.synchronize()
+                    ms = ev0.elapsed_time(ev1)
                 else:
-                    if resident is None:
-                        resident = [on_device(t, True) for t in batch]
-                    train_step(resident, step, read_back=False)
+                    ms = (time.perf_counter() - t_wall) * 1e3
+                wall_ms = (time.perf_counter() - t_wall) * 1e3
+                barrier()
+                region.ms.append(ms)
+                region.wall_ms.append(wall_ms)
+                region.launches += launches_now() - n0
+                if sampler is not None:
+                    got = sampler.stop()
+                    if got and (clocks is None
+                                or got["samples"] > clocks["samples"]):
+                        clocks = got
+                break
+            timed = step >= w
+            if region.name == "e2e":
+                h2d_bytes = sum(t.numel() * t.element_size() for t in batch)
+                if timed:
+                    region.samples += int(batch[0].shape[0])
+                if trainer is not None:
+                    # pinned host tensors go straight into the step
+                    # (copied H2D into the graph's static inputs)
+                    train_step(batch, step, read_back=True)
+                else:
+                    train_step([on_device(t, False) for t in batch],
+                               step, read_back=True)
+            else:
+                if resident is None or \
+                        resident[0].shape[0] != batch[0].shape[0]:
+                    resident = [on_device(t, True) for t in batch]
+                if timed:
+                    region.samples += int(resident[0].shape[0])
+                train_step(resident, step, read_back=False)
+        if region.target is None:
+            # agree on the number of windows (max over ranks of the first)
+            first = torch.tensor([region.ms[0]], dtype=torch.float64,
+                                 device=device)
+            if world > 1:
+                dist.all_reduce(first, op=dist.ReduceOp.MAX)
+            want = math.ceil(args.min_timed_ms / max(float(first), 1e-3))
+            region.target = max(1, min(args.max_windows, want))
     if device.type == "cuda":
         torch.cuda.synchronize()
     assert bool(torch.isfinite(loss_host[:W + K]).all()), "non-finite loss"
 
-    # max over ranks of the device time
-    times = torch.tensor([results["device"][0], results["e2e"][0],
-                          results["device"][1], results["e2e"][1]],
-                         dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, dev_wall, e2e_wall = times.tolist()
-    value = global_bsz * K / (dev_ms / 1e3)
-    e2e_value = global_bsz * K / (e2e_ms / 1e3)
+    out = {"global_bsz": global_bsz, "clocks": clocks,
+           "h2d_bytes": h2d_bytes, "net": net, "trainer": trainer}
+    for region in todo:
+        n = len(region.ms)
+        # per window: max over ranks; totals over windows
+        per_window = torch.tensor(region.ms + region.wall_ms,
+                                  dtype=torch.float64, device=device)
+        samples = torch.tensor([float(region.samples)], dtype=torch.float64,
+                               device=device)
+        if world > 1:
+            dist.all_reduce(per_window, op=dist.ReduceOp.MAX)
+            dist.all_reduce(samples, op=dist.ReduceOp.SUM)
+        per_window = per_window.tolist()
+        dev_ms, wall_ms = per_window[:n], per_window[n:]
+        out[region.name] = {
+            "windows_ms": dev_ms, "total_ms": sum(dev_ms),
+            "wall_total_ms": sum(wall_ms), "steps": n * K,
+            "samples": float(samples), "launches": region.launches,
+        }
+    return out
+
+
+def run(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    own = args.impl == "own"
+    if args.device == "cuda" and not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (use --device cpu "
+                         "only for plumbing checks)")
+    device = torch.device("cuda", local_rank) if args.device == "cuda" \
+        else torch.device("cpu")
+    if device.type == "cuda":
+        torch.cuda.set_device(device)
+        torch.backends.cudnn.benchmark = True
+
+    if own:
+        sys.path.insert(0, ROOT)
+        import adaptdl_b200.torch as adl
+    else:
+        import numpy as np
+        if not hasattr(np, "int"):       # numpy >= 1.24 dropped the aliases
+            np.int, np.float = int, float
+        sys.path.insert(0, os.path.join(ROOT, "baseline"))
+        sys.path.insert(0, os.path.join(ROOT, "baseline", "shims"))
+        sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref"))
+        sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref",
+                                        "_ref_examples"))
+        import adaptdl.torch as adl
+
+    adl.init_process_group("nccl" if device.type == "cuda" else "gloo")
+    workload = Workload(args.workload, own)
+    K = args.steps
+    bf16_params = (own and args.param_dtype == "bf16" and not args.no_graph
+                   and device.type == "cuda")
+    main = run_program(args, adl, device, rank, world, local_rank, workload,
+                       args.param_dtype, ("e2e", "device"))
+    net, trainer = main["net"], main["trainer"]
+    global_bsz = main["global_bsz"]
+    fp32_variant = None
+    if bf16_params and not args.no_fp32_variant:
+        # like-for-like precision on the gradient path: fp32 parameters and
+        # fp32 gradients (what the reference arm reduces), same engine
+        extra = run_program(args, adl, device, rank, world, local_rank,
+                            workload, "fp32", ("device",),
+                            name="fp32-variant", sample_clocks=False)
+        d = extra["device"]
+        fp32_variant = {
+            "param_dtype": "fp32", "grad_dtype": "fp32",
+            "value": d["samples"] / (d["total_ms"] / 1e3),
+            "ms_per_step": d["total_ms"] / d["steps"],
+            "steps_timed": d["steps"]}
+
+    dev, e2e = main["device"], main["e2e"]
+    value = dev["samples"] / (dev["total_ms"] / 1e3)
+    e2e_value = e2e["samples"] / (e2e["total_ms"] / 1e3)
     if rank == 0:
         line = {
             "metric": "samples/sec (device-timed, max over ranks)",
             "value": value, "unit": workload.unit, "n_gpus": world,
-            "steps": K, "warmup": args.warmup, "warmup_run": W,
-            "ms_per_step": dev_ms / K,
+            "steps": K, "warmup": args.warmup,
+            "warmup_run": warmup_steps(args),
+            "ms_per_step": dev["total_ms"] / dev["steps"],
             "higher_is_better": True, "scaling": "weak",
             "vs_baseline": (value / PUBLISHED_BASELINE
                             if PUBLISHED_BASELINE else None),
             "dtype": "bf16", "data": "synthetic",
             "impl": args.impl,
+            # the WORKLOAD (identical strings in both arms) ...
             "config": {
                 "workload": workload.name,
                 "model": workload.describe()[0],
@@ -500,38 +624,53 @@ def run(args, rank, world, local_rank):
                 "parallelism": "dp{}".format(world),
                 "optimizer": workload.describe()[1],
                 "adaptive": "autoscale_batch_size(max=32x, local 32..1024)",
-                "memory_format": ("channels_last, " if workload.channels_last
-                                  else "") + "bf16 autocast",
-                "params": ("bf16 weights, fp32 masters + fp32 optimizer "
-                           "state in the fused optimizer"
-                           if (own and args.param_dtype == "bf16"
-                               and not args.no_graph and device.type == "cuda")
-                           else "fp32 weights (autocast casts per step)"),
-                "l2": "working set > L2 (activations of a 128-sample batch "
-                      "exceed 126 MB) and a fresh batch every e2e step",
-                "step": ("eager" if (not own or args.no_graph)
-                         else "CUDA graph (whole step), device-resident "
-                              "GNS estimator, fused optimizer, fused "
-                              "BN+residual+ReLU kernels (resnet) / tcgen05 "
-                              "Linear+bias+GELU (bert)"),
+                "compute": ("channels_last, " if workload.channels_last
+                            else "") + "bf16 autocast",
+                "l2": workload.l2_note(),
             },
+            # ... and how THIS arm implements it
+            "param_dtype": ("bf16 weights + fp32 masters and fp32 optimizer "
+                            "state in the fused optimizer" if bf16_params
+                            else "fp32"),
+            "grad_dtype": "bf16" if bf16_params else "fp32",
+            "step_mode": ("cuda_graph" if (own and trainer is not None
+                                           and trainer.replays > 0)
+                          else "eager"),
+            "windows": {"per_window_steps": K,
+                        "device_ms": dev["windows_ms"],
+                        "e2e_ms": e2e["windows_ms"]},
+            "steps_timed": dev["steps"],
             "e2e": {"value": e2e_value, "unit": workload.unit,
-                    "ms_per_step": e2e_ms / K,
-                    "h2d_bytes_per_step": h2d_bytes,
+                    "ms_per_step": e2e["total_ms"] / e2e["steps"],
+                    "steps_timed": e2e["steps"],
+                    "h2d_bytes_per_step": main["h2d_bytes"],
                     "d2h_bytes_per_step": 4},
-            "wall_ms_per_step": {"device": dev_wall / K, "e2e": e2e_wall / K},
-            "gpu_launches": (launches.get("device") if own else None),
-            "gpu_launches_e2e": (launches.get("e2e") if own else None),
-            "clocks": clocks,
+            "wall_ms_per_step": {
+                "device": dev["wall_total_ms"] / dev["steps"],
+                "e2e": e2e["wall_total_ms"] / e2e["steps"]},
+            "gpu_launches": (round(dev["launches"] * K / dev["steps"])
+                             if own else None),
+            "gpu_launches_e2e": (round(e2e["launches"] * K / e2e["steps"])
+                                 if own else None),
+            "clocks": main["clocks"],
         }
+        if fp32_variant is not None:
+            line["fp32_grad_variant"] = fp32_variant
         if own:
-            line["reducer"] = type(net.reducer).__name__
+            red = net.reducer
+            line["reducer"] = type(red).__name__
             line["graph_replays"] = trainer.replays
             line["eager_steps"] = trainer.eager_steps
             line["device_engine"] = net.engine is not None
-            prov = getattr(net.reducer, "_provider", None)
+            prov = getattr(red, "_provider", None)
             line["symmetric_memory"] = getattr(prov, "name", None)
-            line["nvls_launches"] = getattr(net.reducer, "nvls_launches", 0)
+            line["buckets"] = getattr(red, "num_buckets", None)
+            line["nvls_launches"] = getattr(red, "nvls_launches", 0)
+            line["oneshot_launches"] = getattr(red, "oneshot_launches", 0)
+            from adaptdl_b200.torch import _metrics
+            timer = _metrics.device_timer()
+            line["device_timed_profile_steps"] = \
+                timer.booked if timer is not None else 0
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -542,12 +681,6 @@ def run(args, rank, world, local_rank):
 def main():
     args = parse_args()
     rank, world, local_rank = setup_env(args)
-    if args.impl == "reference" and args.workload == "bert":
-        if rank == 0:
-            print(json.dumps({"impl": "reference", "unavailable":
-                              "the reference's BERT example model imports "
-                              "torchtext.nn (not installable offline)"}))
-        return
     if args.impl == "reference":
         ref = os.path.join(ROOT, "baseline", "_ref", "adaptdl")
         if not os.path.isdir(ref):

@@ -1048,9 +1048,12 @@ int adl_sm_count(int dev) {
 // dtype: 0 = fp32, 1 = bf16, 2 = fp16
 // flavour: 0 = two-shot P2P, 1 = one-shot push (args->stage), 2 = NVLS (args->mc_buf)
 // fin: finalize arguments when args->fuse_fin (else ignored; may be nullptr)
+// threads: CTA size (a power of two, 64..ADL_THREADS); small CTAs leave registers and warp slots
+//          of their SM to the backward kernels running next to them
 int adl_allreduce_gns(const ReduceArgs* args, const FinalizeArgs* fin, int dtype, int flavour,
-                      int grid, void* stream) {
+                      int grid, int threads, void* stream) {
   if (g_device >= 0) ADL_CHECK(cudaSetDevice(g_device));
+  if (threads < 64 || threads > ADL_THREADS || (threads & (threads - 1))) return -8;
   const size_t smem = sizeof(double) * 2 * args->n_groups;
   if (smem > ADL_MAX_STAT_SMEM) return -4;
   if (dtype < 0 || dtype > 2) return -2;
@@ -1062,7 +1065,7 @@ int adl_allreduce_gns(const ReduceArgs* args, const FinalizeArgs* fin, int dtype
   cudaStream_t s = (cudaStream_t)stream;
   if (args->world > 1 && flavour == 2) {
     if (args->mc_buf == nullptr) return -7;
-#define CALL_NVLS(T, P) allreduce_nvls_kernel<T, P><<<grid, ADL_THREADS, smem, s>>>(*args, f)
+#define CALL_NVLS(T, P) allreduce_nvls_kernel<T, P><<<grid, threads, smem, s>>>(*args, f)
     ADL_DISPATCH_TP(dtype, pinv, CALL_NVLS);
 #undef CALL_NVLS
     return (int)cudaGetLastError();
@@ -1071,10 +1074,10 @@ int adl_allreduce_gns(const ReduceArgs* args, const FinalizeArgs* fin, int dtype
 #define CALL_OS(T, P)                                                                                  \
   do {                                                                                                 \
     switch (args->world) {                                                                             \
-      case 2: allreduce_oneshot_kernel<T, 2, P><<<grid, ADL_THREADS, smem, s>>>(*args, f); break;      \
-      case 4: allreduce_oneshot_kernel<T, 4, P><<<grid, ADL_THREADS, smem, s>>>(*args, f); break;      \
-      case 8: allreduce_oneshot_kernel<T, 8, P><<<grid, ADL_THREADS, smem, s>>>(*args, f); break;      \
-      default: allreduce_oneshot_kernel<T, 0, P><<<grid, ADL_THREADS, smem, s>>>(*args, f); break;     \
+      case 2: allreduce_oneshot_kernel<T, 2, P><<<grid, threads, smem, s>>>(*args, f); break;      \
+      case 4: allreduce_oneshot_kernel<T, 4, P><<<grid, threads, smem, s>>>(*args, f); break;      \
+      case 8: allreduce_oneshot_kernel<T, 8, P><<<grid, threads, smem, s>>>(*args, f); break;      \
+      default: allreduce_oneshot_kernel<T, 0, P><<<grid, threads, smem, s>>>(*args, f); break;     \
     }                                                                                                  \
   } while (0)
     ADL_DISPATCH_TP(dtype, pinv, CALL_OS);
@@ -1084,11 +1087,11 @@ int adl_allreduce_gns(const ReduceArgs* args, const FinalizeArgs* fin, int dtype
 #define CALL_AR(T, P)                                                                              \
   do {                                                                                             \
     switch (args->world) {                                                                         \
-      case 1: allreduce_gns_kernel<T, 1, P><<<grid, ADL_THREADS, smem, s>>>(*args, f); break;      \
-      case 2: allreduce_gns_kernel<T, 2, P><<<grid, ADL_THREADS, smem, s>>>(*args, f); break;      \
-      case 4: allreduce_gns_kernel<T, 4, P><<<grid, ADL_THREADS, smem, s>>>(*args, f); break;      \
-      case 8: allreduce_gns_kernel<T, 8, P><<<grid, ADL_THREADS, smem, s>>>(*args, f); break;      \
-      default: allreduce_gns_kernel<T, 0, P><<<grid, ADL_THREADS, smem, s>>>(*args, f); break;     \
+      case 1: allreduce_gns_kernel<T, 1, P><<<grid, threads, smem, s>>>(*args, f); break;      \
+      case 2: allreduce_gns_kernel<T, 2, P><<<grid, threads, smem, s>>>(*args, f); break;      \
+      case 4: allreduce_gns_kernel<T, 4, P><<<grid, threads, smem, s>>>(*args, f); break;      \
+      case 8: allreduce_gns_kernel<T, 8, P><<<grid, threads, smem, s>>>(*args, f); break;      \
+      default: allreduce_gns_kernel<T, 0, P><<<grid, threads, smem, s>>>(*args, f); break;     \
     }                                                                                              \
   } while (0)
   ADL_DISPATCH_TP(dtype, pinv, CALL_AR);

@@ -53,7 +53,7 @@ setuptools.setup(
                                                "adaptdl_b200.*"]),
     package_data={"adaptdl_b200._native": ["*.so"]},
     python_requires=">=3.9",
-    install_requires=["numpy", "scipy", "torch", "requests"],
+    install_requires=["numpy", "scipy", "torch>=2.1", "requests"],
     extras_require={
         "sched": ["aiohttp", "prometheus_client", "kubernetes_asyncio",
                   "pyyaml"],

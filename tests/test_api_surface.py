@@ -108,3 +108,50 @@ def test_leading_parameters(owner):
               if p != "self"]
     want = SIGNATURES[owner]
     assert params[:len(want)] == want, (owner, params)
+
+
+def test_reference_import_names_resolve_to_this_framework():
+    """``import adaptdl`` / ``adaptdl.torch`` / ``adaptdl_sched`` ... are the
+    same module objects as their ``adaptdl_b200`` counterparts
+    (adaptdl_b200/compat.py), so module state is shared."""
+    import adaptdl
+    import adaptdl.torch as adl
+    import adaptdl.torch.data as data_alias
+    import adaptdl_b200
+    import adaptdl_b200.torch
+    import adaptdl_b200.torch.data
+    assert adaptdl is adaptdl_b200
+    assert adl is adaptdl_b200.torch
+    assert data_alias is adaptdl_b200.torch.data
+    from adaptdl.torch._metrics import profile_step_start  # noqa: F401
+    import adaptdl.checkpoint
+    import adaptdl.collective
+    import adaptdl.env  # noqa: F401
+    import adaptdl_cli  # noqa: F401
+    import adaptdl_ray.tune  # noqa: F401
+    import adaptdl_sched.policy.pollux as pollux
+    import adaptdl_b200.sched.policy.pollux as pollux_real
+    assert pollux is pollux_real
+    assert adaptdl.checkpoint.State is adaptdl_b200.checkpoint.State
+    assert adaptdl.collective is adaptdl_b200.collective
+
+
+def test_unmodified_reference_example_runs_on_the_alias(tmp_path):
+    """The reference's own examples/linear_regression/main.py, byte for
+    byte, trains on this framework (CPU, one replica)."""
+    import os
+    import subprocess
+    import sys
+    script = "/root/reference/examples/linear_regression/main.py"
+    if not os.path.exists(script):
+        pytest.skip("reference checkout not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = {k: v for k, v in os.environ.items()
+           if not k.startswith("ADAPTDL_")}
+    env["PYTHONPATH"] = root
+    proc = subprocess.run([sys.executable, script, "--epochs", "2"],
+                          env=env, cwd=str(tmp_path), timeout=300,
+                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                          text=True)
+    assert proc.returncode == 0, proc.stdout[-3000:]
+    assert "Loss" in proc.stdout

@@ -208,6 +208,8 @@ def test_multi_gpu_fused_allreduce(provider):
     env["ADAPTDL_B200_SYMM"] = provider.split("-")[0]
     if provider == "native-nvls":
         env["ADAPTDL_B200_NVLS_MIN_MB"] = "0"
+        env["ADAPTDL_B200_NVLS_MIN_WORLD"] = "2"
+        env["ADAPTDL_B200_ONESHOT_KB"] = "0"     # else it takes every bucket
         env["ADAPTDL_EXPECT_NVLS"] = "1"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
            "--nproc-per-node", str(n), "--master-addr", "127.0.0.1",

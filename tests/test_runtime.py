@@ -333,3 +333,34 @@ def test_resaving_a_generation_never_leaves_the_disk_without_a_checkpoint(
     checkpoint.save_all_states()
     assert sorted(os.listdir(tmp_path)) == ["checkpoint-1"]
     checkpoint._reset_registry_for_tests()
+
+
+def test_reducer_many_large_async_allreduces_do_not_deadlock():
+    """Several outstanding multi-megabyte all-reduces per replica (a
+    blocking server wedges here: it is stuck sending result k to a client
+    that is itself stuck sending frame k+1)."""
+    import threading
+    import numpy as np
+    from adaptdl_b200.reducer import Reducer
+    from adaptdl_b200.utils.testing import pick_unused_port
+    port = pick_unused_port()
+    replicas, rounds, n = 2, 3, 3 * 1024 * 1024      # ~24 MB float64 each
+    out = {}
+
+    def worker(rank):
+        red = Reducer(rank, replicas, "127.0.0.1", port)
+        futures = [red.allreduce_async(np.full(n, float(rank + 1 + k)))
+                   for k in range(rounds)]
+        out[rank] = [float(f.result()[0]) for f in futures]
+        red.broadcast(None)
+        red.close()
+    threads = [threading.Thread(target=worker, args=(r,), daemon=True)
+               for r in range(replicas)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(120)
+    assert not any(t.is_alive() for t in threads), "control plane deadlocked"
+    want = [float(sum(r + 1 + k for r in range(replicas)))
+            for k in range(rounds)]
+    assert out[0] == want and out[1] == want

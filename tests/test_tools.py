@@ -110,3 +110,41 @@ def test_conv_bench_plumbing_on_cpu():
             for spec in bench.RESNET18_CONVS[:3]]
     assert {"fprop_us", "dgrad_us", "wgrad_us"} <= set(rows[0])
     assert all(r["fprop_us"] > 0 and r["gflop"] > 0 for r in rows)
+
+
+def test_bench_contract_two_ranks_on_cpu(tmp_path):
+    """bench.py's driver contract on the CPU plumbing path (gloo, 2 ranks):
+    one JSON line from rank 0 with the keys the driver reads, K-step windows
+    repeated until the requested device time is covered."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = {k: v for k, v in os.environ.items()
+           if not k.startswith("ADAPTDL_")}
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+           "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29733", os.path.join(root, "bench.py"),
+           "--gpus", "2", "--steps", "2", "--warmup", "3", "--device", "cpu",
+           "--workload", "ncf", "--min-timed-ms", "1e9", "--max-windows",
+           "2"]
+    proc = subprocess.run(cmd, env=env, stdout=subprocess.PIPE,
+                          stderr=subprocess.PIPE, text=True, timeout=600,
+                          cwd=str(tmp_path))
+    assert proc.returncode == 0, proc.stderr[-3000:]
+    lines = [ln for ln in proc.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    out = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup",
+                "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "e2e", "gpu_launches", "clocks",
+                "param_dtype", "grad_dtype", "step_mode"):
+        assert key in out, key
+    assert out["n_gpus"] == 2 and out["steps"] == 2
+    assert out["steps_timed"] == 4 and len(out["windows"]["device_ms"]) == 2
+    assert out["config"]["global_batch"] == 512
+    assert out["value"] > 0 and out["e2e"]["value"] > 0
+    assert set(out["config"]) == {"workload", "model", "global_batch",
+                                  "local_batch", "seq_len", "parallelism",
+                                  "optimizer", "adaptive", "compute", "l2"}

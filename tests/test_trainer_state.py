@@ -570,3 +570,56 @@ def test_preemption_beat_relearns_its_pace_in_every_loop():
         beat.beat()
         assert beat.interval == 1
     return 0
+
+
+def test_accumulator_checkpoint_layout_and_delta_protocol(tmp_path):
+    """The file an Accumulator writes is the reference's
+    ``(history: {epoch: [snapshot...]}, results)`` pickle; in-loop sessions
+    take no replay slot; deltas are immutable values."""
+    import io
+    import pickle
+    from adaptdl_b200 import collective
+    from adaptdl_b200.torch import accumulator as acc_mod
+    collective.initialize()
+    try:
+        acc_mod._reset_for_tests()
+        accum = acc_mod.Accumulator(seen=0)
+        accum["seen"] += 2
+        accum["loss"] += 1.5
+        accum["loss"] -= 0.5
+        delta = accum["loss"]
+        assert (delta + 1).amount == 1 and delta.amount == 0   # immutable
+        with pytest.raises(AttributeError):
+            delta.amount = 7
+        with pytest.raises(TypeError):
+            accum["loss"] = accum["seen"] + accum["loss"]
+        with accum.synchronized():
+            assert dict(accum) == {"seen": 2, "loss": 1.0}
+            with accum.synchronized():        # re-entrant
+                accum["extra"] = "set inside"
+        accum["seen"] += 1
+        with accum.synchronized():
+            assert accum["seen"] == 3 and accum["extra"] == "set inside"
+        buf = io.BytesIO()
+        accum._ledger.save(buf)
+        history, results = pickle.loads(buf.getvalue())
+        assert results == {"seen": 3, "loss": 1.0, "extra": "set inside"}
+        assert list(history) == [None] and len(history[None]) == 2
+        assert history[None][0]["seen"] == 2 and history[None][1]["seen"] == 3
+        # a fresh accumulator loading that file replays both positions
+        accum._ledger.unregister()
+        acc_mod._reset_for_tests()
+        again = acc_mod.Accumulator()
+        again._ledger.load(io.BytesIO(buf.getvalue()))
+        again["seen"] += 100                  # re-executed work: dropped
+        with again.synchronized():
+            assert again["seen"] == 2
+        with again.synchronized():
+            assert again["seen"] == 3
+        again["seen"] += 1                    # new work after the replay
+        with again.synchronized():
+            assert again["seen"] == 4
+        again._ledger.unregister()
+    finally:
+        collective.teardown()
+        acc_mod._reset_for_tests()

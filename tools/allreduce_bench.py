@@ -11,6 +11,9 @@ alone, (c) what the reference does around it for the same result (all-reduce
 
 Two timings per flavour:
 
+Everything is timed as CUDA-graph replays (no host launch cost), the way
+the kernels run inside a captured training step.
+
 ``isolated``   one bucket = one optimizer step: the bucket kernel carries the
                fused finalize (statistics exchange + the step's closing peer
                barrier), i.e. a COMPLETE all-reduce whose result is visible on
@@ -55,6 +58,26 @@ def timed(fn, iters, warmup=5, stream=None):
     return float(ms)
 
 
+def graphed(fn, warmup=3):
+    """``fn`` (kernels on the reducer's comm stream, joined to the current
+    stream by events) captured into a CUDA graph: replaying it costs no
+    Python / launch-API time per kernel, which at these sizes is most of an
+    eager launch."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(warmup):
+            fn()
+        side.synchronize()
+        dist.barrier()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            fn()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    return graph
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=None)
@@ -97,6 +120,7 @@ def main():
         if world > 2 or args.sweep:
             configs += [("nvls%d" % c, {"ADAPTDL_B200_NVLS_MIN_MB": "0",
                                         "ADAPTDL_B200_ONESHOT_KB": "0",
+                                        "ADAPTDL_B200_NVLS_MIN_WORLD": "2",
                                         "ADAPTDL_B200_NVLS_CTAS": str(c)})
                         for c in nvls_grids]
         picked = None
@@ -129,9 +153,10 @@ def main():
                 for _ in range(8):
                     red._reduce(arena, bucket, 1.0 / world, True)
                 isolated()
-            t_iso = timed(isolated, iters, stream=red._comm) * 1e3
-            t_pipe = timed(pipelined, max(iters // 8, 5),
-                           stream=red._comm) * 1e3 / 9
+            g_iso, g_pipe = graphed(isolated), graphed(pipelined)
+            t_iso = timed(g_iso.replay, iters) * 1e3
+            t_pipe = timed(g_pipe.replay, max(iters // 8, 5)) * 1e3 / 9
+            del g_iso, g_pipe
             variants[tag] = {"flavour": flavour, "isolated_us": t_iso,
                              "pipelined_us": t_pipe}
             if tag == "auto":

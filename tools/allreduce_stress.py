@@ -44,6 +44,7 @@ def main():
         # every bucket the one-shot flavour does not take goes through the
         # switch
         os.environ["ADAPTDL_B200_NVLS_MIN_MB"] = "0.05"
+        os.environ["ADAPTDL_B200_NVLS_MIN_WORLD"] = "2"
     from adaptdl_b200.parallel.reducer_cuda import CudaGradReducer
     # ONE reducer over parameters of very different sizes with a small bucket
     # cap: every step launches a chain of bucket kernels of all flavours
