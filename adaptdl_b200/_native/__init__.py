@@ -276,7 +276,7 @@ def _declare(lib):
                                       c.POINTER(FinalizeArgs), c.c_int,
                                       c.c_int, c.c_int, c.c_int, c.c_void_p]
     lib.adl_local.argtypes = [c.POINTER(LocalArgs), c.POINTER(FinalizeArgs),
-                              c.c_int, c.c_int, c.c_int, c.c_void_p]
+                              c.c_int, c.c_int, c.c_int, c.c_int, c.c_void_p]
     lib.adl_finalize_stats.argtypes = [c.POINTER(FinalizeArgs), c.c_void_p]
     lib.adl_stamp.argtypes = [c.c_void_p, c.c_void_p]
     lib.adl_step_mark.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p]

@@ -28,6 +28,11 @@ def set_exit_flag(value=True):
 
 def _on_signal(signum, frame):
     set_exit_flag(True)
+    try:
+        from adaptdl_b200.utils import rescale_trace
+        rescale_trace.mark("signal_received")
+    except Exception:  # noqa: BLE001 - never fail inside a signal handler
+        pass
     if signum == signal.SIGINT:
         LOG.info("SIGINT: finishing this step then checkpointing; "
                  "send it again to force exit")

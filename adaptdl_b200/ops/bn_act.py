@@ -119,21 +119,31 @@ def _fused_max_grid(device):
     got = _FUSED.get(device.index)
     if got is not None:
         return got
-    if os.environ.get("ADAPTDL_B200_BN_SINGLE", "1") == "0":
+    # default OFF: measured on ResNet-18 (profiles/r2_n2), the first version
+    # of the single-launch kernel lost to the two-kernel path (2.19 vs 2.07
+    # ms/step), and so did programmatic dependent launch between the two
+    # kernels (2.09 vs 2.07)
+    if os.environ.get("ADAPTDL_B200_BN_SINGLE", "0") != "1":
         _FUSED[device.index] = 0
+        _config_pdl()
         return 0
     if torch.cuda.is_current_stream_capturing():
         return 0                       # decide outside of a capture
     from adaptdl_b200 import _native
     lib = _native.load()
     lib.adl_set_device(device.index)
-    lib.adl_bn_config(0 if os.environ.get("ADAPTDL_B200_BN_PDL", "1") == "0"
-                      else 1)
+    _config_pdl()
     limit = max(int(lib.adl_bn_fused_max_grid(device.index)), 0)
     _FUSED[device.index] = limit
     if limit and not _probe_capturable(device):
         _FUSED[device.index] = limit = 0
     return limit
+
+
+def _config_pdl():
+    from adaptdl_b200 import _native
+    _native.load().adl_bn_config(
+        1 if os.environ.get("ADAPTDL_B200_BN_PDL", "0") == "1" else 0)
 
 
 def _probe_capturable(device):
@@ -171,9 +181,13 @@ def _fused_grid(device, m, c, vec, unroll):
     limit = _fused_max_grid(device)
     if not limit or c > _FUSED_MAX_C:
         return 0
-    rpi = 256 // (c // vec)
+    tpr = c // vec
+    q = 2 * c // 4                         # float4 columns of the fold
+    if tpr > 512 or 512 % tpr or q > 512 or 512 % q:
+        return 0
+    rpi = 512 // tpr
     need = (m + rpi * unroll - 1) // (rpi * unroll)
-    by_fold = max(8, (160 * 256) // (2 * c))
+    by_fold = max(4, 8192 // c)            # one round trip of loads per thread
     return max(1, min(need, limit, by_fold))
 
 

@@ -203,6 +203,8 @@ class CudaGradReducer(GradReducer):
         # are bandwidth-bound and keep 512
         self._reduce_threads = int(os.environ.get(
             "ADAPTDL_B200_REDUCE_THREADS", "256"))
+        self._local_ctas = max(1, int(os.environ.get(
+            "ADAPTDL_B200_LOCAL_CTAS", "64")))
         super()._attach()
         for i, arena in enumerate(self.arenas):
             self._build_seg_tables(i, arena)
@@ -252,8 +254,21 @@ class CudaGradReducer(GradReducer):
         self._comm.wait_event(ev)
 
     def _local_grid(self, n_vec):
+        """Grid of a kernel that has the GPU to itself (stand-alone use)."""
         return max(1, min(2 * self._sm_count,
                           (n_vec + 2 * 512 - 1) // (2 * 512)))
+
+    def _thin_grid(self, n_vec):
+        """``(CTAs, threads)`` of a local pass that runs NEXT TO backward on
+        the high-priority comm stream: a fraction of the SMs' thread and
+        register budget (a full-width grid stalls the backward kernels for
+        the ~10 us of launch + latency every such kernel has, measured as
+        +10-15 us of step time per bucket), four vectors per tensor in
+        flight per thread for bandwidth."""
+        threads = self._reduce_threads
+        per_cta = threads * 8
+        return max(1, min(self._local_ctas,
+                          (n_vec + per_cta - 1) // per_cta)), threads
 
     def _local_args(self, arena, bucket, mode):
         ai = self._arena_index(arena)
@@ -354,10 +369,11 @@ class CudaGradReducer(GradReducer):
             args.ticket = self._ticket.data_ptr()
             self._fin_fused = True
         self._order_after_compute()
+        grid, threads = self._thin_grid(n_vec)
         check(self._lib.adl_local(
             ctypes.byref(args), ctypes.byref(fin) if fin is not None else None,
-            mode, _DTYPE_CODE[arena.dtype],
-            self._local_grid(n_vec), self._comm.cuda_stream), "adl_local")
+            mode, _DTYPE_CODE[arena.dtype], grid, threads,
+            self._comm.cuda_stream), "adl_local")
         self.launches += 1
 
     def _fold_acc(self, arena, bucket):

@@ -304,6 +304,10 @@ def main(argv=None):
                              "seconds (checkpoint + exit)")
     parser.add_argument("--report", default=None,
                         help="write the event log (JSON) here")
+    parser.add_argument("--trace-rescale", action="store_true",
+                        help="have every replica record its life-cycle "
+                             "events (utils/rescale_trace.py) and add the "
+                             "per-generation phase breakdown to the report")
     parser.add_argument("script", nargs=argparse.REMAINDER)
     args = parser.parse_args(argv)
     logging.basicConfig(level=logging.INFO)
@@ -319,14 +323,34 @@ def main(argv=None):
     command = args.script
     if command[0].endswith(".py"):
         command = [sys.executable] + command
-    job = LocalElasticJob(command, gpus, args.checkpoint_dir)
+    extra_env = {}
+    trace_dir = None
+    if args.trace_rescale:
+        trace_dir = tempfile.mkdtemp(prefix="adaptdl-b200-rescale-trace-")
+        extra_env["ADAPTDL_B200_RESCALE_TRACE"] = trace_dir
+    job = LocalElasticJob(command, gpus, args.checkpoint_dir, env=extra_env)
     schedule = [int(x) for x in args.schedule.split(",") if x]
     state = job.run(schedule, args.interval, args.adaptive,
                     stop_after=args.stop_after)
     if args.report:
+        rows = [{"t": t, "event": what, **detail}
+                for t, what, detail in job.events]
+        if trace_dir:
+            from adaptdl_b200.utils import rescale_trace
+            traced = rescale_trace.collect(trace_dir)
+            rows.append({"event": "rescale_phases_seconds",
+                         "by_generation": rescale_trace.summarize(traced)})
+            # launcher-side view: SIGTERM sent -> every replica exited ->
+            # next generation's first optimizer step
+            first_step = {}
+            for row in traced:
+                if row["event"] == "first_step_done":
+                    gen = row["generation"]
+                    first_step[gen] = max(first_step.get(gen, 0), row["t"])
+            rows.append({"event": "first_step_done_at",
+                         "by_generation": first_step})
         with open(args.report, "w") as f:
-            json.dump([{"t": t, "event": what, **detail}
-                       for t, what, detail in job.events], f, indent=1)
+            json.dump(rows, f, indent=1)
     return 0 if state in ("finished", "stopped") else 1
 
 

@@ -22,6 +22,10 @@ from adaptdl_b200 import _signal  # noqa: F401  (isort: skip)
 
 import torch.distributed
 
+from adaptdl_b200.utils import rescale_trace as _rescale_trace
+
+_rescale_trace.mark("interpreter_up")        # python + torch are loaded
+
 from adaptdl_b200 import __version__, collective, env
 from adaptdl_b200.utils import parse_version, pick_unused_port
 from .epoch import current_epoch, finished_epochs, remaining_epochs_until
@@ -152,3 +156,5 @@ def init_process_group(backend, init_method=None, world_size=None,
     os.environ.pop("TORCHELASTIC_USE_AGENT_STORE", None)
     torch.distributed.init_process_group(backend, store_url)
     LOG.info("torch.distributed initialized")
+    from adaptdl_b200.utils import rescale_trace
+    rescale_trace.mark("process_group_ready")

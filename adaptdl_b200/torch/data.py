@@ -107,7 +107,11 @@ class _PreemptionBeat(object):
         if self.pending is not None:
             flagged, agreed = self.pending.result()
             if flagged:
+                from adaptdl_b200.utils import rescale_trace
+                rescale_trace.mark("exit_consensus")
                 checkpoint.save_all_states()
+                rescale_trace.mark("checkpoint_written")
+                rescale_trace.mark("exiting")
                 sys.exit(EXIT_CODE_PREEMPTED)
             self.interval = 1 if self.relearn else agreed
         self.relearn = False

@@ -128,6 +128,8 @@ class AdaptiveDataParallel(torch.nn.Module):
             # fresh start, or a checkpoint written without the engine: the
             # masters are the (broadcast / loaded) 16-bit weights
             self._engine.resync_master()
+        from adaptdl_b200.utils import rescale_trace
+        rescale_trace.mark("wrapper_ready")
 
     # ------------------------------------------------------------------
 

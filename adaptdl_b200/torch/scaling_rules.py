@@ -36,6 +36,19 @@ __all__ = ["ScalingRuleBase", "AdaScale", "AdamScale", "LinearScale",
            "SqrtScale", "LEGWScale"]
 
 
+def _mark_first_step():
+    """Rescale trace: the job is training again (first optimizer step of
+    this process)."""
+    global _mark_first_step
+    from adaptdl_b200.utils import rescale_trace
+    if rescale_trace.enabled():
+        import torch
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        rescale_trace.mark("first_step_done")
+    _mark_first_step = lambda: None      # noqa: E731 - one-shot
+
+
 class _HookedOptimizerMethods(object):
     """Re-routes ``optimizer.step`` and ``optimizer.zero_grad`` of ONE
     optimizer instance to a scaling rule while keeping the originals
@@ -132,6 +145,7 @@ class ScalingRuleBase(object):
                              "AdaptiveDataParallel attached")
         if not adp.require_backward_grad_sync:
             return None
+        _mark_first_step()
         engine = vars(adp).get("_engine")
         if engine is not None and engine.enabled and not (args or kwargs):
             # factors and progress were produced on the device; one fused

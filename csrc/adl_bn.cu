@@ -283,7 +283,7 @@ bn_apply_kernel(const BnArgs a) {
 // The apply kernel is a programmatic dependent of the reduce kernel (PDL): its launch latency
 // (2-3 us, 40 kernel pairs per ResNet-18 step) hides behind the reduction; under stream capture
 // the attribute becomes a programmatic edge of the CUDA graph.
-static int g_bn_pdl = 1;
+static int g_bn_pdl = 0;
 
 template <typename T, bool BWD>
 int launch_pair(const BnArgs& a, dim3 grid, int grid_apply, cudaStream_t s) {
@@ -330,6 +330,7 @@ int run(const BnArgs& a, int backward, int grid_y, int grid_apply, cudaStream_t 
 // runtime, also under stream capture); the barrier is two self-resetting counters.
 // ---------------------------------------------------------------------------
 constexpr int BN_FUSED_MAX_C = 1024;
+constexpr int BN_FUSED_THREADS = 512;               // one CTA per SM: 512 threads of loads in flight
 
 __device__ __forceinline__ void bn_grid_barrier(int* ctr, int n_cta) {
   __syncthreads();
@@ -347,15 +348,16 @@ __device__ __forceinline__ void bn_grid_barrier(int* ctr, int n_cta) {
 }
 
 template <typename T, bool BWD>
-__global__ void __launch_bounds__(BN_THREADS)
+__global__ void __launch_bounds__(BN_FUSED_THREADS, 1)
 bn_fused_kernel(const BnArgs a) {
   constexpr int V = VecTraits<T>::N;
   constexpr int U = BnUnroll<BWD>::U;
-  __shared__ float red[2 * BN_THREADS * 8];       // [2][rows_per_iter][C] (rpi * C == 256 * V)
+  constexpr int NT = BN_FUSED_THREADS;
+  __shared__ float red[2 * NT * 8];               // [2][rows_per_iter][C] (rpi * C == NT * V); fold scratch
   __shared__ float ks[2 * BN_FUSED_MAX_C];        // forward (scale, shift); backward (s1/M, s2/M)
   const int C = a.C;
   const int tpr = C / V;                          // threads per row
-  const int rpi = BN_THREADS / tpr;               // rows per iteration
+  const int rpi = NT / tpr;                       // rows per iteration
   const int my_c = (threadIdx.x % tpr) * V;
   const int my_r = threadIdx.x / tpr;
   const int G = gridDim.x;
@@ -416,7 +418,7 @@ bn_fused_kernel(const BnArgs a) {
   }
   __syncthreads();
   float* mine = a.partial + (size_t)blockIdx.x * 2 * C;
-  for (int c = threadIdx.x; c < 2 * C; c += BN_THREADS) {
+  for (int c = threadIdx.x; c < 2 * C; c += NT) {
     const float* src = (c < C) ? (r0s + c) : (r1s + (c - C));
     float t = 0.f;
     for (int r = 0; r < rpi; ++r) t += src[r * C];
@@ -424,22 +426,41 @@ bn_fused_kernel(const BnArgs a) {
   }
   bn_grid_barrier(a.counters, G);
 
-  // ---- fold all CTAs' partials (fixed order: identical in every CTA, deterministic) ----
-  for (int c = threadIdx.x; c < 2 * C; c += BN_THREADS) {
-    const float* col = a.partial + c;
-    float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
-    int g = 0;
-    for (; g + 3 < G; g += 4) {
-      t0 += __ldcg(col + (size_t)g * 2 * C);
-      t1 += __ldcg(col + (size_t)(g + 1) * 2 * C);
-      t2 += __ldcg(col + (size_t)(g + 2) * 2 * C);
-      t3 += __ldcg(col + (size_t)(g + 3) * 2 * C);
+  // ---- fold all CTAs' partials: identical (fixed order) in every CTA, deterministic.
+  // The [G][2C] matrix is read as float4 columns by all 512 threads, eight rows in flight per
+  // thread (one L2 round trip for G * C <= 8192), then combined through shared memory.
+  {
+    const int q = 2 * C / 4;                      // float4 columns
+    const int L = NT / q > 0 ? NT / q : 1;        // row lanes
+    float* fold = red;                            // [L][2C]
+    for (int qi0 = 0; qi0 < q; qi0 += NT) {       // q > NT only for C > 1024 (never: C <= 1024)
+      const int qi = qi0 + (int)(threadIdx.x % q);
+      const int li = threadIdx.x / q;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (li < L && qi < q) {
+        const float4* base = reinterpret_cast<const float4*>(a.partial) + qi;
+        for (int g0 = li; g0 < G; g0 += 8 * L) {
+          float4 t[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int g = g0 + j * L;
+            t[j] = (g < G) ? __ldcg(base + (size_t)g * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { acc.x += t[j].x; acc.y += t[j].y; acc.z += t[j].z; acc.w += t[j].w; }
+        }
+        reinterpret_cast<float4*>(fold)[li * q + qi] = acc;
+      }
     }
-    for (; g < G; ++g) t0 += __ldcg(col + (size_t)g * 2 * C);
-    ks[c] = (float)(((double)t0 + (double)t1 + (double)t2 + (double)t3) / (double)a.M);
+    __syncthreads();
+    for (int c = threadIdx.x; c < 2 * C; c += NT) {
+      double t = 0.0;
+      for (int l = 0; l < L; ++l) t += (double)fold[l * 2 * C + c];
+      ks[c] = (float)(t / (double)a.M);
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  for (int c = threadIdx.x; c < C; c += BN_THREADS) {
+  for (int c = threadIdx.x; c < C; c += NT) {
     const float m0 = ks[c], m1 = ks[C + c];
     if (!BWD) {
       const float var = fmaxf(m1 - m0 * m0, 0.f);
@@ -454,6 +475,7 @@ bn_fused_kernel(const BnArgs a) {
           a.running_var[c] = (1.f - a.momentum) * a.running_var[c] + a.momentum * unbiased;
         }
       }
+      // (scale, shift) replace (mean, mean-of-squares): same thread, same slots
       ks[c] = scale;
       ks[C + c] = a.beta[c] - m0 * scale;
     } else if (blockIdx.x == 0) {
@@ -528,7 +550,7 @@ int launch_fused(const BnArgs& a, int grid, cudaStream_t s) {
   BnArgs copy = a;
   void* params[1] = {&copy};
   cudaError_t e = cudaLaunchCooperativeKernel(
-      reinterpret_cast<const void*>(&bn_fused_kernel<T, BWD>), dim3(grid), dim3(BN_THREADS),
+      reinterpret_cast<const void*>(&bn_fused_kernel<T, BWD>), dim3(grid), dim3(BN_FUSED_THREADS),
       params, 0, s);
   if (e != cudaSuccess) return (int)e;
   return (int)cudaGetLastError();
@@ -556,8 +578,8 @@ int adl_bn_fused_max_grid(int dev) {
   if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess || !coop) return 0;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bn_fused_kernel<__nv_bfloat16, true>,
-                                                    BN_THREADS, 0) != cudaSuccess) return 0;
-  return per_sm > 0 ? sms * (per_sm > 2 ? 2 : per_sm) : 0;   // at most two CTAs per SM are ever used
+                                                    BN_FUSED_THREADS, 0) != cudaSuccess) return 0;
+  return per_sm > 0 ? sms : 0;      // one CTA per SM
 }
 
 // Single cooperative launch per direction. `grid` CTAs (<= adl_bn_fused_max_grid), a.partial holds
@@ -568,8 +590,9 @@ int adl_bn_act_fused(const void* args, int dtype, int backward, int grid, void* 
   const int v = dtype == 0 ? 4 : 8;
   if (a->C % v != 0 || a->C > BN_FUSED_MAX_C) return -20;
   const int tpr = a->C / v;
-  if (tpr > BN_THREADS || BN_THREADS % tpr != 0) return -21;
+  if (tpr > BN_FUSED_THREADS || BN_FUSED_THREADS % tpr != 0) return -21;
   if (grid <= 0 || a->n_partial != grid) return -22;
+  if ((2 * a->C / 4) > BN_FUSED_THREADS || BN_FUSED_THREADS % (2 * a->C / 4) != 0) return -25;
   cudaStream_t s = (cudaStream_t)stream;
   switch (dtype) {
     case 0: return run_fused<float>(*a, backward, grid, s);

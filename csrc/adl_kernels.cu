@@ -167,11 +167,43 @@ struct Precond {
   }
 };
 
+// The bucket's segment table, staged in shared memory once per CTA (one coalesced round trip)
+// when it fits: the per-thread binary search and cursor advance then cost shared-memory
+// latency instead of a chain of dependent L2 round trips at the start of every kernel.
+#define ADL_SEG_SMEM 512
+struct SegCache {
+  const int* end;
+  const int* group;
+  int n_seg;
+  __device__ __forceinline__ void load(const SegTable& t, int* s_end, int* s_group) {
+    n_seg = t.n_seg;
+    if (t.n_seg <= ADL_SEG_SMEM) {
+      for (int i = threadIdx.x; i < t.n_seg; i += blockDim.x) {
+        s_end[i] = __ldg(t.seg_end + i);
+        s_group[i] = __ldg(t.seg_group + i);
+      }
+      end = s_end;
+      group = s_group;
+    } else {
+      end = t.seg_end;
+      group = t.seg_group;
+    }
+    __syncthreads();
+  }
+};
+
 // statistics group of bucket-relative vector v (monotone cursor per lane)
-__device__ __forceinline__ int group_of(const SegTable& segs, int v, int& cur) {
-  if (cur < 0) cur = seg_find(segs, v);
-  while (__ldg(segs.seg_end + cur) <= v) ++cur;
-  return __ldg(segs.seg_group + cur);
+__device__ __forceinline__ int group_of(const SegCache& segs, int v, int& cur) {
+  if (cur < 0) {
+    int lo = 0, hi = segs.n_seg - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (segs.end[mid] > v) hi = mid; else lo = mid + 1;
+    }
+    cur = lo;
+  }
+  while (segs.end[cur] <= v) ++cur;
+  return segs.group[cur];
 }
 
 // ---------------------------------------------------------------------------
@@ -230,30 +262,66 @@ struct FinalizeArgs {
   const float* amp_scale;          // device: AMP loss scale the gradients carry (or nullptr)
 };
 
-// all threads of the CTA; blockDim.x a power of two <= ADL_THREADS
-__device__ __forceinline__ double block_sum(double x, double* scratch) {
-  __syncthreads();
-  scratch[threadIdx.x] = x;
-  __syncthreads();
-  for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
-    if ((int)threadIdx.x < o) scratch[threadIdx.x] += scratch[threadIdx.x + o];
-    __syncthreads();
+// Sum of (x, y) over the CTA (blockDim.x a multiple of 32, <= ADL_THREADS): warp shuffles, then
+// one shared-memory stage. All threads call it and get the totals.
+__device__ __forceinline__ void block_sum2(double& x, double& y, double* scratch) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    x += __shfl_xor_sync(0xffffffffu, x, o);
+    y += __shfl_xor_sync(0xffffffffu, y, o);
   }
-  return scratch[0];
+  const int warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+  __syncthreads();                            // scratch may still be read from a previous call
+  if ((threadIdx.x & 31) == 0) { scratch[2 * warp] = x; scratch[2 * warp + 1] = y; }
+  __syncthreads();
+  double sx = 0.0, sy = 0.0;
+  for (int w = 0; w < nwarp; ++w) { sx += scratch[2 * w]; sy += scratch[2 * w + 1]; }
+  x = sx; y = sy;
 }
 
-// Executed by ONE CTA (all of its threads) once every bucket kernel of the
-// step has completed on this rank.
+// Executed by ONE CTA (all of its threads) once every bucket kernel of the step has completed on
+// this rank. It sits on the step's critical path (the optimizer waits for it), so it is written
+// against latency: every scalar and every per-group state word it will need is requested up
+// front, in parallel and BEFORE the peer barrier; after the barrier there is one round of
+// (remote) loads for the sums, then arithmetic on registers only, two block reductions, and one
+// system fence before the mailbox sequence number.
 __device__ __noinline__ void finalize_body(const FinalizeArgs& a) {
-  __shared__ double scratch[ADL_THREADS];
+  __shared__ double scratch[2 * (ADL_THREADS / 32)];
+  __shared__ double sh_c[24];                // preloaded scalars (see the enum below)
   __shared__ double sh_t[3];                 // step_ns, sync_entry_ns, accum_ns (max over ranks)
   __shared__ unsigned long long sh_entry;
+  enum { C_ACCUM_SCALE = 0, C_SMOOTHING, C_RULE, C_RULE_ARG, C_ENABLED, C_AMP, C_SQR_UNBIAS, C_VAR_UNBIAS,
+         C_PROGRESS, C_BIASED, C_PAIR_STATE, C_ERR, C_N };
   const int G = a.n_groups;
   const int n = a.n_rows * G;
   const int XS = 4 * G + ADL_XCHG_TAIL;
+  const bool has_state = a.gns_state != nullptr;
+  // ---- requests that do not depend on anything (one round trip, all in flight together) ----
+  if (threadIdx.x < C_N) {
+    double v = 0.0;
+    const int c = threadIdx.x;
+    if (c <= C_ENABLED) v = (has_state && a.gns_ctrl) ? a.gns_ctrl[c] : 0.0;
+    else if (c == C_AMP) v = a.amp_scale ? (double)(*a.amp_scale) : 1.0;
+    else if (c >= C_SQR_UNBIAS && c <= C_BIASED) v = has_state ? a.gns_state[4 * G + (c - C_SQR_UNBIAS)] : 0.0;
+    else if (c == C_PAIR_STATE) v = a.pair_state ? (double)(*a.pair_state) : 0.0;
+    else if (c == C_ERR) v = (double)(*a.err);
+    sh_c[c] = v;
+  }
   const uint32_t step = *reinterpret_cast<volatile uint32_t*>(a.step_ctr);
   const int parity = step & 1;
   double* mine = a.xchg[a.rank] + (size_t)parity * XS;
+  // per-group estimator state of "my" groups (g = threadIdx.x, + blockDim.x, ...): at most
+  // GPT groups per thread live in registers, the rest (huge group counts) is re-read later
+  constexpr int GPT = 4;
+  double st_sb[GPT], st_vb[GPT], st_sa[GPT], st_va[GPT];
+#pragma unroll
+  for (int k = 0; k < GPT; ++k) {
+    const int g = threadIdx.x + k * blockDim.x;
+    if (has_state && g < G) {
+      st_sb[k] = a.gns_state[g]; st_vb[k] = a.gns_state[G + g];
+      st_sa[k] = a.gns_state[2 * G + g]; st_va[k] = a.gns_state[3 * G + g];
+    } else { st_sb[k] = st_vb[k] = st_sa[k] = st_va[k] = 0.0; }
+  }
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const int r = i / G;
     mine[i] = __ldcg(a.rows[r] + (i - r * G));
@@ -262,9 +330,9 @@ __device__ __noinline__ void finalize_body(const FinalizeArgs& a) {
     const unsigned long long now = globaltimer_ns();
     const unsigned long long last = a.last_stamp ? *a.last_stamp : 0ull;
     const unsigned long long t0 = a.t_start ? *a.t_start : now;
-    if (a.last_stamp) *a.last_stamp = now;
     double accum_ns = 0.0, accum_cnt = 0.0;
     if (a.clock) { accum_ns = a.clock[0]; accum_cnt = a.clock[1]; a.clock[0] = 0.0; a.clock[1] = 0.0; }
+    if (a.last_stamp) *a.last_stamp = now;
     mine[4 * G + 0] = (last != 0ull && now > last) ? (double)(now - last) : 0.0;
     mine[4 * G + 1] = now > t0 ? (double)(now - t0) : 0.0;
     mine[4 * G + 2] = accum_ns;
@@ -283,14 +351,19 @@ __device__ __noinline__ void finalize_body(const FinalizeArgs& a) {
   }
   __syncthreads();
   double* slot = a.mailbox + (size_t)(step % a.ring) * a.slot_doubles;
-  double* summed = a.result;                 // [4][G] device scratch (always provided)
+  double* summed = a.result;                 // [4][G] device copy of the summed rows
+  // ---- the sums: one round of loads over the peers' exchange records ----
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const int r = i / G;
     double x;
     if (a.world > 1 && ((a.sum_mask >> r) & 1)) {
+      double part[ADL_MAX_RANKS];
+#pragma unroll
+      for (int p = 0; p < ADL_MAX_RANKS; ++p)
+        part[p] = (p < a.world) ? *reinterpret_cast<volatile double*>(a.xchg[p] + (size_t)parity * XS + i) : 0.0;
       x = 0.0;
-      for (int p = 0; p < a.world; ++p)       // fixed order: identical on all ranks
-        x += *reinterpret_cast<volatile double*>(a.xchg[p] + (size_t)parity * XS + i);
+#pragma unroll
+      for (int p = 0; p < ADL_MAX_RANKS; ++p) x += part[p];      // fixed order: identical on all ranks
     } else {
       x = mine[i];
     }
@@ -309,131 +382,133 @@ __device__ __noinline__ void finalize_body(const FinalizeArgs& a) {
   }
   __syncthreads();
 
-  const bool device_mode = a.gns_state != nullptr && a.gns_ctrl[CTL_ENABLED] != 0.0;
+  const bool device_mode = has_state && sh_c[C_ENABLED] != 0.0;
   double finite_flag = 1.0, gain = 1.0, progress = 0.0, scale_out = 0.0;
-  const double amp = a.amp_scale ? (double)(*a.amp_scale) : 1.0;
+  const double amp = sh_c[C_AMP];
   if (!device_mode) {
     for (int i = threadIdx.x; i < n; i += blockDim.x) slot[ADL_MBOX_HDR + i] = summed[i];
   } else {
     double* st = a.gns_state;
     double* tail = st + 4 * G;
-    const double accum_scale = a.gns_ctrl[CTL_ACCUM_SCALE];
-    const double smoothing = a.gns_ctrl[CTL_SMOOTHING];
-    const int rule = (int)a.gns_ctrl[CTL_RULE];
+    const double accum_scale = sh_c[C_ACCUM_SCALE];
+    const double smoothing = sh_c[C_SMOOTHING];
+    const int rule = (int)sh_c[C_RULE];
     const double inv_amp2 = 1.0 / (amp * amp);  // the statistics are of amp-scaled gradients
     const double* L = summed;
     const double* T = summed + G;
-    // non-finite gradients: skip the statistics update (and the progress)
-    double bad = 0.0;
-    for (int g = threadIdx.x; g < G; g += blockDim.x)
-      if (!isfinite(T[g]) || !isfinite(L[g])) bad += 1.0;
-    bad = block_sum(bad, scratch);
+    const int count = a.world * a.micro_steps;
+    const double scale = accum_scale * a.micro_steps;
+    const double lr_scale = scale;            // ScalingRuleBase.step uses accum_scale * k
+    const bool had_stash = a.pair_mode && sh_c[C_PAIR_STATE] != 0.0;
+    const bool was_biased = sh_c[C_BIASED] != 0.0;
+    // candidate update of my groups, computed unconditionally (committed once `finite` is known)
+    const bool restart = count > 1 && was_biased;     // biased -> unbiased: the averages restart
+    const double theta = pow(smoothing, (count > 1) ? scale : 2.0 * accum_scale);
+    const double su = theta * (restart ? 0.0 : sh_c[C_SQR_UNBIAS]) + (1.0 - theta);
+    const double vu = theta * (restart ? 0.0 : sh_c[C_VAR_UNBIAS]) + (1.0 - theta);
+    double bad = 0.0, unused = 0.0;
+    double nsb[GPT], nvb[GPT];
+#pragma unroll
+    for (int k = 0; k < GPT; ++k) { nsb[k] = 0.0; nvb[k] = 0.0; }
+    for (int g = threadIdx.x, k = 0; g < G; g += blockDim.x, ++k) {
+      const double Lg = L[g], Tg = T[g];
+      if (!isfinite(Tg) || !isfinite(Lg)) bad += 1.0;
+      double local, total, cnt, sc;
+      if (count > 1) {
+        local = Lg * inv_amp2 / count; total = Tg * inv_amp2; cnt = count; sc = scale;
+      } else {
+        local = 0.5 * (summed[2 * G + g] + Tg) * inv_amp2; total = summed[3 * G + g] * inv_amp2;
+        cnt = 2.0; sc = 2.0 * accum_scale;
+      }
+      const double grad_sqr = (cnt * total - local) / (cnt - 1.0);
+      const double grad_var = (local - total) * sc / (cnt - 1.0);
+      const double sb0 = (k < GPT) ? st_sb[k] : st[g];
+      const double vb0 = (k < GPT) ? st_vb[k] : st[G + g];
+      const double sb = theta * (restart ? 0.0 : sb0) + (1.0 - theta) * grad_sqr;
+      const double vb = theta * (restart ? 0.0 : vb0) + (1.0 - theta) * grad_var;
+      if (k < GPT) { nsb[k] = sb; nvb[k] = vb; }
+      else { summed[2 * G + g] = sb; summed[3 * G + g] = vb; }   // spill (only with > GPT groups per thread)
+    }
+    block_sum2(bad, unused, scratch);
     const bool finite = bad == 0.0;
     finite_flag = finite ? 1.0 : 0.0;
-    int count = a.world * a.micro_steps;
-    double scale = accum_scale * a.micro_steps;
-    const double lr_scale = scale;            // ScalingRuleBase.step uses accum_scale * k
-    const bool had_stash = a.pair_mode && a.pair_state && (*a.pair_state != 0);
-    bool update = finite;
-    bool was_biased = tail[GNS_BIASED] != 0.0;
-    __syncthreads();
-    if (finite) {
-      if (count > 1) {
-        if (was_biased) {                     // biased -> unbiased: restart the averages
-          for (int g = threadIdx.x; g < G; g += blockDim.x) { st[g] = 0.0; st[G + g] = 0.0; }
-          __syncthreads();
-          if (threadIdx.x == 0) { tail[GNS_SQR_UNBIAS] = 0.0; tail[GNS_VAR_UNBIAS] = 0.0; }
-        }
-        if (threadIdx.x == 0) tail[GNS_BIASED] = 0.0;
-      } else {
-        if (threadIdx.x == 0) tail[GNS_BIASED] = 1.0;
-        if (!had_stash) update = false;       // first sample: nothing to difference yet
-      }
-    }
-    __syncthreads();
-    if (update) {
-      const double theta_scale = (count > 1) ? scale : 2.0 * accum_scale;
-      const double theta = pow(smoothing, theta_scale);
-      const double su = theta * tail[GNS_SQR_UNBIAS] + (1.0 - theta);
-      const double vu = theta * tail[GNS_VAR_UNBIAS] + (1.0 - theta);
-      for (int g = threadIdx.x; g < G; g += blockDim.x) {
-        double local, total, cnt, sc;
-        if (count > 1) {
-          local = L[g] * inv_amp2 / count; total = T[g] * inv_amp2; cnt = count; sc = scale;
-        } else {
-          const double* Pp = summed + 2 * G;
-          const double* Pa = summed + 3 * G;
-          local = 0.5 * (Pp[g] + T[g]) * inv_amp2; total = Pa[g] * inv_amp2;
-          cnt = 2.0; sc = 2.0 * accum_scale;
-        }
-        const double grad_sqr = (cnt * total - local) / (cnt - 1.0);
-        const double grad_var = (local - total) * sc / (cnt - 1.0);
-        const double sb = theta * st[g] + (1.0 - theta) * grad_sqr;
-        const double vb = theta * st[G + g] + (1.0 - theta) * grad_var;
-        st[g] = sb; st[G + g] = vb;
-        st[2 * G + g] = sb / su; st[3 * G + g] = vb / vu;
-      }
-      __syncthreads();
-      if (threadIdx.x == 0) { tail[GNS_SQR_UNBIAS] = su; tail[GNS_VAR_UNBIAS] = vu; }
-    }
-    __syncthreads();
-    if (a.pair_state && threadIdx.x == 0)
-      *a.pair_state = (a.pair_mode && finite) ? 1 : 0;
-    // learning-rate factors and gain from the (possibly just updated) averages
+    // non-finite gradients: skip the statistics update (and the progress); a single sample
+    // without a stash has nothing to difference yet
+    const bool update = finite && (count > 1 || had_stash);
     double sqr_sum = 0.0, var_sum = 0.0;
-    for (int g = threadIdx.x; g < G; g += blockDim.x) {
-      const double var = fmax(st[3 * G + g], 1e-6);
-      const double sqr = fmax(st[2 * G + g], 0.0);
-      sqr_sum += sqr; var_sum += var;
-    }
-    sqr_sum = block_sum(sqr_sum, scratch);
-    var_sum = block_sum(var_sum, scratch);
-    gain = (var_sum + sqr_sum) / (var_sum / lr_scale + sqr_sum);
-    progress = tail[GNS_PROGRESS];
-    for (int g = threadIdx.x; g < G; g += blockDim.x) {
-      const double var = fmax(st[3 * G + g], 1e-6);
-      const double sqr = fmax(st[2 * G + g], 0.0);
-      const double ada = (var + sqr) / (var / lr_scale + sqr);
-      double f;
-      if (rule == RULE_ADASCALE) f = ada;
-      else if (rule == RULE_ADAMSCALE) f = sqrt(ada);
-      else if (rule == RULE_LINEAR) f = lr_scale;
-      else if (rule == RULE_SQRT) f = sqrt(lr_scale);
-      else {                                  // LEGW: sqrt(scale) with progress warm-up
-        const double total_steps = a.gns_ctrl[CTL_RULE_ARG] * lr_scale;
-        f = sqrt(lr_scale) * ((progress < total_steps) ? progress / total_steps : 1.0);
+    for (int g = threadIdx.x, k = 0; g < G; g += blockDim.x, ++k) {
+      double sa, va;
+      if (update) {
+        const double sb = (k < GPT) ? nsb[k] : summed[2 * G + g];
+        const double vb = (k < GPT) ? nvb[k] : summed[3 * G + g];
+        st[g] = sb; st[G + g] = vb;
+        sa = sb / su; va = vb / vu;
+        st[2 * G + g] = sa; st[3 * G + g] = va;
+      } else {
+        if (finite && restart) { st[g] = 0.0; st[G + g] = 0.0; }
+        sa = (k < GPT) ? st_sa[k] : st[2 * G + g];
+        va = (k < GPT) ? st_va[k] : st[3 * G + g];
       }
-      a.lr_factor[g] = (float)f;
-      slot[ADL_MBOX_HDR + g] = st[2 * G + g];
-      slot[ADL_MBOX_HDR + G + g] = st[3 * G + g];
-      slot[ADL_MBOX_HDR + 2 * G + g] = f;
+      if (k < GPT) { st_sa[k] = sa; st_va[k] = va; }
+      sqr_sum += fmax(sa, 0.0);
+      var_sum += fmax(va, 1e-6);
     }
-    __syncthreads();
+    block_sum2(sqr_sum, var_sum, scratch);
+    gain = (var_sum + sqr_sum) / (var_sum / lr_scale + sqr_sum);
+    progress = sh_c[C_PROGRESS];
+    const double rule_arg = sh_c[C_RULE_ARG];
+    for (int g = threadIdx.x, k = 0; g < G; g += blockDim.x, ++k) {
+      const double sa = (k < GPT) ? st_sa[k] : st[2 * G + g];
+      const double va = (k < GPT) ? st_va[k] : st[3 * G + g];
+      const double var = fmax(va, 1e-6);
+      const double sqr = fmax(sa, 0.0);
+      const double ada = (var + sqr) / (var / lr_scale + sqr);
+      double fct;
+      if (rule == RULE_ADASCALE) fct = ada;
+      else if (rule == RULE_ADAMSCALE) fct = sqrt(ada);
+      else if (rule == RULE_LINEAR) fct = lr_scale;
+      else if (rule == RULE_SQRT) fct = sqrt(lr_scale);
+      else {                                  // LEGW: sqrt(scale) with progress warm-up
+        const double total_steps = rule_arg * lr_scale;
+        fct = sqrt(lr_scale) * ((progress < total_steps) ? progress / total_steps : 1.0);
+      }
+      a.lr_factor[g] = (float)fct;
+      slot[ADL_MBOX_HDR + g] = sa;
+      slot[ADL_MBOX_HDR + G + g] = va;
+      slot[ADL_MBOX_HDR + 2 * G + g] = fct;
+    }
     if (threadIdx.x == 0) {
       a.lr_factor[G] = finite ? 1.f : 0.f;    // the fused optimizer skips non-finite steps
-      if (finite) {                           // progress advances with every update
-        progress += gain;
+      if (finite) {
+        if (count > 1) {
+          tail[GNS_BIASED] = 0.0;
+        } else {
+          tail[GNS_BIASED] = 1.0;
+        }
+        if (update) { tail[GNS_SQR_UNBIAS] = su; tail[GNS_VAR_UNBIAS] = vu; }
+        else if (restart) { tail[GNS_SQR_UNBIAS] = 0.0; tail[GNS_VAR_UNBIAS] = 0.0; }
+        progress += gain;                     // progress advances with every finite step
         tail[GNS_PROGRESS] = progress;
       }
+      if (a.pair_state) *a.pair_state = (a.pair_mode && finite) ? 1 : 0;
     }
     scale_out = lr_scale;
   }
-  __threadfence_system();
-  __syncthreads();
+  __syncthreads();                            // every thread's mailbox payload has been issued
   if (threadIdx.x == 0) {
     const unsigned long long now = globaltimer_ns();
     slot[1] = finite_flag;
     slot[2] = gain;
     slot[3] = progress;
     slot[4] = sh_t[1] + (double)(now > sh_entry ? now - sh_entry : 0ull);
-    slot[5] = (double)(*a.err);
+    slot[5] = sh_c[C_ERR];
     slot[6] = scale_out;
     slot[7] = (double)a.n_rows;
     slot[8] = sh_t[0];
     slot[9] = sh_t[2];
     slot[10] = mine[4 * G + 3];
     slot[11] = amp;
-    __threadfence_system();
+    __threadfence_system();                   // payload (all threads') before the sequence number
     *reinterpret_cast<volatile double*>(slot) = (double)(step + 1);   // publish last
     *a.step_ctr = step + 1;                                           // next optimizer step
   }
@@ -442,16 +517,22 @@ __device__ __noinline__ void finalize_body(const FinalizeArgs& a) {
 // Tail of every statistics-producing kernel. All threads of all CTAs call it
 // after their last global access. With `fuse`, the last CTA of the grid to
 // get here runs the step's finalize.
-__device__ __forceinline__ void kernel_tail(bool fuse, uint32_t* ticket, const FinalizeArgs& f) {
-  __threadfence_system();                     // this thread's (remote) stores and atomics have landed
-  if (!fuse) return;
+__device__ __forceinline__ void kernel_tail(bool fuse, bool peers, uint32_t* ticket, const FinalizeArgs& f) {
   __shared__ int s_last;
-  __syncthreads();
+  __syncthreads();                            // every thread of the CTA has issued its stores / atomics
   if (threadIdx.x == 0) {
-    const unsigned t = atomicAdd(ticket, 1u);
-    s_last = (t == gridDim.x - 1);
-    if (s_last) *ticket = 0u;                 // everybody else has drawn: reset for the next step
+    // one cumulative fence per CTA (the flag-barrier idiom): the CTA's (remote) stores and
+    // statistics atomics are performed before anything this thread does next
+    if (peers) __threadfence_system(); else __threadfence();
+    int last = 0;
+    if (fuse) {
+      const unsigned t = atomicAdd(ticket, 1u);
+      last = (t == gridDim.x - 1);
+      if (last) *ticket = 0u;                 // everybody else has drawn: reset for the next step
+    }
+    s_last = last;
   }
+  if (!fuse) return;
   __syncthreads();
   if (s_last) {
     __threadfence();
@@ -481,6 +562,9 @@ allreduce_gns_kernel(const ReduceArgs a, const FinalizeArgs f) {
   smem_stats_zero(s_stats, 2 * a.n_groups);
   GroupAccum<2> accum;
   accum.init(s_stats, a.n_groups);
+  __shared__ int s_seg_end[ADL_SEG_SMEM], s_seg_group[ADL_SEG_SMEM];
+  SegCache segs;
+  segs.load(a.segs, s_seg_end, s_seg_group);
 
   const int world = (W > 0) ? W : a.world;
   if (world > 1) cta_barrier_peers(a, 0);             // every rank's grads are ready
@@ -527,7 +611,7 @@ allreduce_gns_kernel(const ReduceArgs a, const FinalizeArgs f) {
       int g = -1;
       if (active[u]) {
         const int v = base + idx[u];
-        g = group_of(a.segs, v, cur[u]);
+        g = group_of(segs, v, cur[u]);
         float sum[N], pinv[N];
         if (PINV) pc[u].finish(a.pinv_coef, a.pinv_wide, g, pinv);
 #pragma unroll
@@ -563,7 +647,7 @@ allreduce_gns_kernel(const ReduceArgs a, const FinalizeArgs f) {
   accum.flush_warp();
   double* outs[2] = {a.want_local ? a.L : nullptr, a.T};
   smem_stats_flush<2>(s_stats, a.n_groups, outs);
-  kernel_tail(a.fuse_fin != 0, a.ticket, f);
+  kernel_tail(a.fuse_fin != 0, world > 1, a.ticket, f);
 }
 
 // ---------------------------------------------------------------------------
@@ -586,6 +670,9 @@ allreduce_oneshot_kernel(const ReduceArgs a, const FinalizeArgs f) {
   smem_stats_zero(s_stats, 2 * a.n_groups);
   GroupAccum<2> accum;
   accum.init(s_stats, a.n_groups);
+  __shared__ int s_seg_end[ADL_SEG_SMEM], s_seg_group[ADL_SEG_SMEM];
+  SegCache segs;
+  segs.load(a.segs, s_seg_end, s_seg_group);
   const int world = (W > 0) ? W : a.world;
   const int stride = gridDim.x * blockDim.x;
   const int first = blockIdx.x * blockDim.x + threadIdx.x;
@@ -624,7 +711,7 @@ allreduce_oneshot_kernel(const ReduceArgs a, const FinalizeArgs f) {
           in[r] = (r == a.rank) ? ld_vec(mine + v) : ld_vec(lanes + (size_t)r * a.n_vec + v);
       }
       pc.issue(a.pinv, a.pinv_wide, v);
-      g = group_of(a.segs, v, cur);
+      g = group_of(segs, v, cur);
       float sum[N], pinv[N];
       if (PINV) pc.finish(a.pinv_coef, a.pinv_wide, g, pinv);
 #pragma unroll
@@ -658,7 +745,7 @@ allreduce_oneshot_kernel(const ReduceArgs a, const FinalizeArgs f) {
   accum.flush_warp();
   double* outs[2] = {a.want_local ? a.L : nullptr, a.T};
   smem_stats_flush<2>(s_stats, a.n_groups, outs);
-  kernel_tail(a.fuse_fin != 0, a.ticket, f);
+  kernel_tail(a.fuse_fin != 0, true, a.ticket, f);
 }
 
 // ---------------------------------------------------------------------------
@@ -713,6 +800,9 @@ allreduce_nvls_kernel(const ReduceArgs a, const FinalizeArgs f) {
   smem_stats_zero(s_stats, 2 * a.n_groups);
   GroupAccum<2> accum;
   accum.init(s_stats, a.n_groups);
+  __shared__ int s_seg_end[ADL_SEG_SMEM], s_seg_group[ADL_SEG_SMEM];
+  SegCache segs;
+  segs.load(a.segs, s_seg_end, s_seg_group);
   const int stride = gridDim.x * blockDim.x;
   const int first = blockIdx.x * blockDim.x + threadIdx.x;
   const Vec16* mine = static_cast<const Vec16*>(a.buf[a.rank]);
@@ -745,7 +835,7 @@ allreduce_nvls_kernel(const ReduceArgs a, const FinalizeArgs f) {
           int g = -1;
           if (idx[u] < slice) {
             const int v = q * slice + idx[u];
-            g = group_of(a.segs, v, cur[u]);
+            g = group_of(segs, v, cur[u]);
             float x[N], pinv[N];
             unpack<T>(in[u], x);
             if (PINV) pc[u].finish(a.pinv_coef, a.pinv_wide, g, pinv);
@@ -795,7 +885,7 @@ allreduce_nvls_kernel(const ReduceArgs a, const FinalizeArgs f) {
       int g = -1;
       if (idx[u] < slice) {
         const int v = base + idx[u];
-        g = group_of(a.segs, v, cur[u]);
+        g = group_of(segs, v, cur[u]);
         float x[N], pinv[N];
         if (PINV) pc[u].finish(a.pinv_coef, a.pinv_wide, g, pinv);
         if (a.want_local) {
@@ -821,7 +911,7 @@ allreduce_nvls_kernel(const ReduceArgs a, const FinalizeArgs f) {
   accum.flush_warp();
   double* outs[2] = {a.want_local ? a.L : nullptr, a.T};
   smem_stats_flush<2>(s_stats, a.n_groups, outs);
-  kernel_tail(a.fuse_fin != 0, a.ticket, f);
+  kernel_tail(a.fuse_fin != 0, true, a.ticket, f);
 }
 
 // ---------------------------------------------------------------------------
@@ -851,67 +941,82 @@ local_kernel(const LocalArgs a, const FinalizeArgs f) {
   extern __shared__ double s_stats[];                 // [3][n_groups]
   constexpr int N = VecTraits<T>::N;
   constexpr int K = 3;
+  constexpr int U = 4;                                // vectors in flight per thread and tensor
   smem_stats_zero(s_stats, K * a.n_groups);
   GroupAccum<K> accum;
   accum.init(s_stats, a.n_groups);
+  __shared__ int s_seg_end[ADL_SEG_SMEM], s_seg_group[ADL_SEG_SMEM];
+  SegCache segs;
+  segs.load(a.segs, s_seg_end, s_seg_group);
   const int stride = gridDim.x * blockDim.x;
   const int first = blockIdx.x * blockDim.x + threadIdx.x;
-  const int iters = (a.n_vec + stride - 1) / stride;
+  const int iters = (a.n_vec + stride * U - 1) / (stride * U);
   const bool have_prev = a.flag_ptr ? (*a.flag_ptr != 0) : (a.flag != 0);
-  int cur = -1;
+  int cur[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) cur[u] = -1;
   for (int it = 0; it < iters; ++it) {
-    const int v = first + it * stride;
-    const bool active = v < a.n_vec;
-    float sq[K] = {0.f, 0.f, 0.f};
-    int grp = -1;
-    if (active) {
-      float g[N], o[N], pinv[N];
-      const Vec16 gv = ld_vec(static_cast<const Vec16*>(a.g) + v);
-      Vec16 ov;
-      if (MODE == 2) ov = ld_vec(static_cast<const Vec16*>(a.pv) + v);
-      else ov = ld_vec(static_cast<const Vec16*>(a.a) + v);
-      Precond<T, PINV> pc;
-      pc.issue(a.pinv, a.pinv_wide, v);
-      grp = group_of(a.segs, v, cur);
-      if (PINV) pc.finish(a.pinv_coef, a.pinv_wide, grp, pinv);
-      unpack<T>(gv, g);
-      unpack<T>(ov, o);
+    Vec16 gv[U], ov[U];
+    Precond<T, PINV> pc[U];
+    int idx[U];
 #pragma unroll
-      for (int e = 0; e < N; ++e) {
-        const float y = PINV ? g[e] * pinv[e] : g[e];
-        sq[0] = fmaf(y, y, sq[0]);
-      }
-      if (MODE == 0) {
-#pragma unroll
-        for (int e = 0; e < N; ++e) o[e] += g[e];
-        st_vec(static_cast<Vec16*>(a.a) + v, pack<T>(o));
-        Vec16 z; z.w[0] = z.w[1] = z.w[2] = z.w[3] = 0u;
-        st_vec(static_cast<Vec16*>(a.g) + v, z);
-      } else if (MODE == 1) {
-#pragma unroll
-        for (int e = 0; e < N; ++e) g[e] += o[e];
-        st_vec(static_cast<Vec16*>(a.g) + v, pack<T>(g));
-        Vec16 z; z.w[0] = z.w[1] = z.w[2] = z.w[3] = 0u;
-        st_vec(static_cast<Vec16*>(a.a) + v, z);
-      } else {
-        if (have_prev) {
-#pragma unroll
-          for (int e = 0; e < N; ++e) {
-            const float p = PINV ? o[e] * pinv[e] : o[e];
-            const float m = 0.5f * ((PINV ? g[e] * pinv[e] : g[e]) + p);
-            sq[1] = fmaf(p, p, sq[1]);
-            sq[2] = fmaf(m, m, sq[2]);
-          }
-        }
-        st_vec(static_cast<Vec16*>(a.pv) + v, gv);
+    for (int u = 0; u < U; ++u) {
+      idx[u] = first + (it * U + u) * stride;
+      if (idx[u] < a.n_vec) {
+        gv[u] = ld_vec(static_cast<const Vec16*>(a.g) + idx[u]);
+        if (MODE == 2) ov[u] = ld_vec(static_cast<const Vec16*>(a.pv) + idx[u]);
+        else ov[u] = ld_vec(static_cast<const Vec16*>(a.a) + idx[u]);
+        pc[u].issue(a.pinv, a.pinv_wide, idx[u]);
       }
     }
-    accum.add(grp, sq);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int v = idx[u];
+      float sq[K] = {0.f, 0.f, 0.f};
+      int grp = -1;
+      if (v < a.n_vec) {
+        float g[N], o[N], pinv[N];
+        grp = group_of(segs, v, cur[u]);
+        if (PINV) pc[u].finish(a.pinv_coef, a.pinv_wide, grp, pinv);
+        unpack<T>(gv[u], g);
+        unpack<T>(ov[u], o);
+#pragma unroll
+        for (int e = 0; e < N; ++e) {
+          const float y = PINV ? g[e] * pinv[e] : g[e];
+          sq[0] = fmaf(y, y, sq[0]);
+        }
+        if (MODE == 0) {
+#pragma unroll
+          for (int e = 0; e < N; ++e) o[e] += g[e];
+          st_vec(static_cast<Vec16*>(a.a) + v, pack<T>(o));
+          Vec16 z; z.w[0] = z.w[1] = z.w[2] = z.w[3] = 0u;
+          st_vec(static_cast<Vec16*>(a.g) + v, z);
+        } else if (MODE == 1) {
+#pragma unroll
+          for (int e = 0; e < N; ++e) g[e] += o[e];
+          st_vec(static_cast<Vec16*>(a.g) + v, pack<T>(g));
+          Vec16 z; z.w[0] = z.w[1] = z.w[2] = z.w[3] = 0u;
+          st_vec(static_cast<Vec16*>(a.a) + v, z);
+        } else {
+          if (have_prev) {
+#pragma unroll
+            for (int e = 0; e < N; ++e) {
+              const float p = PINV ? o[e] * pinv[e] : o[e];
+              const float m = 0.5f * ((PINV ? g[e] * pinv[e] : g[e]) + p);
+              sq[1] = fmaf(p, p, sq[1]);
+              sq[2] = fmaf(m, m, sq[2]);
+            }
+          }
+          st_vec(static_cast<Vec16*>(a.pv) + v, gv[u]);
+        }
+      }
+      accum.add(grp, sq);
+    }
   }
   accum.flush_warp();
   double* outs[K] = {a.s0, a.s1, a.s2};
   smem_stats_flush<K>(s_stats, a.n_groups, outs);
-  if (MODE == 2) kernel_tail(a.fuse_fin != 0, a.ticket, f);
+  if (MODE == 2 && a.fuse_fin) kernel_tail(true, false, a.ticket, f);
 }
 
 __global__ void __launch_bounds__(256, 1) finalize_stats_kernel(const FinalizeArgs a) {
@@ -1101,8 +1206,9 @@ int adl_allreduce_gns(const ReduceArgs* args, const FinalizeArgs* fin, int dtype
 
 // mode: 0 fold_acc, 1 fold_final, 2 pair
 int adl_local(const LocalArgs* args, const FinalizeArgs* fin, int mode, int dtype, int grid,
-              void* stream) {
+              int threads, void* stream) {
   if (g_device >= 0) ADL_CHECK(cudaSetDevice(g_device));
+  if (threads < 64 || threads > ADL_THREADS || (threads & (threads - 1))) return -8;
   const size_t smem = sizeof(double) * 3 * args->n_groups;
   if (smem > ADL_MAX_STAT_SMEM) return -4;
   if (dtype < 0 || dtype > 2) return -2;
@@ -1114,9 +1220,9 @@ int adl_local(const LocalArgs* args, const FinalizeArgs* fin, int mode, int dtyp
   cudaStream_t s = (cudaStream_t)stream;
 #define CALL_L(T, P)                                                                         \
   do {                                                                                       \
-    if (mode == 0) local_kernel<T, 0, P><<<grid, ADL_THREADS, smem, s>>>(*args, f);          \
-    else if (mode == 1) local_kernel<T, 1, P><<<grid, ADL_THREADS, smem, s>>>(*args, f);     \
-    else if (mode == 2) local_kernel<T, 2, P><<<grid, ADL_THREADS, smem, s>>>(*args, f);     \
+    if (mode == 0) local_kernel<T, 0, P><<<grid, threads, smem, s>>>(*args, f);          \
+    else if (mode == 1) local_kernel<T, 1, P><<<grid, threads, smem, s>>>(*args, f);     \
+    else if (mode == 2) local_kernel<T, 2, P><<<grid, threads, smem, s>>>(*args, f);     \
     else return -3;                                                                          \
   } while (0)
   ADL_DISPATCH_TP(dtype, pinv, CALL_L);

@@ -384,9 +384,12 @@ def test_step_profile_comes_from_device_stamps():
     kernel's %globaltimer stamps (not host clocks), booked asynchronously;
     reference: torch/_metrics.py:43-59,104-127."""
     adl = _single_process_runtime()
-    from adaptdl_b200.torch import _metrics
+    from adaptdl_b200.torch import _metrics, data as adl_data
     from adaptdl_b200.torch.scaling_rules import AdaScale
     _metrics._reset_for_tests()
+    # "the training loader" is a per-process singleton (first wins): earlier
+    # tests of this process own it, and only its steps are committed
+    adl_data.AdaptiveDataLoaderHelper._training = None
     _, _, net, _, _ = _train(adl, _sgd, AdaScale, True, True, steps=20)
     timer = _metrics.device_timer()
     assert timer is not None and timer.reducer is net.reducer
@@ -404,6 +407,7 @@ def test_step_profile_comes_from_device_stamps():
         assert 0 < mean_sync <= mean_step
     # accumulation micro-steps arrive with the optimizer step closing them
     _metrics._reset_for_tests()
+    adl_data.AdaptiveDataLoaderHelper._training = None
     _, _, net2, _, _ = _train(adl, _sgd, AdaScale, True, False, steps=8,
                               accum=True)
     _metrics._book_device_records(wait=True)
@@ -627,14 +631,25 @@ def test_tcgen05_linear_gelu_autograd_matches_torch():
 # fused BatchNorm (+ residual) (+ ReLU), channels-last (csrc/adl_bn.cu)
 # ---------------------------------------------------------------------------
 @pytest.mark.gpu
+@pytest.mark.parametrize("single", [False, True])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("shape,residual,relu", [
     ((32, 64, 16, 16), True, True), ((16, 128, 8, 8), False, True),
     ((8, 512, 4, 4), True, False), ((7, 256, 5, 3), False, False),
     ((128, 64, 32, 32), True, True)])
-def test_fused_bn_act_matches_torch(dtype, shape, residual, relu):
+def test_fused_bn_act_matches_torch(dtype, shape, residual, relu, single,
+                                    monkeypatch):
+    """``single``: the one-launch cooperative kernel (reduce -> grid barrier
+    -> apply; opt-in) instead of the default reduce + apply pair."""
     from adaptdl_b200.ops import BatchNormAct2d
     from adaptdl_b200.ops.bn_act import supported
+    # (the package re-exports the FUNCTION bn_act over the submodule's name)
+    bn_mod = sys.modules["adaptdl_b200.ops.bn_act"]
+    monkeypatch.setenv("ADAPTDL_B200_BN_SINGLE", "1" if single else "0")
+    bn_mod._FUSED.clear()
+    if single:
+        assert bn_mod._fused_max_grid(torch.device("cuda:0")) > 0, \
+            "cooperative launch unavailable / not capturable"
     torch.manual_seed(1)
     dev = torch.device("cuda:0")
     c = shape[1]
@@ -676,6 +691,7 @@ def test_fused_bn_act_matches_torch(dtype, shape, residual, relu):
     def close(a, b, t):
         scale = b.abs().max().item() + 1e-6
         return (a.float() - b).abs().max().item() <= t * scale
+    bn_mod._FUSED.clear()
     gtol = 2e-4 if dtype == torch.float32 else 4e-2
     assert close(x1.grad, x2.grad, gtol)
     assert close(fused.weight.grad, plain.weight.grad, gtol)

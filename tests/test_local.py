@@ -64,12 +64,23 @@ def test_hints_server_round_trip():
 
 def test_rescale_a_running_job_1_to_2_replicas(tmp_path):
     script = os.path.join(ROOT, "examples", "linear_regression", "main.py")
+    trace_dir = tmp_path / "rescale-trace"
     env = {"PYTHONPATH": ROOT, "CUDA_VISIBLE_DEVICES": "",
-           "OMP_NUM_THREADS": "1"}
+           "OMP_NUM_THREADS": "1",
+           "ADAPTDL_B200_RESCALE_TRACE": str(trace_dir)}
     job = local.LocalElasticJob(
         [sys.executable, script, "--epochs", "400", "--size", "4000"], 2,
         checkpoint_dir=str(tmp_path), env=env)
     state = job.run(schedule=[1, 2], interval=8.0, stop_after=22.0)
+    # every replica recorded where the rescale spent its time
+    from adaptdl_b200.utils import rescale_trace
+    phases = rescale_trace.summarize(rescale_trace.collect(str(trace_dir)))
+    assert 0 in phases and 1 in phases, phases
+    assert "signal_received->exit_consensus" in phases[0], phases
+    assert "exit_consensus->checkpoint_written" in phases[0], phases
+    assert "interpreter_up->process_group_ready" in phases[1], phases
+    assert "wrapper_ready->first_step_done" in phases[1], phases
+    assert all(v >= 0 for gen in phases.values() for v in gen.values())
     events = [(what, detail) for _, what, detail in job.events]
     started = [d["replicas"] for w, d in events if w == "started"]
     assert started[:2] == [1, 2], events

@@ -83,6 +83,12 @@ def main():
 
     red._ensure(arena, "acc")
     red._ensure(arena, "prev")
+    # (a) the shape these kernels have inside a training step: thin grids
+    # (64 CTAs x 256 threads) that share the GPU with the backward kernels
+    report("pair_norm_stash thin", timed(lambda: red._pair(arena, bucket), stream=red._comm), 3)
+    report("fold_acc thin", timed(lambda: red._fold_acc(arena, bucket), stream=red._comm), 4)
+    # (b) the same kernels with the GPU to themselves (2 CTAs/SM x 512)
+    red._local_ctas, red._reduce_threads = 2 * red._sm_count, 512
     report("pair_norm_stash (F2)", timed(lambda: red._pair(arena, bucket), stream=red._comm), 3)
     report("fold_acc", timed(lambda: red._fold_acc(arena, bucket), stream=red._comm), 4)
     report("fold_final", timed(lambda: red._fold_final(arena, bucket), stream=red._comm), 4)
