@@ -30,7 +30,7 @@ LIB_PATH = os.path.join(_HERE, "libadl_b200.so")
 STAMP_PATH = os.path.join(_HERE, "libadl_b200.stamp")
 
 SOURCES = ["adl_kernels.cu", "adl_optim.cu", "adl_gemm.cu", "adl_bn.cu",
-           "adl_ln.cu", "adl_symm.cpp"]
+           "adl_ln.cu", "adl_transformer.cu", "adl_symm.cpp"]
 HEADERS = ["adl_common.cuh"]
 
 NVCC_FLAGS = [
@@ -314,13 +314,17 @@ def _declare(lib):
         c.c_void_p, c.c_void_p, c.c_void_p]
     lib.adl_bn_act.argtypes = [c.POINTER(BnArgs), c.c_int, c.c_int, c.c_int,
                                c.c_int, c.c_void_p]
-    lib.adl_bn_act_fused.argtypes = [c.POINTER(BnArgs), c.c_int, c.c_int,
-                                     c.c_int, c.c_void_p]
-    lib.adl_bn_config.argtypes = [c.c_int]
-    lib.adl_bn_config.restype = None
-    lib.adl_bn_fused_max_grid.argtypes = [c.c_int]
+
     lib.adl_dropout_add_ln.argtypes = [c.POINTER(LnArgs), c.c_int, c.c_int,
                                        c.c_int, c.c_void_p]
+    lib.adl_heads_permute.argtypes = [c.c_void_p, c.c_void_p, c.c_int,
+                                      c.c_int, c.c_int, c.c_int, c.c_int,
+                                      c.c_int, c.c_void_p]
+    lib.adl_colsum.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p,
+                               c.c_void_p, c.c_int, c.c_int, c.c_int,
+                               c.c_int, c.c_void_p]
+    lib.adl_slice_cast.argtypes = [c.c_void_p, c.c_void_p, c.c_int, c.c_int,
+                                   c.c_int, c.c_int, c.c_void_p]
     for name, struct in (("adl_sizeof_bn_args", BnArgs),
                          ("adl_sizeof_ln_args", LnArgs),
                          ("adl_sizeof_optim_args", OptimArgs),

@@ -15,6 +15,8 @@ import torch.nn.functional as F
 
 from adaptdl_b200.ops.layer_norm import dropout_add_layer_norm
 from adaptdl_b200.ops.linear_act import linear_act
+from adaptdl_b200.ops.transformer import (linear, merge_heads, padded_logits,
+                                          split_heads)
 
 __all__ = ["BertModel", "MLMTask", "NextSentenceTask", "QuestionAnswerTask",
            "bert_base_mlm"]
@@ -57,23 +59,26 @@ class EncoderLayer(nn.Module):
         self.activation = F.gelu if activation == "gelu" else F.relu
 
     def forward(self, x, attn_mask=None, is_causal=False):
-        n, s, e = x.shape
-        qkv = self.qkv(x).view(n, s, 3, self.nhead, e // self.nhead)
-        q, k, v = qkv.permute(2, 0, 3, 1, 4)          # [3, N, H, S, D]
+        # fused QKV GEMM, then [N, S, 3*E] -> three contiguous [N, H, S, D]
+        # (and the inverse pack in backward) with dedicated copy kernels
+        qkv = linear(x, self.qkv.weight, self.qkv.bias)
+        q, k, v = split_heads(qkv, self.nhead, 3)
         attn = F.scaled_dot_product_attention(
             q, k, v, attn_mask=attn_mask, is_causal=is_causal,
             dropout_p=self.drop if self.training else 0.0)
-        attn = attn.transpose(1, 2).reshape(n, s, e)
+        attn = merge_heads(attn)                      # [N, S, E]
         # dropout + residual + LayerNorm: one fused kernel per direction
-        x = dropout_add_layer_norm(x, self.out_proj(attn), self.norm1.weight,
-                                   self.norm1.bias, self.drop, self.training,
-                                   self.norm1.eps)
+        x = dropout_add_layer_norm(
+            x, linear(attn, self.out_proj.weight, self.out_proj.bias),
+            self.norm1.weight, self.norm1.bias, self.drop, self.training,
+            self.norm1.eps)
         if self.activation is F.gelu:
             # bias + GELU fused into the tcgen05 GEMM epilogue on B200
             h = linear_act(x, self.linear1.weight, self.linear1.bias, "gelu")
         else:
             h = self.activation(self.linear1(x))
-        h = self.linear2(F.dropout(h, self.drop, self.training))
+        h = linear(F.dropout(h, self.drop, self.training),
+                   self.linear2.weight, self.linear2.bias)
         return dropout_add_layer_norm(x, h, self.norm2.weight,
                                       self.norm2.bias, self.drop,
                                       self.training, self.norm2.eps)
@@ -110,16 +115,8 @@ def aligned_linear(x, weight, bias, multiple=64):
     """``F.linear`` for an output width that is not a multiple of 8 (the
     28 996-token vocabulary of the MLM head): cuBLAS falls back to sm_80
     ``mma.sync`` kernels for such shapes (3x slower forward, dgrad and wgrad
-    on B200). Zero rows are appended to the weight so that all three GEMMs
-    take the tcgen05 path; the extra logits are dropped again."""
-    n = weight.shape[0]
-    pad = (-n) % multiple
-    if pad == 0 or not x.is_cuda:
-        return F.linear(x, weight, bias)
-    weight = F.pad(weight, (0, 0, 0, pad))
-    if bias is not None:
-        bias = F.pad(bias, (0, pad))
-    return F.linear(x, weight, bias)[..., :n].contiguous()
+    on B200). See :func:`adaptdl_b200.ops.transformer.padded_logits`."""
+    return padded_logits(x, weight, bias, multiple)
 
 
 class MLMTask(nn.Module):
@@ -136,8 +133,9 @@ class MLMTask(nn.Module):
 
     def forward(self, src, token_type_input=None):
         out = self.bert_model(src, token_type_input)
-        out = self.norm_layer(F.gelu(self.mlm_span(out)))
-        return aligned_linear(out, self.mlm_head.weight, self.mlm_head.bias)
+        out = self.norm_layer(F.gelu(linear(out, self.mlm_span.weight,
+                                            self.mlm_span.bias)))
+        return padded_logits(out, self.mlm_head.weight, self.mlm_head.bias)
 
 
 class NextSentenceTask(nn.Module):

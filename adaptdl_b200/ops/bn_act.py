@@ -105,105 +105,6 @@ def _launch(args, dtype, backward, grid, grid_apply, device):
     _count.add(2)                     # reduce(+finalize) and apply
 
 
-# ---------------------------------------------------------------------------
-# single-launch (cooperative) variant: reduce -> grid barrier -> apply
-# ---------------------------------------------------------------------------
-_FUSED = {}          # device index -> max co-resident grid (0 = unavailable)
-_FUSED_MAX_C = 1024
-
-
-def _fused_max_grid(device):
-    """Co-resident CTAs of the single-launch kernels on ``device``; 0 when
-    the path is switched off (``ADAPTDL_B200_BN_SINGLE=0``), unsupported, or
-    not capturable into CUDA graphs on this driver."""
-    got = _FUSED.get(device.index)
-    if got is not None:
-        return got
-    # default OFF: measured on ResNet-18 (profiles/r2_n2), the first version
-    # of the single-launch kernel lost to the two-kernel path (2.19 vs 2.07
-    # ms/step), and so did programmatic dependent launch between the two
-    # kernels (2.09 vs 2.07)
-    if os.environ.get("ADAPTDL_B200_BN_SINGLE", "0") != "1":
-        _FUSED[device.index] = 0
-        _config_pdl()
-        return 0
-    if torch.cuda.is_current_stream_capturing():
-        return 0                       # decide outside of a capture
-    from adaptdl_b200 import _native
-    lib = _native.load()
-    lib.adl_set_device(device.index)
-    _config_pdl()
-    limit = max(int(lib.adl_bn_fused_max_grid(device.index)), 0)
-    _FUSED[device.index] = limit
-    if limit and not _probe_capturable(device):
-        _FUSED[device.index] = limit = 0
-    return limit
-
-
-def _config_pdl():
-    from adaptdl_b200 import _native
-    _native.load().adl_bn_config(
-        1 if os.environ.get("ADAPTDL_B200_BN_PDL", "0") == "1" else 0)
-
-
-def _probe_capturable(device):
-    """Cooperative launches must survive stream capture (the training step
-    is one CUDA graph): try it once on a toy tensor."""
-    try:
-        x = torch.randn(64, 32, device=device)
-        w = torch.ones(32, device=device)
-        b = torch.zeros(32, device=device)
-        side = torch.cuda.Stream(device)
-        side.wait_stream(torch.cuda.current_stream(device))
-        with torch.cuda.stream(side):
-            _BnAct.apply(x, w, b, None, None, None, True, 0.1, 1e-5)
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, stream=side):
-                y = _BnAct.apply(x, w, b, None, None, None, True, 0.1, 1e-5)
-            graph.replay()
-        torch.cuda.current_stream(device).wait_stream(side)
-        torch.cuda.synchronize(device)
-        ref = F.relu(F.batch_norm(x, None, None, w, b, True, 0.1, 1e-5))
-        return bool(torch.allclose(y, ref, atol=1e-4, rtol=1e-4))
-    except Exception:  # noqa: BLE001 - any failure means "use two kernels"
-        try:
-            torch.cuda.synchronize(device)
-        except Exception:  # noqa: BLE001
-            pass
-        return False
-
-
-def _fused_grid(device, m, c, vec, unroll):
-    """CTAs of the single-launch kernel for an [m, c] activation, or 0 to
-    use the two-kernel path. Every CTA folds all CTAs' partial sums itself
-    (grid x 2c floats out of L2), so the grid is capped by that cost as well
-    as by co-residency."""
-    limit = _fused_max_grid(device)
-    if not limit or c > _FUSED_MAX_C:
-        return 0
-    tpr = c // vec
-    q = 2 * c // 4                         # float4 columns of the fold
-    if tpr > 512 or 512 % tpr or q > 512 or 512 % q:
-        return 0
-    rpi = 512 // tpr
-    need = (m + rpi * unroll - 1) // (rpi * unroll)
-    by_fold = max(4, 8192 // c)            # one round trip of loads per thread
-    return max(1, min(need, limit, by_fold))
-
-
-def _launch_fused(args, dtype, backward, grid, device):
-    from adaptdl_b200 import _native
-    lib = _native.load()
-    code = lib.adl_bn_act_fused(ctypes.byref(args), _DTYPES[dtype], backward,
-                                grid,
-                                torch.cuda.current_stream(device).cuda_stream)
-    if code < 0:
-        raise RuntimeError("adl_bn_act_fused rejected the call (code {})"
-                           .format(code))
-    _native.check(code, "adl_bn_act_fused")
-    _count.add(1)
-
-
 def _ptr(t):
     return t.data_ptr() if t is not None else None
 
@@ -228,9 +129,7 @@ class _BnAct(torch.autograd.Function):
         y = torch.empty_like(x)           # preserve_format: channels-last
         mean = torch.empty(c, dtype=torch.float32, device=dev)
         rstd = torch.empty(c, dtype=torch.float32, device=dev)
-        single = _fused_grid(dev, m, c, vec, 4)
-        cb, grid = (c, single) if single else \
-            _reduce_grid(dev, m, c, vec, 4)
+        cb, grid = _reduce_grid(dev, m, c, vec, 6)
         scratch = torch.empty((grid + 1) * 2 * c, dtype=torch.float32,
                               device=dev)
         gamma = weight.float() if weight is not None else \
@@ -246,12 +145,9 @@ class _BnAct(torch.autograd.Function):
         a.partial = scratch.data_ptr()
         a.coef = scratch.data_ptr() + grid * 2 * c * 4
         a.M, a.C, a.n_partial, a.relu = m, c, grid, int(relu)
-        a.cb, a.counters = cb, _tickets(dev, max(c // cb, 2))
+        a.cb, a.counters = cb, _tickets(dev, c // cb)
         a.eps, a.momentum = eps, momentum
-        if single:
-            _launch_fused(a, x.dtype, 0, grid, dev)
-        else:
-            _launch(a, x.dtype, 0, grid, _grid(dev, m, c, vec, 4), dev)
+        _launch(a, x.dtype, 0, grid, _grid(dev, m, c, vec, 6), dev)
         ctx.save_for_backward(x, y if relu else None, gamma, mean, rstd)
         ctx.relu = bool(relu)
         ctx.has_res = residual is not None
@@ -274,9 +170,7 @@ class _BnAct(torch.autograd.Function):
         dres = torch.empty_like(x) if (ctx.has_res and ctx.relu) else None
         dgamma = torch.empty(c, dtype=torch.float32, device=dev)
         dbeta = torch.empty(c, dtype=torch.float32, device=dev)
-        single = _fused_grid(dev, m, c, vec, 2)
-        cb, grid = (c, single) if single else \
-            _reduce_grid(dev, m, c, vec, 2)
+        cb, grid = _reduce_grid(dev, m, c, vec, 3)
         scratch = torch.empty((grid + 1) * 2 * c, dtype=torch.float32,
                               device=dev)
         a = BnArgs()
@@ -288,11 +182,8 @@ class _BnAct(torch.autograd.Function):
         a.partial = scratch.data_ptr()
         a.coef = scratch.data_ptr() + grid * 2 * c * 4
         a.M, a.C, a.n_partial, a.relu = m, c, grid, int(ctx.relu)
-        a.cb, a.counters = cb, _tickets(dev, max(c // cb, 2))
-        if single:
-            _launch_fused(a, x.dtype, 1, grid, dev)
-        else:
-            _launch(a, x.dtype, 1, grid, _grid(dev, m, c, vec, 2), dev)
+        a.cb, a.counters = cb, _tickets(dev, c // cb)
+        _launch(a, x.dtype, 1, grid, _grid(dev, m, c, vec, 3), dev)
         if ctx.has_res and not ctx.relu:
             dres = dy
         return (dx, dgamma if ctx.has_affine[0] else None,

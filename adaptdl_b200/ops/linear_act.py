@@ -122,7 +122,8 @@ class _LinearAct(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dw = dz.t() @ x2d
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = dz.sum(0, dtype=torch.float32)
+            from adaptdl_b200.ops.transformer import colsum
+            db = colsum(dz.contiguous())
         return dx, dw, db, None
 
 

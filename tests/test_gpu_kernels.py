@@ -631,25 +631,14 @@ def test_tcgen05_linear_gelu_autograd_matches_torch():
 # fused BatchNorm (+ residual) (+ ReLU), channels-last (csrc/adl_bn.cu)
 # ---------------------------------------------------------------------------
 @pytest.mark.gpu
-@pytest.mark.parametrize("single", [False, True])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("shape,residual,relu", [
     ((32, 64, 16, 16), True, True), ((16, 128, 8, 8), False, True),
     ((8, 512, 4, 4), True, False), ((7, 256, 5, 3), False, False),
     ((128, 64, 32, 32), True, True)])
-def test_fused_bn_act_matches_torch(dtype, shape, residual, relu, single,
-                                    monkeypatch):
-    """``single``: the one-launch cooperative kernel (reduce -> grid barrier
-    -> apply; opt-in) instead of the default reduce + apply pair."""
+def test_fused_bn_act_matches_torch(dtype, shape, residual, relu):
     from adaptdl_b200.ops import BatchNormAct2d
     from adaptdl_b200.ops.bn_act import supported
-    # (the package re-exports the FUNCTION bn_act over the submodule's name)
-    bn_mod = sys.modules["adaptdl_b200.ops.bn_act"]
-    monkeypatch.setenv("ADAPTDL_B200_BN_SINGLE", "1" if single else "0")
-    bn_mod._FUSED.clear()
-    if single:
-        assert bn_mod._fused_max_grid(torch.device("cuda:0")) > 0, \
-            "cooperative launch unavailable / not capturable"
     torch.manual_seed(1)
     dev = torch.device("cuda:0")
     c = shape[1]
@@ -691,7 +680,6 @@ def test_fused_bn_act_matches_torch(dtype, shape, residual, relu, single,
     def close(a, b, t):
         scale = b.abs().max().item() + 1e-6
         return (a.float() - b).abs().max().item() <= t * scale
-    bn_mod._FUSED.clear()
     gtol = 2e-4 if dtype == torch.float32 else 4e-2
     assert close(x1.grad, x2.grad, gtol)
     assert close(fused.weight.grad, plain.weight.grad, gtol)
@@ -803,3 +791,123 @@ def test_fused_dropout_add_layer_norm_random_mask_and_eval(monkeypatch):
     assert torch.isfinite(a).all()
 
 
+
+
+# ---------------------------------------------------------------------------
+# transformer layout / reduction ops (csrc/adl_transformer.cu)
+# ---------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(32, 128, 12, 64), (3, 7, 2, 8),
+                                   (2, 130, 5, 128)])
+def test_split_and_merge_heads_match_views(shape):
+    from adaptdl_b200.ops.transformer import merge_heads, split_heads
+    n, s, h, d = shape
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    qkv = torch.randn(n, s, 3 * h * d, device=dev).bfloat16() \
+        .requires_grad_(True)
+    ref = qkv.detach().clone().requires_grad_(True)
+    q, k, v = split_heads(qkv, h, 3)
+    rq, rk, rv = ref.view(n, s, 3, h, d).permute(2, 0, 3, 1, 4)
+    for a, b in ((q, rq), (k, rk), (v, rv)):
+        assert a.is_contiguous() and a.shape == (n, h, s, d)
+        assert torch.equal(a, b)
+    out = merge_heads(q * 2 + k - v)
+    rout = (rq * 2 + rk - rv).transpose(1, 2).reshape(n, s, h * d)
+    assert out.shape == (n, s, h * d) and torch.equal(out, rout)
+    g = torch.randn_like(out)
+    out.backward(g)
+    rout.backward(g)
+    assert torch.equal(qkv.grad, ref.grad)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("shape", [(4096, 768), (4096, 3072), (37, 40),
+                                   (1, 8), (5000, 2304)])
+def test_colsum_matches_torch(dtype, shape):
+    from adaptdl_b200.ops.transformer import colsum
+    dev = torch.device("cuda:0")
+    torch.manual_seed(1)
+    x = torch.randn(shape, device=dev).to(dtype)
+    got = colsum(x)
+    want = x.double().sum(0)
+    assert got.dtype == torch.float32 and got.shape == (shape[1],)
+    tol = 1e-5 * (shape[0] ** 0.5) + 1e-6
+    assert (got.double() - want).abs().max().item() <= \
+        tol * (1 + want.abs().max().item())
+    assert torch.equal(colsum(x), got)          # deterministic
+
+
+@pytest.mark.gpu
+def test_linear_with_fused_bias_grad_and_padded_logits():
+    from adaptdl_b200.ops.transformer import linear, padded_logits
+    dev = torch.device("cuda:0")
+    torch.manual_seed(2)
+    x = torch.randn(6, 33, 64, device=dev)
+    w = torch.randn(96, 64, device=dev).bfloat16().requires_grad_(True)
+    b = torch.randn(96, device=dev).requires_grad_(True)
+    w2, b2 = (t.detach().clone().requires_grad_(True) for t in (w, b))
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = linear(x, w, b)
+        y2 = torch.nn.functional.linear(x, w2, b2)
+    assert y.dtype == torch.bfloat16
+    torch.testing.assert_close(y, y2)
+    g = torch.randn_like(y)
+    y.backward(g)
+    y2.backward(g)
+    torch.testing.assert_close(w.grad, w2.grad, rtol=2e-2, atol=2e-2)
+    assert b.grad.dtype == torch.float32
+    # the fp32 column sum is MORE accurate than the bf16 reduction autograd
+    # does under autocast: compare against the fp64 truth
+    truth = g.double().reshape(-1, 96).sum(0)
+    assert (b.grad.double() - truth).abs().max() <= \
+        (b2.grad.double() - truth).abs().max() + 1e-3
+
+    # vocabulary of 100 (not a multiple of 8): padded GEMM, fp32 logits
+    n = 100
+    w = torch.randn(n, 64, device=dev).bfloat16().requires_grad_(True)
+    b = torch.randn(n, device=dev).requires_grad_(True)
+    w2, b2 = (t.detach().clone().requires_grad_(True) for t in (w, b))
+    xs = torch.randn(5, 9, 64, device=dev, requires_grad=True)
+    xs2 = xs.detach().clone().requires_grad_(True)
+    tgt = torch.randint(0, n, (45,), device=dev)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        logits = padded_logits(xs, w, b)
+        loss = torch.nn.functional.cross_entropy(logits.view(-1, n), tgt)
+        ref = torch.nn.functional.linear(xs2, w2, b2)
+        loss2 = torch.nn.functional.cross_entropy(ref.view(-1, n), tgt)
+    assert logits.dtype == torch.float32 and logits.is_contiguous()
+    assert logits.shape == (5, 9, n)
+    torch.testing.assert_close(logits, ref.float(), rtol=2e-2, atol=2e-2)
+    loss.backward()
+    loss2.backward()
+    for a, c in ((xs.grad, xs2.grad), (w.grad, w2.grad), (b.grad, b2.grad)):
+        torch.testing.assert_close(a.float(), c.float(), rtol=3e-2,
+                                   atol=3e-3)
+
+
+@pytest.mark.gpu
+def test_bert_layer_with_fused_layout_ops_matches_plain_composition(
+        monkeypatch):
+    """One encoder layer + MLM head: the dedicated layout / reduction kernels
+    against the same model with them switched off."""
+    from adaptdl_b200.models.bert import MLMTask
+    dev = torch.device("cuda:0")
+    results = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("ADAPTDL_B200_FUSED_TRANSFORMER", flag)
+        torch.manual_seed(3)
+        net = MLMTask(1004, 128, 2, 256, 1, dropout=0.0, max_len=64).to(dev)
+        x = torch.randint(0, 1004, (4, 48), device=dev)
+        t = torch.randint(0, 1004, (4, 48), device=dev)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = net(x)
+            loss = torch.nn.functional.cross_entropy(
+                out.view(-1, 1004), t.view(-1))
+        loss.backward()
+        results.append((loss.item(),
+                        [p.grad.float().clone() for p in net.parameters()]))
+    assert abs(results[0][0] - results[1][0]) < 2e-2
+    for a, b in zip(results[0][1], results[1][1]):
+        assert (a - b).norm() <= 5e-2 * (b.norm() + 1e-3)
