@@ -317,9 +317,12 @@ def _declare(lib):
 
     lib.adl_dropout_add_ln.argtypes = [c.POINTER(LnArgs), c.c_int, c.c_int,
                                        c.c_int, c.c_void_p]
-    lib.adl_heads_permute.argtypes = [c.c_void_p, c.c_void_p, c.c_int,
-                                      c.c_int, c.c_int, c.c_int, c.c_int,
-                                      c.c_int, c.c_void_p]
+    lib.adl_heads_permute.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p,
+                                      c.c_void_p, c.c_int, c.c_int, c.c_int,
+                                      c.c_int, c.c_int, c.c_int, c.c_void_p]
+    lib.adl_gelu_dropout_bwd.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p,
+                                         c.c_void_p, c.c_longlong, c.c_float,
+                                         c.c_int, c.c_void_p]
     lib.adl_colsum.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p,
                                c.c_void_p, c.c_int, c.c_int, c.c_int,
                                c.c_int, c.c_void_p]

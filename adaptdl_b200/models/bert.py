@@ -73,12 +73,15 @@ class EncoderLayer(nn.Module):
             self.norm1.weight, self.norm1.bias, self.drop, self.training,
             self.norm1.eps)
         if self.activation is F.gelu:
-            # bias + GELU fused into the tcgen05 GEMM epilogue on B200
-            h = linear_act(x, self.linear1.weight, self.linear1.bias, "gelu")
+            # bias + GELU fused into the tcgen05 GEMM epilogue on B200; the
+            # hidden dropout belongs to the same op so that its backward and
+            # the GELU derivative are one elementwise pass
+            h = linear_act(x, self.linear1.weight, self.linear1.bias, "gelu",
+                           dropout_p=self.drop, training=self.training)
         else:
-            h = self.activation(self.linear1(x))
-        h = linear(F.dropout(h, self.drop, self.training),
-                   self.linear2.weight, self.linear2.bias)
+            h = F.dropout(self.activation(self.linear1(x)), self.drop,
+                          self.training)
+        h = linear(h, self.linear2.weight, self.linear2.bias)
         return dropout_add_layer_norm(x, h, self.norm2.weight,
                                       self.norm2.bias, self.drop,
                                       self.training, self.norm2.eps)

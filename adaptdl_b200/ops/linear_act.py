@@ -96,24 +96,55 @@ def gemm_bias_act(x2d, weight, bias, act="gelu", save_preact=True,
     return y, z
 
 
+def _gelu_dropout_backward(dy2d, z, keep, scale):
+    """``dy * keep * scale * gelu'(z)`` in one pass (``keep`` may be
+    ``None``)."""
+    from adaptdl_b200 import _native
+    lib = _native.load()
+    dy2d = dy2d.contiguous()
+    dz = torch.empty_like(z)
+    code = lib.adl_gelu_dropout_bwd(
+        dy2d.data_ptr(), z.data_ptr(),
+        keep.data_ptr() if keep is not None else None, dz.data_ptr(),
+        z.numel(), float(scale), 1 if z.dtype == torch.bfloat16 else 2,
+        torch.cuda.current_stream(z.device).cuda_stream)
+    if code < 0:
+        raise RuntimeError("adl_gelu_dropout_bwd rejected the call ({})"
+                           .format(code))
+    _native.check(code, "adl_gelu_dropout_bwd")
+    _count.add(1)
+    return dz
+
+
 class _LinearAct(torch.autograd.Function):
+    """``dropout(act(x @ W^T + b), p)``: the GEMM with its fused bias + GELU
+    epilogue, ``aten::native_dropout`` for the mask (generator-driven, CUDA-
+    graph safe), and a backward whose dropout and GELU derivatives are ONE
+    elementwise pass (instead of ``masked_scale`` + ``gelu_backward``)."""
+
     @staticmethod
-    def forward(ctx, x, weight, bias, act):
+    def forward(ctx, x, weight, bias, act, p):
         x2d = x.reshape(-1, x.shape[-1])
         need_grad = any(ctx.needs_input_grad[:3])
         y, z = gemm_bias_act(x2d, weight, bias, act,
                              save_preact=need_grad and act == "gelu")
+        keep = None
+        if p > 0.0:
+            y, keep = torch.native_dropout(y, p, True)
         ctx.act = act
+        ctx.scale = 1.0 / (1.0 - p) if p > 0.0 else 1.0
         ctx.has_bias = bias is not None
-        ctx.save_for_backward(x2d, weight, z)
+        ctx.save_for_backward(x2d, weight, z, keep)
         return y.view(*x.shape[:-1], weight.shape[0])
 
     @staticmethod
     def backward(ctx, dy):
-        x2d, weight, z = ctx.saved_tensors
+        x2d, weight, z, keep = ctx.saved_tensors
         dy2d = dy.reshape(-1, dy.shape[-1])
         if ctx.act == "gelu":
-            dz = torch.ops.aten.gelu_backward(dy2d, z, approximate="none")
+            dz = _gelu_dropout_backward(dy2d, z, keep, ctx.scale)
+        elif keep is not None:
+            dz = dy2d * keep * ctx.scale
         else:
             dz = dy2d
         dx = dw = db = None
@@ -124,12 +155,15 @@ class _LinearAct(torch.autograd.Function):
         if ctx.has_bias and ctx.needs_input_grad[2]:
             from adaptdl_b200.ops.transformer import colsum
             db = colsum(dz.contiguous())
-        return dx, dw, db, None
+        return dx, dw, db, None, None
 
 
-def linear_act(x, weight, bias=None, act="gelu"):
-    """``act(x @ weight.T + bias)``; fused tcgen05 kernel for bf16 CUDA
-    inputs (or under bf16 autocast), PyTorch composition otherwise."""
+def linear_act(x, weight, bias=None, act="gelu", dropout_p=0.0,
+               training=True):
+    """``dropout(act(x @ weight.T + bias), dropout_p)``; fused tcgen05
+    kernel for bf16 CUDA inputs (or under bf16 autocast), PyTorch composition
+    otherwise."""
+    p = float(dropout_p) if training else 0.0
     use_bf16 = x.is_cuda and (
         x.dtype == torch.bfloat16 or
         (torch.is_autocast_enabled("cuda") and
@@ -138,10 +172,11 @@ def linear_act(x, weight, bias=None, act="gelu"):
         with torch.autocast("cuda", enabled=False):
             out = _LinearAct.apply(
                 x.to(torch.bfloat16), weight.to(torch.bfloat16),
-                bias.float() if bias is not None else None, act)
+                bias.float() if bias is not None else None, act, p)
         return out
     out = F.linear(x, weight, bias)
-    return F.gelu(out) if act == "gelu" else out
+    out = F.gelu(out) if act == "gelu" else out
+    return F.dropout(out, p, True) if p > 0.0 else out
 
 
 class LinearGELU(torch.nn.Linear):

@@ -71,10 +71,15 @@ def _heads_ok(t, d):
         and d % 8 == 0
 
 
-def _permute(src, dst, a, b, w, h, d, merge):
-    lib = _lib(src.device)
-    _check(lib.adl_heads_permute(src.data_ptr(), dst.data_ptr(), a, b, w, h,
-                                 d, merge, _stream(src.device)),
+def _permute(srcs, dst, a, b, w, h, d, merge):
+    """split: ``srcs`` is the packed tensor; merge: a list of ``w`` planes
+    ``[a, h, b, d]`` (separately allocated, contiguous)."""
+    if torch.is_tensor(srcs):
+        srcs = [srcs]
+    lib = _lib(dst.device)
+    ptrs = [t.data_ptr() for t in srcs] + [None] * (3 - len(srcs))
+    _check(lib.adl_heads_permute(ptrs[0], ptrs[1], ptrs[2], dst.data_ptr(),
+                                 a, b, w, h, d, merge, _stream(dst.device)),
            "adl_heads_permute")
 
 
@@ -94,16 +99,13 @@ class _SplitHeads(torch.autograd.Function):
     def backward(ctx, *grads):
         n, s, parts, nhead, d = ctx.dims
         ref = next(g for g in grads if g is not None)
-        stacked = torch.empty((parts, n, nhead, s, d), dtype=ref.dtype,
-                              device=ref.device)
-        for i, g in enumerate(grads):
-            if g is None:
-                stacked[i].zero_()
-            elif g.data_ptr() != stacked[i].data_ptr():
-                stacked[i].copy_(g)
+        # the attention backward hands over three separately allocated
+        # [N, H, S, D] gradients: the pack kernel reads them in place
+        planes = [torch.zeros_like(ref) if g is None else g.contiguous()
+                  for g in grads]
         dqkv = torch.empty((n, s, parts * nhead * d), dtype=ref.dtype,
                            device=ref.device)
-        _permute(stacked, dqkv, n, s, parts, nhead, d, 1)
+        _permute(planes, dqkv, n, s, parts, nhead, d, 1)
         return dqkv, None, None
 
 
@@ -113,7 +115,7 @@ class _MergeHeads(torch.autograd.Function):
         n, h, s, d = x.shape
         x = x.contiguous()
         out = torch.empty((n, s, h * d), dtype=x.dtype, device=x.device)
-        _permute(x, out, n, s, 1, h, d, 1)
+        _permute([x], out, n, s, 1, h, d, 1)
         ctx.dims = (n, h, s, d)
         return out
 

@@ -66,6 +66,14 @@ template <typename T, int NV>
 __global__ void __launch_bounds__(LN_THREADS)
 ln_fwd_kernel(const LnArgs a) {
   constexpr int V = VecTraits<T>::N;
+  // gamma / beta once per CTA into shared memory: a lane's columns are the same for every row it
+  // visits, and 48 scalar global loads per row (stride 32 B across the warp: one 4-byte word used
+  // per 32-byte sector) were 4/5 of this kernel's L1 traffic and its actual limiter (ncu:
+  // profiles/r2_bert/ncu_ln_before.txt)
+  __shared__ __align__(16) float s_gamma[32 * LN_MAXV * 8];
+  __shared__ __align__(16) float s_beta[32 * LN_MAXV * 8];
+  for (int c = threadIdx.x; c < a.D; c += LN_THREADS) { s_gamma[c] = a.gamma[c]; s_beta[c] = a.beta[c]; }
+  __syncthreads();
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int nvec = a.D / V;
@@ -115,10 +123,14 @@ ln_fwd_kernel(const LnArgs a) {
     for (int i = 0; i < NV; ++i) {
       const int v = lane + 32 * i;
       if (v < nvec) {
-        float out[V];
+        float out[V], gm[V], bt[V];
 #pragma unroll
-        for (int e = 0; e < V; ++e)
-          out[e] = fmaf((zr[i][e] - mean) * rstd, __ldg(a.gamma + v * V + e), __ldg(a.beta + v * V + e));
+        for (int e = 0; e < V; e += 4) {
+          *reinterpret_cast<float4*>(gm + e) = *reinterpret_cast<const float4*>(s_gamma + v * V + e);
+          *reinterpret_cast<float4*>(bt + e) = *reinterpret_cast<const float4*>(s_beta + v * V + e);
+        }
+#pragma unroll
+        for (int e = 0; e < V; ++e) out[e] = fmaf((zr[i][e] - mean) * rstd, gm[e], bt[e]);
         st_vec(static_cast<T*>(a.y) + base + (size_t)v * V, pack<T>(out));
       }
     }
@@ -131,7 +143,12 @@ template <typename T, int NV>
 __global__ void __launch_bounds__(LN_THREADS)
 ln_bwd_kernel(const LnArgs a) {
   constexpr int V = VecTraits<T>::N;
-  __shared__ float acc[2 * 32 * LN_MAXV * 8];          // [2][D], D <= 1024
+  __shared__ __align__(16) float acc[2 * 32 * LN_MAXV * 8];   // [2][D], D <= 1024
+  // gamma staged in the second half of `acc` during the row loop (see ln_fwd_kernel); the
+  // partial-sum fold below only starts after a barrier
+  float* s_gamma = acc + 32 * LN_MAXV * 8;
+  for (int c = threadIdx.x; c < a.D; c += LN_THREADS) s_gamma[c] = a.gamma[c];
+  __syncthreads();
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int nvec = a.D / V;
@@ -152,13 +169,16 @@ ln_bwd_kernel(const LnArgs a) {
       const int v = lane + 32 * i;
       if (v < nvec) {
         const size_t off = base + (size_t)v * V;
-        float fz[V], fdy[V];
+        float fz[V], fdy[V], gm[V];
         unpack<T>(ld_vec(static_cast<const T*>(a.z) + off), fz);
         unpack<T>(ld_vec(static_cast<const T*>(a.h) + off), fdy);   // a.h carries dy
 #pragma unroll
+        for (int e = 0; e < V; e += 4)
+          *reinterpret_cast<float4*>(gm + e) = *reinterpret_cast<const float4*>(s_gamma + v * V + e);
+#pragma unroll
         for (int e = 0; e < V; ++e) {
           xh[i][e] = (fz[e] - mean) * rstd;
-          g[i][e] = fdy[e] * __ldg(a.gamma + v * V + e);
+          g[i][e] = fdy[e] * gm[e];
           s1 += g[i][e];
           s2 = fmaf(g[i][e], xh[i][e], s2);
           dg[i][e] = fmaf(fdy[e], xh[i][e], dg[i][e]);
@@ -189,6 +209,7 @@ ln_bwd_kernel(const LnArgs a) {
     }
   }
   // fold the eight warps' partials in a fixed order and store this CTA's row of partial sums
+  __syncthreads();                                     // everybody is done reading s_gamma
   for (int idx = threadIdx.x; idx < 2 * a.D; idx += LN_THREADS) acc[idx] = 0.f;
   __syncthreads();
   for (int w = 0; w < LN_WARPS; ++w) {
@@ -211,28 +232,40 @@ ln_bwd_kernel(const LnArgs a) {
   for (int idx = threadIdx.x; idx < 2 * a.D; idx += LN_THREADS) out[idx] = acc[idx];
 }
 
-// column sums of the per-CTA partials: CTA = 32 columns, warp w takes partials w, w+8, ...
+// column sums of the per-CTA partials [n_partial][2 * D]: a CTA owns 64 consecutive floats of the
+// 2*D-wide row (16 float4 columns x 16 row lanes), every thread keeps EIGHT rows in flight (the
+// first version walked its rows one dependent load at a time: 23 us for 1.8 MB, pure latency),
+// the row lanes are combined through shared memory in a fixed order (deterministic).
 __global__ void __launch_bounds__(LN_THREADS)
 ln_param_grad_kernel(const LnArgs a) {
-  __shared__ float red[2][LN_WARPS][32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int col = blockIdx.x * 32 + lane;
-  float tg = 0.f, tb = 0.f;
-  if (col < a.D) {
-    for (int p = warp; p < a.n_partial; p += LN_WARPS) {
-      tg += a.partial[(size_t)p * 2 * a.D + col];
-      tb += a.partial[(size_t)p * 2 * a.D + a.D + col];
+  constexpr int QC = 16;                               // float4 columns per CTA
+  constexpr int LANES = LN_THREADS / QC;               // 16 row lanes
+  __shared__ float4 red[LANES][QC];
+  const int qi = threadIdx.x % QC, li = threadIdx.x / QC;
+  const int q = 2 * a.D / 4;                           // float4 columns of a partial row
+  const int col4 = blockIdx.x * QC + qi;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (col4 < q) {
+    const float4* base = reinterpret_cast<const float4*>(a.partial) + col4;
+    for (int p0 = li; p0 < a.n_partial; p0 += 8 * LANES) {
+      float4 t[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int p = p0 + j * LANES;
+        t[j] = (p < a.n_partial) ? __ldcg(base + (size_t)p * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { acc.x += t[j].x; acc.y += t[j].y; acc.z += t[j].z; acc.w += t[j].w; }
     }
   }
-  red[0][warp][lane] = tg;
-  red[1][warp][lane] = tb;
+  red[li][qi] = acc;
   __syncthreads();
-  if (warp == 0 && col < a.D) {
-    float g = 0.f, b = 0.f;
-#pragma unroll
-    for (int w = 0; w < LN_WARPS; ++w) { g += red[0][w][lane]; b += red[1][w][lane]; }
-    a.dgamma[col] = g;
-    a.dbeta[col] = b;
+  if (threadIdx.x < QC && col4 < q) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int l = 0; l < LANES; ++l) { const float4 r = red[l][qi]; t.x += r.x; t.y += r.y; t.z += r.z; t.w += r.w; }
+    const int c = col4 * 4;                            // position in the [dgamma | dbeta] row
+    float* dst = (c < a.D) ? (a.dgamma + c) : (a.dbeta + (c - a.D));
+    *reinterpret_cast<float4*>(dst) = t;
   }
 }
 
@@ -242,7 +275,7 @@ void launch(const LnArgs& a, int backward, int grid, cudaStream_t s) {
     ln_fwd_kernel<T, NV><<<grid, LN_THREADS, 0, s>>>(a);
   } else {
     ln_bwd_kernel<T, NV><<<grid, LN_THREADS, 0, s>>>(a);
-    ln_param_grad_kernel<<<(a.D + 31) / 32, LN_THREADS, 0, s>>>(a);
+    ln_param_grad_kernel<<<(2 * a.D / 4 + 15) / 16, LN_THREADS, 0, s>>>(a);
   }
 }
 

@@ -51,11 +51,12 @@ heads_split_kernel(const Vec16* __restrict__ src, Vec16* __restrict__ dst, int A
   }
 }
 
-// src[w][a][h][b][v] -> dst[a][b][w*H + h][v]
+// W source planes (each [a][h][b][v], separately allocated) -> dst[a][b][w*H + h][v]
+struct Planes { const Vec16* p[4]; };
+
 __global__ void __launch_bounds__(TR_THREADS)
-heads_merge_kernel(const Vec16* __restrict__ src, Vec16* __restrict__ dst, int A, int B, int W, int H, int vecs) {
+heads_merge_kernel(const Planes src, Vec16* __restrict__ dst, int A, int B, int W, int H, int vecs) {
   const long long total = (long long)A * B * W * H * vecs;
-  const long long plane = (long long)A * H * B * vecs;
   const long long stride = (long long)gridDim.x * blockDim.x;
   // iterate in DESTINATION order (coalesced stores; the loads are whole 128-byte head rows)
   for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += 4 * stride) {
@@ -71,7 +72,7 @@ heads_merge_kernel(const Vec16* __restrict__ src, Vec16* __restrict__ dst, int A
         const int b = (int)(r % B);
         const int a = (int)(r / B);
         const int w = c / H, h = c - w * H;
-        val[u] = ld_vec(src + w * plane + (((long long)a * H + h) * B + b) * vecs + v);
+        val[u] = ld_vec(src.p[w] + (((long long)a * H + h) * B + b) * vecs + v);
       }
     }
 #pragma unroll
@@ -205,6 +206,53 @@ f32_to_slice_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ d
   }
 }
 
+// ---------------------------------------------------------------------------
+// dZ = dD * keep * scale * gelu'(Z)      (backward of  D = dropout(gelu(Z)) in one pass)
+// gelu'(z) = Phi(z) + z * phi(z)  (erf form, matching aten::gelu_backward "none")
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(TR_THREADS)
+gelu_dropout_bwd_kernel(const T* __restrict__ dd, const T* __restrict__ z, const uint8_t* __restrict__ keep,
+                        T* __restrict__ dz, long long n_vec, float scale) {
+  constexpr int V = VecTraits<T>::N;                  // 8
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n_vec; i0 += 2 * stride) {
+    Vec16 vd[2], vz[2];
+    uint2 vm[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < n_vec) {
+        vd[u] = ld_vec(dd + i * V);
+        vz[u] = ld_vec(z + i * V);
+        if (keep) vm[u] = *reinterpret_cast<const uint2*>(keep + i * V);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < n_vec) {
+        float fd[V], fz[V], out[V];
+        unpack<T>(vd[u], fd);
+        unpack<T>(vz[u], fz);
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+          float k = scale;
+          if (keep) {
+            const uint32_t word = e < 4 ? vm[u].x : vm[u].y;
+            k = ((word >> (8 * (e & 3))) & 0xffu) ? scale : 0.f;
+          }
+          const float x = fz[e];
+          const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752f));
+          const float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
+          out[e] = fd[e] * k * fmaf(x, pdf, cdf);
+        }
+        st_vec(dz + i * V, pack<T>(out));
+      }
+    }
+  }
+}
+
 int grid_for(long long items, int per_thread) {
   long long need = (items + (long long)TR_THREADS * per_thread - 1) / ((long long)TR_THREADS * per_thread);
   if (need < 1) need = 1;
@@ -218,19 +266,27 @@ extern "C" int adl_bind_thread();
 
 extern "C" {
 
-// 2-byte elements (bf16 / fp16): D % 8 == 0. split: src [A,B,W*H,D] -> dst [W][A,H,B,D];
-// merge: src [W][A,H,B,D] -> dst [A,B,W*H,D].
-int adl_heads_permute(const void* src, void* dst, int A, int B, int W, int H, int D, int merge, void* stream) {
+// 2-byte elements (bf16 / fp16): D % 8 == 0. split: src [A,B,W*H,D] -> dst [W][A,H,B,D]
+// (one buffer); merge: W separately allocated planes [A,H,B,D] (src0..src2; W <= 3) ->
+// dst [A,B,W*H,D].
+int adl_heads_permute(const void* src0, const void* src1, const void* src2, void* dst, int A, int B, int W,
+                      int H, int D, int merge, void* stream) {
   if (int rc = adl_bind_thread()) return rc;
-  if (D % 8 != 0 || A <= 0 || B <= 0 || W <= 0 || H <= 0) return -40;
+  if (D % 8 != 0 || A <= 0 || B <= 0 || W <= 0 || W > 3 || H <= 0) return -40;
   const int vecs = D / 8;
   const long long total = (long long)A * B * W * H * vecs;
   const int grid = grid_for(total, 4);
   cudaStream_t s = (cudaStream_t)stream;
-  if (merge)
-    heads_merge_kernel<<<grid, TR_THREADS, 0, s>>>(static_cast<const Vec16*>(src), static_cast<Vec16*>(dst), A, B, W, H, vecs);
-  else
-    heads_split_kernel<<<grid, TR_THREADS, 0, s>>>(static_cast<const Vec16*>(src), static_cast<Vec16*>(dst), A, B, W, H, vecs);
+  if (merge) {
+    Planes planes;
+    planes.p[0] = static_cast<const Vec16*>(src0);
+    planes.p[1] = static_cast<const Vec16*>(src1);
+    planes.p[2] = static_cast<const Vec16*>(src2);
+    planes.p[3] = nullptr;
+    heads_merge_kernel<<<grid, TR_THREADS, 0, s>>>(planes, static_cast<Vec16*>(dst), A, B, W, H, vecs);
+  } else {
+    heads_split_kernel<<<grid, TR_THREADS, 0, s>>>(static_cast<const Vec16*>(src0), static_cast<Vec16*>(dst), A, B, W, H, vecs);
+  }
   return (int)cudaGetLastError();
 }
 
@@ -249,6 +305,28 @@ int adl_colsum(const void* x, float* out, float* partial, int* tickets, int M, i
     case 2: colsum_kernel<__half><<<grid, TR_THREADS, 0, s>>>(static_cast<const __half*>(x), out, partial, tickets, M, N); break;
     default: return -42;
   }
+  return (int)cudaGetLastError();
+}
+
+// dz = dd * keep * scale * gelu'(z); 16-bit tensors of n elements (n % 8 == 0), keep: bytes (1 = kept)
+// or nullptr. dtype 1 bf16, 2 fp16.
+int adl_gelu_dropout_bwd(const void* dd, const void* z, const void* keep, void* dz, long long n, float scale,
+                         int dtype, void* stream) {
+  if (int rc = adl_bind_thread()) return rc;
+  if (n <= 0 || n % 8 != 0) return -44;
+  const long long n_vec = n / 8;
+  const int grid = grid_for(n_vec, 2);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == 1)
+    gelu_dropout_bwd_kernel<__nv_bfloat16><<<grid, TR_THREADS, 0, s>>>(
+        static_cast<const __nv_bfloat16*>(dd), static_cast<const __nv_bfloat16*>(z),
+        static_cast<const uint8_t*>(keep), static_cast<__nv_bfloat16*>(dz), n_vec, scale);
+  else if (dtype == 2)
+    gelu_dropout_bwd_kernel<__half><<<grid, TR_THREADS, 0, s>>>(
+        static_cast<const __half*>(dd), static_cast<const __half*>(z), static_cast<const uint8_t*>(keep),
+        static_cast<__half*>(dz), n_vec, scale);
+  else
+    return -45;
   return (int)cudaGetLastError();
 }
 

@@ -911,3 +911,32 @@ def test_bert_layer_with_fused_layout_ops_matches_plain_composition(
     assert abs(results[0][0] - results[1][0]) < 2e-2
     for a, b in zip(results[0][1], results[1][1]):
         assert (a - b).norm() <= 5e-2 * (b.norm() + 1e-3)
+
+
+@pytest.mark.gpu
+def test_linear_gelu_dropout_backward_is_one_fused_pass():
+    """``linear_act(..., dropout_p)``: forward = GEMM(+bias+GELU) + dropout,
+    backward = ONE kernel for the dropout and GELU derivatives; checked
+    against the PyTorch composition replayed with the same keep-mask."""
+    from adaptdl_b200.ops import linear_act
+    dev = torch.device("cuda:0")
+    torch.manual_seed(5)
+    m, k, n, p = 256, 128, 256, 0.3
+    x = (torch.randn(m, k, device=dev) * 0.5).bfloat16().requires_grad_(True)
+    w = (torch.randn(n, k, device=dev) * 0.1).bfloat16().requires_grad_(True)
+    b = torch.randn(n, device=dev).requires_grad_(True)
+    y = linear_act(x, w, b, "gelu", dropout_p=p, training=True)
+    keep = (y != 0)
+    frac = keep.float().mean().item()
+    assert 0.6 < frac < 0.8                      # ~ 1 - p
+    x2, w2, b2 = (t.detach().float().requires_grad_(True) for t in (x, w, b))
+    ref = torch.nn.functional.gelu(x2 @ w2.t() + b2) * keep / (1 - p)
+    torch.testing.assert_close(y.float(), ref, rtol=3e-2, atol=3e-2)
+    g = torch.randn(m, n, device=dev)
+    y.backward(g.bfloat16())
+    ref.backward(g.bfloat16().float())
+    for a, c in ((x.grad, x2.grad), (w.grad, w2.grad), (b.grad, b2.grad)):
+        assert (a.float() - c).norm() <= 3e-2 * c.norm()
+    # eval mode: no dropout
+    y_eval = linear_act(x, w, b, "gelu", dropout_p=p, training=False)
+    assert (y_eval != 0).float().mean().item() > 0.95

@@ -54,7 +54,8 @@ def main():
         return dropout_add_layer_norm(x, h, w, b, 0.1, True)
 
     def torch_fwd():
-        return F.layer_norm(x + F.dropout(h, 0.1, True), (d,), w, b)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            return F.layer_norm(x + F.dropout(h, 0.1, True), (d,), w, b)
 
     out = {}
     for name, fwd in (("fused", fused_fwd), ("torch", torch_fwd)):

@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
 set -u
 export OMP_NUM_THREADS=1
-OUT=gpurun_out/call6
+OUT=gpurun_out/call7
 mkdir -p "$OUT"
 summ() { python - "$1" <<'PY'
 import json, sys, statistics
@@ -23,7 +23,7 @@ ADAPTDL_B200_FUSED_TRANSFORMER=0 timeout 400 python bench.py --workload bert --s
 timeout 300 python bench.py --workload ncf --steps 20 --warmup 5 --no-fp32-variant > "$OUT/ncf_n1.log" 2>&1; summ "$OUT/ncf_n1.log"
 echo "== 3. LayerNorm op"
 timeout 200 python tools/ln_bench.py --out "$OUT/ln_bench.json" > "$OUT/ln_bench.log" 2>&1; cat "$OUT/ln_bench.log" | tr '\n' ' '; echo
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:ln_ -s 12 -c 4 -o "$OUT/ncu_ln" python tools/ln_bench.py --iters 2 > "$OUT/ncu_ln.log" 2>&1; ls -la "$OUT" | grep ncu
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:ln_ -s 12 -c 6 -o "$OUT/ncu_ln" python tools/ln_bench.py --iters 2 > "$OUT/ncu_ln.log" 2>&1; ls -la "$OUT" | grep ncu
 echo "== 4. op profile"
 timeout 300 python tools/op_profile.py --model bert --top 60 > "$OUT/op_profile_bert.log" 2>&1; grep -v "void \|nvjet\|cudnn_generated\|anonymous" "$OUT/op_profile_bert.log" | head -40 | cut -c1-200
 echo "== 5. launch list resnet (eager, bf16 params)"
