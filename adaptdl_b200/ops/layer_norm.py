@@ -37,12 +37,16 @@ def supported(h):
     return d % vec == 0 and d // vec <= 128 and h.numel() > 0
 
 
-def _grid(device, m):
+def _grid(device, m, per_sm=2):
+    """CTAs (8 warps = 8 rows at a time). The forward is pure load latency
+    per row, so it takes one row per warp when the machine can hold them all
+    (4 CTAs/SM); the backward carries per-CTA partial sums, so fewer, longer
+    CTAs (2/SM = its register-limited residency)."""
     n = _SM.get(device.index)
     if n is None:
         n = torch.cuda.get_device_properties(device).multi_processor_count
         _SM[device.index] = n
-    return max(1, min((m + 7) // 8, 2 * n))
+    return max(1, min((m + 7) // 8, per_sm * n))
 
 
 def _launch(args, dtype, backward, grid, device):
@@ -81,7 +85,7 @@ class _DropoutAddLN(torch.autograd.Function):
         a.gamma, a.beta = gamma.data_ptr(), beta.data_ptr()
         a.mean, a.rstd = mean.data_ptr(), rstd.data_ptr()
         a.M, a.D, a.scale, a.eps = m, d, scale, eps
-        _launch(a, h2.dtype, 0, _grid(dev, m), dev)
+        _launch(a, h2.dtype, 0, _grid(dev, m, 4), dev)
         ctx.save_for_backward(z, mask, gamma, mean, rstd)
         ctx.scale = scale
         ctx.shape = h.shape

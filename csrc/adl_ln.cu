@@ -143,10 +143,9 @@ template <typename T, int NV>
 __global__ void __launch_bounds__(LN_THREADS)
 ln_bwd_kernel(const LnArgs a) {
   constexpr int V = VecTraits<T>::N;
-  __shared__ __align__(16) float acc[2 * 32 * LN_MAXV * 8];   // [2][D], D <= 1024
-  // gamma staged in the second half of `acc` during the row loop (see ln_fwd_kernel); the
-  // partial-sum fold below only starts after a barrier
-  float* s_gamma = acc + 32 * LN_MAXV * 8;
+  // gamma staged in shared memory (see ln_fwd_kernel); `slab` is the fold scratch, one row per warp
+  __shared__ __align__(16) float s_gamma[32 * LN_MAXV * 8];
+  __shared__ __align__(16) float slab[LN_WARPS][32 * LN_MAXV * 8];   // 32 KB
   for (int c = threadIdx.x; c < a.D; c += LN_THREADS) s_gamma[c] = a.gamma[c];
   __syncthreads();
   const int lane = threadIdx.x & 31;
@@ -208,28 +207,34 @@ ln_bwd_kernel(const LnArgs a) {
       }
     }
   }
-  // fold the eight warps' partials in a fixed order and store this CTA's row of partial sums
-  __syncthreads();                                     // everybody is done reading s_gamma
-  for (int idx = threadIdx.x; idx < 2 * a.D; idx += LN_THREADS) acc[idx] = 0.f;
-  __syncthreads();
-  for (int w = 0; w < LN_WARPS; ++w) {
-    if (warp == w) {
+  // fold the eight warps' partials in a fixed order and store this CTA's row of partial sums:
+  // every warp drops its registers into its own shared-memory row (plain stores), then all
+  // threads add the eight rows column by column. (The first version let the warps take turns
+  // doing read-modify-writes on one row: 15 of the 26 stall cycles per instruction were that
+  // barrier, profiles/r2_bert/ncu_ln_before.txt.)
+  float* out = a.partial + (size_t)blockIdx.x * 2 * a.D;
 #pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const int v = lane + 32 * i;
-        if (v < nvec) {
+  for (int pass = 0; pass < 2; ++pass) {
+    __syncthreads();                                   // previous pass has been read out
 #pragma unroll
-          for (int e = 0; e < V; ++e) {
-            acc[v * V + e] += dg[i][e];
-            acc[a.D + v * V + e] += db[i][e];
-          }
+    for (int i = 0; i < NV; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nvec) {
+#pragma unroll
+        for (int e = 0; e < V; e += 4) {
+          const float* src = pass == 0 ? &dg[i][e] : &db[i][e];
+          *reinterpret_cast<float4*>(&slab[warp][v * V + e]) = make_float4(src[0], src[1], src[2], src[3]);
         }
       }
     }
     __syncthreads();
+    for (int c = threadIdx.x; c < a.D; c += LN_THREADS) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < LN_WARPS; ++w) t += slab[w][c];
+      out[pass * a.D + c] = t;
+    }
   }
-  float* out = a.partial + (size_t)blockIdx.x * 2 * a.D;
-  for (int idx = threadIdx.x; idx < 2 * a.D; idx += LN_THREADS) out[idx] = acc[idx];
 }
 
 // column sums of the per-CTA partials [n_partial][2 * D]: a CTA owns 64 consecutive floats of the

@@ -43,8 +43,4 @@ PY
 echo "== 5. BERT"
 bench bert_own_n8 $N --workload bert --steps 10 --no-fp32-variant
 bench bert_ref_n8 $N --workload bert --steps 10 --impl reference
-echo "== 6. N=4 points"
-bench resnet_own_n4 4 --no-fp32-variant
-bench bert_own_n4 4 --workload bert --steps 10 --no-fp32-variant
-bench bert_ref_n4 4 --workload bert --steps 10 --impl reference
 echo done
