@@ -5,6 +5,7 @@ import json
 import os
 import subprocess
 import sys
+import threading
 import time
 import uuid
 from datetime import datetime
@@ -41,13 +42,38 @@ def _load_yaml(path):
         return yaml.safe_load(f)
 
 
+class _RegistryTunnel(object):
+    """``localhost:port`` -> the in-cluster insecure registry, through the
+    API server's service proxy (``cli/proxy.py``, what the reference does
+    with mitmproxy); ``kubectl port-forward`` if the kubeconfig cannot be
+    used that way (exec credential plugins)."""
+
+    def __init__(self, port, namespace="default"):
+        self._stack = None
+        self._forward = None
+        try:
+            import contextlib
+            from adaptdl_b200.cli.proxy import service_proxy
+            self._stack = contextlib.ExitStack()
+            self._stack.enter_context(service_proxy(
+                namespace, "adaptdl-registry:registry", listen_port=port))
+        except Exception:  # noqa: BLE001 - any failure: plain port-forward
+            self._stack = None
+            self._forward = subprocess.Popen(
+                ["kubectl", "port-forward", "service/adaptdl-registry",
+                 "{}:5000".format(port)],
+                stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            time.sleep(2)
+
+    def terminate(self):
+        if self._stack is not None:
+            self._stack.close()
+        if self._forward is not None:
+            self._forward.terminate()
+
+
 def _registry_port_forward(port):
-    """Forward localhost:port to the in-cluster insecure registry (the
-    reference runs a mitmproxy reverse proxy for this)."""
-    return subprocess.Popen(
-        ["kubectl", "port-forward", "service/adaptdl-registry",
-         "{}:5000".format(port)],
-        stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    return _RegistryTunnel(port)
 
 
 def _build_push(project, dockerfile, proxy_port):
@@ -61,8 +87,6 @@ def _build_push(project, dockerfile, proxy_port):
     subprocess.check_call(build)
     forward = None if external else _registry_port_forward(proxy_port)
     try:
-        if forward is not None:
-            time.sleep(2)
         subprocess.check_call(["docker", "push", image])
     finally:
         if forward is not None:
@@ -176,8 +200,19 @@ def tensorboard(args, remaining):
     elif args.tb_command == "proxy":
         full = manifests.TENSORBOARD_PREFIX + args.name
         print("TensorBoard at http://localhost:{}".format(args.port))
-        _kubectl("port-forward", "service/" + full,
-                 "{}:6006".format(args.port), capture=False)
+        try:
+            from adaptdl_b200.cli.proxy import service_proxy
+            namespace = _kubectl(
+                "config", "view", "--minify", "-o",
+                "jsonpath={..namespace}").strip() or "default"
+            with service_proxy(namespace, full + ":6006",
+                               listen_port=args.port):
+                threading.Event().wait()        # until interrupted
+        except KeyboardInterrupt:
+            pass
+        except Exception:  # noqa: BLE001 - e.g. exec credential plugins
+            _kubectl("port-forward", "service/" + full,
+                     "{}:6006".format(args.port), capture=False)
 
 
 def build_parser():

@@ -105,11 +105,16 @@ class CudaGradReducer(GradReducer):
             itemsize = torch.empty((), dtype=arena.dtype).element_size()
             cursor += _round_up(max(arena.total, 1) * itemsize, _ALIGN)
         # NVLS: buckets at least this large go through the switch
-        # (profiles/README.md: all-reduce sweep at N=8)
+        # Measured at N=8 (graph replays, profiles/r2_n8/allreduce_n8.json):
+        # the two-shot P2P flavour wins up to 64 MB (16 MB: 66 vs 100 us,
+        # 64 MB: 210 vs 217 us per kernel), NVLS with 96 CTAs wins at
+        # 256 MB (708 vs 778 us) -- the switch path pays a second pass over
+        # the local bucket for the per-replica statistic. So only buckets of
+        # at least 128 MB (single huge parameters) take it.
         self._nvls_min_bytes = int(float(os.environ.get(
-            "ADAPTDL_B200_NVLS_MIN_MB", "16")) * (1 << 20))
+            "ADAPTDL_B200_NVLS_MIN_MB", "128")) * (1 << 20))
         self._nvls_ctas = max(1, min(int(os.environ.get(
-            "ADAPTDL_B200_NVLS_CTAS", "64")), MAX_CTAS - 1))
+            "ADAPTDL_B200_NVLS_CTAS", "96")), MAX_CTAS - 1))
         # the switch moves (1 + 1/N) B per GPU against 2 (N-1)/N B for the
         # two-shot flavour: no gain at N = 2 (measured 2x slower), 1.55x
         # fewer bytes at N = 8
@@ -430,14 +435,16 @@ class CudaGradReducer(GradReducer):
             grid = max(1, min(self._reduce_ctas,
                               (n_vec + threads - 1) // threads))
         elif self.world_size > 1:
-            # each thread keeps 16/W vectors in flight per iteration; a CTA
-            # moves >= 64 KB of its slice so that small buckets leave the
-            # SMs to backward
+            # each thread keeps 16/W vectors in flight per iteration. Within
+            # the CTA cap, prefer more CTAs over more iterations: an
+            # iteration is a full NVLink round trip (~3 us), so a 1 MB bucket
+            # on 2 CTAs spent 8 round trips where 8 CTAs need 2 (measured at
+            # N=8, profiles/r2_n8/allreduce_n8.json: 40 us per 1 MB kernel)
             threads = self._reduce_threads
-            per_cta = max(threads * max(16 // self.world_size, 1),
-                          (64 << 10) // layout.VEC_BYTES)
+            per_iter = threads * max(16 // self.world_size, 1)
             grid = max(1, min(self._reduce_ctas,
-                              (slice_vec + per_cta - 1) // per_cta))
+                              (slice_vec + 2 * per_iter - 1)
+                              // (2 * per_iter)))
         else:
             threads = 512
             grid = self._local_grid(n_vec)

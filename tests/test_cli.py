@@ -141,3 +141,88 @@ def test_pod_per_node_flag_wraps_python_commands():
                                         "--x"]
     assert containers[1]["command"] == ["/bin/sidecar"]
     assert "command" not in containers[2]
+
+
+def test_service_proxy_relays_through_the_api_server():
+    """``service_proxy``: requests to the local port arrive at
+    ``<api-server>/api/v1/namespaces/<ns>/services/<svc>/proxy<path>`` with
+    the kubeconfig's bearer token, bodies and status codes pass through
+    (reference: cli/adaptdl_cli/proxy.py:30-70)."""
+    import json
+    import threading
+    import urllib.request
+    from http.server import BaseHTTPRequestHandler, ThreadingHTTPServer
+    from adaptdl_b200.cli.proxy import load_kube_access, service_proxy
+    seen = []
+
+    class ApiServer(BaseHTTPRequestHandler):
+        def log_message(self, *args):
+            pass
+
+        def _any(self):
+            n = int(self.headers.get("Content-Length") or 0)
+            body = self.rfile.read(n) if n else b""
+            seen.append((self.command, self.path,
+                         self.headers.get("Authorization"), body))
+            payload = json.dumps({"path": self.path,
+                                  "echo": body.decode()}).encode()
+            self.send_response(201 if self.command == "PUT" else 200)
+            self.send_header("Content-Type", "application/json")
+            self.send_header("Docker-Distribution-Api-Version", "registry/2.0")
+            self.send_header("Content-Length", str(len(payload)))
+            self.end_headers()
+            self.wfile.write(payload)
+        do_GET = do_PUT = _any
+
+    api = ThreadingHTTPServer(("127.0.0.1", 0), ApiServer)
+    threading.Thread(target=api.serve_forever, daemon=True).start()
+    try:
+        access = load_kube_access({
+            "clusters": [{"cluster": {
+                "server": "http://127.0.0.1:{}".format(
+                    api.server_address[1])}}],
+            "users": [{"user": {"token": "s3cret"}}]})
+        with service_proxy("ns1", "adaptdl-registry:registry",
+                           access=access) as addr:
+            with urllib.request.urlopen(
+                    "http://{}/v2/_catalog?n=5".format(addr)) as resp:
+                assert resp.status == 200
+                assert resp.headers["Docker-Distribution-Api-Version"]
+                got = json.loads(resp.read())
+            assert got["path"] == ("/api/v1/namespaces/ns1/services/"
+                                   "adaptdl-registry:registry/proxy"
+                                   "/v2/_catalog?n=5")
+            req = urllib.request.Request(
+                "http://{}/v2/blob".format(addr), data=b"layer-bytes",
+                method="PUT")
+            with urllib.request.urlopen(req) as resp:
+                assert resp.status == 201
+                assert json.loads(resp.read())["echo"] == "layer-bytes"
+        assert [s[0] for s in seen] == ["GET", "PUT"]
+        assert all(s[2] == "Bearer s3cret" for s in seen)
+    finally:
+        api.shutdown()
+        api.server_close()
+
+
+def test_kube_access_materialises_inline_credentials():
+    import base64
+    import os
+    from adaptdl_b200.cli.proxy import load_kube_access
+    blob = base64.b64encode(b"PEM").decode()
+    access = load_kube_access({
+        "clusters": [{"cluster": {"server": "https://k:6443/",
+                                  "certificate-authority-data": blob}}],
+        "users": [{"user": {"client-certificate-data": blob,
+                            "client-key-data": blob}}]})
+    try:
+        assert access.server == "https://k:6443"
+        assert open(access.verify, "rb").read() == b"PEM"
+        assert all(open(p, "rb").read() == b"PEM" for p in access.cert)
+        paths = [access.verify] + list(access.cert)
+    finally:
+        access.close()
+    assert not any(os.path.exists(p) for p in paths)
+    insecure = load_kube_access({"clusters": [{"cluster": {
+        "server": "https://k", "insecure-skip-tls-verify": True}}]})
+    assert insecure.verify is False and insecure.cert is None
