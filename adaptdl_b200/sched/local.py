@@ -125,8 +125,18 @@ class LocalElasticJob(object):
     """One elastic job on this machine's GPUs."""
 
     def __init__(self, command, max_replicas, checkpoint_dir=None,
-                 job_id="local/job", env=None, gpu_ids=None):
+                 job_id="local/job", env=None, gpu_ids=None, standby=False,
+                 preload=()):
+        """``standby``: keep ``max_replicas`` warm interpreters
+        (:mod:`adaptdl_b200.sched.standby`) so that a new generation skips
+        the ~6.5 s of ``import torch`` / ``torch.optim``; needs a command of
+        the form ``python script.py ...``. ``preload``: extra modules the
+        standbys import ahead of time (e.g. ``torchvision``)."""
         self.command = list(command)
+        self.preload = tuple(preload)
+        self.standby = bool(standby) and self._standby_command() is not None
+        self.pool = []               # idle warm interpreters
+        self._pool_due = None        # when to top the pool up again
         self.max_replicas = max_replicas
         self.checkpoint_dir = checkpoint_dir or tempfile.mkdtemp(
             prefix="adaptdl-b200-ckpt-")
@@ -143,6 +153,98 @@ class LocalElasticJob(object):
         self.events.append((time.time(), what, detail))
         LOG.info("%s %s", what, detail)
 
+    _STALE = ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR",
+              "MASTER_PORT")
+
+    def _job_env(self):
+        """Variables every process of this job gets, whatever its
+        generation."""
+        return {
+            "ADAPTDL_JOB_ID": self.job_id,
+            "ADAPTDL_CHECKPOINT_PATH": self.checkpoint_dir,
+            "ADAPTDL_MASTER_ADDR": "127.0.0.1",
+            "ADAPTDL_NUM_NODES": "1",
+            "ADAPTDL_SUPERVISOR_URL": "",
+            "ADAPTDL_HINTS_URL": self.server.url,
+        }
+
+    def _replica_env(self, replicas, rank, port):
+        """Variables of one replica of one generation."""
+        return {
+            "ADAPTDL_MASTER_PORT": str(port),
+            "ADAPTDL_NUM_REPLICAS": str(replicas),
+            "ADAPTDL_REPLICA_RANK": str(rank),
+            "ADAPTDL_NUM_RESTARTS": str(self.num_restarts),
+            "ADAPTDL_LOCAL_RANK": str(
+                self.gpu_ids[rank] if self.gpu_ids else rank),
+        }
+
+    def _base_env(self):
+        env = dict(os.environ)
+        env.update(self.extra_env)
+        env.update(self._job_env())
+        for stale in self._STALE:
+            env.pop(stale, None)
+        return env
+
+    def _standby_command(self):
+        """``python -m adaptdl_b200.sched.standby script.py ...`` for a
+        ``python script.py ...`` command, else ``None``."""
+        cmd = self.command
+        if len(cmd) >= 2 and cmd[1].endswith(".py") and \
+                os.path.basename(cmd[0]).startswith("python"):
+            head = [cmd[0], "-m", "adaptdl_b200.sched.standby"]
+            if self.preload:
+                head += ["--preload", ",".join(self.preload)]
+            return head + ["--"] + cmd[1:]
+        return None
+
+    def fill_pool(self):
+        """Top the pool of warm interpreters up to ``max_replicas``."""
+        self._pool_due = None
+        if not self.standby:
+            return
+        self.pool = [p for p in self.pool if p.poll() is None]
+        env = self._base_env()
+        # the repository root must be importable for ``-m``
+        root = os.path.dirname(os.path.dirname(os.path.dirname(
+            os.path.abspath(__file__))))
+        env["PYTHONPATH"] = os.pathsep.join(
+            [root] + [p for p in env.get("PYTHONPATH", "").split(os.pathsep)
+                      if p])
+        while len(self.pool) < self.max_replicas:
+            self.pool.append(subprocess.Popen(
+                self._standby_command(), env=env, stdin=subprocess.PIPE))
+
+    def maintain(self):
+        """Periodic housekeeping (called from :meth:`run`'s loop)."""
+        if self._pool_due is not None and time.time() >= self._pool_due:
+            self.fill_pool()
+
+    def _release(self, proc, env):
+        """Turn a warm interpreter into a replica."""
+        order = {"env": env, "unset": list(self._STALE)}
+        try:
+            proc.stdin.write((json.dumps(order) + "\n").encode())
+            proc.stdin.close()
+            return True
+        except (OSError, ValueError):
+            return False
+
+    def drain_pool(self):
+        for p in self.pool:
+            try:
+                p.stdin.close()          # EOF = "not needed": exits 0
+            except (OSError, ValueError):
+                pass
+        for p in self.pool:
+            try:
+                p.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                p.kill()
+                p.wait()
+        self.pool = []
+
     def start(self, replicas, gpu_ids=None):
         """Start a generation with ``replicas`` processes; ``gpu_ids``
         (optional) are the device indices of this generation's replicas."""
@@ -152,28 +254,26 @@ class LocalElasticJob(object):
             self.gpu_ids = list(gpu_ids)
         port = pick_unused_port()
         self.replicas = self.server.replicas = replicas
+        self.pool = [p for p in self.pool if p.poll() is None]
+        warm = 0
         for rank in range(replicas):
-            env = dict(os.environ)
-            env.update(self.extra_env)
-            env.update({
-                "ADAPTDL_JOB_ID": self.job_id,
-                "ADAPTDL_CHECKPOINT_PATH": self.checkpoint_dir,
-                "ADAPTDL_MASTER_ADDR": "127.0.0.1",
-                "ADAPTDL_MASTER_PORT": str(port),
-                "ADAPTDL_NUM_NODES": "1",
-                "ADAPTDL_NUM_REPLICAS": str(replicas),
-                "ADAPTDL_REPLICA_RANK": str(rank),
-                "ADAPTDL_NUM_RESTARTS": str(self.num_restarts),
-                "ADAPTDL_SUPERVISOR_URL": "",
-                "ADAPTDL_LOCAL_RANK": str(
-                    self.gpu_ids[rank] if self.gpu_ids else rank),
-                "ADAPTDL_HINTS_URL": self.server.url,
-            })
-            for stale in ("RANK", "WORLD_SIZE", "LOCAL_RANK",
-                          "MASTER_ADDR", "MASTER_PORT"):
-                env.pop(stale, None)
-            self.procs.append(subprocess.Popen(self.command, env=env))
-        self._log("started", replicas=replicas, generation=self.num_restarts)
+            mine = self._replica_env(replicas, rank, port)
+            proc = None
+            while self.pool and proc is None:
+                candidate = self.pool.pop(0)
+                if self._release(candidate, mine):
+                    proc, warm = candidate, warm + 1
+            if proc is None:
+                env = self._base_env()
+                env.update(mine)
+                proc = subprocess.Popen(self.command, env=env)
+            self.procs.append(proc)
+        if self.standby:
+            # refill once the new generation is through its own start-up
+            # (the imports of 8 standbys would compete with it for the CPU)
+            self._pool_due = time.time() + 5.0
+        self._log("started", replicas=replicas, generation=self.num_restarts,
+                  warm=warm)
 
     def poll(self):
         """``None`` while running; else ``"finished"`` / ``"preempted"`` /
@@ -210,6 +310,7 @@ class LocalElasticJob(object):
         for p in self.procs:
             p.wait()
         self.procs = []
+        self.drain_pool()
 
     def rescale(self, replicas, timeout=300.0, gpu_ids=None):
         """SIGTERM -> wait for the checkpoint exit -> start the next
@@ -261,6 +362,7 @@ class LocalElasticJob(object):
                     self._log("stopped", state=state,
                               seconds=time.time() - t0)
                     return "stopped"
+                self.maintain()
                 state = self.poll()
                 if state in ("finished", "failed"):
                     self._log(state)
@@ -308,6 +410,16 @@ def main(argv=None):
                         help="have every replica record its life-cycle "
                              "events (utils/rescale_trace.py) and add the "
                              "per-generation phase breakdown to the report")
+    parser.add_argument("--standby", action="store_true",
+                        help="keep a pool of warm interpreters (torch "
+                             "already imported) for the next generation")
+    parser.add_argument("--fast-exit", action="store_true",
+                        help="replicas leave with os._exit once their "
+                             "checkpoint is written (atexit handlers still "
+                             "run; interpreter/torch teardown is skipped)")
+    parser.add_argument("--preload", default="",
+                        help="with --standby: extra modules to import ahead "
+                             "of time, comma-separated")
     parser.add_argument("script", nargs=argparse.REMAINDER)
     args = parser.parse_args(argv)
     logging.basicConfig(level=logging.INFO)
@@ -328,7 +440,11 @@ def main(argv=None):
     if args.trace_rescale:
         trace_dir = tempfile.mkdtemp(prefix="adaptdl-b200-rescale-trace-")
         extra_env["ADAPTDL_B200_RESCALE_TRACE"] = trace_dir
-    job = LocalElasticJob(command, gpus, args.checkpoint_dir, env=extra_env)
+    if args.fast_exit:
+        extra_env["ADAPTDL_B200_FAST_EXIT"] = "1"
+    job = LocalElasticJob(command, gpus, args.checkpoint_dir, env=extra_env,
+                          standby=args.standby,
+                          preload=[m for m in args.preload.split(",") if m])
     schedule = [int(x) for x in args.schedule.split(",") if x]
     state = job.run(schedule, args.interval, args.adaptive,
                     stop_after=args.stop_after)

@@ -38,6 +38,29 @@ LOG = logging.getLogger(__name__)
 EXIT_CODE_PREEMPTED = 143     # the contract with the job controller
 
 
+def _leave_preempted():
+    """The checkpoint is on disk: exit with the preemption code.
+
+    ``ADAPTDL_B200_FAST_EXIT=1`` (set by ``sched.local --fast-exit``) skips
+    the interpreter's and torch's own teardown -- module destructors, process
+    group and CUDA context destruction: 0.7 s of a CPU replica's 1.2 s exit,
+    more with a CUDA context -- after running the registered ``atexit``
+    handlers and flushing the standard streams; the next generation cannot
+    start before every replica of this one is gone."""
+    from adaptdl_b200.utils import rescale_trace
+    rescale_trace.mark("exiting")
+    if os.environ.get("ADAPTDL_B200_FAST_EXIT") == "1":
+        import atexit
+        try:
+            atexit._run_exitfuncs()
+            logging.shutdown()
+            sys.stdout.flush()
+            sys.stderr.flush()
+        finally:
+            os._exit(EXIT_CODE_PREEMPTED)
+    sys.exit(EXIT_CODE_PREEMPTED)
+
+
 class _PreemptionBeat(object):
     """Exit-flag consensus of the replicas, off the step path.
 
@@ -111,8 +134,7 @@ class _PreemptionBeat(object):
                 rescale_trace.mark("exit_consensus")
                 checkpoint.save_all_states()
                 rescale_trace.mark("checkpoint_written")
-                rescale_trace.mark("exiting")
-                sys.exit(EXIT_CODE_PREEMPTED)
+                _leave_preempted()
             self.interval = 1 if self.relearn else agreed
         self.relearn = False
         # rank 0 is the left-most operand of the fold: its suggestion wins

@@ -21,16 +21,30 @@ import time
 
 _DIR = os.environ.get("ADAPTDL_B200_RESCALE_TRACE")
 _SEEN = set()
+_SUSPENDED = False
 
 
 def enabled():
     return bool(_DIR)
 
 
+def suspend():
+    """Stop recording (a warm standby interpreter is not a replica yet)."""
+    global _SUSPENDED
+    _SUSPENDED = True
+
+
+def resume():
+    """Start the life cycle afresh: the process has just become a replica."""
+    global _SUSPENDED
+    _SUSPENDED = False
+    _SEEN.clear()
+
+
 def mark(event, once=True, **fields):
     """Record ``event`` now (wall clock, comparable across processes of one
     host). ``once``: only the first occurrence per process is kept."""
-    if not _DIR:
+    if not _DIR or _SUSPENDED:
         return
     if once:
         if event in _SEEN:

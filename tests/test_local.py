@@ -92,6 +92,62 @@ def test_rescale_a_running_job_1_to_2_replicas(tmp_path):
                for name in os.listdir(str(tmp_path)))
 
 
+def test_rescale_through_warm_standbys(tmp_path):
+    """``standby=True``: the second generation's replicas are released warm
+    interpreters (no ``import torch`` on the critical path), they restore the
+    first generation's checkpoint, and the idle ones go away with the job."""
+    script = os.path.join(ROOT, "examples", "linear_regression", "main.py")
+    trace_dir = tmp_path / "rescale-trace"
+    env = {"PYTHONPATH": ROOT, "CUDA_VISIBLE_DEVICES": "",
+           "OMP_NUM_THREADS": "1", "ADAPTDL_B200_FAST_EXIT": "1",
+           "ADAPTDL_B200_RESCALE_TRACE": str(trace_dir)}
+    job = local.LocalElasticJob(
+        [sys.executable, script, "--epochs", "400", "--size", "4000"], 2,
+        checkpoint_dir=str(tmp_path), env=env, standby=True)
+    assert job.standby
+    state = job.run(schedule=[1, 2], interval=10.0, stop_after=24.0)
+    assert state in ("stopped", "finished")
+    started = [d for _, w, d in job.events if w == "started"]
+    assert [d["replicas"] for d in started[:2]] == [1, 2], job.events
+    assert started[0]["warm"] == 0 and started[1]["warm"] == 2, job.events
+    assert job.pool == []                      # drained on the way out
+    from adaptdl_b200.utils import rescale_trace
+    rows = rescale_trace.collect(str(trace_dir))
+    warm_up = [r for r in rows if r["event"] == "interpreter_up"
+               and r.get("standby")]
+    assert sorted(r["rank"] for r in warm_up) == [0, 1], warm_up
+    assert all(r["generation"] == 1 and r["replicas"] == 2 for r in warm_up)
+    phases = rescale_trace.summarize(rows)
+    assert "wrapper_ready->first_step_done" in phases[1], phases
+    # generation 1 wrote its own checkpoint on the way out: it had restored
+    # generation 0's (checkpoint-<n> only appears after a successful restore
+    # of checkpoint-<n-1> in a restarted job)
+    assert any(name == "checkpoint-1" for name in os.listdir(str(tmp_path))), \
+        os.listdir(str(tmp_path))
+
+
+def test_standby_leaves_quietly_when_not_needed():
+    import subprocess
+    proc = subprocess.Popen(
+        [sys.executable, "-m", "adaptdl_b200.sched.standby", "--",
+         "/nonexistent/script.py"], stdin=subprocess.PIPE,
+        env=dict(os.environ, PYTHONPATH=ROOT, CUDA_VISIBLE_DEVICES=""))
+    proc.stdin.close()
+    assert proc.wait(timeout=120) == 0
+
+
+def test_only_python_scripts_get_standbys(tmp_path):
+    job = local.LocalElasticJob(["/bin/sleep", "60"], 2,
+                                checkpoint_dir=str(tmp_path), standby=True)
+    try:
+        assert not job.standby
+        job.fill_pool()
+        assert job.pool == []
+    finally:
+        job.kill()
+        job.server.close()
+
+
 def test_two_jobs_share_a_box_under_the_pollux_policy(tmp_path):
     """The multi-job single-box scheduler: two elastic jobs, three "GPUs"
     (CPU/gloo processes here), Pollux decides who gets how many replicas;
