@@ -138,55 +138,135 @@ def identity_collate(batch):
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock and throttle reasons of one GPU, sampled ONLY while a timed
+    window is open (``begin`` ... ``end``). NVML in-process (every 10 ms;
+    a window of 20 ResNet steps is 40 ms, far too short for an
+    ``nvidia-smi`` start-up); if ``pynvml`` is unusable, one long-running
+    ``nvidia-smi -lms 50`` whose lines are kept while a window is open."""
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,"
              "clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
+    # nvmlClocksEventReason* bits
+    REASON_BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown",
+                   0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+                   0x80: "hw_power_brake_slowdown"}
+    PERIOD_S = 0.010
 
-    def __init__(self, enabled, gpu_index):
-        self.proc = None
-        self.gpu_index = gpu_index
-        if enabled:
-            try:
-                self.proc = subprocess.Popen(
-                    ["nvidia-smi", "--query-gpu=" + self.QUERY,
-                     "--format=csv,noheader,nounits", "-lms", "100",
-                     "-i", str(gpu_index)],
-                    stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
-                    text=True)
-            except OSError:
-                self.proc = None
+    def __init__(self, enabled, gpu_index, uuid=None):
+        import threading
+        self.rows = []               # (sm_mhz, sm_max_mhz, reasons)
+        self.source = None
+        self._open = False
+        self._halt = threading.Event()
+        self._thread = None
+        self._proc = None
+        if not enabled:
+            return
+        target = self._nvml(gpu_index, uuid) or self._smi(gpu_index)
+        if target is not None:
+            self._thread = threading.Thread(target=target, daemon=True)
+            self._thread.start()
 
-    def stop(self):
-        if self.proc is None:
-            return None
-        self.proc.terminate()
+    def _nvml(self, gpu_index, uuid):
         try:
-            out, _ = self.proc.communicate(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-            out, _ = self.proc.communicate()
-        sm, mx, reasons = [], [], set()
+            import pynvml
+            pynvml.nvmlInit()
+            handle = None
+            if uuid:
+                try:
+                    handle = pynvml.nvmlDeviceGetHandleByUUID(
+                        uuid if isinstance(uuid, bytes) else uuid.encode())
+                except Exception:  # noqa: BLE001
+                    handle = None
+            if handle is None:
+                handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(
+                handle, pynvml.NVML_CLOCK_SM))
+            reasons_fn = getattr(
+                pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            reasons_fn(handle)       # fail here, not in the thread
+        except Exception:  # noqa: BLE001
+            return None
+        self.source = "nvml"
+
+        def loop():
+            while not self._halt.wait(self.PERIOD_S):
+                if not self._open:
+                    continue
+                try:
+                    sm = float(pynvml.nvmlDeviceGetClockInfo(
+                        handle, pynvml.NVML_CLOCK_SM))
+                    mask = int(reasons_fn(handle))
+                except Exception:  # noqa: BLE001
+                    continue
+                if self._open:
+                    self.rows.append((sm, sm_max, frozenset(
+                        name for bit, name in self.REASON_BITS.items()
+                        if mask & bit)))
+        return loop
+
+    def _smi(self, gpu_index):
+        try:
+            self._proc = subprocess.Popen(
+                ["nvidia-smi", "--query-gpu=" + self.QUERY,
+                 "--format=csv,noheader,nounits", "-lms", "50",
+                 "-i", str(gpu_index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self._proc = None
+            return None
+        self.source = "nvidia-smi"
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
                  "sw_power_cap"]
-        for line in out.splitlines():
-            parts = [p.strip() for p in line.split(",")]
-            if len(parts) < 8:
-                continue
+
+        def loop():
+            for line in self._proc.stdout:
+                if self._halt.is_set():
+                    break
+                parts = [p.strip() for p in line.split(",")]
+                if len(parts) < 8 or not self._open:
+                    continue
+                try:
+                    sm, mx = float(parts[1]), float(parts[2])
+                except ValueError:
+                    continue
+                self.rows.append((sm, mx, frozenset(
+                    name for name, val in zip(names, parts[4:8])
+                    if val.lower().startswith("active"))))
+        return loop
+
+    def begin(self):
+        self._open = True
+
+    def end(self):
+        self._open = False
+
+    def close(self):
+        """Stop sampling; the summary of every sample taken inside a window
+        (``None`` without samples)."""
+        self._open = False
+        self._halt.set()
+        if self._proc is not None:
+            self._proc.terminate()
             try:
-                sm.append(float(parts[1]))
-                mx.append(float(parts[2]))
-            except ValueError:
-                continue
-            for name, val in zip(names, parts[4:8]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
+                self._proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self._proc.kill()
+        if self._thread is not None:
+            self._thread.join(timeout=5)
+        if not self.rows:
             return None
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx),
-                "reasons": sorted(reasons), "samples": len(sm)}
+        reasons = set()
+        for _, _, r in self.rows:
+            reasons |= r
+        return {"sm_mhz": statistics.median(r[0] for r in self.rows),
+                "sm_min_mhz": min(r[0] for r in self.rows),
+                "sm_max_mhz": max(r[1] for r in self.rows),
+                "reasons": sorted(reasons), "samples": len(self.rows),
+                "source": self.source}
 
 
 class SyntheticNCF(object):
@@ -450,7 +530,16 @@ def run_program(args, adl, device, rank, world, local_rank, workload,
         return net.reducer.launches + ops_launch_count() if own else 0
 
     todo = [Region(r) for r in regions]
-    clocks = None
+    gpu_uuid = None
+    if device.type == "cuda":
+        try:
+            gpu_uuid = "GPU-" + str(
+                torch.cuda.get_device_properties(device).uuid)
+        except Exception:  # noqa: BLE001 - older torch: index it is
+            gpu_uuid = None
+    sampler = ClockSampler(
+        sample_clocks and rank == 0 and device.type == "cuda", local_rank,
+        gpu_uuid)
     resident = None
     h2d_bytes = 0
     epochs = adl.remaining_epochs_until(10 ** 6)
@@ -463,14 +552,12 @@ def run_program(args, adl, device, rank, world, local_rank, workload,
         # autotuning, graph capture); later ones the recipe's minimum
         w = W if not region.ms else 3
         t_wall = ev0 = ev1 = None
-        sampler = None
         n0 = 0
         for step, batch in enumerate(loader):
             if step == w:
                 barrier()
-                sampler = ClockSampler(
-                    sample_clocks and rank == 0 and device.type == "cuda"
-                    and region.name == "device", local_rank)
+                if region.name == "device":
+                    sampler.begin()
                 if device.type == "cuda":
                     ev0 = torch.cuda.Event(enable_timing=True)
                     ev1 = torch.cuda.Event(enable_timing=True)
@@ -485,15 +572,11 @@ def run_program(args, adl, device, rank, world, local_rank, workload,
                 else:
                     ms = (time.perf_counter() - t_wall) * 1e3
                 wall_ms = (time.perf_counter() - t_wall) * 1e3
+                sampler.end()
                 barrier()
                 region.ms.append(ms)
                 region.wall_ms.append(wall_ms)
                 region.launches += launches_now() - n0
-                if sampler is not None:
-                    got = sampler.stop()
-                    if got and (clocks is None
-                                or got["samples"] > clocks["samples"]):
-                        clocks = got
                 break
             timed = step >= w
             if region.name == "e2e":
@@ -524,6 +607,7 @@ def run_program(args, adl, device, rank, world, local_rank, workload,
             region.target = max(1, min(args.max_windows, want))
     if device.type == "cuda":
         torch.cuda.synchronize()
+    clocks = sampler.close()
     assert bool(torch.isfinite(loss_host[:W + K]).all()), "non-finite loss"
 
     out = {"global_bsz": global_bsz, "clocks": clocks,

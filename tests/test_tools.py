@@ -148,3 +148,57 @@ def test_bench_contract_two_ranks_on_cpu(tmp_path):
     assert set(out["config"]) == {"workload", "model", "global_batch",
                                   "local_batch", "seq_len", "parallelism",
                                   "optimizer", "adaptive", "compute", "l2"}
+
+
+def test_bench_clock_sampler_only_keeps_samples_inside_windows(monkeypatch):
+    """The sampler polls NVML in-process and keeps a row only while a timed
+    window is open (a 40 ms window is too short for an ``nvidia-smi``
+    start-up: the N=8 headline run of round 2 came back without clocks)."""
+    import importlib.util
+    import os
+    import sys
+    import time
+    import types
+    fake = types.ModuleType("pynvml")
+    fake.NVML_CLOCK_SM = 1
+    fake.calls = 0
+    fake.nvmlInit = lambda: None
+    fake.nvmlDeviceGetHandleByIndex = lambda i: ("gpu", i)
+
+    def by_uuid(uuid):
+        raise RuntimeError("unknown uuid")
+    fake.nvmlDeviceGetHandleByUUID = by_uuid
+    fake.nvmlDeviceGetMaxClockInfo = lambda h, kind: 1965
+
+    def clock(h, kind):
+        fake.calls += 1
+        return 1950
+    fake.nvmlDeviceGetClockInfo = clock
+    fake.nvmlDeviceGetCurrentClocksEventReasons = lambda h: 0x4 | 0x1
+    monkeypatch.setitem(sys.modules, "pynvml", fake)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location(
+        "bench_under_test", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+
+    idle = bench.ClockSampler(False, 0)
+    idle.begin()
+    idle.end()
+    assert idle.close() is None
+
+    sampler = bench.ClockSampler(True, 3, "GPU-not-there")
+    assert sampler.source == "nvml"
+    time.sleep(0.05)
+    assert sampler.rows == [] and fake.calls == 0     # no window open yet
+    sampler.begin()
+    time.sleep(0.12)
+    sampler.end()
+    kept = len(sampler.rows)
+    assert kept >= 3
+    time.sleep(0.05)
+    assert len(sampler.rows) == kept                  # closed window
+    got = sampler.close()
+    assert got["samples"] == kept and got["source"] == "nvml"
+    assert got["sm_mhz"] == 1950 and got["sm_max_mhz"] == 1965
+    assert got["reasons"] == ["sw_power_cap"]         # gpu_idle bit ignored
