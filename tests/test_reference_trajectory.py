@@ -1,0 +1,109 @@
+"""Adaptive-training trajectories against the unmodified reference package.
+
+The same deterministic 2-replica job (``tests/trajectory_job.py``) runs under
+``baseline/_ref`` and under this framework: data partitioning, gradient-noise
+statistics, gain, scaled learning rates and the parameters themselves must
+follow the reference step by step (CPU, gloo, host estimator = the semantics
+the device estimator is validated against on GPUs).
+"""
+
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+from adaptdl_b200.utils import pick_unused_port
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "baseline", "_ref")
+JOB = os.path.join(ROOT, "tests", "trajectory_job.py")
+
+pytestmark = pytest.mark.skipif(
+    not os.path.isdir(os.path.join(REF, "adaptdl")),
+    reason="reference package not installed (baseline/install_reference.sh)")
+
+
+def _run(impl, replicas, workdir, *job_args):
+    base = {k: v for k, v in os.environ.items()
+            if not k.startswith("ADAPTDL_") and k != "PYTHONPATH"}
+    if impl == "reference":
+        path = [REF, os.path.join(ROOT, "baseline", "shims")]
+        base["TORCH_FORCE_NO_WEIGHTS_ONLY_LOAD"] = "1"
+    else:
+        path = [ROOT]
+    port = pick_unused_port()
+    procs = []
+    for rank in range(replicas):
+        env = dict(base, PYTHONPATH=os.pathsep.join(path),
+                   OMP_NUM_THREADS="1", CUDA_VISIBLE_DEVICES="",
+                   ADAPTDL_MASTER_ADDR="127.0.0.1",
+                   ADAPTDL_MASTER_PORT=str(port),
+                   ADAPTDL_NUM_REPLICAS=str(replicas),
+                   ADAPTDL_REPLICA_RANK=str(rank),
+                   ADAPTDL_NUM_NODES="1")
+        procs.append(subprocess.Popen(
+            [sys.executable, JOB] + list(job_args), env=env,
+            stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+            cwd=str(workdir)))
+    outs = [p.communicate(timeout=300) for p in procs]
+    for p, (_, err) in zip(procs, outs):
+        assert p.returncode == 0, err[-3000:]
+    return [json.loads(line[len("STATE "):])
+            for line in outs[0][0].splitlines() if line.startswith("STATE ")]
+
+
+def _compare(ours, theirs, rtol):
+    assert len(ours) == len(theirs) > 0
+    for a, b in zip(ours, theirs):
+        where = "step {}: own {} reference {}".format(a["step"], a, b)
+        assert a["first"] == pytest.approx(b["first"]), where   # same data
+        for key in ("bsz", "local_bsz", "accum"):
+            assert a[key] == b[key], where
+        for key in ("loss", "sqr_avg", "var_avg", "progress"):
+            assert a[key] == pytest.approx(b[key], rel=rtol, abs=1e-7), \
+                (key, where)
+        assert a["lr"] == pytest.approx(b["lr"], rel=rtol), where
+        assert a["params"] == pytest.approx(b["params"], rel=rtol,
+                                            abs=1e-6), where
+    # ``net.gain``: the reference refreshes the attribute in a backward
+    # callback that runs BEFORE this step's statistics are folded in, so it
+    # shows the gain of the previous step (the gain actually applied to the
+    # learning rate and to the progress counter is the current one in both:
+    # parameters and progress agree above). Here the attribute is current.
+    for mine, later in zip(ours, theirs[1:]):
+        assert mine["gain"] == pytest.approx(later["gain"], rel=rtol), \
+            (mine, later)
+
+
+# a batch size the replicas cannot split evenly: ceil(9 / 4) = 3 per replica,
+# 12 in total, i.e. a batch-size scale of 4/3 without any (timing-dependent)
+# batch-size autoscaling -- gain and learning-rate factors leave 1.0
+UNEVEN = ("--batch-size", "9")
+
+
+@pytest.mark.parametrize("replicas,args", [
+    (4, ("--rule", "adascale") + UNEVEN),
+    (2, ("--rule", "adascale")),
+    (1, ("--rule", "adascale")),                 # differenced estimator
+    # AdamW with the default rule (AdamScale learning-rate scaling on plain
+    # statistics: what the BERT and NCF examples get). An explicit
+    # ``AdamScale()`` cannot be compared: the reference's preconditioned
+    # path resets Adam's state with an integer ``step``, which torch >= 2.x
+    # rejects ("state_steps must contain singleton tensors"); that path of
+    # this framework is covered by tests/test_gns_scaling.py and, on GPUs,
+    # against its own host implementation
+    (4, ("--rule", "default", "--optimizer", "adamw") + UNEVEN),
+    (4, ("--rule", "sqrt") + UNEVEN),
+], ids=["adascale-4-uneven", "adascale-2", "adascale-1",
+        "adamw-default-4-uneven", "sqrt-4-uneven"])
+def test_trajectory_follows_the_reference(tmp_path, replicas, args):
+    theirs = _run("reference", replicas, tmp_path, "--steps", "40", *args)
+    ours = _run("own", replicas, tmp_path, "--steps", "40", *args)
+    assert theirs[0]["impl"] == "adaptdl" and ours[0]["impl"] == "adaptdl_b200"
+    if UNEVEN[1] in args:
+        assert theirs[0]["bsz"] == 12
+        if "sqrt" not in args:
+            assert any(row["gain"] > 1.001 for row in theirs[5:]), theirs[-1]
+    _compare(ours, theirs, rtol=2e-4)
