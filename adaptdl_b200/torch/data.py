@@ -149,10 +149,14 @@ _PREEMPTION = _PreemptionBeat()
 
 
 def _shuffle_seed(epoch, pass_index):
-    # Explicit integer mix (the reference seeds with Python's hash() of a
-    # tuple, which is an implementation detail of CPython).
-    return (int(epoch) * 0x9E3779B1 + int(pass_index) * 0x85EBCA77
-            + 0x5BD1E995) & 0x7FFFFFFFFFFFFFFF
+    # Compatibility point, not a design choice: the reference seeds the
+    # permutation with CPython's hash of the (epoch, pass) tuple
+    # (``torch/data.py:74``). Using the same number means a job preempted
+    # mid-epoch under the reference and resumed here (or the other way round)
+    # continues on exactly the samples that were left
+    # (tests/test_reference_interop.py). Tuples of ints hash independently of
+    # PYTHONHASHSEED.
+    return hash((epoch, pass_index))
 
 
 class ElasticSampler(Sampler):

@@ -33,7 +33,7 @@ def main():
     features = torch.randn(192, 8)
     targets = features @ torch.arange(8.0).unsqueeze(1) + 0.5
     dataset = torch.utils.data.TensorDataset(features, targets)
-    loader = adl.AdaptiveDataLoader(dataset, batch_size=16, shuffle=False,
+    loader = adl.AdaptiveDataLoader(dataset, batch_size=16, shuffle=True,
                                     drop_last=True)
     model = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.Tanh(),
                                 torch.nn.Linear(16, 1))

@@ -85,7 +85,7 @@ UNEVEN = ("--batch-size", "9")
 
 @pytest.mark.parametrize("replicas,args", [
     (4, ("--rule", "adascale") + UNEVEN),
-    (2, ("--rule", "adascale")),
+    (2, ("--rule", "adascale", "--shuffle")),    # same permutations too
     (1, ("--rule", "adascale")),                 # differenced estimator
     # AdamW with the default rule (AdamScale learning-rate scaling on plain
     # statistics: what the BERT and NCF examples get). An explicit
@@ -96,11 +96,12 @@ UNEVEN = ("--batch-size", "9")
     # against its own host implementation
     (4, ("--rule", "default", "--optimizer", "adamw") + UNEVEN),
     (4, ("--rule", "sqrt") + UNEVEN),
-], ids=["adascale-4-uneven", "adascale-2", "adascale-1",
+], ids=["adascale-4-uneven", "adascale-2-shuffled", "adascale-1",
         "adamw-default-4-uneven", "sqrt-4-uneven"])
 def test_trajectory_follows_the_reference(tmp_path, replicas, args):
-    theirs = _run("reference", replicas, tmp_path, "--steps", "40", *args)
-    ours = _run("own", replicas, tmp_path, "--steps", "40", *args)
+    # 70 steps of 64 samples cross an epoch boundary of the 4096-sample set
+    theirs = _run("reference", replicas, tmp_path, "--steps", "70", *args)
+    ours = _run("own", replicas, tmp_path, "--steps", "70", *args)
     assert theirs[0]["impl"] == "adaptdl" and ours[0]["impl"] == "adaptdl_b200"
     if UNEVEN[1] in args:
         assert theirs[0]["bsz"] == 12

@@ -14,6 +14,7 @@ def main():
     parser.add_argument("--optimizer", default="sgd")
     parser.add_argument("--batch-size", type=int, default=64)
     parser.add_argument("--accumulation", action="store_true")
+    parser.add_argument("--shuffle", action="store_true")
     parser.add_argument("--autoscale", action="store_true")
     args = parser.parse_args()
 
@@ -35,7 +36,7 @@ def main():
     targets = features @ weights + 0.3 * torch.randn(4096, 1)
     dataset = torch.utils.data.TensorDataset(features, targets)
     loader = adl.AdaptiveDataLoader(dataset, batch_size=args.batch_size,
-                                    shuffle=False,
+                                    shuffle=args.shuffle,
                                     drop_last=True)
     if args.autoscale:
         loader.autoscale_batch_size(
@@ -44,7 +45,7 @@ def main():
     model = torch.nn.Sequential(torch.nn.Linear(12, 24), torch.nn.ReLU(),
                                 torch.nn.Linear(24, 1))
     if args.optimizer == "sgd":
-        optimizer = torch.optim.SGD(model.parameters(), lr=0.05,
+        optimizer = torch.optim.SGD(model.parameters(), lr=0.01,
                                     momentum=0.9, weight_decay=1e-4)
     else:
         optimizer = torch.optim.AdamW(model.parameters(), lr=0.01)
