@@ -50,8 +50,12 @@ def _run(impl, replicas, workdir, *job_args):
     outs = [p.communicate(timeout=300) for p in procs]
     for p, (_, err) in zip(procs, outs):
         assert p.returncode == 0, err[-3000:]
-    return [json.loads(line[len("STATE "):])
+    rows = [json.loads(line[len("STATE "):])
             for line in outs[0][0].splitlines() if line.startswith("STATE ")]
+    rows[0]["epochs"] = [json.loads(line[len("EPOCH "):])
+                         for line in outs[0][0].splitlines()
+                         if line.startswith("EPOCH ")]
+    return rows
 
 
 def _compare(ours, theirs, rtol):
@@ -108,3 +112,11 @@ def test_trajectory_follows_the_reference(tmp_path, replicas, args):
         if "sqrt" not in args:
             assert any(row["gain"] > 1.001 for row in theirs[5:]), theirs[-1]
     _compare(ours, theirs, rtol=2e-4)
+    # Accumulator totals over all replicas at the end of the first epoch
+    mine, ref = ours[0]["epochs"], theirs[0]["epochs"]
+    assert len(mine) == len(ref)
+    if "--batch-size" not in args:          # 64 steps of 64 = one epoch
+        assert len(ref) == 1
+    for a, b in zip(mine, ref):
+        assert a["samples"] == b["samples"] and a["batches"] == b["batches"]
+        assert a["loss_sum"] == pytest.approx(b["loss_sum"], rel=2e-4)

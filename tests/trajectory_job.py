@@ -57,12 +57,16 @@ def main():
     net = adl.AdaptiveDataParallel(model, optimizer, scaling_rule=rule)
 
     steps = 0
+    stats = adl.Accumulator()
     for epoch in adl.remaining_epochs_until(1000):
         for x, y in loader:
             optimizer.zero_grad()
             loss = torch.nn.functional.mse_loss(net(x), y)
             loss.backward()
             optimizer.step()
+            stats["loss_sum"] += float(loss) * len(x)
+            stats["samples"] += len(x)
+            stats.update({"batches": 1})
             is_step = not args.accumulation or \
                 not loader._elastic.is_accum_step()
             if not is_step:
@@ -85,6 +89,11 @@ def main():
                     "first": float(x[0, 0])}), flush=True)
             if steps >= args.steps:
                 return 0
+        with stats.synchronized():
+            if rank == 0:
+                print("EPOCH " + json.dumps(dict(stats, epoch=epoch)),
+                      flush=True)
+            stats.clear()
     return 0
 
 
