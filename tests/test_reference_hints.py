@@ -93,8 +93,12 @@ def _run(impl, workdir, replicas=2):
 
 
 def test_discovery_and_hints_requests_match_the_reference(tmp_path):
-    theirs, their_grad = _run("reference", tmp_path)
-    ours, our_grad = _run("own", tmp_path)
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(2) as pool:          # the two arms side by side
+        theirs = pool.submit(_run, "reference", tmp_path)
+        ours = pool.submit(_run, "own", tmp_path)
+        (theirs, their_grad), (ours, our_grad) = theirs.result(), \
+            ours.result()
 
     def discover(requests):
         return sorted(path for method, path, _ in requests

@@ -62,12 +62,10 @@ def test_checkpoint_written_by_one_is_resumed_by_the_other(tmp_path, first,
     whole.mkdir()
     split.mkdir()
     # uninterrupted run of the first implementation: the trajectory to match
-    proc, ref_rows = _run(first, whole, 0, "--epochs", str(EPOCHS))
-    assert proc.returncode == 0, proc.stderr[-3000:]
-    expected = "adaptdl" if first == "reference" else "adaptdl_b200"
-    assert ref_rows[0]["impl"] == expected, ref_rows[0]
-    assert (REF in ref_rows[0]["file"]) == (first == "reference")
-
+    # (in the background while the preempted one runs)
+    from concurrent.futures import ThreadPoolExecutor
+    pool = ThreadPoolExecutor(1)
+    whole_run = pool.submit(_run, first, whole, 0, "--epochs", str(EPOCHS))
     # same job, preempted early in epoch 1 (12 steps per epoch). The
     # reference checkpoints at the very next iteration; this framework agrees
     # on the iteration through its ~0.1 s consensus beat, i.e. some (tiny,
@@ -85,6 +83,12 @@ def test_checkpoint_written_by_one_is_resumed_by_the_other(tmp_path, first,
     # ... and resumed by the OTHER implementation
     proc, b_rows = _run(second, split, 1, "--epochs", str(EPOCHS))
     assert proc.returncode == 0, proc.stderr[-3000:]
+    whole_proc, ref_rows = whole_run.result()
+    pool.shutdown()
+    assert whole_proc.returncode == 0, whole_proc.stderr[-3000:]
+    expected = "adaptdl" if first == "reference" else "adaptdl_b200"
+    assert ref_rows[0]["impl"] == expected, ref_rows[0]
+    assert (REF in ref_rows[0]["file"]) == (first == "reference")
     start = b_rows[0]
     assert start["impl"] != a_rows[0]["impl"]
     assert _close(start["params"], saved["params"]), (start, saved)

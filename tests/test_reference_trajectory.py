@@ -104,8 +104,13 @@ UNEVEN = ("--batch-size", "9")
         "adamw-default-4-uneven", "sqrt-4-uneven"])
 def test_trajectory_follows_the_reference(tmp_path, replicas, args):
     # 70 steps of 64 samples cross an epoch boundary of the 4096-sample set
-    theirs = _run("reference", replicas, tmp_path, "--steps", "70", *args)
-    ours = _run("own", replicas, tmp_path, "--steps", "70", *args)
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(2) as pool:          # the two arms side by side
+        theirs = pool.submit(_run, "reference", replicas, tmp_path,
+                             "--steps", "70", *args)
+        ours = pool.submit(_run, "own", replicas, tmp_path,
+                           "--steps", "70", *args)
+        theirs, ours = theirs.result(), ours.result()
     assert theirs[0]["impl"] == "adaptdl" and ours[0]["impl"] == "adaptdl_b200"
     if UNEVEN[1] in args:
         assert theirs[0]["bsz"] == 12
