@@ -162,6 +162,8 @@ class ClockSampler(object):
         self._halt = threading.Event()
         self._thread = None
         self._proc = None
+        self._read_once = None
+        self._rows_at_begin = 0
         if not enabled:
             return
         target = self._nvml(gpu_index, uuid) or self._smi(gpu_index)
@@ -192,20 +194,25 @@ class ClockSampler(object):
             return None
         self.source = "nvml"
 
+        def read_once():
+            try:
+                sm = float(pynvml.nvmlDeviceGetClockInfo(
+                    handle, pynvml.NVML_CLOCK_SM))
+                mask = int(reasons_fn(handle))
+            except Exception:  # noqa: BLE001
+                return None
+            return (sm, sm_max, frozenset(
+                name for bit, name in self.REASON_BITS.items()
+                if mask & bit))
+        self._read_once = read_once
+
         def loop():
             while not self._halt.wait(self.PERIOD_S):
                 if not self._open:
                     continue
-                try:
-                    sm = float(pynvml.nvmlDeviceGetClockInfo(
-                        handle, pynvml.NVML_CLOCK_SM))
-                    mask = int(reasons_fn(handle))
-                except Exception:  # noqa: BLE001
-                    continue
-                if self._open:
-                    self.rows.append((sm, sm_max, frozenset(
-                        name for bit, name in self.REASON_BITS.items()
-                        if mask & bit)))
+                row = read_once()
+                if row is not None and self._open:
+                    self.rows.append(row)
         return loop
 
     def _smi(self, gpu_index):
@@ -239,7 +246,18 @@ class ClockSampler(object):
         return loop
 
     def begin(self):
+        self._rows_at_begin = len(self.rows)
         self._open = True
+
+    def poke(self):
+        """Called by the timing loop in the middle of a window: if the
+        sampling thread has not been scheduled since ``begin`` (a window can
+        be as short as 40 ms), read the clocks once from this thread."""
+        if self._open and self._read_once is not None and \
+                len(self.rows) == self._rows_at_begin:
+            row = self._read_once()
+            if row is not None:
+                self.rows.append(row)
 
     def end(self):
         self._open = False
@@ -564,6 +582,8 @@ def run_program(args, adl, device, rank, world, local_rank, workload,
                     ev0.record()
                 t_wall = time.perf_counter()
                 n0 = launches_now()
+            if step == w + K // 2:
+                sampler.poke()
             if step == w + K:
                 if device.type == "cuda":
                     ev1.record()

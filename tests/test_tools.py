@@ -202,3 +202,15 @@ def test_bench_clock_sampler_only_keeps_samples_inside_windows(monkeypatch):
     assert got["samples"] == kept and got["source"] == "nvml"
     assert got["sm_mhz"] == 1950 and got["sm_max_mhz"] == 1965
     assert got["reasons"] == ["sw_power_cap"]         # gpu_idle bit ignored
+
+    # a window the sampling thread never got to: the timing loop's mid-window
+    # poke reads the clocks once itself; a second poke adds nothing
+    monkeypatch.setattr(bench.ClockSampler, "PERIOD_S", 60.0)
+    sampler = bench.ClockSampler(True, 0)
+    sampler.begin()
+    sampler.poke()
+    sampler.poke()
+    sampler.end()
+    sampler.poke()                                    # closed: ignored
+    assert len(sampler.rows) == 1
+    assert sampler.close()["samples"] == 1
