@@ -6,9 +6,12 @@ genetic search over job x node replica matrices, maximising the sum of
 dominant-share-scaled speedups and minimising the number of nodes used, with
 a restart penalty, warm start from the previous cycle, "virtual" nodes for
 cluster autoscaling and a utilisation band that picks the desired cluster
-size) -- but implemented on the small in-house NSGA-II in ``nsga2.py`` rather
-than on pymoo, with the problem's operators written against this module's
-own state layout.
+size) -- but implemented on an in-house NSGA-II rather than on pymoo, with
+the problem's operators written against this module's own state layout. The
+search exists twice: vectorised numpy (``nsga2.py`` + the operators of
+``ClusterProblem`` below, the executable specification) and the C++ core
+``csrc/host/adl_pollux.cpp`` (``native.py``), which is what runs when the
+host library can be built or loaded.
 
 State layout: ``states[p, j, n]`` = replicas of job ``j`` on node ``n`` in
 candidate ``p``. Nodes ``[0, N)`` are the real nodes (non-preemptible first),
@@ -19,9 +22,11 @@ cluster were bigger").
 import collections
 import copy
 import logging
+import os
 
 import numpy as np
 
+from adaptdl_b200.sched.policy import native as native_search
 from adaptdl_b200.sched.policy import nsga2
 
 LOG = logging.getLogger(__name__)
@@ -248,10 +253,19 @@ class ClusterProblem(object):
 
 class PolluxPolicy(object):
 
-    def __init__(self, pop_size=POP_SIZE, generations=GENERATIONS, seed=None):
+    def __init__(self, pop_size=POP_SIZE, generations=GENERATIONS, seed=None,
+                 native=None):
+        """``native``: run the search on the C++ core
+        (``csrc/host/adl_pollux.cpp``, ~20x faster at cluster scale) rather
+        than on numpy. ``None`` = when it can be loaded, unless
+        ``ADAPTDL_B200_NATIVE_POLICY=0``."""
         self._pop_size = pop_size
         self._generations = generations
         self._rng = np.random.default_rng(seed)
+        if native is None:
+            native = os.environ.get("ADAPTDL_B200_NATIVE_POLICY", "1") != "0"
+        self._native = bool(native) and native_search.available()
+        self._grow = os.environ.get("ADAPTDL_B200_POLICY_GROW", "1") != "0"
         self._prev_states = None
         self._prev_jobs = None
         self._prev_nodes = None
@@ -290,12 +304,11 @@ class PolluxPolicy(object):
     @staticmethod
     def _state_to_allocations(state, jobs, nodes):
         node_keys = list(nodes)
-        out = {}
-        for j, key in enumerate(jobs):
-            placement = []
-            for n, node in enumerate(node_keys):
-                placement.extend([node] * int(state[j, n]))
-            out[key] = placement
+        out = {key: [] for key in jobs}
+        job_keys = list(jobs)
+        rows, cols = np.nonzero(state)        # row-major: nodes in order
+        for j, n in zip(rows.tolist(), cols.tolist()):
+            out[job_keys[j]].extend([node_keys[n]] * int(state[j, n]))
         return out
 
     def _warm_start(self, jobs, nodes):
@@ -304,7 +317,7 @@ class PolluxPolicy(object):
         prev = self._prev_states
         P = prev.shape[0]
         N = len(nodes)
-        out = np.zeros((P, len(jobs), 2 * N), dtype=np.int64)
+        out = np.zeros((P, len(jobs), 2 * N), dtype=STATE_DTYPE)
         prev_job = {key: i for i, key in enumerate(self._prev_jobs)}
         src_rows = [prev_job[k] for k in jobs if k in prev_job]
         dst_rows = [i for i, k in enumerate(jobs) if k in prev_job]
@@ -313,8 +326,10 @@ class PolluxPolicy(object):
         prev_node = {key: i for i, key in enumerate(self._prev_nodes)}
         spare = len(self._prev_nodes)         # next unused virtual column
         width = prev.shape[2]
+        node_keys = list(nodes)
+        src_cols, dst_cols = [], []
         for col in range(2 * N):
-            key = list(nodes)[col] if col < N else None
+            key = node_keys[col] if col < N else None
             if key is not None and key in prev_node:
                 src = prev_node[key]
             elif spare < width:
@@ -322,7 +337,11 @@ class PolluxPolicy(object):
                 spare += 1
             else:
                 continue
-            out[:, dst_rows, col] = prev[:, src_rows, src]
+            src_cols.append(src)
+            dst_cols.append(col)
+        # one gather / scatter for the whole population
+        out[:, np.array(dst_rows)[:, None], np.array(dst_cols)[None, :]] = \
+            prev[:, np.array(src_rows)[:, None], np.array(src_cols)[None, :]]
         return out
 
     # -- choosing from the Pareto front -------------------------------------------
@@ -335,14 +354,28 @@ class PolluxPolicy(object):
         return int(np.argmin(np.where(ok, values[:, 0], 0.0)))
 
     def _desired_nodes(self, utilities, values, num_nodes):
+        """Cluster size whose utilisation sits closest to the middle of the
+        band, unless the best allocation on the present nodes is already
+        inside it. The search for that size only looks in the direction the
+        present utilisation points to: an over-used cluster never shrinks
+        and an under-used one never grows. (The reference compares every
+        size on the Pareto front, ``pollux.py:121-142``: with hundreds of
+        jobs a two-node candidate that happens to sit at 50 % wins against
+        the 80 % of the full cluster, and since the allocation is then
+        chosen within the desired size, a cycle evicts nearly every job --
+        seen at 1000 jobs x 256 nodes with ``tools/policy_bench.py``.)"""
         idx = self._best_within(values, num_nodes)
         if idx is not None and \
                 self._min_util <= utilities[idx] <= self._max_util:
             return num_nodes
+        grow = idx is not None and utilities[idx] > self._max_util
+        shrink = idx is not None and utilities[idx] < self._min_util
         target = (self._min_util + self._max_util) / 2
         best_util, best_nodes = np.inf, num_nodes
         for util, (_, size) in zip(utilities, values):
             if util < self._min_util:
+                continue
+            if (grow and size < num_nodes) or (shrink and size > num_nodes):
                 continue
             if np.isclose(util, best_util) and size > best_nodes:
                 best_nodes = size
@@ -387,9 +420,10 @@ class PolluxPolicy(object):
         problem = ClusterProblem(list(jobs.values()),
                                  list(nodes.values()) + [node_template] * N,
                                  base, rng=self._rng)
-        states, values = nsga2.minimize(problem, initial, self._pop_size,
-                                        self._generations, self._rng)
-        self._prev_states = states.copy()
+        search = native_search.minimize if self._native else nsga2.minimize
+        states, values = search(problem, initial, self._pop_size,
+                                self._generations, self._rng)
+        self._prev_states = states       # a fresh array: ours to keep
         self._prev_jobs = list(jobs)
         self._prev_nodes = list(nodes)
         front = nsga2.non_dominated_fronts(values)[0]
@@ -406,6 +440,10 @@ class PolluxPolicy(object):
         allocations = self._state_to_allocations(states[idx][:, :N], jobs,
                                                  nodes)
         self._place_starved(allocations, jobs, nodes)
+        if self._grow:
+            self._grow_into_idle(allocations, jobs, nodes, base_allocations,
+                                 list(nodes)[:min(N, desired)],
+                                 RESTART_PENALTY)
         return allocations, desired
 
     @staticmethod
@@ -440,6 +478,153 @@ class PolluxPolicy(object):
                         free[name][rtype] -= amount * want
                     in_use.add(name)
                     break
+
+    @staticmethod
+    def _grow_into_idle(allocations, jobs, nodes, base_allocations,
+                        usable_nodes, restart_penalty=RESTART_PENALTY):
+        """Hand idle capacity of the nodes the cycle may use to the jobs that
+        gain most from it, one replica at a time (lazy greedy on the marginal
+        gain of the search's own objective: speedup x dominant share, times
+        ``1 - restart_penalty`` for a job whose allocation differs from the
+        one it runs with).
+
+        The genetic search re-draws about two entries of EVERY job in every
+        child (the reference's mutation too, ``pollux.py:377-392``). With tens
+        of jobs that explores well; with hundreds, no child is a small step
+        away from a good allocation any more, the restart penalty on every
+        job outweighs what a few lucky re-draws win, and the search returns
+        its starting point with a third of the GPUs idle (1000 jobs x 256
+        nodes, ``tools/policy_bench.py``). This pass is the small-step
+        improvement the search cannot make at that scale; at small scale it
+        picks up the last idle GPUs. It never takes anything away, never
+        touches a pinned job, keeps a node to one multi-node job and stays
+        inside ``usable_nodes`` (the cluster size the cycle decided on)."""
+        import heapq
+        usable = [n for n in usable_nodes if n in nodes]
+        if not usable:
+            return
+        free = {key: dict(node.resources) for key, node in nodes.items()}
+        placed = {key: collections.Counter(allocations.get(key) or [])
+                  for key in jobs}
+        for key, count in placed.items():
+            for node, reps in count.items():
+                for rtype, amount in jobs[key].resources.items():
+                    free[node][rtype] = free[node].get(rtype, 0) - \
+                        amount * reps
+        # nodes that host a multi-node job (rule: at most one per node)
+        spread_on = {}
+        for key, count in placed.items():
+            if len(count) > 1:
+                for node in count:
+                    spread_on[node] = key
+        totals = collections.Counter()
+        for node in nodes.values():
+            totals.update(node.resources)
+        in_use = {node for count in placed.values() for node in count}
+
+        def weight(job):
+            return max((amount / totals[rtype]
+                        for rtype, amount in job.resources.items()
+                        if totals.get(rtype, 0) > 0), default=0.0)
+
+        def fits(job, node, reps=1):
+            return all(free[node].get(rtype, 0) >= amount * reps
+                       for rtype, amount in job.resources.items()
+                       if amount > 0)
+
+        def value(key, num_nodes, replicas, moved):
+            if replicas == 0:
+                return 0.0
+            speedup = float(jobs[key].speedup_fn(num_nodes, replicas))
+            return speedup * (1.0 - restart_penalty if moved else 1.0)
+
+        moved = {key: placed[key] != collections.Counter(
+                     base_allocations.get(key) or []) for key in jobs}
+        weights = {}
+
+        def is_moved(key):
+            return moved[key]
+
+        def proposal(key):
+            """Best single step for this job: ``(gain, node, replicas)``."""
+            job, count = jobs[key], placed[key]
+            replicas = sum(count.values())
+            if replicas == 0 or replicas >= job.max_replicas:
+                return None
+            if not job.preemptible and base_allocations.get(key):
+                return None                      # pinned
+            now = value(key, len(count), replicas, is_moved(key))
+            best = None
+            own = [n for n in count if fits(job, n)]
+            if own:
+                node = max(own, key=lambda n: count[n])
+                steps = [1]
+                if not is_moved(key):
+                    # a job that has not been disturbed yet pays the restart
+                    # penalty once: also look at the largest jump
+                    room = min((free[node].get(rtype, 0) // amount
+                                for rtype, amount in job.resources.items()
+                                if amount > 0), default=0)
+                    steps.append(min(room, job.max_replicas - replicas))
+                for reps in sorted(set(k for k in steps if k >= 1)):
+                    gain = value(key, len(count), replicas + reps, True) - now
+                    if best is None or gain > best[0]:
+                        best = (gain, node, reps)
+            else:
+                # a further node: neither end may break the one-multi-node-
+                # job-per-node rule
+                if any(spread_on.get(n, key) != key for n in count):
+                    return None
+                for node in sorted(usable, key=lambda n: n not in in_use):
+                    if node in count or node in spread_on or \
+                            not fits(job, node):
+                        continue
+                    gain = value(key, len(count) + 1, replicas + 1, True) - now
+                    best = (gain, node, 1)
+                    break
+            if best is None or best[0] <= 0:
+                return None
+            if key not in weights:
+                weights[key] = weight(job)
+            return (best[0] * weights[key], best[1], best[2])
+
+        heap = []
+        order = {key: i for i, key in enumerate(jobs)}
+        for key in jobs:
+            found = proposal(key)
+            if found:
+                heapq.heappush(heap, (-found[0], order[key], key, found[1],
+                                      found[2]))
+        while heap:
+            neg_gain, _, key, node, reps = heapq.heappop(heap)
+            fresh = proposal(key)
+            if fresh is None:
+                continue
+            if fresh[1] != node or fresh[2] != reps or \
+                    fresh[0] < -neg_gain - 1e-12:
+                # the node filled up meanwhile: queue the job's current best
+                heapq.heappush(heap, (-fresh[0], order[key], key, fresh[1],
+                                      fresh[2]))
+                continue
+            job, count = jobs[key], placed[key]
+            count[node] += reps
+            moved[key] = True
+            for rtype, amount in job.resources.items():
+                free[node][rtype] = free[node].get(rtype, 0) - amount * reps
+            in_use.add(node)
+            if len(count) > 1:
+                for n in count:
+                    spread_on[n] = key
+            again = proposal(key)
+            if again:
+                heapq.heappush(heap, (-again[0], order[key], key, again[1],
+                                      again[2]))
+        node_order = {key: i for i, key in enumerate(nodes)}
+        for key, count in placed.items():
+            if sum(count.values()) != len(allocations.get(key) or []):
+                allocations[key] = [
+                    node for node in sorted(count, key=node_order.get)
+                    for _ in range(count[node])]
 
 
 _ = copy

@@ -24,13 +24,16 @@ class BuildNative(Command):
         import sys
         sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
         from adaptdl_b200 import _native
-        print(_native.build(force=True))
+        from adaptdl_b200._native import host
+        print(host.build(force=True))        # g++ only (scheduler pods)
+        print(_native.build(force=True))     # nvcc, sm_100a
 
 
 class BuildPyWithCsrc(build_py):
-    """Installed packages carry the CUDA sources (``csrc/``) inside
-    ``adaptdl_b200/_native/csrc`` so ``adaptdl_b200._native.build()`` can
-    compile them on the target machine."""
+    """Installed packages carry the native sources (``csrc/``: CUDA, and
+    ``csrc/host``: plain C++) inside ``adaptdl_b200/_native/csrc`` so
+    ``adaptdl_b200._native.build()`` / ``_native.host.build()`` can compile
+    them on the target machine."""
 
     def run(self):
         super().run()
@@ -38,9 +41,12 @@ class BuildPyWithCsrc(build_py):
         target = os.path.join(self.build_lib, "adaptdl_b200", "_native",
                               "csrc")
         os.makedirs(target, exist_ok=True)
-        for name in sorted(os.listdir(os.path.join(here, "csrc"))):
-            if name.endswith((".cu", ".cuh", ".cpp", ".h")):
-                shutil.copy2(os.path.join(here, "csrc", name), target)
+        for sub in ("", "host"):
+            os.makedirs(os.path.join(target, sub), exist_ok=True)
+            for name in sorted(os.listdir(os.path.join(here, "csrc", sub))):
+                if name.endswith((".cu", ".cuh", ".cpp", ".h")):
+                    shutil.copy2(os.path.join(here, "csrc", sub, name),
+                                 os.path.join(target, sub))
 
 
 setuptools.setup(

@@ -1,5 +1,6 @@
 """Scheduling policy: NSGA-II, speedup memoisation, Pollux allocation
 invariants (ideas from the reference's policy/*_test.py)."""
+import collections
 import copy
 import random
 from collections import Counter
@@ -352,3 +353,72 @@ def test_non_dominated_sorting_properties():
                     assert np.isinf(dist[np.argmin(col)]) or \
                         np.isinf(dist).sum() >= 2
     check()
+
+
+def test_idle_capacity_goes_to_the_jobs_that_gain_most():
+    """The greedy pass after the search: one replica at a time to the best
+    marginal gain, inside the usable nodes, never breaking the rules."""
+    gpu = "nvidia.com/gpu"
+    nodes = collections.OrderedDict(
+        (name, NodeInfo({gpu: 4, "pods": 8}, False)) for name in "abcd")
+
+    def mk(t, fn, cap=8, lo=0, preemptible=True):
+        return JobInfo({gpu: 1, "pods": 1}, fn, t, lo, cap,
+                       preemptible=preemptible)
+    # crossing nodes costs: replicas / nodes ** 0.25
+    scal = lambda n, r: r / max(n, 1) ** 0.25 if r else 0.0      # noqa: E731
+    flat = lambda n, r: min(r, 2)                                # noqa: E731
+    jobs = collections.OrderedDict([
+        ("scales", mk(0, scal)),
+        ("flat", mk(1, flat)),                 # nothing to gain beyond 2
+        ("capped", mk(2, scal, cap=2)),
+        ("pinned", mk(3, scal, preemptible=False)),
+        ("waiting", mk(4, scal, cap=16, lo=9)),   # not running: left alone
+    ])
+    base = {"scales": ["a"], "flat": ["a", "a"], "capped": ["b", "b"],
+            "pinned": ["b"], "waiting": []}
+    alloc = {k: list(v) for k, v in base.items()}
+    PolluxPolicy._grow_into_idle(alloc, jobs, nodes, base, ["a", "b", "c"])
+    assert alloc["flat"] == ["a", "a"]
+    assert alloc["capped"] == ["b", "b"]
+    assert alloc["pinned"] == ["b"]
+    assert alloc["waiting"] == []
+    # "scales" takes the free GPU of its own node first, then the free GPU
+    # of "b" (nodes in use before empty ones), then all of "c"; "d" is not
+    # usable
+    assert Counter(alloc["scales"]) == Counter({"a": 2, "b": 1, "c": 4})
+    per_node = Counter()
+    for placement in alloc.values():
+        per_node.update(placement)
+    assert all(per_node[n] <= 4 for n in per_node)
+    # a second multi-node job may not share a node with the first one
+    jobs2 = collections.OrderedDict([("one", mk(0, scal)), ("two", mk(1, scal))])
+    base2 = {"one": ["a", "a", "b", "b"], "two": ["c", "c", "c", "c"]}
+    alloc2 = {k: list(v) for k, v in base2.items()}
+    PolluxPolicy._grow_into_idle(alloc2, jobs2, nodes, {}, list("abcd"))
+    spread = {k: set(v) for k, v in alloc2.items() if len(set(v)) > 1}
+    for node in nodes:
+        assert sum(node in s for s in spread.values()) <= 1
+    assert len(alloc2["one"]) == 8 and set(alloc2["one"]) == {"a", "b"}
+    assert Counter(alloc2["two"]) == Counter({"c": 4, "d": 4})
+
+
+def test_growth_respects_the_restart_penalty():
+    gpu = "nvidia.com/gpu"
+    nodes = collections.OrderedDict(
+        [("a", NodeInfo({gpu: 8, "pods": 8}, False))])
+    # 5 % per extra replica: not worth a restart one replica at a time, but
+    # four more at once are (1.2 x 0.9 > 1)
+    slow = lambda n, r: 1 + 0.05 * (r - 1) if r else 0.0         # noqa: E731
+    jobs = collections.OrderedDict(
+        [("j", JobInfo({gpu: 1, "pods": 1}, slow, 0, 0, 5))])
+    alloc = {"j": ["a"]}
+    PolluxPolicy._grow_into_idle(alloc, jobs, nodes, {"j": ["a"]}, ["a"])
+    assert alloc["j"] == ["a"] * 5
+    jobs["j"] = JobInfo({gpu: 1, "pods": 1}, slow, 0, 0, 2)
+    alloc = {"j": ["a"]}
+    PolluxPolicy._grow_into_idle(alloc, jobs, nodes, {"j": ["a"]}, ["a"])
+    assert alloc["j"] == ["a"]                  # 1.05 x 0.9 < 1: stays
+    alloc = {"j": ["a"]}                        # already being restarted
+    PolluxPolicy._grow_into_idle(alloc, jobs, nodes, {}, ["a"])
+    assert alloc["j"] == ["a", "a"]

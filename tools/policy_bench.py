@@ -11,6 +11,8 @@ scheduler is meant for. Jobs get randomised but realistic goodput models
 configuration runs ``--cycles`` warm-started cycles and reports the wall time
 of each, the GPUs allocated and the sum of speedups of the chosen allocation
 (the quantity the search maximises; useful to compare code versions).
+``--search both`` runs the C++ core and the numpy implementation on the same
+clusters.
 """
 import argparse
 import json
@@ -48,10 +50,10 @@ def make_cluster(num_jobs, num_nodes, gpus_per_node, seed):
     return jobs, nodes, NodeInfo(dict(resources), True)
 
 
-def run(num_jobs, num_nodes, gpus_per_node, cycles, seed):
+def run(num_jobs, num_nodes, gpus_per_node, cycles, seed, native=None):
     jobs, nodes, template = make_cluster(num_jobs, num_nodes, gpus_per_node,
                                          seed)
-    policy = PolluxPolicy(seed=seed)
+    policy = PolluxPolicy(seed=seed, native=native)
     previous, seconds = {}, []
     for _ in range(cycles):
         start = time.perf_counter()
@@ -67,6 +69,7 @@ def run(num_jobs, num_nodes, gpus_per_node, cycles, seed):
     value = sum(float(jobs[k].speedup_fn(len(set(a)), len(a)))
                 for k, a in allocations.items() if a)
     return {"jobs": num_jobs, "nodes": num_nodes,
+            "search": "native" if policy._native else "numpy",
             "gpus": num_nodes * gpus_per_node,
             "cycle_seconds": [round(s, 3) for s in seconds],
             "gpus_allocated": sum(per_node.values()),
@@ -81,15 +84,28 @@ def main():
     parser.add_argument("--gpus-per-node", type=int, default=8)
     parser.add_argument("--cycles", type=int, default=3)
     parser.add_argument("--seed", type=int, default=0)
+    parser.add_argument("--search", default="native",
+                        choices=["native", "numpy", "both"],
+                        help="C++ core (csrc/host/adl_pollux.cpp), the numpy "
+                             "implementation, or one after the other")
+    parser.add_argument("--numpy-max-jobs", type=int, default=200,
+                        help="with --search both: largest job count the "
+                             "numpy search is run on")
     parser.add_argument("--out")
     args = parser.parse_args()
     rows = []
     for size in args.sizes.split(","):
         num_jobs, num_nodes = (int(v) for v in size.split("x"))
-        row = run(num_jobs, num_nodes, args.gpus_per_node, args.cycles,
-                  args.seed)
-        rows.append(row)
-        print(json.dumps(row), flush=True)
+        flavours = {"native": [True], "numpy": [False],
+                    "both": [True, False]}[args.search]
+        for native in flavours:
+            if not native and args.search == "both" and \
+                    num_jobs > args.numpy_max_jobs:
+                continue
+            row = run(num_jobs, num_nodes, args.gpus_per_node, args.cycles,
+                      args.seed, native)
+            rows.append(row)
+            print(json.dumps(row), flush=True)
     if args.out:
         with open(args.out, "w") as f:
             json.dump({"config": vars(args), "cpu_count": os.cpu_count(),
