@@ -89,7 +89,7 @@ def main():
             steps += 1
             tokens += x.numel()          # this replica's share of the batch
             if steps == 1:
-                mark("first_step", epoch=epoch, loss=float(loss))
+                mark("first_step", epoch=epoch, loss=loss.item())
             elif steps % 10 == 0:
                 mark("progress", steps=steps, tokens=tokens)
         scheduler.step()
