@@ -92,8 +92,6 @@ def _bind(lib):
     lib.adl_pollux_create.argtypes = [
         c.c_int, c.c_int, c.c_int, p64, p64, p32, pu8, p32, p32, p32, p32,
         pf64, c.c_double, c.c_int, c.c_int, c.c_uint64, c.c_int]
-    lib.adl_pollux_set_row_rate.restype = None
-    lib.adl_pollux_set_row_rate.argtypes = [c.c_void_p, c.c_double]
     lib.adl_pollux_destroy.restype = None
     lib.adl_pollux_destroy.argtypes = [c.c_void_p]
     lib.adl_pollux_seed.restype = c.c_int

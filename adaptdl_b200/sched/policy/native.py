@@ -66,13 +66,6 @@ class NativeSearch(object):
             int(seed) & (2 ** 64 - 1), int(threads))
         if not self._handle:
             raise RuntimeError("adl_pollux_create rejected the problem")
-        rate = os.environ.get("ADAPTDL_B200_POLICY_ROW_RATE")
-        if rate is not None:
-            self._lib.adl_pollux_set_row_rate(
-                self._handle, min(1.0, float(rate) / max(J, 1)))
-        self._max_rep = max_rep
-        self._prefetch = os.environ.get(
-            "ADAPTDL_B200_POLICY_PREFETCH", "1") != "0"
         self.round_trips = 0
         self.entries_filled = 0
 
@@ -100,47 +93,24 @@ class NativeSearch(object):
             _ptr(nodes, ctypes.c_int32), _ptr(replicas, ctypes.c_int32),
             count)
         assert got == count
-        # The search walks through neighbouring allocations (one replica
-        # more or less, one node more): hand those back too, the goodput
-        # model prices a few more allocations of a job in the same
-        # vectorised call and the search comes back far less often.
-        jobs_out, nodes_out, reps_out, values_out = [], [], [], []
+        value = np.empty(count, dtype=np.float64)
         order = np.argsort(job, kind="stable")
         bounds = np.flatnonzero(np.diff(job[order])) + 1
         for idx in np.split(order, bounds):
-            j = int(job[idx[0]])
-            n = nodes[idx].astype(np.int64)
-            r = replicas[idx].astype(np.int64)
-            if self._prefetch:
-                n = np.concatenate([n, n, n, n + 1])
-                r = np.concatenate([r, r + 1, r - 1, r[:len(idx)] + 1])
-                cap = int(self._max_rep[j])
-                ok = (n >= 1) & (n <= r) & (r <= max(cap, 1)) & \
-                    (n <= self.shape[1])
-                ok[:len(idx)] = True          # what was asked for, always
-                pairs = np.unique(np.stack([n[ok], r[ok]]), axis=1)
-                n, r = pairs[0], pairs[1]
-            fn = self._problem.jobs[j].speedup_fn
+            fn = self._problem.jobs[int(job[idx[0]])].speedup_fn
             fn = getattr(fn, "lookup", fn)
-            v = np.broadcast_to(np.asarray(fn(n, r), dtype=np.float64),
-                                n.shape)
-            jobs_out.append(np.full(len(n), j, dtype=np.int32))
-            nodes_out.append(n.astype(np.int32))
-            reps_out.append(r.astype(np.int32))
-            values_out.append(v)
-        job = np.ascontiguousarray(np.concatenate(jobs_out))
-        nodes = np.ascontiguousarray(np.concatenate(nodes_out))
-        replicas = np.ascontiguousarray(np.concatenate(reps_out))
-        value = np.ascontiguousarray(np.nan_to_num(
-            np.concatenate(values_out), nan=0.0, posinf=0.0, neginf=0.0))
+            value[idx] = np.asarray(
+                fn(nodes[idx].astype(np.int64),
+                   replicas[idx].astype(np.int64)), dtype=np.float64)
+        value = np.nan_to_num(value, nan=0.0, posinf=0.0, neginf=0.0)
         rc = self._lib.adl_pollux_fill(
-            self._handle, len(job), _ptr(job, ctypes.c_int32),
+            self._handle, count, _ptr(job, ctypes.c_int32),
             _ptr(nodes, ctypes.c_int32), _ptr(replicas, ctypes.c_int32),
             _ptr(value, ctypes.c_double))
         if rc != 0:
             raise RuntimeError("adl_pollux_fill failed")
         self.round_trips += 1
-        self.entries_filled += len(job)
+        self.entries_filled += count
 
     def run(self):
         while True:

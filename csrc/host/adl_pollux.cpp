@@ -148,7 +148,6 @@ struct Search {
   std::vector<int32_t> min_fill, max_fit;              // [J][W]
   std::vector<double> weight;                          // [J] dominant share x W
   double restart_penalty;
-  double row_rate = 1.0;                               // probability that a mutation touches a given job
   int pop_size, n_gen, threads;
   uint64_t seed;
 
@@ -313,10 +312,6 @@ struct Search {
     const int limit = (int)std::min<uint64_t>((uint64_t)W, (uint64_t)size + 1 + rng.skips(0.5));
     for (int j = 0; j < J; ++j) {
       auto& row = w.rows[j];
-      if (row_rate < 1.0 && rng.uniform() >= row_rate) {   // this job is left alone
-        apply_floor(row, j);
-        continue;
-      }
       const int32_t* lo = min_fill.data() + (size_t)j * W;
       const int32_t* hi = max_fit.data() + (size_t)j * W;
       auto draw = [&](int c) {
@@ -641,10 +636,6 @@ void* adl_pollux_create(int J, int W, int R, const int64_t* job_res, const int64
     t.dense[0] = 0.0;                                  // nothing allocated
   }
   return s;
-}
-
-void adl_pollux_set_row_rate(void* h, double rate) {
-  static_cast<Search*>(h)->row_rate = rate < 0 ? 0.0 : (rate > 1 ? 1.0 : rate);
 }
 
 void adl_pollux_destroy(void* h) { delete static_cast<Search*>(h); }
