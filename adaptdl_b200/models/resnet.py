@@ -10,8 +10,6 @@ names and shapes are those of the plain ``nn.BatchNorm2d`` model, so state
 dicts are interchangeable.
 """
 
-import os
-
 import torch
 import torch.nn as nn
 import torch.nn.functional as F

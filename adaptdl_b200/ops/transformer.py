@@ -24,7 +24,6 @@ the same data movement with 16-byte vectors and coalesced accesses:
 All have pure-PyTorch fallbacks (CPU, unsupported shapes / dtypes).
 """
 
-import ctypes
 import os
 
 import torch

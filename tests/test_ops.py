@@ -6,7 +6,6 @@ same signature, state-dict layout and numerics as the modules it replaces
 
 import io
 
-import pytest
 
 import torch
 import torch.nn.functional as F
