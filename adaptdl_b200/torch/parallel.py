@@ -13,6 +13,7 @@ running. On CPU (gloo) the same control flow runs on stock torch ops.
 
 import contextlib
 import logging
+import os
 import warnings
 from typing import Optional
 
@@ -362,6 +363,48 @@ def mixed_precision_params(model, dtype=torch.bfloat16, min_dim=2):
     return model
 
 
+def _save_fast(obj, fileobj):
+    """``torch.save`` without the per-record CRC-32. The zip writer's
+    checksum runs at 0.4-1 GB/s on one core and is most of the time a
+    checkpoint of a large model takes (1.36 GB of model + AdamW state:
+    1.2-3.2 s with, 0.55 s without; ``profiles/r2_elastic/README.md``), on the
+    path where a preempted job races its grace period. Nothing reads the
+    checksum back (``torch.load`` does not verify it), and the file stays an
+    ordinary ``torch.save`` file for the reference and for older
+    checkpoints' readers."""
+    get = getattr(torch.serialization, "get_crc32_options", None)
+    put = getattr(torch.serialization, "set_crc32_options", None)
+    if get is None or put is None or \
+            os.environ.get("ADAPTDL_B200_CHECKPOINT_CRC", "0") == "1":
+        torch.save(obj, fileobj)
+        return
+    previous = get()
+    put(False)
+    try:
+        torch.save(obj, fileobj)
+    finally:
+        put(previous)
+
+
+def _load_fast(fileobj):
+    """``torch.load`` of a data-parallel state, memory-mapped when the file
+    object is a real file: tensors are not read into fresh host memory first
+    (2.1 s + 2.3 s of page faults and copies for 1.36 GB against 0.1 s +
+    0.4 s), every replica of a node shares the same page-cache pages instead
+    of holding its own copy, and ``load_state_dict`` moves them straight to
+    the device. ``weights_only=False``: the numpy arrays inside
+    ``optimizer.state["gns"]`` need full unpickling."""
+    path = getattr(fileobj, "name", None)
+    if isinstance(path, str) and os.path.isfile(path) and \
+            os.environ.get("ADAPTDL_B200_CHECKPOINT_MMAP", "1") != "0":
+        try:
+            return torch.load(path, map_location="cpu", weights_only=False,
+                              mmap=True)
+        except (RuntimeError, ValueError, TypeError, OSError):
+            fileobj.seek(0)          # legacy (non-zip) file, odd filesystem
+    return torch.load(fileobj, map_location="cpu", weights_only=False)
+
+
 class _AdaptiveDataParallelState(checkpoint.State):
     """``torch.save(([model_sd, optim_sd, sched_sd|None, scaler_sd|None],
     gain, lr_factor))`` -- the reference's layout (App. B); the GNS running
@@ -404,12 +447,10 @@ class _AdaptiveDataParallelState(checkpoint.State):
                 # masters + optimizer state of bf16/fp16 parameters, which
                 # Optimizer.load_state_dict would round to the param dtype
                 state_dicts.append(wide)
-        torch.save((state_dicts, self.gain, self.lr_factor), fileobj)
+        _save_fast((state_dicts, self.gain, self.lr_factor), fileobj)
 
     def load(self, fileobj):
-        # numpy arrays inside optimizer.state["gns"] need full unpickling
-        state_dicts, self.gain, self.lr_factor = torch.load(
-            fileobj, map_location="cpu", weights_only=False)
+        state_dicts, self.gain, self.lr_factor = _load_fast(fileobj)
         self.model.load_state_dict(state_dicts[0])
         self.optimizer.load_state_dict(state_dicts[1])
         if state_dicts[2] is not None and self.lr_scheduler is not None:

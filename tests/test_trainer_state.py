@@ -623,3 +623,59 @@ def test_accumulator_checkpoint_layout_and_delta_protocol(tmp_path):
     finally:
         collective.teardown()
         acc_mod._reset_for_tests()
+
+
+def test_data_parallel_state_file_is_fast_and_still_plain_torch(tmp_path):
+    """The model/optimizer state is written without zip CRCs and read back
+    memory-mapped; the file is still something a plain ``torch.load`` (what
+    the reference calls) understands, and file objects without a path fall
+    back to ordinary reading."""
+    import io
+    import zipfile
+    from adaptdl_b200.torch import parallel
+    payload = ([{"w": torch.arange(12.0).reshape(3, 4)},
+                {"state": {"gns": {"progress": 1.5}}}, None, None], 1.25, 0.5)
+    path = tmp_path / "adaptdl-dataparallel"
+    with open(path, "wb") as f:
+        parallel._save_fast(payload, f)
+    # an ordinary torch.save archive (CRC fields are simply left empty)
+    with zipfile.ZipFile(path) as z:
+        assert any(n.endswith("data.pkl") for n in z.namelist())
+    plain = torch.load(str(path), weights_only=False)
+    assert plain[1:] == (1.25, 0.5)
+    assert torch.equal(plain[0][0]["w"], payload[0][0]["w"])
+    with open(path, "rb") as f:
+        mapped = parallel._load_fast(f)
+    assert mapped[1:] == (1.25, 0.5)
+    assert torch.equal(mapped[0][0]["w"], payload[0][0]["w"])
+    assert mapped[0][1]["state"]["gns"]["progress"] == 1.5
+    # an in-memory file object: no path to map
+    buf = io.BytesIO(path.read_bytes())
+    again = parallel._load_fast(buf)
+    assert torch.equal(again[0][0]["w"], payload[0][0]["w"])
+    # the process-wide CRC option is left as it was found
+    get = getattr(torch.serialization, "get_crc32_options", None)
+    if get is not None:
+        assert get() is True
+
+
+def test_checkpoint_fsync_can_be_switched_off(tmp_path, monkeypatch):
+    from adaptdl_b200 import checkpoint
+    synced = []
+    monkeypatch.setattr(os, "fsync", lambda fd: synced.append(fd))
+
+    class Tiny(checkpoint.State):
+        def save(self, f):
+            f.write(b"x")
+
+        def load(self, f):
+            pass
+    state = Tiny("tiny-fsync-state")
+    for flag, expect in ((None, 1), ("0", 0), ("1", 1)):
+        if flag is None:
+            monkeypatch.delenv("ADAPTDL_CHECKPOINT_FSYNC", raising=False)
+        else:
+            monkeypatch.setenv("ADAPTDL_CHECKPOINT_FSYNC", flag)
+        del synced[:]
+        checkpoint.save_state(state, str(tmp_path))
+        assert len(synced) == expect
