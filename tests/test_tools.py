@@ -232,6 +232,11 @@ def test_gradient_path_protocol_model():
     assert model.explore_all(model.Config(3, 1, 2)) > 10000
     assert model.explore_all(
         model.Config(2, 1, 2, buckets=("one", "two", "one"))) > 1000
+    assert model.explore_all(
+        model.Config(2, 1, 2, buckets=("nvls", "one", "two"))) > 1000
+    assert model.explore_all(model.Config(3, 1, 1, buckets=("nvls",))) > 1000
+    model.explore_random(
+        model.Config(3, 2, 3, buckets=("nvls", "two")), 200, seed=4)
     model.explore_random(model.Config(3, 2, 4), 300, seed=5)
     model.explore_random(
         model.Config(4, 2, 3, buckets=("two", "two", "one")), 100, seed=6)

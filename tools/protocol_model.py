@@ -24,6 +24,11 @@ What is modelled, per rank (one process per GPU), for every optimizer step:
   stripe of the own bucket into lane ``rank`` of every peer's staging area,
   then the same flag round, then sums the lanes locally and overwrites the own
   bucket;
+* **NVLS** kernel (``allreduce_nvls_kernel``): for every foreign slice the CTA
+  first reads its own copy (the per-replica statistic) and only then raises
+  its flag on the slice's owner; after the flags of all peers it reads the
+  own slice through the switch (``multimem.ld_reduce``: every rank's copy) and
+  writes the result into every arena (``multimem.st``);
 * every kernel ends with the CTA ticket; the last CTA of the step's LAST
   bucket kernel runs the **finalize**: writes this rank's statistics record
   into the exchange buffer of the step's parity, one more flag round on the
@@ -58,7 +63,7 @@ class Config(object):
     def __init__(self, ranks=2, ctas=1, steps=2, buckets=("two", "one"),
                  no_finalize_barrier=False, single_xchg=False,
                  same_epoch=False, no_start_barrier=False,
-                 push_after_barrier=False):
+                 push_after_barrier=False, nvls_flag_first=False):
         self.ranks, self.ctas, self.steps = ranks, ctas, steps
         self.buckets = tuple(buckets)          # in backward (launch) order
         # broken variants
@@ -67,6 +72,7 @@ class Config(object):
         self.same_epoch = same_epoch
         self.no_start_barrier = no_start_barrier
         self.push_after_barrier = push_after_barrier
+        self.nvls_flag_first = nvls_flag_first
 
 
 def build_programs(cfg):
@@ -88,6 +94,36 @@ def build_programs(cfg):
                     k = s * B + b                  # kernel ordinal on the stream
                     site = 0 if cfg.same_epoch else b + 1
                     ops.append(("launch", k, b, s))
+                    if flavour == "nvls":
+                        # per foreign slice: this rank's own copy feeds the
+                        # per-replica statistic BEFORE the owner is told it
+                        # may overwrite it (multimem.st lands in every arena)
+                        for d in range(1, R):
+                            q = (r + d) % R
+                            if cfg.nvls_flag_first:
+                                ops.append(("flag", q, ("cta", c), site))
+                                ops.append(("read_own_copy", q, b, s))
+                            else:
+                                ops.append(("read_own_copy", q, b, s))
+                                ops.append(("flag", q, ("cta", c), site))
+                        ops.append(("wait_peers", ("cta", c), site))
+                        for q in range(R):          # multimem.ld_reduce
+                            ops.append(("read_grad", q, b, s))
+                        for q in range(R):          # multimem.st
+                            ops.append(("write_sum", q, b, s))
+                        ops.append(("ticket", b == B - 1))
+                        if b == B - 1:
+                            fin_site = 0 if cfg.same_epoch else B + 1
+                            ops.append(("fin_record", s))
+                            if not cfg.no_finalize_barrier:
+                                for q in range(R):
+                                    ops.append(("fin_flag", q, fin_site))
+                                ops.append(("fin_wait", fin_site))
+                            for q in range(R):
+                                ops.append(("fin_read", q, s))
+                            ops.append(("fin_publish", s))
+                        ops.append(("done", k))
+                        continue
                     if flavour == "one" and not cfg.push_after_barrier:
                         for q in range(R):
                             if q != r:
@@ -177,6 +213,10 @@ class State(object):
             epoch = self.get(("step", r)) * SITES + op[2]
             return all(self.get(("pad", r, op[1], q), -1) >= epoch
                        for q in range(cfg.ranks))
+        if kind == "wait_peers":
+            epoch = self.get(("step", r)) * SITES + op[2]
+            return all(self.get(("pad", r, op[1], q), -1) >= epoch
+                       for q in range(cfg.ranks) if q != r)
         if kind == "fin_wait":
             if not self.last[t]:
                 return True
@@ -206,8 +246,15 @@ class State(object):
                         raise Violation(
                             "optimizer of rank {} step {} reads bucket {} "
                             "part {} = {}".format(r, s, b, part, got))
-        elif kind in ("launch", "wait", "await_finalize"):
+        elif kind in ("launch", "wait", "wait_peers", "await_finalize"):
             pass
+        elif kind == "read_own_copy":
+            _, q, b, s = op
+            got = self.get(("G", r, b, ("two", q, c)), None)
+            if got != ("L", r, s):
+                raise Violation(
+                    "rank {} cta {} step {} reads its own copy of slice {} "
+                    "of bucket {} = {}".format(r, c, s, q, b, got))
         elif kind == "flag":
             _, q, slot, site = op
             epoch = self.get(("step", r)) * SITES + site
@@ -219,7 +266,7 @@ class State(object):
             mem[("stage", q, b, r, c)] = mine
         elif kind == "read_grad":
             _, q, b, s = op
-            part = ("two", r, c) if cfg.buckets[b] == "two" else ("one", c)
+            part = ("one", c) if cfg.buckets[b] == "one" else ("two", r, c)
             got = self.get(("G", q, b, part), None)
             if got != ("L", q, s):
                 raise Violation(
@@ -278,7 +325,7 @@ class State(object):
 
     def _parts(self, b):
         cfg = self.cfg
-        if cfg.buckets[b] == "two":
+        if cfg.buckets[b] in ("two", "nvls"):
             return [("two", q, c) for q in range(cfg.ranks)
                     for c in range(cfg.ctas)]
         return [("one", c) for c in range(cfg.ctas)]
@@ -338,6 +385,8 @@ BROKEN = {
     "same epoch for every launch of a step": dict(same_epoch=True),
     "no start barrier in the bucket kernels": dict(no_start_barrier=True),
     "one-shot pushes after the flag round": dict(push_after_barrier=True),
+    "NVLS tells the owner before reading its own copy": dict(
+        nvls_flag_first=True),
 }
 
 
@@ -351,6 +400,8 @@ BROKEN = {
 def check_broken(name, runs=3000, **shape):
     """A broken variant must produce a violation (exhaustively for the
     smallest shape, else within ``runs`` random schedules)."""
+    if "NVLS" in name:
+        shape = dict(shape, buckets=("nvls", "two"))
     cfg = Config(**dict(shape, **BROKEN[name]))
     try:
         explore_random(cfg, runs, seed=1)
