@@ -652,6 +652,35 @@ def run_program(args, adl, device, rank, world, local_rank, workload,
     return out
 
 
+def step_profile(own):
+    """What the framework's OWN step profiler (the numbers its goodput model
+    is fitted to) booked during the run, rank 0: mean optimizer-step time and
+    mean "sync" time = last gradient ready -> gradients reduced, i.e. the
+    communication a step could not hide under backward. Own arm: %globaltimer
+    stamps of the kernels; reference arm: its CUDA events. Bookkeeping only --
+    never allowed to break the benchmark line."""
+    try:
+        if own:
+            from adaptdl_b200.torch import _metrics
+        else:
+            from adaptdl.torch import _metrics
+        steps = step_s = sync_s = 0.0
+        for row in list(_metrics._metrics_state().profile.values()):
+            count = row.get("optim_count", 0)
+            if not count:
+                continue
+            steps += count
+            step_s += row.get("optim_step_time", 0.0)
+            sync_s += row.get("optim_sync_time", 0.0)
+        if not steps:
+            return None
+        return {"steps": int(steps),
+                "step_ms": round(1e3 * step_s / steps, 4),
+                "sync_ms": round(1e3 * sync_s / steps, 4)}
+    except Exception as exc:  # noqa: BLE001
+        return {"error": str(exc)[:200]}
+
+
 def run(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -775,6 +804,7 @@ def run(args, rank, world, local_rank):
             timer = _metrics.device_timer()
             line["device_timed_profile_steps"] = \
                 timer.booked if timer is not None else 0
+        line["step_profile"] = step_profile(own)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -145,6 +145,9 @@ def test_bench_contract_two_ranks_on_cpu(tmp_path):
     assert out["steps_timed"] == 4 and len(out["windows"]["device_ms"]) == 2
     assert out["config"]["global_batch"] == 512
     assert out["value"] > 0 and out["e2e"]["value"] > 0
+    # the framework's own step profiler, as booked during the run
+    assert out["step_profile"]["steps"] > 0
+    assert out["step_profile"]["step_ms"] >= out["step_profile"]["sync_ms"] >= 0
     assert set(out["config"]) == {"workload", "model", "global_batch",
                                   "local_batch", "seq_len", "parallelism",
                                   "optimizer", "adaptive", "compute", "l2"}
