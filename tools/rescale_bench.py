@@ -23,8 +23,9 @@ iteration, checkpoint, interpreter teardown), start -> first optimizer step
 of the next generation finished on every replica (interpreter + imports,
 rendezvous, checkpoint load, first step), and their sum; per generation the
 tokens/s it trained at. The job writes the marks itself, so they mean the
-same thing in all arms. CPU numbers: CUDA context creation, peer-memory
-mapping and graph capture are not in them.
+same thing in all arms. Default: CPU replicas (CUDA context creation,
+peer-memory mapping and graph capture are then not in the numbers);
+``--device cuda`` gives every replica a GPU.
 """
 import argparse
 import json
@@ -42,9 +43,11 @@ from adaptdl_b200.sched.local import LocalElasticJob  # noqa: E402
 WORKER = os.path.join(ROOT, "tools", "rescale_worker.py")
 
 
-def arm_env(arm, marks):
-    env = {"OMP_NUM_THREADS": "1", "CUDA_VISIBLE_DEVICES": "",
-           "RESCALE_MARKS": marks}
+def arm_env(arm, marks, device="cpu"):
+    env = {"OMP_NUM_THREADS": "1", "RESCALE_MARKS": marks,
+           "RESCALE_DEVICE": device}
+    if device != "cuda":
+        env["CUDA_VISIBLE_DEVICES"] = ""
     if arm == "reference":
         env["PYTHONPATH"] = os.pathsep.join(
             [os.path.join(ROOT, "baseline", "_ref"),
@@ -91,11 +94,12 @@ def hold(job, seconds):
         time.sleep(0.1)
 
 
-def run_arm(arm, schedule, hold_s, pool_warmup, timeout):
+def run_arm(arm, schedule, hold_s, pool_warmup, timeout, device="cpu"):
     marks = tempfile.mkdtemp(prefix="rescale-marks-")
     ckpt = tempfile.mkdtemp(prefix="rescale-ckpt-")
     job = LocalElasticJob([sys.executable, WORKER], max(schedule),
-                          checkpoint_dir=ckpt, env=arm_env(arm, marks),
+                          checkpoint_dir=ckpt,
+                          env=arm_env(arm, marks, device),
                           standby=(arm == "own-standby"))
     transitions, generations = [], []
     try:
@@ -182,6 +186,10 @@ def main():
                         help="seconds the standby pool gets before the job "
                              "starts (a launcher keeps it warm all the time)")
     parser.add_argument("--timeout", type=float, default=180.0)
+    parser.add_argument("--device", default="cpu", choices=["cpu", "cuda"],
+                        help="cuda: one GPU per replica (NCCL; this "
+                             "framework then uses its fused reducer, the "
+                             "CUDA-side costs of a restart are included)")
     parser.add_argument("--out")
     args = parser.parse_args()
     schedule = [int(v) for v in args.schedule.split(",")]
@@ -193,7 +201,7 @@ def main():
                               "baseline/_ref not installed"}))
             continue
         result = run_arm(arm, schedule, args.hold, args.pool_warmup,
-                         args.timeout)
+                         args.timeout, args.device)
         results.append(result)
         for t in result["transitions"]:
             print("{:12s} {}->{}: signal->exit {:.2f} s, exit->first step "

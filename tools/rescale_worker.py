@@ -64,14 +64,21 @@ class TinyLM(nn.Module):
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(1)
-    adl.init_process_group("gloo")
+    on_gpu = os.environ.get("RESCALE_DEVICE", "cpu") == "cuda" and \
+        torch.cuda.is_available()
+    device = torch.device("cpu")
+    if on_gpu:
+        device = torch.device("cuda", int(os.environ.get(
+            "ADAPTDL_LOCAL_RANK", os.environ.get("ADAPTDL_REPLICA_RANK", 0))))
+        torch.cuda.set_device(device)
+    adl.init_process_group("nccl" if on_gpu else "gloo")
     mark("process_group", impl=adl.__name__, file=adl.__file__)
     g = torch.Generator().manual_seed(1)
     stream = torch.randint(0, VOCAB, (SAMPLES, BPTT + 1), generator=g)
     dataset = torch.utils.data.TensorDataset(stream[:, :-1], stream[:, 1:])
     loader = adl.AdaptiveDataLoader(dataset, batch_size=BATCH, shuffle=True,
                                     drop_last=True)
-    model = TinyLM()
+    model = TinyLM().to(device)
     optimizer = torch.optim.SGD(model.parameters(), lr=0.5)
     scheduler = torch.optim.lr_scheduler.StepLR(optimizer, 1, gamma=0.95)
     net = adl.AdaptiveDataParallel(model, optimizer, scheduler)
@@ -80,6 +87,7 @@ def main():
     steps = tokens = 0
     for epoch in adl.remaining_epochs_until(10 ** 6):
         for x, y in loader:
+            x, y = x.to(device), y.to(device)
             optimizer.zero_grad()
             loss = nn.functional.cross_entropy(
                 net(x).reshape(-1, VOCAB), y.reshape(-1))
