@@ -21,9 +21,11 @@ the Pollux policy; 5 % hysteresis like the reference's Ray-AWS optimiser,
 """
 
 import argparse
+import atexit
 import json
 import logging
 import os
+import shutil
 import signal
 import subprocess
 import sys
@@ -121,6 +123,24 @@ def best_replicas(hints, max_replicas, current, hysteresis=0.05):
     return best
 
 
+def scratch_checkpoint_dir(prefix):
+    """Directory for checkpoints that only have to live as long as the
+    launcher (a rescale hands them from one generation to the next): memory
+    backed when the machine has a writable ``/dev/shm``, so that a large
+    model is written and read at memory speed and never waits for a disk
+    (``ADAPTDL_B200_SCRATCH`` names another place). Pass ``--checkpoint-dir``
+    for checkpoints that must survive the launcher."""
+    base = os.environ.get("ADAPTDL_B200_SCRATCH")
+    if base is None and os.path.isdir("/dev/shm") and \
+            os.access("/dev/shm", os.W_OK | os.X_OK):
+        base = "/dev/shm"
+    path = tempfile.mkdtemp(prefix=prefix, dir=base or None)
+    # scratch means scratch: gone when the launcher process ends (memory-
+    # backed files would otherwise hold RAM until the next reboot)
+    atexit.register(shutil.rmtree, path, ignore_errors=True)
+    return path
+
+
 class LocalElasticJob(object):
     """One elastic job on this machine's GPUs."""
 
@@ -138,8 +158,8 @@ class LocalElasticJob(object):
         self.pool = []               # idle warm interpreters
         self._pool_due = None        # when to top the pool up again
         self.max_replicas = max_replicas
-        self.checkpoint_dir = checkpoint_dir or tempfile.mkdtemp(
-            prefix="adaptdl-b200-ckpt-")
+        self.checkpoint_dir = checkpoint_dir or scratch_checkpoint_dir(
+            "adaptdl-b200-ckpt-")
         self.job_id = job_id
         self.extra_env = dict(env or {})
         self.gpu_ids = list(gpu_ids) if gpu_ids is not None else None

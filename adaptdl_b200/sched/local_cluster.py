@@ -27,7 +27,8 @@ import sys
 import time
 
 from adaptdl_b200.sched.allocator import job_info_from
-from adaptdl_b200.sched.local import LocalElasticJob
+from adaptdl_b200.sched.local import (LocalElasticJob,
+                                      scratch_checkpoint_dir)
 from adaptdl_b200.sched.policy import NodeInfo, PolluxPolicy
 
 LOG = logging.getLogger(__name__)
@@ -41,11 +42,10 @@ class LocalCluster(object):
 
     def __init__(self, jobs, gpus, checkpoint_root=None, policy=None,
                  resource=GPU):
-        import tempfile
         self.gpus = gpus
         self.resource = resource
         self.policy = policy or PolluxPolicy(pop_size=50, generations=40)
-        root = checkpoint_root or tempfile.mkdtemp(prefix="adaptdl-b200-lc-")
+        root = checkpoint_root or scratch_checkpoint_dir("adaptdl-b200-lc-")
         self.jobs = {}
         self.specs = {}
         for i, spec in enumerate(jobs):
