@@ -123,6 +123,9 @@ def best_replicas(hints, max_replicas, current, hysteresis=0.05):
     return best
 
 
+SCRATCH_MIN_FREE = 8 << 30        # bytes /dev/shm must have free to be used
+
+
 def scratch_checkpoint_dir(prefix):
     """Directory for checkpoints that only have to live as long as the
     launcher (a rescale hands them from one generation to the next): memory
@@ -133,7 +136,12 @@ def scratch_checkpoint_dir(prefix):
     base = os.environ.get("ADAPTDL_B200_SCRATCH")
     if base is None and os.path.isdir("/dev/shm") and \
             os.access("/dev/shm", os.W_OK | os.X_OK):
-        base = "/dev/shm"
+        try:       # containers often get a 64 MB /dev/shm: not for checkpoints
+            roomy = shutil.disk_usage("/dev/shm").free >= SCRATCH_MIN_FREE
+        except OSError:
+            roomy = False
+        if roomy:
+            base = "/dev/shm"
     path = tempfile.mkdtemp(prefix=prefix, dir=base or None)
     # scratch means scratch: gone when the launcher process ends (memory-
     # backed files would otherwise hold RAM until the next reboot)
