@@ -17,4 +17,13 @@ mkdir -p "$HERE/_ref/_ref_examples"
 cp -r /root/reference/examples/pytorch-cifar/models "$HERE/_ref/_ref_examples/cifar_models"
 cp /root/reference/examples/BERT/model.py "$HERE/_ref/_ref_examples/bert_model.py"
 cp /root/reference/examples/NCF/model.py "$HERE/_ref/_ref_examples/ncf_model.py"
+# the reference's scheduling policy (sched/adaptdl_sched/policy: pollux.py,
+# speedup.py, utils.py), unmodified, for tools/sched_sim.py --policy reference
+# and tools/policy_bench.py --search reference (needs the pymoo stand-in in
+# baseline/shims/)
+mkdir -p "$HERE/_ref/_ref_sched/adaptdl_sched/policy"
+touch "$HERE/_ref/_ref_sched/adaptdl_sched/__init__.py"
+for f in __init__.py pollux.py speedup.py utils.py; do
+    cp "/root/reference/sched/adaptdl_sched/policy/$f" "$HERE/_ref/_ref_sched/adaptdl_sched/policy/$f"
+done
 echo "reference installed into $HERE/_ref"

@@ -53,7 +53,18 @@ def make_cluster(num_jobs, num_nodes, gpus_per_node, seed):
 def run(num_jobs, num_nodes, gpus_per_node, cycles, seed, native=None):
     jobs, nodes, template = make_cluster(num_jobs, num_nodes, gpus_per_node,
                                          seed)
-    policy = PolluxPolicy(seed=seed, native=native)
+    if native == "reference":
+        # the reference's unmodified pollux.py on the stand-in NSGA-II engine
+        # of baseline/shims/pymoo (baseline/ref_policy.py)
+        import logging
+        from baseline import ref_policy
+        policy = ref_policy.load()[0]()
+        logging.getLogger("adaptdl_sched.policy.pollux").setLevel(
+            logging.WARNING)
+        np.random.seed(seed)
+        policy._native = None
+    else:
+        policy = PolluxPolicy(seed=seed, native=native)
     previous, seconds = {}, []
     for _ in range(cycles):
         start = time.perf_counter()
@@ -69,7 +80,9 @@ def run(num_jobs, num_nodes, gpus_per_node, cycles, seed, native=None):
     value = sum(float(jobs[k].speedup_fn(len(set(a)), len(a)))
                 for k, a in allocations.items() if a)
     return {"jobs": num_jobs, "nodes": num_nodes,
-            "search": "native" if policy._native else "numpy",
+            "search": "reference policy (stand-in engine)"
+            if policy._native is None
+            else ("native" if policy._native else "numpy"),
             "gpus": num_nodes * gpus_per_node,
             "cycle_seconds": [round(s, 3) for s in seconds],
             "gpus_allocated": sum(per_node.values()),
@@ -85,7 +98,7 @@ def main():
     parser.add_argument("--cycles", type=int, default=3)
     parser.add_argument("--seed", type=int, default=0)
     parser.add_argument("--search", default="native",
-                        choices=["native", "numpy", "both"],
+                        choices=["native", "numpy", "both", "reference"],
                         help="C++ core (csrc/host/adl_pollux.cpp), the numpy "
                              "implementation, or one after the other")
     parser.add_argument("--numpy-max-jobs", type=int, default=200,
@@ -97,7 +110,8 @@ def main():
     for size in args.sizes.split(","):
         num_jobs, num_nodes = (int(v) for v in size.split("x"))
         flavours = {"native": [True], "numpy": [False],
-                    "both": [True, False]}[args.search]
+                    "both": [True, False],
+                    "reference": ["reference"]}[args.search]
         for native in flavours:
             if not native and args.search == "both" and \
                     num_jobs > args.numpy_max_jobs:

@@ -126,7 +126,22 @@ class SimJob(object):
         return float(fn.evaluate(nodes, n, atomic, 0))
 
 
-def simulate(rate_per_hour, args, adaptive, seed, static_gpus=None):
+def reference_policy(seed):
+    """The UNMODIFIED reference policy (``baseline/ref_policy.py``: its
+    pollux.py on a stand-in NSGA-II engine, population 100 x 100 generations
+    as hard-coded there); ``None`` when the reference is not installed."""
+    from baseline import ref_policy
+    if not ref_policy.available():
+        return None
+    import logging
+    policy_class = ref_policy.load()[0]
+    logging.getLogger("adaptdl_sched.policy.pollux").setLevel(logging.WARNING)
+    np.random.seed(seed)                 # the reference draws from the global
+    return policy_class()
+
+
+def simulate(rate_per_hour, args, adaptive, seed, static_gpus=None,
+             policy_name="own"):
     rng = np.random.default_rng(seed)
     kinds = list(ZOO)
     weights = np.array([0.5, 0.1, 0.2, 0.2])
@@ -147,8 +162,11 @@ def simulate(rate_per_hour, args, adaptive, seed, static_gpus=None):
                                                 "pods": 32}, False)
              for i in range(args.nodes)}
     template = NodeInfo({GPU: args.gpus_per_node, "pods": 32}, True)
-    policy = PolluxPolicy(pop_size=args.pop, generations=args.generations,
-                          seed=seed)
+    if policy_name == "reference":
+        policy = reference_policy(seed)
+    else:
+        policy = PolluxPolicy(pop_size=args.pop, generations=args.generations,
+                              seed=seed)
     now, pending, active = 0.0, collections.deque(jobs), []
     dt = args.interval
     policy_seconds = 0.0
@@ -237,6 +255,9 @@ def main():
     ap.add_argument("--pop", type=int, default=50)
     ap.add_argument("--generations", type=int, default=40)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--reference-policy", action="store_true",
+                    help="add an arm that schedules with the reference's "
+                         "unmodified policy (baseline/ref_policy.py)")
     ap.add_argument("--out", default=None)
     args = ap.parse_args()
     rows = []
@@ -247,6 +268,13 @@ def main():
                 ("static_whole_node", False, args.gpus_per_node),
                 ("adaptive", True, None)):
             row[name] = simulate(rate, args, adaptive, args.seed, fixed)
+        if args.reference_policy and reference_policy(args.seed) is not None:
+            row["reference_policy"] = simulate(rate, args, True, args.seed,
+                                               None, "reference")
+            r = row["reference_policy"]["avg_jct_hours"]
+            own = row["adaptive"]["avg_jct_hours"]
+            row["avg_jct_ratio_reference_policy_over_adaptive"] = \
+                (r / own) if (r and own) else None
         a, s = row["adaptive"]["avg_jct_hours"], row["static"]["avg_jct_hours"]
         row["avg_jct_ratio_static_over_adaptive"] = \
             (s / a) if (a and s) else None
