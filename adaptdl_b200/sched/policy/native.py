@@ -2,9 +2,10 @@
 
 :func:`minimize` has the contract of :func:`nsga2.minimize` for a
 :class:`pollux.ClusterProblem`: same operators, objectives and survival rule,
-executed candidate by candidate in C++ (one pass while the 100 KB candidate
-sits in cache, candidates spread over threads) instead of ~25 numpy passes
-per generation over the ``[population, jobs, nodes]`` tensor. The one thing
+executed candidate by candidate in C++ on a sparse representation (per job
+the few (node, replicas) entries it has; every operator costs O(entries),
+candidates spread over threads) instead of ~25 numpy passes per generation
+over the dense ``[population, jobs, nodes]`` tensor. The one thing
 that stays in Python is the goodput model: the core keeps a speedup table per
 job, stops when a candidate needs an entry it does not have, and the entries
 are computed here through the jobs' ``SpeedupFunction`` objects (vectorised,
