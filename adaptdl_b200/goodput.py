@@ -217,6 +217,21 @@ def _objective(params, num_nodes, num_replicas, atomic_bsz,
     return value, grad
 
 
+def _obj_fn(params, num_nodes, num_replicas, atomic_bsz,
+            accum_step_time, optim_step_time):
+    """Value of the fit objective at ``params`` (the name the reference's own
+    ``fit_test.py`` evaluates; ``goodput.py:201-233`` there)."""
+    return _objective(np.asarray(params, dtype=float), np.asarray(num_nodes),
+                      np.asarray(num_replicas), np.asarray(atomic_bsz),
+                      np.asarray(accum_step_time),
+                      np.asarray(optim_step_time), want_grad=False)
+
+
+# names under which the reference keeps the two time models
+_predict_accum_time = _accum_time
+_predict_network_time = _network_time
+
+
 def fit_perf_params(num_nodes, num_replicas, atomic_bsz,
                     accum_step_time, optim_step_time):
     """Fit :class:`PerfParams` to measured per-configuration step times.

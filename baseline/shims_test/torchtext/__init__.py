@@ -1,0 +1,6 @@
+"""Test-only stand-in for the *legacy* torchtext API (<= 0.8: ``data.Field``,
+``data.Example``, ``data.Dataset``, ``data.utils.get_tokenizer``), which is
+not installable here and which the reference's own ``data_test.py`` builds its
+BPTT fixture from. Only what that fixture touches; used by
+``tests/test_reference_suite.py`` and nowhere on a product path."""
+from . import data  # noqa: F401
