@@ -52,8 +52,10 @@ def parse_args():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--local-bsz", type=int, default=None)
     ap.add_argument("--workload", default="resnet18",
-                    choices=["resnet18", "ncf", "bert"],
-                    help="resnet18 = the headline config (default); ncf = "
+                    choices=["resnet18", "ncf", "bert", "linreg"],
+                    help="resnet18 = the headline config (default); linreg "
+                         "= BASELINE config 1, the CPU / gloo plumbing "
+                         "config (run it with --device cpu); ncf = "
                          "small-model/latency path; bert = BERT-base MLM "
                          "bf16 (reference arm: the same model in stock "
                          "PyTorch modules, baseline/models/bert_plain.py, "
@@ -340,6 +342,34 @@ class SyntheticMLM(object):
         return self.x[idx], self.y[idx]
 
 
+class SyntheticPoly(object):
+    """The reference's ``examples/linear_regression`` problem (BASELINE
+    config 1, the CPU / gloo plumbing config): features [x, x^2, x^3, x^4] of
+    a normal x, target a fixed linear function of them plus noise."""
+    DEGREE = 4
+
+    def __init__(self, size, pin):
+        import torch
+        g = torch.Generator().manual_seed(1234)
+        x = torch.randn(size, generator=g).unsqueeze(1)
+        self.x = torch.cat([x ** i for i in range(1, self.DEGREE + 1)], 1)
+        w = torch.randn(self.DEGREE, 1, generator=g) * 5
+        self.y = self.x.mm(w) + 0.25 * torch.randn(size, 1, generator=g)
+        if pin:
+            self.x, self.y = self.x.pin_memory(), self.y.pin_memory()
+
+    def __len__(self):
+        return self.x.shape[0]
+
+    def __getitem__(self, k):
+        return self.x[k], self.y[k]
+
+    def __getitems__(self, idx):
+        import torch
+        idx = torch.as_tensor(idx)
+        return self.x[idx], self.y[idx]
+
+
 class Workload(object):
     """One benchmark configuration: dataset, model, optimizer, loss."""
 
@@ -347,13 +377,14 @@ class Workload(object):
         self.name, self.own = name, own
         self.channels_last = name == "resnet18"
         self.default_local_bsz = {"resnet18": 128, "ncf": 256,
-                                  "bert": 32}[name]
+                                  "bert": 32, "linreg": 64}[name]
         self.unit = {"resnet18": "samples/s", "ncf": "samples/s",
-                     "bert": "sequences/s"}[name]
+                     "bert": "sequences/s", "linreg": "samples/s"}[name]
 
     def dataset(self, size, pin):
         return {"resnet18": SyntheticCIFAR, "ncf": SyntheticNCF,
-                "bert": SyntheticMLM}[self.name](size, pin)
+                "bert": SyntheticMLM, "linreg": SyntheticPoly}[self.name](
+                    size, pin)
 
     def model(self):
         if self.name == "resnet18":
@@ -362,6 +393,9 @@ class Workload(object):
                 return resnet18()
             from cifar_models.resnet import ResNet18
             return ResNet18()
+        if self.name == "linreg":
+            import torch
+            return torch.nn.Linear(SyntheticPoly.DEGREE, 1)
         if self.name == "ncf":
             if self.own:
                 from adaptdl_b200.models import NCF
@@ -381,6 +415,11 @@ class Workload(object):
 
     def optimizer(self, model):
         import torch
+        if self.name == "linreg":
+            opt = torch.optim.SGD(model.parameters(), lr=0.1, momentum=0.9,
+                                  weight_decay=5e-4)
+            return opt, torch.optim.lr_scheduler.MultiStepLR(opt, [30, 45],
+                                                             0.1)
         if self.name == "resnet18":
             opt = torch.optim.SGD([{"params": [p]}
                                    for p in model.parameters()],
@@ -400,6 +439,9 @@ class Workload(object):
         if self.name == "resnet18":
             ce = torch.nn.CrossEntropyLoss()
             return lambda net, x, y: ce(net(x), y)
+        if self.name == "linreg":
+            return lambda net, x, y: torch.nn.functional.smooth_l1_loss(
+                net(x), y)
         if self.name == "ncf":
             bce = torch.nn.BCEWithLogitsLoss()
             return lambda net, u, i, y: bce(net(u, i), y)
@@ -408,6 +450,9 @@ class Workload(object):
             net(x).view(-1, SyntheticMLM.NTOKEN), y.view(-1))
 
     def l2_note(self):
+        if self.name == "linreg":
+            return ("framework-overhead config (5 parameters): nothing to "
+                    "flush; a fresh batch every step")
         if self.name == "ncf":
             return ("latency-bound config: parameters + optimizer state "
                     "(26 MB) fit the 126 MB L2, no flush between steps; a "
@@ -424,6 +469,9 @@ class Workload(object):
                          "(62 GNS groups), AdaScale LR"),
             "ncf": ("NeuMF-end NCF (MovieLens-1M shape, 1.6 M params, "
                     "random init)", "Adam lr=1e-3, AdamScale LR"),
+            "linreg": ("linear regression on 4 polynomial features "
+                       "(examples/linear_regression)",
+                       "SGD m=0.9 wd=5e-4, MultiStepLR, AdaScale LR"),
             "bert": ("BERT-base MLM (768/3072/12L/12H, seq 128, untied "
                      "head, random init)", "AdamW lr=1e-4, AdamScale LR"),
         }[self.name]
@@ -736,7 +784,9 @@ def run(args, rank, world, local_rank):
     e2e_value = e2e["samples"] / (e2e["total_ms"] / 1e3)
     if rank == 0:
         line = {
-            "metric": "samples/sec (device-timed, max over ranks)",
+            "metric": ("samples/sec (device-timed, max over ranks)"
+                       if device.type == "cuda" else
+                       "samples/sec (host-timed, max over ranks)"),
             "value": value, "unit": workload.unit, "n_gpus": world,
             "steps": K, "warmup": args.warmup,
             "warmup_run": warmup_steps(args),
@@ -744,7 +794,8 @@ def run(args, rank, world, local_rank):
             "higher_is_better": True, "scaling": "weak",
             "vs_baseline": (value / PUBLISHED_BASELINE
                             if PUBLISHED_BASELINE else None),
-            "dtype": "bf16", "data": "synthetic",
+            "dtype": "bf16" if device.type == "cuda" else "fp32",
+            "data": "synthetic",
             "impl": args.impl,
             # the WORKLOAD (identical strings in both arms) ...
             "config": {
@@ -757,8 +808,9 @@ def run(args, rank, world, local_rank):
                 "parallelism": "dp{}".format(world),
                 "optimizer": workload.describe()[1],
                 "adaptive": "autoscale_batch_size(max=32x, local 32..1024)",
-                "compute": ("channels_last, " if workload.channels_last
-                            else "") + "bf16 autocast",
+                "compute": (("channels_last, " if workload.channels_last
+                             else "") + "bf16 autocast"
+                            if device.type == "cuda" else "fp32, CPU / gloo"),
                 "l2": workload.l2_note(),
             },
             # ... and how THIS arm implements it

@@ -5,6 +5,8 @@ import importlib.util
 import os
 import types
 
+import pytest
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -151,6 +153,45 @@ def test_bench_contract_two_ranks_on_cpu(tmp_path):
     assert set(out["config"]) == {"workload", "model", "global_batch",
                                   "local_batch", "seq_len", "parallelism",
                                   "optimizer", "adaptive", "compute", "l2"}
+
+
+@pytest.mark.parametrize("impl", ["own", "reference"])
+def test_bench_config1_linreg_both_arms_on_cpu(tmp_path, impl):
+    """BASELINE config 1 (linear regression, 2 gloo replicas on the CPU)
+    through bench.py, own arm and the unmodified reference arm: the same
+    workload description in both lines, a positive value, and the
+    reference arm really is the package under baseline/_ref."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if impl == "reference" and not os.path.isdir(
+            os.path.join(root, "baseline", "_ref", "adaptdl")):
+        pytest.skip("baseline/_ref is not installed")
+    env = {k: v for k, v in os.environ.items()
+           if not k.startswith("ADAPTDL_")}
+    port = "29735" if impl == "own" else "29737"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+           "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", port, os.path.join(root, "bench.py"),
+           "--gpus", "2", "--steps", "10", "--warmup", "3", "--device", "cpu",
+           "--workload", "linreg", "--impl", impl, "--min-timed-ms", "0"]
+    proc = subprocess.run(cmd, env=env, stdout=subprocess.PIPE,
+                          stderr=subprocess.PIPE, text=True, timeout=600,
+                          cwd=str(tmp_path))
+    assert proc.returncode == 0, proc.stderr[-3000:]
+    lines = [ln for ln in proc.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    out = json.loads(lines[0])
+    assert out["impl"] == impl and out["n_gpus"] == 2
+    assert out["config"]["workload"] == "linreg"
+    assert out["config"]["global_batch"] == 128
+    assert out["dtype"] == "fp32" and "host-timed" in out["metric"]
+    assert out["value"] > 0 and out["e2e"]["value"] > 0
+    assert out["step_profile"]["steps"] > 0
+    if impl == "reference":
+        assert out["gpu_launches"] is None and "reducer" not in out
 
 
 def test_bench_clock_sampler_only_keeps_samples_inside_windows(monkeypatch):
