@@ -47,8 +47,8 @@ class _AliasFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
         if spec is None:
             return None
         return importlib.machinery.ModuleSpec(
-            fullname, self, is_package=spec.submodule_search_locations
-            is not None)
+            fullname, self, origin=spec.origin,
+            is_package=spec.submodule_search_locations is not None)
 
     def create_module(self, spec):
         # the real module object itself: one module, two names
@@ -56,6 +56,31 @@ class _AliasFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
 
     def exec_module(self, module):
         pass
+
+    # ``python -m adaptdl_sched.allocator`` (the commands of the reference's
+    # helm chart): runpy asks the loader for the code object and runs it as
+    # ``__main__``
+    def _real_loader(self, fullname):
+        real = self._real_name(fullname)
+        spec = importlib.util.find_spec(real)
+        if spec is None or spec.loader is None:
+            raise ImportError("no module named " + fullname)
+        return real, spec
+
+    def get_code(self, fullname):
+        real, spec = self._real_loader(fullname)
+        return spec.loader.get_code(real)
+
+    def get_source(self, fullname):
+        real, spec = self._real_loader(fullname)
+        return spec.loader.get_source(real)
+
+    def get_filename(self, fullname):
+        return self._real_loader(fullname)[1].origin
+
+    def is_package(self, fullname):
+        spec = self._real_loader(fullname)[1]
+        return spec.submodule_search_locations is not None
 
 
 def alias(name, target):

@@ -217,3 +217,8 @@ class AdaptDLAllocator(object):
                          wanted)
                 await self._cluster.patch_job_status(
                     key[0], key[1], {"status": {"allocation": wanted}})
+
+
+if __name__ == "__main__":      # ``python -m adaptdl_sched.allocator``, as in
+    from adaptdl_b200.sched.__main__ import main  # the reference's chart
+    main(["allocator"])

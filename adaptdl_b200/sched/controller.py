@@ -475,3 +475,8 @@ class AdaptDLController(object):
             return {"phase": "Failed", "reason": "PodCreationError",
                     "message": str(exc)}
         return None
+
+
+if __name__ == "__main__":      # ``python -m adaptdl_sched.controller``, as in
+    from adaptdl_b200.sched.__main__ import main  # the reference's chart
+    main(["controller"])

@@ -100,3 +100,8 @@ class Supervisor(object):
 
     def run(self):
         web.run_app(self.app, host=self._host, port=self._port)
+
+
+if __name__ == "__main__":      # ``python -m adaptdl_sched.supervisor``, as in
+    from adaptdl_b200.sched.__main__ import main  # the reference's chart
+    main(["supervisor"])
