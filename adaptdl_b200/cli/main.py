@@ -199,24 +199,29 @@ def tensorboard(args, remaining):
             print(item["metadata"]["labels"]["adaptdl/tensorboard"])
     elif args.tb_command == "proxy":
         full = manifests.TENSORBOARD_PREFIX + args.name
-        print("TensorBoard at http://localhost:{}".format(args.port))
+        print("TensorBoard at http://{}:{}".format(args.address, args.port))
         try:
             from adaptdl_b200.cli.proxy import service_proxy
             namespace = _kubectl(
                 "config", "view", "--minify", "-o",
                 "jsonpath={..namespace}").strip() or "default"
             with service_proxy(namespace, full + ":6006",
+                               listen_host=args.address,
                                listen_port=args.port):
                 threading.Event().wait()        # until interrupted
         except KeyboardInterrupt:
             pass
         except Exception:  # noqa: BLE001 - e.g. exec credential plugins
-            _kubectl("port-forward", "service/" + full,
-                     "{}:6006".format(args.port), capture=False)
+            _kubectl("port-forward", "--address", args.address,
+                     "service/" + full, "{}:6006".format(args.port),
+                     capture=False)
 
 
 def build_parser():
-    parser = argparse.ArgumentParser(prog="adaptdl-b200")
+    name = os.path.basename(sys.argv[0] or "") if sys.argv else ""
+    # installed under both names (setup.py); "adaptdl" is the reference's
+    parser = argparse.ArgumentParser(
+        prog=name if name in ("adaptdl", "adaptdl-b200") else "adaptdl-b200")
     sub = parser.add_subparsers(dest="command", required=True)
     p = sub.add_parser("submit", help="build, push and submit a job")
     p.add_argument("project", help="directory with the job's Dockerfile")
@@ -245,7 +250,8 @@ def build_parser():
     tb = p.add_subparsers(dest="tb_command", required=True)
     c = tb.add_parser("create")
     c.add_argument("name")
-    c.add_argument("--storage-class")
+    c.add_argument("--storage-class", "--storageclass",
+                   dest="storage_class")      # second spelling: reference's
     c.add_argument("--size", default="1Gi")
     c.add_argument("--nodeport", action="store_true",
                    help="expose TensorBoard on a node port")
@@ -253,6 +259,8 @@ def build_parser():
         c = tb.add_parser(verb)
         c.add_argument("name")
         if verb == "proxy":
+            c.add_argument("--address", default="127.0.0.1",
+                           help="local address to bind")
             c.add_argument("-p", "--port", type=int, default=6006)
     tb.add_parser("list")
     p.set_defaults(handler=tensorboard)

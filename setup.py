@@ -67,6 +67,9 @@ setuptools.setup(
     },
     entry_points={"console_scripts": [
         "adaptdl-b200=adaptdl_b200.cli.main:main",
+        # the reference's command names (cli/bin/adaptdl, ray/setup.py:49)
+        "adaptdl=adaptdl_b200.cli.main:main",
+        "adaptdl_on_ray_aws=adaptdl_b200.ray.aws.launch_job:main",
         "adaptdl-b200-launch=adaptdl_b200.launch:main",
         "adaptdl-b200-local=adaptdl_b200.sched.local:main",
         "adaptdl-b200-local-cluster=adaptdl_b200.sched.local_cluster:main",

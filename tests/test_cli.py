@@ -226,3 +226,32 @@ def test_kube_access_materialises_inline_credentials():
     insecure = load_kube_access({"clusters": [{"cluster": {
         "server": "https://k", "insecure-skip-tls-verify": True}}]})
     assert insecure.verify is False and insecure.cert is None
+
+
+def test_parser_accepts_the_reference_command_lines():
+    """Every flag of the reference's ``adaptdl`` command (cli/bin/adaptdl:
+    400-480, cli/adaptdl_cli/tensorboard.py:180-211) parses here, with the
+    reference's spellings."""
+    from adaptdl_b200.cli.main import build_parser
+    parser = build_parser()
+    a = parser.parse_args(["submit", "proj", "-f", "job.yaml", "-d",
+                           "Dockerfile", "-n", "name", "--tensorboard", "tb",
+                           "--checkpoint-storage-size", "2Gi",
+                           "--checkpoint-storage-class", "efs",
+                           "--proxy-port", "1234"])
+    assert (a.project, a.jobfile, a.dockerfile, a.name, a.tensorboard) == \
+        ("proj", "job.yaml", "Dockerfile", "name", "tb")
+    assert a.checkpoint_storage_size == "2Gi" and a.proxy_port == 1234
+    assert parser.parse_args(["logs", "job"]).jobname == "job"
+    assert parser.parse_args(["ls"]).command == "ls"
+    a = parser.parse_args(["cp", "job:/adaptdl/checkpoint/x", "out"])
+    assert a.source == "job:/adaptdl/checkpoint/x" and a.destination == "out"
+    a = parser.parse_args(["tensorboard", "create", "tb", "--nodeport",
+                           "--storageclass", "fast", "--size", "5Gi"])
+    assert a.storage_class == "fast" and a.nodeport and a.size == "5Gi"
+    a = parser.parse_args(["tensorboard", "proxy", "tb", "--address",
+                           "0.0.0.0", "-p", "7007"])
+    assert a.address == "0.0.0.0" and a.port == 7007
+    for verb in ("delete", "list"):
+        parser.parse_args(["tensorboard", verb] + (["tb"] if verb == "delete"
+                                                   else []))
