@@ -26,15 +26,25 @@ _INSTALLED = {}
 
 class _AliasFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
 
-    def __init__(self, name, target):
+    def __init__(self, name, target, renames=None):
         self.name, self.target = name, target
+        # modules that are laid out differently here: alias-relative dotted
+        # prefix -> target-relative dotted prefix ("" = the target itself),
+        # longest prefix first
+        self.renames = sorted((renames or {}).items(),
+                              key=lambda kv: -len(kv[0]))
 
     def _real_name(self, fullname):
         if fullname == self.name:
             return self.target
-        if fullname.startswith(self.name + "."):
-            return self.target + fullname[len(self.name):]
-        return None
+        if not fullname.startswith(self.name + "."):
+            return None
+        rest = fullname[len(self.name) + 1:]
+        for old, new in self.renames:
+            if rest == old or rest.startswith(old + "."):
+                rest = (new + rest[len(old):]).lstrip(".")
+                break
+        return self.target + ("." + rest if rest else "")
 
     def find_spec(self, fullname, path=None, target=None):
         real = self._real_name(fullname)
@@ -83,11 +93,13 @@ class _AliasFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
         return spec.submodule_search_locations is not None
 
 
-def alias(name, target):
-    """Make ``import <name>[.sub]`` return ``<target>[.sub]``."""
+def alias(name, target, renames=None):
+    """Make ``import <name>[.sub]`` return ``<target>[.sub]``; ``renames``
+    maps sub-module paths of the alias that are named differently in the
+    target."""
     if _INSTALLED.get(name) == target:
         return sys.modules.get(name)
-    finder = _AliasFinder(name, target)
+    finder = _AliasFinder(name, target, renames)
     sys.meta_path.insert(0, finder)
     _INSTALLED[name] = target
     module = importlib.import_module(target)

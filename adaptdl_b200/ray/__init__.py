@@ -39,3 +39,19 @@ def tune_checkpoint_dir(for_save):
         return session.get_session().get_checkpoint()
     except Exception:  # noqa: BLE001
         return None
+
+
+
+def __getattr__(name):
+    # ``from adaptdl_ray.adaptdl import AdaptDLAllocator, AdaptDLJobMixin,
+    # default_device`` (the reference's ray/adaptdl_ray/adaptdl/__init__.py)
+    if name == "AdaptDLAllocator":
+        from adaptdl_b200.ray.allocator import AdaptDLAllocator
+        return AdaptDLAllocator
+    if name == "AdaptDLJobMixin":
+        from adaptdl_b200.ray.job_mixin import AdaptDLJobMixin
+        return AdaptDLJobMixin
+    if name == "default_device":
+        from adaptdl_b200.ray.config import default_device
+        return default_device
+    raise AttributeError(name)

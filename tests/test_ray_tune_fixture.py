@@ -137,3 +137,26 @@ def test_allocation_round_trip_through_placement_groups(tune):
     assert ray_utils.pgf_to_allocation(pgf) == alloc
     assert ray_utils.pgf_to_num_replicas(pgf) == 3
     assert ray_utils.unique_nodes(pgf.bundles[1:]) == 2
+
+
+def test_reference_module_paths_of_the_ray_package(tune):
+    """``from adaptdl_ray.tune.adaptdl_trial_sched import AdaptDLScheduler``
+    (the import line of the reference's Tune examples and tutorial) and the
+    other module paths of ``ray/adaptdl_ray`` resolve to the classes here."""
+    from adaptdl_ray.tune.adaptdl_trial_sched import AdaptDLScheduler
+    from adaptdl_ray.tune.adaptdl_trial import AdaptDLTrial
+    from adaptdl_ray.tune.adaptdl_trainable import AdaptDLTrainableCreator
+    from adaptdl_ray.tune import AdaptDLScheduler as again
+    assert AdaptDLScheduler is tune.AdaptDLScheduler is again
+    assert AdaptDLTrial is tune.AdaptDLTrial
+    assert AdaptDLTrainableCreator is tune.AdaptDLTrainableCreator
+    from adaptdl_ray.adaptdl import AdaptDLAllocator, AdaptDLJobMixin
+    from adaptdl_ray.adaptdl.adaptdl_allocator import AdaptDLAllocator as a2
+    from adaptdl_ray.adaptdl.adaptdl_job_mixin import AdaptDLJobMixin as m2
+    from adaptdl_ray.adaptdl.utils import pgf_to_allocation  # noqa: F401
+    from adaptdl_ray.adaptdl.config import default_device  # noqa: F401
+    import adaptdl_b200.ray.allocator
+    assert a2 is AdaptDLAllocator is adaptdl_b200.ray.allocator.AdaptDLAllocator
+    assert m2 is AdaptDLJobMixin
+    for name in ("controller", "worker", "launch_job", "optimizer", "utils"):
+        __import__("adaptdl_ray.aws." + name)
