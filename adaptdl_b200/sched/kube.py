@@ -28,6 +28,7 @@ class ApiError(Exception):
     def __init__(self, status, message=""):
         super().__init__("{} {}".format(status, message))
         self.status = status
+        self.message = message
 
 
 def job_key(job):

@@ -17,6 +17,7 @@ The rules are plain functions (:func:`verdict_for_create`,
 """
 
 import argparse
+import json
 import logging
 import ssl
 from http import HTTPStatus
@@ -47,11 +48,14 @@ def pod_of_template(job):
 
 
 async def verdict_for_create(cluster, namespace, job):
+    pod = pod_of_template(job)
+    if isinstance(cluster, _TemplateDryRun):
+        pod["_template"] = job["spec"].get("template")
     try:
-        await cluster.create_pod(namespace, pod_of_template(job),
-                                 dry_run=True)
+        await cluster.create_pod(namespace, pod, dry_run=True)
     except ApiError as exc:
-        return refuse("Invalid", str(exc))
+        return refuse("Invalid", exc.message
+                      if isinstance(cluster, _TemplateDryRun) else str(exc))
     spec = job["spec"]
     lowest = spec.get("minReplicas", 0)
     highest = spec.get("maxReplicas")
@@ -69,11 +73,42 @@ def verdict_for_update(old_job, new_job):
                                "after creation")
 
 
+class _TemplateDryRun(object):
+    """``create_pod``-shaped front of the Kubernetes core API for a
+    :class:`Validator` that was built without a cluster backend: the job's
+    pod template is submitted as a dry-run ``PodTemplate`` object (nothing is
+    persisted), the API server's own message is what the user gets back."""
+
+    def __init__(self):
+        import kubernetes_asyncio as kubernetes
+        self._kubernetes = kubernetes
+        self.core_api = kubernetes.client.CoreV1Api()
+
+    async def create_pod(self, namespace, pod, dry_run=True):
+        body = {"metadata": {"name": pod["metadata"].get("name")},
+                "template": pod.pop("_template")}
+        try:
+            await self.core_api.create_namespaced_pod_template(
+                namespace, body, dry_run="All")
+        except self._kubernetes.client.rest.ApiException as exc:
+            message = str(exc)
+            try:
+                message = json.loads(exc.body)["message"]
+            except (AttributeError, KeyError, TypeError, ValueError):
+                pass
+            raise ApiError(exc.status, message)
+
+
 class Validator(object):
     """The webhook server. ``cluster`` is a :mod:`adaptdl_b200.sched.kube`
-    backend (only ``create_pod(..., dry_run=True)`` is used)."""
+    backend (only ``create_pod(..., dry_run=True)`` is used); without one
+    (``Validator()``, as the reference constructs it) the checks go to the
+    in-cluster Kubernetes API directly (needs ``kubernetes_asyncio``)."""
 
-    def __init__(self, cluster):
+    def __init__(self, cluster=None):
+        if cluster is None:
+            cluster = _TemplateDryRun()
+            self._core_api = cluster.core_api
         self._cluster = cluster
         self._app = web.Application()
         self._app.router.add_get("/healthz", self._healthz)

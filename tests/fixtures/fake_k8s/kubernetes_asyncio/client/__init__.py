@@ -79,6 +79,16 @@ class CoreV1Api(object):
             STATE["events"].append(("pod", "ADDED", pod))
         return _Model(pod)
 
+    async def create_namespaced_pod_template(self, namespace, body,
+                                             dry_run=None):
+        spec = (body.get("template") or {}).get("spec") or {}
+        if not spec.get("containers"):
+            exc = ApiException(422, "Unprocessable Entity")
+            exc.body = ('{"kind": "Status", "message": "PodTemplate is '
+                        'invalid: template.spec.containers: Required value"}')
+            raise exc
+        return _Model(copy.deepcopy(body))
+
     async def delete_namespaced_pod(self, name, namespace):
         if (namespace, name) not in STATE["pods"]:
             raise ApiException(404, "not found")

@@ -94,3 +94,28 @@ def test_adapter_translates_requests_and_errors(k8s):
         await asyncio.wait_for(consume(), 5)
         assert ("job", "j1") in seen and ("pod", "p0") in seen
     asyncio.run(scenario())
+
+
+def test_validator_without_a_cluster_backend_asks_the_api_server(k8s):
+    """``Validator()`` (how the reference constructs it): the job's template
+    is checked with a dry-run PodTemplate creation and the API server's own
+    message comes back in the admission response."""
+    from adaptdl_b200.sched.validator import Validator, verdict_for_create
+    validator = Validator()
+    assert validator._core_api is validator._cluster.core_api
+
+    async def scenario():
+        bad = {"spec": {"template": {"spec": {"containers": []}}}}
+        verdict = await verdict_for_create(validator._cluster, "ns", bad)
+        assert not verdict["allowed"]
+        assert verdict["status"]["reason"] == "Invalid"
+        assert verdict["status"]["message"].startswith("PodTemplate is")
+        good = {"spec": {"minReplicas": 1, "maxReplicas": 2, "template": {
+            "spec": {"containers": [{"name": "main", "image": "x"}]}}}}
+        assert (await verdict_for_create(validator._cluster, "ns",
+                                         good))["allowed"]
+        good["spec"]["maxReplicas"] = 0
+        assert not (await verdict_for_create(validator._cluster, "ns",
+                                             good))["allowed"]
+        assert not k8s.STATE["pods"]          # nothing was persisted
+    asyncio.run(scenario())

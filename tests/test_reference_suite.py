@@ -16,15 +16,16 @@ through the ``__init__.py`` chain -- and a pytest subprocess runs them with
 (stand-ins for the third-party modules that are not installable here:
 ``portpicker``, legacy ``torchtext.data``).
 
+``validator_test.py`` needs the ``aiohttp_client`` fixture (aiohttp's own
+pytest plugin, loaded with ``-p``) and a ``kubernetes_asyncio`` module for its
+``ApiException`` (``tests/fixtures/fake_k8s``).
+
 Not run, and why:
 
-* ``sched/adaptdl_sched/validator_test.py`` -- every case replaces the private
-  attribute ``validator._core_api`` with a mock; this framework's validator is
-  built on a cluster backend object instead (``sched/validator.py``), the same
-  rules are tested in ``tests/test_sched.py``.
 * ``ray/adaptdl_ray/**`` -- they start a real Ray cluster (``ray.init``,
-  ``tune.run``); Ray is not installable here. ``tests/test_ray*.py`` drive the
-  same classes against recorded API fixtures.
+  ``tune.run``) or replace private members of the reference's controller;
+  Ray is not installable here. ``tests/test_ray*.py`` drive the same classes
+  against recorded API fixtures.
 
 The suite is skipped where the reference checkout does not exist (e.g. on the
 GPU box).
@@ -67,8 +68,7 @@ GROUPS = {
     "runtime_and_trainer": (
         ["adaptdl/adaptdl", "adaptdl/adaptdl/torch"], (), 750),
     "scheduler": (
-        ["sched/adaptdl_sched", "sched/adaptdl_sched/policy"],
-        ("validator_test.py",), 26),
+        ["sched/adaptdl_sched", "sched/adaptdl_sched/policy"], (), 30),
 }
 
 
@@ -93,7 +93,8 @@ def _run(tmp_path, group):
         os.path.join(ROOT, "baseline", "shims_test"),
         os.path.join(ROOT, "tests", "fixtures", "fake_k8s")])
     cmd = [sys.executable, "-m", "pytest", "-q", "--no-header",
-           "-p", "no:cacheprovider", "-W", "ignore", "--rootdir", str(work)]
+           "-p", "no:cacheprovider", "-p", "aiohttp.pytest_plugin",
+           "-W", "ignore", "--rootdir", str(work)]
     try:
         import xdist  # noqa: F401
         cmd += ["-n", str(min(4, os.cpu_count() or 1))]
@@ -127,5 +128,5 @@ def test_reference_runtime_and_trainer_tests_pass_unmodified(tmp_path):
 
 def test_reference_scheduler_tests_pass_unmodified(tmp_path):
     """Pollux policy (incl. non-preemptible jobs), speedup function, resource
-    arithmetic."""
+    arithmetic, admission webhook."""
     _run(tmp_path, "scheduler")
