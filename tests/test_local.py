@@ -8,6 +8,8 @@ import sys
 import time
 import urllib.request
 
+import pytest
+
 from adaptdl_b200.sched import local
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -215,3 +217,27 @@ def test_sigterm_during_startup_counts_as_preemption(tmp_path):
         state = job.poll()
         time.sleep(0.1)
     assert state == "preempted", (state, job.events)
+
+
+def test_unmodified_reference_script_is_rescaled_1_to_2_replicas(tmp_path):
+    """The reference's own examples/linear_regression/main.py (byte for
+    byte, through the ``adaptdl`` alias) as an elastic job of the single-box
+    scheduler: preempted at one replica (SIGTERM -> consensus -> checkpoint ->
+    exit 143), resumed at two from that checkpoint."""
+    script = "/root/reference/examples/linear_regression/main.py"
+    if not os.path.exists(script):
+        pytest.skip("reference checkout not available")
+    env = {"PYTHONPATH": ROOT, "CUDA_VISIBLE_DEVICES": "",
+           "OMP_NUM_THREADS": "1"}
+    job = local.LocalElasticJob(
+        [sys.executable, script, "--epochs", "100000"], 2,
+        checkpoint_dir=str(tmp_path), env=env)
+    state = job.run(schedule=[1, 2], interval=8.0, stop_after=20.0)
+    events = [(what, detail) for _, what, detail in job.events]
+    started = [d["replicas"] for w, d in events if w == "started"]
+    assert started[:2] == [1, 2], events
+    rescaled = [d for w, d in events if w == "rescaled"]
+    assert rescaled and rescaled[0]["replicas"] == 2, events
+    assert state in ("stopped", "finished")
+    assert any(name.startswith("checkpoint-")
+               for name in os.listdir(str(tmp_path)))
