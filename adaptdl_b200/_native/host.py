@@ -127,9 +127,15 @@ def load():
     if _lib is not None or _failed:
         return _lib
     try:
-        if is_stale():
-            build()
-        lib = _bind(ctypes.CDLL(LIB_PATH))
+        # a differently built copy (tools/sanitize_host.sh: ASan / UBSan /
+        # TSan instrumented) instead of the in-tree one
+        override = os.environ.get("ADAPTDL_B200_HOST_LIB")
+        if override:
+            lib = _bind(ctypes.CDLL(override))
+        else:
+            if is_stale():
+                build()
+            lib = _bind(ctypes.CDLL(LIB_PATH))
     except (OSError, RuntimeError, AttributeError) as exc:
         LOG.warning("host native library unavailable (%s); using the numpy "
                     "implementations", str(exc).splitlines()[0])
