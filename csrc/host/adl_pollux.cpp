@@ -373,8 +373,9 @@ struct Search {
       double sp = 0.0;
       tables[j].get(nodes, reps, &sp);
       double scaled = sp * weight[j];
+      // (memcmp's pointers must not be null even for zero bytes: an empty row has no storage)
       const bool moved = g.len(j) != base.len(j) ||
-          std::memcmp(g.row(j), base.row(j), sizeof(Entry) * g.len(j)) != 0;
+          (g.len(j) != 0 && std::memcmp(g.row(j), base.row(j), sizeof(Entry) * g.len(j)) != 0);
       if (moved) scaled *= 1.0 - restart_penalty;
       total += scaled;
     }
@@ -667,6 +668,7 @@ int adl_pollux_run(void* h) { return static_cast<Search*>(h)->run(); }
 int adl_pollux_missing(void* h, int32_t* job, int32_t* nodes, int32_t* replicas, int capacity) {
   Search* s = static_cast<Search*>(h);
   const int count = (int)std::min<size_t>(s->miss_job.size(), (size_t)std::max(capacity, 0));
+  if (count == 0) return 0;                      // nothing to copy (and data() may be null)
   std::memcpy(job, s->miss_job.data(), sizeof(int32_t) * count);
   std::memcpy(nodes, s->miss_nodes.data(), sizeof(int32_t) * count);
   std::memcpy(replicas, s->miss_rep.data(), sizeof(int32_t) * count);

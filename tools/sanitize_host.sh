@@ -20,7 +20,8 @@ cd "$(dirname "$0")/.."
 OUT=${SANITIZE_OUT:-profiles/r2_sanitize}
 mkdir -p "$OUT"
 SRC=csrc/host/adl_pollux.cpp
-CXX=${CXX:-g++}
+# not $CXX: a toolchain without the sanitizer runtimes may be configured there
+CXX=${SANITIZE_CXX:-/usr/bin/g++}
 STATUS=0
 run() {   # name, sanitizer flags, runtime library, runtime options
   local name=$1 flags=$2 runtime=$3 opts=$4
