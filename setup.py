@@ -55,8 +55,13 @@ setuptools.setup(
     description="Blackwell-native elastic data-parallel training engine with "
                 "adaptive batch size / learning rate and goodput-driven "
                 "scheduling",
-    packages=setuptools.find_packages(include=["adaptdl_b200",
-                                               "adaptdl_b200.*"]),
+    # adaptdl / adaptdl_sched / adaptdl_ray / adaptdl_cli: three-line alias
+    # packages that resolve the reference's import names to this framework
+    # (adaptdl_b200/compat.py), so scripts and manifests written for
+    # petuum/adaptdl keep working after `pip install`
+    packages=setuptools.find_packages(include=[
+        "adaptdl_b200", "adaptdl_b200.*", "adaptdl", "adaptdl_sched",
+        "adaptdl_ray", "adaptdl_cli"]),
     package_data={"adaptdl_b200._native": ["*.so"]},
     python_requires=">=3.9",
     install_requires=["numpy", "scipy", "torch>=2.1", "requests"],

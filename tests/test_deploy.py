@@ -5,6 +5,7 @@ import glob
 import os
 import re
 
+import pytest
 import yaml
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -87,9 +88,11 @@ def test_plain_manifests_parse():
     assert [group["name"] for group in tagged] == ["gpu"]
 
 
-def test_tutorial_job_goes_through_the_submit_path():
+@pytest.mark.parametrize("manifest", [("tutorial", "mnist-job.yaml"),
+                                      ("examples", "BERT", "adaptdljob.yaml")])
+def test_shipped_jobs_go_through_the_submit_path(manifest):
     from adaptdl_b200.cli import manifests
-    resource = yaml.safe_load(_read(ROOT, "tutorial", "mnist-job.yaml"))
+    resource = yaml.safe_load(_read(ROOT, *manifest))
     job, pvc = manifests.prepare_job(resource, "registry/img@sha256:0", [],
                                      name="tutorial")
     container = job["spec"]["template"]["spec"]["containers"][0]
@@ -105,9 +108,36 @@ def test_tutorial_job_goes_through_the_submit_path():
 def test_dockerfiles_copy_paths_that_exist():
     for rel in ("deploy/docker/Dockerfile.sched",
                 "deploy/docker/Dockerfile.trainer", "examples/Dockerfile",
-                "tutorial/Dockerfile"):
+                "examples/BERT/Dockerfile", "tutorial/Dockerfile"):
         for line in _read(ROOT, rel).splitlines():
             if line.startswith("COPY "):
                 for src in line.split()[1:-1]:
                     assert os.path.exists(os.path.join(ROOT, src)), \
                         (rel, src)
+
+
+def test_distribution_ships_the_reference_import_names_and_commands():
+    """``pip install`` must carry the alias packages (``import adaptdl`` ...)
+    and the reference's command names, or a switched-over user finds neither
+    after installing; images that build from a partial copy of the tree must
+    copy them too."""
+    import setuptools
+    text = _read(ROOT, "setup.py")
+    include = ["adaptdl_b200", "adaptdl_b200.*", "adaptdl", "adaptdl_sched",
+               "adaptdl_ray", "adaptdl_cli"]
+    for name in include:
+        assert '"{}"'.format(name) in text, name
+    found = set(setuptools.find_packages(ROOT, include=include))
+    assert {"adaptdl", "adaptdl_sched", "adaptdl_ray", "adaptdl_cli",
+            "adaptdl_b200.torch", "adaptdl_b200.sched.policy"} <= found
+    for script in ('"adaptdl=adaptdl_b200.cli.main:main"',
+                   '"adaptdl_on_ray_aws=adaptdl_b200.ray.aws.launch_job:main"'):
+        assert script in text, script
+    for rel in ("deploy/docker/Dockerfile.sched", "examples/Dockerfile",
+                "examples/BERT/Dockerfile", "tutorial/Dockerfile"):
+        copied = [line.split()[1] for line in _read(ROOT, rel).splitlines()
+                  if line.startswith("COPY ")]
+        if "." in copied:
+            continue
+        assert {"adaptdl", "adaptdl_sched", "adaptdl_ray",
+                "adaptdl_cli"} <= set(copied), rel
