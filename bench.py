@@ -141,7 +141,8 @@ def identity_collate(batch):
 
 class ClockSampler(object):
     """SM clock and throttle reasons of one GPU, sampled ONLY while a timed
-    window is open (``begin`` ... ``end``). NVML in-process (every 10 ms;
+    window is open (``begin`` ... ``end``). NVML in-process (every 25 ms,
+    plus one read from the timing loop itself in the middle of each window;
     a window of 20 ResNet steps is 40 ms, far too short for an
     ``nvidia-smi`` start-up); if ``pynvml`` is unusable, one long-running
     ``nvidia-smi -lms 50`` whose lines are kept while a window is open."""
@@ -154,7 +155,9 @@ class ClockSampler(object):
     REASON_BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown",
                    0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
                    0x80: "hw_power_brake_slowdown"}
-    PERIOD_S = 0.010
+    # sparse on purpose: the queries go through the driver of the GPU that
+    # is being timed, from a thread of the process that launches its work
+    PERIOD_S = 0.025
 
     def __init__(self, enabled, gpu_index, uuid=None):
         import threading

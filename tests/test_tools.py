@@ -236,7 +236,7 @@ def test_bench_clock_sampler_only_keeps_samples_inside_windows(monkeypatch):
     time.sleep(0.05)
     assert sampler.rows == [] and fake.calls == 0     # no window open yet
     sampler.begin()
-    time.sleep(0.12)
+    time.sleep(0.25)
     sampler.end()
     kept = len(sampler.rows)
     assert kept >= 3
