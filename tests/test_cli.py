@@ -1,4 +1,7 @@
 """CLI manifest construction (pure functions)."""
+import json
+import os
+import sys
 from datetime import datetime
 
 import pytest
@@ -255,3 +258,148 @@ def test_parser_accepts_the_reference_command_lines():
     for verb in ("delete", "list"):
         parser.parse_args(["tensorboard", verb] + (["tb"] if verb == "delete"
                                                    else []))
+
+
+def _run_cli(tmp_path, *argv, env_extra=None):
+    """``python -m adaptdl_b200.cli.main ...`` with stand-ins for kubectl
+    and docker in front of PATH (tests/fixtures/fake_bin); returns the
+    process plus the recorded kubectl / docker invocations."""
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    root = os.path.dirname(here)
+    klog, dlog = tmp_path / "kubectl.jsonl", tmp_path / "docker.jsonl"
+    env = dict(os.environ, PYTHONPATH=root,
+               PATH=os.path.join(here, "fixtures", "fake_bin") + os.pathsep
+               + os.environ["PATH"],
+               FAKE_KUBECTL_LOG=str(klog), FAKE_DOCKER_LOG=str(dlog),
+               KUBECONFIG=str(tmp_path / "no-kubeconfig"))
+    env.update(env_extra or {})
+    proc = subprocess.run(
+        [sys.executable, "-m", "adaptdl_b200.cli.main"] + list(argv),
+        env=env, cwd=str(tmp_path), stdout=subprocess.PIPE,
+        stderr=subprocess.STDOUT, text=True, timeout=120)
+
+    def rows(path):
+        if not path.exists():
+            return []
+        return [json.loads(line) for line in path.read_text().splitlines()]
+    return proc, rows(klog), rows(dlog)
+
+
+def test_submit_end_to_end_against_stand_in_kubectl_and_docker(tmp_path):
+    """``adaptdl submit``: image built and pushed, digest-pinned image and
+    the checkpoint volume in the job that is created, PVC owned by the job
+    (capabilities of cli/bin/adaptdl:183-316)."""
+    project = tmp_path / "proj"
+    project.mkdir()
+    (project / "Dockerfile").write_text("FROM scratch\n")
+    (project / "adaptdljob.yaml").write_text(
+        "apiVersion: adaptdl.petuum.com/v1\nkind: AdaptDLJob\n"
+        "metadata: {generateName: demo-}\n"
+        "spec:\n  template:\n    spec:\n      containers:\n"
+        "      - {name: main, command: [python3, train.py]}\n")
+    proc, kube, docker = _run_cli(
+        tmp_path, "submit", str(project), "--checkpoint-storage-size", "2Gi",
+        env_extra={"ADAPTDL_SUBMIT_REPO": "registry.example/team/img"})
+    assert proc.returncode == 0, proc.stdout
+    assert "submitted" in proc.stdout
+    assert [d[:2] for d in docker] == [["build", "-t"], ["push",
+                                                         "registry.example"
+                                                         "/team/img"],
+                                       ["image", "inspect"]]
+    created = [json.loads(k["stdin"]) for k in kube
+               if k["argv"][:1] == ["create"]]
+    job, pvc = created
+    assert job["kind"] == "AdaptDLJob"
+    container = job["spec"]["template"]["spec"]["containers"][0]
+    assert container["image"] == "registry.example/team/img@sha256:" \
+        + "0" * 64
+    env = {e["name"]: e.get("value") for e in container["env"]}
+    assert env["ADAPTDL_CHECKPOINT_PATH"] == "/adaptdl/checkpoint"
+    assert pvc["kind"] == "PersistentVolumeClaim"
+    assert pvc["spec"]["storageClassName"] == "efs"      # cluster default
+    assert pvc["spec"]["resources"]["requests"]["storage"] == "2Gi"
+    assert pvc["metadata"]["ownerReferences"][0]["kind"] == "AdaptDLJob"
+    claim = [v for v in job["spec"]["template"]["spec"]["volumes"]
+             if v["name"] == "adaptdl-pvc"][0]
+    assert claim["persistentVolumeClaim"]["claimName"] == \
+        pvc["metadata"]["name"]
+
+
+def test_ls_logs_cp_and_tensorboard_commands_end_to_end(tmp_path):
+    proc, kube, _ = _run_cli(tmp_path, "ls")
+    assert proc.returncode == 0, proc.stdout
+    assert "job-abc" in proc.stdout and "Running" in proc.stdout
+
+    proc, kube, _ = _run_cli(tmp_path, "logs", "job-abc", "-f")
+    assert proc.returncode == 0, proc.stdout
+    assert "line from replica 0" in proc.stdout
+    assert kube[-1]["argv"] == ["logs", "-l", "adaptdl/job=job-abc", "-f"]
+
+    proc, kube, _ = _run_cli(tmp_path, "cp", "job-abc:/adaptdl/checkpoint/x",
+                             "out")
+    assert proc.returncode == 0, proc.stdout
+    verbs = [k["argv"][0] for k in kube if k["argv"][0] in
+             ("get", "create", "wait", "cp", "delete")][-5:]
+    assert verbs == ["get", "create", "wait", "cp", "delete"], kube
+    copy_pod = json.loads([k for k in kube
+                           if k["argv"][0] == "create"][-1]["stdin"])
+    volume = copy_pod["spec"]["volumes"][0]["persistentVolumeClaim"]
+    assert volume["claimName"] == "adaptdl-pvc-1234"
+    cp_call = [k["argv"] for k in kube if k["argv"][0] == "cp"][-1]
+    assert cp_call[1].endswith(":/adaptdl_pvc/adaptdl/checkpoint/x")
+    assert cp_call[2] == "out"
+    proc, _, _ = _run_cli(tmp_path, "cp", "job-abc:relative/path", "out")
+    assert proc.returncode != 0 and "absolute path" in proc.stdout
+
+    proc, kube, _ = _run_cli(tmp_path, "tensorboard", "create", "tb1",
+                             "--storageclass", "gp2", "--size", "3Gi",
+                             "--nodeport")
+    assert proc.returncode == 0, proc.stdout
+    kinds = [json.loads(k["stdin"])["kind"] for k in kube
+             if k["argv"][0] == "create"][-3:]
+    assert sorted(kinds) == ["Deployment", "PersistentVolumeClaim",
+                             "Service"]
+    proc, _, _ = _run_cli(tmp_path, "tensorboard", "list")
+    assert proc.returncode == 0 and "tb1" in proc.stdout
+    proc, kube, _ = _run_cli(tmp_path, "tensorboard", "delete", "tb1")
+    assert proc.returncode == 0, proc.stdout
+    deleted = [k["argv"][1:3] for k in kube if k["argv"][0] == "delete"][-3:]
+    assert deleted == [["deployment", "adaptdl-tensorboard-tb1"],
+                       ["service", "adaptdl-tensorboard-tb1"],
+                       ["pvc", "adaptdl-tensorboard-tb1"]]
+
+
+def test_submit_through_the_in_cluster_registry(tmp_path):
+    """Without ``ADAPTDL_SUBMIT_REPO`` the image goes to the chart's
+    insecure registry through a local tunnel (API-server proxy, or ``kubectl
+    port-forward`` when the kubeconfig cannot be used -- the case here) and
+    the job pulls it from the node-local address."""
+    project = tmp_path / "proj"
+    project.mkdir()
+    (project / "Dockerfile").write_text("FROM scratch\n")
+    (project / "job.yaml").write_text(
+        "apiVersion: adaptdl.petuum.com/v1\nkind: AdaptDLJob\n"
+        "metadata: {generateName: demo-}\n"
+        "spec:\n  template:\n    spec:\n      containers:\n"
+        "      - {name: main, command: [python3, train.py]}\n")
+    proc, kube, docker = _run_cli(
+        tmp_path, "submit", str(project), "-f", str(project / "job.yaml"),
+        "--proxy-port", "59999", "--pod-per-node", "--", "--epochs", "3")
+    assert proc.returncode == 0, proc.stdout
+    assert docker[0][:3] == ["build", "-t", "localhost:59999/adaptdl-submit"]
+    assert docker[1] == ["push", "localhost:59999/adaptdl-submit"]
+    assert any(k["argv"][:2] == ["port-forward", "service/adaptdl-registry"]
+               for k in kube), kube
+    job = json.loads([k for k in kube
+                      if k["argv"][:1] == ["create"]][0]["stdin"])
+    container = job["spec"]["template"]["spec"]["containers"][0]
+    assert container["image"].startswith(
+        "localhost:32000/adaptdl-submit@sha256:")
+    assert job["spec"]["podPerNode"] is True
+    # python commands are wrapped in the replica launcher, user arguments
+    # are appended
+    assert container["command"][:4] == ["python3", "-m",
+                                        "adaptdl_b200.launch", "train.py"]
+    assert (container.get("args") or container["command"])[-2:] == \
+        ["--epochs", "3"]
