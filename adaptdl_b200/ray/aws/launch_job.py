@@ -20,7 +20,8 @@ def main(argv=None):
     parser.add_argument("--gpus", type=int, default=0)
     parser.add_argument("--port-offset", type=int, default=0)
     parser.add_argument("--checkpoint-timeout", type=int, default=120)
-    parser.add_argument("--rescale-timeout", type=int, default=60)
+    parser.add_argument("--rescale-timeout", "--cluster-rescale-timeout",
+                        dest="rescale_timeout", type=int, default=60)
     parser.add_argument("arguments", nargs=argparse.REMAINDER)
     args = parser.parse_args(argv)
     script_args = args.arguments[1:] if args.arguments[:1] == ["--"] \

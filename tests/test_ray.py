@@ -167,3 +167,15 @@ def test_ray_missing_is_reported_clearly():
         require_ray()
     with pytest.raises(ImportError):
         from adaptdl_b200.ray.tune import AdaptDLScheduler  # noqa: F401
+
+
+def test_launch_job_parses_the_reference_command_line(tmp_path):
+    """Every flag of the reference's ``adaptdl_on_ray_aws`` (ray/adaptdl_ray/
+    aws/launch_job.py) is accepted; parsing ends at the missing script."""
+    from adaptdl_b200.ray.aws.launch_job import main
+    with pytest.raises(SystemExit) as exc:
+        main(["-f", "train.py", "-u", "auto", "-m", "4", "--gpus", "1",
+              "--cpus", "2", "--port-offset", "100", "-d", str(tmp_path),
+              "--checkpoint-timeout", "30", "--cluster-rescale-timeout", "5",
+              "--", "--epochs", "1"])
+    assert "train.py not found" in str(exc.value)
