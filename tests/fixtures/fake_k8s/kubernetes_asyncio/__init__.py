@@ -5,4 +5,4 @@ behind them. Objects are returned the way the real client returns them --
 model objects with ``to_dict`` for the core API, plain dicts for custom
 objects -- so the adapter's ``sanitize_for_serialization`` path is
 exercised."""
-from . import client, watch  # noqa: F401
+from . import client, config, watch  # noqa: F401

@@ -119,3 +119,93 @@ def test_validator_without_a_cluster_backend_asks_the_api_server(k8s):
                                              good))["allowed"]
         assert not k8s.STATE["pods"]          # nothing was persisted
     asyncio.run(scenario())
+
+
+def _seed_file(tmp_path):
+    import json
+    job = {"apiVersion": "adaptdl.petuum.com/v1", "kind": "AdaptDLJob",
+           "metadata": {"name": "j1", "namespace": "ns", "uid": "u1",
+                        "creationTimestamp": "2026-01-01T00:00:00Z"},
+           "spec": {"template": {"spec": {"containers": [
+               {"name": "main", "image": "x", "resources": {
+                   "limits": {"nvidia.com/gpu": 1}}}]}}},
+           "status": {"phase": "Running", "group": 0,
+                      "allocation": ["n0", "n0"], "replicas": 2}}
+    pods = [{"metadata": {"name": "j1-{}".format(rank), "namespace": "ns",
+                          "labels": {"adaptdl/job": "j1"},
+                          "annotations": {"adaptdl/group": "0",
+                                          "adaptdl/replicas": "2",
+                                          "adaptdl/rank": str(rank)}},
+             "spec": {"nodeName": "n0", "containers": [
+                 {"name": "main", "image": "x"}]},
+             "status": {"phase": "Running",
+                        "podIP": "10.0.0.{}".format(rank + 1)}}
+            for rank in range(2)]
+    node = {"metadata": {"name": "n0", "labels": {}},
+            "status": {"allocatable": {"nvidia.com/gpu": "8", "pods": "110",
+                                       "cpu": "64", "memory": "512Gi"}},
+            "spec": {}}
+    path = tmp_path / "state.json"
+    path.write_text(json.dumps({"nodes": [node], "jobs": [job],
+                                "pods": pods}))
+    return str(path)
+
+
+@pytest.mark.parametrize("module", ["adaptdl_sched", "adaptdl_sched.allocator",
+                                    "adaptdl_sched.supervisor"])
+def test_scheduler_containers_start_with_the_reference_commands(tmp_path,
+                                                                module):
+    """The three long-running scheduler processes, started the way the
+    reference's chart starts them (``python -m adaptdl_sched[...]``), come up
+    against the stand-in API server, stay up, and the supervisor answers a
+    replica's rendezvous and hints requests."""
+    import json
+    import signal
+    import socket
+    import subprocess
+    import time
+    import urllib.request
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([root, FIXTURE]),
+               FAKE_K8S_STATE=_seed_file(tmp_path),
+               ADAPTDL_SUPERVISOR_SERVICE_PORT=str(port),
+               ADAPTDL_NAMESPACE="ns")
+    log = open(str(tmp_path / "out.log"), "w")
+    proc = subprocess.Popen([sys.executable, "-m", module], env=env,
+                            cwd=str(tmp_path), stdout=log,
+                            stderr=subprocess.STDOUT)
+    try:
+        if module.endswith("supervisor"):
+            base = "http://127.0.0.1:{}".format(port)
+            deadline = time.time() + 60
+            while True:
+                try:
+                    urllib.request.urlopen(base + "/healthz", timeout=2)
+                    break
+                except OSError:
+                    assert proc.poll() is None and time.time() < deadline, \
+                        open(log.name).read()[-3000:]
+                    time.sleep(0.2)
+            with urllib.request.urlopen(
+                    base + "/discover/ns/j1/0?timeout=5") as resp:
+                assert json.loads(resp.read()) == ["10.0.0.1", "10.0.0.2"]
+            body = json.dumps({"initBatchSize": 128}).encode()
+            req = urllib.request.Request(base + "/hints/ns/j1", data=body,
+                                         method="PUT")
+            with urllib.request.urlopen(req) as resp:
+                assert resp.status == 200
+        else:
+            time.sleep(6.0)           # imports + a few loop iterations
+        assert proc.poll() is None, open(log.name).read()[-3000:]
+    finally:
+        proc.send_signal(signal.SIGTERM)
+        try:
+            proc.wait(timeout=20)
+        except subprocess.TimeoutExpired:
+            proc.kill()
+        log.close()
+    text = open(log.name).read()
+    assert "Traceback" not in text, text[-3000:]
