@@ -17,6 +17,7 @@ itself needs Ray.
 import asyncio
 import copy
 import logging
+import os
 import time
 import uuid
 
@@ -116,8 +117,12 @@ def make_controller_actor():
         def __init__(self, cluster_size, rescale_timeout=120):
             self._cluster_size = cluster_size
             self._rescale_timeout = rescale_timeout
-            self._url = "http://{}:8080".format(
-                ray.util.get_node_ip_address())
+            # the reference's fixed port; overridable where 8080 is taken
+            self._port = int(os.environ.get(
+                "ADAPTDL_B200_RAY_CONTROLLER_PORT", "8080"))
+            self._url = "http://{}:{}".format(
+                os.environ.get("ADAPTDL_B200_RAY_CONTROLLER_HOST")
+                or ray.util.get_node_ip_address(), self._port)
             self._job = None
             self._terminating = set()
             self._force = asyncio.Event()
@@ -139,11 +144,22 @@ def make_controller_actor():
                 web.put("/hints/{ns}/{name}", self._hints)])
             self._runner = web.AppRunner(app)
             await self._runner.setup()
-            await web.TCPSite(self._runner, "0.0.0.0", 8080).start()
+            await web.TCPSite(self._runner, "0.0.0.0", self._port).start()
             self._ready.set()
 
         async def _discover(self, request):
-            ips = [ip for _, ip in sorted(self._job.workers.items())]
+            # a worker registers itself with a fire-and-forget call just
+            # before its script starts, so the first replicas can ask before
+            # the last one is known: hold the answer until the generation is
+            # complete (408 = "ask again", what the trainer's client expects)
+            job = self._job
+            deadline = time.monotonic() + float(
+                request.query.get("timeout", "30"))
+            while not job.tasks or len(job.workers) < len(job.tasks):
+                if time.monotonic() >= deadline:
+                    return web.json_response(None, status=408)
+                await asyncio.sleep(0.1)
+            ips = [ip for _, ip in sorted(job.workers.items())]
             return web.json_response(ips)
 
         async def _hints(self, request):

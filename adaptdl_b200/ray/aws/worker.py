@@ -65,11 +65,40 @@ def worker_environment(job_key, job_uid, rank, replicas, num_restarts,
     }
 
 
+def _forget_previous_generation():
+    """Ray reuses idle worker processes: a task of the next generation can
+    land in the process that ran the previous one to its checkpoint (the
+    script left through ``SystemExit``, the process lived on). The
+    framework's process-global state -- control-plane connection, torch
+    process group, state registry, epoch / loader / metrics singletons, exit
+    flag -- belongs to that finished generation and must go before the
+    script starts again."""
+    if "adaptdl_b200.torch" not in sys.modules and \
+            "adaptdl_b200.collective" not in sys.modules:
+        return
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:  # noqa: BLE001
+        LOG.warning("could not destroy the previous process group",
+                    exc_info=True)
+    from adaptdl_b200 import collective
+    if collective.is_initialized():
+        try:
+            collective.teardown()
+        except Exception:  # noqa: BLE001
+            pass
+    from adaptdl_b200.utils.testing import reset_global_state
+    reset_global_state()
+
+
 def run_script(path, argv, environment, checkpoint=None):
     """Execute the user's training script as ``__main__`` inside this
     process. Returns ``(Status, checkpoint_obj|None)``; a ``SystemExit``
     (rescale request: the trainer checkpointed and exited with 143) yields
     the serialised checkpoint directory."""
+    _forget_previous_generation()
     os.environ.update(environment)
     ckpt_dir = environment["ADAPTDL_CHECKPOINT_PATH"]
     shutil.rmtree(ckpt_dir, ignore_errors=True)

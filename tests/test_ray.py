@@ -179,3 +179,58 @@ def test_launch_job_parses_the_reference_command_line(tmp_path):
               "--checkpoint-timeout", "30", "--cluster-rescale-timeout", "5",
               "--", "--epochs", "1"])
     assert "train.py not found" in str(exc.value)
+
+
+def _run_ray_aws_job(tmp_path, *extra, epochs="30"):
+    import json
+    import socket
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    root = os.path.dirname(here)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    env = {k: v for k, v in os.environ.items()
+           if not k.startswith("ADAPTDL_")}
+    env["PYTHONPATH"] = os.pathsep.join(
+        [root, os.path.join(here, "fixtures", "fake_ray")])
+    env["OMP_NUM_THREADS"] = "1"
+    script = os.path.join(root, "examples", "linear_regression", "main.py")
+    proc = subprocess.run(
+        [sys.executable, os.path.join(here, "ray_aws_job.py"), script,
+         str(port)] + list(extra) + ["--", "--epochs", epochs, "--size",
+                                     "2000"],
+        env=env, cwd=str(tmp_path), stdout=subprocess.PIPE,
+        stderr=subprocess.PIPE, text=True, timeout=300)
+    assert proc.returncode == 0, proc.stderr[-3000:]
+    lines = [ln for ln in proc.stdout.splitlines() if ln.startswith("{")]
+    assert lines, proc.stdout[-2000:] + proc.stderr[-2000:]
+    return json.loads(lines[-1]), proc.stderr
+
+
+def test_ray_aws_controller_runs_a_job_to_completion(tmp_path):
+    """The controller actor end to end on the in-process stand-in for Ray
+    (reference scenario: ray/adaptdl_ray/aws/test_controller.py): worker
+    task started on the first allocation, the training script finds rank 0
+    through the controller's ``/discover``, its hints arrive at ``/hints``,
+    the job ends ``SUCCEEDED``."""
+    out, _ = _run_ray_aws_job(tmp_path)
+    assert out["status"] == 1, out                  # Status.SUCCEEDED
+    assert out["generations"] >= 1
+    assert ["actor", "Controller"] in out["calls"]
+    assert ["task", "run_adaptdl"] in out["calls"]
+    assert ["task", "listen_for_spot_termination"] in out["calls"]
+    assert out["resource_requests"] >= 1            # autoscaler was asked
+
+
+def test_ray_aws_controller_moves_the_job_off_a_spot_node(tmp_path):
+    """A spot-termination notice on the worker's node: the node is excluded,
+    the worker is cancelled (SIGINT -> checkpoint -> exit 143), its
+    checkpoint travels through the object store, and the next generation
+    resumes from it on the other node and finishes."""
+    out, err = _run_ray_aws_job(tmp_path, "--spot-after", "4", epochs="1200")
+    assert out["status"] == 1, (out, err[-2000:])
+    assert out["terminating"] == ["127.0.0.1"], out
+    assert out["generations"] >= 2 and out["had_checkpoint"], out
+    assert ["cancel", None] in out["calls"]
