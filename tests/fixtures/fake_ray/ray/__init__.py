@@ -9,8 +9,8 @@ imported, subclass their Ray bases and be driven through their callbacks."""
 __version__ = "2.9.0+fixture"
 
 from . import _actors, autoscaler, util  # noqa: E402,F401
-from ._actors import (cancel, get, get_actor, put,  # noqa: E402,F401
-                      remote)
+from ._actors import (cancel, get, get_actor, kill,  # noqa: E402,F401
+                      put, remote, wait)
 
 _NODES = [
     {"NodeManagerAddress": "10.0.0.1", "Alive": True,

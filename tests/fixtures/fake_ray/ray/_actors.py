@@ -45,6 +45,18 @@ class _Method(object):
         fn = getattr(self._handle._obj, self._name)
         loop = self._handle._loop
         future = concurrent.futures.Future()
+        if loop is None:
+            # threaded actor (created outside an event loop; Ray:
+            # max_concurrency > 1): every call in its own thread
+            def run():
+                _LOCAL.ip = WORKER_IP
+                try:
+                    future.set_result(fn(*args, **kwargs))
+                except BaseException as exc:  # noqa: BLE001
+                    future.set_exception(exc)
+            threading.Thread(target=run, daemon=True,
+                             name="ray-actor-" + self._name).start()
+            return ObjectRef(future)
 
         async def call():
             try:
@@ -81,7 +93,10 @@ class ActorClass(object):
         return ActorClass(self._cls, dict(self._options, **kwargs))
 
     def remote(self, *args, **kwargs):
-        loop = asyncio.get_event_loop()
+        try:
+            loop = asyncio.get_running_loop()
+        except RuntimeError:
+            loop = None
         handle = ActorHandle(self._cls(*args, **kwargs), loop)
         CALLS.append(("actor", self._cls.__name__, dict(self._options)))
         if self._options.get("name"):
@@ -164,3 +179,15 @@ def cancel(ref, force=False):
 
 def get_actor(name):
     return _ACTORS[name]
+
+
+def wait(refs, num_returns=1, timeout=None):
+    refs = list(refs)
+    concurrent.futures.wait([r.future for r in refs], timeout=timeout)
+    done = [r for r in refs if r.future.done()]
+    return done[:num_returns] if len(done) > num_returns else done, \
+        [r for r in refs if not r.future.done()]
+
+
+def kill(actor, no_restart=True):
+    CALLS.append(("kill", type(actor._obj).__name__, {}))

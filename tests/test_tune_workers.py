@@ -100,3 +100,30 @@ def test_elastic_trial_save_and_restore_in_a_clone():
         assert clone.step() == {"done": True}
     finally:
         clone.stop()
+
+
+@pytest.mark.timeout(300)
+def test_ray_actor_spawner_rescales_through_an_in_memory_checkpoint(tmp_path):
+    """``RayActorSpawner`` (replicas as Ray actors, the production path of
+    the Tune trainable) on the in-process stand-in for Ray's actor calls:
+    same scenario as the process spawner above."""
+    import json
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = {k: v for k, v in os.environ.items()
+           if not k.startswith("ADAPTDL_")}
+    env.update(ENV)
+    env["PYTHONPATH"] = os.pathsep.join(
+        [ROOT, os.path.join(here, "fixtures", "fake_ray"), here])
+    proc = subprocess.run(
+        [sys.executable, os.path.join(here, "ray_tune_actor_job.py")],
+        env=env, cwd=str(tmp_path), stdout=subprocess.PIPE,
+        stderr=subprocess.PIPE, text=True, timeout=280)
+    assert proc.returncode == 0, proc.stderr[-3000:]
+    out = json.loads([ln for ln in proc.stdout.splitlines()
+                      if ln.startswith("{")][-1])
+    assert out["first_epochs"] == [0, 1, 2] and not out["finished_first"]
+    assert out["snapshot_files"][0].startswith("checkpoint-0")
+    assert out["resumed_at"] >= 3 and out["restarts"] == 1
+    assert out["finished"] and out["last_epoch"] == 11
+    assert out["calls"].count(["actor", "Replica"]) == 2
