@@ -28,3 +28,36 @@ class PlacementGroupFactory(object):
 
     def __hash__(self):
         return hash(repr(self._bundles))
+
+
+class Trainable(object):
+    """``ray.tune.Trainable`` as Tune drives it: ``setup`` once,
+    ``train()`` -> ``step()``, ``save()`` -> ``save_checkpoint``,
+    ``restore(state)`` -> ``load_checkpoint``, ``stop()`` -> ``cleanup``."""
+
+    def __init__(self, config=None, trial_id="trial_0", **kwargs):
+        self.config = dict(config or {})
+        self.trial_id = trial_id
+        self.iteration = 0
+        self.setup(self.config)
+
+    def setup(self, config):
+        pass
+
+    def train(self):
+        result = self.step()
+        self.iteration += 1
+        result.setdefault("training_iteration", self.iteration)
+        return result
+
+    def save(self, checkpoint_dir=None):
+        return self.save_checkpoint(checkpoint_dir)
+
+    def restore(self, state):
+        self.load_checkpoint(state)
+
+    def stop(self):
+        self.cleanup()
+
+    def cleanup(self):
+        pass

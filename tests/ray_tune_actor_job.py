@@ -35,12 +35,44 @@ while True:
     if result is None:
         break
     last = result
+group.shutdown()
+
+# the same thing one level up: the Tune trainable built by
+# AdaptDLTrainableCreator, driven the way Tune drives a Trainable (train /
+# save / stop, then restore in a clone and train to the end)
+_forget_previous_generation()
+from adaptdl_b200.ray.tune import AdaptDLTrainableCreator  # noqa: E402
+cls = AdaptDLTrainableCreator(tune_workload.train_fn, num_workers=1,
+                              resources_per_replica={"CPU": 1})
+trial = cls(config={"lr": 0.05, "epochs": 8, "pause": 0.05},
+            trial_id="t1")
+steps = [trial.train() for _ in range(2)]
+state = trial.save()
+trial.stop()
+_forget_previous_generation()
+clone = cls(config={"lr": 0.05, "epochs": 8, "pause": 0.05}, trial_id="t1")
+clone.restore(state)
+tail = []
+while True:
+    result = clone.train()
+    if result.get("done"):
+        break
+    tail.append(result)
+clone.stop()
+trainable = {
+    "name": cls.__name__, "first": [r["epoch"] for r in steps],
+    "generation_saved": state["generation"],
+    "resumed": [r["epoch"] for r in tail][:1] + [r["epoch"]
+                                                 for r in tail][-1:],
+    "resumed_generation": tail[0]["generation"],
+    "resources": cls.default_resource_request({}).bundles}
+
 print(json.dumps({
+    "trainable": trainable,
     "first_epochs": [r["epoch"] for r in seen],
     "finished_first": finished_first,
     "snapshot_files": sorted(snapshot)[:3],
     "resumed_at": first["epoch"], "restarts": first["restarts"],
     "last_epoch": last["epoch"], "finished": group.finished,
     "calls": [[k, n] for k, n, _ in ray._actors.CALLS]}))
-group.shutdown()
 os._exit(0)

@@ -126,4 +126,12 @@ def test_ray_actor_spawner_rescales_through_an_in_memory_checkpoint(tmp_path):
     assert out["snapshot_files"][0].startswith("checkpoint-0")
     assert out["resumed_at"] >= 3 and out["restarts"] == 1
     assert out["finished"] and out["last_epoch"] == 11
-    assert out["calls"].count(["actor", "Replica"]) == 2
+    assert out["calls"].count(["actor", "Replica"]) == 4
+    # ... and the Tune trainable of AdaptDLTrainableCreator on top of it
+    trainable = out["trainable"]
+    assert trainable["name"] == "AdaptDL_train_fn"
+    assert trainable["first"] == [0, 1]
+    assert trainable["generation_saved"] == 1
+    assert trainable["resumed_generation"] == 1
+    assert trainable["resumed"][0] >= 2 and trainable["resumed"][1] == 7
+    assert len(trainable["resources"]) == 2        # driver + one replica
