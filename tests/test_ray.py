@@ -229,7 +229,7 @@ def test_ray_aws_controller_moves_the_job_off_a_spot_node(tmp_path):
     the worker is cancelled (SIGINT -> checkpoint -> exit 143), its
     checkpoint travels through the object store, and the next generation
     resumes from it on the other node and finishes."""
-    out, err = _run_ray_aws_job(tmp_path, "--spot-after", "4", epochs="1200")
+    out, err = _run_ray_aws_job(tmp_path, "--spot-after", "4", epochs="1500")
     assert out["status"] == 1, (out, err[-2000:])
     assert out["terminating"] == ["127.0.0.1"], out
     assert out["generations"] >= 2 and out["had_checkpoint"], out
