@@ -158,5 +158,12 @@ def serve(port):
     """Serve the exposition from a background thread (allocator container)."""
     if _prom is None:
         return False
-    _prom.start_http_server(port)
+    try:
+        _prom.start_http_server(port)
+    except OSError as exc:
+        # observability must not take the allocator down with it
+        import logging
+        logging.getLogger(__name__).warning(
+            "metrics endpoint not started on port %s: %s", port, exc)
+        return False
     return True
