@@ -162,8 +162,7 @@ def serve(port):
         _prom.start_http_server(port)
     except OSError as exc:
         # observability must not take the allocator down with it
-        import logging
-        logging.getLogger(__name__).warning(
-            "metrics endpoint not started on port %s: %s", port, exc)
+        LOG.warning("metrics endpoint not started on port %s: %s", port,
+                    exc)
         return False
     return True
