@@ -12,6 +12,18 @@ def reset():
         value.clear()
 
 
+def _dump():
+    """``FAKE_K8S_DUMP``: keep a JSON copy of the pods on disk so that a test
+    can watch what a scheduler process it started has created."""
+    import json
+    import os
+    path = os.environ.get("FAKE_K8S_DUMP")
+    if path:
+        with open(path + ".tmp", "w") as f:
+            json.dump(list(STATE["pods"].values()), f)
+        os.replace(path + ".tmp", path)
+
+
 class _Model(object):
     """What the generated client returns for core objects."""
 
@@ -77,6 +89,7 @@ class CoreV1Api(object):
         if dry_run != "All":
             STATE["pods"][key] = pod
             STATE["events"].append(("pod", "ADDED", pod))
+            _dump()
         return _Model(pod)
 
     async def create_namespaced_pod_template(self, namespace, body,

@@ -209,3 +209,53 @@ def test_scheduler_containers_start_with_the_reference_commands(tmp_path,
         log.close()
     text = open(log.name).read()
     assert "Traceback" not in text, text[-3000:]
+
+
+def test_controller_process_creates_the_pods_of_an_allocated_job(tmp_path):
+    """``python -m adaptdl_sched`` (the controller container) against the
+    stand-in API server: a job that has an allocation but no pods gets one
+    pod per replica, with the replica's rank / world size in its
+    environment (the contract of controller.py:310-420 in the reference)."""
+    import json
+    import signal
+    import subprocess
+    import time
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    seed = json.loads(open(_seed_file(tmp_path)).read())
+    seed["pods"] = []
+    seed["jobs"][0]["status"] = {"phase": "Pending", "group": 0,
+                                 "allocation": ["n0", "n0"]}
+    (tmp_path / "state.json").write_text(json.dumps(seed))
+    dump = tmp_path / "pods.json"
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([root, FIXTURE]),
+               FAKE_K8S_STATE=str(tmp_path / "state.json"),
+               FAKE_K8S_DUMP=str(dump), ADAPTDL_NAMESPACE="ns")
+    log = open(str(tmp_path / "out.log"), "w")
+    proc = subprocess.Popen([sys.executable, "-m", "adaptdl_sched"], env=env,
+                            cwd=str(tmp_path), stdout=log,
+                            stderr=subprocess.STDOUT)
+    try:
+        deadline = time.time() + 90
+        pods = []
+        while time.time() < deadline and len(pods) < 2:
+            assert proc.poll() is None, open(log.name).read()[-3000:]
+            if dump.exists():
+                pods = json.loads(dump.read_text())
+            time.sleep(0.3)
+        assert len(pods) == 2, open(log.name).read()[-3000:]
+    finally:
+        proc.send_signal(signal.SIGTERM)
+        try:
+            proc.wait(timeout=20)
+        except subprocess.TimeoutExpired:
+            proc.kill()
+        log.close()
+    ranks = []
+    for pod in pods:
+        assert pod["metadata"]["labels"]["adaptdl/job"] == "j1"
+        assert "n0" in json.dumps(pod["spec"])        # pinned to its node
+        env_vars = {e["name"]: e.get("value")
+                    for e in pod["spec"]["containers"][0]["env"]}
+        assert env_vars["ADAPTDL_NUM_REPLICAS"] == "2"
+        ranks.append(env_vars["ADAPTDL_REPLICA_RANK"])
+    assert sorted(ranks) == ["0", "1"]
