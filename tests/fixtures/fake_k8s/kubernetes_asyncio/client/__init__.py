@@ -14,13 +14,14 @@ def reset():
 
 def _dump():
     """``FAKE_K8S_DUMP``: keep a JSON copy of the pods on disk so that a test
-    can watch what a scheduler process it started has created."""
+    can watch what a scheduler process it started has created / patched."""
     import json
     import os
     path = os.environ.get("FAKE_K8S_DUMP")
     if path:
         with open(path + ".tmp", "w") as f:
-            json.dump(list(STATE["pods"].values()), f)
+            json.dump({"pods": list(STATE["pods"].values()),
+                       "jobs": list(STATE["jobs"].values())}, f)
         os.replace(path + ".tmp", path)
 
 
@@ -138,4 +139,5 @@ class CustomObjectsApi(object):
         job = STATE["jobs"][(namespace, name)]
         job.setdefault("status", {}).update(body.get("status", {}))
         STATE["events"].append(("job", "MODIFIED", job))
+        _dump()
         return copy.deepcopy(job)

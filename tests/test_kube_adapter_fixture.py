@@ -240,7 +240,7 @@ def test_controller_process_creates_the_pods_of_an_allocated_job(tmp_path):
         while time.time() < deadline and len(pods) < 2:
             assert proc.poll() is None, open(log.name).read()[-3000:]
             if dump.exists():
-                pods = json.loads(dump.read_text())
+                pods = json.loads(dump.read_text())["pods"]
             time.sleep(0.3)
         assert len(pods) == 2, open(log.name).read()[-3000:]
     finally:
@@ -259,3 +259,45 @@ def test_controller_process_creates_the_pods_of_an_allocated_job(tmp_path):
         assert env_vars["ADAPTDL_NUM_REPLICAS"] == "2"
         ranks.append(env_vars["ADAPTDL_REPLICA_RANK"])
     assert sorted(ranks) == ["0", "1"]
+
+
+def test_allocator_process_gives_a_new_job_its_first_allocation(tmp_path):
+    """``python -m adaptdl_sched.allocator`` against the stand-in API server:
+    a job without an allocation is placed right away (the fast path that
+    does not wait for the next optimisation cycle; allocator.py:48-80 in the
+    reference) and the decision is written to the job's status."""
+    import json
+    import signal
+    import subprocess
+    import time
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    seed = json.loads(open(_seed_file(tmp_path)).read())
+    seed["pods"] = []
+    seed["jobs"][0]["status"] = {"phase": "Pending"}
+    (tmp_path / "state.json").write_text(json.dumps(seed))
+    dump = tmp_path / "state-now.json"
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([root, FIXTURE]),
+               FAKE_K8S_STATE=str(tmp_path / "state.json"),
+               FAKE_K8S_DUMP=str(dump), ADAPTDL_NAMESPACE="ns")
+    log = open(str(tmp_path / "out.log"), "w")
+    proc = subprocess.Popen([sys.executable, "-m", "adaptdl_sched.allocator"],
+                            env=env, cwd=str(tmp_path), stdout=log,
+                            stderr=subprocess.STDOUT)
+    try:
+        deadline = time.time() + 90
+        allocation = None
+        while time.time() < deadline and not allocation:
+            assert proc.poll() is None, open(log.name).read()[-3000:]
+            if dump.exists():
+                job = json.loads(dump.read_text())["jobs"][0]
+                allocation = (job.get("status") or {}).get("allocation")
+            time.sleep(0.3)
+        assert allocation and set(allocation) == {"n0"}, \
+            open(log.name).read()[-3000:]
+    finally:
+        proc.send_signal(signal.SIGTERM)
+        try:
+            proc.wait(timeout=20)
+        except subprocess.TimeoutExpired:
+            proc.kill()
+        log.close()
