@@ -148,6 +148,19 @@ class Validator(object):
             "response": dict(verdict, uid=review["uid"])})
 
 
+def _load_cluster_credentials():
+    """The webhook asks the API server for dry runs, so its client needs
+    the pod's service-account credentials like the other scheduler
+    containers (outside a cluster: whatever the client library defaults to,
+    with a warning)."""
+    import kubernetes_asyncio as kubernetes
+    try:
+        kubernetes.config.load_incluster_config()
+    except Exception as exc:  # noqa: BLE001 - ConfigException outside a pod
+        LOG.warning("no in-cluster credentials (%s); using the client "
+                    "library's defaults", exc)
+
+
 def main(argv=None):
     from adaptdl_b200.sched.kube import KubernetesCluster
     parser = argparse.ArgumentParser(description=__doc__.split("\n")[0])
@@ -160,6 +173,7 @@ def main(argv=None):
     if args.tls_crt and args.tls_key:
         tls = ssl.SSLContext(ssl.PROTOCOL_TLS_SERVER)
         tls.load_cert_chain(args.tls_crt, args.tls_key)
+    _load_cluster_credentials()
     Validator(KubernetesCluster()).run(args.host, args.port, tls)
 
 

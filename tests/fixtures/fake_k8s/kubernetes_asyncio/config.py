@@ -25,7 +25,14 @@ def _seed():
         client.STATE["events"].append(("pod", "ADDED", pod))
 
 
+LOADED = []
+
+
 def load_incluster_config():
+    LOADED.append("incluster")
+    marker = os.environ.get("FAKE_K8S_CONFIG_MARKER")
+    if marker:
+        open(marker, "w").write("incluster")
     _seed()
 
 

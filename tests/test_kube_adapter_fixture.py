@@ -301,3 +301,64 @@ def test_allocator_process_gives_a_new_job_its_first_allocation(tmp_path):
         except subprocess.TimeoutExpired:
             proc.kill()
         log.close()
+
+
+def test_validator_process_uses_cluster_credentials_and_rejects_bad_jobs(
+        tmp_path):
+    """``python -m adaptdl_sched.validator`` (the webhook container): loads
+    the in-cluster credentials before talking to the API server, answers
+    ``/healthz``, and turns the API server's dry-run verdict into an
+    admission response."""
+    import json
+    import signal
+    import socket
+    import subprocess
+    import time
+    import urllib.request
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    marker = tmp_path / "config-loaded"
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([root, FIXTURE]),
+               FAKE_K8S_CONFIG_MARKER=str(marker))
+    log = open(str(tmp_path / "out.log"), "w")
+    proc = subprocess.Popen(
+        [sys.executable, "-m", "adaptdl_sched.validator", "--host",
+         "127.0.0.1", "--port", str(port)], env=env, cwd=str(tmp_path),
+        stdout=log, stderr=subprocess.STDOUT)
+    base = "http://127.0.0.1:{}".format(port)
+
+    def review(spec):
+        body = json.dumps({"request": {
+            "uid": "u1", "operation": "CREATE", "namespace": "ns",
+            "object": {"spec": spec}}}).encode()
+        req = urllib.request.Request(
+            base + "/validate", data=body, method="POST",
+            headers={"Content-Type": "application/json"})
+        with urllib.request.urlopen(req, timeout=10) as resp:
+            return json.loads(resp.read())["response"]
+    try:
+        deadline = time.time() + 60
+        while True:
+            try:
+                urllib.request.urlopen(base + "/healthz", timeout=2)
+                break
+            except OSError:
+                assert proc.poll() is None and time.time() < deadline, \
+                    open(log.name).read()[-3000:]
+                time.sleep(0.2)
+        assert marker.read_text() == "incluster"
+        bad = review({"template": {"spec": {"containers": []}}})
+        assert bad["uid"] == "u1" and not bad["allowed"]
+        assert bad["status"]["code"] == 422
+        good = review({"minReplicas": 1, "maxReplicas": 4, "template": {
+            "spec": {"containers": [{"name": "main", "image": "x"}]}}})
+        assert good["allowed"], good
+    finally:
+        proc.send_signal(signal.SIGTERM)
+        try:
+            proc.wait(timeout=20)
+        except subprocess.TimeoutExpired:
+            proc.kill()
+        log.close()
