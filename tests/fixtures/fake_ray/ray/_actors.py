@@ -97,6 +97,14 @@ class ActorClass(object):
             loop = asyncio.get_running_loop()
         except RuntimeError:
             loop = None
+        is_async = any(inspect.iscoroutinefunction(member) for _, member
+                       in inspect.getmembers(self._cls))
+        if loop is None and is_async:
+            # an async actor created from synchronous code (the driver
+            # script): it gets its own event-loop thread, as in Ray
+            loop = asyncio.new_event_loop()
+            threading.Thread(target=loop.run_forever, daemon=True,
+                             name="ray-async-actor").start()
         handle = ActorHandle(self._cls(*args, **kwargs), loop)
         CALLS.append(("actor", self._cls.__name__, dict(self._options)))
         if self._options.get("name"):

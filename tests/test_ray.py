@@ -234,3 +234,35 @@ def test_ray_aws_controller_moves_the_job_off_a_spot_node(tmp_path):
     assert out["terminating"] == ["127.0.0.1"], out
     assert out["generations"] >= 2 and out["had_checkpoint"], out
     assert ["cancel", None] in out["calls"]
+
+
+def test_adaptdl_on_ray_aws_command_runs_a_job(tmp_path):
+    """The command a user types (reference: ``adaptdl_on_ray_aws -f
+    train.py -m 2 --cpus 1 -- args``) from argument parsing to the exit
+    code, on the in-process stand-in for Ray."""
+    import socket
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    root = os.path.dirname(here)
+    workdir = os.path.join(root, "examples", "linear_regression")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    env = {k: v for k, v in os.environ.items()
+           if not k.startswith("ADAPTDL_")}
+    env["PYTHONPATH"] = os.pathsep.join(
+        [root, os.path.join(here, "fixtures", "fake_ray")])
+    env["OMP_NUM_THREADS"] = "1"
+    proc = subprocess.run(
+        [sys.executable, os.path.join(here, "ray_aws_launch.py"), str(port),
+         "-f", "main.py", "-d", workdir, "-m", "1", "--cpus", "1",
+         "--port-offset", str(port % 400), "--cluster-rescale-timeout", "5",
+         "--", "--epochs", "20", "--size", "2000"],
+        # Ray's runtime_env working_dir: the workers run inside it
+        env=env, cwd=workdir, stdout=subprocess.PIPE,
+        stderr=subprocess.PIPE, text=True, timeout=300)
+    assert proc.returncode == 0, proc.stderr[-3000:]
+    assert "job finished with status 1" in proc.stdout, proc.stdout
+    assert "EXIT 0" in proc.stdout
+    assert "['actor', 'Controller']" in proc.stdout
