@@ -403,3 +403,39 @@ def test_submit_through_the_in_cluster_registry(tmp_path):
                                         "adaptdl_b200.launch", "train.py"]
     assert (container.get("args") or container["command"])[-2:] == \
         ["--epochs", "3"]
+
+
+def test_workload_suite_submits_through_the_cli_and_soaks(tmp_path):
+    """tests/workloads/workloads.py (the reference's tests/*-workload/*.sh
+    and testworkload.sh as one table-driven script): ``submit`` pipes the
+    generated AdaptDLJob into ``adaptdl submit -f -``, ``soak`` tops the
+    cluster up to N active jobs -- against the stand-in kubectl / docker."""
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    root = os.path.dirname(here)
+    klog, dlog = tmp_path / "kubectl.jsonl", tmp_path / "docker.jsonl"
+    env = dict(os.environ, PYTHONPATH=root,
+               PATH=os.path.join(here, "fixtures", "fake_bin") + os.pathsep
+               + os.environ["PATH"],
+               FAKE_KUBECTL_LOG=str(klog), FAKE_DOCKER_LOG=str(dlog),
+               ADAPTDL_SUBMIT_REPO="registry.example/team/img")
+    script = os.path.join(here, "workloads", "workloads.py")
+
+    def run(*argv):
+        return subprocess.run([sys.executable, script] + list(argv), env=env,
+                              cwd=str(tmp_path), stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True,
+                              timeout=300)
+    proc = run("submit", "resnet18-cifar10-short")
+    assert proc.returncode == 0 and "submitted" in proc.stdout, proc.stdout
+    created = [json.loads(line) for line in klog.read_text().splitlines()]
+    job = json.loads([k for k in created
+                      if k["argv"][:1] == ["create"]][0]["stdin"])
+    command = job["spec"]["template"]["spec"]["containers"][0]["command"]
+    assert any(part.endswith("pytorch-cifar/main.py") for part in command)
+    # the stand-in cluster always shows one active job: two wanted -> one
+    # more is submitted per round
+    proc = run("soak", "--suite", "short", "--jobs", "2", "--rounds", "1",
+               "--period", "0")
+    assert proc.returncode == 0, proc.stdout
+    assert proc.stdout.count("submitting") == 1, proc.stdout
